@@ -1,0 +1,211 @@
+/* xb200 -- C ABI of the B200-native xVIO EKF/MSCKF hot path (libxb200.so).
+ *
+ * This is the drop-in boundary for jpl-x/x_multi_agent's filter back-end.  The reference has no
+ * FFI of its own; its operator API is the C++ classes x::Ekf / x::Updater / x::VioUpdater /
+ * x::State / x::StateManager.  Every entry point below names the reference interface it replaces
+ * (file:line relative to the reference tree).  The C++ shim in include/x/ re-implements those
+ * classes' method bodies on top of this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types; all floating-point data is fp64.
+ *   - every function returns an int status: >=0 success (1/0 = "state produced"/"std::nullopt"
+ *     where the reference returns std::optional<State>), <0 an XB_E_* error;
+ *     xb_last_error() returns the message of the last failure on the calling thread.
+ *   - one CUDA stream per filter; calls on one filter must be serialised by the caller exactly
+ *     as Ekf::lock()/unlock() does in the reference (include/x/ekf/ekf.h:128-133).
+ *   - the library has NO CPU fallback: if no sm_100 device is usable xb_create fails.
+ *
+ * State vector ("xvec", XB_XVEC_LEN(M,F) doubles), reference members include/x/ekf/state.h:240-337:
+ *   [0:3) p   [3:6) v   [6:10) q (x,y,z,w)   [10:13) b_w   [13:16) b_a   [16:20) q_ic (x,y,z,w)
+ *   [20:23) p_ic   [23:26) w_m   [26:29) a_m   [29] time   [30] seq   [31] pad
+ *   [32:32+3M) p_array   [..+4M) q_array (x,y,z,w per pose)   [..+3F) f_array (alpha,beta,rho)
+ * Error-state / covariance order (src/x/ekf/state.cpp:201-214):
+ *   [p v theta b_w b_a | p_array 3M | theta_array 3M | f_array 3F],  N = 15 + 6M + 3F.
+ * Covariances cross the ABI as dense N x N fp64, ROW-major P(i,j) at [i*N+j]
+ * (an Eigen column-major caller passes layout = XB_COL_MAJOR).
+ */
+#ifndef XB200_H_
+#define XB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define XB_API __attribute__((visibility("default")))
+#else
+#define XB_API
+#endif
+
+#define XB_CORE 15
+#define XB_XVEC_LEN(M, F) (32 + 7 * (M) + 3 * (F))
+#define XB_NERR(M, F) (15 + 6 * (M) + 3 * (F))
+
+enum { XB_ROW_MAJOR = 0, XB_COL_MAJOR = 1 };
+
+enum {
+  XB_OK = 0,
+  XB_E_INVALID = -1,      /* bad argument (std::invalid_argument in the reference) */
+  XB_E_CUDA = -2,         /* CUDA runtime failure / no usable sm_100 device */
+  XB_E_RUNTIME = -3,      /* std::runtime_error sites (ekf.cpp:46, ci.cpp:59-62, multi_slam_update.cpp:83-88) */
+  XB_E_MISMATCH = -4,     /* init_bfr_mismatch (ekf.h:202, ekf.cpp:50-59) */
+  XB_E_CAPACITY = -5,     /* more tracks/observations/features than the filter was created for */
+  XB_E_UNSUPPORTED = -6   /* NLopt-optimised CI weights (w<0), out of scope */
+};
+
+typedef struct xb_filter xb_filter; /* one agent's sliding-window filter, resident on one GPU */
+
+/* Ekf::set (src/x/ekf/ekf.cpp:32-41) + VioUpdater ctor (include/x/vio/vio_updater.h:45-49)
+ * + State(n_poses, n_features) (src/x/ekf/state.cpp:23-37). */
+typedef struct xb_config {
+  int n_poses_max;        /* M */
+  int n_features_max;     /* F */
+  int n_slots;            /* state_buffer_sz (include/x/vio/types.h:188), default 250 */
+  int n_generations;      /* P_vv generations kept on device (>=2); see DESIGN.md */
+  int device;             /* CUDA device ordinal */
+  int max_tracks;         /* capacity: MSCKF + short + MSCKF-SLAM tracks per update */
+  int max_obs;            /* capacity: total observations over those tracks */
+  int iekf_iter;          /* Updater::iekf_iter_ (updater.h:65) */
+  int min_track_length;   /* kept for API parity; used by the (out-of-scope) TrackManager */
+  unsigned delta_seq_imu; /* Ekf::set */
+  double g[3];            /* gravity, Ekf::set */
+  double n_w, n_bw, n_a, n_ba; /* ImuNoise (include/x/common/types.h:65-85) */
+  double a_m_max;         /* accel-spike threshold (ekf.cpp:84) */
+  double time_margin;     /* StateBuffer time margin (state_buffer.cpp:26-46) */
+  double sigma_img, sigma_range, rho_0, sigma_rho_0;
+  double sigma_landmark, ci_msckf_w, ci_slam_w;
+  int downdate_precision; /* 0 = fp64 CUDA cores, 1 = 3xTF32 tcgen05 tensor-core downdate */
+  int reserved;
+} xb_config;
+
+/* One track list in CSR form: track t owns observations [off[t], off[t+1]) of `obs`, each
+ * observation 2 doubles (normalised image x,y), oldest first (include/x/vision/track.h:32-85). */
+typedef struct xb_track_list {
+  int n_tracks;
+  const int* off;      /* n_tracks+1 */
+  const double* obs;   /* 2*off[n_tracks] */
+} xb_track_list;
+
+/* What VioUpdater::preProcess leaves behind (src/x/vio/vio_updater.cpp:172-179): the seam at which
+ * the hot path starts. */
+typedef struct xb_measurement {
+  double timestamp;
+  xb_track_list slam;            /* slam_trks_: entry j belongs to SLAM feature j */
+  xb_track_list msckf;           /* msckf_trks_ */
+  xb_track_list msckf_short;     /* msckf_short_trks_ */
+  xb_track_list new_slam_std;    /* new_slam_std_trks_ */
+  xb_track_list new_msckf_slam;  /* new_msckf_slam_trks_ */
+  int n_lost;
+  const int* lost_slam_idxs;     /* lost_slam_trk_idxs_ */
+} xb_measurement;
+
+/* Another agent's snapshot: SimpleState (include/x/ekf/simple_state.h:30-75) + the match lists of
+ * include/x/vision/types.h:83-116.  cov is N_peer x N_peer (layout as given). */
+typedef struct xb_peer_state {
+  int n_poses_max, n_features_max;
+  const double* positions;     /* 3*M */
+  const double* orientations;  /* 4*M (x,y,z,w) */
+  const double* features;      /* 3*F */
+  const int* anchor_idxs;      /* F */
+  const double* cov;           /* N x N, may be NULL when `cov_blocks` is given */
+  int cov_layout;
+  double translation[3];
+} xb_peer_state;
+
+typedef struct xb_slam_match {   /* SlamMatch, include/x/vision/types.h:102-116 */
+  int peer;                      /* index into the peers array */
+  int current_feature_id;
+  int received_feature_id;
+} xb_slam_match;
+
+typedef struct xb_msckf_match {  /* MsckfMatch, include/x/vision/types.h:83-100 */
+  int peer;
+  int id_current_track;          /* index into the msckf / msckf_short list it refers to */
+  int n_obs;
+  const double* obs;             /* 2*n_obs, the peer's track */
+} xb_msckf_match;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+XB_API void xb_default_config(xb_config* cfg);                 /* reference defaults (types.h:65-85, vio/types.h:33-189) */
+XB_API int xb_create(const xb_config* cfg, xb_filter** out);   /* Ekf::Ekf + Ekf::set, ekf.cpp:25-41 */
+XB_API int xb_destroy(xb_filter* f);
+XB_API const char* xb_last_error(void);
+XB_API const char* xb_version(void);
+XB_API int xb_set_stream(xb_filter* f, void* cuda_stream);     /* adopt the caller's CUDA stream */
+XB_API int xb_synchronize(xb_filter* f);
+XB_API int xb_n_error_states(const xb_filter* f);              /* State::nErrorStates, state.cpp:171-175 */
+XB_API int xb_xvec_len(const xb_filter* f);
+
+/* ---- x::Ekf --------------------------------------------------------------------------------- */
+/* Ekf::initializeFromState (ekf.cpp:43-64).  Also clears the StateManager (vio.cpp:54-111). */
+XB_API int xb_ekf_initialize_from_state(xb_filter* f, const double* xvec, const double* cov, int cov_layout);
+/* Ekf::processImu (ekf.cpp:66-140): 1 = propagated state written to xvec_out (may be NULL), 0 = nullopt. */
+XB_API int xb_ekf_process_imu(xb_filter* f, double timestamp, unsigned seq, const double w_m[3],
+                       const double a_m[3], double* xvec_out);
+/* VioUpdater::setMeasurement (vio_updater.cpp:122-124) at the preProcess seam: copies the track lists
+ * to the device (the only host->device traffic of an update). */
+XB_API int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m);
+/* Ekf::processUpdateMeasurement (ekf.cpp:179-213): closest state, Updater::update, re-propagation.
+ * 1 = updated state written to xvec_out (may be NULL: no device->host copy), 0 = nullopt. */
+XB_API int xb_ekf_process_update(xb_filter* f, double* xvec_out);
+/* Ekf::processOthersMeasurement (ekf.cpp:143-176) + Updater::collaborativeUpdate (updater.cpp:22-36):
+ * SLAM-SLAM covariance-intersection update against peers' snapshots. */
+XB_API int xb_ekf_process_others(xb_filter* f, double timestamp, const xb_peer_state* peers, int n_peers,
+                          const xb_slam_match* matches, int n_matches, double* xvec_out);
+/* MULTI_UAV build of Updater::update (updater.cpp:58-97): MSCKF-MSCKF matches used by the next
+ * xb_ekf_process_update (VioUpdater::msckf_matches_, vio_updater.cpp:185). */
+XB_API int xb_vio_set_msckf_matches(xb_filter* f, const xb_peer_state* peers, int n_peers,
+                             const xb_msckf_match* matches, int n_matches);
+/* State getters on the newest state / on ring slot `slot` (state.h:74-115). slot<0: newest. */
+XB_API int xb_ekf_get_state(xb_filter* f, int slot, double* xvec_out);
+XB_API int xb_ekf_get_covariance(xb_filter* f, int slot, double* cov_out, int cov_layout);
+XB_API int xb_ekf_newest_slot(const xb_filter* f);
+
+/* ---- x::StateManager bookkeeping (include/x/vio/state_manager.h) ---------------------------- */
+XB_API int xb_sm_n_poses(const xb_filter* f);
+XB_API int xb_sm_n_features(const xb_filter* f);
+XB_API int xb_sm_anchor_idxs(const xb_filter* f, int* out /* F */);
+XB_API int xb_sm_set(xb_filter* f, int n_poses, int n_features, const int* anchor_idxs, int filled_before);
+
+/* ---- stage-level entry points (Updater / VioUpdater / StateManager / Propagator methods) ------
+ * They act on the filter's *work state*: xb_work_load(slot) copies a ring slot into it (the
+ * `State update_state = buffer[i]` of ekf.cpp:196), xb_work_store writes it back.            */
+XB_API int xb_work_load(xb_filter* f, int slot);
+XB_API int xb_work_store(xb_filter* f, int slot);
+XB_API int xb_work_set(xb_filter* f, const double* xvec, const double* cov, int cov_layout);
+XB_API int xb_work_get(xb_filter* f, double* xvec_out, double* cov_out, int cov_layout);
+/* StateManager::manage (state_manager.cpp:31-149) */
+XB_API int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost);
+/* VioUpdater::constructUpdate (vio_updater.cpp:266-423) / constructShortMsckfUpdate (:217-264):
+ * builds the compressed (H, r) on the device. which: 0 = main update, 1 = short-MSCKF. */
+XB_API int xb_vio_construct_update(xb_filter* f, int which);
+/* Updater::applyUpdate (updater.cpp:117-141) on the device-resident compressed (H, r). */
+XB_API int xb_updater_apply_constructed(xb_filter* f, int cov_update);
+/* Updater::applyUpdate with caller-supplied dense H (m x N row-major), res (m), R diagonal (m). */
+XB_API int xb_updater_apply_update(xb_filter* f, const double* H, const double* res, const double* r_diag,
+                            int m, double* correction_total /* N, in/out */, int cov_update);
+/* Updater::applyCI (updater.cpp:144-161): K = P_j H^T S^-1, P = (I-KH) P_j.  P_j = work cov with the
+ * listed 3x3 diagonal blocks scaled by w (msckf_update.cpp:258-267, multi_slam_update.cpp:229-239). */
+XB_API int xb_updater_apply_ci(xb_filter* f, const double* H, const double* res, const double* S, int m,
+                        const int* scaled_block_cols, int n_blocks, double w_result);
+/* VioUpdater::postUpdate (vio_updater.cpp:425-449) */
+XB_API int xb_vio_post_update(xb_filter* f);
+/* Updater::update (updater.cpp:39-115) = the whole template method on the work state. */
+XB_API int xb_updater_update(xb_filter* f);
+/* Propagator::propagateState + propagateCovariance (propagator.cpp:30-72) slot_from -> slot_to. */
+XB_API int xb_propagate(xb_filter* f, int slot_from, int slot_to);
+
+/* ---- multi-agent compressed payload ---------------------------------------------- */
+XB_API int xb_ci_payload_len(const xb_filter* f);                       /* doubles per agent slot */
+XB_API int xb_ci_pack(xb_filter* f, int slot, double* dev_payload);     /* device pointer */
+
+/* ---- introspection for tests / profiling ------------------------------------------------------ */
+XB_API int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles); /* returns count */
+XB_API int xb_debug_read_int(xb_filter* f, const char* name, int* out, int max_ints);
+XB_API long long xb_kernel_launches(const xb_filter* f);                /* kernels launched so far */
+XB_API double xb_chi2_quantile(double p, double dof);                   /* boost::math::quantile(chi_squared) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XB200_H_ */

@@ -1,0 +1,229 @@
+"""Covariance-intersection fusion (oracle; test infrastructure only).
+
+reference: src/x/ekf/ci.cpp, src/x/vio/multi_slam_update.cpp, src/x/ekf/simple_state.cpp,
+           src/x/vio/msckf_update.cpp:88-139,175-279 (MULTI_UAV build).
+Only the fixed-weight branch (0 < w <= 1) is restated; the w < 0 branch calls NLopt 2.7.1 LN_COBYLA
+(third-party, CMakeLists.txt:135, ci.cpp:143-190) on singular inverses and stays out of scope.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .quat import rot, skew
+from .state import K_CORE
+from .state_manager import _mat_ivd
+from .triangulation import Triangulation
+from .updates import chi2_quantile, global_feature_position, householder_q, msckf_track_jacobians
+
+
+def _check_w(w_other):
+    if w_other > 1.0 or w_other == 0 or w_other < -1:  # ci.cpp:59-62, 98-101
+        raise RuntimeError("The CI weights must be lower than 1.0 and larger than 0.0")
+    if w_other < 0.0:
+        raise NotImplementedError("NLopt-optimised CI weights are out of scope (SURVEY.md 8f-4)")
+
+
+def fuse_ci_pair(cov_a, H_a, cov_b, H_b, w_other):
+    """reference: ci.cpp:94-127.  Returns (S, w_result)."""
+    _check_w(w_other)
+    P_a = H_a @ cov_a @ H_a.T
+    P_b = H_b @ cov_b @ H_b.T
+    w_result = 1.0 / (1.0 - w_other)
+    S = (1.0 / (1.0 - w_other)) * P_a + (1.0 / w_other) * P_b
+    return S, w_result
+
+
+def fuse_ci_multi(cov_a, H_curr, covs, Hs, w_other):
+    """reference: ci.cpp:49-92 (k-agent form).  Returns (S, w_result)."""
+    _check_w(w_other)
+    w0 = 1.0 - len(Hs) * w_other
+    S = (1.0 / w0) * H_curr @ cov_a @ H_curr.T
+    for H, c in zip(Hs, covs):
+        S = S + (1.0 / w_other) * H @ c @ H.T
+    return S, 1.0 / w0
+
+
+@dataclass
+class SimpleState:
+    """Peer snapshot = the inter-agent wire payload.  reference: include/x/ekf/simple_state.h:30-75."""
+    dynamic_state: np.ndarray
+    positions_state: np.ndarray
+    orientations_state: np.ndarray
+    features_state: np.ndarray
+    cov: np.ndarray
+    anchor_idxs: list
+    translation: np.ndarray = field(default_factory=lambda: np.zeros(3))
+
+    def n_poses_max(self):
+        return self.positions_state.size // 3
+
+    def camera_attitudes(self):  # simple_state.cpp:34-49
+        return [self.orientations_state[4 * i:4 * i + 4] for i in range(self.n_poses_max())]
+
+    def camera_positions(self):  # simple_state.cpp:51-65
+        return [self.positions_state[3 * i:3 * i + 3] + self.translation for i in range(self.n_poses_max())]
+
+
+@dataclass
+class SlamMatch:
+    """reference: include/x/vision/types.h:102-116."""
+    state: SimpleState
+    current_feature_id: int
+    received_feature_id: int
+
+
+class MultiSlamUpdate:
+    """reference: multi_slam_update.cpp:21-246.  Produces the (S, P_j, H, res) lists consumed by applyCI."""
+
+    def __init__(self, quats, poss, feature_states, anchor_idxs, P, n_poses_max, sigma_landmark, matches, ci_slam_w):
+        self.S_list, self.P_list, self.H_list, self.res_list = [], [], [], []
+        self.gamma, self.inlier = [], []
+        var_lm = sigma_landmark * sigma_landmark
+        for m in matches:
+            o = m.state
+            self._one(quats, poss, feature_states, anchor_idxs[m.current_feature_id], m.current_feature_id, P,
+                      n_poses_max, o.camera_attitudes(), o.camera_positions(), o.features_state,
+                      o.anchor_idxs[m.received_feature_id], m.received_feature_id, o.cov, o.n_poses_max(),
+                      var_lm, ci_slam_w)
+
+    @staticmethod
+    def jacobian(quats, poss, feats, anchor, fid, n_poses_max, cols, sign):
+        """3 x N world-point Jacobian of one agent (multi_slam_update.cpp:116-203)."""
+        a, b, r = feats[3 * fid:3 * fid + 3]
+        if anchor < 0:
+            raise RuntimeError("anchor_idx < 0")
+        if r == 0:
+            raise RuntimeError("rho = 0")
+        R_a = rot(quats[anchor])
+        G_p_f = (1.0 / r) * R_a @ np.array([a, b, 1.0]) + poss[anchor]
+        h = np.zeros((3, cols))
+        c = K_CORE + anchor * 3
+        h[:, c:c + 3] = sign * np.eye(3)
+        c += n_poses_max * 3
+        h[:, c:c + 3] = sign * (-(1.0 / r) * R_a @ skew(np.array([a, b, 1.0])))
+        c = K_CORE + (n_poses_max * 2 + fid) * 3
+        h[:, c:c + 3] = sign * ((1.0 / r) * R_a @ _mat_ivd(a, b, r))
+        return h, G_p_f
+
+    def _one(self, quats, poss, feats, anchor, fid, P, M, o_quats, o_poss, o_feats, o_anchor, o_fid, o_P, o_M,
+             var_lm, ci_slam_w):
+        h_j, G_p_f = self.jacobian(quats, poss, feats, anchor, fid, M, P.shape[1], +1.0)
+        oh_j, oG_p_f = self.jacobian(o_quats, o_poss, o_feats, o_anchor, o_fid, o_M, o_P.shape[1], -1.0)
+        res_j = -G_p_f + oG_p_f
+        r_j = var_lm * np.eye(3)
+        S_gate = h_j @ P @ h_j.T + oh_j @ o_P @ oh_j.T + r_j
+        gamma = float(res_j @ np.linalg.inv(S_gate) @ res_j)
+        chi = chi2_quantile(0.9, 3)
+        self.gamma.append(gamma)
+        self.inlier.append(gamma < chi)
+        if gamma < chi:
+            S_j, w_result = fuse_ci_pair(P, h_j, o_P, oh_j, ci_slam_w)
+            S_j = S_j + r_j
+            P_j = P.copy()
+            for c in (K_CORE + anchor * 3, K_CORE + anchor * 3 + M * 3, K_CORE + (M * 2 + fid) * 3):
+                P_j[c:c + 3, c:c + 3] *= w_result  # only the three diagonal 3x3 blocks, :229-239
+            self.H_list.append(h_j)
+            self.S_list.append(S_j)
+            self.res_list.append(res_j)
+            self.P_list.append(P_j)
+
+
+@dataclass
+class MsckfMatch:
+    """reference: include/x/vision/types.h:83-100."""
+    state: SimpleState
+    id_current_track: int
+    received_track: np.ndarray  # (L_peer, 2)
+
+
+def multi_msckf_one_track(track, track_id, quats, poss, P, n_poses_max, sigma_img, matches, ci_msckf_w,
+                          max_iter=10, term=1e-5):
+    """Joint multi-agent MSCKF block for ONE own track (msckf_update.cpp:65-281, MULTI_UAV build).
+
+    Returns dict(own=(inlier, gamma), multi=None | (S_j, P_j, h_j, res_pf)).  `matches` is the list of
+    MsckfMatch whose id_current_track == track_id (the reference erases them from the shared list, :137)."""
+    var_img = sigma_img * sigma_img
+    track = np.asarray(track, dtype=float)
+    L = track.shape[0]
+    mine = [m for m in matches if m.id_current_track == track_id]
+    tmp_q, tmp_p, tmp_trk = [], [], []
+    sizes = [P.shape[1]]
+    for m in mine:  # :96-139 -- peers first, own poses last
+        Lp = m.received_track.shape[0]
+        tmp_p += m.state.camera_positions()[-Lp:]
+        tmp_q += m.state.camera_attitudes()[-Lp:]
+        tmp_trk.append(m.received_track)
+        sizes.append(m.state.cov.shape[0])
+    tmp_p += poss[len(poss) - L:]
+    tmp_q += quats[len(quats) - L:]
+    tmp_trk.append(track)
+    tmp_trk = np.vstack(tmp_trk)
+    tri = Triangulation(tmp_q, tmp_p, max_iter, term)
+    ivd = tri.triangulate_gn(tmp_trk)
+    G_p_fj = global_feature_position(ivd, tmp_q[-1], tmp_p[-1])
+
+    def project(trk, q_l, p_l, M, cols):
+        out = msckf_track_jacobians(trk, q_l, p_l, M, cols, G_p_fj)
+        if out is None:
+            return None
+        jac_j, Hf_j, res_j = out
+        q = householder_q(Hf_j)
+        return jac_j, Hf_j, res_j, q[:, :3], q[:, 3:]
+
+    own = project(track, quats, poss, n_poses_max, P.shape[1])
+    if own is None:
+        return dict(own=(False, np.nan), multi=None)
+    jac_j, Hf_j, res_j, A_up, A = own
+    res0, jac0 = A.T @ res_j, A.T @ jac_j
+    S = jac0 @ P @ jac0.T + var_img * np.eye(2 * L - 3)
+    gamma = float(res0 @ np.linalg.inv(S) @ res0)
+    inl = gamma < chi2_quantile(0.95, 2.0 * L - 3.0)
+    result = dict(own=(inl, gamma), multi=None, jac0=jac0, res0=res0)
+    if not (inl and mine):
+        return result
+    k = len(mine)
+    tot_cols = sum(sizes)
+    jac_x_pf = np.zeros((3 * (k + 1), tot_cols))
+    jac_pf = np.zeros((3 * (k + 1), 3))
+    res_pf = np.zeros(3 * (k + 1))
+    jac_x_pf[0:3, 0:sizes[0]] = A_up.T @ jac_j
+    jac_pf[0:3] = A_up.T @ Hf_j
+    res_pf[0:3] = A_up.T @ res_j
+    col = sizes[0]
+    for i, m in enumerate(mine):
+        o = m.state
+        pr = project(m.received_track, o.camera_attitudes(), o.camera_positions(), o.n_poses_max(), o.cov.shape[0])
+        if pr is not None:
+            oj, oHf, ores, oA_up, _ = pr
+            jac_x_pf[3 * (i + 1):3 * (i + 2), col:col + sizes[i + 1]] = oA_up.T @ oj
+            jac_pf[3 * (i + 1):3 * (i + 2)] = oA_up.T @ oHf
+            res_pf[3 * (i + 1):3 * (i + 2)] = oA_up.T @ ores
+        col += sizes[i + 1]
+    q = householder_q(jac_pf)  # nullSpaceProjection, :494-501
+    A2 = q[:, 3:]
+    jac_x_pf = A2.T @ jac_x_pf
+    res_pf = A2.T @ res_pf
+    h_j = jac_x_pf[:, :sizes[0]]
+    S_j = h_j @ P @ h_j.T
+    Hs = []
+    col = sizes[0]
+    for i, m in enumerate(mine):
+        Hs.append(jac_x_pf[:, col:col + sizes[i + 1]])
+        col += sizes[i + 1]
+        S_j = S_j + Hs[i] @ m.state.cov @ Hs[i].T
+    S_j = S_j + var_img * np.eye(S_j.shape[0])
+    gamma_m = float(res_pf @ np.linalg.inv(S_j) @ res_pf)
+    chi_m = chi2_quantile(0.95, 2.0 * tmp_trk.shape[0] - 3.0)
+    result["multi_gate"] = (gamma_m, chi_m)
+    if gamma_m < chi_m:
+        S_ci, w_result = fuse_ci_multi(P, h_j, [m.state.cov for m in mine], Hs, ci_msckf_w)
+        S_ci = S_ci + var_img * np.eye(S_ci.shape[0])
+        P_j = P.copy()
+        n_p = len(quats)
+        for i in range(L):  # :258-267
+            c = K_CORE + (n_p - L + i) * 3
+            P_j[c:c + 3, c:c + 3] *= w_result
+            c += n_poses_max * 3
+            P_j[c:c + 3, c:c + 3] *= w_result
+        result["multi"] = (S_ci, P_j, h_j, res_pf)
+    return result

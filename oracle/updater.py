@@ -1,0 +1,137 @@
+"""Kalman update + the VioUpdater template method (oracle; test infrastructure only).
+
+reference: src/x/ekf/updater.cpp, src/x/vio/vio_updater.cpp:200-512.
+The front end (tracker / track manager) is out of scope: the five track lists + lost-feature
+indexes that `VioUpdater::preProcess` leaves behind (vio_updater.cpp:172-179) are injected directly.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .state_manager import StateManager
+from .updates import MsckfSlamUpdate, MsckfUpdate, SlamUpdate
+
+
+def apply_qr_decomposition(h, res, R_diag, sigma_img):
+    """reference: vio_updater.cpp:487-512.  Returns (h, res, R) -- R as a dense matrix like the reference."""
+    rows, cols = h.shape
+    if rows > cols + 1:
+        hres = np.hstack([h, res[:, None]])
+        thz = np.triu(np.linalg.qr(hres, mode="r"))
+        h = thz[:cols, :cols].copy()
+        res = thz[:cols, cols].copy()
+        R = sigma_img * sigma_img * np.eye(cols)
+    else:
+        R = np.diag(R_diag)
+    return h, res, R
+
+
+def apply_update(state, H, res, R, correction_total, cov_update=True):
+    """reference: updater.cpp:117-141 (explicit inverse, dense (I-KH)P, symmetrise)."""
+    P = state.cov
+    S = H @ P @ H.T + R
+    K = P @ H.T @ np.linalg.inv(S)
+    correction = K @ (res + H @ correction_total) - correction_total
+    n = P.shape[0]
+    if cov_update:
+        P = (np.eye(n) - K @ H) @ P
+        P = 0.5 * (P + P.T)
+        state.cov = P
+    state.correct(correction)
+    correction_total += correction
+    return correction
+
+
+def apply_ci(state, ci_P, H, res, S):
+    """reference: updater.cpp:144-161."""
+    K = ci_P @ H.T @ np.linalg.inv(S)
+    correction = K @ res
+    n = ci_P.shape[0]
+    P = (np.eye(n) - K @ H) @ ci_P
+    state.cov = 0.5 * (P + P.T)
+    state.correct(correction)
+    return correction
+
+
+@dataclass
+class VisualMeasurement:
+    """Output of VioUpdater::preProcess (vio_updater.cpp:172-179), injected at the seam."""
+    timestamp: float = 0.0
+    slam_trks: list = field(default_factory=list)            # one per active SLAM feature (index = feature id)
+    msckf_trks: list = field(default_factory=list)
+    msckf_short_trks: list = field(default_factory=list)
+    new_slam_std_trks: list = field(default_factory=list)
+    new_msckf_slam_trks: list = field(default_factory=list)
+    lost_slam_trk_idxs: list = field(default_factory=list)
+
+
+class VioUpdaterOracle:
+    """Restates Updater::update (updater.cpp:39-115, single-UAV build) with VioUpdater's overrides."""
+
+    def __init__(self, n_poses_max, n_features_max, sigma_img, rho_0=0.5, sigma_rho_0=0.25, iekf_iter=1):
+        self.sm = StateManager(n_poses_max, n_features_max)
+        self.sigma_img = sigma_img
+        self.rho_0 = rho_0
+        self.sigma_rho_0 = sigma_rho_0
+        self.iekf_iter = iekf_iter
+        self.meas = VisualMeasurement()
+        self.last = {}
+
+    def set_measurement(self, meas):
+        self.meas = meas
+
+    def get_time(self):
+        return self.meas.timestamp
+
+    # vio_updater.cpp:217-264 (single-UAV)
+    def construct_short_msckf_update(self, state):
+        quats = self.sm.camera_attitudes(state)
+        poss = self.sm.camera_positions(state)
+        msckf = MsckfUpdate(self.meas.msckf_short_trks, quats, poss, state.cov, state.n_poses_max(), self.sigma_img)
+        self.last["short"] = msckf
+        return apply_qr_decomposition(msckf.jac, msckf.res, msckf.cov_m_diag, self.sigma_img)
+
+    # vio_updater.cpp:266-423 (range / sun-sensor rows out of scope: absent from every BASELINE config)
+    def construct_update(self, state):
+        quats = self.sm.camera_attitudes(state)
+        poss = self.sm.camera_positions(state)
+        P = state.cov
+        M = state.n_poses_max()
+        msckf = MsckfUpdate(self.meas.msckf_trks, quats, poss, P, M, self.sigma_img)
+        msckf_slam = MsckfSlamUpdate(self.meas.new_msckf_slam_trks, quats, poss, P, M, self.sigma_img)
+        slam = SlamUpdate(self.meas.slam_trks, quats, poss, state.f_array, self.sm.anchor_idxs, P, M, self.sigma_img)
+        self.last.update(msckf=msckf, msckf_slam=msckf_slam, slam=slam)
+        h = np.vstack([msckf.jac, msckf_slam.jac, slam.jac])
+        r_diag = np.concatenate([msckf.cov_m_diag, msckf_slam.cov_m_diag, slam.cov_m_diag])
+        res = np.concatenate([msckf.res, msckf_slam.res, slam.res])
+        return apply_qr_decomposition(h, res, r_diag, self.sigma_img)
+
+    # vio_updater.cpp:425-449
+    def post_update(self, state, correction):
+        if self.meas.new_msckf_slam_trks:
+            ms = self.last["msckf_slam"]
+            self.sm.init_msckf_slam_features(state, ms.H1, ms.H2, ms.r1, ms.features, correction, self.sigma_img)
+        if self.meas.new_slam_std_trks:
+            ivds = SlamUpdate.compute_inverse_depths_new(self.meas.new_slam_std_trks, self.rho_0)
+            self.sm.init_standard_slam_features(state, ivds, self.sigma_img, self.sigma_rho_0)
+
+    # updater.cpp:39-115
+    def update(self, state):
+        correction = np.zeros(state.n_error_states())
+        if self.meas.msckf_short_trks:  # preUpdateShortMsckf, vio_updater.cpp:209-215
+            h, res, r = self.construct_short_msckf_update(state)
+            if h.size > 0:
+                apply_update(state, h, res, r, correction, True)
+        self.sm.manage(state, list(self.meas.lost_slam_trk_idxs))  # preUpdate, vio_updater.cpp:200-207
+        m = self.meas
+        requested = bool(m.msckf_trks or m.slam_trks or m.new_slam_std_trks or m.new_msckf_slam_trks)
+        if requested:
+            correction = np.zeros(state.n_error_states())
+            for i in range(self.iekf_iter):
+                h, res, r = self.construct_update(state)
+                self.last.update(h=h, res=res, r=r)
+                if h.size > 0:
+                    apply_update(state, h, res, r, correction, i == self.iekf_iter - 1)
+            self.post_update(state, correction)
+        self.last["correction"] = correction
+        return state

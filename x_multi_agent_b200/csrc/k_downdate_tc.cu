@@ -1,0 +1,5 @@
+// placeholder: tcgen05 downdate lands in a later milestone
+#include "xb_kernels.h"
+namespace xb {
+void downdate_tc(cudaStream_t, double*, int, const double*, int, int, void*) {}
+}

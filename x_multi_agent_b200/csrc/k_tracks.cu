@@ -1,0 +1,802 @@
+// Per-track MSCKF / MSCKF-SLAM measurement construction: triangulation, reprojection Jacobians,
+// left-nullspace projection and chi-square gating -- one warp per track.
+//
+// reference: src/x/vision/triangulation.cpp:48-206 (DLT + Gauss-Newton),
+//            src/x/vio/msckf_update.cpp:283-492 (Jacobians, OC projection, nullspace, gate),
+//            src/x/vio/msckf_slam_update.cpp:64-267 (Li 2012 promotion: H1, H2, r1),
+//            src/x/vio/slam_update.cpp:49-214 (inverse-depth SLAM rows).
+//
+// Formulation.  With U an orthonormal basis of range(Hf_j) (2L x 3) and A its orthogonal complement,
+// the reference stacks jac0 = A^T J, res0 = A^T r.  Everything downstream depends on A only through
+// the projector Pi = A A^T = I - U U^T:
+//   gate   gamma = (Pi r)^T (Pi J P J^T Pi + s^2 I)^-1 (Pi r)       (2L x 2L, identical value)
+//   update jac0^T jac0 = J^T J - B^T B,  jac0^T res0 = J^T r - B^T (U^T r),   B = U^T J  (3 x 6M)
+// so the 2L-3 dense rows are never formed: a track emits its sparse J blocks and the 3 dense rows B.
+#include "xb_kernels.h"
+
+namespace xb {
+
+// ---- 4x4 one-sided Jacobi: right singular vector of the smallest singular value -----------------
+// cv::triangulatePoints (OpenCV calib3d/triangulate.cpp) solves the same 4x4 homogeneous system by SVD.
+__device__ void smallest_right_singular_vector4(double* A /*4x4 row-major, destroyed*/, double* v /*4*/) {
+  double V[16];
+  for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int i = 0; i < 4; ++i) {
+          al += A[i * 4 + p] * A[i * 4 + p];
+          be += A[i * 4 + q] * A[i * 4 + q];
+          ga += A[i * 4 + p] * A[i * 4 + q];
+        }
+        const double lim = 1e-15 * sqrt(al * be);
+        if (fabs(ga) <= lim || ga == 0.0) continue;
+        off = fmax(off, fabs(ga) / fmax(sqrt(al * be), 1e-300));
+        const double zeta = (be - al) / (2.0 * ga);
+        const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+        for (int i = 0; i < 4; ++i) {
+          const double ap = A[i * 4 + p], aq = A[i * 4 + q];
+          A[i * 4 + p] = c * ap - s * aq;
+          A[i * 4 + q] = s * ap + c * aq;
+          const double vp = V[i * 4 + p], vq = V[i * 4 + q];
+          V[i * 4 + p] = c * vp - s * vq;
+          V[i * 4 + q] = s * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  int best = 0;
+  double bn = 1e300;
+  for (int p = 0; p < 4; ++p) {
+    double n = 0.0;
+    for (int i = 0; i < 4; ++i) n += A[i * 4 + p] * A[i * 4 + p];
+    if (n < bn) { bn = n; best = p; }
+  }
+  for (int i = 0; i < 4; ++i) v[i] = V[i * 4 + best];
+}
+
+__device__ __forceinline__ int tri_idx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
+
+// Per-warp shared-memory carve-up (doubles), Lm = max track length handled by the launch.
+struct WarpSmem {
+  double *Jp, *Ja, *Jap, *Jaa, *Hf, *U, *Y, *V, *res, *X;
+  __device__ WarpSmem(double* base, int Lm) {
+    Jp = base; base += 6 * Lm;
+    Ja = base; base += 6 * Lm;
+    Jap = base; base += 6 * Lm;
+    Jaa = base; base += 6 * Lm;
+    Hf = base; base += 6 * Lm;
+    U = base; base += 6 * Lm;
+    Y = base; base += 6 * Lm;
+    V = base; base += 6 * Lm;
+    res = base; base += 2 * Lm;
+    X = base;  // (2Lm+1)(2Lm+2)/2 packed lower triangle incl. the augmented residual row
+  }
+  static __host__ __device__ size_t doubles(int Lm) { return (size_t)50 * Lm + (size_t)(2 * Lm + 1) * (2 * Lm + 2) / 2; }
+};
+
+// dot of two length-n smem vectors with stride, over the warp
+__device__ __forceinline__ double wdot(const double* a, int sa, const double* b, int sb, int n, int lane) {
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) s = fma(a[i * sa], b[i * sb], s);
+  return xb_warp_sum(s);
+}
+
+template <int OPL>  // observations per lane (track length <= 32*OPL)
+__global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int M = tp.M, np = tp.n_poses;
+  double* Rk = smem;            // [M][9]  rot(q_k) (body -> global), normalised
+  double* pk = Rk + 9 * M;      // [M][3]
+  double* wbase = pk + 3 * M + warp * WarpSmem::doubles(tp.Lmax);
+  WarpSmem ws(wbase, tp.Lmax);
+
+  const double* parr = tp.xv + XV_ARR;
+  const double* qarr = tp.xv + XV_ARR + 3 * M;
+  for (int k = threadIdx.x; k < np; k += blockDim.x) {
+    xb_rot(qarr + 4 * k, Rk + 9 * k);
+    pk[3 * k] = parr[3 * k]; pk[3 * k + 1] = parr[3 * k + 1]; pk[3 * k + 2] = parr[3 * k + 2];
+  }
+  __syncthreads();
+
+  const int trk = blockIdx.x * nwarp + warp;
+  if (trk >= tp.n_tracks) return;
+  const int o0 = tp.off[trk], L = tp.off[trk + 1] - o0;
+  const int W = 6 * M + 1;  // width of a B row: pose columns + residual column
+  double* Bt = tp.B + (size_t)trk * 3 * W;
+  const int i1 = np - L;  // window slot of the first observation (msckf_update.cpp:329-331)
+  const bool slam_mode = tp.mode == 1;
+  bool bad = (L < 2) || (i1 < 0) || (L > 32 * OPL);
+
+  // ---------------------------------------------------------------- triangulation (triangulation.cpp:102-206)
+  const double* Rl = Rk + 9 * (np - 1);  // last pose = inverse-depth anchor
+  const double* pl = pk + 3 * (np - 1);
+  double alpha = 0.0, beta = 0.0, rho = 1.0;
+  if (!bad) {
+    if (lane == 0) {
+      // projection matrices [R^T | -R^T p] of the first and last pose (triangulation.cpp:208-216)
+      const double* z1 = tp.obs + 2 * (size_t)o0;
+      const double* z2 = tp.obs + 2 * (size_t)(o0 + L - 1);
+      const double* R1 = Rk + 9 * i1;
+      const double* p1 = pk + 3 * i1;
+      double A[16], P1[12], P2[12];
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) { P1[r * 4 + c] = R1[c * 3 + r]; P2[r * 4 + c] = Rl[c * 3 + r]; }
+        P1[r * 4 + 3] = -(R1[0 * 3 + r] * p1[0] + R1[1 * 3 + r] * p1[1] + R1[2 * 3 + r] * p1[2]);
+        P2[r * 4 + 3] = -(Rl[0 * 3 + r] * pl[0] + Rl[1 * 3 + r] * pl[1] + Rl[2 * 3 + r] * pl[2]);
+      }
+      for (int c = 0; c < 4; ++c) {
+        A[0 + c] = z1[0] * P1[8 + c] - P1[0 + c];
+        A[4 + c] = z1[1] * P1[8 + c] - P1[4 + c];
+        A[8 + c] = z2[0] * P2[8 + c] - P2[0 + c];
+        A[12 + c] = z2[1] * P2[8 + c] - P2[4 + c];
+      }
+      double vh[4];
+      smallest_right_singular_vector4(A, vh);
+      const double x = vh[0] / vh[3], y = vh[1] / vh[3], z = vh[2] / vh[3];
+      double c2[3];
+      for (int r = 0; r < 3; ++r) c2[r] = P2[r * 4] * x + P2[r * 4 + 1] * y + P2[r * 4 + 2] * z + P2[r * 4 + 3];
+      alpha = c2[0] / c2[2];
+      beta = c2[1] / c2[2];
+      rho = 1.0 / c2[2];
+    }
+    alpha = __shfl_sync(0xffffffffu, alpha, 0);
+    beta = __shfl_sync(0xffffffffu, beta, 0);
+    rho = __shfl_sync(0xffffffffu, rho, 0);
+
+    // iteration-invariant relative poses of this lane's observations
+    double dR[OPL][9], dp[OPL][3], zz[OPL][2];
+#pragma unroll
+    for (int o = 0; o < OPL; ++o) {
+      const int i = lane + 32 * o;
+      if (i < L) {
+        const double* Ri = Rk + 9 * (i1 + i);
+        const double* pi = pk + 3 * (i1 + i);
+        // rot = R_i^T ; delta_rot = rot * rot_a^T = R_i^T R_l ; delta_pos = rot p_a - rot p_i
+        for (int r = 0; r < 3; ++r) {
+          for (int c = 0; c < 3; ++c)
+            dR[o][r * 3 + c] = Ri[0 * 3 + r] * Rl[0 * 3 + c] + Ri[1 * 3 + r] * Rl[1 * 3 + c] + Ri[2 * 3 + r] * Rl[2 * 3 + c];
+          const double a = Ri[0 * 3 + r] * pl[0] + Ri[1 * 3 + r] * pl[1] + Ri[2 * 3 + r] * pl[2];
+          const double b = Ri[0 * 3 + r] * pi[0] + Ri[1 * 3 + r] * pi[1] + Ri[2 * 3 + r] * pi[2];
+          dp[o][r] = a - b;
+        }
+        zz[o][0] = tp.obs[2 * (size_t)(o0 + i)];
+        zz[o][1] = tp.obs[2 * (size_t)(o0 + i) + 1];
+      }
+    }
+    double r_norm_last = 1000.0, r_norm = 100.0;
+    int iter = 0;
+    while (r_norm_last - r_norm > tp.gn_term) {
+      ++iter;
+      if (iter > tp.gn_max_iter) break;
+      double jtj[6] = {0, 0, 0, 0, 0, 0}, jtr[3] = {0, 0, 0}, rr = 0.0;
+#pragma unroll
+      for (int o = 0; o < OPL; ++o) {
+        const int i = lane + 32 * o;
+        if (i < L) {
+          double h[3];
+          for (int r = 0; r < 3; ++r)
+            h[r] = dR[o][r * 3] * alpha + dR[o][r * 3 + 1] * beta + dR[o][r * 3 + 2] + rho * dp[o][r];
+          const double r0 = zz[o][0] - h[0] / h[2], r1 = zz[o][1] - h[1] / h[2];
+          const double j1a = -1.0 / h[2], j1b = h[0] / (h[2] * h[2]), j1c = h[1] / (h[2] * h[2]);
+          // J = j1 * j0, j0 = [dR(:,0) dR(:,1) dp]
+          double J0[3], J1[3];
+          const double c0[3] = {dR[o][0], dR[o][3], dR[o][6]}, c1[3] = {dR[o][1], dR[o][4], dR[o][7]};
+          J0[0] = j1a * c0[0] + j1b * c0[2]; J0[1] = j1a * c1[0] + j1b * c1[2]; J0[2] = j1a * dp[o][0] + j1b * dp[o][2];
+          J1[0] = j1a * c0[1] + j1c * c0[2]; J1[1] = j1a * c1[1] + j1c * c1[2]; J1[2] = j1a * dp[o][1] + j1c * dp[o][2];
+          jtj[0] += J0[0] * J0[0] + J1[0] * J1[0];
+          jtj[1] += J0[0] * J0[1] + J1[0] * J1[1];
+          jtj[2] += J0[0] * J0[2] + J1[0] * J1[2];
+          jtj[3] += J0[1] * J0[1] + J1[1] * J1[1];
+          jtj[4] += J0[1] * J0[2] + J1[1] * J1[2];
+          jtj[5] += J0[2] * J0[2] + J1[2] * J1[2];
+          jtr[0] += J0[0] * r0 + J1[0] * r1;
+          jtr[1] += J0[1] * r0 + J1[1] * r1;
+          jtr[2] += J0[2] * r0 + J1[2] * r1;
+          rr += r0 * r0 + r1 * r1;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 6; ++e) jtj[e] = xb_warp_sum(jtj[e]);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) jtr[e] = xb_warp_sum(jtr[e]);
+      rr = xb_warp_sum(rr);
+      const double Am[9] = {jtj[0], jtj[1], jtj[2], jtj[1], jtj[3], jtj[4], jtj[2], jtj[4], jtj[5]};
+      double Ai[9];
+      xb_inv33(Am, Ai);
+      double d[3];
+      xb_mv33(Ai, jtr, d);
+      alpha -= d[0];
+      beta -= d[1];
+      rho -= d[2];
+      r_norm_last = r_norm;
+      r_norm = sqrt(rr);
+    }
+  }
+  if (lane == 0) { tp.ivd[3 * trk] = alpha; tp.ivd[3 * trk + 1] = beta; tp.ivd[3 * trk + 2] = rho; }
+
+  // ---------------------------------------------------------------- Jacobians
+  // global feature position (msckf_update.cpp:283-304): 1/rho * R_l (alpha,beta,1) + p_l
+  double Gf[3];
+  {
+    const double ab1[3] = {alpha, beta, 1.0};
+    double t3[3];
+    xb_mv33(Rl, ab1, t3);
+    for (int e = 0; e < 3; ++e) Gf[e] = 1.0 / rho * t3[e] + pl[e];
+  }
+  int nan_flag = 0;
+  for (int i = lane; i < L && !bad; i += 32) {
+    const int pos = i1 + i;
+    const double* R = Rk + 9 * pos;
+    const double* pc = pk + 3 * pos;
+    const double dG[3] = {Gf[0] - pc[0], Gf[1] - pc[1], Gf[2] - pc[2]};
+    double cp[3];
+    xb_mtv33(R, dG, cp);  // R^T (G_p_f - p_c)
+    if (!(cp[0] == cp[0] && cp[1] == cp[1] && cp[2] == cp[2])) nan_flag = 1;
+    const double z0 = tp.obs[2 * (size_t)(o0 + i)], z1 = tp.obs[2 * (size_t)(o0 + i) + 1];
+    ws.res[2 * i] = z0 - cp[0] / cp[2];
+    ws.res[2 * i + 1] = z1 - cp[1] / cp[2];
+    const double Ji[6] = {1.0 / cp[2], 0.0, -cp[0] / (cp[2] * cp[2]), 0.0, 1.0 / cp[2], -cp[1] / (cp[2] * cp[2])};
+    double Rt[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = R[c * 3 + r];
+    double Jpos[6], Jatt[6], sk[9];
+    xb_mm23(Ji, Rt, Jpos);
+    for (int e = 0; e < 6; ++e) Jpos[e] = -Jpos[e];
+    xb_skew(cp, sk);
+    xb_mm23(Ji, sk, Jatt);
+    double* Jp = ws.Jp + 6 * i;
+    double* Ja = ws.Ja + 6 * i;
+    double* Jap = ws.Jap + 6 * i;
+    double* Jaa = ws.Jaa + 6 * i;
+    double* Hf = ws.Hf + 6 * i;
+    if (!slam_mode) {
+      // observability-constrained projection (msckf_update.cpp:393-406), g hard-coded
+      const double g[3] = {0.0, 0.0, -9.81};
+      double u[3], t2[2];
+      xb_mv33(R, g, u);
+      double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+      for (int r = 0; r < 2; ++r) t2[r] = (Jpos[r * 3] * u[0] + Jpos[r * 3 + 1] * u[1] + Jpos[r * 3 + 2] * u[2]) * (1.0 / uu);
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) Jpos[r * 3 + c] -= t2[r] * u[c];
+      double skd[9];
+      xb_skew(dG, skd);
+      xb_mv33(skd, g, u);
+      uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+      for (int r = 0; r < 2; ++r) t2[r] = (Jatt[r * 3] * u[0] + Jatt[r * 3 + 1] * u[1] + Jatt[r * 3 + 2] * u[2]) * (1.0 / uu);
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) Jatt[r * 3 + c] -= t2[r] * u[c];
+      for (int e = 0; e < 6; ++e) { Jp[e] = Jpos[e]; Ja[e] = Jatt[e]; Jap[e] = 0.0; Jaa[e] = 0.0; Hf[e] = -Jpos[e]; }
+    } else if (i == L - 1) {  // msckf_slam_update.cpp:133-143
+      for (int e = 0; e < 6; ++e) { Jp[e] = 0.0; Ja[e] = 0.0; Jap[e] = 0.0; Jaa[e] = 0.0; Hf[e] = 0.0; }
+      Hf[0] = 1.0;
+      Hf[4] = 1.0;
+    } else {  // msckf_slam_update.cpp:144-198
+      double RtRn[9], JR[6], skab[9], m3[9], tmp[6];
+      xb_mm33(Rt, Rl, RtRn);
+      xb_mm23(Ji, RtRn, JR);
+      const double ab1[3] = {alpha, beta, 1.0};
+      xb_skew(ab1, skab);
+      xb_mm23(JR, skab, tmp);
+      for (int e = 0; e < 6; ++e) { Jaa[e] = -1.0 / rho * tmp[e]; Jap[e] = -Jpos[e]; Jp[e] = Jpos[e]; Ja[e] = Jatt[e]; }
+      xb_mat_ivd(alpha, beta, rho, m3);
+      xb_mm23(JR, m3, tmp);
+      for (int e = 0; e < 6; ++e) Hf[e] = 1.0 / rho * tmp[e];
+    }
+  }
+  nan_flag = __any_sync(0xffffffffu, nan_flag);
+  bad = bad || nan_flag;
+  __syncwarp();
+
+  // ---------------------------------------------------------------- U = orth(Hf): MGS with re-orthogonalisation
+  // (msckf_update.cpp:423: Hf.householderQr().householderQ(); only range(Hf) matters)
+  const int R2 = 2 * L;
+  if (!bad) {
+    for (int i = lane; i < R2 * 3; i += 32) ws.U[i] = ws.Hf[i];
+    __syncwarp();
+    for (int c = 0; c < 3; ++c) {
+      for (int pass = 0; pass < 2; ++pass)
+        for (int p = 0; p < c; ++p) {
+          const double d = wdot(ws.U + p, 3, ws.U + c, 3, R2, lane);
+          for (int i = lane; i < R2; i += 32) ws.U[i * 3 + c] -= d * ws.U[i * 3 + p];
+          __syncwarp();
+        }
+      const double n2 = wdot(ws.U + c, 3, ws.U + c, 3, R2, lane);
+      const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+      for (int i = lane; i < R2; i += 32) ws.U[i * 3 + c] *= inv;
+      __syncwarp();
+    }
+  }
+
+  // ---------------------------------------------------------------- B = U^T [J | r]   (3 x (6M+1))
+  for (int e = lane; e < 3 * W; e += 32) Bt[e] = 0.0;
+  __syncwarp();
+  double ur[3] = {0, 0, 0};
+  if (!bad) {
+    double anc[18];
+    for (int e = 0; e < 18; ++e) anc[e] = 0.0;
+    for (int i = lane; i < L; i += 32) {
+      const int pos = i1 + i;
+      const double* U0 = ws.U + 6 * i;  // rows 2i, 2i+1 (3 each)
+      const double* Jp = ws.Jp + 6 * i;
+      const double* Ja = ws.Ja + 6 * i;
+      for (int u = 0; u < 3; ++u) {
+        for (int c = 0; c < 3; ++c) {
+          Bt[u * W + 3 * pos + c] = U0[u] * Jp[c] + U0[3 + u] * Jp[3 + c];
+          Bt[u * W + 3 * M + 3 * pos + c] = U0[u] * Ja[c] + U0[3 + u] * Ja[3 + c];
+        }
+        ur[u] += U0[u] * ws.res[2 * i] + U0[3 + u] * ws.res[2 * i + 1];
+      }
+      if (slam_mode) {
+        const double* Jap = ws.Jap + 6 * i;
+        const double* Jaa = ws.Jaa + 6 * i;
+        for (int u = 0; u < 3; ++u)
+          for (int c = 0; c < 3; ++c) {
+            anc[u * 6 + c] += U0[u] * Jap[c] + U0[3 + u] * Jap[3 + c];
+            anc[u * 6 + 3 + c] += U0[u] * Jaa[c] + U0[3 + u] * Jaa[3 + c];
+          }
+      }
+    }
+    for (int u = 0; u < 3; ++u) ur[u] = xb_warp_sum(ur[u]);
+    __syncwarp();
+    if (slam_mode) {
+      for (int e = 0; e < 18; ++e) anc[e] = xb_warp_sum(anc[e]);
+      if (lane == 0) {
+        const int pos = np - 1;  // own block of the last observation is zero, so plain stores are exact
+        for (int u = 0; u < 3; ++u)
+          for (int c = 0; c < 3; ++c) {
+            Bt[u * W + 3 * pos + c] = anc[u * 6 + c];
+            Bt[u * W + 3 * M + 3 * pos + c] = anc[u * 6 + 3 + c];
+          }
+      }
+      // H2 = U^T Hf (3x3), msckf_slam_update.cpp:225
+      double h2[9];
+      for (int u = 0; u < 3; ++u)
+        for (int c = 0; c < 3; ++c) h2[u * 3 + c] = wdot(ws.U + u, 3, ws.Hf + c, 3, R2, lane);
+      if (lane == 0)
+        for (int e = 0; e < 9; ++e) tp.H2[9 * (size_t)trk + e] = h2[e];
+    }
+    if (lane == 0)
+      for (int u = 0; u < 3; ++u) Bt[u * W + 6 * M] = ur[u];
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- gate: X = J P J^T over block pairs (k <= i)
+  double gamma = NAN;
+  int inl = 0;
+  if (!bad) {
+    const double* P = tp.P;
+    const int ld = tp.ldp;
+    const int npairs = L * (L + 1) / 2;
+    const int nslot = slam_mode ? 2 : 1;
+    for (int e = lane; e < npairs; e += 32) {
+      int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while (i * (i + 1) / 2 > e) --i;
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      const int k = e - i * (i + 1) / 2;
+      double x00 = 0, x01 = 0, x10 = 0, x11 = 0;
+      for (int si = 0; si < nslot; ++si) {
+        const int pi_ = si ? np - 1 : i1 + i;
+        const double* Ji_p = (si ? ws.Jap : ws.Jp) + 6 * i;
+        const double* Ji_a = (si ? ws.Jaa : ws.Ja) + 6 * i;
+        for (int sk = 0; sk < nslot; ++sk) {
+          const int pk_ = sk ? np - 1 : i1 + k;
+          const double* Jk_p = (sk ? ws.Jap : ws.Jp) + 6 * k;
+          const double* Jk_a = (sk ? ws.Jaa : ws.Ja) + 6 * k;
+          // T (2x6) = [Ji_p Ji_a] * P[pose pi_, pose pk_]
+          double T[12];
+          const int rp = XB_CORE + 3 * pi_, ra = XB_CORE + 3 * M + 3 * pi_;
+          const int cpn = XB_CORE + 3 * pk_, can = XB_CORE + 3 * M + 3 * pk_;
+          for (int c = 0; c < 3; ++c) {
+            double tp0 = 0, tp1 = 0, ta0 = 0, ta1 = 0;
+            for (int a = 0; a < 3; ++a) {
+              const double ppp = P[(size_t)(rp + a) * ld + cpn + c], pap = P[(size_t)(ra + a) * ld + cpn + c];
+              const double ppa = P[(size_t)(rp + a) * ld + can + c], paa = P[(size_t)(ra + a) * ld + can + c];
+              tp0 = fma(Ji_p[a], ppp, tp0); tp0 = fma(Ji_a[a], pap, tp0);
+              tp1 = fma(Ji_p[3 + a], ppp, tp1); tp1 = fma(Ji_a[3 + a], pap, tp1);
+              ta0 = fma(Ji_p[a], ppa, ta0); ta0 = fma(Ji_a[a], paa, ta0);
+              ta1 = fma(Ji_p[3 + a], ppa, ta1); ta1 = fma(Ji_a[3 + a], paa, ta1);
+            }
+            T[c] = tp0; T[6 + c] = tp1; T[3 + c] = ta0; T[9 + c] = ta1;
+          }
+          for (int c = 0; c < 3; ++c) {
+            x00 = fma(T[c], Jk_p[c], x00); x00 = fma(T[3 + c], Jk_a[c], x00);
+            x01 = fma(T[c], Jk_p[3 + c], x01); x01 = fma(T[3 + c], Jk_a[3 + c], x01);
+            x10 = fma(T[6 + c], Jk_p[c], x10); x10 = fma(T[9 + c], Jk_a[c], x10);
+            x11 = fma(T[6 + c], Jk_p[3 + c], x11); x11 = fma(T[9 + c], Jk_a[3 + c], x11);
+          }
+        }
+      }
+      ws.X[tri_idx(2 * i, 2 * k)] = x00;
+      ws.X[tri_idx(2 * i + 1, 2 * k)] = x10;
+      ws.X[tri_idx(2 * i + 1, 2 * k + 1)] = x11;
+      if (k < i) ws.X[tri_idx(2 * i, 2 * k + 1)] = x01;
+    }
+    __syncwarp();
+    // Y = X U  (2L x 3)
+    for (int r = lane; r < R2; r += 32) {
+      double y0 = 0, y1 = 0, y2 = 0;
+      for (int c = 0; c < R2; ++c) {
+        const double x = (c <= r) ? ws.X[tri_idx(r, c)] : ws.X[tri_idx(c, r)];
+        y0 = fma(x, ws.U[c * 3], y0);
+        y1 = fma(x, ws.U[c * 3 + 1], y1);
+        y2 = fma(x, ws.U[c * 3 + 2], y2);
+      }
+      ws.Y[r * 3] = y0; ws.Y[r * 3 + 1] = y1; ws.Y[r * 3 + 2] = y2;
+    }
+    __syncwarp();
+    double Z[9];  // U^T X U
+    for (int u = 0; u < 3; ++u)
+      for (int v = 0; v < 3; ++v) Z[u * 3 + v] = wdot(ws.U + u, 3, ws.Y + v, 3, R2, lane);
+    for (int r = lane; r < R2; r += 32)
+      for (int v = 0; v < 3; ++v)
+        ws.V[r * 3 + v] = ws.U[r * 3] * Z[v] + ws.U[r * 3 + 1] * Z[3 + v] + ws.U[r * 3 + 2] * Z[6 + v];
+    __syncwarp();
+    // S = Pi X Pi + var I (in place, packed), augmented row R2 = (Pi r)^T
+    const int nel = R2 * (R2 + 1) / 2;
+    for (int e = lane; e < nel; e += 32) {
+      int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while (r * (r + 1) / 2 > e) --r;
+      while ((r + 1) * (r + 2) / 2 <= e) ++r;
+      const int c = e - r * (r + 1) / 2;
+      double s = ws.X[e];
+      for (int u = 0; u < 3; ++u)
+        s += -ws.U[r * 3 + u] * ws.Y[c * 3 + u] - ws.Y[r * 3 + u] * ws.U[c * 3 + u] + ws.V[r * 3 + u] * ws.U[c * 3 + u];
+      if (r == c) s += tp.var_img;
+      ws.X[e] = s;
+    }
+    double* aug = ws.X + tri_idx(R2, 0);
+    for (int r = lane; r < R2; r += 32)
+      aug[r] = ws.res[r] - (ws.U[r * 3] * ur[0] + ws.U[r * 3 + 1] * ur[1] + ws.U[r * 3 + 2] * ur[2]);
+    __syncwarp();
+    // Cholesky of the (R2+1)-row augmented lower triangle; last row becomes y = L^-1 (Pi r)
+    bool spd = true;
+    for (int c = 0; c < R2; ++c) {
+      const double piv = ws.X[tri_idx(c, c)];
+      if (!(piv > 0.0)) { spd = false; break; }
+      const double d = sqrt(piv);
+      __syncwarp();
+      for (int r = c + 1 + lane; r <= R2; r += 32) ws.X[tri_idx(r, c)] /= d;
+      __syncwarp();
+      for (int r = c + 1 + lane; r <= R2; r += 32) {
+        const double lrc = ws.X[tri_idx(r, c)];
+        double* row = ws.X + tri_idx(r, 0);
+        const int kend = (r < R2) ? r : R2 - 1;  // the augmented row has no diagonal entry
+        for (int k = c + 1; k <= kend; ++k) row[k] = fma(-lrc, ws.X[tri_idx(k, c)], row[k]);
+      }
+      __syncwarp();
+    }
+    if (spd) {
+      gamma = wdot(aug, 1, aug, 1, R2, lane);
+      const double chi = tp.chi2_95[2 * L - 3];
+      inl = gamma < chi;
+    }
+  }
+  if (lane == 0) {
+    tp.gamma[trk] = gamma;
+    tp.inlier[trk] = inl;
+  }
+  // emit the sparse J blocks + residuals of the track (used by the Gram stage)
+  for (int i = lane; i < L; i += 32) {
+    double* o = tp.Jout + 14 * (size_t)(o0 + i);
+    for (int e = 0; e < 6; ++e) { o[e] = bad ? 0.0 : ws.Jp[6 * i + e]; o[6 + e] = bad ? 0.0 : ws.Ja[6 * i + e]; }
+    o[12] = bad ? 0.0 : ws.res[2 * i];
+    o[13] = bad ? 0.0 : ws.res[2 * i + 1];
+  }
+  if (slam_mode && (bad || !inl)) {
+    double* D = tp.D + (size_t)2 * o0 * W;
+    for (int e = lane; e < 2 * L * W; e += 32) D[e] = 0.0;
+  } else if (slam_mode) {
+    // dense rows D = Pi J (2L x W) for the Gram stage: D = J - U B   (mode-1 tracks are few)
+    double* D = tp.D + (size_t)2 * o0 * W;
+    __syncwarp();
+    for (int e = lane; e < R2 * W; e += 32) {
+      const int r = e / W, c = e % W;
+      double v = -(ws.U[r * 3] * Bt[c] + ws.U[r * 3 + 1] * Bt[W + c] + ws.U[r * 3 + 2] * Bt[2 * W + c]);
+      const int i = r >> 1, h = r & 1;
+      const int pos = i1 + i;
+      if (c == 6 * M) v += ws.res[r];
+      else {
+        const bool att = c >= 3 * M;
+        const int cc = att ? c - 3 * M : c;
+        const int cpz = cc / 3, a = cc % 3;
+        if (cpz == pos) v += (att ? ws.Ja : ws.Jp)[6 * i + 3 * h + a];
+        if (cpz == np - 1) v += (att ? ws.Jaa : ws.Jap)[6 * i + 3 * h + a];
+      }
+      D[e] = v;
+    }
+  }
+  // outliers contribute nothing downstream: B is kept only for inliers in MSCKF mode.  In MSCKF-SLAM
+  // mode B (= H1) and U^T r (= r1) also feed the feature initialisation of *every* new track
+  // (vio_updater.cpp:430-437), so they are copied out before B is masked.
+  if (slam_mode) {
+    double* h1 = tp.H1 + (size_t)trk * 3 * W;
+    for (int e = lane; e < 3 * W; e += 32) h1[e] = Bt[e];
+  }
+  __syncwarp();
+  if (!inl)
+    for (int e = lane; e < 3 * W; e += 32) Bt[e] = 0.0;
+}
+
+size_t tracks_smem_bytes(int M, int Lmax, int warps) {
+  return sizeof(double) * ((size_t)12 * M + (size_t)warps * WarpSmem::doubles(Lmax));
+}
+
+int launch_tracks(cudaStream_t s, const TrackParams& tp) {
+  if (tp.n_tracks <= 0) return 0;
+  int warps = 4;
+  const size_t cap = 220 * 1024;
+  while (warps > 1 && tracks_smem_bytes(tp.M, tp.Lmax, warps) > cap) --warps;
+  const size_t bytes = tracks_smem_bytes(tp.M, tp.Lmax, warps);
+  if (bytes > cap) return -1;
+  const int grid = (tp.n_tracks + warps - 1) / warps;
+  if (tp.Lmax <= 32) {
+    cudaFuncSetAttribute(k_tracks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_tracks<1><<<grid, warps * 32, bytes, s>>>(tp);
+  } else if (tp.Lmax <= 64) {
+    cudaFuncSetAttribute(k_tracks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_tracks<2><<<grid, warps * 32, bytes, s>>>(tp);
+  } else {
+    return -1;
+  }
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SLAM rows (slam_update.cpp:49-214): one thread per SLAM feature; emits 2 sparse rows (<=15 columns).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_slam_rows(SlamParams sp) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= sp.n_tracks) return;
+  const int M = sp.M, np = sp.n_poses, N = sp.N;
+  const double* parr = sp.xv + XV_ARR;
+  const double* qarr = sp.xv + XV_ARR + 3 * M;
+  const double* farr = sp.xv + XV_ARR + 7 * M;
+  int* cols = sp.cols + 15 * j;
+  double* vals = sp.vals + 30 * j;
+  for (int e = 0; e < 15; ++e) cols[e] = 0;
+  for (int e = 0; e < 30; ++e) vals[e] = 0.0;
+  sp.res[2 * j] = 0.0;
+  sp.res[2 * j + 1] = 0.0;
+  sp.inlier[j] = 0;
+  sp.gamma[j] = NAN;
+  const int L = sp.off[j + 1] - sp.off[j];
+  if (L < 1) return;
+  const double a = farr[3 * j], b = farr[3 * j + 1], r = farr[3 * j + 2];
+  const int anchor = sp.anchor[j];
+  if (anchor < 0 || anchor >= np) return;
+  double Ra[9], Rn[9];
+  xb_rot(qarr + 4 * anchor, Ra);
+  xb_rot(qarr + 4 * (np - 1), Rn);
+  const double ab1[3] = {a, b, 1.0};
+  double t3[3], Gf[3], dG[3], cp[3];
+  xb_mv33(Ra, ab1, t3);
+  for (int e = 0; e < 3; ++e) { Gf[e] = 1.0 / r * t3[e] + parr[3 * anchor + e]; dG[e] = Gf[e] - parr[3 * (np - 1) + e]; }
+  xb_mtv33(Rn, dG, cp);
+  const double* z = sp.obs + 2 * (size_t)(sp.off[j + 1] - 1);
+  const double r0 = z[0] - cp[0] / cp[2], r1 = z[1] - cp[1] / cp[2];
+  const int pos = np - 1;
+  const int fcol = XB_CORE + (2 * M + j) * 3;
+  int nc;
+  double h[30];
+  for (int e = 0; e < 30; ++e) h[e] = 0.0;
+  if (anchor == pos) {  // slam_update.cpp:120-130
+    nc = 3;
+    for (int c = 0; c < 3; ++c) cols[c] = fcol + c;
+    h[0] = 1.0;
+    h[15 + 1] = 1.0;
+  } else {
+    nc = 15;
+    const double Ji[6] = {1.0 / cp[2], 0.0, -cp[0] / (cp[2] * cp[2]), 0.0, 1.0 / cp[2], -cp[1] / (cp[2] * cp[2])};
+    double Rt[9], sk[9], Jpos[6], Jatt[6], RtRa[9], JR[6], skab[9], Jaa[6], m3[9], Hf[6];
+    for (int rr = 0; rr < 3; ++rr)
+      for (int c = 0; c < 3; ++c) Rt[rr * 3 + c] = Rn[c * 3 + rr];
+    xb_skew(cp, sk);
+    xb_mm23(Ji, sk, Jatt);
+    xb_mm23(Ji, Rt, Jpos);
+    for (int e = 0; e < 6; ++e) Jpos[e] = -Jpos[e];
+    xb_mm33(Rt, Ra, RtRa);
+    xb_mm23(Ji, RtRa, JR);
+    xb_skew(ab1, skab);
+    xb_mm23(JR, skab, Jaa);
+    xb_mat_ivd(a, b, r, m3);
+    xb_mm23(JR, m3, Hf);
+    for (int c = 0; c < 3; ++c) {
+      cols[c] = XB_CORE + 3 * pos + c;
+      cols[3 + c] = XB_CORE + 3 * M + 3 * pos + c;
+      cols[6 + c] = XB_CORE + 3 * anchor + c;
+      cols[9 + c] = XB_CORE + 3 * M + 3 * anchor + c;
+      cols[12 + c] = fcol + c;
+      for (int rr = 0; rr < 2; ++rr) {
+        h[rr * 15 + c] = Jpos[rr * 3 + c];
+        h[rr * 15 + 3 + c] = Jatt[rr * 3 + c];
+        h[rr * 15 + 6 + c] = -Jpos[rr * 3 + c];
+        h[rr * 15 + 9 + c] = -1.0 / r * Jaa[rr * 3 + c];
+        h[rr * 15 + 12 + c] = 1.0 / r * Hf[rr * 3 + c];
+      }
+    }
+  }
+  // gate: S = h P h^T + var I (2x2), chi2(0.9, 2*track_size)  (slam_update.cpp:192-199)
+  double s00 = 0, s01 = 0, s11 = 0;
+  for (int c = 0; c < nc; ++c) {
+    double t0 = 0, t1 = 0;
+    for (int d = 0; d < nc; ++d) {
+      const double p = sp.P[(size_t)cols[d] * N + cols[c]];
+      t0 = fma(h[d], p, t0);
+      t1 = fma(h[15 + d], p, t1);
+    }
+    s00 = fma(t0, h[c], s00);
+    s01 = fma(t0, h[15 + c], s01);
+    s11 = fma(t1, h[15 + c], s11);
+  }
+  s00 += sp.var_img;
+  s11 += sp.var_img;
+  const double det = s00 * s11 - s01 * s01;
+  const double gamma = (r0 * (s11 * r0 - s01 * r1) + r1 * (s00 * r1 - s01 * r0)) / det;
+  sp.gamma[j] = gamma;
+  const int inl = gamma < sp.chi2[j];
+  sp.inlier[j] = inl;
+  if (inl) {
+    for (int e = 0; e < 30; ++e) vals[e] = h[e];
+    sp.res[2 * j] = r0;
+    sp.res[2 * j + 1] = r1;
+  }
+}
+
+void launch_slam_rows(cudaStream_t s, const SlamParams& sp) {
+  if (sp.n_tracks <= 0) return;
+  k_slam_rows<<<(sp.n_tracks + 63) / 64, 64, 0, s>>>(sp);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gram stage:  G = sum_inliers [J|r]^T [J|r] - B_all^T B_all + D^T D   ((6M+1) x (6M+1))
+//   k_gram_partial: split-K  A^T A  of a tall row-major matrix A [rows x W] -> partial[z][W x W]
+//   k_gram_reduce : fixed-order sum of the partials (deterministic), block-diagonal J^T J terms and
+//                   scatter into the tall Cholesky buffer [G ; g^T].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gram_partial(const double* __restrict__ A, int rows, int W, int chunk,
+                                                      double* __restrict__ part) {
+  __shared__ double As[16][64 + 4];
+  __shared__ double Bs[16][64 + 4];
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, z = blockIdx.z;
+  const int kb = z * chunk, ke = min(rows, kb + chunk);
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = kb; k0 < ke; k0 += 16) {
+    const int kk = t >> 4, c = (t & 15) * 4;
+    const int gk = k0 + kk;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ga = m0 + c + u, gb = n0 + c + u;
+      As[kk][c + u] = (gk < ke && ga < W) ? A[(size_t)gk * W + ga] : 0.0;
+      Bs[kk][c + u] = (gk < ke && gb < W) ? A[(size_t)gk * W + gb] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k2][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k2][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double* out = part + (size_t)z * W * W;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gr = m0 + ty * 4 + i;
+    if (gr >= W) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = n0 + tx * 4 + j;
+      if (gc < W) out[(size_t)gr * W + gc] = acc[i][j];
+    }
+  }
+}
+
+// One CTA per window pose: sum over the tracks' observations at that pose of [Jp Ja r]^T [Jp Ja r] (7x7).
+// pose of observation i of track t = n_poses - L_t + i.
+__global__ void __launch_bounds__(128) k_gram_jtj(const int* __restrict__ off, const int* __restrict__ inlier, int n_tracks,
+                                                  const double* __restrict__ Jout, int n_poses, double* __restrict__ blocks) {
+  const int pose = blockIdx.x;
+  __shared__ double red[128][29];
+  double acc[28];
+  for (int e = 0; e < 28; ++e) acc[e] = 0.0;
+  for (int t = threadIdx.x; t < n_tracks; t += blockDim.x) {
+    if (!inlier[t]) continue;
+    const int L = off[t + 1] - off[t];
+    const int i = pose - (n_poses - L);
+    if (i < 0 || i >= L) continue;
+    const double* o = Jout + 14 * (size_t)(off[t] + i);
+    // 7 "columns": Jp(:,0..2), Ja(:,0..2), r ; rows 0/1
+    double c0[7], c1[7];
+    for (int e = 0; e < 3; ++e) { c0[e] = o[e]; c1[e] = o[3 + e]; c0[3 + e] = o[6 + e]; c1[3 + e] = o[9 + e]; }
+    c0[6] = o[12];
+    c1[6] = o[13];
+    int q = 0;
+    for (int a = 0; a < 7; ++a)
+      for (int b = a; b < 7; ++b) acc[q++] += c0[a] * c0[b] + c1[a] * c1[b];
+  }
+  for (int e = 0; e < 28; ++e) red[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int e = 0; e < 28; ++e) red[threadIdx.x][e] += red[threadIdx.x + s][e];
+    __syncthreads();
+  }
+  if (threadIdx.x < 28) blocks[28 * pose + threadIdx.x] = red[0][threadIdx.x];
+}
+
+__global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const double* __restrict__ partD, int nzD,
+                              const double* __restrict__ blocks, int M, int n_poses, double* __restrict__ T, int ld,
+                              int rows_pad, int cols_pad) {
+  // T is the tall buffer [cols_pad (G) + 32 (row 0 = g^T)] x ld ; everything outside G/g is identity/zero padding.
+  const int W = 6 * M + 1;
+  const int r = blockIdx.y * 16 + threadIdx.y, c = blockIdx.x * 16 + threadIdx.x;
+  if (r >= rows_pad || c >= cols_pad) return;
+  const int n = 6 * M;
+  double v = 0.0;
+  int gr = -1;
+  if (r < n) gr = r;
+  else if (r == cols_pad) gr = n;  // augmented row: g^T
+  if (gr >= 0 && c < n) {
+    for (int z = 0; z < nzB; ++z) v -= partB[(size_t)z * W * W + (size_t)gr * W + c];
+    for (int z = 0; z < nzD; ++z) v += partD[(size_t)z * W * W + (size_t)gr * W + c];
+    // block-diagonal J^T J: element (gr, c) is non-zero when both belong to the same pose (or gr is the r column)
+    auto pose_of = [&](int x, int& k) { const bool att = x >= 3 * M; const int xx = att ? x - 3 * M : x; k = (att ? 3 : 0) + xx % 3; return xx / 3; };
+    int kc, pc = pose_of(c, kc);
+    int kr = 6, pr = pc;
+    if (gr < n) pr = pose_of(gr, kr);
+    if (pr == pc && pc < n_poses) {
+      const int a = min(kr, kc), b = max(kr, kc);
+      const int q = a * 7 - a * (a - 1) / 2 + (b - a);
+      v += blocks[28 * pc + q];
+    }
+  } else if (r == c && r >= n && r < cols_pad) {
+    v = 1.0;  // identity padding keeps the factor well defined
+  }
+  T[(size_t)r * ld + c] = v;
+}
+
+void launch_gram(cudaStream_t s, const GramParams& gp) {
+  const int W = 6 * gp.M + 1;
+  const int tiles = (W + 63) / 64;
+  int nzB = 0, nzD = 0;
+  if (gp.rowsB > 0) {
+    nzB = gp.nzB;
+    const int chunk = ((gp.rowsB + nzB - 1) / nzB + 15) / 16 * 16;
+    dim3 g(tiles, tiles, nzB);
+    k_gram_partial<<<g, 256, 0, s>>>(gp.B, gp.rowsB, W, chunk, gp.partB);
+    count_launch();
+  }
+  if (gp.rowsD > 0) {
+    nzD = gp.nzD;
+    const int chunk = ((gp.rowsD + nzD - 1) / nzD + 15) / 16 * 16;
+    dim3 g(tiles, tiles, nzD);
+    k_gram_partial<<<g, 256, 0, s>>>(gp.D, gp.rowsD, W, chunk, gp.partD);
+    count_launch();
+  }
+  k_gram_jtj<<<gp.M, 128, 0, s>>>(gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
+  count_launch();
+  dim3 b(16, 16), g((gp.cols_pad + 15) / 16, (gp.rows_pad + 15) / 16);
+  k_gram_reduce<<<g, b, 0, s>>>(gp.partB, nzB, gp.partD, nzD, gp.blocks, gp.M, gp.n_poses, gp.T, gp.ld, gp.rows_pad,
+                                gp.cols_pad);
+  count_launch();
+}
+
+}  // namespace xb

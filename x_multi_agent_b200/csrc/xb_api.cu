@@ -1,0 +1,1032 @@
+// C ABI + host orchestration of the device-resident filter (see include/xb200.h).
+// Host logic mirrors: src/x/ekf/ekf.cpp (driver), src/x/ekf/state_buffer.cpp (ring buffer),
+// src/x/ekf/updater.cpp (template method), src/x/vio/vio_updater.cpp (construct/post update),
+// src/x/vio/state_manager.cpp (integer bookkeeping only; the arithmetic runs in k_manage.cu).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/xb200.h"
+#include "xb_kernels.h"
+
+namespace xb {
+static thread_local long long g_launches = 0;
+void count_launch() { ++g_launches; }
+}  // namespace xb
+
+using namespace xb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(XB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+  } while (0)
+
+// ---- chi-square quantile (boost::math::quantile(chi_squared_distribution<>(dof), p)) ------------------
+static double gammap(double a, double x) {  // regularised lower incomplete gamma P(a, x)
+  if (x <= 0.0) return 0.0;
+  const double lg = std::lgamma(a);
+  if (x < a + 1.0) {
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 0; n < 1000; ++n) {
+      ap += 1.0;
+      del *= x / ap;
+      sum += del;
+      if (std::fabs(del) < std::fabs(sum) * 1e-17) break;
+    }
+    return sum * std::exp(-x + a * std::log(x) - lg);
+  }
+  double b = x + 1.0 - a, c = 1.0 / 1e-300, d = 1.0 / b, h = d;
+  for (int i = 1; i < 1000; ++i) {
+    const double an = -i * (i - a);
+    b += 2.0;
+    d = an * d + b;
+    if (std::fabs(d) < 1e-300) d = 1e-300;
+    c = b + an / c;
+    if (std::fabs(c) < 1e-300) c = 1e-300;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (std::fabs(del - 1.0) < 1e-17) break;
+  }
+  return 1.0 - std::exp(-x + a * std::log(x) - lg) * h;
+}
+extern "C" double xb_chi2_quantile(double p, double dof) {
+  if (!(p > 0.0 && p < 1.0) || !(dof > 0.0)) return NAN;
+  const double a = 0.5 * dof;
+  // Wilson-Hilferty start, then safeguarded Newton on P(a, x/2) = p
+  const double t = std::sqrt(2.0) * [&] {  // inverse error function via Newton on erf
+    double y = 2.0 * p - 1.0, z = 0.0;
+    for (int i = 0; i < 60; ++i) z -= (std::erf(z) - y) / (2.0 / std::sqrt(M_PI) * std::exp(-z * z));
+    return z;
+  }();
+  double x = dof * std::pow(1.0 - 2.0 / (9.0 * dof) + t * std::sqrt(2.0 / (9.0 * dof)), 3.0);
+  if (!(x > 0.0)) x = 1e-3;
+  double lo = 0.0, hi = INFINITY;
+  const double lg = std::lgamma(a);
+  for (int it = 0; it < 200; ++it) {
+    const double f = gammap(a, 0.5 * x) - p;
+    if (f > 0.0) hi = std::min(hi, x); else lo = std::max(lo, x);
+    const double pdf = 0.5 * std::exp((a - 1.0) * std::log(0.5 * x) - 0.5 * x - lg);
+    double xn = x - f / pdf;
+    if (!(xn > lo && xn < hi)) xn = std::isinf(hi) ? 2.0 * x : 0.5 * (lo + hi);
+    if (std::fabs(xn - x) <= 1e-15 * std::fabs(x)) { x = xn; break; }
+    x = xn;
+  }
+  return x;
+}
+
+// ---- filter object -----------------------------------------------------------------------------------
+struct ListDev {
+  int cap_tracks = 0, cap_obs = 0;
+  int n = 0, n_obs = 0, Lmax = 0;
+  int* d_off = nullptr;
+  double* d_obs = nullptr;
+  std::vector<int> h_off;
+};
+
+struct xb_filter {
+  xb_config cfg;
+  int M, F, N, LX, NS, NG;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // ring buffer (state_buffer.cpp)
+  double* d_xv = nullptr;      // NS x LX
+  double* d_strip = nullptr;   // NS x 15 x N
+  std::vector<double> h_time;  // mirror of State::time_
+  std::vector<double> h_am;    // mirror of a_m (accel-spike substitution, ekf.cpp:119-128)
+  std::vector<int> slot_gen;
+  int tail = 0, head = 0, n_valid = 0;
+  int status = 0;  // 0 not initialised, 1 stand-by, 2 initialised
+  unsigned last_seq = 0;
+  // covariance generations
+  double* d_Pgen = nullptr;  // NG x N x N
+  int cur_gen = 0;
+  // work state
+  double* d_xw = nullptr;   // LX
+  double* d_WA = nullptr;   // N x N scratch / assembled covariance
+  double* d_Pw = nullptr;   // points at WA or a generation
+  double* d_corr = nullptr; // N correction_total
+  double* d_delta = nullptr;
+  double* d_FQ = nullptr;
+  // state manager bookkeeping (state_manager.h)
+  int n_poses = 0, n_features = 0, filled_before = 0;
+  std::vector<int> anchor;
+  // measurement
+  double meas_time = 0.0;
+  ListDev l_slam, l_msckf, l_short, l_newstd, l_newms;
+  std::vector<int> lost;
+  double* d_slam_chi2 = nullptr;
+  double* h_pin = nullptr;  // pinned staging
+  size_t pin_bytes = 0;
+  // device tables / scratch
+  double* d_chi95 = nullptr;
+  int chi_len = 0;
+  // track outputs (mode 0 / mode 1)
+  double *d_ivd0, *d_gamma0, *d_B0, *d_J0;
+  int* d_inl0;
+  double *d_ivd1, *d_gamma1, *d_B1, *d_J1, *d_H1, *d_H2, *d_D1;
+  int* d_inl1;
+  // slam rows
+  int* d_scols; double *d_svals, *d_sres, *d_sgamma; int* d_sinl; int* d_anchor;
+  // gram
+  double *d_partB, *d_partD, *d_blocks, *d_Tg, *d_Rg;
+  int gcols_pad = 0, grows_pad = 0, nz = 1;
+  int* d_flags = nullptr;
+  int* d_err = nullptr;
+  // kalman tall buffer
+  double* d_T = nullptr;
+  size_t T_doubles = 0;
+  int last_m = 0, last_nslam = 0, last_which = 0;
+  bool constructed_any = false;
+  // manage
+  int *d_rowmap, *d_ccols, *d_featsrc, *d_reanch;
+  double *d_cvals, *d_mscratch, *d_Tm, *d_T2;
+  int* h_ipin = nullptr;
+  // feature-init scratch
+  double* d_fscratch = nullptr;
+  // dense-H scratch
+  double* d_Hdense = nullptr; size_t Hdense_doubles = 0;
+  void* d_tcws = nullptr;
+  std::vector<void*> allocs;
+};
+
+static int dalloc(xb_filter* f, void** p, size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) return fail(XB_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  cudaMemset(*p, 0, bytes);
+  f->allocs.push_back(*p);
+  return 0;
+}
+#define DA(ptr, count, type)                                                        \
+  do {                                                                              \
+    int rc_ = dalloc(f, (void**)&(ptr), sizeof(type) * (size_t)(count));            \
+    if (rc_) return rc_;                                                            \
+  } while (0)
+
+static int pad32(int x) { return (x + 31) / 32 * 32; }
+
+extern "C" void xb_default_config(xb_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->n_poses_max = 15;      // vio/types.h:141
+  c->n_features_max = 15;   // vio/types.h:146
+  c->n_slots = 250;         // vio/types.h:188
+  c->n_generations = 4;
+  c->device = 0;
+  c->max_tracks = 1024;
+  c->max_obs = 0;
+  c->iekf_iter = 1;
+  c->min_track_length = 10;
+  c->delta_seq_imu = 1;
+  c->g[0] = 0.0; c->g[1] = 0.0; c->g[2] = -9.81;
+  c->n_w = 0.0083; c->n_bw = 0.00083; c->n_a = 0.0013; c->n_ba = 0.00013;  // common/types.h:65-85 (n_ba: intended value)
+  c->a_m_max = 50.0;
+  c->time_margin = 0.005;
+  c->sigma_img = 1.0 / 320.0;
+  c->sigma_range = 0.05;
+  c->rho_0 = 0.5;
+  c->sigma_rho_0 = 0.25;
+  c->sigma_landmark = 0.0;
+  c->ci_msckf_w = -1.0;
+  c->ci_slam_w = -1.0;
+  c->downdate_precision = 0;
+}
+
+extern "C" const char* xb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* xb_version(void) { return "xb200 0.1 (sm_100a)"; }
+extern "C" long long xb_kernel_launches(const xb_filter*) { return g_launches; }
+
+static int list_alloc(xb_filter* f, ListDev& l, int cap_tracks, int cap_obs) {
+  l.cap_tracks = cap_tracks;
+  l.cap_obs = cap_obs;
+  DA(l.d_off, cap_tracks + 1, int);
+  DA(l.d_obs, 2 * (size_t)cap_obs, double);
+  return 0;
+}
+
+extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
+  if (!cfg || !out) return fail(XB_E_INVALID, "null argument");
+  if (cfg->n_poses_max < 1 || cfg->n_poses_max > 64 || cfg->n_features_max < 0 || cfg->n_slots < 1)
+    return fail(XB_E_INVALID, "n_poses_max must be in [1,64], n_features_max >= 0, n_slots >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(XB_E_CUDA, "no CUDA device: libxb200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(XB_E_INVALID, "bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) return fail(XB_E_CUDA, "libxb200 is built for sm_100a only");
+
+  xb_filter* f = new xb_filter();
+  f->cfg = *cfg;
+  f->M = cfg->n_poses_max;
+  f->F = cfg->n_features_max;
+  f->N = XB_NERR(f->M, f->F);
+  f->LX = XB_XVEC_LEN(f->M, f->F);
+  f->NS = cfg->n_slots;
+  f->NG = std::max(2, cfg->n_generations);
+  const int M = f->M, F = f->F, N = f->N, LX = f->LX, NS = f->NS;
+  if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete f;
+    return fail(XB_E_CUDA, "cudaStreamCreate failed");
+  }
+  f->own_stream = true;
+  const int W = 6 * M + 1;
+  const int maxT = std::max(1, cfg->max_tracks);
+  const int maxO = cfg->max_obs > 0 ? cfg->max_obs : maxT * M;
+  const int maxT1 = std::max(1, F), maxO1 = std::max(1, F) * M;
+
+  DA(f->d_xv, (size_t)NS * LX, double);
+  DA(f->d_strip, (size_t)NS * 15 * N, double);
+  DA(f->d_Pgen, (size_t)f->NG * N * N, double);
+  DA(f->d_xw, LX, double);
+  DA(f->d_WA, (size_t)N * N, double);
+  DA(f->d_corr, N, double);
+  DA(f->d_delta, N, double);
+  DA(f->d_FQ, (size_t)128 * 450, double);
+  f->h_time.assign(NS, -1.0);
+  f->h_am.assign(3 * (size_t)NS, 0.0);
+  f->slot_gen.assign(NS, -1);
+  f->anchor.assign(std::max(F, 1), -1);
+
+  int rc;
+  if ((rc = list_alloc(f, f->l_slam, std::max(1, F), std::max(1, F) * 4 * M))) return rc;
+  if ((rc = list_alloc(f, f->l_msckf, maxT, maxO))) return rc;
+  if ((rc = list_alloc(f, f->l_short, maxT, maxO))) return rc;
+  if ((rc = list_alloc(f, f->l_newstd, maxT1, maxO1))) return rc;
+  if ((rc = list_alloc(f, f->l_newms, maxT1, maxO1))) return rc;
+  DA(f->d_slam_chi2, std::max(1, F), double);
+
+  f->chi_len = 2 * 64 + 2;
+  {
+    std::vector<double> tab(f->chi_len, 0.0);
+    for (int d = 1; d < f->chi_len; ++d) tab[d] = xb_chi2_quantile(0.95, (double)d);
+    DA(f->d_chi95, f->chi_len, double);
+    CK(cudaMemcpy(f->d_chi95, tab.data(), sizeof(double) * f->chi_len, cudaMemcpyHostToDevice));
+  }
+  DA(f->d_ivd0, 3 * (size_t)maxT, double);
+  DA(f->d_gamma0, maxT, double);
+  DA(f->d_inl0, maxT, int);
+  DA(f->d_B0, (size_t)maxT * 3 * W, double);
+  DA(f->d_J0, 14 * (size_t)maxO, double);
+  DA(f->d_ivd1, 3 * (size_t)maxT1, double);
+  DA(f->d_gamma1, maxT1, double);
+  DA(f->d_inl1, maxT1, int);
+  DA(f->d_B1, (size_t)maxT1 * 3 * W, double);
+  DA(f->d_J1, 14 * (size_t)maxO1, double);
+  DA(f->d_H1, (size_t)maxT1 * 3 * W, double);
+  DA(f->d_H2, 9 * (size_t)maxT1, double);
+  DA(f->d_D1, (size_t)2 * maxO1 * W, double);
+  DA(f->d_scols, 15 * (size_t)std::max(1, F), int);
+  DA(f->d_svals, 30 * (size_t)std::max(1, F), double);
+  DA(f->d_sres, 2 * (size_t)std::max(1, F), double);
+  DA(f->d_sgamma, std::max(1, F), double);
+  DA(f->d_sinl, std::max(1, F), int);
+  DA(f->d_anchor, std::max(1, F), int);
+
+  const int tiles = (W + 63) / 64;
+  f->nz = std::max(1, std::min(32, (148 + tiles * tiles - 1) / (tiles * tiles)));
+  DA(f->d_partB, (size_t)f->nz * W * W, double);
+  DA(f->d_partD, (size_t)f->nz * W * W, double);
+  DA(f->d_blocks, 28 * (size_t)M, double);
+  f->gcols_pad = pad32(6 * M);
+  f->grows_pad = f->gcols_pad + 32;
+  DA(f->d_Tg, (size_t)f->grows_pad * f->gcols_pad, double);
+  DA(f->d_Rg, (size_t)f->gcols_pad * f->gcols_pad, double);
+
+  const int m_max = std::max(6 * M + 2 * F, N);  // dense-H path allows up to N rows
+  const int m_pad = pad32(m_max), n_pad = pad32(N);
+  f->T_doubles = (size_t)(m_pad + n_pad + 32) * m_pad;
+  DA(f->d_T, f->T_doubles, double);
+  DA(f->d_flags, (size_t)((m_pad + n_pad + 32) / 32) * (m_pad / 32) + 64, int);
+  DA(f->d_err, 4, int);
+
+  DA(f->d_rowmap, N, int);
+  DA(f->d_ccols, 15 * (size_t)(6 + 3 * std::max(1, F)), int);
+  DA(f->d_cvals, 15 * (size_t)(6 + 3 * std::max(1, F)), double);
+  DA(f->d_featsrc, std::max(1, F), int);
+  DA(f->d_reanch, std::max(1, F), int);
+  DA(f->d_mscratch, 7 * (size_t)M + 3 * (size_t)F + 8, double);
+  DA(f->d_Tm, (size_t)(6 + 3 * std::max(1, F)) * N, double);
+  DA(f->d_T2, (size_t)(6 + 3 * std::max(1, F)) * 15, double);
+  {
+    const size_t n3 = 3 * (size_t)maxT1;
+    DA(f->d_fscratch, n3 * 6 * M + 9 * (size_t)maxT1 + n3 * N + n3 * n3, double);
+  }
+  f->Hdense_doubles = (size_t)m_pad * N + 2 * (size_t)m_pad + 64;
+  DA(f->d_Hdense, f->Hdense_doubles, double);
+  DA(f->d_tcws, (size_t)n_pad * m_pad * 3 * 4 + 1024, char);
+
+  // pinned staging: measurement lists + manage tables
+  f->pin_bytes = sizeof(double) * (2 * (size_t)(maxO * 2 + maxO1 * 2 + std::max(1, F) * 4 * M) + (size_t)LX + 4096) +
+                 sizeof(int) * (size_t)(2 * maxT + 2 * maxT1 + 4 * std::max(1, F) + 64);
+  if (cudaMallocHost((void**)&f->h_pin, f->pin_bytes) != cudaSuccess) return fail(XB_E_CUDA, "cudaMallocHost failed");
+  if (cudaMallocHost((void**)&f->h_ipin, sizeof(int) * (size_t)(N + 16 * (6 + 3 * std::max(1, F)) + 2 * std::max(1, F) + 64)) !=
+      cudaSuccess)
+    return fail(XB_E_CUDA, "cudaMallocHost failed");
+  CK(cudaDeviceSynchronize());
+  *out = f;
+  return XB_OK;
+}
+
+extern "C" int xb_destroy(xb_filter* f) {
+  if (!f) return XB_OK;
+  cudaSetDevice(f->cfg.device);
+  cudaStreamSynchronize(f->stream);
+  for (void* p : f->allocs) cudaFree(p);
+  if (f->h_pin) cudaFreeHost(f->h_pin);
+  if (f->h_ipin) cudaFreeHost(f->h_ipin);
+  if (f->own_stream) cudaStreamDestroy(f->stream);
+  delete f;
+  return XB_OK;
+}
+
+extern "C" int xb_set_stream(xb_filter* f, void* s) {
+  if (!f) return fail(XB_E_INVALID, "null filter");
+  cudaStreamSynchronize(f->stream);
+  if (f->own_stream) cudaStreamDestroy(f->stream);
+  f->stream = (cudaStream_t)s;
+  f->own_stream = false;
+  return XB_OK;
+}
+extern "C" int xb_synchronize(xb_filter* f) {
+  CK(cudaStreamSynchronize(f->stream));
+  int err = 0;
+  CK(cudaMemcpy(&err, f->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    cudaMemset(f->d_err, 0, sizeof(int));
+    return fail(XB_E_RUNTIME, "tile Cholesky dependency wait timed out");
+  }
+  return XB_OK;
+}
+extern "C" int xb_n_error_states(const xb_filter* f) { return f->N; }
+extern "C" int xb_xvec_len(const xb_filter* f) { return f->LX; }
+extern "C" int xb_ekf_newest_slot(const xb_filter* f) { return f->tail; }
+
+// ---- covariance transfer helpers -----------------------------------------------------------------------
+static int upload_cov(xb_filter* f, const double* cov, int layout, double* d_dst) {
+  const size_t nn = (size_t)f->N * f->N;
+  if (layout == XB_COL_MAJOR) {
+    CK(cudaMemcpyAsync(f->d_T, cov, sizeof(double) * nn, cudaMemcpyHostToDevice, f->stream));
+    transpose(f->stream, f->d_T, d_dst, f->N, f->N);
+  } else {
+    CK(cudaMemcpyAsync(d_dst, cov, sizeof(double) * nn, cudaMemcpyHostToDevice, f->stream));
+  }
+  return 0;
+}
+static int download_cov(xb_filter* f, const double* d_src, double* cov, int layout) {
+  const size_t nn = (size_t)f->N * f->N;
+  if (layout == XB_COL_MAJOR) {
+    transpose(f->stream, d_src, f->d_T, f->N, f->N);
+    CK(cudaMemcpyAsync(cov, f->d_T, sizeof(double) * nn, cudaMemcpyDeviceToHost, f->stream));
+  } else {
+    CK(cudaMemcpyAsync(cov, d_src, sizeof(double) * nn, cudaMemcpyDeviceToHost, f->stream));
+  }
+  CK(cudaStreamSynchronize(f->stream));
+  return 0;
+}
+
+// ---- StateBuffer (state_buffer.cpp) ----------------------------------------------------------------------
+static int next_idx(const xb_filter* f, int i) { return (i + 1) % f->NS; }
+static int prev_idx(const xb_filter* f, int i) { return i == 0 ? f->NS - 1 : i - 1; }
+static int closest_idx(const xb_filter* f, double t) {  // state_buffer.cpp:26-63
+  if (t > f->h_time[f->tail] + f->cfg.time_margin) return -1;
+  if (t < f->h_time[f->head] - f->cfg.time_margin) return -1;
+  double off = std::fabs(t - f->h_time[f->tail]);
+  int idx = prev_idx(f, f->tail);
+  int count = 1;
+  while (std::fabs(t - f->h_time[idx]) < off && count < f->n_valid) {
+    off = std::fabs(t - f->h_time[idx]);
+    idx = prev_idx(f, idx);
+    ++count;
+  }
+  return next_idx(f, idx);
+}
+
+extern "C" int xb_sm_n_poses(const xb_filter* f) { return f->n_poses; }
+extern "C" int xb_sm_n_features(const xb_filter* f) { return f->n_features; }
+extern "C" int xb_sm_anchor_idxs(const xb_filter* f, int* out) {
+  for (int i = 0; i < f->F; ++i) out[i] = f->anchor[i];
+  return XB_OK;
+}
+extern "C" int xb_sm_set(xb_filter* f, int n_poses, int n_features, const int* anchor_idxs, int filled_before) {
+  if (n_poses < 0 || n_poses > f->M || n_features < 0 || n_features > f->F) return fail(XB_E_INVALID, "bad counts");
+  f->n_poses = n_poses;
+  f->n_features = n_features;
+  f->filled_before = filled_before;
+  for (int i = 0; i < f->F; ++i) f->anchor[i] = anchor_idxs ? anchor_idxs[i] : -1;
+  return XB_OK;
+}
+
+// ---- Ekf::initializeFromState (ekf.cpp:43-64) -------------------------------------------------------------
+extern "C" int xb_ekf_initialize_from_state(xb_filter* f, const double* xvec, const double* cov, int layout) {
+  if (!f || !xvec || !cov) return fail(XB_E_INVALID, "null argument");
+  CK(cudaSetDevice(f->cfg.device));
+  // StateBuffer::resetFromState (state_buffer.cpp:90-102)
+  std::fill(f->h_time.begin(), f->h_time.end(), -1.0);
+  std::fill(f->slot_gen.begin(), f->slot_gen.end(), -1);
+  f->tail = f->head = 0;
+  f->n_valid = 1;
+  f->cur_gen = 0;
+  CK(cudaMemcpyAsync(f->d_xv, xvec, sizeof(double) * f->LX, cudaMemcpyHostToDevice, f->stream));
+  int rc = upload_cov(f, cov, layout, f->d_Pgen);
+  if (rc) return rc;
+  launch_extract_strip(f->stream, f->N, f->d_Pgen, f->d_strip);
+  CK(cudaStreamSynchronize(f->stream));
+  f->h_time[0] = xvec[XV_TIME];
+  for (int e = 0; e < 3; ++e) f->h_am[e] = xvec[XV_AM + e];
+  f->slot_gen[0] = 0;
+  f->status = 1;
+  // VIO::initAtTime clears the state manager (vio.cpp:54-111, state_manager.cpp:22-29)
+  f->n_poses = 0;
+  f->n_features = 0;
+  f->filled_before = 0;
+  std::fill(f->anchor.begin(), f->anchor.end(), -1);
+  return XB_OK;
+}
+
+static PropParams prop_params(const xb_filter* f) {
+  PropParams pp;
+  for (int e = 0; e < 3; ++e) pp.g[e] = f->cfg.g[e];
+  pp.n_w = f->cfg.n_w; pp.n_bw = f->cfg.n_bw; pp.n_a = f->cfg.n_a; pp.n_ba = f->cfg.n_ba;
+  return pp;
+}
+
+static void propagate_chain(xb_filter* f, int start, int n_steps, const ImuSample& in) {
+  ImuSample none{};
+  int done = 0;
+  while (done < n_steps) {
+    const int n = std::min(128, n_steps - done);
+    const bool last = done + n == n_steps;
+    launch_propagate(f->stream, f->d_xv, f->LX, f->d_strip, f->N, f->NS, (start + done) % f->NS, n, last ? in : none,
+                     prop_params(f), f->d_FQ);
+    done += n;
+  }
+}
+
+// ---- Ekf::processImu (ekf.cpp:66-140) ----------------------------------------------------------------------
+extern "C" int xb_ekf_process_imu(xb_filter* f, double t, unsigned seq, const double w[3], const double a[3],
+                                  double* xvec_out) {
+  if (!f) return fail(XB_E_INVALID, "null filter");
+  if (f->status == 0) return 0;
+  const double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  if (f->status == 1) {
+    if (!(an < f->cfg.a_m_max)) return 0;
+    double imu[8] = {w[0], w[1], w[2], a[0], a[1], a[2], t, (double)seq};
+    double* xl = f->d_xv + (size_t)f->tail * f->LX;
+    CK(cudaMemcpyAsync(xl + XV_WM, imu, sizeof(double) * 8, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    f->h_time[f->tail] = t;
+    for (int e = 0; e < 3; ++e) f->h_am[3 * f->tail + e] = a[e];
+    f->last_seq = seq;
+    f->status = 2;
+    if (xvec_out) return xb_ekf_get_state(f, f->tail, xvec_out) < 0 ? XB_E_CUDA : 1;
+    return 1;
+  }
+  if (t <= f->h_time[f->tail]) return 0;
+  f->last_seq = seq;
+  const int last = f->tail;
+  double as[3] = {a[0], a[1], a[2]};
+  if (!(an < f->cfg.a_m_max))
+    for (int e = 0; e < 3; ++e) as[e] = f->h_am[3 * last + e];
+  // StateBuffer::enqueueInPlace (state_buffer.cpp:76-88)
+  f->tail = (f->tail + 1) % f->NS;
+  if (f->n_valid < f->NS) ++f->n_valid; else f->head = (f->head + 1) % f->NS;
+  ImuSample in;
+  in.valid = 1;
+  in.t = t;
+  in.seq = (double)seq;
+  for (int e = 0; e < 3; ++e) { in.w[e] = w[e]; in.a[e] = as[e]; }
+  propagate_chain(f, last, 1, in);
+  f->h_time[f->tail] = t;
+  for (int e = 0; e < 3; ++e) f->h_am[3 * f->tail + e] = as[e];
+  f->slot_gen[f->tail] = f->slot_gen[last];
+  if (xvec_out) return xb_ekf_get_state(f, f->tail, xvec_out) < 0 ? XB_E_CUDA : 1;
+  return 1;
+}
+
+extern "C" int xb_ekf_get_state(xb_filter* f, int slot, double* xvec_out) {
+  if (slot < 0) slot = f->tail;
+  if (slot >= f->NS) return fail(XB_E_INVALID, "bad slot");
+  CK(cudaMemcpyAsync(xvec_out, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return XB_OK;
+}
+extern "C" int xb_ekf_get_covariance(xb_filter* f, int slot, double* cov_out, int layout) {
+  if (slot < 0) slot = f->tail;
+  if (slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid covariance");
+  launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
+                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_WA);
+  return download_cov(f, f->d_WA, cov_out, layout);
+}
+
+// ---- measurement upload ---------------------------------------------------------------------------------------
+static int stage_list(xb_filter* f, ListDev& l, const xb_track_list& in, char*& pin, const char* name) {
+  l.n = in.n_tracks;
+  l.n_obs = 0;
+  l.Lmax = 0;
+  if (in.n_tracks <= 0) { l.n = 0; return 0; }
+  if (!in.off || !in.obs) return fail(XB_E_INVALID, std::string(name) + ": null track list");
+  if (in.n_tracks > l.cap_tracks) return fail(XB_E_CAPACITY, std::string(name) + ": too many tracks");
+  l.n_obs = in.off[in.n_tracks] - in.off[0];
+  if (l.n_obs > l.cap_obs) return fail(XB_E_CAPACITY, std::string(name) + ": too many observations");
+  l.h_off.assign(in.off, in.off + in.n_tracks + 1);
+  for (int t = 0; t < in.n_tracks; ++t) l.Lmax = std::max(l.Lmax, in.off[t + 1] - in.off[t]);
+  int* po = (int*)pin;
+  const int o0 = in.off[0];
+  for (int t = 0; t <= in.n_tracks; ++t) po[t] = in.off[t] - o0;
+  for (int t = 0; t <= in.n_tracks; ++t) l.h_off[t] -= o0;
+  pin += sizeof(int) * (((size_t)in.n_tracks + 1 + 1) / 2 * 2);
+  double* pd = (double*)pin;
+  std::memcpy(pd, in.obs + 2 * (size_t)o0, sizeof(double) * 2 * (size_t)l.n_obs);
+  pin += sizeof(double) * 2 * (size_t)l.n_obs;
+  CK(cudaMemcpyAsync(l.d_off, po, sizeof(int) * ((size_t)in.n_tracks + 1), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(l.d_obs, pd, sizeof(double) * 2 * (size_t)l.n_obs, cudaMemcpyHostToDevice, f->stream));
+  return 0;
+}
+
+extern "C" int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m) {
+  if (!f || !m) return fail(XB_E_INVALID, "null argument");
+  CK(cudaSetDevice(f->cfg.device));
+  CK(cudaStreamSynchronize(f->stream));  // staging buffer reuse
+  f->meas_time = m->timestamp;
+  char* pin = (char*)f->h_pin;
+  int rc;
+  if ((rc = stage_list(f, f->l_slam, m->slam, pin, "slam"))) return rc;
+  if ((rc = stage_list(f, f->l_msckf, m->msckf, pin, "msckf"))) return rc;
+  if ((rc = stage_list(f, f->l_short, m->msckf_short, pin, "msckf_short"))) return rc;
+  if ((rc = stage_list(f, f->l_newstd, m->new_slam_std, pin, "new_slam_std"))) return rc;
+  if ((rc = stage_list(f, f->l_newms, m->new_msckf_slam, pin, "new_msckf_slam"))) return rc;
+  if (f->l_msckf.Lmax > 64 || f->l_short.Lmax > 64 || f->l_newms.Lmax > 64)
+    return fail(XB_E_CAPACITY, "track longer than 64 observations");
+  f->lost.assign(m->lost_slam_idxs, m->lost_slam_idxs + std::max(0, m->n_lost));
+  if (f->l_slam.n > 0) {  // chi2(0.9, 2*track_size) per SLAM track (slam_update.cpp:196-197)
+    double* pc = (double*)pin;
+    for (int j = 0; j < f->l_slam.n; ++j)
+      pc[j] = xb_chi2_quantile(0.9, 2.0 * (f->l_slam.h_off[j + 1] - f->l_slam.h_off[j]));
+    CK(cudaMemcpyAsync(f->d_slam_chi2, pc, sizeof(double) * f->l_slam.n, cudaMemcpyHostToDevice, f->stream));
+  }
+  return XB_OK;
+}
+
+// ---- work state ---------------------------------------------------------------------------------------------------
+extern "C" int xb_work_load(xb_filter* f, int slot) {
+  if (slot < 0 || slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid state");
+  CK(cudaMemcpyAsync(f->d_xw, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
+  launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
+                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_WA);
+  f->d_Pw = f->d_WA;
+  return XB_OK;
+}
+// claim the next covariance generation as destination; slots still pointing at it lose their state
+static double* claim_generation(xb_filter* f) {
+  f->cur_gen = (f->cur_gen + 1) % f->NG;
+  for (int s = 0; s < f->NS; ++s)
+    if (f->slot_gen[s] == f->cur_gen) { f->slot_gen[s] = -1; }
+  return f->d_Pgen + (size_t)f->cur_gen * f->N * f->N;
+}
+extern "C" int xb_work_store(xb_filter* f, int slot) {
+  if (slot < 0 || slot >= f->NS) return fail(XB_E_INVALID, "bad slot");
+  const size_t nn = (size_t)f->N * f->N;
+  bool in_gen = f->d_Pw >= f->d_Pgen && f->d_Pw < f->d_Pgen + (size_t)f->NG * nn;
+  if (!in_gen) {
+    double* g = claim_generation(f);
+    CK(cudaMemcpyAsync(g, f->d_Pw, sizeof(double) * nn, cudaMemcpyDeviceToDevice, f->stream));
+    f->d_Pw = g;
+  }
+  CK(cudaMemcpyAsync(f->d_xv + (size_t)slot * f->LX, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
+  launch_extract_strip(f->stream, f->N, f->d_Pw, f->d_strip + (size_t)slot * 15 * f->N);
+  f->slot_gen[slot] = f->cur_gen;
+  return XB_OK;
+}
+extern "C" int xb_work_set(xb_filter* f, const double* xvec, const double* cov, int layout) {
+  CK(cudaSetDevice(f->cfg.device));
+  if (xvec) CK(cudaMemcpyAsync(f->d_xw, xvec, sizeof(double) * f->LX, cudaMemcpyHostToDevice, f->stream));
+  if (cov) {
+    int rc = upload_cov(f, cov, layout, f->d_WA);
+    if (rc) return rc;
+    f->d_Pw = f->d_WA;
+  }
+  CK(cudaStreamSynchronize(f->stream));
+  return XB_OK;
+}
+extern "C" int xb_work_get(xb_filter* f, double* xvec_out, double* cov_out, int layout) {
+  if (xvec_out) CK(cudaMemcpyAsync(xvec_out, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToHost, f->stream));
+  if (cov_out) {
+    if (!f->d_Pw) return fail(XB_E_INVALID, "no work covariance");
+    if (f->d_Pw == f->d_WA && layout == XB_ROW_MAJOR) {
+      CK(cudaMemcpyAsync(cov_out, f->d_Pw, sizeof(double) * (size_t)f->N * f->N, cudaMemcpyDeviceToHost, f->stream));
+    } else {
+      int rc = download_cov(f, f->d_Pw, cov_out, layout);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaStreamSynchronize(f->stream));
+  return XB_OK;
+}
+
+// ---- StateManager::manage (state_manager.cpp:31-149): integer bookkeeping here, arithmetic on the device ----------
+extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
+  const int M = f->M, F = f->F, N = f->N;
+  if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  int* ip = f->h_ipin;
+  int* rowmap = ip;                       // N
+  int* ccols = rowmap + N;                // 15 * n_comp
+  // feature removal: compaction map over ALL F slots (state_manager.cpp:52-112)
+  std::vector<int> src(F), anc(F);
+  for (int k = 0; k < F; ++k) { src[k] = k; anc[k] = f->anchor[k]; }
+  std::vector<unsigned> del(lost_idxs, lost_idxs + std::max(0, n_lost));
+  std::sort(del.begin(), del.end());
+  int nf = f->n_features;
+  for (size_t i = del.size(); i > 0; --i) {
+    const int idx = (int)del[i - 1];
+    if (idx < 0 || idx >= F) return fail(XB_E_INVALID, "lost SLAM feature index out of range");
+    src.erase(src.begin() + idx);
+    src.push_back(-1);
+    anc.erase(anc.begin() + idx);
+    anc.push_back(-1);
+    --nf;
+  }
+  const int slide = f->n_poses == M;
+  std::vector<int> reanch;
+  if (slide)
+    for (int k = 0; k < nf; ++k)
+      if (anc[k] == 0) reanch.push_back(k);
+  const int n_comp = 6 + 3 * (int)reanch.size();
+  const int pos = slide ? M - 1 : f->n_poses;
+  const int P0 = XB_CORE, A0 = XB_CORE + 3 * M, F0 = XB_CORE + 6 * M;
+  // composite row map
+  for (int i = 0; i < XB_CORE; ++i) rowmap[i] = i;
+  for (int s = 0; s < M; ++s)
+    for (int c = 0; c < 3; ++c) {
+      int vp, va;
+      if (s == pos) { vp = -2 - c; va = -2 - (3 + c); }
+      else if (s < pos) {
+        const int so = slide ? s + 1 : s;
+        vp = P0 + 3 * so + c;
+        va = A0 + 3 * so + c;
+      } else {
+        // slots beyond the new clone: identity once the window has been filled, else zeroed by J (state_manager.cpp:276-284)
+        vp = f->filled_before ? P0 + 3 * s + c : -1;
+        va = f->filled_before ? A0 + 3 * s + c : -1;
+        if (slide) { vp = -1; va = -1; }
+      }
+      rowmap[P0 + 3 * s + c] = vp;
+      rowmap[A0 + 3 * s + c] = va;
+    }
+  for (int k = 0; k < F; ++k)
+    for (int c = 0; c < 3; ++c) {
+      int v;
+      const bool active = k < nf;
+      if (!active && !f->filled_before) v = -1;
+      else v = src[k] >= 0 ? F0 + 3 * src[k] + c : -1;
+      rowmap[F0 + 3 * k + c] = v;
+    }
+  for (int e = 0; e < 15 * n_comp; ++e) ccols[e] = 0;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) { ccols[r * 15 + c] = c; ccols[r * 15 + 3 + c] = 6 + c; }
+    for (int c = 0; c < 3; ++c) ccols[(3 + r) * 15 + c] = 6 + c;
+  }
+  for (size_t i = 0; i < reanch.size(); ++i) {
+    const int k = reanch[i];
+    for (int r = 0; r < 3; ++r) {
+      int* cc = ccols + (6 + 3 * i + r) * 15;
+      for (int c = 0; c < 3; ++c) {
+        cc[c] = P0 + 3 * (M - 1) + c;
+        cc[3 + c] = A0 + 3 * (M - 1) + c;
+        cc[6 + c] = P0 + c;
+        cc[9 + c] = A0 + c;
+        cc[12 + c] = F0 + 3 * src[k] + c;
+      }
+      rowmap[F0 + 3 * k + r] = -2 - (6 + 3 * (int)i + r);
+    }
+  }
+  int* fs = ccols + 15 * n_comp;
+  int* ra = fs + F;
+  for (int k = 0; k < F; ++k) fs[k] = src[k];
+  for (size_t i = 0; i < reanch.size(); ++i) ra[i] = reanch[i];
+  CK(cudaStreamSynchronize(f->stream));  // pinned table reuse
+  CK(cudaMemcpyAsync(f->d_rowmap, rowmap, sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_ccols, ccols, sizeof(int) * 15 * n_comp, cudaMemcpyHostToDevice, f->stream));
+  if (F > 0) CK(cudaMemcpyAsync(f->d_featsrc, fs, sizeof(int) * F, cudaMemcpyHostToDevice, f->stream));
+  if (!reanch.empty())
+    CK(cudaMemcpyAsync(f->d_reanch, ra, sizeof(int) * reanch.size(), cudaMemcpyHostToDevice, f->stream));
+  // destination: a fresh generation (or WA when the source already is a generation buffer)
+  double* src_P = f->d_Pw;
+  double* dst_P = (src_P == f->d_WA) ? claim_generation(f) : f->d_WA;
+  launch_manage_dev(f->stream, M, F, N, f->n_poses, nf, slide, (int)reanch.size(), f->d_featsrc, f->d_reanch, f->d_rowmap,
+                    f->d_ccols, f->d_cvals, f->d_mscratch, f->d_xw, src_P, dst_P, f->d_Tm, f->d_T2);
+  f->d_Pw = dst_P;
+  // bookkeeping after the call
+  for (int k = 0; k < F; ++k) f->anchor[k] = anc[k];
+  f->n_features = nf;
+  if (slide) {
+    for (size_t i = 0; i < reanch.size(); ++i) f->anchor[reanch[i]] = M - 1;
+    for (int k = 0; k < nf; ++k) f->anchor[k] -= 1;  // slideWindow, state_manager.cpp:530-533
+    f->n_poses -= 1;
+  }
+  if (pos + 1 == M) f->filled_before = 1;
+  f->n_poses += 1;
+  return XB_OK;
+}
+
+// ---- VioUpdater::constructUpdate / constructShortMsckfUpdate ----------------------------------------------------------
+static TrackParams track_params(xb_filter* f, const ListDev& l, int mode) {
+  TrackParams tp{};
+  tp.xv = f->d_xw;
+  tp.M = f->M;
+  tp.n_poses = f->n_poses;
+  tp.P = f->d_Pw;
+  tp.ldp = f->N;
+  tp.off = l.d_off;
+  tp.obs = l.d_obs;
+  tp.n_tracks = l.n;
+  tp.mode = mode;
+  tp.Lmax = std::max(2, l.Lmax);
+  tp.var_img = f->cfg.sigma_img * f->cfg.sigma_img;
+  tp.chi2_95 = f->d_chi95;
+  tp.gn_term = 1e-5;   // vio_updater.cpp:283-285
+  tp.gn_max_iter = 10;
+  if (mode == 0) {
+    tp.ivd = f->d_ivd0; tp.gamma = f->d_gamma0; tp.inlier = f->d_inl0; tp.B = f->d_B0; tp.Jout = f->d_J0;
+    tp.H1 = nullptr; tp.H2 = nullptr; tp.D = nullptr;
+  } else {
+    tp.ivd = f->d_ivd1; tp.gamma = f->d_gamma1; tp.inlier = f->d_inl1; tp.B = f->d_B1; tp.Jout = f->d_J1;
+    tp.H1 = f->d_H1; tp.H2 = f->d_H2; tp.D = f->d_D1;
+  }
+  return tp;
+}
+
+extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
+  if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  const int M = f->M;
+  const ListDev& l0 = which == 0 ? f->l_msckf : f->l_short;
+  const int n0 = l0.n, n1 = which == 0 ? f->l_newms.n : 0, ns = which == 0 ? f->l_slam.n : 0;
+  if (ns > f->n_features) return fail(XB_E_INVALID, "more SLAM tracks than SLAM features in the state");
+  f->last_which = which;
+  f->last_nslam = ns;
+  f->constructed_any = (n0 + n1 + ns) > 0;
+  if (!f->constructed_any) return XB_OK;
+  if (f->n_poses < 1) return fail(XB_E_INVALID, "empty pose window");
+  const size_t gbytes = sizeof(double) * (size_t)f->grows_pad * f->gcols_pad;
+  if (n0 + n1 > 0) {
+    if (n0 > 0 && launch_tracks(f->stream, track_params(f, l0, 0))) return fail(XB_E_CAPACITY, "track kernel shared memory");
+    if (n1 > 0 && launch_tracks(f->stream, track_params(f, f->l_newms, 1))) return fail(XB_E_CAPACITY, "track kernel shared memory");
+    GramParams gp{};
+    gp.M = M; gp.n_poses = f->n_poses;
+    gp.B = f->d_B0; gp.rowsB = 3 * n0; gp.nzB = f->nz; gp.partB = f->d_partB;
+    gp.D = f->d_D1; gp.rowsD = 2 * f->l_newms.n_obs * (n1 > 0); gp.nzD = f->nz; gp.partD = f->d_partD;
+    gp.off = l0.d_off; gp.inlier = f->d_inl0; gp.n_tracks_msckf = n0; gp.Jout = f->d_J0;
+    gp.blocks = f->d_blocks;
+    gp.T = f->d_Tg; gp.ld = f->gcols_pad; gp.rows_pad = f->grows_pad; gp.cols_pad = f->gcols_pad;
+    launch_gram(f->stream, gp);
+    tallchol(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, f->d_flags, f->d_err, 1e-14);
+    transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
+  } else {
+    CK(cudaMemsetAsync(f->d_Tg, 0, gbytes, f->stream));
+    CK(cudaMemsetAsync(f->d_Rg, 0, sizeof(double) * (size_t)f->gcols_pad * f->gcols_pad, f->stream));
+  }
+  if (ns > 0) {
+    CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * f->F, cudaMemcpyHostToDevice, f->stream));
+    SlamParams sp{};
+    sp.xv = f->d_xw; sp.M = M; sp.N = f->N; sp.n_poses = f->n_poses; sp.P = f->d_Pw;
+    sp.off = f->l_slam.d_off; sp.obs = f->l_slam.d_obs; sp.anchor = f->d_anchor; sp.chi2 = f->d_slam_chi2;
+    sp.n_tracks = ns; sp.var_img = f->cfg.sigma_img * f->cfg.sigma_img;
+    sp.cols = f->d_scols; sp.vals = f->d_svals; sp.res = f->d_sres; sp.gamma = f->d_sgamma; sp.inlier = f->d_sinl;
+    launch_slam_rows(f->stream, sp);
+  }
+  return XB_OK;
+}
+
+static UpdateDims update_dims(const xb_filter* f, int nslam) {
+  UpdateDims d;
+  d.M = f->M; d.F = f->F; d.N = f->N;
+  d.ms = 6 * f->M;
+  d.nslam = nslam;
+  d.m = d.ms + 2 * nslam;
+  d.m_pad = pad32(d.m);
+  d.n_pad = pad32(f->N);
+  d.ld = d.m_pad;
+  return d;
+}
+
+static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total) {
+  const int N = f->N;
+  tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 32, m_pad, f->d_flags, f->d_err, 0.0);
+  launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_xw, corr_total, f->d_delta);
+  if (cov_update) {
+    const double* W = f->d_T + (size_t)m_pad * m_pad;
+    if (f->cfg.downdate_precision == 1) downdate_tc(f->stream, f->d_Pw, N, W, m_pad, m_pad, f->d_tcws);
+    else downdate_f64(f->stream, f->d_Pw, N, W, m_pad, m_pad);
+  }
+  return XB_OK;
+}
+
+extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
+  if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  if (!f->constructed_any) return XB_OK;  // h.size() == 0 (updater.cpp:106)
+  const UpdateDims d = update_dims(f, f->last_nslam);
+  const size_t tb = sizeof(double) * (size_t)(d.m_pad + d.n_pad + 32) * d.m_pad;
+  CK(cudaMemsetAsync(f->d_T, 0, tb, f->stream));
+  const double* zg = f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad;
+  launch_build_pht(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_T);
+  launch_build_s(f->stream, d, f->d_Rg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, f->d_corr,
+                 f->cfg.sigma_img * f->cfg.sigma_img, f->d_T);
+  return apply_from_tall(f, d.m_pad, d.n_pad, cov_update, f->d_corr);
+}
+
+extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const double* res, const double* r_diag, int m,
+                                       double* correction_total, int cov_update) {
+  if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  const int N = f->N;
+  if (m <= 0) return XB_OK;
+  const int m_pad = pad32(m), n_pad = pad32(N);
+  if ((size_t)(m_pad + n_pad + 32) * m_pad > f->T_doubles || (size_t)m * N + 2 * (size_t)m > f->Hdense_doubles)
+    return fail(XB_E_CAPACITY, "dense update has too many rows (max N after QR compression)");
+  double* dH = f->d_Hdense;
+  double* dres = dH + (size_t)m * N;
+  double* drd = dres + m;
+  CK(cudaMemcpyAsync(dH, H, sizeof(double) * (size_t)m * N, cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(dres, res, sizeof(double) * m, cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(drd, r_diag, sizeof(double) * m, cudaMemcpyHostToDevice, f->stream));
+  if (correction_total) CK(cudaMemcpyAsync(f->d_corr, correction_total, sizeof(double) * N, cudaMemcpyHostToDevice, f->stream));
+  else CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * N, f->stream));
+  CK(cudaMemsetAsync(f->d_T, 0, sizeof(double) * (size_t)(m_pad + n_pad + 32) * m_pad, f->stream));
+  launch_dense_prepare(f->stream, m, m_pad, N, n_pad, f->d_Pw, dH, dres, drd, f->d_corr, f->d_T);
+  int rc = apply_from_tall(f, m_pad, n_pad, cov_update, f->d_corr);
+  if (rc) return rc;
+  if (correction_total) CK(cudaMemcpyAsync(correction_total, f->d_corr, sizeof(double) * N, cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return XB_OK;
+}
+
+// Updater::applyCI (updater.cpp:144-161): K = P_j H^T S^-1; delta = K r; P = (I - K H) P_j; symmetrise; correct.
+extern "C" int xb_updater_apply_ci(xb_filter* f, const double* H, const double* res, const double* S, int m,
+                                   const int* scaled_block_cols, int n_blocks, double w_result) {
+  if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  const int N = f->N;
+  if (m <= 0 || m > 96) return fail(XB_E_INVALID, "applyCI: 0 < rows <= 96");
+  const int m_pad = pad32(m), n_pad = pad32(N);
+  double* dH = f->d_Hdense;
+  double* dres = dH + (size_t)m * N;
+  int* dcols = (int*)(dres + m + 2);
+  CK(cudaMemcpyAsync(dH, H, sizeof(double) * (size_t)m * N, cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(dres, res, sizeof(double) * m, cudaMemcpyHostToDevice, f->stream));
+  if (n_blocks > 0) {
+    if (n_blocks > 256) return fail(XB_E_INVALID, "too many scaled blocks");
+    CK(cudaMemcpyAsync(dcols, scaled_block_cols, sizeof(int) * n_blocks, cudaMemcpyHostToDevice, f->stream));
+    launch_scale_blocks(f->stream, f->d_Pw, N, dcols, n_blocks, w_result);  // P_j (only diagonal 3x3 blocks)
+  }
+  CK(cudaMemsetAsync(f->d_T, 0, sizeof(double) * (size_t)(m_pad + n_pad + 32) * m_pad, f->stream));
+  // rows [0,m): S given by the caller; rows m_pad..: P_j H^T ; last: res
+  std::vector<double> Sp((size_t)m_pad * m_pad, 0.0);
+  for (int r = 0; r < m_pad; ++r)
+    for (int c = 0; c < m_pad; ++c)
+      Sp[(size_t)r * m_pad + c] = (r < m && c < m) ? 0.5 * (S[(size_t)r * m + c] + S[(size_t)c * m + r]) : (r == c ? 1.0 : 0.0);
+  CK(cudaMemcpyAsync(f->d_T, Sp.data(), sizeof(double) * Sp.size(), cudaMemcpyHostToDevice, f->stream));
+  gemm_nt(f->stream, N, m, N, 1.0, f->d_Pw, N, dH, N, 0.0, f->d_T + (size_t)m_pad * m_pad, m_pad);
+  CK(cudaMemcpyAsync(f->d_T + (size_t)(m_pad + n_pad) * m_pad, dres, sizeof(double) * m, cudaMemcpyDeviceToDevice, f->stream));
+  CK(cudaStreamSynchronize(f->stream));  // Sp lifetime
+  // NOTE: with P_j != P the reference's (I-KH)P_j is not symmetric before 0.5(P+P^T); P_j differs from a
+  // symmetric matrix only by a symmetric scaling of diagonal blocks, so P_j stays symmetric and the
+  // Cholesky form applies unchanged.
+  return apply_from_tall(f, m_pad, n_pad, 1, nullptr);
+}
+
+// ---- VioUpdater::postUpdate (vio_updater.cpp:425-449) -----------------------------------------------------------------
+extern "C" int xb_vio_post_update(xb_filter* f) {
+  const int M = f->M, F = f->F, N = f->N;
+  const double var = f->cfg.sigma_img * f->cfg.sigma_img;
+  if (f->l_newms.n > 0) {
+    const int n_new = f->l_newms.n;
+    if (f->n_features + n_new > F) return fail(XB_E_CAPACITY, "no free SLAM feature slot (state_manager.cpp:208)");
+    FeatInitParams fp{};
+    fp.M = M; fp.F = F; fp.N = N; fp.n_poses = f->n_poses; fp.n_features = f->n_features; fp.n_new = n_new;
+    fp.H1 = f->d_H1; fp.H2 = f->d_H2; fp.ivd = f->d_ivd1; fp.corr = f->d_corr; fp.var_img = var;
+    launch_init_msckf_slam(f->stream, fp, f->d_xw, f->d_Pw, f->d_fscratch);
+    for (int i = 0; i < n_new; ++i) f->anchor[f->n_features + i] = f->n_poses - 1;
+    f->n_features += n_new;
+  }
+  if (f->l_newstd.n > 0) {
+    const int n_new = f->l_newstd.n;
+    if (f->n_features + n_new > F) return fail(XB_E_CAPACITY, "no free SLAM feature slot (state_manager.cpp:208)");
+    launch_init_std_slam(f->stream, M, F, N, f->n_features, n_new, f->l_newstd.d_off, f->l_newstd.d_obs, f->cfg.rho_0, var,
+                         f->cfg.sigma_rho_0 * f->cfg.sigma_rho_0, f->d_xw, f->d_Pw);
+    for (int i = 0; i < n_new; ++i) f->anchor[f->n_features + i] = f->n_poses - 1;
+    f->n_features += n_new;
+  }
+  return XB_OK;
+}
+
+// ---- Updater::update (updater.cpp:39-115, single-UAV build) -------------------------------------------------------------
+extern "C" int xb_updater_update(xb_filter* f) {
+  int rc;
+  CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * f->N, f->stream));
+  if (f->l_short.n > 0) {  // preUpdateShortMsckf (vio_updater.cpp:209-215)
+    if ((rc = xb_vio_construct_update(f, 1)) < 0) return rc;
+    if ((rc = xb_updater_apply_constructed(f, 1)) < 0) return rc;
+  }
+  if ((rc = xb_sm_manage(f, f->lost.data(), (int)f->lost.size())) < 0) return rc;  // preUpdate (vio_updater.cpp:200-207)
+  const bool requested = f->l_msckf.n || f->l_slam.n || f->l_newstd.n || f->l_newms.n;
+  if (requested) {
+    CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * f->N, f->stream));
+    const int iters = std::max(1, f->cfg.iekf_iter);
+    for (int i = 0; i < iters; ++i) {
+      if ((rc = xb_vio_construct_update(f, 0)) < 0) return rc;
+      if ((rc = xb_updater_apply_constructed(f, i == iters - 1)) < 0) return rc;
+    }
+    if ((rc = xb_vio_post_update(f)) < 0) return rc;
+  }
+  return XB_OK;
+}
+
+extern "C" int xb_propagate(xb_filter* f, int slot_from, int slot_to) {
+  if (slot_to != (slot_from + 1) % f->NS) return fail(XB_E_INVALID, "slot_to must follow slot_from in the ring");
+  ImuSample none{};
+  propagate_chain(f, slot_from, 1, none);
+  f->slot_gen[slot_to] = f->slot_gen[slot_from];
+  return XB_OK;
+}
+
+static int repropagate_from(xb_filter* f, int idx) {  // ekf.cpp:227-255
+  int n = 0;
+  for (int c = idx; c != f->tail; c = next_idx(f, c)) ++n;
+  ImuSample none{};
+  propagate_chain(f, idx, n, none);
+  for (int c = idx, k = 0; k < n; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; }
+  return n;
+}
+
+// ---- Ekf::processUpdateMeasurement (ekf.cpp:179-213) ---------------------------------------------------------------------
+extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
+  if (!f) return fail(XB_E_INVALID, "null filter");
+  if (f->status == 0) return 0;
+  const int idx = closest_idx(f, f->meas_time);
+  if (idx < 0 || f->slot_gen[idx] < 0) return 0;
+  int rc;
+  if ((rc = xb_work_load(f, idx)) < 0) return rc;
+  if ((rc = xb_updater_update(f)) < 0) return rc;
+  if ((rc = xb_work_store(f, idx)) < 0) return rc;
+  repropagate_from(f, idx);
+  if (xvec_out) {
+    CK(cudaMemcpyAsync(xvec_out, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToHost, f->stream));
+    if ((rc = xb_synchronize(f)) < 0) return rc;
+  }
+  return 1;
+}
+
+// ---- introspection ----------------------------------------------------------------------------------------------------------
+extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles) {
+  const std::string n(name);
+  const double* src = nullptr;
+  size_t cnt = 0;
+  const int W = 6 * f->M + 1;
+  if (n == "gamma0") { src = f->d_gamma0; cnt = f->last_which ? f->l_short.n : f->l_msckf.n; }
+  else if (n == "ivd0") { src = f->d_ivd0; cnt = 3 * (size_t)(f->last_which ? f->l_short.n : f->l_msckf.n); }
+  else if (n == "gamma1") { src = f->d_gamma1; cnt = f->l_newms.n; }
+  else if (n == "ivd1") { src = f->d_ivd1; cnt = 3 * (size_t)f->l_newms.n; }
+  else if (n == "H1") { src = f->d_H1; cnt = (size_t)f->l_newms.n * 3 * W; }
+  else if (n == "H2") { src = f->d_H2; cnt = 9 * (size_t)f->l_newms.n; }
+  else if (n == "B0") { src = f->d_B0; cnt = (size_t)(f->last_which ? f->l_short.n : f->l_msckf.n) * 3 * W; }
+  else if (n == "slam_gamma") { src = f->d_sgamma; cnt = f->l_slam.n; }
+  else if (n == "slam_vals") { src = f->d_svals; cnt = 30 * (size_t)f->l_slam.n; }
+  else if (n == "slam_res") { src = f->d_sres; cnt = 2 * (size_t)f->l_slam.n; }
+  else if (n == "Tg") { src = f->d_Tg; cnt = (size_t)f->grows_pad * f->gcols_pad; }
+  else if (n == "Rg") { src = f->d_Rg; cnt = (size_t)f->gcols_pad * f->gcols_pad; }
+  else if (n == "corr") { src = f->d_corr; cnt = f->N; }
+  else if (n == "delta") { src = f->d_delta; cnt = f->N; }
+  else if (n == "T") { src = f->d_T; cnt = f->T_doubles; }
+  else return fail(XB_E_INVALID, "unknown debug buffer " + n);
+  if ((size_t)max_doubles < cnt) cnt = max_doubles;
+  CK(cudaStreamSynchronize(f->stream));
+  CK(cudaMemcpy(out, src, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+  return (int)cnt;
+}
+extern "C" int xb_debug_read_int(xb_filter* f, const char* name, int* out, int max_ints) {
+  const std::string n(name);
+  const int* src = nullptr;
+  size_t cnt = 0;
+  if (n == "inlier0") { src = f->d_inl0; cnt = f->last_which ? f->l_short.n : f->l_msckf.n; }
+  else if (n == "inlier1") { src = f->d_inl1; cnt = f->l_newms.n; }
+  else if (n == "slam_inlier") { src = f->d_sinl; cnt = f->l_slam.n; }
+  else if (n == "slam_cols") { src = f->d_scols; cnt = 15 * (size_t)f->l_slam.n; }
+  else if (n == "slot_gen") {
+    cnt = std::min((size_t)max_ints, (size_t)f->NS);
+    for (size_t i = 0; i < cnt; ++i) out[i] = f->slot_gen[i];
+    return (int)cnt;
+  } else return fail(XB_E_INVALID, "unknown debug buffer " + n);
+  if ((size_t)max_ints < cnt) cnt = max_ints;
+  CK(cudaStreamSynchronize(f->stream));
+  CK(cudaMemcpy(out, src, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+  return (int)cnt;
+}

@@ -1,0 +1,132 @@
+// Internal interface between the host orchestration (xb_api.cu) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "xb_common.cuh"
+
+namespace xb {
+
+void count_launch();  // bumps the per-thread kernel-launch counter (xb_kernel_launches)
+
+// ---- propagation --------------------------------------------------------------------------------
+struct ImuSample { int valid; double t, seq, w[3], a[3]; };
+struct PropParams { double g[3]; double n_w, n_bw, n_a, n_ba; };
+void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,
+                      const ImuSample& in, const PropParams& pp, double* FQ);
+
+// ---- dense linear algebra -----------------------------------------------------------------------
+void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+             double beta, double* C, int ldc);
+void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+             double beta, double* C, int ldc);
+void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol);
+void downdate_f64(cudaStream_t s, double* P, int n, const double* W, int ldw, int kdim);
+void symmetrise(cudaStream_t s, double* P, int n);
+void gemv(cudaStream_t s, int rows, int cols, const double* A, int lda, const double* x, double* y);
+void transpose(cudaStream_t s, const double* in, double* out, int rows, int cols);
+
+// ---- per-track measurement construction ---------------------------------------------------------
+struct TrackParams {
+  const double* xv;   // work estimates (poses are read from p_array / q_array)
+  int M, n_poses;
+  const double* P;    // work covariance, N x N
+  int ldp;
+  const int* off;     // CSR offsets (device)
+  const double* obs;  // 2 doubles per observation
+  int n_tracks;
+  int mode;           // 0 = MSCKF, 1 = MSCKF-SLAM
+  int Lmax;           // longest track of the launch
+  double var_img;
+  const double* chi2_95;  // table: index = dof
+  double gn_term;
+  int gn_max_iter;
+  // outputs
+  double* ivd;     // [K][3]
+  double* gamma;   // [K]
+  int* inlier;     // [K]
+  double* B;       // [K][3][6M+1]   U^T [J | r], zeroed for outliers
+  double* Jout;    // [obs][14]      Jp(2x3) Ja(2x3) r(2)
+  double* H1;      // [K][3][6M+1]   mode 1: unmasked U^T [h | r]  (H1 and r1 of Li 2012)
+  double* H2;      // [K][9]         mode 1: U^T Hf
+  double* D;       // [2*obs][6M+1]  mode 1: Pi [h | r]
+};
+int launch_tracks(cudaStream_t s, const TrackParams& tp);
+
+struct SlamParams {
+  const double* xv;
+  int M, N, n_poses;
+  const double* P;
+  const int* off;
+  const double* obs;
+  const int* anchor;
+  const double* chi2;  // per track: quantile(0.9, 2*track_size)
+  int n_tracks;
+  double var_img;
+  int* cols;      // [F][15]
+  double* vals;   // [F][2][15]
+  double* res;    // [F][2]
+  double* gamma;  // [F]
+  int* inlier;    // [F]
+};
+void launch_slam_rows(cudaStream_t s, const SlamParams& sp);
+
+struct GramParams {
+  int M, n_poses;
+  const double* B; int rowsB; int nzB; double* partB;
+  const double* D; int rowsD; int nzD; double* partD;
+  const int* off; const int* inlier; int n_tracks_msckf; const double* Jout;
+  double* blocks;  // [M][28]
+  double* T; int ld, rows_pad, cols_pad;
+};
+void launch_gram(cudaStream_t s, const GramParams& gp);
+
+// ---- update assembly / state correction / state management (k_update.cu, k_manage.cu) -----------
+struct UpdateDims {
+  int M, F, N;
+  int ms;       // slab rows = 6M
+  int nslam;    // SLAM tracks (2 rows each)
+  int m;        // ms + 2*nslam
+  int m_pad;    // m rounded up to 32
+  int n_pad;    // N rounded up to 32
+  int ld;       // leading dimension of the tall buffer (= m_pad)
+};
+// PHt[:, 0:6M] = P[:, pose] * Rg^T ; PHt[:, 6M+2j+r] = sum_e P[:, col_e] * val ; written into the tall buffer rows m_pad..
+void launch_build_pht(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
+                      const double* svals, double* T);
+// S = Hc * PHt + var I (rows 0..m-1 of the tall buffer), identity padding and the r_eff row.
+void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, int ldr, const double* zg, const int* scols,
+                    const double* svals, const double* sres, const double* corr_total, double var, double* T);
+// dense-H variant (Updater::applyUpdate with a caller-supplied H)
+void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, const double* P, const double* H,
+                          const double* res, const double* rdiag, const double* corr_total, double* T);
+// delta = W z - corr_total ; State::correct ; corr_total += delta
+void launch_correct(cudaStream_t s, int M, int F, int N, const double* T, int m_pad, int n_pad, double* xv,
+                    double* corr_total, double* delta_out);
+void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta, double* xv, double* corr_total);
+// 3xTF32 tcgen05 tensor-core covariance downdate (k_downdate_tc.cu)
+void downdate_tc(cudaStream_t s, double* P, int n, const double* W, int ldw, int kdim, void* ws);
+
+// StateManager::manage arithmetic: P' = A P A^T as one gather pass + thin products (k_manage.cu)
+void launch_manage_dev(cudaStream_t s, int M, int F, int N, int n_poses, int n_features, int slide, int n_reanch,
+                       const int* d_feat_src, const int* d_reanch, const int* d_rowmap, const int* d_ccols,
+                       double* d_cvals, double* d_scratch, double* xv, const double* Pold, double* Pnew, double* Tm,
+                       double* T2);
+// P(full) <- strip rows/cols + P_vv of a generation buffer
+void launch_assemble(cudaStream_t s, int N, const double* strip, const double* Pgen, double* Pwork);
+void launch_extract_strip(cudaStream_t s, int N, const double* Pwork, double* strip);
+// MSCKF-SLAM / standard SLAM feature initialisation (state_manager.cpp:151-227)
+struct FeatInitParams {
+  int M, F, N, n_poses, n_features, n_new;
+  const double* H1;   // [n_new][3][6M+1]
+  const double* H2;   // [n_new][9]
+  const double* ivd;  // [n_new][3]
+  const double* corr; // [N]
+  double var_img;
+};
+void launch_init_msckf_slam(cudaStream_t s, const FeatInitParams& fp, double* xv, double* P, double* scratch);
+void launch_init_std_slam(cudaStream_t s, int M, int F, int N, int n_features, int n_new, const int* off,
+                          const double* obs, double rho0, double var_img, double var_rho0, double* xv, double* P);
+void launch_scale_blocks(cudaStream_t s, double* P, int N, const int* cols, int n_blocks, double w);
+void launch_add_diag(cudaStream_t s, double* A, int ld, int n, double v);
+
+}  // namespace xb

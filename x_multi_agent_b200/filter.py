@@ -1,0 +1,270 @@
+"""Host-side Python mirror of the reference's operator API for the hot path, on top of the C ABI.
+
+Names follow the reference: x::Ekf (include/x/ekf/ekf.h:53-195), x::VioUpdater
+(include/x/vio/vio_updater.h:35-335), x::State (include/x/ekf/state.h:36-337), x::StateManager.
+All arithmetic runs in libxb200.so on the GPU; this module only marshals buffers.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lib as L
+
+K_CORE = 15
+
+
+def xvec_len(M, F):
+    return 32 + 7 * M + 3 * F
+
+
+class State:
+    """Estimates of one x::State as views into a flat xvec (layout: include/xb200.h)."""
+
+    def __init__(self, M, F, xvec=None):
+        self.M, self.F = M, F
+        self.x = np.zeros(xvec_len(M, F)) if xvec is None else np.array(xvec, dtype=np.float64)
+        if xvec is None:
+            self.x[9] = 1.0   # q = identity (x,y,z,w)
+            self.x[19] = 1.0  # q_ic
+            self.x[29] = -1.0  # kInvalid time (common/types.h:90)
+        self.cov = None
+
+    p = property(lambda s: s.x[0:3])
+    v = property(lambda s: s.x[3:6])
+    q = property(lambda s: s.x[6:10])
+    b_w = property(lambda s: s.x[10:13])
+    b_a = property(lambda s: s.x[13:16])
+    q_ic = property(lambda s: s.x[16:20])
+    p_ic = property(lambda s: s.x[20:23])
+    w_m = property(lambda s: s.x[23:26])
+    a_m = property(lambda s: s.x[26:29])
+    p_array = property(lambda s: s.x[32:32 + 3 * s.M])
+    q_array = property(lambda s: s.x[32 + 3 * s.M:32 + 7 * s.M])
+    f_array = property(lambda s: s.x[32 + 7 * s.M:32 + 7 * s.M + 3 * s.F])
+
+    @property
+    def time(self):
+        return float(self.x[29])
+
+    @time.setter
+    def time(self, t):
+        self.x[29] = t
+
+    def n_error_states(self):
+        return K_CORE + 6 * self.M + 3 * self.F
+
+    @classmethod
+    def from_oracle(cls, s):
+        """Build from an oracle.State (tests only)."""
+        M, F = s.n_poses_max(), s.n_features_max()
+        o = cls(M, F)
+        o.x[0:3], o.x[3:6], o.x[6:10], o.x[10:13], o.x[13:16] = s.p, s.v, s.q, s.b_w, s.b_a
+        o.x[16:20], o.x[20:23], o.x[23:26], o.x[26:29] = s.q_ic, s.p_ic, s.w_m, s.a_m
+        o.x[29], o.x[30] = s.time, s.seq
+        o.p_array[:], o.q_array[:], o.f_array[:] = s.p_array, s.q_array, s.f_array
+        o.cov = np.array(s.cov, dtype=np.float64)
+        return o
+
+
+@dataclass
+class Measurement:
+    """Output of VioUpdater::preProcess (vio_updater.cpp:172-179); tracks are (L,2) arrays, oldest first."""
+    timestamp: float = 0.0
+    slam_trks: list = field(default_factory=list)
+    msckf_trks: list = field(default_factory=list)
+    msckf_short_trks: list = field(default_factory=list)
+    new_slam_std_trks: list = field(default_factory=list)
+    new_msckf_slam_trks: list = field(default_factory=list)
+    lost_slam_trk_idxs: list = field(default_factory=list)
+
+
+def _csr(tracks):
+    off = np.zeros(len(tracks) + 1, dtype=np.int32)
+    if tracks:
+        off[1:] = np.cumsum([np.asarray(t).shape[0] for t in tracks])
+        obs = np.ascontiguousarray(np.vstack([np.asarray(t, dtype=np.float64).reshape(-1, 2) for t in tracks]))
+    else:
+        obs = np.zeros((0, 2))
+    return off, obs
+
+
+class PackedMeasurement:
+    """A Measurement marshalled once into the CSR buffers the C ABI takes (keeps them alive)."""
+
+    def __init__(self, m: Measurement):
+        self.keep = []
+        self.c = L.XbMeasurement()
+        self.c.timestamp = m.timestamp
+        self.h2d_bytes = 0
+        for name, trks in (("slam", m.slam_trks), ("msckf", m.msckf_trks), ("msckf_short", m.msckf_short_trks),
+                           ("new_slam_std", m.new_slam_std_trks), ("new_msckf_slam", m.new_msckf_slam_trks)):
+            off, obs = _csr(trks)
+            self.keep += [off, obs]
+            tl = L.XbTrackList(len(trks), L.iptr(off), L.dptr(obs))
+            setattr(self.c, name, tl)
+            if trks:
+                self.h2d_bytes += off.nbytes + obs.nbytes
+        lost = np.asarray(m.lost_slam_trk_idxs, dtype=np.int32)
+        self.keep.append(lost)
+        self.c.n_lost = len(lost)
+        self.c.lost_slam_idxs = L.iptr(lost)
+
+
+class Filter:
+    """One agent's filter on one GPU: x::Ekf + x::VioUpdater + x::StateManager behind the C ABI."""
+
+    def __init__(self, n_poses_max, n_features_max, **kw):
+        lib = L.load()
+        self.lib = lib
+        cfg = L.XbConfig()
+        lib.xb_default_config(C.byref(cfg))
+        cfg.n_poses_max, cfg.n_features_max = n_poses_max, n_features_max
+        for k, v in kw.items():
+            if k == "g":
+                for i in range(3):
+                    cfg.g[i] = v[i]
+            elif not hasattr(cfg, k):
+                raise TypeError(f"unknown config field {k}")
+            else:
+                setattr(cfg, k, v)
+        self.cfg = cfg
+        self.M, self.F = n_poses_max, n_features_max
+        self.N = K_CORE + 6 * self.M + 3 * self.F
+        self.LX = xvec_len(self.M, self.F)
+        h = C.c_void_p()
+        L.check(lib.xb_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.xb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- x::Ekf ----------------------------------------------------------------------------
+    def initialize_from_state(self, state: State):
+        x = L.f64(state.x)
+        cov = L.f64(state.cov)
+        if x.size != self.LX or cov.shape != (self.N, self.N):
+            raise ValueError("init_bfr_mismatch")  # ekf.cpp:50-59
+        L.check(self.lib.xb_ekf_initialize_from_state(self.h, L.dptr(x), L.dptr(cov), 0))
+
+    def process_imu(self, t, seq, w_m, a_m, want_state=True):
+        out = np.empty(self.LX) if want_state else None
+        w, a = L.f64(w_m), L.f64(a_m)
+        rc = L.check(self.lib.xb_ekf_process_imu(self.h, float(t), int(seq), L.dptr(w), L.dptr(a), L.dptr(out)))
+        if rc == 0:
+            return None
+        return State(self.M, self.F, out) if want_state else True
+
+    def set_measurement(self, m):
+        pm = m if isinstance(m, PackedMeasurement) else PackedMeasurement(m)
+        self._pm = pm
+        L.check(self.lib.xb_vio_set_measurement(self.h, C.byref(pm.c)))
+        return pm
+
+    def process_update_measurement(self, want_state=True):
+        out = np.empty(self.LX) if want_state else None
+        rc = L.check(self.lib.xb_ekf_process_update(self.h, L.dptr(out)))
+        if rc == 0:
+            return None
+        return State(self.M, self.F, out) if want_state else True
+
+    def get_state(self, slot=-1):
+        out = np.empty(self.LX)
+        L.check(self.lib.xb_ekf_get_state(self.h, slot, L.dptr(out)))
+        return State(self.M, self.F, out)
+
+    def get_covariance(self, slot=-1):
+        out = np.empty((self.N, self.N))
+        L.check(self.lib.xb_ekf_get_covariance(self.h, slot, L.dptr(out), 0))
+        return out
+
+    def newest_slot(self):
+        return self.lib.xb_ekf_newest_slot(self.h)
+
+    def synchronize(self):
+        L.check(self.lib.xb_synchronize(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        L.check(self.lib.xb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- x::StateManager bookkeeping --------------------------------------------------------
+    @property
+    def n_poses(self):
+        return self.lib.xb_sm_n_poses(self.h)
+
+    @property
+    def n_features(self):
+        return self.lib.xb_sm_n_features(self.h)
+
+    @property
+    def anchor_idxs(self):
+        out = np.zeros(max(self.F, 1), dtype=np.int32)
+        self.lib.xb_sm_anchor_idxs(self.h, L.iptr(out))
+        return out[:self.F].tolist()
+
+    def sm_set(self, n_poses, n_features, anchor_idxs, filled_before):
+        a = np.full(max(self.F, 1), -1, dtype=np.int32)
+        a[:len(anchor_idxs)] = anchor_idxs
+        L.check(self.lib.xb_sm_set(self.h, n_poses, n_features, L.iptr(a), int(filled_before)))
+
+    # ---- stage-level (Updater / VioUpdater / StateManager methods on the work state) -----------
+    def work_set(self, state: State):
+        x, cov = L.f64(state.x), L.f64(state.cov)
+        L.check(self.lib.xb_work_set(self.h, L.dptr(x), L.dptr(cov), 0))
+
+    def work_get(self, with_cov=True):
+        x = np.empty(self.LX)
+        cov = np.empty((self.N, self.N)) if with_cov else None
+        L.check(self.lib.xb_work_get(self.h, L.dptr(x), L.dptr(cov), 0))
+        s = State(self.M, self.F, x)
+        s.cov = cov
+        return s
+
+    def manage(self, lost=()):
+        a = np.asarray(list(lost), dtype=np.int32)
+        L.check(self.lib.xb_sm_manage(self.h, L.iptr(a), len(a)))
+
+    def construct_update(self, which=0):
+        L.check(self.lib.xb_vio_construct_update(self.h, which))
+
+    def apply_constructed(self, cov_update=True):
+        L.check(self.lib.xb_updater_apply_constructed(self.h, int(cov_update)))
+
+    def apply_update(self, H, res, r_diag, correction_total=None, cov_update=True):
+        H, res, r_diag = L.f64(H), L.f64(res), L.f64(r_diag)
+        ct = None if correction_total is None else correction_total
+        L.check(self.lib.xb_updater_apply_update(self.h, L.dptr(H), L.dptr(res), L.dptr(r_diag), H.shape[0],
+                                                 L.dptr(ct), int(cov_update)))
+
+    def apply_ci(self, H, res, S, scaled_block_cols=(), w_result=1.0):
+        H, res, S = L.f64(H), L.f64(res), L.f64(S)
+        cols = np.asarray(list(scaled_block_cols), dtype=np.int32)
+        L.check(self.lib.xb_updater_apply_ci(self.h, L.dptr(H), L.dptr(res), L.dptr(S), H.shape[0], L.iptr(cols),
+                                             len(cols), float(w_result)))
+
+    def post_update(self):
+        L.check(self.lib.xb_vio_post_update(self.h))
+
+    def updater_update(self):
+        L.check(self.lib.xb_updater_update(self.h))
+
+    def debug(self, name, count):
+        out = np.zeros(int(count))
+        n = L.check(self.lib.xb_debug_read(self.h, name.encode(), L.dptr(out), int(count)))
+        return out[:n]
+
+    def debug_int(self, name, count):
+        out = np.zeros(int(count), dtype=np.int32)
+        n = L.check(self.lib.xb_debug_read_int(self.h, name.encode(), L.iptr(out), int(count)))
+        return out[:n]
+
+    def kernel_launches(self):
+        return int(self.lib.xb_kernel_launches(self.h))
