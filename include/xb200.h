@@ -179,6 +179,8 @@ XB_API int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost);
 /* VioUpdater::constructUpdate (vio_updater.cpp:266-423) / constructShortMsckfUpdate (:217-264):
  * builds the compressed (H, r) on the device. which: 0 = main update, 1 = short-MSCKF. */
 XB_API int xb_vio_construct_update(xb_filter* f, int which);
+/* `Matrix correction = Matrix::Zero(...)` (updater.cpp:43,86): clears the device-resident correction_total. */
+XB_API int xb_updater_reset_correction(xb_filter* f);
 /* Updater::applyUpdate (updater.cpp:117-141) on the device-resident compressed (H, r). */
 XB_API int xb_updater_apply_constructed(xb_filter* f, int cov_update);
 /* Updater::applyUpdate with caller-supplied dense H (m x N row-major), res (m), R diagonal (m). */

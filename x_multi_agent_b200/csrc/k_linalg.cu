@@ -248,46 +248,91 @@ void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Covariance downdate  P <- (P + P^T)/2 - W W^T   (fp64 CUDA-core variant)
-//   reference: updater.cpp:131-136 ( (I-KH)P then symmetrise ).  W is [n x kdim] with leading dim ldw.
-//   One CTA per 32x32 tile pair (I <= J); it owns both P(I,J) and P(J,I), so the update is in place.
+// Covariance downdate (fp64 CUDA-core variant), reference: updater.cpp:131-136 ((I-KH)P, then symmetrise):
+//   P_ij <- (P_ij + P_ji)/2 - (W1_i.W2_j + W2_i.W1_j)/2 + (Z_i.Y_j + Y_i.Z_j)/2
+// W1 = rows m_pad.. of the tall buffer; W2 = W1 except on the Omega rows (core + newest clone), which come
+// from the Omega tile; Z/Y are the 32-wide rank-21 Woodbury factors (k_update.cu).  One CTA per 32x32
+// tile pair (I <= J): it owns both P(I,J) and P(J,I), so the update is in place.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_downdate(double* __restrict__ P, int n, const double* __restrict__ W, int ldw,
-                                                 int kdim) {
-  // linear block -> (I, J), I <= J
+__global__ void __launch_bounds__(64) k_downdate(double* __restrict__ P, int n, const double* __restrict__ T, int m_pad,
+                                                 int n_pad, const int* __restrict__ omega_inv,
+                                                 const int* __restrict__ tileflag, const double* __restrict__ Zb,
+                                                 const double* __restrict__ Yb) {
   const int nt = (n + TC - 1) / TC;
   int b = blockIdx.x, I = 0;
   while (b >= nt - I) { b -= nt - I; ++I; }
   const int J = I + b;
   const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
-  __shared__ double As[TC][TC + 1];
-  __shared__ double Bs[TC][TC + 1];
-  double acc[4][4];
+  __shared__ double As[TC][TC + 1], Bs[TC][TC + 1], As2[TC][TC + 1], Bs2[TC][TC + 1];
+  const double* W1 = T + (size_t)m_pad * m_pad;
+  const double* W2o = T + (size_t)(m_pad + n_pad + 32) * m_pad;
+  const bool two = tileflag[I] | tileflag[J];
+  double acc[4][4], acc2[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-  for (int k0 = 0; k0 < kdim; k0 += TC) {
+    for (int c = 0; c < 4; ++c) { acc[a][c] = 0.0; acc2[a][c] = 0.0; }
+  // K loop over the m_pad columns of W, plus one final 32-wide block holding the Woodbury factors
+  for (int k0 = 0; k0 <= m_pad; k0 += TC) {
+    const bool last = k0 == m_pad;
     for (int e = t; e < TC * TC; e += 64) {
       const int r = e >> 5, c = e & 31;
-      const int gi = I * TC + r, gj = J * TC + r, gk = k0 + c;
-      As[c][r] = (gi < n && gk < kdim) ? W[(size_t)gi * ldw + gk] : 0.0;
-      Bs[c][r] = (gj < n && gk < kdim) ? W[(size_t)gj * ldw + gk] : 0.0;
+      const int gi = I * TC + r, gj = J * TC + r;
+      if (!last) {
+        const double a1 = gi < n ? W1[(size_t)gi * m_pad + k0 + c] : 0.0;
+        const double b1 = gj < n ? W1[(size_t)gj * m_pad + k0 + c] : 0.0;
+        As[c][r] = a1;
+        Bs[c][r] = b1;
+        if (two) {
+          const int oi = gi < n ? omega_inv[gi] : -1, oj = gj < n ? omega_inv[gj] : -1;
+          As2[c][r] = oi >= 0 ? W2o[(size_t)oi * m_pad + k0 + c] : a1;
+          Bs2[c][r] = oj >= 0 ? W2o[(size_t)oj * m_pad + k0 + c] : b1;
+        }
+      } else {  // acc -= Z_i.Y_j , acc2 -= Y_i.Z_j
+        As[c][r] = gi < n ? -Zb[(size_t)gi * 32 + c] : 0.0;
+        Bs2[c][r] = gj < n ? Yb[(size_t)gj * 32 + c] : 0.0;
+        As2[c][r] = gi < n ? Yb[(size_t)gi * 32 + c] : 0.0;
+        Bs[c][r] = gj < n ? -Zb[(size_t)gj * 32 + c] : 0.0;
+      }
     }
     __syncthreads();
+    if (two || last) {
+#pragma unroll 4
+      for (int kk = 0; kk < TC; ++kk) {
+        double a[4], bb[4], a2[4], b2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; a2[u] = As2[kk][ty * 4 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { bb[u] = Bs[kk][tx * 4 + u]; b2[u] = Bs2[kk][tx * 4 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            acc[u][v] = fma(a[u], b2[v], acc[u][v]);    // W1_i . W2_j
+            acc2[u][v] = fma(a2[u], bb[v], acc2[u][v]); // W2_i . W1_j
+          }
+      }
+    } else {
 #pragma unroll 8
-    for (int kk = 0; kk < TC; ++kk) {
-      double a[4], bb[4];
+      for (int kk = 0; kk < TC; ++kk) {
+        double a[4], bb[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = As[kk][ty * 4 + u];
+        for (int u = 0; u < 4; ++u) a[u] = As[kk][ty * 4 + u];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) bb[u] = Bs[kk][tx * 4 + u];
+        for (int u = 0; u < 4; ++u) bb[u] = Bs[kk][tx * 4 + u];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], bb[v], acc[u][v]);
+          for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], bb[v], acc[u][v]);
+      }
     }
     __syncthreads();
+    if (!two && k0 + TC == m_pad) {  // symmetric part accumulated once: mirror it before the two-sided tail
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc2[a][c] = acc[a][c];
+    }
   }
   // stage P(I,J) and P(J,I)^T, then write both
   for (int e = t; e < TC * TC; e += 64) {
@@ -305,16 +350,17 @@ __global__ void __launch_bounds__(64) k_downdate(double* __restrict__ P, int n, 
       const int r = ty * 4 + a, cc = tx * 4 + c;
       const int gi = I * TC + r, gj = J * TC + cc;
       if (gi < n && gj < n) {
-        const double v = 0.5 * (As[r][cc] + Bs[r][cc]) - acc[a][c];
+        const double v = 0.5 * (As[r][cc] + Bs[r][cc]) - 0.5 * (acc[a][c] + acc2[a][c]);
         P[(size_t)gi * n + gj] = v;
         if (I != J) P[(size_t)gj * n + gi] = v;
       }
     }
 }
 
-void downdate_f64(cudaStream_t s, double* P, int n, const double* W, int ldw, int kdim) {
+void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
+                  const int* tileflag, const double* Zb, const double* Yb) {
   const int nt = (n + TC - 1) / TC;
-  k_downdate<<<nt * (nt + 1) / 2, 64, 0, s>>>(P, n, W, ldw, kdim);
+  k_downdate<<<nt * (nt + 1) / 2, 64, 0, s>>>(P, n, T, m_pad, n_pad, omega_inv, tileflag, Zb, Yb);
   count_launch();
 }
 

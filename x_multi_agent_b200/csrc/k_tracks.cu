@@ -73,9 +73,9 @@ struct WarpSmem {
     Y = base; base += 6 * Lm;
     V = base; base += 6 * Lm;
     res = base; base += 2 * Lm;
-    X = base;  // (2Lm+1)(2Lm+2)/2 packed lower triangle incl. the augmented residual row
+    X = base;  // (2Lm+7)(2Lm+8)/2 packed lower triangle incl. 7 augmented rows (Pi r and the 6 clone columns)
   }
-  static __host__ __device__ size_t doubles(int Lm) { return (size_t)50 * Lm + (size_t)(2 * Lm + 1) * (2 * Lm + 2) / 2; }
+  static __host__ __device__ size_t doubles(int Lm) { return (size_t)50 * Lm + (size_t)(2 * Lm + 7) * (2 * Lm + 8) / 2; }
 };
 
 // dot of two length-n smem vectors with stride, over the warp
@@ -394,8 +394,14 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
           for (int c = 0; c < 3; ++c) {
             double tp0 = 0, tp1 = 0, ta0 = 0, ta1 = 0;
             for (int a = 0; a < 3; ++a) {
-              const double ppp = P[(size_t)(rp + a) * ld + cpn + c], pap = P[(size_t)(ra + a) * ld + cpn + c];
-              const double ppa = P[(size_t)(rp + a) * ld + can + c], paa = P[(size_t)(ra + a) * ld + can + c];
+              double ppp = P[(size_t)(rp + a) * ld + cpn + c], pap = P[(size_t)(ra + a) * ld + cpn + c];
+              double ppa = P[(size_t)(rp + a) * ld + can + c], paa = P[(size_t)(ra + a) * ld + can + c];
+              if (pi_ == np - 1 && pk_ == np - 1) {  // the newest clone's own block is not symmetric: use sym(P)
+                ppp = 0.5 * (ppp + P[(size_t)(cpn + c) * ld + rp + a]);
+                pap = 0.5 * (pap + P[(size_t)(cpn + c) * ld + ra + a]);
+                ppa = 0.5 * (ppa + P[(size_t)(can + c) * ld + rp + a]);
+                paa = 0.5 * (paa + P[(size_t)(can + c) * ld + ra + a]);
+              }
               tp0 = fma(Ji_p[a], ppp, tp0); tp0 = fma(Ji_a[a], pap, tp0);
               tp1 = fma(Ji_p[3 + a], ppp, tp1); tp1 = fma(Ji_a[3 + a], pap, tp1);
               ta0 = fma(Ji_p[a], ppa, ta0); ta0 = fma(Ji_a[a], paa, ta0);
@@ -452,6 +458,20 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     double* aug = ws.X + tri_idx(R2, 0);
     for (int r = lane; r < R2; r += 32)
       aug[r] = ws.res[r] - (ws.U[r * 3] * ur[0] + ws.U[r * 3 + 1] * ur[1] + ws.U[r * 3 + 2] * ur[2]);
+    // rows R2+1+k: V^T, V = Pi J_c with J_c = J[:, 6 columns of the newest clone]  (antisymmetric part of P lives there)
+    const int ccol[6] = {3 * (np - 1), 3 * (np - 1) + 1, 3 * (np - 1) + 2, 3 * M + 3 * (np - 1), 3 * M + 3 * (np - 1) + 1,
+                         3 * M + 3 * (np - 1) + 2};
+    for (int k = 0; k < 6; ++k) {
+      double* vr = ws.X + tri_idx(R2 + 1 + k, 0);
+      const double b0 = Bt[ccol[k]], b1 = Bt[W + ccol[k]], b2 = Bt[2 * W + ccol[k]];
+      for (int r = lane; r < R2; r += 32) {
+        const int i = r >> 1, h = r & 1;
+        double jc = 0.0;
+        if (i1 + i == np - 1) jc += (k < 3 ? ws.Jp : ws.Ja)[6 * i + 3 * h + (k % 3)];
+        if (slam_mode) jc += (k < 3 ? ws.Jap : ws.Jaa)[6 * i + 3 * h + (k % 3)];
+        vr[r] = jc - (ws.U[r * 3] * b0 + ws.U[r * 3 + 1] * b1 + ws.U[r * 3 + 2] * b2);
+      }
+    }
     __syncwarp();
     // Cholesky of the (R2+1)-row augmented lower triangle; last row becomes y = L^-1 (Pi r)
     bool spd = true;
@@ -460,18 +480,71 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       if (!(piv > 0.0)) { spd = false; break; }
       const double d = sqrt(piv);
       __syncwarp();
-      for (int r = c + 1 + lane; r <= R2; r += 32) ws.X[tri_idx(r, c)] /= d;
+      for (int r = c + 1 + lane; r <= R2 + 6; r += 32) ws.X[tri_idx(r, c)] /= d;
       __syncwarp();
-      for (int r = c + 1 + lane; r <= R2; r += 32) {
+      for (int r = c + 1 + lane; r <= R2 + 6; r += 32) {
         const double lrc = ws.X[tri_idx(r, c)];
         double* row = ws.X + tri_idx(r, 0);
-        const int kend = (r < R2) ? r : R2 - 1;  // the augmented row has no diagonal entry
+        const int kend = (r < R2) ? r : R2 - 1;  // the augmented rows have no diagonal entries
         for (int k = c + 1; k <= kend; ++k) row[k] = fma(-lrc, ws.X[tri_idx(k, c)], row[k]);
       }
       __syncwarp();
     }
     if (spd) {
+      // gamma = r^T S^-1 r with S = S_s + V E V^T (E = antisymmetric part of the clone block of P):
+      //   y^T y - (Vt^T y)^T E (I + G E)^-1 (Vt^T y),  Vt = L^-1 V,  G = Vt^T Vt      (Woodbury)
       gamma = wdot(aug, 1, aug, 1, R2, lane);
+      double Em[36], emax = 0.0;
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) {
+          Em[a * 6 + b] = 0.5 * (P[(size_t)(XB_CORE + ccol[a]) * ld + XB_CORE + ccol[b]] -
+                                 P[(size_t)(XB_CORE + ccol[b]) * ld + XB_CORE + ccol[a]]);
+          emax = fmax(emax, fabs(Em[a * 6 + b]));
+        }
+      if (emax > 0.0) {
+        double Gm[36], gv[6], Am[6][12];
+        for (int a = 0; a < 6; ++a) {
+          gv[a] = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, aug, 1, R2, lane);
+          for (int b = 0; b <= a; ++b) {
+            Gm[a * 6 + b] = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, ws.X + tri_idx(R2 + 1 + b, 0), 1, R2, lane);
+            Gm[b * 6 + a] = Gm[a * 6 + b];
+          }
+        }
+        for (int a = 0; a < 6; ++a)
+          for (int b = 0; b < 12; ++b) {
+            double v = 0.0;
+            if (b < 6) {
+              v = (a == b) ? 1.0 : 0.0;
+              for (int x = 0; x < 6; ++x) v = fma(Gm[a * 6 + x], Em[x * 6 + b], v);
+            } else {
+              v = (b - 6 == a) ? 1.0 : 0.0;
+            }
+            Am[a][b] = v;
+          }
+        for (int c = 0; c < 6; ++c) {  // Gauss-Jordan, partial pivoting (all lanes redundantly)
+          int best = c;
+          for (int r = c + 1; r < 6; ++r)
+            if (fabs(Am[r][c]) > fabs(Am[best][c])) best = r;
+          if (best != c)
+            for (int b = 0; b < 12; ++b) { const double tmp = Am[c][b]; Am[c][b] = Am[best][b]; Am[best][b] = tmp; }
+          const double d = Am[c][c];
+          for (int b = 0; b < 12; ++b) Am[c][b] /= d;
+          for (int r = 0; r < 6; ++r)
+            if (r != c) {
+              const double fct = Am[r][c];
+              for (int b = 0; b < 12; ++b) Am[r][b] = fma(-fct, Am[c][b], Am[r][b]);
+            }
+        }
+        double t6[6];
+        for (int a = 0; a < 6; ++a) {
+          t6[a] = 0.0;
+          for (int b = 0; b < 6; ++b) t6[a] = fma(Am[a][6 + b], gv[b], t6[a]);  // (I+GE)^-1 g
+        }
+        double corr = 0.0;
+        for (int a = 0; a < 6; ++a)
+          for (int b = 0; b < 6; ++b) corr = fma(gv[a] * Em[a * 6 + b], t6[b], corr);
+        gamma -= corr;
+      }
       const double chi = tp.chi2_95[2 * L - 3];
       inl = gamma < chi;
     }
@@ -622,7 +695,8 @@ __global__ void k_slam_rows(SlamParams sp) {
     }
   }
   // gate: S = h P h^T + var I (2x2), chi2(0.9, 2*track_size)  (slam_update.cpp:192-199)
-  double s00 = 0, s01 = 0, s11 = 0;
+  // S = h P h^T + var I is evaluated with the (possibly non-symmetric) P exactly as the reference does
+  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
   for (int c = 0; c < nc; ++c) {
     double t0 = 0, t1 = 0;
     for (int d = 0; d < nc; ++d) {
@@ -632,12 +706,13 @@ __global__ void k_slam_rows(SlamParams sp) {
     }
     s00 = fma(t0, h[c], s00);
     s01 = fma(t0, h[15 + c], s01);
+    s10 = fma(t1, h[c], s10);
     s11 = fma(t1, h[15 + c], s11);
   }
   s00 += sp.var_img;
   s11 += sp.var_img;
-  const double det = s00 * s11 - s01 * s01;
-  const double gamma = (r0 * (s11 * r0 - s01 * r1) + r1 * (s00 * r1 - s01 * r0)) / det;
+  const double det = s00 * s11 - s01 * s10;
+  const double gamma = (r0 * (s11 * r0 - s01 * r1) + r1 * (s00 * r1 - s10 * r0)) / det;
   sp.gamma[j] = gamma;
   const int inl = gamma < sp.chi2[j];
   sp.inlier[j] = inl;
@@ -770,6 +845,7 @@ __global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const d
   } else if (r == c && r >= n && r < cols_pad) {
     v = 1.0;  // identity padding keeps the factor well defined
   }
+  if (r < cols_pad && (c >> 5) > (r >> 5)) v = 0.0;  // tiles above the diagonal: the factor is lower triangular
   T[(size_t)r * ld + c] = v;
 }
 

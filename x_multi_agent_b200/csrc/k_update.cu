@@ -5,11 +5,23 @@
 //
 // Tall buffer T (leading dimension ld = m_pad):
 //   rows [0, m_pad)                S = Hc P Hc^T + var I   (identity on the padding)
-//   rows [m_pad, m_pad + n_pad)    P Hc^T
-//   row  m_pad + n_pad             r_eff^T = (res + Hc * correction_total)^T
+//   rows [m_pad, m_pad + n_pad)    A1 = P Hc^T
+//   row  m_pad + n_pad             r_eff^T = (res + Hc * correction_total)^T          (aux tile, 32 rows)
+//   rows m_pad + n_pad + 32 + k    A2[Omega_k, :] = (P^T Hc^T)[Omega_k, :], k < 21       (Omega tile, 32 rows)
+//   rows m_pad + n_pad + 64 + k    V^T[k] = Hc[:, Omega_k]^T, k < 21                     (V tile, 32 rows)
+//
+// Omega = the 15 core states + the 6 states of the newest clone: between two updates the reference's P is
+// NOT symmetric there (its Q_d is not symmetric, propagator.cpp:207-840, and augmentCovariance copies the
+// core block into the clone, state_manager.cpp:273-349).  With E = (P - P^T)/2 (support Omega x Omega) the
+// reference's  K = P H^T (H P H^T + R)^-1,  P <- sym((I - K H) P)  is evaluated exactly as
+//   S_s = sym(H P H^T) + R = L L^T,  W1 = A1 L^-T,  W2 = A2 L^-T (differs from W1 on Omega rows only),
+//   Vt = L^-1 V,  G = Vt^T Vt,  C = E (I + G E)^-1                                   (Woodbury, rank <= 21)
+//   K A2^T = W1 W2^T - (W1 Vt) C (W2 Vt)^T ,   K r = W1 z - (W1 Vt) C (Vt^T z).
 #include "xb_kernels.h"
 
 namespace xb {
+
+#define NOM 21  // |Omega| = 15 core + 6 clone states
 
 // PHt[i, ms + 2j + r] = sum_e P[i, col_e] * val[j][r][e]
 __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int* __restrict__ scols,
@@ -71,6 +83,7 @@ __global__ void k_s_finish(UpdateDims d, const double* __restrict__ Rg, int ldr,
   reff[a] = r;
 }
 
+void launch_sym_lower(cudaStream_t s, double* T, int ld, int m);
 void launch_build_pht(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
                       const double* svals, double* T) {
   // slab columns: PHt[:, 0:ms] = P[:, pose] * Rg^T
@@ -91,6 +104,7 @@ void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, int l
     k_s_slam<<<g, 128, 0, s>>>(d, scols, svals, T);
     count_launch();
   }
+  launch_sym_lower(s, T, d.ld, d.m);
   k_s_finish<<<(d.m_pad + 127) / 128, 128, 0, s>>>(d, Rg, ldr, zg, scols, svals, sres, corr_total, var, T);
   count_launch();
 }
@@ -112,25 +126,160 @@ __global__ void k_dense_finish(int m, int m_pad, int n_pad, int N, const double*
     for (int b = 0; b < N; ++b) r = fma(H[(size_t)a * N + b], corr[b], r);
   reff[a] = r;
 }
-void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, const double* P, const double* H,
-                          const double* res, const double* rdiag, const double* corr_total, double* T) {
-  gemm_nt(s, N, m, N, 1.0, P, N, H, N, 0.0, T + (size_t)m_pad * m_pad, m_pad);          // P H^T
-  gemm_nn(s, m, m, N, 1.0, H, N, T + (size_t)m_pad * m_pad, m_pad, 0.0, T, m_pad);      // H (P H^T)
-  k_dense_finish<<<(m_pad + 127) / 128, 128, 0, s>>>(m, m_pad, n_pad, N, H, res, rdiag, corr_total, T);
-  count_launch();
+// ---- Omega rows for the VIO (structured Hc) path ------------------------------------------------------
+__global__ void k_omega_rows(UpdateDims d, const double* __restrict__ P, const double* __restrict__ Rg, int ldr,
+                             const int* __restrict__ scols, const double* __restrict__ svals, const int* __restrict__ omega,
+                             double* __restrict__ T) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (a >= d.m) return;
+  const int ok = omega[k];
+  double v = 0.0, a2 = 0.0;
+  if (a < d.ms) {
+    if (ok >= XB_CORE && ok < XB_CORE + d.ms) v = Rg[(size_t)a * ldr + ok - XB_CORE];
+    for (int b = 0; b < d.ms; ++b) a2 = fma(P[(size_t)(XB_CORE + b) * d.N + ok], Rg[(size_t)a * ldr + b], a2);
+  } else {
+    const int j = (a - d.ms) >> 1, h = (a - d.ms) & 1;
+    for (int e = 0; e < 15; ++e) {
+      const int col = scols[15 * j + e];
+      const double hv = svals[30 * j + 15 * h + e];
+      if (col == ok) v += hv;
+      a2 = fma(P[(size_t)col * d.N + ok], hv, a2);
+    }
+  }
+  T[(size_t)(d.m_pad + d.n_pad + 32 + k) * d.ld + a] = a2;
+  T[(size_t)(d.m_pad + d.n_pad + 64 + k) * d.ld + a] = v;
+}
+// dense-H variant
+__global__ void k_omega_rows_dense(int m, int m_pad, int n_pad, int N, const double* __restrict__ P,
+                                   const double* __restrict__ H, const int* __restrict__ omega, double* __restrict__ T) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (a >= m) return;
+  const int ok = omega[k];
+  double a2 = 0.0;
+  for (int j = 0; j < N; ++j) a2 = fma(P[(size_t)j * N + ok], H[(size_t)a * N + j], a2);
+  T[(size_t)(m_pad + n_pad + 32 + k) * m_pad + a] = a2;
+  T[(size_t)(m_pad + n_pad + 64 + k) * m_pad + a] = H[(size_t)a * N + ok];
+}
+// lower(S) <- lower((S + S^T)/2)
+__global__ void k_sym_lower(double* __restrict__ T, int ld, int m) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r < m && c < r) T[(size_t)r * ld + c] = 0.5 * (T[(size_t)r * ld + c] + T[(size_t)c * ld + r]);
 }
 
-// delta = W z - corr_total   (updater.cpp:127-129), one warp per state row
-__global__ void k_delta(int N, int m_pad, int n_pad, const double* __restrict__ T, const double* __restrict__ corr,
-                        double* __restrict__ delta) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= N) return;
-  const double* Wr = T + (size_t)(m_pad + w) * m_pad;
+// After the tile Cholesky: G = Vt Vt^T, q = Vt z, E from P, C = E (I + G E)^-1.   om = [C 21x21 | q 21]
+__global__ void __launch_bounds__(256) k_omega_small(int N, int m_pad, int n_pad, const double* __restrict__ T,
+                                                     const double* __restrict__ P, const int* __restrict__ omega,
+                                                     double* __restrict__ om) {
+  __shared__ double G[NOM][NOM], E[NOM][NOM], A[NOM][2 * NOM + 1], q[NOM];
+  __shared__ int piv;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const double* Vt = T + (size_t)(m_pad + n_pad + 64) * m_pad;
   const double* z = T + (size_t)(m_pad + n_pad) * m_pad;
-  double s = 0.0;
-  for (int k = lane; k < m_pad; k += 32) s = fma(Wr[k], z[k], s);
-  s = xb_warp_sum(s);
-  if (lane == 0) delta[w] = s - (corr ? corr[w] : 0.0);
+  for (int e = w; e < NOM * NOM + NOM; e += 8) {  // one warp per dot product
+    const int k = e / NOM, l = e % NOM;
+    const double* a = Vt + (size_t)(e < NOM * NOM ? k : e - NOM * NOM) * m_pad;
+    const double* b = e < NOM * NOM ? Vt + (size_t)l * m_pad : z;
+    double s = 0.0;
+    for (int c = lane; c < m_pad; c += 32) s = fma(a[c], b[c], s);
+    s = xb_warp_sum(s);
+    if (lane == 0) {
+      if (e < NOM * NOM) G[k][l] = s; else q[e - NOM * NOM] = s;
+    }
+  }
+  for (int e = t; e < NOM * NOM; e += 256) {
+    const int k = e / NOM, l = e % NOM;
+    E[k][l] = 0.5 * (P[(size_t)omega[k] * N + omega[l]] - P[(size_t)omega[l] * N + omega[k]]);
+  }
+  __syncthreads();
+  // A = [I + G E | I]
+  for (int e = t; e < NOM * 2 * NOM; e += 256) {
+    const int r = e / (2 * NOM), c = e % (2 * NOM);
+    double v;
+    if (c < NOM) {
+      v = (r == c) ? 1.0 : 0.0;
+      for (int x = 0; x < NOM; ++x) v = fma(G[r][x], E[x][c], v);
+    } else {
+      v = (c - NOM == r) ? 1.0 : 0.0;
+    }
+    A[r][c] = v;
+  }
+  __syncthreads();
+  for (int c = 0; c < NOM; ++c) {  // Gauss-Jordan with partial pivoting
+    if (t == 0) {
+      int best = c;
+      double bv = fabs(A[c][c]);
+      for (int r = c + 1; r < NOM; ++r)
+        if (fabs(A[r][c]) > bv) { bv = fabs(A[r][c]); best = r; }
+      piv = best;
+    }
+    __syncthreads();
+    if (piv != c && t < 2 * NOM) { const double tmp = A[c][t]; A[c][t] = A[piv][t]; A[piv][t] = tmp; }
+    __syncthreads();
+    const double d = A[c][c];
+    __syncthreads();
+    if (t < 2 * NOM) A[c][t] /= d;
+    __syncthreads();
+    for (int e = t; e < NOM * 2 * NOM; e += 256) {
+      const int r = e / (2 * NOM), cc = e % (2 * NOM);
+      if (r != c && cc != c) A[r][cc] = fma(-A[r][c], A[c][cc], A[r][cc]);
+    }
+    __syncthreads();
+    if (t < NOM && t != c) A[t][c] = 0.0;
+    __syncthreads();
+  }
+  // C = E * inv
+  for (int e = t; e < NOM * NOM; e += 256) {
+    const int r = e / NOM, c = e % NOM;
+    double v = 0.0;
+    for (int x = 0; x < NOM; ++x) v = fma(E[r][x], A[x][NOM + c], v);
+    om[e] = v;
+  }
+  if (t < NOM) om[NOM * NOM + t] = q[t];
+}
+
+// One warp per state row i:  Y1 = W1_i Vt^T, Y2f (Omega rows use W2), Z1 = Y1 C,
+//   delta_i = W1_i z - Z1 . q - corr_i      (updater.cpp:127-129)
+__global__ void __launch_bounds__(128) k_omega_rowsolve(int N, int m_pad, int n_pad, const double* __restrict__ T,
+                                                        const double* __restrict__ om, const int* __restrict__ omega_inv,
+                                                        const double* __restrict__ corr, double* __restrict__ delta,
+                                                        double* __restrict__ Zb, double* __restrict__ Yb) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const double* W1 = T + (size_t)(m_pad + i) * m_pad;
+  const int ki = omega_inv[i];
+  const double* W2 = ki >= 0 ? T + (size_t)(m_pad + n_pad + 32 + ki) * m_pad : W1;
+  const double* Vt = T + (size_t)(m_pad + n_pad + 64) * m_pad;
+  const double* z = T + (size_t)(m_pad + n_pad) * m_pad;
+  double y1[NOM], y2[NOM], wz = 0.0;
+#pragma unroll
+  for (int k = 0; k < NOM; ++k) { y1[k] = 0.0; y2[k] = 0.0; }
+  for (int c = lane; c < m_pad; c += 32) {
+    const double a = W1[c], b = W2[c];
+    wz = fma(a, z[c], wz);
+#pragma unroll
+    for (int k = 0; k < NOM; ++k) {
+      const double v = Vt[(size_t)k * m_pad + c];
+      y1[k] = fma(a, v, y1[k]);
+      y2[k] = fma(b, v, y2[k]);
+    }
+  }
+  wz = xb_warp_sum(wz);
+#pragma unroll
+  for (int k = 0; k < NOM; ++k) { y1[k] = xb_warp_sum(y1[k]); y2[k] = xb_warp_sum(y2[k]); }
+  // Z1[l] = sum_k y1[k] C[k][l]   (lane l)
+  double zl = 0.0;
+  if (lane < NOM)
+#pragma unroll
+    for (int k = 0; k < NOM; ++k) zl = fma(y1[k], om[k * NOM + lane], zl);
+  double zq = (lane < NOM) ? zl * om[NOM * NOM + lane] : 0.0;
+  zq = xb_warp_sum(zq);
+  double y2l = 0.0;
+#pragma unroll
+  for (int k = 0; k < NOM; ++k)
+    if (lane == k) y2l = y2[k];
+  Zb[(size_t)i * 32 + lane] = (lane < NOM) ? zl : 0.0;
+  Yb[(size_t)i * 32 + lane] = (lane < NOM) ? y2l : 0.0;
+  if (lane == 0) delta[i] = wz - zq - (corr ? corr[i] : 0.0);
 }
 
 // State::correct (state.cpp:197-249) + correction_total += correction (updater.cpp:140)
@@ -158,11 +307,58 @@ __global__ void k_correct(int M, int F, int N, const double* __restrict__ delta,
   }
 }
 
-void launch_correct(cudaStream_t s, int M, int F, int N, const double* T, int m_pad, int n_pad, double* xv,
+void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, const double* P, const double* H,
+                          const double* res, const double* rdiag, const double* corr_total, const int* omega, double* T) {
+  gemm_nt(s, N, m, N, 1.0, P, N, H, N, 0.0, T + (size_t)m_pad * m_pad, m_pad);          // P H^T
+  gemm_nn(s, m, m, N, 1.0, H, N, T + (size_t)m_pad * m_pad, m_pad, 0.0, T, m_pad);      // H (P H^T)
+  launch_sym_lower(s, T, m_pad, m);
+  {
+    dim3 g((m + 127) / 128, NOM);
+    k_omega_rows_dense<<<g, 128, 0, s>>>(m, m_pad, n_pad, N, P, H, omega, T);
+    count_launch();
+  }
+  k_dense_finish<<<(m_pad + 127) / 128, 128, 0, s>>>(m, m_pad, n_pad, N, H, res, rdiag, corr_total, T);
+  count_launch();
+}
+
+void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
+                       const double* svals, const int* omega, double* T) {
+  dim3 g((d.m + 127) / 128, NOM);
+  k_omega_rows<<<g, 128, 0, s>>>(d, P, Rg, ldr, scols, svals, omega, T);
+  count_launch();
+}
+void launch_sym_lower(cudaStream_t s, double* T, int ld, int m) {
+  dim3 b(32, 8), g((m + 31) / 32, (m + 7) / 8);
+  k_sym_lower<<<g, b, 0, s>>>(T, ld, m);
+  count_launch();
+}
+void launch_correct(cudaStream_t s, int M, int F, int N, const double* T, int m_pad, int n_pad, const double* P,
+                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* xv,
                     double* corr_total, double* delta_out) {
-  k_delta<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, m_pad, n_pad, T, corr_total, delta_out);
+  k_omega_small<<<1, 256, 0, s>>>(N, m_pad, n_pad, T, P, omega, om);
+  count_launch();
+  k_omega_rowsolve<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, m_pad, n_pad, T, om, omega_inv, corr_total, delta_out, Zb, Yb);
   count_launch();
   launch_apply_delta(s, M, F, N, delta_out, xv, corr_total);
+}
+// P <- sym(P_j - K (H P_j))   (updater.cpp:153-156), m small
+__global__ void __launch_bounds__(256) k_ci_cov(double* __restrict__ P, int N, const double* __restrict__ K,
+                                                const double* __restrict__ HP, int m) {
+  const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (i >= N || j >= N || i > j) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < m; ++k) {
+    a = fma(K[(size_t)i * m + k], HP[(size_t)k * N + j], a);
+    b = fma(K[(size_t)j * m + k], HP[(size_t)k * N + i], b);
+  }
+  const double v = 0.5 * ((P[(size_t)i * N + j] - a) + (P[(size_t)j * N + i] - b));
+  P[(size_t)i * N + j] = v;
+  P[(size_t)j * N + i] = v;
+}
+void launch_ci_cov(cudaStream_t s, double* P, int N, const double* K, const double* HP, int m) {
+  dim3 g((N + 15) / 16, (N + 15) / 16);
+  k_ci_cov<<<g, 256, 0, s>>>(P, N, K, HP, m);
+  count_launch();
 }
 void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta, double* xv, double* corr_total) {
   k_correct<<<(N + 127) / 128, 128, 0, s>>>(M, F, N, delta, xv, corr_total);

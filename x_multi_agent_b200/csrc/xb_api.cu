@@ -157,6 +157,10 @@ struct xb_filter {
   // dense-H scratch
   double* d_Hdense = nullptr; size_t Hdense_doubles = 0;
   void* d_tcws = nullptr;
+  // Omega (core + newest clone) bookkeeping for the non-symmetric part of P
+  int *d_omega = nullptr, *d_omega_inv = nullptr, *d_tileflag = nullptr;
+  double *d_om = nullptr, *d_Zb = nullptr, *d_Yb = nullptr;
+  int omega_slot = -2;
   std::vector<void*> allocs;
 };
 
@@ -306,9 +310,15 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
 
   const int m_max = std::max(6 * M + 2 * F, N);  // dense-H path allows up to N rows
   const int m_pad = pad32(m_max), n_pad = pad32(N);
-  f->T_doubles = (size_t)(m_pad + n_pad + 32) * m_pad;
+  f->T_doubles = (size_t)(m_pad + n_pad + 96) * m_pad;
   DA(f->d_T, f->T_doubles, double);
-  DA(f->d_flags, (size_t)((m_pad + n_pad + 32) / 32) * (m_pad / 32) + 64, int);
+  DA(f->d_flags, (size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64, int);
+  DA(f->d_omega, 32, int);
+  DA(f->d_omega_inv, n_pad, int);
+  DA(f->d_tileflag, n_pad / 32 + 1, int);
+  DA(f->d_om, 21 * 21 + 32, double);
+  DA(f->d_Zb, (size_t)n_pad * 32, double);
+  DA(f->d_Yb, (size_t)n_pad * 32, double);
   DA(f->d_err, 4, int);
 
   DA(f->d_rowmap, N, int);
@@ -820,15 +830,39 @@ static UpdateDims update_dims(const xb_filter* f, int nslam) {
   return d;
 }
 
+// Omega = 15 core states + the 6 states of the newest clone (where P is not symmetric between updates)
+static int set_omega(xb_filter* f) {
+  const int slot = std::max(0, f->n_poses - 1);
+  if (slot == f->omega_slot) return 0;
+  const int N = f->N, M = f->M, n_pad = pad32(N);
+  std::vector<int> om(32, 0), inv(n_pad, -1), flag(n_pad / 32 + 1, 0);
+  for (int k = 0; k < 15; ++k) om[k] = k;
+  for (int c = 0; c < 3; ++c) { om[15 + c] = XB_CORE + 3 * slot + c; om[18 + c] = XB_CORE + 3 * M + 3 * slot + c; }
+  for (int k = 0; k < 21; ++k) { inv[om[k]] = k; flag[om[k] / 32] = 1; }
+  CK(cudaMemcpyAsync(f->d_omega, om.data(), sizeof(int) * 32, cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_omega_inv, inv.data(), sizeof(int) * n_pad, cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_tileflag, flag.data(), sizeof(int) * flag.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  f->omega_slot = slot;
+  return 0;
+}
+
 static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total) {
   const int N = f->N;
-  tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 32, m_pad, f->d_flags, f->d_err, 0.0);
-  launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_xw, corr_total, f->d_delta);
+  tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0);
+  launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
+                 f->d_Yb, f->d_xw, corr_total, f->d_delta);
   if (cov_update) {
-    const double* W = f->d_T + (size_t)m_pad * m_pad;
-    if (f->cfg.downdate_precision == 1) downdate_tc(f->stream, f->d_Pw, N, W, m_pad, m_pad, f->d_tcws);
-    else downdate_f64(f->stream, f->d_Pw, N, W, m_pad, m_pad);
+    if (f->cfg.downdate_precision == 1)
+      downdate_tc(f->stream, f->d_Pw, N, f->d_T, m_pad, n_pad, f->d_omega_inv, f->d_tileflag, f->d_Zb, f->d_Yb, f->d_tcws);
+    else
+      downdate_f64(f->stream, f->d_Pw, N, f->d_T, m_pad, n_pad, f->d_omega_inv, f->d_tileflag, f->d_Zb, f->d_Yb);
   }
+  return XB_OK;
+}
+
+extern "C" int xb_updater_reset_correction(xb_filter* f) {
+  CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * f->N, f->stream));
   return XB_OK;
 }
 
@@ -836,12 +870,15 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   if (!f->constructed_any) return XB_OK;  // h.size() == 0 (updater.cpp:106)
   const UpdateDims d = update_dims(f, f->last_nslam);
-  const size_t tb = sizeof(double) * (size_t)(d.m_pad + d.n_pad + 32) * d.m_pad;
+  const size_t tb = sizeof(double) * (size_t)(d.m_pad + d.n_pad + 96) * d.m_pad;
+  int rc0 = set_omega(f);
+  if (rc0) return rc0;
   CK(cudaMemsetAsync(f->d_T, 0, tb, f->stream));
   const double* zg = f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad;
   launch_build_pht(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_T);
   launch_build_s(f->stream, d, f->d_Rg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, f->d_corr,
                  f->cfg.sigma_img * f->cfg.sigma_img, f->d_T);
+  launch_omega_rows(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_omega, f->d_T);
   return apply_from_tall(f, d.m_pad, d.n_pad, cov_update, f->d_corr);
 }
 
@@ -851,7 +888,7 @@ extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const doub
   const int N = f->N;
   if (m <= 0) return XB_OK;
   const int m_pad = pad32(m), n_pad = pad32(N);
-  if ((size_t)(m_pad + n_pad + 32) * m_pad > f->T_doubles || (size_t)m * N + 2 * (size_t)m > f->Hdense_doubles)
+  if ((size_t)(m_pad + n_pad + 96) * m_pad > f->T_doubles || (size_t)m * N + 2 * (size_t)m > f->Hdense_doubles)
     return fail(XB_E_CAPACITY, "dense update has too many rows (max N after QR compression)");
   double* dH = f->d_Hdense;
   double* dres = dH + (size_t)m * N;
@@ -861,8 +898,10 @@ extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const doub
   CK(cudaMemcpyAsync(drd, r_diag, sizeof(double) * m, cudaMemcpyHostToDevice, f->stream));
   if (correction_total) CK(cudaMemcpyAsync(f->d_corr, correction_total, sizeof(double) * N, cudaMemcpyHostToDevice, f->stream));
   else CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * N, f->stream));
-  CK(cudaMemsetAsync(f->d_T, 0, sizeof(double) * (size_t)(m_pad + n_pad + 32) * m_pad, f->stream));
-  launch_dense_prepare(f->stream, m, m_pad, N, n_pad, f->d_Pw, dH, dres, drd, f->d_corr, f->d_T);
+  int rc0 = set_omega(f);
+  if (rc0) return rc0;
+  CK(cudaMemsetAsync(f->d_T, 0, sizeof(double) * (size_t)(m_pad + n_pad + 96) * m_pad, f->stream));
+  launch_dense_prepare(f->stream, m, m_pad, N, n_pad, f->d_Pw, dH, dres, drd, f->d_corr, f->d_omega, f->d_T);
   int rc = apply_from_tall(f, m_pad, n_pad, cov_update, f->d_corr);
   if (rc) return rc;
   if (correction_total) CK(cudaMemcpyAsync(correction_total, f->d_corr, sizeof(double) * N, cudaMemcpyDeviceToHost, f->stream));
@@ -871,36 +910,60 @@ extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const doub
 }
 
 // Updater::applyCI (updater.cpp:144-161): K = P_j H^T S^-1; delta = K r; P = (I - K H) P_j; symmetrise; correct.
+// S is the caller's (CI-fused) innovation covariance; it is tiny (3k x 3k), so S^-1 is formed on the host by
+// partial-pivoting Gauss-Jordan exactly like the reference's S.inverse(); everything N-sized runs on the device.
 extern "C" int xb_updater_apply_ci(xb_filter* f, const double* H, const double* res, const double* S, int m,
                                    const int* scaled_block_cols, int n_blocks, double w_result) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   const int N = f->N;
   if (m <= 0 || m > 96) return fail(XB_E_INVALID, "applyCI: 0 < rows <= 96");
-  const int m_pad = pad32(m), n_pad = pad32(N);
+  std::vector<double> A((size_t)m * 2 * m, 0.0);
+  for (int r = 0; r < m; ++r) {
+    for (int c = 0; c < m; ++c) A[(size_t)r * 2 * m + c] = S[(size_t)r * m + c];
+    A[(size_t)r * 2 * m + m + r] = 1.0;
+  }
+  for (int c = 0; c < m; ++c) {
+    int best = c;
+    for (int r = c + 1; r < m; ++r)
+      if (std::fabs(A[(size_t)r * 2 * m + c]) > std::fabs(A[(size_t)best * 2 * m + c])) best = r;
+    if (A[(size_t)best * 2 * m + c] == 0.0) return fail(XB_E_RUNTIME, "applyCI: singular S");
+    if (best != c)
+      for (int k = 0; k < 2 * m; ++k) std::swap(A[(size_t)c * 2 * m + k], A[(size_t)best * 2 * m + k]);
+    const double d = A[(size_t)c * 2 * m + c];
+    for (int k = 0; k < 2 * m; ++k) A[(size_t)c * 2 * m + k] /= d;
+    for (int r = 0; r < m; ++r)
+      if (r != c) {
+        const double fct = A[(size_t)r * 2 * m + c];
+        if (fct != 0.0)
+          for (int k = 0; k < 2 * m; ++k) A[(size_t)r * 2 * m + k] -= fct * A[(size_t)c * 2 * m + k];
+      }
+  }
+  std::vector<double> Sinv((size_t)m * m);
+  for (int r = 0; r < m; ++r)
+    for (int c = 0; c < m; ++c) Sinv[(size_t)r * m + c] = A[(size_t)r * 2 * m + m + c];
   double* dH = f->d_Hdense;
   double* dres = dH + (size_t)m * N;
   int* dcols = (int*)(dres + m + 2);
+  double* A1 = f->d_T;                   // N x m
+  double* Kd = A1 + (size_t)N * m;       // N x m
+  double* HP = Kd + (size_t)N * m;       // m x N
+  double* dSinv = HP + (size_t)N * m;    // m x m
   CK(cudaMemcpyAsync(dH, H, sizeof(double) * (size_t)m * N, cudaMemcpyHostToDevice, f->stream));
   CK(cudaMemcpyAsync(dres, res, sizeof(double) * m, cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(dSinv, Sinv.data(), sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, f->stream));
   if (n_blocks > 0) {
     if (n_blocks > 256) return fail(XB_E_INVALID, "too many scaled blocks");
     CK(cudaMemcpyAsync(dcols, scaled_block_cols, sizeof(int) * n_blocks, cudaMemcpyHostToDevice, f->stream));
     launch_scale_blocks(f->stream, f->d_Pw, N, dcols, n_blocks, w_result);  // P_j (only diagonal 3x3 blocks)
   }
-  CK(cudaMemsetAsync(f->d_T, 0, sizeof(double) * (size_t)(m_pad + n_pad + 32) * m_pad, f->stream));
-  // rows [0,m): S given by the caller; rows m_pad..: P_j H^T ; last: res
-  std::vector<double> Sp((size_t)m_pad * m_pad, 0.0);
-  for (int r = 0; r < m_pad; ++r)
-    for (int c = 0; c < m_pad; ++c)
-      Sp[(size_t)r * m_pad + c] = (r < m && c < m) ? 0.5 * (S[(size_t)r * m + c] + S[(size_t)c * m + r]) : (r == c ? 1.0 : 0.0);
-  CK(cudaMemcpyAsync(f->d_T, Sp.data(), sizeof(double) * Sp.size(), cudaMemcpyHostToDevice, f->stream));
-  gemm_nt(f->stream, N, m, N, 1.0, f->d_Pw, N, dH, N, 0.0, f->d_T + (size_t)m_pad * m_pad, m_pad);
-  CK(cudaMemcpyAsync(f->d_T + (size_t)(m_pad + n_pad) * m_pad, dres, sizeof(double) * m, cudaMemcpyDeviceToDevice, f->stream));
-  CK(cudaStreamSynchronize(f->stream));  // Sp lifetime
-  // NOTE: with P_j != P the reference's (I-KH)P_j is not symmetric before 0.5(P+P^T); P_j differs from a
-  // symmetric matrix only by a symmetric scaling of diagonal blocks, so P_j stays symmetric and the
-  // Cholesky form applies unchanged.
-  return apply_from_tall(f, m_pad, n_pad, 1, nullptr);
+  gemm_nt(f->stream, N, m, N, 1.0, f->d_Pw, N, dH, N, 0.0, A1, m);    // P_j H^T
+  gemm_nn(f->stream, N, m, m, 1.0, A1, m, dSinv, m, 0.0, Kd, m);      // K
+  gemm_nn(f->stream, m, N, N, 1.0, dH, N, f->d_Pw, N, 0.0, HP, N);    // H P_j
+  gemv(f->stream, N, m, Kd, m, dres, f->d_delta);                      // delta = K r
+  launch_apply_delta(f->stream, f->M, f->F, N, f->d_delta, f->d_xw, nullptr);
+  launch_ci_cov(f->stream, f->d_Pw, N, Kd, HP, m);
+  CK(cudaStreamSynchronize(f->stream));  // host staging lifetime
+  return XB_OK;
 }
 
 // ---- VioUpdater::postUpdate (vio_updater.cpp:425-449) -----------------------------------------------------------------

@@ -235,6 +235,9 @@ class Filter:
     def construct_update(self, which=0):
         L.check(self.lib.xb_vio_construct_update(self.h, which))
 
+    def reset_correction(self):
+        L.check(self.lib.xb_updater_reset_correction(self.h))
+
     def apply_constructed(self, cov_update=True):
         L.check(self.lib.xb_updater_apply_constructed(self.h, int(cov_update)))
 

@@ -85,6 +85,7 @@ SIGNATURES = {
     "xb_work_get": (C.c_int, [_VP, c_double_p, c_double_p, C.c_int]),
     "xb_sm_manage": (C.c_int, [_VP, c_int_p, C.c_int]),
     "xb_vio_construct_update": (C.c_int, [_VP, C.c_int]),
+    "xb_updater_reset_correction": (C.c_int, [_VP]),
     "xb_updater_apply_constructed": (C.c_int, [_VP, C.c_int]),
     "xb_updater_apply_update": (C.c_int, [_VP, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int]),
     "xb_updater_apply_ci": (C.c_int, [_VP, c_double_p, c_double_p, c_double_p, C.c_int, c_int_p, C.c_int, C.c_double]),
