@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""EKF visual updates/sec on BASELINE cfg-2 (30-pose window, 200 SLAM + 800 MSCKF features), one agent per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     (the fp64 CPU port of the reference, host cores)
+
+A step = one Ekf::processUpdateMeasurement()-equivalent: manage + constructUpdate (MSCKF,
+SLAM) + compression + applyUpdate + postUpdate + re-propagation of the 10 buffered IMU states.  Inputs are
+synthetic normalised track lists at the VioUpdater::preProcess seam (x_multi_agent_b200/synth.py).
+`value` is device-timed (CUDA events on the filter's stream, inputs resident in HBM, L2 flushed between
+steps); `e2e` goes through the C ABI with HOST buffers (track upload + state readback inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, os.fspath(ROOT))
+
+METRIC = "ekf_visual_updates_per_sec"
+UNIT = "updates/s"
+CFG2 = dict(M=30, F=200, K=800)
+FILL_K = 40          # MSCKF tracks per update while the window fills (warm-up to steady state, untimed)
+N_FILL = 33          # frames until the window is full and all 200 SLAM features are initialised
+
+
+def workload_config(n_gpus, extra=None):
+    c = {"workload": "cfg-2: single-agent 30-pose window, 200 SLAM + 800 MSCKF (30-obs) tracks per update, "
+                     "10 IMU states re-propagated per update, ring buffer 250",
+         "window": 30, "slam_features": 200, "msckf_tracks": 800, "n_error_states": 795,
+         "agents": n_gpus, "parallelism": f"one agent per GPU x{n_gpus}, no data-path collective",
+         "l2": "flushed between steps (256 MiB write)",
+         "timing": "per-step CUDA events on the filter stream; IMU feed + track upload + L2 flush between steps untimed"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def build_scenario(seed):
+    from x_multi_agent_b200.synth import Scenario, SynthConfig, record
+    cfg = SynthConfig(M=CFG2["M"], F=CFG2["F"], K=FILL_K, seed=seed, slam_init_frame=CFG2["M"])
+    scn = Scenario(cfg)
+    fill = record(scn, N_FILL)
+    scn.c.K = CFG2["K"]
+    return scn, fill
+
+
+def steady_events(scn, k0, n):
+    """n further frames: ([imu samples between frames], measurement) with the 10-sample latency tail."""
+    c = scn.c
+    out = []
+    fed = (k0 - 1) * c.imu_per_frame + c.latency_imu
+    for k in range(k0, k0 + n):
+        upto = k * c.imu_per_frame + c.latency_imu
+        imu = []
+        for i in range(fed + 1, upto + 1):
+            t = i * scn.dt_imu
+            imu.append((t, i, *scn.imu_sample(t)))
+        fed = upto
+        out.append((imu, scn.measurement(k)))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_one_update(prior_state, sm_state, meas, sigma_img, k_sample=None):
+    """Time the fp64 CPU port of the reference (oracle/) on one update; returns (seconds_per_update, detail).
+    With k_sample < K the per-track stage runs on a sample of the MSCKF tracks and the row-proportional stages
+    are extrapolated to the full update (the dense formulation is linear in the number of tracks)."""
+    sys.path.insert(0, os.fspath(ROOT / "tests"))
+    import oracle
+    from oracle.updater import apply_qr_decomposition, apply_update
+    from oracle.updates import MsckfSlamUpdate, MsckfUpdate, SlamUpdate
+    from oracle_driver import to_oracle_state
+    s = to_oracle_state(prior_state)
+    M, F = prior_state.M, prior_state.F
+    upd = oracle.VioUpdaterOracle(M, F, sigma_img)
+    upd.sm.n_poses, upd.sm.n_features, upd.sm.anchor_idxs, upd.sm.filled_before = sm_state
+    upd.sm.anchor_idxs = list(upd.sm.anchor_idxs)
+    K = len(meas.msckf_trks)
+    ks = K if not k_sample else min(k_sample, K)
+    t = {}
+    t0 = time.perf_counter()
+    upd.sm.manage(s, list(meas.lost_slam_trk_idxs))
+    t["manage"] = time.perf_counter() - t0
+    quats, poss = upd.sm.camera_attitudes(s), upd.sm.camera_positions(s)
+    t0 = time.perf_counter()
+    ms = MsckfUpdate(meas.msckf_trks[:ks], quats, poss, s.cov, M, sigma_img)
+    t["msckf"] = (time.perf_counter() - t0) * K / ks
+    t0 = time.perf_counter()
+    mss = MsckfSlamUpdate(meas.new_msckf_slam_trks, quats, poss, s.cov, M, sigma_img)
+    sl = SlamUpdate(meas.slam_trks, quats, poss, s.f_array, upd.sm.anchor_idxs, s.cov, M, sigma_img)
+    t["slam"] = time.perf_counter() - t0
+    h = np.vstack([ms.jac, mss.jac, sl.jac])
+    res = np.concatenate([ms.res, mss.res, sl.res])
+    rd = np.concatenate([ms.cov_m_diag, mss.cov_m_diag, sl.cov_m_diag])
+    t0 = time.perf_counter()
+    hq, rq, Rq = apply_qr_decomposition(h, res, rd, sigma_img)
+    rows_full = h.shape[0] + (K - ks) * (2 * M - 3)
+    t["qr"] = (time.perf_counter() - t0) * rows_full / max(h.shape[0], 1)
+    corr = np.zeros(s.n_error_states())
+    t0 = time.perf_counter()
+    apply_update(s, hq, rq, Rq, corr, True)
+    t["apply"] = time.perf_counter() - t0
+    # re-propagation of the 10 buffered IMU states (ekf.cpp:227-255)
+    prop = oracle.Propagator()
+    a, b = s.copy(), s.copy()
+    t0 = time.perf_counter()
+    for i in range(10):
+        b.set_imu(a.time + 0.005, 0, a.w_m, a.a_m)
+        prop.propagate_state(a, b)
+        prop.propagate_covariance(a, b)
+        a, b = b, a
+    t["repropagate"] = time.perf_counter() - t0
+    return sum(t.values()), {k: round(v, 4) for k, v in t.items()}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the fp64 CPU port of the reference (numpy + OpenBLAS, all host threads), rank 0 only."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.fspath(ROOT / "tests"))
+    from oracle_driver import OracleFilter
+    from x_multi_agent_b200.filter import State
+    from x_multi_agent_b200.synth import replay
+    scn, fill = build_scenario(seed=0)
+    ora = OracleFilter(CFG2["M"], CFG2["F"], n_slots=64)
+    replay(fill, ora)
+    ev = steady_events(scn, N_FILL, 1)
+    for (t, i, w, a) in ev[0][0]:
+        ora.process_imu(t, i, w, a)
+    meas = ev[0][1]
+    idx = ora.ekf.buf.closest_idx(meas.timestamp)
+    prior = State.from_oracle(ora.ekf.buf.states[idx])
+    smst = (ora.upd.sm.n_poses, ora.upd.sm.n_features, list(ora.upd.sm.anchor_idxs), ora.upd.sm.filled_before)
+    ks = 50  # bounded sample: 50 of the 800 MSCKF tracks per step, row-proportional stages extrapolated
+    times = []
+    for i in range(args.warmup + args.steps):
+        sec, detail = oracle_one_update(prior, smst, meas, scn.c.sigma_img, k_sample=ks)
+        if i >= args.warmup:
+            times.append(sec)
+    sec = float(np.mean(times))
+    val = 1.0 / sec
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"one cfg-2 update per step on {ks}/800 MSCKF tracks + all 200 SLAM rows at full N=795; "
+                                       "per-track and QR stages scaled linearly to 800 tracks (dense reference formulation, "
+                                       "numpy/OpenBLAS fp64)", "stages_s": detail},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("XB_DOWNDATE_PRECISION", "0")))
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from x_multi_agent_b200 import Filter, PackedMeasurement
+    from x_multi_agent_b200.synth import replay
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scn, fill = build_scenario(seed=rank)
+    flt = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank, downdate_precision=args.precision)
+    stream = torch.cuda.Stream()
+    flt.set_stream(stream.cuda_stream)
+    replay(fill, flt)
+    assert flt.n_poses == CFG2["M"] and flt.n_features == CFG2["F"], "warm-up did not reach steady state"
+    W, K = max(args.warmup, 3), args.steps
+    events = steady_events(scn, N_FILL, 2 * (W + K))
+    packed = [PackedMeasurement(m) for _, m in events]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def feed(i):
+        for (t, seq, w, a) in events[i][0]:
+            flt.process_imu(t, seq, w, a, want_state=False)
+
+    # ---- phase A: device-timed throughput, inputs resident in HBM ------------------------------------------
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+    sampler = ClockSampler(local_rank)
+    launches0 = 0
+    barrier()
+    for i in range(W + K):
+        if i == W:
+            barrier()
+            flt.profile(True)
+            launches0 = flt.kernel_launches()
+            sampler.start()
+        feed(i)
+        flt.set_measurement(packed[i])
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            ev0[i].record(stream)
+        flt.process_update_measurement(want_state=False)
+        ev1[i].record(stream)
+    barrier()
+    sampler.stop_flag = True
+    launches = flt.kernel_launches() - launches0
+    stage = flt.profile_read()
+    flt.profile(False)
+    dev_ms = sum(ev0[i].elapsed_time(ev1[i]) for i in range(W, W + K))
+    # ---- phase B: end to end through the C ABI with host buffers ---------------------------------------------
+    e2e_s = 0.0
+    barrier()
+    for j in range(W + K):
+        i = W + K + j
+        feed(i)
+        flt.synchronize()
+        t0 = time.perf_counter()
+        flt.set_measurement(packed[i])                      # host -> device: track lists
+        st = flt.process_update_measurement(want_state=True)  # device -> host: updated state (+ stream sync)
+        t1 = time.perf_counter()
+        if j >= W:
+            e2e_s += t1 - t0
+    barrier()
+    assert np.all(np.isfinite(st.x)), "non-finite state after the benchmark"
+    tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * K / (dev_ms_max * 1e-3)
+    e2e = world * K / (e2e_ms_max * 1e-3)
+    # ---- roofline of the dominant stage -------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    which_peak = "measured (MEASURED_PEAKS.json, burst copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    N, M, F = 795, 30, 200
+    m_rows = 6 * M + 2 * F
+    m_pad = (m_rows + 31) // 32 * 32
+    per_stage = {k: (v[0] / max(v[1], 1), v[1], v[0]) for k, v in stage.items() if v[1] > 0}
+    dom = max(per_stage, key=lambda k: per_stage[k][2])
+    # algorithmic bytes per launch (fp64): see DESIGN.md "kernels and rooflines"
+    alg_bytes = {
+        "tallchol": 8 * ((m_pad * (m_pad + 1)) // 2 + (N + 22) * m_pad) * 2,      # read + write S(lower), A1, aux rows
+        "downdate": 8 * (2 * N * N + N * m_pad),                                     # read+write P, read W
+        "manage": 8 * 2 * N * N,
+        "assemble": 8 * 2 * N * N,
+        "tracks": 8 * (CFG2["K"] * M * 2 + 7 * M + (6 * M) ** 2 + CFG2["K"] * (3 * (6 * M + 1) + 14 * M)),
+        "build_s_pht": 8 * (N * 6 * M + N * m_pad + m_pad * m_pad),
+    }
+    ab = alg_bytes.get(dom)
+    avg_ms = per_stage[dom][0]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": (ab / (avg_ms * 1e-3) / 1e9) if ab else None, "peak": hbm_peak,
+                "unit": "GB/s", "frac": (ab / (avg_ms * 1e-3) / 1e9 / hbm_peak) if ab else None, "traffic": None,
+                "avg_launch_ms": avg_ms, "algorithmic_bytes": ab, "peak_source": which_peak,
+                "note": "N=795 keeps P (5 MB) L2-resident; this path is latency-bound (serial Cholesky chain), see DESIGN.md"}
+    stages_ms = {k: round(v[0], 4) for k, v in sorted(per_stage.items(), key=lambda kv: -kv[1][2])}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        # bounded sample of the same workload on the host cores: the fp64 port of the reference's dense formulation
+        slot = (flt.newest_slot() - scn.c.latency_imu) % 250
+        more = steady_events(scn, N_FILL + 2 * (W + K), 1)
+        for (t, seq, w, a) in more[0][0]:
+            flt.process_imu(t, seq, w, a, want_state=False)
+        slot = (flt.newest_slot() - scn.c.latency_imu) % 250
+        prior = flt.get_state(slot)
+        prior.cov = flt.get_covariance(slot)
+        smst = (flt.n_poses, flt.n_features, list(flt.anchor_idxs), True)
+        sec, detail = oracle_one_update(prior, smst, more[0][1], scn.c.sigma_img, k_sample=100)
+        cpu_baseline = {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": "one cfg-2 update from the device's own prior: 100/800 MSCKF tracks + 200 SLAM rows at N=795, "
+                                  "per-track and QR stages scaled linearly to 800 tracks (numpy/OpenBLAS fp64 port of the dense "
+                                  "reference formulation)", "stages_s": detail}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == 0 else "f64 state, 3xTF32 tensor-core downdate", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms_max / K,
+                    "h2d_bytes_per_step": int(np.mean([p.h2d_bytes for p in packed])) + 4 * (795 + 16 * 6 + 2 * 200),
+                    "d2h_bytes_per_step": flt.LX * 8},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": sampler.summary(), "stage_ms_per_update": stages_ms}
+    print(json.dumps(line))
+    flt.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

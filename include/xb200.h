@@ -204,6 +204,9 @@ XB_API int xb_ci_pack(xb_filter* f, int slot, double* dev_payload);     /* devic
 /* ---- introspection for tests / profiling ------------------------------------------------------ */
 XB_API int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles); /* returns count */
 XB_API int xb_debug_read_int(xb_filter* f, const char* name, int* out, int max_ints);
+/* per-stage CUDA-event timers on the filter's stream (bench.py roofline line); names/ms/counts hold 16 entries */
+XB_API int xb_profile_enable(xb_filter* f, int on);
+XB_API int xb_profile_read(xb_filter* f, const char** names, double* ms, long long* counts, int reset);
 XB_API long long xb_kernel_launches(const xb_filter* f);                /* kernels launched so far */
 XB_API double xb_chi2_quantile(double p, double dof);                   /* boost::math::quantile(chi_squared) */
 

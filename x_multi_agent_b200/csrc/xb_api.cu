@@ -94,8 +94,20 @@ struct ListDev {
   std::vector<int> h_off;
 };
 
+enum { ST_ASSEMBLE, ST_MANAGE, ST_TRACKS, ST_GRAM, ST_CHOLG, ST_SLAMROWS, ST_BUILD, ST_TALLCHOL, ST_CORRECT, ST_DOWNDATE,
+       ST_POST, ST_STORE, ST_PROPAGATE, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"assemble", "manage", "tracks", "gram", "chol_gram", "slam_rows", "build_s_pht",
+                                            "tallchol", "correct", "downdate", "post_update", "store", "propagate"};
+struct ProfSpan { int stage; cudaEvent_t e0, e1; };
+
 struct xb_filter {
   xb_config cfg;
+  // optional per-stage CUDA-event timers (xb_profile_enable / xb_profile_read)
+  bool prof = false;
+  std::vector<ProfSpan> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  double stage_ms[ST_COUNT] = {0};
+  long long stage_n[ST_COUNT] = {0};
   int M, F, N, LX, NS, NG;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -163,6 +175,46 @@ struct xb_filter {
   int omega_slot = -2;
   std::vector<void*> allocs;
 };
+
+static cudaEvent_t prof_event(xb_filter* f) {
+  cudaEvent_t e;
+  if (!f->ev_pool.empty()) { e = f->ev_pool.back(); f->ev_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+struct StageTimer {  // RAII: records a CUDA event pair around a stage on the filter's stream when profiling is on
+  xb_filter* f; int idx = -1;
+  StageTimer(xb_filter* f_, int stage) : f(f_) {
+    if (!f->prof) return;
+    ProfSpan sp{stage, prof_event(f), prof_event(f)};
+    cudaEventRecord(sp.e0, f->stream);
+    f->spans.push_back(sp);
+    idx = (int)f->spans.size() - 1;
+  }
+  ~StageTimer() { if (idx >= 0) cudaEventRecord(f->spans[idx].e1, f->stream); }
+};
+extern "C" int xb_profile_enable(xb_filter* f, int on) {
+  f->prof = on != 0;
+  return XB_OK;
+}
+// Accumulated device time per stage since the last reset. names: ST_COUNT pointers (may be NULL). Returns stage count.
+extern "C" int xb_profile_read(xb_filter* f, const char** names, double* ms, long long* counts, int reset) {
+  cudaStreamSynchronize(f->stream);
+  for (auto& sp : f->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) { f->stage_ms[sp.stage] += t; f->stage_n[sp.stage] += 1; }
+    f->ev_pool.push_back(sp.e0);
+    f->ev_pool.push_back(sp.e1);
+  }
+  f->spans.clear();
+  for (int i = 0; i < ST_COUNT; ++i) {
+    if (names) names[i] = kStageNames[i];
+    if (ms) ms[i] = f->stage_ms[i];
+    if (counts) counts[i] = f->stage_n[i];
+    if (reset) { f->stage_ms[i] = 0; f->stage_n[i] = 0; }
+  }
+  return ST_COUNT;
+}
 
 static int dalloc(xb_filter* f, void** p, size_t bytes) {
   if (bytes == 0) bytes = 8;
@@ -592,6 +644,7 @@ extern "C" int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m) {
 // ---- work state ---------------------------------------------------------------------------------------------------
 extern "C" int xb_work_load(xb_filter* f, int slot) {
   if (slot < 0 || slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid state");
+  StageTimer st_(f, ST_ASSEMBLE);
   CK(cudaMemcpyAsync(f->d_xw, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
   launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
                   f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_WA);
@@ -607,6 +660,7 @@ static double* claim_generation(xb_filter* f) {
 }
 extern "C" int xb_work_store(xb_filter* f, int slot) {
   if (slot < 0 || slot >= f->NS) return fail(XB_E_INVALID, "bad slot");
+  StageTimer st_(f, ST_STORE);
   const size_t nn = (size_t)f->N * f->N;
   bool in_gen = f->d_Pw >= f->d_Pgen && f->d_Pw < f->d_Pgen + (size_t)f->NG * nn;
   if (!in_gen) {
@@ -649,6 +703,7 @@ extern "C" int xb_work_get(xb_filter* f, double* xvec_out, double* cov_out, int 
 extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
   const int M = f->M, F = f->F, N = f->N;
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  StageTimer st_(f, ST_MANAGE);
   int* ip = f->h_ipin;
   int* rowmap = ip;                       // N
   int* ccols = rowmap + N;                // 15 * n_comp
@@ -790,8 +845,11 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   if (f->n_poses < 1) return fail(XB_E_INVALID, "empty pose window");
   const size_t gbytes = sizeof(double) * (size_t)f->grows_pad * f->gcols_pad;
   if (n0 + n1 > 0) {
-    if (n0 > 0 && launch_tracks(f->stream, track_params(f, l0, 0))) return fail(XB_E_CAPACITY, "track kernel shared memory");
-    if (n1 > 0 && launch_tracks(f->stream, track_params(f, f->l_newms, 1))) return fail(XB_E_CAPACITY, "track kernel shared memory");
+    {
+      StageTimer st_(f, ST_TRACKS);
+      if (n0 > 0 && launch_tracks(f->stream, track_params(f, l0, 0))) return fail(XB_E_CAPACITY, "track kernel shared memory");
+      if (n1 > 0 && launch_tracks(f->stream, track_params(f, f->l_newms, 1))) return fail(XB_E_CAPACITY, "track kernel shared memory");
+    }
     GramParams gp{};
     gp.M = M; gp.n_poses = f->n_poses;
     gp.B = f->d_B0; gp.rowsB = 3 * n0; gp.nzB = f->nz; gp.partB = f->d_partB;
@@ -799,7 +857,8 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     gp.off = l0.d_off; gp.inlier = f->d_inl0; gp.n_tracks_msckf = n0; gp.Jout = f->d_J0;
     gp.blocks = f->d_blocks;
     gp.T = f->d_Tg; gp.ld = f->gcols_pad; gp.rows_pad = f->grows_pad; gp.cols_pad = f->gcols_pad;
-    launch_gram(f->stream, gp);
+    { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp); }
+    StageTimer st_(f, ST_CHOLG);
     tallchol(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, f->d_flags, f->d_err, 1e-14);
     transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
   } else {
@@ -807,6 +866,7 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     CK(cudaMemsetAsync(f->d_Rg, 0, sizeof(double) * (size_t)f->gcols_pad * f->gcols_pad, f->stream));
   }
   if (ns > 0) {
+    StageTimer st_(f, ST_SLAMROWS);
     CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * f->F, cudaMemcpyHostToDevice, f->stream));
     SlamParams sp{};
     sp.xv = f->d_xw; sp.M = M; sp.N = f->N; sp.n_poses = f->n_poses; sp.P = f->d_Pw;
@@ -849,10 +909,14 @@ static int set_omega(xb_filter* f) {
 
 static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total) {
   const int N = f->N;
-  tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0);
-  launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
-                 f->d_Yb, f->d_xw, corr_total, f->d_delta);
+  { StageTimer st_(f, ST_TALLCHOL); tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0); }
+  {
+    StageTimer st_(f, ST_CORRECT);
+    launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
+                   f->d_Yb, f->d_xw, corr_total, f->d_delta);
+  }
   if (cov_update) {
+    StageTimer st_(f, ST_DOWNDATE);
     if (f->cfg.downdate_precision == 1)
       downdate_tc(f->stream, f->d_Pw, N, f->d_T, m_pad, n_pad, f->d_omega_inv, f->d_tileflag, f->d_Zb, f->d_Yb, f->d_tcws);
     else
@@ -873,12 +937,15 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   const size_t tb = sizeof(double) * (size_t)(d.m_pad + d.n_pad + 96) * d.m_pad;
   int rc0 = set_omega(f);
   if (rc0) return rc0;
+  {
+  StageTimer st_(f, ST_BUILD);
   CK(cudaMemsetAsync(f->d_T, 0, tb, f->stream));
   const double* zg = f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad;
   launch_build_pht(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_T);
   launch_build_s(f->stream, d, f->d_Rg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, f->d_corr,
                  f->cfg.sigma_img * f->cfg.sigma_img, f->d_T);
   launch_omega_rows(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_omega, f->d_T);
+  }
   return apply_from_tall(f, d.m_pad, d.n_pad, cov_update, f->d_corr);
 }
 
@@ -970,6 +1037,7 @@ extern "C" int xb_updater_apply_ci(xb_filter* f, const double* H, const double* 
 extern "C" int xb_vio_post_update(xb_filter* f) {
   const int M = f->M, F = f->F, N = f->N;
   const double var = f->cfg.sigma_img * f->cfg.sigma_img;
+  StageTimer st_(f, ST_POST);
   if (f->l_newms.n > 0) {
     const int n_new = f->l_newms.n;
     if (f->n_features + n_new > F) return fail(XB_E_CAPACITY, "no free SLAM feature slot (state_manager.cpp:208)");
@@ -1024,6 +1092,7 @@ extern "C" int xb_propagate(xb_filter* f, int slot_from, int slot_to) {
 static int repropagate_from(xb_filter* f, int idx) {  // ekf.cpp:227-255
   int n = 0;
   for (int c = idx; c != f->tail; c = next_idx(f, c)) ++n;
+  StageTimer st_(f, ST_PROPAGATE);
   ImuSample none{};
   propagate_chain(f, idx, n, none);
   for (int c = idx, k = 0; k < n; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; }

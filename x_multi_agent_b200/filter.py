@@ -269,5 +269,16 @@ class Filter:
         n = L.check(self.lib.xb_debug_read_int(self.h, name.encode(), L.iptr(out), int(count)))
         return out[:n]
 
+    def profile(self, on=True):
+        L.check(self.lib.xb_profile_enable(self.h, int(on)))
+
+    def profile_read(self, reset=True):
+        """{stage: (total_ms, count)} accumulated by the per-stage CUDA-event timers."""
+        names = (C.c_char_p * 16)()
+        ms = np.zeros(16)
+        cnt = (C.c_longlong * 16)()
+        n = L.check(self.lib.xb_profile_read(self.h, names, L.dptr(ms), cnt, int(reset)))
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     def kernel_launches(self):
         return int(self.lib.xb_kernel_launches(self.h))

@@ -96,6 +96,8 @@ SIGNATURES = {
     "xb_ci_pack": (C.c_int, [_VP, C.c_int, _VP]),
     "xb_debug_read": (C.c_int, [_VP, C.c_char_p, c_double_p, C.c_int]),
     "xb_debug_read_int": (C.c_int, [_VP, C.c_char_p, c_int_p, C.c_int]),
+    "xb_profile_enable": (C.c_int, [_VP, C.c_int]),
+    "xb_profile_read": (C.c_int, [_VP, C.POINTER(C.c_char_p), c_double_p, C.POINTER(C.c_longlong), C.c_int]),
     "xb_kernel_launches": (C.c_longlong, [_VP]),
     "xb_chi2_quantile": (C.c_double, [C.c_double, C.c_double]),
 }

@@ -97,6 +97,7 @@ class Scenario:
         self.feat_lm = []           # landmark id per active SLAM feature slot
         self.feat_obs = []          # observation history per active SLAM feature
         self.imu_seq = 0
+        self._cam_cache = {}
 
     # ---- truth ---------------------------------------------------------------------------------------
     def pose(self, t):
@@ -119,8 +120,13 @@ class Scenario:
         return p, R, v, a, w
 
     def cam_pose(self, t):
-        p, R, *_ = self.pose(t)
-        return p + R @ self.p_ic, R @ self.R_ic
+        key = round(t * 1e9)
+        hit = self._cam_cache.get(key)
+        if hit is None:
+            p, R, *_ = self.pose(t)
+            hit = (p + R @ self.p_ic, R @ self.R_ic)
+            self._cam_cache[key] = hit
+        return hit
 
     def frame_time(self, k):
         return k / self.c.cam_rate
@@ -190,13 +196,17 @@ class Scenario:
 
     def _tracks(self, frames, n, outliers=True):
         lms = self._sample_visible(frames, n)
-        trks = []
-        for lm in lms:
-            z = self._project(lm, frames)
-            if outliers and self.rng.uniform() < self.c.outlier_frac:
-                z[self.rng.integers(len(frames))] = self.rng.uniform(-0.8, 0.8, 2)
-            trks.append(z)
-        return trks
+        Z = np.empty((n, len(frames), 2))
+        for i, k in enumerate(frames):
+            pc, Rc = self.cam_pose(self.frame_time(k))
+            x = (lms - pc) @ Rc
+            Z[:, i, :] = x[:, :2] / x[:, 2:3]
+        Z += self.rng.normal(0, self.c.sigma_img, Z.shape)
+        if outliers:
+            bad = np.nonzero(self.rng.uniform(size=n) < self.c.outlier_frac)[0]
+            for j in bad:
+                Z[j, self.rng.integers(len(frames))] = self.rng.uniform(-0.8, 0.8, 2)
+        return [Z[j] for j in range(n)]
 
     def measurement(self, k):
         """Track lists for the update at camera frame k (the window then holds frames k-n+1..k)."""
