@@ -1,0 +1,23 @@
+"""Timeline of the dataflow tile Cholesky on one steady-state cfg-2 update (set XB_CHOL_TRACE=1)."""
+import os, sys
+os.environ["XB_CHOL_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+from x_multi_agent_b200 import Filter
+from x_multi_agent_b200.synth import replay
+
+scn, fill = bench.build_scenario(0)
+flt = Filter(30, 200, max_tracks=800, n_slots=250)
+replay(fill, flt)
+ev = bench.steady_events(scn, bench.N_FILL, 3)
+for imu, m in ev:
+    for (t, i, w, a) in imu:
+        flt.process_imu(t, i, w, a, want_state=False)
+    flt.set_measurement(m)
+    flt.process_update_measurement()
+tr = flt.debug("chol_trace", 6 * 19).reshape(-1, 6)
+t0 = tr[0, 2]
+print("critical-path CTA, per tile column (us since start): col_start  potrf_start  potrf_done  E_published")
+for r in tr:
+    print(f"{int(r[0]):3d} | {(r[2]-t0)/1e3:8.1f} {(r[3]-t0)/1e3:8.1f} {(r[4]-t0)/1e3:8.1f} {(r[5]-t0)/1e3:8.1f}")

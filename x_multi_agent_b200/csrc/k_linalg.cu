@@ -101,13 +101,23 @@ void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
 
 // ------------------------------------------------------------------------------------------------
 // Tall tile Cholesky (single launch, dataflow over 32x32 tiles).
-//   T is [rows_pad x ld] row-major with ct = cols_pad/32 tile columns and rt = rows_pad/32 tile rows.
+//   T is [rows_pad x ld] row-major with ct = cols_pad/32 tile columns and rt = rows_pad/32 > ct tile rows.
 //   The top ct x ct tiles hold a symmetric (semi-)definite matrix S (lower part is read); on exit the
 //   lower part holds L (S = L L^T, strictly-upper part of the diagonal tiles zeroed) and every tile row
 //   below holds X L^-T for the rows X stored there (TRSM), e.g. W = (P H^T) L^-T and z^T = r^T L^-T.
-//   One CTA per tile in column-major tile order; tile (i,j) accumulates  T(i,j) - sum_{k<j} T(i,k) T(j,k)^T
-//   as soon as the producers publish their flags, then factors (i==j) or solves against L(j,j).
 //   Pivots <= piv_tol * (original diagonal) are treated as zero (column zeroed): semi-definite Gram input.
+//
+//   The factorisation of an m x m matrix has a serial chain of m pivots; everything here is organised around
+//   that chain (measured on B200: a 32x32 fp64 potrf by one warp = 8.1k cycles warm, 22-45k cycles with a
+//   cold instruction cache, tools/bench_potrf.cu):
+//     block 0 ("critical-path CTA") is persistent and walks the diagonal: for column j it owns tiles
+//       D=(j,j) and E=(j+1,j); it applies the last panel update from shared memory, factors D (one warp,
+//       rows in registers, left-looking), solves E against it, and publishes both -- consecutive columns
+//       hand over through shared memory, not through L2, and its code stays hot in the instruction cache;
+//     blocks 1.. ("workers", persistent, round-robin over a dependency-ordered task list) do everything
+//       with slack: the TRSM tiles (i,j), i >= j+2 (left-looking accumulation, then solve against L(j,j)),
+//       and the partial sums of D/E over the panels k <= j-2 ("pre" tasks).
+//   Tiles are handed over through global memory + release/acquire flags; all tile reads bypass L1 (ld.cg).
 // ------------------------------------------------------------------------------------------------
 #define TC 32
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -115,135 +125,316 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-__device__ __forceinline__ bool tc_wait(const int* flag, int* err) {
-  if (threadIdx.x == 0) {
-    long long spins = 0;
-    while (ld_acquire(flag) == 0) {
-      __nanosleep(20);
-      if (++spins > (1ll << 26)) { atomicExch(err, 1); break; }
-    }
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// one thread polls (relaxed), then a single acquire orders the tile reads that follow
+__device__ __forceinline__ void flag_spin(const int* flag, int* err) {
+  long long spins = 0;
+  while (ld_relaxed(flag) == 0) {
+    if (++spins > (1ll << 22)) { atomicExch(err, 1); break; }
   }
-  __syncthreads();
-  return true;
+  (void)ld_acquire(flag);
 }
 
-__global__ void __launch_bounds__(64) k_tallchol(double* __restrict__ T, int ld, int rt, int ct, int* __restrict__ flags,
-                                                 int* __restrict__ err, double piv_tol) {
-  // map block index -> tile (i, j), column-major over the trapezoid
-  int b = blockIdx.x;
-  int j = 0;
-  {
-    int rem = b;
-    while (rem >= rt - j) { rem -= rt - j; ++j; }
-    b = rem;
-  }
-  const int i = j + b;
-  const int t = threadIdx.x;
-  const int ty = t >> 3, tx = t & 7;  // 8x8 threads, 4x4 each
-
-  __shared__ double As[TC][TC + 1];
-  __shared__ double Bs[TC][TC + 1];
-  __shared__ double Cs[TC][TC + 1];
-  __shared__ double dorig[TC];
-
-  double acc[4][4];
-  const double* Tij = T + (size_t)i * TC * ld + (size_t)j * TC;
+// 32x32 lower Cholesky by one warp: lane r keeps row r in registers, finished rows of L are mirrored in
+// shared memory (Ls) and read back as broadcasts (left-looking).  Cs: in = tile, out = L (upper part zero).
+__device__ __forceinline__ void warp_potrf32(double (*Cs)[TC + 1], double (*Ls)[TC + 1], const double* dorig,
+                                             double piv_tol, int lane) {
+  double a[TC];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int k = 0; k < TC; ++k) a[k] = Cs[lane][k];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = __ldcg(&Tij[(size_t)(ty * 4 + a) * ld + tx * 4 + c]);
-  if (i == j && t < TC) dorig[t] = __ldcg(&Tij[(size_t)t * ld + t]);
-
-  for (int k = 0; k < j; ++k) {
-    tc_wait(&flags[i * ct + k], err);
-    if (i != j) tc_wait(&flags[j * ct + k], err);
-    const double* Aik = T + (size_t)i * TC * ld + (size_t)k * TC;
-    const double* Bjk = T + (size_t)j * TC * ld + (size_t)k * TC;
-    for (int e = t; e < TC * TC; e += 64) {
-      const int r = e >> 5, c = e & 31;
-      As[c][r] = __ldcg(&Aik[(size_t)r * ld + c]);  // stored k-major
-      Bs[c][r] = (i == j) ? As[c][r] : __ldcg(&Bjk[(size_t)r * ld + c]);
+  for (int c = 0; c < TC; ++c) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < c; ++k) {
+      const double lc = Ls[c][k];
+      if ((k & 3) == 0) s0 = fma(a[k], lc, s0);
+      else if ((k & 3) == 1) s1 = fma(a[k], lc, s1);
+      else if ((k & 3) == 2) s2 = fma(a[k], lc, s2);
+      else s3 = fma(a[k], lc, s3);
     }
-    __syncthreads();
+    const double v = a[c] - ((s0 + s1) + (s2 + s3));
+    const double piv = __shfl_sync(0xffffffffu, v, c);
+    const bool ok = piv > piv_tol * fabs(dorig[c]) && piv > 0.0;
+    const double rs = ok ? rsqrt(piv) : 0.0;
+    double l = 0.0;
+    if (lane == c) l = piv * rs;
+    else if (lane > c) l = v * rs;
+    a[c] = l;
+    Ls[lane][c] = l;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int k = 0; k < TC; ++k) Cs[lane][k] = a[k];
+}
+// X L^T = C for the 32 rows of C (lane = row, registers), L and its reciprocal diagonal in shared memory.
+__device__ __forceinline__ void warp_trsm32(double (*Cs)[TC + 1], double (*Ls)[TC + 1], const double* rd, int lane) {
+  double a[TC];
+#pragma unroll
+  for (int k = 0; k < TC; ++k) a[k] = Cs[lane][k];
+#pragma unroll
+  for (int c = 0; c < TC; ++c) {
+    const double x = a[c] * rd[c];
+    a[c] = x;
+#pragma unroll
+    for (int k = c + 1; k < TC; ++k) a[k] = fma(-x, Ls[k][c], a[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < TC; ++k) Cs[lane][k] = a[k];
+}
+// C(32x32, smem) -= A(32x32) * B(32x32)^T with A, B stored k-major (At[k][r], Bt[k][c]); nthreads >= 64
+__device__ __forceinline__ void tile_gemm_sub(double (*Cs)[TC + 1], double (*At)[TC + 1], double (*Bt)[TC + 1], int t,
+                                              int nthreads) {
+  for (int e = t; e < 64; e += nthreads) {  // 64 micro-tiles of 4x4
+    const int ty = e >> 3, tx = e & 7;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = Cs[ty * 4 + u][tx * 4 + v];
 #pragma unroll 8
     for (int kk = 0; kk < TC; ++kk) {
-      double a[4], bb[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = As[kk][ty * 4 + u];
+      for (int u = 0; u < 4; ++u) a[u] = At[kk][ty * 4 + u];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) bb[u] = Bs[kk][tx * 4 + u];
+      for (int u = 0; u < 4; ++u) b[u] = Bt[kk][tx * 4 + u];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(-a[u], bb[v], acc[u][v]);
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(-a[u], b[v], acc[u][v]);
     }
-    __syncthreads();
-  }
-
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) Cs[ty * 4 + a][tx * 4 + c] = acc[a][c];
-  __syncthreads();
-
-  double* Tw = T + (size_t)i * TC * ld + (size_t)j * TC;
-  if (i == j) {
-    // in-place lower Cholesky of Cs
-    for (int c = 0; c < TC; ++c) {
-      const double piv = Cs[c][c];
-      const bool ok = piv > piv_tol * fabs(dorig[c]) && piv > 0.0;
-      const double d = ok ? sqrt(piv) : 0.0;
-      __syncthreads();
-      if (t < TC) {
-        if (t == c) Cs[c][c] = d;
-        else if (t > c) Cs[t][c] = ok ? Cs[t][c] / d : 0.0;
-        else Cs[t][c] = 0.0;  // strictly upper part
-      }
-      __syncthreads();
-      for (int e = t; e < TC * TC; e += 64) {
-        const int r = e >> 5, k2 = e & 31;
-        if (k2 > c && k2 <= r) Cs[r][k2] = fma(-Cs[r][c], Cs[k2][c], Cs[r][k2]);
-      }
-      __syncthreads();
-    }
-  } else {
-    // X L^T = C  (L = L(j,j)), column by column
-    tc_wait(&flags[j * ct + j], err);
-    const double* Ljj = T + (size_t)j * TC * ld + (size_t)j * TC;
-    for (int e = t; e < TC * TC; e += 64) {
-      const int r = e >> 5, c = e & 31;
-      Bs[r][c] = __ldcg(&Ljj[(size_t)r * ld + c]);
-    }
-    __syncthreads();
-    for (int c = 0; c < TC; ++c) {
-      const double d = Bs[c][c];
-      if (t < TC) Cs[t][c] = (d != 0.0) ? Cs[t][c] / d : 0.0;
-      __syncthreads();
-      for (int e = t; e < TC * TC; e += 64) {
-        const int r = e >> 5, k2 = e & 31;
-        if (k2 > c) Cs[r][k2] = fma(-Cs[r][c], Bs[k2][c], Cs[r][k2]);
-      }
-      __syncthreads();
-    }
+      for (int v = 0; v < 4; ++v) Cs[ty * 4 + u][tx * 4 + v] = acc[u][v];
   }
-  for (int e = t; e < TC * TC; e += 64) {
+}
+__device__ __forceinline__ void tile_load(double (*S)[TC + 1], const double* g, int ld, int t, int nthreads, bool transpose) {
+  for (int e = t; e < TC * TC; e += nthreads) {
     const int r = e >> 5, c = e & 31;
-    Tw[(size_t)r * ld + c] = Cs[r][c];
+    const double v = __ldcg(&g[(size_t)r * ld + c]);
+    if (transpose) S[c][r] = v; else S[r][c] = v;
   }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) st_release(&flags[i * ct + j], 1);
+}
+__device__ __forceinline__ void tile_store(double* g, int ld, double (*S)[TC + 1], int t, int nthreads) {
+  for (int e = t; e < TC * TC; e += nthreads) {
+    const int r = e >> 5, c = e & 31;
+    __stcg(&g[(size_t)r * ld + c], S[r][c]);
+  }
 }
 
-void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol) {
+#define CP_THREADS 128
+// flags: ready[i*ct + j] (L tile published), pre[rt*ct + j] (partial sums of D_j/E_j over k <= j-2 published)
+__global__ void __launch_bounds__(CP_THREADS) k_tallchol(double* __restrict__ T, int ld, int rt, int ct, int* __restrict__ flags,
+                                                         int* __restrict__ err, double piv_tol, const double* __restrict__ diag0,
+                                                         long long* __restrict__ trace) {
+  __shared__ double Ds[TC][TC + 1], Es[2][TC][TC + 1], Ws[TC][TC + 1], Ls[TC][TC + 1];
+  __shared__ double dorig[TC], rd[TC];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int* ready = flags;
+  int* pre = flags + (size_t)rt * ct;
+
+  if (blockIdx.x == 0) {
+    // ------------------------------------------------------------------ critical-path CTA
+    int eb = 0;  // Es[eb^1] holds L(j, j-1)^T-major copy from the previous column
+    for (int j = 0; j < ct; ++j) {
+      const long long tr0 = trace ? gtimer() : 0;
+      if (j >= 2) {
+        if (t == 0) flag_spin(&pre[j], err);
+        __syncthreads();
+      }
+      double* gD = T + (size_t)j * TC * ld + (size_t)j * TC;
+      double* gE = T + (size_t)(j + 1) * TC * ld + (size_t)j * TC;
+      tile_load(Ds, gD, ld, t, CP_THREADS, false);
+      tile_load(Es[eb], gE, ld, t, CP_THREADS, false);
+      __syncthreads();
+      if (t < TC) dorig[t] = diag0 ? diag0[j * TC + t] : 0.0;
+      __syncthreads();
+      // previous column's E (= L(j, j-1)) is in Es[eb^1] row-major; k-major copy into Ws for the rank-32 updates
+      if (j >= 1) {
+        for (int e = t; e < TC * TC; e += CP_THREADS) { const int r = e >> 5, c = e & 31; Ws[c][r] = Es[eb ^ 1][r][c]; }
+        __syncthreads();
+        tile_gemm_sub(Ds, Ws, Ws, t, CP_THREADS);  // D -= L(j,j-1) L(j,j-1)^T
+        __syncthreads();
+      }
+      const long long tr1 = trace ? gtimer() : 0;
+      if (warp == 0) {
+        warp_potrf32(Ds, Ls, dorig, piv_tol, lane);
+        const double d = Ds[lane][lane];
+        rd[lane] = d != 0.0 ? 1.0 / d : 0.0;
+      } else if (j >= 1) {
+        // meanwhile: E -= L(j+1, j-1) L(j, j-1)^T   (L(j+1,j-1) comes from a worker)
+        if (t == 32) flag_spin(&ready[(j + 1) * ct + (j - 1)], err);
+        asm volatile("bar.sync 1, 96;" ::: "memory");
+        // k-major copy of L(j+1,j-1) into Ls is not possible (warp 0 uses Ls): accumulate straight from global
+        const double* gW = T + (size_t)(j + 1) * TC * ld + (size_t)(j - 1) * TC;
+        for (int e = t - 32; e < 64; e += 96) {
+          const int ty = e >> 3, tx = e & 7;
+          double acc[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = Es[eb][ty * 4 + u][tx * 4 + v];
+          for (int kk = 0; kk < TC; kk += 4) {
+            double a[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) a[u][q] = __ldcg(&gW[(size_t)(ty * 4 + u) * ld + kk + q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(-a[u][q], Ws[kk + q][tx * 4 + v], acc[u][v]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) Es[eb][ty * 4 + u][tx * 4 + v] = acc[u][v];
+        }
+      }
+      __syncthreads();
+      const long long tr2 = trace ? gtimer() : 0;
+      // publish L(j,j) (warps 1-3) while warp 0 solves E against it
+      if (warp == 0) {
+        warp_trsm32(Es[eb], Ds, rd, lane);
+      } else {
+        tile_store(gD, ld, Ds, t - 32, 96);
+        asm volatile("bar.sync 1, 96;" ::: "memory");
+        if (t == 32) { __threadfence(); st_release(&ready[j * ct + j], 1); }
+      }
+      __syncthreads();
+      tile_store(gE, ld, Es[eb], t, CP_THREADS);
+      __syncthreads();
+      if (t == 0) {
+        __threadfence();
+        st_release(&ready[(j + 1) * ct + j], 1);
+        if (trace) {
+          long long* o = trace + 6 * (size_t)j;
+          o[0] = j; o[1] = j; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
+        }
+      }
+      eb ^= 1;
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- workers
+  // task list, dependency-ordered:  for j = 0..ct-1:  [pre(j+2) if j+2 < ct]... see task_decode
+  const int nworkers = gridDim.x - 1;
+  // tasks per column j: TRSM tiles i = j+2..rt-1  (rt-j-2 of them), preceded by pre(j+1) when 2 <= j+1 < ct
+  // (pre(j+1) needs only columns <= j-1, so it is scheduled before the TRSM tasks of column j)
+  int task = blockIdx.x - 1;
+  int jcol = 0, base = 0;
+  while (true) {
+    // advance (jcol, base) so that task falls into column jcol's segment
+    int seg;
+    for (;;) {
+      if (jcol >= ct) return;
+      const int has_pre = (jcol + 1 >= 2 && jcol + 1 < ct) ? 1 : 0;
+      seg = has_pre + (rt - jcol - 2);
+      if (task < base + seg) break;
+      base += seg;
+      ++jcol;
+    }
+    const int has_pre = (jcol + 1 >= 2 && jcol + 1 < ct) ? 1 : 0;
+    const int local = task - base;
+    const int ty = (t & 63) >> 3, tx = t & 7;
+    if (has_pre && local == 0) {
+      // ---- pre(jp): D_jp -= sum_{k<=jp-2} L(jp,k) L(jp,k)^T ; E_jp -= sum L(jp+1,k) L(jp,k)^T ; in place
+      const int jp = jcol + 1;
+      double* gD = T + (size_t)jp * TC * ld + (size_t)jp * TC;
+      double* gE = T + (size_t)(jp + 1) * TC * ld + (size_t)jp * TC;
+      tile_load(Ds, gD, ld, t, CP_THREADS, false);
+      tile_load(Es[0], gE, ld, t, CP_THREADS, false);
+      __syncthreads();
+      for (int k = 0; k <= jp - 2; ++k) {
+        if (t == 0) { flag_spin(&ready[jp * ct + k], err); flag_spin(&ready[(jp + 1) * ct + k], err); }
+        __syncthreads();
+        tile_load(Ws, T + (size_t)jp * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);          // L(jp,k) k-major
+        tile_load(Ls, T + (size_t)(jp + 1) * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);    // L(jp+1,k) k-major
+        __syncthreads();
+        if (t < 64) tile_gemm_sub(Ds, Ws, Ws, t, 64);
+        else tile_gemm_sub(Es[0], Ls, Ws, t - 64, 64);
+        __syncthreads();
+      }
+      tile_store(gD, ld, Ds, t, CP_THREADS);
+      tile_store(gE, ld, Es[0], t, CP_THREADS);
+      __syncthreads();
+      if (t == 0) { __threadfence(); st_release(&pre[jp], 1); }
+    } else {
+      // ---- TRSM tile (i, jcol), i >= jcol+2
+      const int i = jcol + 2 + (local - has_pre);
+      const long long tr0 = trace ? gtimer() : 0;
+      double* gC = T + (size_t)i * TC * ld + (size_t)jcol * TC;
+      tile_load(Ds, gC, ld, t, CP_THREADS, false);
+      __syncthreads();
+      for (int k = 0; k < jcol; ++k) {
+        if (t == 0) { flag_spin(&ready[i * ct + k], err); flag_spin(&ready[jcol * ct + k], err); }
+        __syncthreads();
+        tile_load(Ws, T + (size_t)i * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
+        tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
+        __syncthreads();
+        tile_gemm_sub(Ds, Ws, Ls, t, CP_THREADS);
+        __syncthreads();
+      }
+      const long long tr1 = trace ? gtimer() : 0;
+      if (t == 0) flag_spin(&ready[jcol * ct + jcol], err);
+      __syncthreads();
+      tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)jcol * TC, ld, t, CP_THREADS, false);
+      __syncthreads();
+      if (t < TC) { const double d = Ls[t][t]; rd[t] = d != 0.0 ? 1.0 / d : 0.0; }
+      __syncthreads();
+      if (warp == 0) warp_trsm32(Ds, Ls, rd, lane);
+      __syncthreads();
+      const long long tr2 = trace ? gtimer() : 0;
+      tile_store(gC, ld, Ds, t, CP_THREADS);
+      __syncthreads();
+      if (t == 0) {
+        __threadfence();
+        st_release(&ready[i * ct + jcol], 1);
+        if (trace && i < ct + 2) {
+          long long* o = trace + 6 * (size_t)(ct + jcol * 2 + (i - jcol - 2) % 2);
+          o[0] = i; o[1] = jcol; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
+        }
+      }
+      (void)ty; (void)tx;
+    }
+    __syncthreads();
+    task += nworkers;
+  }
+}
+
+void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
+              const double* diag0, long long* trace) {
   const int rt = rows_pad / TC, ct = cols_pad / TC;
-  const int ntiles = ct * (ct + 1) / 2 + (rt - ct) * ct;
-  cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)rt * ct, s);
-  k_tallchol<<<ntiles, 64, 0, s>>>(T, ld, rt, ct, flags, err, piv_tol);
+  int ntasks = 0;
+  for (int j = 0; j < ct; ++j) ntasks += ((j + 1 >= 2 && j + 1 < ct) ? 1 : 0) + (rt - j - 2);
+  static int max_workers = 0;
+  if (!max_workers) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tallchol, CP_THREADS, 0);
+    max_workers = sms * (per_sm > 0 ? per_sm : 1) - 1;  // all CTAs must be co-resident (persistent dataflow)
+  }
+  const int nworkers = ntasks < max_workers ? (ntasks > 0 ? ntasks : 1) : max_workers;
+  cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)rt * ct + ct + 1), s);
+  k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, flags, err, piv_tol, diag0, trace);
   count_launch();
 }
 

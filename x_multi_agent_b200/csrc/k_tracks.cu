@@ -21,9 +21,12 @@ namespace xb {
 __device__ void smallest_right_singular_vector4(double* A /*4x4 row-major, destroyed*/, double* v /*4*/) {
   double V[16];
   for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 30; ++sweep) {
+#pragma unroll 1
+  for (int sweep = 0; sweep < 12; ++sweep) {
     double off = 0.0;
+#pragma unroll 1
     for (int p = 0; p < 3; ++p)
+#pragma unroll 1
       for (int q = p + 1; q < 4; ++q) {
         double al = 0.0, be = 0.0, ga = 0.0;
         for (int i = 0; i < 4; ++i) {
@@ -31,7 +34,7 @@ __device__ void smallest_right_singular_vector4(double* A /*4x4 row-major, destr
           be += A[i * 4 + q] * A[i * 4 + q];
           ga += A[i * 4 + p] * A[i * 4 + q];
         }
-        const double lim = 1e-15 * sqrt(al * be);
+        const double lim = 1e-14 * sqrt(al * be);
         if (fabs(ga) <= lim || ga == 0.0) continue;
         off = fmax(off, fabs(ga) / fmax(sqrt(al * be), 1e-300));
         const double zeta = (be - al) / (2.0 * ga);
@@ -46,7 +49,7 @@ __device__ void smallest_right_singular_vector4(double* A /*4x4 row-major, destr
           V[i * 4 + q] = s * vp + c * vq;
         }
       }
-    if (off < 1e-15) break;
+    if (off == 0.0) break;  // no rotation was needed in this sweep
   }
   int best = 0;
   double bn = 1e300;
@@ -61,21 +64,23 @@ __device__ void smallest_right_singular_vector4(double* A /*4x4 row-major, destr
 __device__ __forceinline__ int tri_idx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
 
 // Per-warp shared-memory carve-up (doubles), Lm = max track length handled by the launch.
+// Y overlays Hf (Hf is dead once U and H2 exist); the anchor blocks exist only in MSCKF-SLAM mode.
 struct WarpSmem {
   double *Jp, *Ja, *Jap, *Jaa, *Hf, *U, *Y, *V, *res, *X;
-  __device__ WarpSmem(double* base, int Lm) {
+  __device__ WarpSmem(double* base, int Lm, int mode) {
     Jp = base; base += 6 * Lm;
     Ja = base; base += 6 * Lm;
-    Jap = base; base += 6 * Lm;
-    Jaa = base; base += 6 * Lm;
-    Hf = base; base += 6 * Lm;
+    Hf = base; Y = base; base += 6 * Lm;
     U = base; base += 6 * Lm;
-    Y = base; base += 6 * Lm;
     V = base; base += 6 * Lm;
     res = base; base += 2 * Lm;
+    Jap = base; Jaa = base;
+    if (mode == 1) { Jaa = base + 6 * Lm; base += 12 * Lm; }
     X = base;  // (2Lm+7)(2Lm+8)/2 packed lower triangle incl. 7 augmented rows (Pi r and the 6 clone columns)
   }
-  static __host__ __device__ size_t doubles(int Lm) { return (size_t)50 * Lm + (size_t)(2 * Lm + 7) * (2 * Lm + 8) / 2; }
+  static __host__ __device__ size_t doubles(int Lm, int mode) {
+    return (size_t)(mode == 1 ? 44 : 32) * Lm + (size_t)(2 * Lm + 7) * (2 * Lm + 8) / 2;
+  }
 };
 
 // dot of two length-n smem vectors with stride, over the warp
@@ -92,8 +97,8 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
   const int M = tp.M, np = tp.n_poses;
   double* Rk = smem;            // [M][9]  rot(q_k) (body -> global), normalised
   double* pk = Rk + 9 * M;      // [M][3]
-  double* wbase = pk + 3 * M + warp * WarpSmem::doubles(tp.Lmax);
-  WarpSmem ws(wbase, tp.Lmax);
+  double* wbase = pk + 3 * M + warp * WarpSmem::doubles(tp.Lmax, tp.mode);
+  WarpSmem ws(wbase, tp.Lmax, tp.mode);
 
   const double* parr = tp.xv + XV_ARR;
   const double* qarr = tp.xv + XV_ARR + 3 * M;
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       for (int r = 0; r < 2; ++r) t2[r] = (Jatt[r * 3] * u[0] + Jatt[r * 3 + 1] * u[1] + Jatt[r * 3 + 2] * u[2]) * (1.0 / uu);
       for (int r = 0; r < 2; ++r)
         for (int c = 0; c < 3; ++c) Jatt[r * 3 + c] -= t2[r] * u[c];
-      for (int e = 0; e < 6; ++e) { Jp[e] = Jpos[e]; Ja[e] = Jatt[e]; Jap[e] = 0.0; Jaa[e] = 0.0; Hf[e] = -Jpos[e]; }
+      for (int e = 0; e < 6; ++e) { Jp[e] = Jpos[e]; Ja[e] = Jatt[e]; Hf[e] = -Jpos[e]; }
     } else if (i == L - 1) {  // msckf_slam_update.cpp:133-143
       for (int e = 0; e < 6; ++e) { Jp[e] = 0.0; Ja[e] = 0.0; Jap[e] = 0.0; Jaa[e] = 0.0; Hf[e] = 0.0; }
       Hf[0] = 1.0;
@@ -473,20 +478,31 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       }
     }
     __syncwarp();
-    // Cholesky of the (R2+1)-row augmented lower triangle; last row becomes y = L^-1 (Pi r)
+    // Cholesky of the augmented lower triangle (rows R2..R2+6 are right-hand sides): the last rows become
+    // y = L^-1 (Pi r) and Vt = L^-1 V.  Lane-owned rows, 4-wide batches so that loads overlap the FMAs.
     bool spd = true;
+    const int Rend = R2 + 6;
     for (int c = 0; c < R2; ++c) {
       const double piv = ws.X[tri_idx(c, c)];
       if (!(piv > 0.0)) { spd = false; break; }
-      const double d = sqrt(piv);
+      const double rs = rsqrt(piv);
       __syncwarp();
-      for (int r = c + 1 + lane; r <= R2 + 6; r += 32) ws.X[tri_idx(r, c)] /= d;
+      for (int r = c + 1 + lane; r <= Rend; r += 32) ws.X[tri_idx(r, c)] *= rs;
       __syncwarp();
-      for (int r = c + 1 + lane; r <= R2 + 6; r += 32) {
+      for (int r = c + 1 + lane; r <= Rend; r += 32) {
         const double lrc = ws.X[tri_idx(r, c)];
         double* row = ws.X + tri_idx(r, 0);
         const int kend = (r < R2) ? r : R2 - 1;  // the augmented rows have no diagonal entries
-        for (int k = c + 1; k <= kend; ++k) row[k] = fma(-lrc, ws.X[tri_idx(k, c)], row[k]);
+        int k = c + 1;
+        int ck = tri_idx(k, c);  // index of X[k][c]; X[k+1][c] is k+1 further
+        for (; k + 3 <= kend; k += 4) {
+          const double l0 = ws.X[ck], l1 = ws.X[ck + k + 1], l2 = ws.X[ck + 2 * k + 3], l3 = ws.X[ck + 3 * k + 6];
+          double r0 = row[k], r1 = row[k + 1], r2 = row[k + 2], r3 = row[k + 3];
+          r0 = fma(-lrc, l0, r0); r1 = fma(-lrc, l1, r1); r2 = fma(-lrc, l2, r2); r3 = fma(-lrc, l3, r3);
+          row[k] = r0; row[k + 1] = r1; row[k + 2] = r2; row[k + 3] = r3;
+          ck += 4 * k + 10;
+        }
+        for (; k <= kend; ++k) { row[k] = fma(-lrc, ws.X[ck], row[k]); ck += k + 1; }
       }
       __syncwarp();
     }
@@ -521,6 +537,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
             }
             Am[a][b] = v;
           }
+#pragma unroll 1
         for (int c = 0; c < 6; ++c) {  // Gauss-Jordan, partial pivoting (all lanes redundantly)
           int best = c;
           for (int r = c + 1; r < 6; ++r)
@@ -595,16 +612,16 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     for (int e = lane; e < 3 * W; e += 32) Bt[e] = 0.0;
 }
 
-size_t tracks_smem_bytes(int M, int Lmax, int warps) {
-  return sizeof(double) * ((size_t)12 * M + (size_t)warps * WarpSmem::doubles(Lmax));
+size_t tracks_smem_bytes(int M, int Lmax, int warps, int mode) {
+  return sizeof(double) * ((size_t)12 * M + (size_t)warps * WarpSmem::doubles(Lmax, mode));
 }
 
 int launch_tracks(cudaStream_t s, const TrackParams& tp) {
   if (tp.n_tracks <= 0) return 0;
   int warps = 4;
-  const size_t cap = 220 * 1024;
-  while (warps > 1 && tracks_smem_bytes(tp.M, tp.Lmax, warps) > cap) --warps;
-  const size_t bytes = tracks_smem_bytes(tp.M, tp.Lmax, warps);
+  const size_t cap = 110 * 1024;  // two CTAs per SM
+  while (warps > 1 && tracks_smem_bytes(tp.M, tp.Lmax, warps, tp.mode) > cap) --warps;
+  const size_t bytes = tracks_smem_bytes(tp.M, tp.Lmax, warps, tp.mode);
   if (bytes > cap) return -1;
   const int grid = (tp.n_tracks + warps - 1) / warps;
   if (tp.Lmax <= 32) {
@@ -819,7 +836,7 @@ __global__ void __launch_bounds__(128) k_gram_jtj(const int* __restrict__ off, c
 
 __global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const double* __restrict__ partD, int nzD,
                               const double* __restrict__ blocks, int M, int n_poses, double* __restrict__ T, int ld,
-                              int rows_pad, int cols_pad) {
+                              int rows_pad, int cols_pad, double* __restrict__ diag0) {
   // T is the tall buffer [cols_pad (G) + 32 (row 0 = g^T)] x ld ; everything outside G/g is identity/zero padding.
   const int W = 6 * M + 1;
   const int r = blockIdx.y * 16 + threadIdx.y, c = blockIdx.x * 16 + threadIdx.x;
@@ -845,6 +862,7 @@ __global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const d
   } else if (r == c && r >= n && r < cols_pad) {
     v = 1.0;  // identity padding keeps the factor well defined
   }
+  if (r == c && r < cols_pad) diag0[r] = v;
   if (r < cols_pad && (c >> 5) > (r >> 5)) v = 0.0;  // tiles above the diagonal: the factor is lower triangular
   T[(size_t)r * ld + c] = v;
 }
@@ -871,7 +889,7 @@ void launch_gram(cudaStream_t s, const GramParams& gp) {
   count_launch();
   dim3 b(16, 16), g((gp.cols_pad + 15) / 16, (gp.rows_pad + 15) / 16);
   k_gram_reduce<<<g, b, 0, s>>>(gp.partB, nzB, gp.partD, nzD, gp.blocks, gp.M, gp.n_poses, gp.T, gp.ld, gp.rows_pad,
-                                gp.cols_pad);
+                                gp.cols_pad, gp.diag0);
   count_launch();
 }
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -151,10 +152,12 @@ struct xb_filter {
   // slam rows
   int* d_scols; double *d_svals, *d_sres, *d_sgamma; int* d_sinl; int* d_anchor;
   // gram
-  double *d_partB, *d_partD, *d_blocks, *d_Tg, *d_Rg;
+  double *d_partB, *d_partD, *d_blocks, *d_Tg, *d_Rg, *d_diag0;
   int gcols_pad = 0, grows_pad = 0, nz = 1;
   int* d_flags = nullptr;
   int* d_err = nullptr;
+  long long* d_trace = nullptr;  // optional tile-Cholesky timeline (XB_CHOL_TRACE=1)
+  int trace_tiles = 0;
   // kalman tall buffer
   double* d_T = nullptr;
   size_t T_doubles = 0;
@@ -359,12 +362,13 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   f->grows_pad = f->gcols_pad + 32;
   DA(f->d_Tg, (size_t)f->grows_pad * f->gcols_pad, double);
   DA(f->d_Rg, (size_t)f->gcols_pad * f->gcols_pad, double);
+  DA(f->d_diag0, f->gcols_pad, double);
 
   const int m_max = std::max(6 * M + 2 * F, N);  // dense-H path allows up to N rows
   const int m_pad = pad32(m_max), n_pad = pad32(N);
   f->T_doubles = (size_t)(m_pad + n_pad + 96) * m_pad;
   DA(f->d_T, f->T_doubles, double);
-  DA(f->d_flags, (size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64, int);
+  DA(f->d_flags, (size_t)((m_pad + n_pad + 96) / 32 + 2) * (m_pad / 32) + 128, int);
   DA(f->d_omega, 32, int);
   DA(f->d_omega_inv, n_pad, int);
   DA(f->d_tileflag, n_pad / 32 + 1, int);
@@ -372,6 +376,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_Zb, (size_t)n_pad * 32, double);
   DA(f->d_Yb, (size_t)n_pad * 32, double);
   DA(f->d_err, 4, int);
+  if (getenv("XB_CHOL_TRACE")) DA(f->d_trace, 6 * ((size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64), long long);
 
   DA(f->d_rowmap, N, int);
   DA(f->d_ccols, 15 * (size_t)(6 + 3 * std::max(1, F)), int);
@@ -856,10 +861,10 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     gp.D = f->d_D1; gp.rowsD = 2 * f->l_newms.n_obs * (n1 > 0); gp.nzD = f->nz; gp.partD = f->d_partD;
     gp.off = l0.d_off; gp.inlier = f->d_inl0; gp.n_tracks_msckf = n0; gp.Jout = f->d_J0;
     gp.blocks = f->d_blocks;
-    gp.T = f->d_Tg; gp.ld = f->gcols_pad; gp.rows_pad = f->grows_pad; gp.cols_pad = f->gcols_pad;
+    gp.T = f->d_Tg; gp.ld = f->gcols_pad; gp.rows_pad = f->grows_pad; gp.cols_pad = f->gcols_pad; gp.diag0 = f->d_diag0;
     { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp); }
     StageTimer st_(f, ST_CHOLG);
-    tallchol(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, f->d_flags, f->d_err, 1e-14);
+    tallchol(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, f->d_flags, f->d_err, 1e-14, f->d_diag0);
     transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
   } else {
     CK(cudaMemsetAsync(f->d_Tg, 0, gbytes, f->stream));
@@ -909,7 +914,8 @@ static int set_omega(xb_filter* f) {
 
 static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total) {
   const int N = f->N;
-  { StageTimer st_(f, ST_TALLCHOL); tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0); }
+  { StageTimer st_(f, ST_TALLCHOL); tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0, nullptr, f->d_trace);
+    f->trace_tiles = (m_pad / 32) * (m_pad / 32 + 1) / 2 + ((n_pad + 96) / 32) * (m_pad / 32); }
   {
     StageTimer st_(f, ST_CORRECT);
     launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
@@ -1138,6 +1144,15 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
   else if (n == "corr") { src = f->d_corr; cnt = f->N; }
   else if (n == "delta") { src = f->d_delta; cnt = f->N; }
   else if (n == "T") { src = f->d_T; cnt = f->T_doubles; }
+  else if (n == "chol_trace") {
+    if (!f->d_trace) return fail(XB_E_INVALID, "set XB_CHOL_TRACE=1 before xb_create");
+    std::vector<long long> tr(6 * (size_t)f->trace_tiles);
+    CK(cudaStreamSynchronize(f->stream));
+    CK(cudaMemcpy(tr.data(), f->d_trace, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost));
+    cnt = std::min((size_t)max_doubles, tr.size());
+    for (size_t i = 0; i < cnt; ++i) out[i] = (double)(tr[i] - ((i % 6) >= 2 ? tr[2] : 0));
+    return (int)cnt;
+  }
   else return fail(XB_E_INVALID, "unknown debug buffer " + n);
   if ((size_t)max_doubles < cnt) cnt = max_doubles;
   CK(cudaStreamSynchronize(f->stream));

@@ -19,7 +19,8 @@ void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
              double beta, double* C, int ldc);
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc);
-void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol);
+void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
+              const double* diag0 = nullptr, long long* trace = nullptr);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                   const int* tileflag, const double* Zb, const double* Yb);
 void symmetrise(cudaStream_t s, double* P, int n);
@@ -78,6 +79,7 @@ struct GramParams {
   const int* off; const int* inlier; int n_tracks_msckf; const double* Jout;
   double* blocks;  // [M][28]
   double* T; int ld, rows_pad, cols_pad;
+  double* diag0;   // [cols_pad] original diagonal of G (relative pivot test of the semi-definite factorisation)
 };
 void launch_gram(cudaStream_t s, const GramParams& gp);
 
