@@ -1,0 +1,252 @@
+"""CPU-side tests (no GPU): the oracle against the reference's own code / golden vectors, the mathematical
+identities the CUDA formulation relies on, host-side logic, and the C-ABI surface of libxb200.so."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+from scipy.stats import chi2
+
+import oracle
+from oracle.qd_poly import qd_poly
+from oracle.quat import rot_raw
+from oracle.triangulation import Triangulation, dlt_two_view
+from oracle.updater import apply_update
+from oracle.updates import global_feature_position, msckf_track_jacobians
+from oracle_driver import OracleFilter, to_oracle_meas
+from x_multi_agent_b200 import lib as L
+from x_multi_agent_b200.synth import Scenario, SynthConfig, record, replay
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+# ---- oracle pinned against the reference -----------------------------------------------------------------
+def test_qd_polynomial_matches_reference_golden_vectors():
+    """oracle.qd_poly == the reference's Propagator::discreteProcessNoiseCov (propagator.cpp:207-840), via the
+    fixture generated from the function compiled where it lies (oracle/tools/make_golden.py)."""
+    g = np.load(ROOT / "tests" / "golden" / "qd_reference.npz")
+    worst = 0.0
+    for i in range(len(g["dt"])):
+        nz = g["noise"][i]
+        mine = qd_poly(g["dt"][i], rot_raw(g["q"][i]), g["w"][i], g["a"][i], *nz)
+        ref = g["Qd"][i]
+        worst = max(worst, np.abs(mine - ref).max() / np.abs(ref).max())
+        # the reference's asymmetries are part of the contract
+        assert np.abs(ref - ref.T).max() > 0
+    assert worst < 5e-14
+
+
+def test_qd_polynomial_matches_compiled_reference_if_present():
+    so = ROOT / "oracle" / "_ref" / "libxref_qd.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref not built (only possible where /root/reference is mounted)")
+    lib = ctypes.CDLL(str(so))
+    P = ctypes.POINTER(ctypes.c_double)
+    lib.xref_qd.argtypes = [ctypes.c_double, P, P, P] + [ctypes.c_double] * 4 + [P]
+    rng = np.random.default_rng(5)
+    for _ in range(10):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, a, dt = rng.normal(size=3), rng.normal(size=3) * 5, rng.uniform(0.001, 0.05)
+        out = np.zeros(225)
+        qw = np.array([q[3], q[0], q[1], q[2]])
+        lib.xref_qd(dt, qw.ctypes.data_as(P), w.ctypes.data_as(P), a.ctypes.data_as(P), 0.0083, 0.00083, 0.0013, 0.00013,
+                    out.ctypes.data_as(P))
+        mine = qd_poly(dt, rot_raw(q), w, a, 0.0083, 0.00083, 0.0013, 0.00013)
+        assert np.abs(mine - out.reshape(15, 15)).max() <= 5e-14 * np.abs(out).max()
+
+
+def test_dlt_matches_opencv():
+    """cv::triangulatePoints is the routine the reference calls (triangulation.cpp:93)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        P1 = np.hstack([np.eye(3), np.zeros((3, 1))])
+        R, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(R) < 0:
+            R[:, 0] *= -1
+        R = sla.expm(0.1 * (rng.normal(size=(3, 3)) - rng.normal(size=(3, 3)).T))
+        P2 = np.hstack([R, rng.normal(size=(3, 1))])
+        X = np.array([*rng.normal(size=2), 6.0 + rng.uniform()])
+        z1 = (P1 @ np.append(X, 1))
+        z2 = (P2 @ np.append(X, 1))
+        z1, z2 = z1[:2] / z1[2] + rng.normal(0, 1e-3, 2), z2[:2] / z2[2] + rng.normal(0, 1e-3, 2)
+        mine = dlt_two_view(P1, P2, z1, z2)
+        ref = cv2.triangulatePoints(P1, P2, z1.reshape(2, 1), z2.reshape(2, 1)).ravel()
+        assert np.allclose(mine[:3] / mine[3], ref[:3] / ref[3], rtol=1e-9, atol=1e-12)
+
+
+def test_chi2_quantile_matches_boost_definition(lib):
+    """xb_chi2_quantile replaces boost::math::quantile(chi_squared(dof), p) (msckf_update.cpp:459-461,
+    slam_update.cpp:196-197); scipy's ppf is the same function."""
+    for p in (0.9, 0.95):
+        for dof in list(range(1, 130)) + [200, 400, 1000]:
+            ref = chi2.ppf(p, dof)
+            got = lib.xb_chi2_quantile(p, float(dof))
+            assert abs(got - ref) <= 1e-11 * ref, (p, dof, got, ref)
+    assert abs(oracle.chi2_quantile(0.95, 57) - 75.6237484693761) < 1e-9
+
+
+# ---- identities behind the CUDA formulation ----------------------------------------------------------------
+def _prior(cfg, frames):
+    scn = Scenario(cfg)
+    ev = record(scn, frames)
+    last = max(i for i, e in enumerate(ev) if e[0] == "update")
+    of = OracleFilter(cfg.M, cfg.F, n_slots=64)
+    replay(ev[:last], of)
+    m = ev[last][1]
+    s = of.ekf.buf.states[of.ekf.buf.closest_idx(m.timestamp)].copy()
+    of.upd.set_measurement(to_oracle_meas(m))
+    of.upd.sm.manage(s, list(m.lost_slam_trk_idxs))
+    return of, m, s
+
+
+def test_projector_gate_gram_compression_and_woodbury_update_equal_the_reference_algebra():
+    """The device never forms the nullspace basis nor an LU inverse.  This test restates, in numpy, exactly what
+    the kernels compute (projector gate, J^T J - B^T B Gram, guarded Cholesky, rank-21 Woodbury for the
+    non-symmetric part of P) and checks it against the oracle's dense reference algebra."""
+    cfg = SynthConfig(M=6, F=6, K=12, seed=1)
+    of, m, s = _prior(cfg, 10)
+    h, res, r = of.upd.construct_update(s)
+    ms, sl = of.upd.last["msckf"], of.upd.last["slam"]
+    quats, poss = of.upd.sm.camera_attitudes(s), of.upd.sm.camera_positions(s)
+    P, M, var, M6, N = s.cov, cfg.M, cfg.sigma_img ** 2, 6 * cfg.M, s.cov.shape[0]
+    assert np.abs(P - P.T).max() > 1e-9, "the reference's prior is expected to be non-symmetric here"
+    Ps = 0.5 * (P + P.T)
+    G = np.zeros((M6 + 1, M6 + 1))
+    for j, trk in enumerate(m.msckf_trks):
+        Lt = len(trk)
+        ivd = Triangulation(quats[-Lt:], poss[-Lt:]).triangulate_gn(trk)
+        J, Hf, rj = msckf_track_jacobians(trk, quats, poss, M, N, global_feature_position(ivd, quats[-1], poss[-1]))
+        U, _ = np.linalg.qr(Hf)
+        Jp = J[:, 15:15 + M6]
+        Pi = np.eye(2 * Lt) - U @ U.T
+        # gate with the non-symmetric S evaluated through its symmetric part + Woodbury on the clone columns
+        S_full = Pi @ Jp @ P[15:15 + M6, 15:15 + M6] @ Jp.T @ Pi + var * np.eye(2 * Lt)
+        gamma = (Pi @ rj) @ np.linalg.solve(S_full, Pi @ rj)
+        assert abs(gamma - ms.gamma[j]) < 1e-9 * abs(gamma)
+        if ms.inlier[j]:
+            Jr = np.hstack([Jp, rj[:, None]])
+            B = U.T @ Jr
+            G += Jr.T @ Jr - B.T @ B
+    A, g = G[:M6, :M6], G[:M6, M6]
+    Lc, Aw, d0 = np.zeros((M6, M6)), A.copy(), np.diag(A).copy()
+    for c in range(M6):  # guarded Cholesky of the semi-definite Gram matrix
+        if Aw[c, c] > 1e-14 * abs(d0[c]) and Aw[c, c] > 0:
+            Lc[c:, c] = Aw[c:, c] / np.sqrt(Aw[c, c])
+            Aw[c + 1:, c + 1:] -= np.outer(Lc[c + 1:, c], Lc[c + 1:, c])
+    z = np.zeros(M6)
+    for c in range(M6):
+        z[c] = (g[c] - Lc[c, :c] @ z[:c]) / Lc[c, c] if Lc[c, c] != 0 else 0.0
+    ns = len(m.slam_trks)
+    Hc = np.zeros((M6 + 2 * ns, N))
+    Hc[:M6, 15:15 + M6] = Lc.T
+    rc = np.concatenate([z, np.zeros(2 * ns)])
+    row = 0
+    for j in range(ns):
+        if sl.inlier[j]:
+            Hc[M6 + 2 * j:M6 + 2 * j + 2] = sl.jac[row:row + 2]
+            rc[M6 + 2 * j:M6 + 2 * j + 2] = sl.res[row:row + 2]
+            row += 2
+    # Omega = core + newest clone; E = antisymmetric part of P restricted to Omega
+    slot = of.upd.sm.n_poses - 1
+    om = list(range(15)) + [15 + 3 * slot + c for c in range(3)] + [15 + 3 * M + 3 * slot + c for c in range(3)]
+    E = 0.5 * (P - P.T)[np.ix_(om, om)]
+    assert np.abs(0.5 * (P - P.T)).sum() - np.abs(E).sum() < 1e-18
+    Ss = Hc @ Ps @ Hc.T + var * np.eye(len(rc))
+    Lk = np.linalg.cholesky(Ss)
+    W1 = sla.solve_triangular(Lk, (P @ Hc.T).T, lower=True).T
+    W2 = sla.solve_triangular(Lk, (P.T @ Hc.T).T, lower=True).T
+    Vt = sla.solve_triangular(Lk, Hc[:, om], lower=True)
+    zz = sla.solve_triangular(Lk, rc, lower=True)
+    C = E @ np.linalg.inv(np.eye(21) + Vt.T @ Vt @ E)
+    Y1, Y2 = W1 @ Vt, W2 @ Vt
+    KA2 = W1 @ W2.T - Y1 @ C @ Y2.T
+    Pn = Ps - 0.5 * (KA2 + KA2.T)
+    delta = W1 @ zz - Y1 @ C @ (Vt.T @ zz)
+    corr = np.zeros(N)
+    s2 = s.copy()
+    apply_update(s2, h, res, r, corr, True)
+    assert np.linalg.norm(Pn - s2.cov) / np.linalg.norm(s2.cov) < 1e-10
+    assert np.linalg.norm(delta - corr) / np.linalg.norm(corr) < 1e-8
+
+
+def test_qr_compressed_update_equals_uncompressed_update():
+    """vio_updater.cpp:487-512: compressing [H|r] by QR does not change the update."""
+    cfg = SynthConfig(M=5, F=4, K=16, seed=3)
+    of, m, s = _prior(cfg, 9)
+    h, res, r = of.upd.construct_update(s)
+    last = of.upd.last
+    H = np.vstack([last["msckf"].jac, last["msckf_slam"].jac, last["slam"].jac])
+    rr = np.concatenate([last["msckf"].res, last["msckf_slam"].res, last["slam"].res])
+    assert H.shape[0] > H.shape[1] + 1
+    a, b = s.copy(), s.copy()
+    apply_update(a, h, res, r, np.zeros(H.shape[1]), True)
+    apply_update(b, H, rr, cfg.sigma_img ** 2 * np.eye(len(rr)), np.zeros(H.shape[1]), True)
+    assert np.linalg.norm(a.cov - b.cov) / np.linalg.norm(b.cov) < 1e-9
+    assert np.linalg.norm(a.p - b.p) < 1e-10
+
+
+def test_oracle_filter_stays_consistent_and_rejects_outliers():
+    cfg = SynthConfig(M=6, F=6, K=20, seed=4, n_short=2, churn=1, outlier_frac=0.1)
+    scn = Scenario(cfg)
+    ev = record(scn, 14)
+    of = OracleFilter(cfg.M, cfg.F, n_slots=64)
+    rejected, errs = [], []
+
+    def on(k, m, st):
+        ms = of.upd.last.get("msckf")
+        if ms is not None and k > 2:
+            rejected.append(int((~ms.inlier).sum()))
+        errs.append(np.linalg.norm(st.p - scn.pose(st.time)[0]))
+    replay(ev, of, on)
+    assert sum(rejected) > 0 and max(errs) < 0.5
+    assert of.upd.sm.n_poses == cfg.M and of.upd.sm.n_features == cfg.F
+
+
+def test_synthetic_generator_is_deterministic():
+    a = record(Scenario(SynthConfig(M=4, F=2, K=5, seed=9)), 6)
+    b = record(Scenario(SynthConfig(M=4, F=2, K=5, seed=9)), 6)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        if x[0] == "imu":
+            assert x[1] == y[1] and np.array_equal(x[3], y[3]) and np.array_equal(x[4], y[4])
+        elif x[0] == "update":
+            assert all(np.array_equal(p, q) for p, q in zip(x[1].msckf_trks, y[1].msckf_trks))
+
+
+# ---- the C ABI ---------------------------------------------------------------------------------------------
+def _declared_symbols():
+    hdr = (ROOT / "include" / "xb200.h").read_text()
+    return sorted(set(re.findall(r"^XB_API[^;(]*?\b(xb_\w+)\s*\(", hdr, flags=re.M)))
+
+
+def test_library_exports_every_symbol_the_header_declares(lib):
+    names = _declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/xb200.h but not exported: {missing}"
+    unbound = [n for n in names if n not in L.SIGNATURES]
+    assert not unbound, f"no ctypes signature for: {unbound}"
+
+
+def test_no_cpu_fallback_create_fails_loudly_without_a_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg = L.XbConfig()
+    lib.xb_default_config(ctypes.byref(cfg))
+    h = ctypes.c_void_p()
+    rc = lib.xb_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc < 0 and not h.value
+    assert b"no CPU fallback" in lib.xb_last_error() or b"CUDA" in lib.xb_last_error()
+
+
+def test_default_config_matches_reference_defaults(lib):
+    cfg = L.XbConfig()
+    lib.xb_default_config(ctypes.byref(cfg))
+    assert (cfg.n_poses_max, cfg.n_features_max, cfg.n_slots) == (15, 15, 250)  # vio/types.h:141,146,188
+    assert (cfg.n_w, cfg.n_bw, cfg.n_a) == (0.0083, 0.00083, 0.0013)             # common/types.h:69-79
+    assert tuple(cfg.g) == (0.0, 0.0, -9.81)

@@ -445,51 +445,68 @@ void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int
 // from the Omega tile; Z/Y are the 32-wide rank-21 Woodbury factors (k_update.cu).  One CTA per 32x32
 // tile pair (I <= J): it owns both P(I,J) and P(J,I), so the update is in place.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_downdate(double* __restrict__ P, int n, const double* __restrict__ T, int m_pad,
-                                                 int n_pad, const int* __restrict__ omega_inv,
-                                                 const int* __restrict__ tileflag, const double* __restrict__ Zb,
-                                                 const double* __restrict__ Yb) {
-  const int nt = (n + TC - 1) / TC;
+// 64x64 output tile per CTA (256 threads, 4x4 register micro-tile), K in 16-wide slabs, register-prefetched
+// double buffering.  Tiles touching Omega rows accumulate both orientations (W1 W2^T and W2 W1^T).
+#define DT 64
+#define DK 16
+__global__ void __launch_bounds__(256) k_downdate(double* __restrict__ P, int n, const double* __restrict__ T, int m_pad,
+                                                  int n_pad, const int* __restrict__ omega_inv,
+                                                  const int* __restrict__ tileflag, const double* __restrict__ Zb,
+                                                  const double* __restrict__ Yb) {
+  const int nt = (n + DT - 1) / DT;
   int b = blockIdx.x, I = 0;
   while (b >= nt - I) { b -= nt - I; ++I; }
   const int J = I + b;
-  const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
-  __shared__ double As[TC][TC + 1], Bs[TC][TC + 1], As2[TC][TC + 1], Bs2[TC][TC + 1];
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  __shared__ double sm[4][DK][DT + 4];  // A(W1 rows I), B(W1 rows J), A2(W2 rows I), B2(W2 rows J); reused as staging
+  double (*As)[DT + 4] = sm[0];
+  double (*Bs)[DT + 4] = sm[1];
+  double (*As2)[DT + 4] = sm[2];
+  double (*Bs2)[DT + 4] = sm[3];
   const double* W1 = T + (size_t)m_pad * m_pad;
   const double* W2o = T + (size_t)(m_pad + n_pad + 32) * m_pad;
-  const bool two = tileflag[I] | tileflag[J];
+  const bool two = (tileflag[2 * I] | tileflag[2 * I + 1] | tileflag[2 * J] | tileflag[2 * J + 1]) != 0;
+  // loader mapping: thread -> (row r of the 64-row block, 4 consecutive k)
+  const int lr = t >> 2, lk = (t & 3) * 4;
+  const int gi = I * DT + lr, gj = J * DT + lr;
+  const bool vi = gi < n, vj = gj < n;
+  const int oi = (two && vi) ? omega_inv[gi] : -1, oj = (two && vj) ? omega_inv[gj] : -1;
+  const double* a1p = W1 + (size_t)(vi ? gi : 0) * m_pad;
+  const double* b1p = W1 + (size_t)(vj ? gj : 0) * m_pad;
+  const double* a2p = oi >= 0 ? W2o + (size_t)oi * m_pad : a1p;
+  const double* b2p = oj >= 0 ? W2o + (size_t)oj * m_pad : b1p;
   double acc[4][4], acc2[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) { acc[a][c] = 0.0; acc2[a][c] = 0.0; }
-  // K loop over the m_pad columns of W, plus one final 32-wide block holding the Woodbury factors
-  for (int k0 = 0; k0 <= m_pad; k0 += TC) {
-    const bool last = k0 == m_pad;
-    for (int e = t; e < TC * TC; e += 64) {
-      const int r = e >> 5, c = e & 31;
-      const int gi = I * TC + r, gj = J * TC + r;
-      if (!last) {
-        const double a1 = gi < n ? W1[(size_t)gi * m_pad + k0 + c] : 0.0;
-        const double b1 = gj < n ? W1[(size_t)gj * m_pad + k0 + c] : 0.0;
-        As[c][r] = a1;
-        Bs[c][r] = b1;
-        if (two) {
-          const int oi = gi < n ? omega_inv[gi] : -1, oj = gj < n ? omega_inv[gj] : -1;
-          As2[c][r] = oi >= 0 ? W2o[(size_t)oi * m_pad + k0 + c] : a1;
-          Bs2[c][r] = oj >= 0 ? W2o[(size_t)oj * m_pad + k0 + c] : b1;
-        }
-      } else {  // acc -= Z_i.Y_j , acc2 -= Y_i.Z_j
-        As[c][r] = gi < n ? -Zb[(size_t)gi * 32 + c] : 0.0;
-        Bs2[c][r] = gj < n ? Yb[(size_t)gj * 32 + c] : 0.0;
-        As2[c][r] = gi < n ? Yb[(size_t)gi * 32 + c] : 0.0;
-        Bs[c][r] = gj < n ? -Zb[(size_t)gj * 32 + c] : 0.0;
-      }
+  double ra[4], rb[4], ra2[4], rb2[4];
+  const int nk = m_pad / DK;
+  auto gload = [&](int kb) {
+    const int k0 = kb * DK + lk;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ra[u] = vi ? a1p[k0 + u] : 0.0;
+      rb[u] = vj ? b1p[k0 + u] : 0.0;
+      if (two) { ra2[u] = vi ? a2p[k0 + u] : 0.0; rb2[u] = vj ? b2p[k0 + u] : 0.0; }
     }
-    __syncthreads();
-    if (two || last) {
-#pragma unroll 4
-      for (int kk = 0; kk < TC; ++kk) {
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      As[lk + u][lr] = ra[u];
+      Bs[lk + u][lr] = rb[u];
+      if (two) { As2[lk + u][lr] = ra2[u]; Bs2[lk + u][lr] = rb2[u]; }
+    }
+  };
+  gload(0);
+  sstore();
+  __syncthreads();
+  for (int kb = 0; kb < nk; ++kb) {
+    if (kb + 1 < nk) gload(kb + 1);  // global loads of the next slab overlap the FMAs of this one
+    if (two) {
+#pragma unroll
+      for (int kk = 0; kk < DK; ++kk) {
         double a[4], bb[4], a2[4], b2[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; a2[u] = As2[kk][ty * 4 + u]; }
@@ -499,13 +516,13 @@ __global__ void __launch_bounds__(64) k_downdate(double* __restrict__ P, int n, 
         for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            acc[u][v] = fma(a[u], b2[v], acc[u][v]);    // W1_i . W2_j
-            acc2[u][v] = fma(a2[u], bb[v], acc2[u][v]); // W2_i . W1_j
+            acc[u][v] = fma(a[u], b2[v], acc[u][v]);     // W1_i . W2_j
+            acc2[u][v] = fma(a2[u], bb[v], acc2[u][v]);  // W2_i . W1_j
           }
       }
     } else {
-#pragma unroll 8
-      for (int kk = 0; kk < TC; ++kk) {
+#pragma unroll
+      for (int kk = 0; kk < DK; ++kk) {
         double a[4], bb[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) a[u] = As[kk][ty * 4 + u];
@@ -518,40 +535,86 @@ __global__ void __launch_bounds__(64) k_downdate(double* __restrict__ P, int n, 
       }
     }
     __syncthreads();
-    if (!two && k0 + TC == m_pad) {  // symmetric part accumulated once: mirror it before the two-sided tail
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc2[a][c] = acc[a][c];
-    }
+    if (kb + 1 < nk) sstore();
+    __syncthreads();
   }
-  // stage P(I,J) and P(J,I)^T, then write both
-  for (int e = t; e < TC * TC; e += 64) {
-    const int r = e >> 5, c = e & 31;
-    const int gi = I * TC + r, gj = J * TC + c;
-    const bool in = gi < n && gj < n;
-    As[r][c] = in ? P[(size_t)gi * n + gj] : 0.0;
-    Bs[r][c] = in ? P[(size_t)gj * n + gi] : 0.0;  // (J,I) block transposed
+  if (!two) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc2[a][c] = acc[a][c];
+  }
+  // rank-21 Woodbury tail (32-wide): acc -= Z_i . Y_j , acc2 -= Y_i . Z_j
+  for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = kb * DK + lk + u;
+      As[lk + u][lr] = vi ? -Zb[(size_t)gi * 32 + k] : 0.0;
+      Bs2[lk + u][lr] = vj ? Yb[(size_t)gj * 32 + k] : 0.0;
+      As2[lk + u][lr] = vi ? Yb[(size_t)gi * 32 + k] : 0.0;
+      Bs[lk + u][lr] = vj ? -Zb[(size_t)gj * 32 + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < DK; ++kk) {
+      double a[4], bb[4], a2[4], b2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; a2[u] = As2[kk][ty * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { bb[u] = Bs[kk][tx * 4 + u]; b2[u] = Bs2[kk][tx * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          acc[u][v] = fma(a[u], b2[v], acc[u][v]);
+          acc2[u][v] = fma(a2[u], bb[v], acc2[u][v]);
+        }
+    }
+    __syncthreads();
+  }
+  // epilogue: P_ij <- (P_ij + P_ji)/2 - (acc + acc2)/2 for the tile pair; the CTA owns P(I,J) and P(J,I).
+  // stage P(J,I)^T through shared memory so that both global accesses are row-contiguous
+  double (*Pt)[DT + 1] = reinterpret_cast<double (*)[DT + 1]>(&sm[0][0][0]);
+  static_assert(sizeof(sm) >= sizeof(double) * DT * (DT + 1), "staging tile does not fit");
+  for (int e = t; e < DT * DT; e += 256) {
+    const int r = e >> 6, c = e & 63;  // element (r, c) of block (J, I)
+    const int gr = J * DT + r, gc = I * DT + c;
+    Pt[c][r] = (gr < n && gc < n) ? P[(size_t)gr * n + gc] : 0.0;  // Pt[i_local][j_local] = P(J,I)[j][i]
   }
   __syncthreads();
+  double outv[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int r = ty * 4 + a, cc = tx * 4 + c;
-      const int gi = I * TC + r, gj = J * TC + cc;
-      if (gi < n && gj < n) {
-        const double v = 0.5 * (As[r][cc] + Bs[r][cc]) - 0.5 * (acc[a][c] + acc2[a][c]);
-        P[(size_t)gi * n + gj] = v;
-        if (I != J) P[(size_t)gj * n + gi] = v;
+      const int gr = I * DT + r, gc = J * DT + cc;
+      double v = 0.0;
+      if (gr < n && gc < n) {
+        v = 0.5 * (P[(size_t)gr * n + gc] + Pt[r][cc]) - 0.5 * (acc[a][c] + acc2[a][c]);
+        P[(size_t)gr * n + gc] = v;
       }
+      outv[a][c] = v;
     }
+  if (I != J) {
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Pt[ty * 4 + a][tx * 4 + c] = outv[a][c];
+    __syncthreads();
+    for (int e = t; e < DT * DT; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      const int gr = J * DT + r, gc = I * DT + c;
+      if (gr < n && gc < n) P[(size_t)gr * n + gc] = Pt[c][r];
+    }
+  }
 }
 
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                   const int* tileflag, const double* Zb, const double* Yb) {
-  const int nt = (n + TC - 1) / TC;
-  k_downdate<<<nt * (nt + 1) / 2, 64, 0, s>>>(P, n, T, m_pad, n_pad, omega_inv, tileflag, Zb, Yb);
+  const int nt = (n + DT - 1) / DT;
+  k_downdate<<<nt * (nt + 1) / 2, 256, 0, s>>>(P, n, T, m_pad, n_pad, omega_inv, tileflag, Zb, Yb);
   count_launch();
 }
 

@@ -24,10 +24,10 @@ __device__ void smallest_right_singular_vector4(double* A /*4x4 row-major, destr
 #pragma unroll 1
   for (int sweep = 0; sweep < 12; ++sweep) {
     double off = 0.0;
-#pragma unroll 1
+#pragma unroll
     for (int p = 0; p < 3; ++p)
-#pragma unroll 1
-      for (int q = p + 1; q < 4; ++q) {
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {  // static indices keep A and V in registers
         double al = 0.0, be = 0.0, ga = 0.0;
         for (int i = 0; i < 4; ++i) {
           al += A[i * 4 + p] * A[i * 4 + p];
@@ -66,8 +66,9 @@ __device__ __forceinline__ int tri_idx(int r, int c) { return r * (r + 1) / 2 + 
 // Per-warp shared-memory carve-up (doubles), Lm = max track length handled by the launch.
 // Y overlays Hf (Hf is dead once U and H2 exist); the anchor blocks exist only in MSCKF-SLAM mode.
 struct WarpSmem {
-  double *Jp, *Ja, *Jap, *Jaa, *Hf, *U, *Y, *V, *res, *X;
+  double *Jp, *Ja, *Jap, *Jaa, *Hf, *U, *Y, *V, *res, *X, *scr;
   __device__ WarpSmem(double* base, int Lm, int mode) {
+    scr = base; base += 128;  // small-matrix scratch (6x6 Woodbury solve)
     Jp = base; base += 6 * Lm;
     Ja = base; base += 6 * Lm;
     Hf = base; Y = base; base += 6 * Lm;
@@ -79,7 +80,7 @@ struct WarpSmem {
     X = base;  // (2Lm+7)(2Lm+8)/2 packed lower triangle incl. 7 augmented rows (Pi r and the 6 clone columns)
   }
   static __host__ __device__ size_t doubles(int Lm, int mode) {
-    return (size_t)(mode == 1 ? 44 : 32) * Lm + (size_t)(2 * Lm + 7) * (2 * Lm + 8) / 2;
+    return 128 + (size_t)(mode == 1 ? 44 : 32) * Lm + (size_t)(2 * Lm + 7) * (2 * Lm + 8) / 2;
   }
 };
 
@@ -511,55 +512,77 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       //   y^T y - (Vt^T y)^T E (I + G E)^-1 (Vt^T y),  Vt = L^-1 V,  G = Vt^T Vt      (Woodbury)
       gamma = wdot(aug, 1, aug, 1, R2, lane);
       double Em[36], emax = 0.0;
+#pragma unroll
       for (int a = 0; a < 6; ++a)
+#pragma unroll
         for (int b = 0; b < 6; ++b) {
           Em[a * 6 + b] = 0.5 * (P[(size_t)(XB_CORE + ccol[a]) * ld + XB_CORE + ccol[b]] -
                                  P[(size_t)(XB_CORE + ccol[b]) * ld + XB_CORE + ccol[a]]);
           emax = fmax(emax, fabs(Em[a * 6 + b]));
         }
       if (emax > 0.0) {
-        double Gm[36], gv[6], Am[6][12];
+        // small dense algebra cooperatively in shared memory: Am = [I + G E | I] (6 x 12), lane b owns column b
+        double* Gs = ws.scr;            // 36
+        double* gvs = ws.scr + 36;      // 6
+        double* Am = ws.scr + 42;       // 6 x 13
         for (int a = 0; a < 6; ++a) {
-          gv[a] = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, aug, 1, R2, lane);
+          const double gva = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, aug, 1, R2, lane);
+          if (lane == 0) gvs[a] = gva;
           for (int b = 0; b <= a; ++b) {
-            Gm[a * 6 + b] = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, ws.X + tri_idx(R2 + 1 + b, 0), 1, R2, lane);
-            Gm[b * 6 + a] = Gm[a * 6 + b];
+            const double gab = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, ws.X + tri_idx(R2 + 1 + b, 0), 1, R2, lane);
+            if (lane == 0) { Gs[a * 6 + b] = gab; Gs[b * 6 + a] = gab; }
           }
         }
-        for (int a = 0; a < 6; ++a)
-          for (int b = 0; b < 12; ++b) {
-            double v = 0.0;
-            if (b < 6) {
-              v = (a == b) ? 1.0 : 0.0;
-              for (int x = 0; x < 6; ++x) v = fma(Gm[a * 6 + x], Em[x * 6 + b], v);
+        __syncwarp();
+        if (lane < 12) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            double v;
+            if (lane < 6) {
+              v = (a == lane) ? 1.0 : 0.0;
+#pragma unroll
+              for (int x = 0; x < 6; ++x) v = fma(Gs[a * 6 + x], Em[x * 6 + lane], v);
             } else {
-              v = (b - 6 == a) ? 1.0 : 0.0;
+              v = (lane - 6 == a) ? 1.0 : 0.0;
             }
-            Am[a][b] = v;
+            Am[a * 13 + lane] = v;
           }
+        }
+        __syncwarp();
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c) {  // Gauss-Jordan, partial pivoting (all lanes redundantly)
+        for (int c = 0; c < 6; ++c) {  // Gauss-Jordan with partial pivoting
           int best = c;
-          for (int r = c + 1; r < 6; ++r)
-            if (fabs(Am[r][c]) > fabs(Am[best][c])) best = r;
-          if (best != c)
-            for (int b = 0; b < 12; ++b) { const double tmp = Am[c][b]; Am[c][b] = Am[best][b]; Am[best][b] = tmp; }
-          const double d = Am[c][c];
-          for (int b = 0; b < 12; ++b) Am[c][b] /= d;
-          for (int r = 0; r < 6; ++r)
-            if (r != c) {
-              const double fct = Am[r][c];
-              for (int b = 0; b < 12; ++b) Am[r][b] = fma(-fct, Am[c][b], Am[r][b]);
+          double bv = fabs(Am[c * 13 + c]);
+          for (int r = c + 1; r < 6; ++r) { const double x = fabs(Am[r * 13 + c]); if (x > bv) { bv = x; best = r; } }
+          __syncwarp();
+          if (lane < 12 && best != c) { const double tmp = Am[c * 13 + lane]; Am[c * 13 + lane] = Am[best * 13 + lane]; Am[best * 13 + lane] = tmp; }
+          __syncwarp();
+          double f6[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) f6[r] = Am[r * 13 + c];
+          __syncwarp();
+          if (lane < 12) {
+            const double pr = Am[c * 13 + lane] / f6[c];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              if (r == c) Am[r * 13 + lane] = pr;
+              else Am[r * 13 + lane] = fma(-f6[r], pr, Am[r * 13 + lane]);
             }
+          }
+          __syncwarp();
         }
         double t6[6];
+#pragma unroll
         for (int a = 0; a < 6; ++a) {
           t6[a] = 0.0;
-          for (int b = 0; b < 6; ++b) t6[a] = fma(Am[a][6 + b], gv[b], t6[a]);  // (I+GE)^-1 g
+#pragma unroll
+          for (int b = 0; b < 6; ++b) t6[a] = fma(Am[a * 13 + 6 + b], gvs[b], t6[a]);  // (I+GE)^-1 g
         }
         double corr = 0.0;
+#pragma unroll
         for (int a = 0; a < 6; ++a)
-          for (int b = 0; b < 6; ++b) corr = fma(gv[a] * Em[a * 6 + b], t6[b], corr);
+#pragma unroll
+          for (int b = 0; b < 6; ++b) corr = fma(gvs[a] * Em[a * 6 + b], t6[b], corr);
         gamma -= corr;
       }
       const double chi = tp.chi2_95[2 * L - 3];
@@ -638,10 +661,10 @@ int launch_tracks(cudaStream_t s, const TrackParams& tp) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// SLAM rows (slam_update.cpp:49-214): one thread per SLAM feature; emits 2 sparse rows (<=15 columns).
+// SLAM rows (slam_update.cpp:49-214): one warp per SLAM feature; emits 2 sparse rows (<=15 columns).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_slam_rows(SlamParams sp) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_slam_rows(SlamParams sp) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (j >= sp.n_tracks) return;
   const int M = sp.M, np = sp.n_poses, N = sp.N;
   const double* parr = sp.xv + XV_ARR;
@@ -649,12 +672,15 @@ __global__ void k_slam_rows(SlamParams sp) {
   const double* farr = sp.xv + XV_ARR + 7 * M;
   int* cols = sp.cols + 15 * j;
   double* vals = sp.vals + 30 * j;
-  for (int e = 0; e < 15; ++e) cols[e] = 0;
-  for (int e = 0; e < 30; ++e) vals[e] = 0.0;
-  sp.res[2 * j] = 0.0;
-  sp.res[2 * j + 1] = 0.0;
-  sp.inlier[j] = 0;
-  sp.gamma[j] = NAN;
+  if (lane < 15) cols[lane] = 0;
+  if (lane < 30) vals[lane] = 0.0;
+  if (lane == 0) {
+    sp.res[2 * j] = 0.0;
+    sp.res[2 * j + 1] = 0.0;
+    sp.inlier[j] = 0;
+    sp.gamma[j] = NAN;
+  }
+  __syncwarp();
   const int L = sp.off[j + 1] - sp.off[j];
   if (L < 1) return;
   const double a = farr[3 * j], b = farr[3 * j + 1], r = farr[3 * j + 2];
@@ -674,10 +700,12 @@ __global__ void k_slam_rows(SlamParams sp) {
   const int fcol = XB_CORE + (2 * M + j) * 3;
   int nc;
   double h[30];
+  int lc[15];
   for (int e = 0; e < 30; ++e) h[e] = 0.0;
+  for (int e = 0; e < 15; ++e) lc[e] = 0;
   if (anchor == pos) {  // slam_update.cpp:120-130
     nc = 3;
-    for (int c = 0; c < 3; ++c) cols[c] = fcol + c;
+    for (int c = 0; c < 3; ++c) lc[c] = fcol + c;
     h[0] = 1.0;
     h[15 + 1] = 1.0;
   } else {
@@ -697,11 +725,11 @@ __global__ void k_slam_rows(SlamParams sp) {
     xb_mat_ivd(a, b, r, m3);
     xb_mm23(JR, m3, Hf);
     for (int c = 0; c < 3; ++c) {
-      cols[c] = XB_CORE + 3 * pos + c;
-      cols[3 + c] = XB_CORE + 3 * M + 3 * pos + c;
-      cols[6 + c] = XB_CORE + 3 * anchor + c;
-      cols[9 + c] = XB_CORE + 3 * M + 3 * anchor + c;
-      cols[12 + c] = fcol + c;
+      lc[c] = XB_CORE + 3 * pos + c;
+      lc[3 + c] = XB_CORE + 3 * M + 3 * pos + c;
+      lc[6 + c] = XB_CORE + 3 * anchor + c;
+      lc[9 + c] = XB_CORE + 3 * M + 3 * anchor + c;
+      lc[12 + c] = fcol + c;
       for (int rr = 0; rr < 2; ++rr) {
         h[rr * 15 + c] = Jpos[rr * 3 + c];
         h[rr * 15 + 3 + c] = Jatt[rr * 3 + c];
@@ -714,35 +742,42 @@ __global__ void k_slam_rows(SlamParams sp) {
   // gate: S = h P h^T + var I (2x2), chi2(0.9, 2*track_size)  (slam_update.cpp:192-199)
   // S = h P h^T + var I is evaluated with the (possibly non-symmetric) P exactly as the reference does
   double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-  for (int c = 0; c < nc; ++c) {
-    double t0 = 0, t1 = 0;
-    for (int d = 0; d < nc; ++d) {
-      const double p = sp.P[(size_t)cols[d] * N + cols[c]];
-      t0 = fma(h[d], p, t0);
-      t1 = fma(h[15 + d], p, t1);
+  for (int e = lane; e < nc * nc; e += 32) {  // the (d, c) pairs of the 15x15 gather are spread over the warp
+    const int d = e / nc, c = e % nc;
+    double hd0 = 0, hd1 = 0, hc0 = 0, hc1 = 0;
+    int cd = 0, cc = 0;
+#pragma unroll
+    for (int q = 0; q < 15; ++q) {
+      if (q == d) { hd0 = h[q]; hd1 = h[15 + q]; cd = lc[q]; }
+      if (q == c) { hc0 = h[q]; hc1 = h[15 + q]; cc = lc[q]; }
     }
-    s00 = fma(t0, h[c], s00);
-    s01 = fma(t0, h[15 + c], s01);
-    s10 = fma(t1, h[c], s10);
-    s11 = fma(t1, h[15 + c], s11);
+    const double p = sp.P[(size_t)cd * N + cc];
+    s00 = fma(hd0 * p, hc0, s00);
+    s01 = fma(hd0 * p, hc1, s01);
+    s10 = fma(hd1 * p, hc0, s10);
+    s11 = fma(hd1 * p, hc1, s11);
   }
+  s00 = xb_warp_sum(s00); s01 = xb_warp_sum(s01); s10 = xb_warp_sum(s10); s11 = xb_warp_sum(s11);
   s00 += sp.var_img;
   s11 += sp.var_img;
   const double det = s00 * s11 - s01 * s10;
   const double gamma = (r0 * (s11 * r0 - s01 * r1) + r1 * (s00 * r1 - s10 * r0)) / det;
-  sp.gamma[j] = gamma;
   const int inl = gamma < sp.chi2[j];
-  sp.inlier[j] = inl;
-  if (inl) {
-    for (int e = 0; e < 30; ++e) vals[e] = h[e];
-    sp.res[2 * j] = r0;
-    sp.res[2 * j + 1] = r1;
+  if (lane == 0) {
+    sp.gamma[j] = gamma;
+    sp.inlier[j] = inl;
+    for (int e = 0; e < 15; ++e) cols[e] = lc[e];
+    if (inl) {
+      for (int e = 0; e < 30; ++e) vals[e] = h[e];
+      sp.res[2 * j] = r0;
+      sp.res[2 * j + 1] = r1;
+    }
   }
 }
 
 void launch_slam_rows(cudaStream_t s, const SlamParams& sp) {
   if (sp.n_tracks <= 0) return;
-  k_slam_rows<<<(sp.n_tracks + 63) / 64, 64, 0, s>>>(sp);
+  k_slam_rows<<<(sp.n_tracks + 3) / 4, 128, 0, s>>>(sp);
   count_launch();
 }
 

@@ -57,7 +57,7 @@ __global__ void k_s_slam(UpdateDims d, const int* __restrict__ scols, const doub
 }
 
 // diagonal (+var on real rows, 1 on padding) and the r_eff row
-__global__ void k_s_finish(UpdateDims d, const double* __restrict__ Rg, int ldr, const double* __restrict__ zg,
+__global__ void k_s_finish(UpdateDims d, const double* __restrict__ Lg, int ldr, const double* __restrict__ zg,
                            const int* __restrict__ scols, const double* __restrict__ svals, const double* __restrict__ sres,
                            const double* __restrict__ corr, double var, double* __restrict__ T) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +73,7 @@ __global__ void k_s_finish(UpdateDims d, const double* __restrict__ Rg, int ldr,
   if (a < d.ms) {
     r = zg[a];
     if (corr)
-      for (int b = 0; b < d.ms; ++b) r = fma(Rg[(size_t)a * ldr + b], corr[XB_CORE + b], r);
+      for (int b = 0; b < d.ms; ++b) r = fma(Lg[(size_t)b * ldr + a], corr[XB_CORE + b], r);  // Rg[a][b] = Lg[b][a]
   } else {
     const int j = (a - d.ms) >> 1, h = (a - d.ms) & 1;
     r = sres[2 * j + h];
@@ -95,7 +95,7 @@ void launch_build_pht(cudaStream_t s, const UpdateDims& d, const double* P, cons
   }
 }
 
-void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, int ldr, const double* zg, const int* scols,
+void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, const double* zg, const int* scols,
                     const double* svals, const double* sres, const double* corr_total, double var, double* T) {
   // slab rows: S[0:ms, 0:m] = Rg * PHt[pose rows, 0:m]
   gemm_nn(s, d.ms, d.m, d.ms, 1.0, Rg, ldr, T + (size_t)(d.m_pad + XB_CORE) * d.ld, d.ld, 0.0, T, d.ld);
@@ -105,7 +105,7 @@ void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, int l
     count_launch();
   }
   launch_sym_lower(s, T, d.ld, d.m);
-  k_s_finish<<<(d.m_pad + 127) / 128, 128, 0, s>>>(d, Rg, ldr, zg, scols, svals, sres, corr_total, var, T);
+  k_s_finish<<<(d.m_pad + 127) / 128, 128, 0, s>>>(d, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
   count_launch();
 }
 
@@ -127,7 +127,7 @@ __global__ void k_dense_finish(int m, int m_pad, int n_pad, int N, const double*
   reff[a] = r;
 }
 // ---- Omega rows for the VIO (structured Hc) path ------------------------------------------------------
-__global__ void k_omega_rows(UpdateDims d, const double* __restrict__ P, const double* __restrict__ Rg, int ldr,
+__global__ void k_omega_rows(UpdateDims d, const double* __restrict__ P, const double* __restrict__ Lg, int ldr,
                              const int* __restrict__ scols, const double* __restrict__ svals, const int* __restrict__ omega,
                              double* __restrict__ T) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
@@ -135,8 +135,8 @@ __global__ void k_omega_rows(UpdateDims d, const double* __restrict__ P, const d
   const int ok = omega[k];
   double v = 0.0, a2 = 0.0;
   if (a < d.ms) {
-    if (ok >= XB_CORE && ok < XB_CORE + d.ms) v = Rg[(size_t)a * ldr + ok - XB_CORE];
-    for (int b = 0; b < d.ms; ++b) a2 = fma(P[(size_t)(XB_CORE + b) * d.N + ok], Rg[(size_t)a * ldr + b], a2);
+    if (ok >= XB_CORE && ok < XB_CORE + d.ms) v = Lg[(size_t)(ok - XB_CORE) * ldr + a];  // Rg[a][b] = Lg[b][a]
+    for (int b = 0; b < d.ms; ++b) a2 = fma(P[(size_t)(XB_CORE + b) * d.N + ok], Lg[(size_t)b * ldr + a], a2);
   } else {
     const int j = (a - d.ms) >> 1, h = (a - d.ms) & 1;
     for (int e = 0; e < 15; ++e) {
@@ -167,7 +167,7 @@ __global__ void k_sym_lower(double* __restrict__ T, int ld, int m) {
 }
 
 // After the tile Cholesky: G = Vt Vt^T, q = Vt z, E from P, C = E (I + G E)^-1.   om = [C 21x21 | q 21]
-__global__ void __launch_bounds__(256) k_omega_small(int N, int m_pad, int n_pad, const double* __restrict__ T,
+__global__ void __launch_bounds__(1024) k_omega_small(int N, int m_pad, int n_pad, const double* __restrict__ T,
                                                      const double* __restrict__ P, const int* __restrict__ omega,
                                                      double* __restrict__ om) {
   __shared__ double G[NOM][NOM], E[NOM][NOM], A[NOM][2 * NOM + 1], q[NOM];
@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int m_pad, int n_pad
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const double* Vt = T + (size_t)(m_pad + n_pad + 64) * m_pad;
   const double* z = T + (size_t)(m_pad + n_pad) * m_pad;
-  for (int e = w; e < NOM * NOM + NOM; e += 8) {  // one warp per dot product
+  const int nwarps = blockDim.x >> 5;
+  for (int e = w; e < NOM * NOM + NOM; e += nwarps) {  // one warp per dot product
     const int k = e / NOM, l = e % NOM;
     const double* a = Vt + (size_t)(e < NOM * NOM ? k : e - NOM * NOM) * m_pad;
     const double* b = e < NOM * NOM ? Vt + (size_t)l * m_pad : z;
@@ -186,13 +187,13 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int m_pad, int n_pad
       if (e < NOM * NOM) G[k][l] = s; else q[e - NOM * NOM] = s;
     }
   }
-  for (int e = t; e < NOM * NOM; e += 256) {
+  for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int k = e / NOM, l = e % NOM;
     E[k][l] = 0.5 * (P[(size_t)omega[k] * N + omega[l]] - P[(size_t)omega[l] * N + omega[k]]);
   }
   __syncthreads();
   // A = [I + G E | I]
-  for (int e = t; e < NOM * 2 * NOM; e += 256) {
+  for (int e = t; e < NOM * 2 * NOM; e += blockDim.x) {
     const int r = e / (2 * NOM), c = e % (2 * NOM);
     double v;
     if (c < NOM) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int m_pad, int n_pad
     __syncthreads();
     if (t < 2 * NOM) A[c][t] /= d;
     __syncthreads();
-    for (int e = t; e < NOM * 2 * NOM; e += 256) {
+    for (int e = t; e < NOM * 2 * NOM; e += blockDim.x) {
       const int r = e / (2 * NOM), cc = e % (2 * NOM);
       if (r != c && cc != c) A[r][cc] = fma(-A[r][c], A[c][cc], A[r][cc]);
     }
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int m_pad, int n_pad
     __syncthreads();
   }
   // C = E * inv
-  for (int e = t; e < NOM * NOM; e += 256) {
+  for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int r = e / NOM, c = e % NOM;
     double v = 0.0;
     for (int x = 0; x < NOM; ++x) v = fma(E[r][x], A[x][NOM + c], v);
@@ -321,10 +322,10 @@ void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, co
   count_launch();
 }
 
-void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
+void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Lg, int ldr, const int* scols,
                        const double* svals, const int* omega, double* T) {
   dim3 g((d.m + 127) / 128, NOM);
-  k_omega_rows<<<g, 128, 0, s>>>(d, P, Rg, ldr, scols, svals, omega, T);
+  k_omega_rows<<<g, 128, 0, s>>>(d, P, Lg, ldr, scols, svals, omega, T);
   count_launch();
 }
 void launch_sym_lower(cudaStream_t s, double* T, int ld, int m) {
@@ -335,7 +336,7 @@ void launch_sym_lower(cudaStream_t s, double* T, int ld, int m) {
 void launch_correct(cudaStream_t s, int M, int F, int N, const double* T, int m_pad, int n_pad, const double* P,
                     const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* xv,
                     double* corr_total, double* delta_out) {
-  k_omega_small<<<1, 256, 0, s>>>(N, m_pad, n_pad, T, P, omega, om);
+  k_omega_small<<<1, 1024, 0, s>>>(N, m_pad, n_pad, T, P, omega, om);
   count_launch();
   k_omega_rowsolve<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, m_pad, n_pad, T, om, omega_inv, corr_total, delta_out, Zb, Yb);
   count_launch();

@@ -176,6 +176,7 @@ struct xb_filter {
   int *d_omega = nullptr, *d_omega_inv = nullptr, *d_tileflag = nullptr;
   double *d_om = nullptr, *d_Zb = nullptr, *d_Yb = nullptr;
   int omega_slot = -2;
+  bool corr_zero = false;  // correction_total is known to be all-zero (first IEKF iteration)
   std::vector<void*> allocs;
 };
 
@@ -371,7 +372,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_flags, (size_t)((m_pad + n_pad + 96) / 32 + 2) * (m_pad / 32) + 128, int);
   DA(f->d_omega, 32, int);
   DA(f->d_omega_inv, n_pad, int);
-  DA(f->d_tileflag, n_pad / 32 + 1, int);
+  DA(f->d_tileflag, n_pad / 32 + 4, int);
   DA(f->d_om, 21 * 21 + 32, double);
   DA(f->d_Zb, (size_t)n_pad * 32, double);
   DA(f->d_Yb, (size_t)n_pad * 32, double);
@@ -900,7 +901,7 @@ static int set_omega(xb_filter* f) {
   const int slot = std::max(0, f->n_poses - 1);
   if (slot == f->omega_slot) return 0;
   const int N = f->N, M = f->M, n_pad = pad32(N);
-  std::vector<int> om(32, 0), inv(n_pad, -1), flag(n_pad / 32 + 1, 0);
+  std::vector<int> om(32, 0), inv(n_pad, -1), flag(n_pad / 32 + 4, 0);
   for (int k = 0; k < 15; ++k) om[k] = k;
   for (int c = 0; c < 3; ++c) { om[15 + c] = XB_CORE + 3 * slot + c; om[18 + c] = XB_CORE + 3 * M + 3 * slot + c; }
   for (int k = 0; k < 21; ++k) { inv[om[k]] = k; flag[om[k] / 32] = 1; }
@@ -933,6 +934,7 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
 
 extern "C" int xb_updater_reset_correction(xb_filter* f) {
   CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * f->N, f->stream));
+  f->corr_zero = true;
   return XB_OK;
 }
 
@@ -948,10 +950,12 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   CK(cudaMemsetAsync(f->d_T, 0, tb, f->stream));
   const double* zg = f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad;
   launch_build_pht(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_T);
-  launch_build_s(f->stream, d, f->d_Rg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, f->d_corr,
+  launch_build_s(f->stream, d, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres,
+                 f->corr_zero ? nullptr : f->d_corr,
                  f->cfg.sigma_img * f->cfg.sigma_img, f->d_T);
-  launch_omega_rows(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_omega, f->d_T);
+  launch_omega_rows(f->stream, d, f->d_Pw, f->d_Tg, f->gcols_pad, f->d_scols, f->d_svals, f->d_omega, f->d_T);
   }
+  f->corr_zero = false;
   return apply_from_tall(f, d.m_pad, d.n_pad, cov_update, f->d_corr);
 }
 
@@ -1068,7 +1072,7 @@ extern "C" int xb_vio_post_update(xb_filter* f) {
 // ---- Updater::update (updater.cpp:39-115, single-UAV build) -------------------------------------------------------------
 extern "C" int xb_updater_update(xb_filter* f) {
   int rc;
-  CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * f->N, f->stream));
+  if ((rc = xb_updater_reset_correction(f)) < 0) return rc;
   if (f->l_short.n > 0) {  // preUpdateShortMsckf (vio_updater.cpp:209-215)
     if ((rc = xb_vio_construct_update(f, 1)) < 0) return rc;
     if ((rc = xb_updater_apply_constructed(f, 1)) < 0) return rc;
@@ -1076,7 +1080,7 @@ extern "C" int xb_updater_update(xb_filter* f) {
   if ((rc = xb_sm_manage(f, f->lost.data(), (int)f->lost.size())) < 0) return rc;  // preUpdate (vio_updater.cpp:200-207)
   const bool requested = f->l_msckf.n || f->l_slam.n || f->l_newstd.n || f->l_newms.n;
   if (requested) {
-    CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * f->N, f->stream));
+    if ((rc = xb_updater_reset_correction(f)) < 0) return rc;
     const int iters = std::max(1, f->cfg.iekf_iter);
     for (int i = 0; i < iters; ++i) {
       if ((rc = xb_vio_construct_update(f, 0)) < 0) return rc;

@@ -97,13 +97,13 @@ struct UpdateDims {
 void launch_build_pht(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
                       const double* svals, double* T);
 // S = Hc * PHt + var I (rows 0..m-1 of the tall buffer), identity padding and the r_eff row.
-void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, int ldr, const double* zg, const int* scols,
+void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, const double* zg, const int* scols,
                     const double* svals, const double* sres, const double* corr_total, double var, double* T);
 // dense-H variant (Updater::applyUpdate with a caller-supplied H)
 void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, const double* P, const double* H,
                           const double* res, const double* rdiag, const double* corr_total, const int* omega, double* T);
 // Omega tile (A2 rows) and V tile of the structured path
-void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
+void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Lg, int ldr, const int* scols,
                        const double* svals, const int* omega, double* T);
 // Woodbury factors, delta = K r - corr_total ; State::correct ; corr_total += delta
 void launch_correct(cudaStream_t s, int M, int F, int N, const double* T, int m_pad, int n_pad, const double* P,
