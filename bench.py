@@ -45,7 +45,7 @@ def workload_config(n_gpus, extra=None):
 
 def build_scenario(seed):
     from x_multi_agent_b200.synth import Scenario, SynthConfig, record
-    cfg = SynthConfig(M=CFG2["M"], F=CFG2["F"], K=FILL_K, seed=seed, slam_init_frame=CFG2["M"])
+    cfg = SynthConfig(M=CFG2["M"], F=CFG2["F"], K=FILL_K, seed=seed, slam_init_frame=CFG2["M"], slam_lm_seed=4242)
     scn = Scenario(cfg)
     fill = record(scn, N_FILL)
     scn.c.K = CFG2["K"]
@@ -218,7 +218,8 @@ def main():
         torch.cuda.synchronize()
 
     scn, fill = build_scenario(seed=rank)
-    flt = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank, downdate_precision=args.precision)
+    flt = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank, downdate_precision=args.precision,
+                 sigma_landmark=0.3, ci_slam_w=0.1)
     stream = torch.cuda.Stream()
     flt.set_stream(stream.cuda_stream)
     replay(fill, flt)
@@ -268,10 +269,39 @@ def main():
         flt.set_measurement(packed[i])                      # host -> device: track lists
         st = flt.process_update_measurement(want_state=True)  # device -> host: updated state (+ stream sync)
         t1 = time.perf_counter()
+        t_last = st.time
         if j >= W:
             e2e_s += t1 - t0
     barrier()
     assert np.all(np.isfinite(st.x)), "non-finite state after the benchmark"
+    # ---- phase C (N > 1): covariance-intersection fusion steps with the compressed payload exchanged over NCCL ----
+    ci = None
+    if world > 1:
+        from x_multi_agent_b200.ci import exchange_payloads, ring_matches
+        PL = flt.ci_payload_len()
+        local = torch.zeros(PL, dtype=torch.float64, device="cuda")
+        matches = ring_matches(rank, world, CFG2["F"])
+        c0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+        c1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+        inl = 0.0
+        barrier()
+        for i in range(W + K):
+            flt.synchronize()
+            with torch.cuda.stream(stream):
+                c0[i].record(stream)
+                flt.ci_pack(local.data_ptr())
+                gathered = exchange_payloads(local)          # the only collective of the path (all-gather, NVLink)
+                flt.process_others_packed(t_last, gathered.data_ptr(), world, matches, want_state=False)
+                c1[i].record(stream)
+            stream.synchronize()
+            inl = float(flt.ci_last_gates(len(matches))[:, 0].mean())
+        barrier()
+        ci_ms = sum(c0[i].elapsed_time(c1[i]) for i in range(W, W + K))
+        tci = torch.tensor([ci_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tci, op=dist.ReduceOp.MAX)
+        ci = {"ci_fusion_steps_per_sec": world * K / (float(tci[0]) * 1e-3), "ms_per_step": float(tci[0]) / K,
+              "matches_per_step": len(matches), "inlier_frac_rank0": inl, "payload_bytes_per_agent": PL * 8,
+              "full_simplestate_bytes": 8 * (795 * 795 + 16 + 7 * 30 + 3 * 200), "collective": "all_gather (NCCL)"}
     tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -338,7 +368,7 @@ def main():
                     "h2d_bytes_per_step": int(np.mean([p.h2d_bytes for p in packed])) + 4 * (795 + 16 * 6 + 2 * 200),
                     "d2h_bytes_per_step": flt.LX * 8},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary(), "stage_ms_per_update": stages_ms}
+            "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci}
     print(json.dumps(line))
     flt.close()
     if world > 1:

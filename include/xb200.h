@@ -197,9 +197,19 @@ XB_API int xb_updater_update(xb_filter* f);
 /* Propagator::propagateState + propagateCovariance (propagator.cpp:30-72) slot_from -> slot_to. */
 XB_API int xb_propagate(xb_filter* f, int slot_from, int slot_to);
 
-/* ---- multi-agent compressed payload ---------------------------------------------- */
+/* ---- multi-agent compressed payload ----------------------------------------------
+ * A SLAM-SLAM match uses the peer only through the matched feature's world position and the 3x3 projection
+ * h P h^T of the peer covariance (multi_slam_update.cpp:116-220).  Each agent packs these per SLAM feature on
+ * its own GPU ([8 header doubles | 13 doubles per feature: valid, G_p_f(3), hPh^T(9)]); the slots are exchanged
+ * with one all-gather and consumed by xb_ekf_process_others_packed.  Replaces shipping SimpleState's N x N
+ * covariance (simple_state.h:65-74) with identical arithmetic. */
 XB_API int xb_ci_payload_len(const xb_filter* f);                       /* doubles per agent slot */
-XB_API int xb_ci_pack(xb_filter* f, int slot, double* dev_payload);     /* device pointer */
+XB_API int xb_ci_pack(xb_filter* f, int slot, double* dev_payload);     /* device pointer; slot<0: newest */
+/* Ekf::processOthersMeasurement on gathered payloads (device pointer, n_agents slots); match.peer = slot index. */
+XB_API int xb_ekf_process_others_packed(xb_filter* f, double timestamp, const double* dev_gathered, int n_agents,
+                                        const xb_slam_match* matches, int n_matches, double* xvec_out);
+/* introspection: per match [inlier, gamma] of the last CI step */
+XB_API int xb_ci_last_gates(xb_filter* f, double* out /* 2*n_matches */, int max_matches);
 
 /* ---- introspection for tests / profiling ------------------------------------------------------ */
 XB_API int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles); /* returns count */

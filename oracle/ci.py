@@ -227,3 +227,45 @@ def multi_msckf_one_track(track, track_id, quats, poss, P, n_poses_max, sigma_im
             P_j[c:c + 3, c:c + 3] *= w_result
         result["multi"] = (S_ci, P_j, h_j, res_pf)
     return result
+
+
+# ---- compressed payload (test infrastructure for the multi-agent exchange, SURVEY 8e) ------------------------
+def pack_payload(state, sm, n_features_max):
+    """[8 header | 13 per feature: valid, G_p_f(3), h P h^T(9)] -- what xb_ci_pack computes on the device."""
+    out = np.zeros(8 + 13 * max(1, n_features_max))
+    out[0], out[1] = sm.n_features, state.time
+    quats, poss = sm.camera_attitudes(state), sm.camera_positions(state)
+    for f in range(sm.n_features):
+        h, G = MultiSlamUpdate.jacobian(quats, poss, state.f_array, sm.anchor_idxs[f], f, sm.n_poses_max,
+                                        state.cov.shape[1], +1.0)
+        o = out[8 + 13 * f:8 + 13 * f + 13]
+        o[0] = 1.0
+        o[1:4] = G
+        o[4:13] = (h @ state.cov @ h.T).ravel()
+    return out
+
+
+def multi_slam_from_payload(quats, poss, feature_states, anchor_idxs, P, n_poses_max, sigma_landmark, gathered, matches,
+                            ci_slam_w):
+    """MultiSlamUpdate restated on gathered payload slots; `matches` = (peer_slot, current_fid, received_fid)."""
+    _check_w(ci_slam_w)
+    var_lm = sigma_landmark * sigma_landmark
+    out = dict(S=[], P=[], H=[], res=[], gamma=[], inlier=[])
+    for peer, cur, rcv in matches:
+        o = gathered[peer][8 + 13 * rcv:8 + 13 * rcv + 13]
+        h_j, G_p_f = MultiSlamUpdate.jacobian(quats, poss, feature_states, anchor_idxs[cur], cur, n_poses_max, P.shape[1], +1.0)
+        Mo, Mp = h_j @ P @ h_j.T, o[4:13].reshape(3, 3)
+        res_j = -G_p_f + o[1:4]
+        gamma = float(res_j @ np.linalg.inv(Mo + Mp + var_lm * np.eye(3)) @ res_j)
+        inl = gamma < chi2_quantile(0.9, 3)
+        out["gamma"].append(gamma)
+        out["inlier"].append(inl)
+        if inl:
+            w_res = 1.0 / (1.0 - ci_slam_w)
+            S_j = w_res * Mo + (1.0 / ci_slam_w) * Mp + var_lm * np.eye(3)
+            P_j = P.copy()
+            a = anchor_idxs[cur]
+            for c in (K_CORE + a * 3, K_CORE + a * 3 + n_poses_max * 3, K_CORE + (n_poses_max * 2 + cur) * 3):
+                P_j[c:c + 3, c:c + 3] *= w_res
+            out["S"].append(S_j); out["P"].append(P_j); out["H"].append(h_j); out["res"].append(res_j)
+    return out

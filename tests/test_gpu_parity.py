@@ -319,3 +319,98 @@ def test_cfg2_properties_and_parity():
     dev.synchronize()
     rp.done()
     dev.close()
+
+
+def _two_agents(frames=8):
+    """Two agents observing the same SLAM landmarks (same seed -> same landmark ids), different trajectories/noise."""
+    out = []
+    for a in range(2):
+        cfg = SynthConfig(M=6, F=6, K=10, seed=11)          # same seed: same landmark set & feature slot order
+        scn = Scenario(cfg)
+        scn.phase = scn.phase + 0.3 * a                      # different trajectory per agent
+        scn.rng = np.random.Generator(np.random.PCG64(100 + a))
+        ev = record(scn, frames)
+        ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+        dev = make_filter(cfg, sigma_landmark=0.3, ci_slam_w=0.1)
+        replay(ev, ora)
+        replay(ev, dev)
+        out.append((cfg, ev, ora, dev))
+    return out
+
+
+def test_slam_slam_covariance_intersection_matches_oracle():
+    """Ekf::processOthersMeasurement -> collaborativeUpdate -> MultiSlamUpdate + applyCI
+    (ekf.cpp:143-176, updater.cpp:22-36,144-161, multi_slam_update.cpp:61-246, ci.cpp:94-127), fixed weight."""
+    from oracle.ci import MultiSlamUpdate, SimpleState, SlamMatch
+    from x_multi_agent_b200 import PeerState
+    (cfg, ev0, ora0, dev0), (_, ev1, ora1, dev1) = _two_agents()
+    sigma_lm, w = 0.3, 0.1
+    s1 = ora1.newest()
+    peer_o = SimpleState(s1.dynamic_states(), s1.p_array.copy(), s1.q_array.copy(), s1.f_array.copy(), s1.cov.copy(),
+                         list(ora1.upd.sm.anchor_idxs))
+    peer_d = PeerState(s1.p_array, s1.q_array, s1.f_array, list(ora1.upd.sm.anchor_idxs), s1.cov)
+    matches = [(0, f, f) for f in range(cfg.F)] + [(0, 2, 4)]   # last one is a wrong association -> gated out
+    t = ora0.newest().time - 0.02                                # a buffered state a few IMU samples back
+    # oracle
+    def collab(state):
+        sm = ora0.upd.sm
+        msu = MultiSlamUpdate(sm.camera_attitudes(state), sm.camera_positions(state), state.f_array, sm.anchor_idxs, state.cov,
+                              cfg.M, sigma_lm, [SlamMatch(peer_o, c, r) for _, c, r in matches], w)
+        collab.msu = msu
+        for Pj, H, res, S in zip(msu.P_list, msu.H_list, msu.res_list, msu.S_list):
+            apply_ci(state, Pj, H, res, S)
+    so = ora0.ekf.process_others_measurement(t, collab)
+    sd = dev0.process_others_measurement(t, [peer_d], matches)
+    assert so is not None and sd is not None
+    rp = Report()
+    gates = dev0.ci_last_gates(len(matches))
+    rp.check("ci inlier mask", float(np.abs(gates[:, 0] - np.array(collab.msu.inlier, float)).sum()), 0.0)
+    rp.check("ci gamma", rel(gates[:, 1], collab.msu.gamma), 1e-8)
+    assert sum(collab.msu.inlier) >= 3 and not collab.msu.inlier[-1]
+    compare_state(rp, "ci state", sd, so, cfg.M, cfg.F, cov=False)
+    dn = dev0.get_state()
+    dn.cov = dev0.get_covariance()
+    compare_state(rp, "ci newest", dn, ora0.newest(), cfg.M, cfg.F)
+    rp.done()
+    dev0.close()
+    dev1.close()
+
+
+def test_compressed_ci_payload_exchange_equals_full_state_exchange():
+    """exchanging [G_p_f | h P h^T] per feature (13 doubles) gives the same update as shipping the peer's
+    SimpleState with its full covariance.  The all-gather is emulated by device copies (one GPU)."""
+    import torch
+    from x_multi_agent_b200 import PeerState
+    (cfg, _, ora0, dev0), (_, _, ora1, dev1) = _two_agents()
+    PL = dev0.ci_payload_len()
+    gathered = torch.zeros(2, PL, dtype=torch.float64, device="cuda")
+    dev0.ci_pack(gathered[0].data_ptr())
+    dev1.ci_pack(gathered[1].data_ptr())
+    dev0.synchronize()
+    dev1.synchronize()
+    matches = [(1, f, f) for f in range(cfg.F)]
+    t = dev0.get_state().time
+    # reference-format exchange on an identical twin of agent 0
+    s1 = dev1.get_state()
+    peer = PeerState(s1.p_array, s1.q_array, s1.f_array, dev1.anchor_idxs, dev1.get_covariance())
+    twin = make_filter(cfg, sigma_landmark=0.3, ci_slam_w=0.1)
+    st0 = dev0.get_state()
+    st0.cov = dev0.get_covariance()
+    for flt in (twin,):
+        flt.initialize_from_state(st0)
+        flt.sm_set(dev0.n_poses, dev0.n_features, dev0.anchor_idxs, True)
+        flt.process_imu(st0.time, 0, st0.w_m, st0.a_m)
+    full = twin.process_others_measurement(t, [peer], [(0, c, r) for _, c, r in matches])
+    # packed exchange on agent 0 itself (also from its newest state)
+    packed = dev0.process_others_packed(t, gathered.data_ptr(), 2, matches)
+    rp = Report()
+    assert full is not None and packed is not None
+    packed.cov = dev0.get_covariance()
+    full.cov = twin.get_covariance()
+    compare_state(rp, "packed vs full", packed, full, cfg.M, cfg.F)
+    g0, g1 = dev0.ci_last_gates(len(matches)), twin.ci_last_gates(len(matches))
+    rp.check("gates equal", float(np.abs(g0 - g1).max()), 1e-9)
+    assert g0[:, 0].sum() >= 3
+    rp.done()
+    for d in (dev0, dev1, twin):
+        d.close()

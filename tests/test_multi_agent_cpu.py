@@ -1,0 +1,84 @@
+"""N > 1 path on CPU (gloo, world_size 2): the payload exchange plumbing, and that the compressed CI payload gives the
+same fusion as shipping the peer's full SimpleState (oracle arithmetic on both sides)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _agent(rank, frames=8):
+    from oracle_driver import OracleFilter
+    from x_multi_agent_b200.synth import Scenario, SynthConfig, record, replay
+    cfg = SynthConfig(M=6, F=6, K=10, seed=11)
+    scn = Scenario(cfg)
+    scn.phase = scn.phase + 0.3 * rank
+    scn.rng = np.random.Generator(np.random.PCG64(100 + rank))
+    ora = OracleFilter(cfg.M, cfg.F, n_slots=64)
+    replay(record(scn, frames), ora)
+    return cfg, ora
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, os.fspath(ROOT))
+    sys.path.insert(0, os.fspath(ROOT / "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.ci import MultiSlamUpdate, SimpleState, SlamMatch, multi_slam_from_payload, pack_payload
+    from oracle.updater import apply_ci
+    from x_multi_agent_b200.ci import exchange_payloads, ring_matches
+    cfg, ora = _agent(rank)
+    s, sm = ora.newest(), ora.upd.sm
+    local = torch.from_numpy(pack_payload(s, sm, cfg.F))
+    gathered = exchange_payloads(local).numpy()
+    assert gathered.shape == (world, local.numel())
+    assert np.array_equal(gathered[rank], local.numpy())
+    matches = ring_matches(rank, world, cfg.F)
+    quats, poss = sm.camera_attitudes(s), sm.camera_positions(s)
+    comp = multi_slam_from_payload(quats, poss, s.f_array, sm.anchor_idxs, s.cov, cfg.M, 0.3, gathered, matches, 0.1)
+    # full-state exchange: ship the whole SimpleState (object all-gather), as the reference does
+    full_states = [None] * world
+    dist.all_gather_object(full_states, (s.dynamic_states(), s.p_array, s.q_array, s.f_array, s.cov, list(sm.anchor_idxs)))
+    peers = [SimpleState(*fs) for fs in full_states]
+    msu = MultiSlamUpdate(quats, poss, s.f_array, sm.anchor_idxs, s.cov, cfg.M, 0.3,
+                          [SlamMatch(peers[p], c, r) for p, c, r in matches], 0.1)
+    a, b = s.copy(), s.copy()
+    for Pj, H, res, S in zip(msu.P_list, msu.H_list, msu.res_list, msu.S_list):
+        apply_ci(a, Pj, H, res, S)
+    for Pj, H, res, S in zip(comp["P"], comp["H"], comp["res"], comp["S"]):
+        apply_ci(b, Pj, H, res, S)
+    ok = (list(msu.inlier) == list(comp["inlier"]) and np.allclose(msu.gamma, comp["gamma"], rtol=1e-10)
+          and np.linalg.norm(a.cov - b.cov) <= 1e-12 * np.linalg.norm(a.cov) and np.linalg.norm(a.p - b.p) < 1e-12
+          and sum(msu.inlier) >= 2)
+    payload_bytes, full_bytes = local.numel() * 8, sum(np.asarray(x).nbytes for x in full_states[rank][:5])
+    q.put((rank, bool(ok), payload_bytes, full_bytes))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_payload_exchange_and_ci_equivalence():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res), res
+    assert all(pb * 10 < fb for _, _, pb, fb in res)   # the compressed slot is >10x smaller than the SimpleState

@@ -5,5 +5,5 @@ include/xb200.h, built into libxb200.so), `lib` (ctypes binding), `filter` (host
 reference's x::Ekf / x::VioUpdater / x::State API) and `synth` (seeded synthetic inputs at the
 VioUpdater::preProcess seam).  There is no CPU fallback.
 """
-from .filter import Filter, Measurement, PackedMeasurement, State  # noqa: F401
+from .filter import Filter, Measurement, PackedMeasurement, PeerState, State  # noqa: F401
 from .lib import LIB_PATH, XbError, load  # noqa: F401

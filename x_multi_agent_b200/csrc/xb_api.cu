@@ -175,6 +175,10 @@ struct xb_filter {
   // Omega (core + newest clone) bookkeeping for the non-symmetric part of P
   int *d_omega = nullptr, *d_omega_inv = nullptr, *d_tileflag = nullptr;
   double *d_om = nullptr, *d_Zb = nullptr, *d_Yb = nullptr;
+  // covariance intersection
+  double *d_ci_own = nullptr, *d_ci_gather = nullptr, *d_ci_rec = nullptr, *d_ci_K = nullptr, *d_ci_delta = nullptr, *d_ci_HP = nullptr;
+  int *d_ci_matches = nullptr, *d_ci_last = nullptr;
+  int ci_payload_len = 0, ci_max_matches = 256, ci_max_agents = 16, ci_last_n = 0;
   int omega_slot = -2;
   bool corr_zero = false;  // correction_total is known to be all-zero (first IEKF iteration)
   std::vector<void*> allocs;
@@ -374,6 +378,15 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_omega_inv, n_pad, int);
   DA(f->d_tileflag, n_pad / 32 + 4, int);
   DA(f->d_om, 21 * 21 + 32, double);
+  f->ci_payload_len = 8 + 13 * std::max(1, F);
+  DA(f->d_ci_own, f->ci_payload_len, double);
+  DA(f->d_ci_gather, (size_t)f->ci_max_agents * f->ci_payload_len, double);
+  DA(f->d_ci_rec, 64 * (size_t)f->ci_max_matches, double);
+  DA(f->d_ci_K, 3 * (size_t)f->ci_max_matches * N, double);
+  DA(f->d_ci_delta, (size_t)f->ci_max_matches * N, double);
+  DA(f->d_ci_HP, 3 * (size_t)N, double);
+  DA(f->d_ci_matches, 3 * (size_t)f->ci_max_matches, int);
+  DA(f->d_ci_last, 4, int);
   DA(f->d_Zb, (size_t)n_pad * 32, double);
   DA(f->d_Yb, (size_t)n_pad * 32, double);
   DA(f->d_err, 4, int);
@@ -1125,6 +1138,144 @@ extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
     if ((rc = xb_synchronize(f)) < 0) return rc;
   }
   return 1;
+}
+
+// ---- covariance-intersection fusion -----------------------------------------------------------------------------------
+extern "C" int xb_ci_payload_len(const xb_filter* f) { return f->ci_payload_len; }
+
+extern "C" int xb_ci_pack(xb_filter* f, int slot, double* dev_payload) {
+  if (!f || !dev_payload) return fail(XB_E_INVALID, "null argument");
+  if (slot < 0) slot = f->tail;
+  if (slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid state");
+  CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * std::max(1, f->F), cudaMemcpyHostToDevice, f->stream));
+  // only pose / feature columns are read, so the generation buffer (P_vv) is the slot's covariance here
+  launch_ci_pack(f->stream, f->d_xv + (size_t)slot * f->LX, f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->N, f->M,
+                 f->F, f->n_poses, f->n_features, f->d_anchor, dev_payload);
+  return XB_OK;
+}
+
+static int check_ci_weight(double w) {  // ci.cpp:98-101
+  if (w > 1.0 || w == 0.0 || w < -1.0) return fail(XB_E_RUNTIME, "The CI weights must be lower than 1.0 and larger than 0.0");
+  if (w < 0.0) return fail(XB_E_UNSUPPORTED, "NLopt-optimised CI weights (ci_slam_w < 0) are out of scope");
+  return 0;
+}
+
+// Updater::collaborativeUpdate (updater.cpp:22-36) on the work state, peers given as gathered payload slots
+static int collaborative_update_packed(xb_filter* f, const double* dev_gathered, const xb_slam_match* matches, int n_matches) {
+  if (n_matches <= 0) return XB_OK;  // preUpdateCI (vio_updater.cpp:76-79)
+  if (n_matches > f->ci_max_matches) return fail(XB_E_CAPACITY, "too many SLAM-SLAM matches");
+  int rc = check_ci_weight(f->cfg.ci_slam_w);
+  if (rc) return rc;
+  std::vector<int> hm(3 * (size_t)n_matches);
+  for (int j = 0; j < n_matches; ++j) {
+    hm[3 * j] = matches[j].peer;
+    hm[3 * j + 1] = matches[j].current_feature_id;
+    hm[3 * j + 2] = matches[j].received_feature_id;
+    if (matches[j].peer < 0 || matches[j].peer >= f->ci_max_agents || matches[j].received_feature_id < 0 ||
+        matches[j].received_feature_id >= f->F)
+      return fail(XB_E_INVALID, "bad SLAM match");
+    if (matches[j].current_feature_id < 0 || matches[j].current_feature_id >= f->n_features || f->anchor[matches[j].current_feature_id] < 0)
+      return fail(XB_E_RUNTIME, "anchor_idx < 0");  // multi_slam_update.cpp:83-85
+  }
+  CK(cudaMemcpyAsync(f->d_ci_matches, hm.data(), sizeof(int) * hm.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * std::max(1, f->F), cudaMemcpyHostToDevice, f->stream));
+  const double var_lm = f->cfg.sigma_landmark * f->cfg.sigma_landmark;
+  launch_ci_slam(f->stream, f->d_xw, f->d_Pw, f->N, f->M, f->F, f->n_poses, f->n_features, f->d_anchor, dev_gathered,
+                 f->ci_payload_len, f->d_ci_matches, n_matches, var_lm, f->cfg.ci_slam_w, xb_chi2_quantile(0.9, 3.0),
+                 f->d_ci_rec, f->d_ci_last, f->d_ci_K, f->d_ci_delta, f->d_ci_HP);
+  f->ci_last_n = n_matches;
+  CK(cudaStreamSynchronize(f->stream));  // hm lifetime
+  return XB_OK;
+}
+
+extern "C" int xb_ekf_process_others_packed(xb_filter* f, double t, const double* dev_gathered, int n_agents,
+                                            const xb_slam_match* matches, int n_matches, double* xvec_out) {
+  if (!f) return fail(XB_E_INVALID, "null filter");
+  if (f->status == 0) return 0;
+  if (n_agents > f->ci_max_agents) return fail(XB_E_CAPACITY, "too many agents");
+  const int idx = closest_idx(f, t);
+  if (idx < 0 || f->slot_gen[idx] < 0) return 0;
+  int rc;
+  if ((rc = xb_work_load(f, idx)) < 0) return rc;
+  if ((rc = collaborative_update_packed(f, dev_gathered, matches, n_matches)) < 0) return rc;
+  if ((rc = xb_work_store(f, idx)) < 0) return rc;
+  repropagate_from(f, idx);
+  if (xvec_out) {
+    CK(cudaMemcpyAsync(xvec_out, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToHost, f->stream));
+    if ((rc = xb_synchronize(f)) < 0) return rc;
+  }
+  return 1;
+}
+
+// Reference-format entry: peers as SimpleState (full covariance).  The host only gathers, per match, the peer's 9x9
+// covariance block and forms the 13-double payload entry; everything N-sized runs on the device.
+extern "C" int xb_ekf_process_others(xb_filter* f, double t, const xb_peer_state* peers, int n_peers,
+                                     const xb_slam_match* matches, int n_matches, double* xvec_out) {
+  if (!f || (n_peers > 0 && !peers)) return fail(XB_E_INVALID, "null argument");
+  if (n_peers > f->ci_max_agents) return fail(XB_E_CAPACITY, "too many peers");
+  const int PL = f->ci_payload_len;
+  std::vector<double> pay((size_t)std::max(1, n_peers) * PL, 0.0);
+  for (int j = 0; j < n_matches; ++j) {
+    const int pi = matches[j].peer, rf = matches[j].received_feature_id;
+    if (pi < 0 || pi >= n_peers) return fail(XB_E_INVALID, "match refers to an unknown peer");
+    const xb_peer_state& ps = peers[pi];
+    if (rf < 0 || rf >= ps.n_features_max || rf >= f->F) return fail(XB_E_INVALID, "bad received feature id");
+    const int Mp = ps.n_poses_max, Np = XB_NERR(Mp, ps.n_features_max);
+    const int an = ps.anchor_idxs[rf];
+    if (an < 0) return fail(XB_E_RUNTIME, "anchor_idx < 0");
+    const double a = ps.features[3 * rf], b = ps.features[3 * rf + 1], r = ps.features[3 * rf + 2];
+    if (r == 0.0) return fail(XB_E_RUNTIME, "rho = 0");
+    double Ra[9], sk[9], m3[9], t3[3], A1[9], A2[9], h9[27];
+    xb_rot(ps.orientations + 4 * an, Ra);
+    const double ab1[3] = {a, b, 1.0};
+    xb_mv33(Ra, ab1, t3);
+    double* o = pay.data() + (size_t)pi * PL + 8 + 13 * rf;
+    o[0] = 1.0;
+    for (int e = 0; e < 3; ++e) o[1 + e] = (1.0 / r) * t3[e] + (ps.positions[3 * an + e] + ps.translation[e]);  // simple_state.cpp:51-65
+    xb_skew(ab1, sk);
+    xb_mm33(Ra, sk, A1);
+    xb_mat_ivd(a, b, r, m3);
+    xb_mm33(Ra, m3, A2);
+    int c9[9];
+    for (int i = 0; i < 3; ++i)
+      for (int c = 0; c < 3; ++c) {
+        h9[i * 9 + c] = -((i == c) ? 1.0 : 0.0);          // other_h_j carries the opposite sign (multi_slam_update.cpp:180-203)
+        h9[i * 9 + 3 + c] = (1.0 / r) * A1[i * 3 + c];
+        h9[i * 9 + 6 + c] = -(1.0 / r) * A2[i * 3 + c];
+      }
+    for (int c = 0; c < 3; ++c) { c9[c] = XB_CORE + 3 * an + c; c9[3 + c] = XB_CORE + 3 * Mp + 3 * an + c; c9[6 + c] = XB_CORE + (2 * Mp + rf) * 3 + c; }
+    auto Pat = [&](int rr, int cc) { return ps.cov_layout == XB_COL_MAJOR ? ps.cov[(size_t)cc * Np + rr] : ps.cov[(size_t)rr * Np + cc]; };
+    double T[27];
+    for (int i = 0; i < 3; ++i)
+      for (int c = 0; c < 9; ++c) {
+        double s = 0.0;
+        for (int d = 0; d < 9; ++d) s += h9[i * 9 + d] * Pat(c9[d], c9[c]);
+        T[i * 9 + c] = s;
+      }
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) {
+        double s = 0.0;
+        for (int c = 0; c < 9; ++c) s += T[i * 9 + c] * h9[k * 9 + c];
+        o[4 + i * 3 + k] = s;
+      }
+  }
+  CK(cudaMemcpyAsync(f->d_ci_gather, pay.data(), sizeof(double) * pay.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return xb_ekf_process_others_packed(f, t, f->d_ci_gather, std::max(1, n_peers), matches, n_matches, xvec_out);
+}
+
+extern "C" int xb_ci_last_gates(xb_filter* f, double* out, int max_matches) {
+  const int n = std::min(max_matches, f->ci_last_n);
+  std::vector<double> rec(64 * (size_t)std::max(1, n));
+  CK(cudaStreamSynchronize(f->stream));
+  CK(cudaMemcpy(rec.data(), f->d_ci_rec, sizeof(double) * 64 * (size_t)n, cudaMemcpyDeviceToHost));
+  for (int j = 0; j < n; ++j) { out[2 * j] = rec[64 * (size_t)j]; out[2 * j + 1] = rec[64 * (size_t)j + 1]; }
+  return n;
+}
+
+extern "C" int xb_vio_set_msckf_matches(xb_filter*, const xb_peer_state*, int, const xb_msckf_match*, int n_matches) {
+  if (n_matches <= 0) return XB_OK;
+  return fail(XB_E_UNSUPPORTED, "multi-agent MSCKF-MSCKF matches (msckf_update.cpp:88-279) are not built yet; SLAM-SLAM CI is");
 }
 
 // ---- introspection ----------------------------------------------------------------------------------------------------------

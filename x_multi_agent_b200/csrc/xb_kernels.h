@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "xb_common.cuh"
 
 namespace xb {
@@ -137,5 +139,13 @@ void launch_init_std_slam(cudaStream_t s, int M, int F, int N, int n_features, i
                           const double* obs, double rho0, double var_img, double var_rho0, double* xv, double* P);
 void launch_scale_blocks(cudaStream_t s, double* P, int N, const int* cols, int n_blocks, double w);
 void launch_add_diag(cudaStream_t s, double* A, int ld, int n, double v);
+
+// ---- covariance-intersection fusion (k_ci.cu) -----------------------------------------------------------
+void launch_ci_pack(cudaStream_t s, const double* xv, const double* P, int N, int M, int F, int n_poses, int n_features,
+                    const int* anchor, double* out);
+void launch_ci_slam(cudaStream_t s, double* xv, double* P, int N, int M, int F, int n_poses, int n_features,
+                    const int* anchor, const double* gathered, int payload_len, const int* matches, int n_matches,
+                    double var_lm, double w_other, double chi2_90_3, double* rec, int* last_inlier, double* Kall,
+                    double* delta, double* HP);
 
 }  // namespace xb

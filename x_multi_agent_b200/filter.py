@@ -79,6 +79,17 @@ class Measurement:
     lost_slam_trk_idxs: list = field(default_factory=list)
 
 
+@dataclass
+class PeerState:
+    """x::SimpleState (include/x/ekf/simple_state.h:30-75): another agent's snapshot."""
+    positions: np.ndarray      # 3*M
+    orientations: np.ndarray   # 4*M (x,y,z,w)
+    features: np.ndarray       # 3*F
+    anchor_idxs: list
+    cov: np.ndarray            # N x N
+    translation: tuple = (0.0, 0.0, 0.0)
+
+
 def _csr(tracks):
     off = np.zeros(len(tracks) + 1, dtype=np.int32)
     if tracks:
@@ -175,6 +186,51 @@ class Filter:
         if rc == 0:
             return None
         return State(self.M, self.F, out) if want_state else True
+
+    def process_others_measurement(self, t, peers, matches, want_state=True):
+        """Ekf::processOthersMeasurement (ekf.cpp:143-176) with SLAM-SLAM matches (peer_idx, current_fid, received_fid)."""
+        keep = []
+        cp = (L.XbPeerState * max(1, len(peers)))()
+        for i, p in enumerate(peers):
+            pos, ori, fe, cov = L.f64(p.positions), L.f64(p.orientations), L.f64(p.features), L.f64(p.cov)
+            an = np.asarray(p.anchor_idxs, dtype=np.int32)
+            keep += [pos, ori, fe, cov, an]
+            cp[i].n_poses_max, cp[i].n_features_max = pos.size // 3, fe.size // 3
+            cp[i].positions, cp[i].orientations, cp[i].features = L.dptr(pos), L.dptr(ori), L.dptr(fe)
+            cp[i].anchor_idxs, cp[i].cov, cp[i].cov_layout = L.iptr(an), L.dptr(cov), 0
+            for k in range(3):
+                cp[i].translation[k] = p.translation[k]
+        cm = (L.XbSlamMatch * max(1, len(matches)))()
+        for j, (pi, cur, rcv) in enumerate(matches):
+            cm[j].peer, cm[j].current_feature_id, cm[j].received_feature_id = pi, cur, rcv
+        out = np.empty(self.LX) if want_state else None
+        rc = L.check(self.lib.xb_ekf_process_others(self.h, float(t), cp, len(peers), cm, len(matches), L.dptr(out)))
+        if rc == 0:
+            return None
+        return State(self.M, self.F, out) if want_state else True
+
+    def ci_payload_len(self):
+        return self.lib.xb_ci_payload_len(self.h)
+
+    def ci_pack(self, dev_ptr, slot=-1):
+        """Pack this agent's compressed CI payload into device memory at `dev_ptr` (e.g. a torch tensor's data_ptr)."""
+        L.check(self.lib.xb_ci_pack(self.h, slot, C.c_void_p(dev_ptr)))
+
+    def process_others_packed(self, t, gathered_dev_ptr, n_agents, matches, want_state=True):
+        cm = (L.XbSlamMatch * max(1, len(matches)))()
+        for j, (pi, cur, rcv) in enumerate(matches):
+            cm[j].peer, cm[j].current_feature_id, cm[j].received_feature_id = pi, cur, rcv
+        out = np.empty(self.LX) if want_state else None
+        rc = L.check(self.lib.xb_ekf_process_others_packed(self.h, float(t), C.c_void_p(gathered_dev_ptr), n_agents, cm,
+                                                           len(matches), L.dptr(out)))
+        if rc == 0:
+            return None
+        return State(self.M, self.F, out) if want_state else True
+
+    def ci_last_gates(self, n):
+        out = np.zeros(2 * max(1, n))
+        k = L.check(self.lib.xb_ci_last_gates(self.h, L.dptr(out), n))
+        return out[:2 * k].reshape(-1, 2)
 
     def get_state(self, slot=-1):
         out = np.empty(self.LX)

@@ -94,6 +94,8 @@ SIGNATURES = {
     "xb_propagate": (C.c_int, [_VP, C.c_int, C.c_int]),
     "xb_ci_payload_len": (C.c_int, [_VP]),
     "xb_ci_pack": (C.c_int, [_VP, C.c_int, _VP]),
+    "xb_ekf_process_others_packed": (C.c_int, [_VP, C.c_double, _VP, C.c_int, C.POINTER(XbSlamMatch), C.c_int, c_double_p]),
+    "xb_ci_last_gates": (C.c_int, [_VP, c_double_p, C.c_int]),
     "xb_debug_read": (C.c_int, [_VP, C.c_char_p, c_double_p, C.c_int]),
     "xb_debug_read_int": (C.c_int, [_VP, C.c_char_p, c_int_p, C.c_int]),
     "xb_profile_enable": (C.c_int, [_VP, C.c_int]),

@@ -70,6 +70,7 @@ class SynthConfig:
     slam_init_frame: int = -1   # frame at which SLAM features are initialised (-1: when the window is full)
     slam_msckf_init_frac: float = 0.5   # fraction initialised through MSCKF-SLAM promotion (rest: standard)
     churn: int = 0              # SLAM features lost (and re-added) per update once running
+    slam_lm_seed: int = -1      # >= 0: SLAM landmark set drawn from this seed (shared by all agents of a CI scenario)
     n_w: float = 0.0083
     n_bw: float = 0.00083
     n_a: float = 0.0013
@@ -91,8 +92,9 @@ class Scenario:
         self.phase = self.rng.uniform(0, 2 * np.pi, 4)
         # SLAM landmarks: a patch under the trajectory centre that stays in view
         n_l = max(cfg.F * 2 + 8, 8)
-        self.slam_lm = np.column_stack([self.rng.uniform(-2.0, 2.0, n_l), self.rng.uniform(-1.5, 1.5, n_l),
-                                        self.rng.uniform(-2.0, 0.5, n_l)])
+        lrng = self.rng if cfg.slam_lm_seed < 0 else np.random.Generator(np.random.PCG64(cfg.slam_lm_seed))
+        self.slam_lm = np.column_stack([lrng.uniform(-2.0, 2.0, n_l), lrng.uniform(-1.5, 1.5, n_l),
+                                        lrng.uniform(-2.0, 0.5, n_l)])
         self.next_lm = 0
         self.feat_lm = []           # landmark id per active SLAM feature slot
         self.feat_obs = []          # observation history per active SLAM feature
