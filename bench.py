@@ -210,6 +210,7 @@ def main():
     from x_multi_agent_b200.synth import replay
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -219,7 +220,7 @@ def main():
 
     scn, fill = build_scenario(seed=rank)
     flt = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank, downdate_precision=args.precision,
-                 sigma_landmark=0.3, ci_slam_w=0.1)
+                 sigma_landmark=1.0, ci_slam_w=0.1)
     stream = torch.cuda.Stream()
     flt.set_stream(stream.cuda_stream)
     replay(fill, flt)
