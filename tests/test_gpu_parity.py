@@ -115,6 +115,7 @@ def _stage_setup(cfg, n_frames):
     (SynthConfig(M=6, F=6, K=12, seed=1, churn=1), 13),             # slide + re-anchoring + feature removal
     (SynthConfig(M=10, F=0, K=50, seed=0), 12),                     # BASELINE cfg-1 shape
     (SynthConfig(M=5, F=4, K=20, seed=5, n_short=3, churn=1), 11),  # short-MSCKF pre-update
+    (SynthConfig(M=34, F=4, K=16, seed=3), 37),                     # window > 32 poses: two observations per lane
 ])
 def test_update_stage_by_stage(cfg, frames):
     """Updater::update (updater.cpp:39-115) split into its stages, each compared with the oracle."""

@@ -445,114 +445,88 @@ void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int
 // from the Omega tile; Z/Y are the 32-wide rank-21 Woodbury factors (k_update.cu).  One CTA per 32x32
 // tile pair (I <= J): it owns both P(I,J) and P(J,I), so the update is in place.
 // ------------------------------------------------------------------------------------------------
-// 64x64 output tile per CTA (256 threads, 4x4 register micro-tile), K in 16-wide slabs, register-prefetched
-// double buffering.  Tiles touching Omega rows accumulate both orientations (W1 W2^T and W2 W1^T).
+// 64x64 output tile per CTA (256 threads, 4x4 register micro-tile), K in 16-wide slabs with register prefetch.
+//   P_ij <- (P_ij + P_ji)/2 - W1_i.W1_j - (Q_i[k(j)] + Q_j[k(i)])/2 + (Z_i.Y_j + Y_i.Z_j)/2
+// where Q_i[k] = W1_i . (W2 - W1)_{Omega_k} carries the rows on which W2 differs from W1 (k(j) = position of j in
+// Omega, absent for every other j) and Z, Y are the 32-wide rank-21 Woodbury factors -- so the N^2 m main loop is
+// the same symmetric product for every tile.
 #define DT 64
 #define DK 16
+#define DKM 32  // K slab of the main loop
 __global__ void __launch_bounds__(256) k_downdate(double* __restrict__ P, int n, const double* __restrict__ T, int m_pad,
-                                                  int n_pad, const int* __restrict__ omega_inv,
-                                                  const int* __restrict__ tileflag, const double* __restrict__ Zb,
-                                                  const double* __restrict__ Yb) {
+                                                  int n_pad, const int* __restrict__ omega_inv, const double* __restrict__ Zb,
+                                                  const double* __restrict__ Yb, const double* __restrict__ Qb) {
   const int nt = (n + DT - 1) / DT;
   int b = blockIdx.x, I = 0;
   while (b >= nt - I) { b -= nt - I; ++I; }
   const int J = I + b;
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
-  __shared__ double sm[4][DK][DT + 4];  // A(W1 rows I), B(W1 rows J), A2(W2 rows I), B2(W2 rows J); reused as staging
+  __shared__ __align__(16) double sm[4][DK][DT + 4];
   double (*As)[DT + 4] = sm[0];
   double (*Bs)[DT + 4] = sm[1];
   double (*As2)[DT + 4] = sm[2];
   double (*Bs2)[DT + 4] = sm[3];
+  // main loop views: two 32 x 68 slabs over the same storage
+  double (*Am)[DT + 4] = reinterpret_cast<double (*)[DT + 4]>(&sm[0][0][0]);
+  double (*Bm)[DT + 4] = reinterpret_cast<double (*)[DT + 4]>(&sm[2][0][0]);
   const double* W1 = T + (size_t)m_pad * m_pad;
-  const double* W2o = T + (size_t)(m_pad + n_pad + 32) * m_pad;
-  const bool two = (tileflag[2 * I] | tileflag[2 * I + 1] | tileflag[2 * J] | tileflag[2 * J + 1]) != 0;
-  // loader mapping: thread -> (row r of the 64-row block, 4 consecutive k)
-  const int lr = t >> 2, lk = (t & 3) * 4;
+  // loader mapping (main loop): thread -> row (t >> 2) of the 64-row block, 8 consecutive k at (t & 3) * 8
+  const int lr = t >> 2, lk8 = (t & 3) * 8, lk = (t & 3) * 4;
   const int gi = I * DT + lr, gj = J * DT + lr;
   const bool vi = gi < n, vj = gj < n;
-  const int oi = (two && vi) ? omega_inv[gi] : -1, oj = (two && vj) ? omega_inv[gj] : -1;
   const double* a1p = W1 + (size_t)(vi ? gi : 0) * m_pad;
   const double* b1p = W1 + (size_t)(vj ? gj : 0) * m_pad;
-  const double* a2p = oi >= 0 ? W2o + (size_t)oi * m_pad : a1p;
-  const double* b2p = oj >= 0 ? W2o + (size_t)oj * m_pad : b1p;
-  double acc[4][4], acc2[4][4];
+  double acc[4][4], zy[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { acc[a][c] = 0.0; acc2[a][c] = 0.0; }
-  double ra[4], rb[4], ra2[4], rb2[4];
-  const int nk = m_pad / DK;
+    for (int c = 0; c < 4; ++c) { acc[a][c] = 0.0; zy[a][c] = 0.0; }
+  double ra[8], rb[8];
+  const int nk = m_pad / DKM;  // m_pad is a multiple of 32
   auto gload = [&](int kb) {
-    const int k0 = kb * DK + lk;
+    const double2* pa = reinterpret_cast<const double2*>(a1p + kb * DKM + lk8);  // 16-byte aligned: m_pad % 32 == 0
+    const double2* pb = reinterpret_cast<const double2*>(b1p + kb * DKM + lk8);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      ra[u] = vi ? a1p[k0 + u] : 0.0;
-      rb[u] = vj ? b1p[k0 + u] : 0.0;
-      if (two) { ra2[u] = vi ? a2p[k0 + u] : 0.0; rb2[u] = vj ? b2p[k0 + u] : 0.0; }
+      const double2 va = vi ? pa[u] : make_double2(0.0, 0.0);
+      const double2 vb = vj ? pb[u] : make_double2(0.0, 0.0);
+      ra[2 * u] = va.x; ra[2 * u + 1] = va.y; rb[2 * u] = vb.x; rb[2 * u + 1] = vb.y;
     }
   };
   auto sstore = [&]() {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      As[lk + u][lr] = ra[u];
-      Bs[lk + u][lr] = rb[u];
-      if (two) { As2[lk + u][lr] = ra2[u]; Bs2[lk + u][lr] = rb2[u]; }
-    }
+    for (int u = 0; u < 8; ++u) { Am[lk8 + u][lr] = ra[u]; Bm[lk8 + u][lr] = rb[u]; }
   };
   gload(0);
   sstore();
   __syncthreads();
   for (int kb = 0; kb < nk; ++kb) {
     if (kb + 1 < nk) gload(kb + 1);  // global loads of the next slab overlap the FMAs of this one
-    if (two) {
 #pragma unroll
-      for (int kk = 0; kk < DK; ++kk) {
-        double a[4], bb[4], a2[4], b2[4];
+    for (int kk = 0; kk < DKM; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&Am[kk][ty * 4]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&Am[kk][ty * 4 + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bm[kk][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bm[kk][tx * 4 + 2]);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y}, bb[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; a2[u] = As2[kk][ty * 4 + u]; }
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { bb[u] = Bs[kk][tx * 4 + u]; b2[u] = Bs2[kk][tx * 4 + u]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            acc[u][v] = fma(a[u], b2[v], acc[u][v]);     // W1_i . W2_j
-            acc2[u][v] = fma(a2[u], bb[v], acc2[u][v]);  // W2_i . W1_j
-          }
-      }
-    } else {
-#pragma unroll
-      for (int kk = 0; kk < DK; ++kk) {
-        double a[4], bb[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = As[kk][ty * 4 + u];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) bb[u] = Bs[kk][tx * 4 + u];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], bb[v], acc[u][v]);
-      }
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], bb[v], acc[u][v]);
     }
     __syncthreads();
     if (kb + 1 < nk) sstore();
     __syncthreads();
   }
-  if (!two) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc2[a][c] = acc[a][c];
-  }
-  // rank-21 Woodbury tail (32-wide): acc -= Z_i . Y_j , acc2 -= Y_i . Z_j
+  // rank-21 Woodbury tail (32-wide): zy = Z_i . Y_j + Y_i . Z_j
   for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int k = kb * DK + lk + u;
-      As[lk + u][lr] = vi ? -Zb[(size_t)gi * 32 + k] : 0.0;
+      As[lk + u][lr] = vi ? Zb[(size_t)gi * 32 + k] : 0.0;
       Bs2[lk + u][lr] = vj ? Yb[(size_t)gj * 32 + k] : 0.0;
       As2[lk + u][lr] = vi ? Yb[(size_t)gi * 32 + k] : 0.0;
-      Bs[lk + u][lr] = vj ? -Zb[(size_t)gj * 32 + k] : 0.0;
+      Bs[lk + u][lr] = vj ? Zb[(size_t)gj * 32 + k] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -565,37 +539,39 @@ __global__ void __launch_bounds__(256) k_downdate(double* __restrict__ P, int n,
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          acc[u][v] = fma(a[u], b2[v], acc[u][v]);
-          acc2[u][v] = fma(a2[u], bb[v], acc2[u][v]);
-        }
+        for (int v = 0; v < 4; ++v) zy[u][v] = fma(a[u], b2[v], fma(a2[u], bb[v], zy[u][v]));
     }
     __syncthreads();
   }
-  // epilogue: P_ij <- (P_ij + P_ji)/2 - (acc + acc2)/2 for the tile pair; the CTA owns P(I,J) and P(J,I).
-  // stage P(J,I)^T through shared memory so that both global accesses are row-contiguous
+  // epilogue: the CTA owns P(I,J) and P(J,I); stage P(J,I)^T through shared memory (row-contiguous global accesses)
   double (*Pt)[DT + 1] = reinterpret_cast<double (*)[DT + 1]>(&sm[0][0][0]);
   static_assert(sizeof(sm) >= sizeof(double) * DT * (DT + 1), "staging tile does not fit");
   for (int e = t; e < DT * DT; e += 256) {
     const int r = e >> 6, c = e & 63;  // element (r, c) of block (J, I)
     const int gr = J * DT + r, gc = I * DT + c;
-    Pt[c][r] = (gr < n && gc < n) ? P[(size_t)gr * n + gc] : 0.0;  // Pt[i_local][j_local] = P(J,I)[j][i]
+    Pt[c][r] = (gr < n && gc < n) ? P[(size_t)gr * n + gc] : 0.0;
   }
   __syncthreads();
   double outv[4][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 4; ++a) {
+    const int r = ty * 4 + a, gr = I * DT + r;
+    const int oi = gr < n ? omega_inv[gr] : -1;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int r = ty * 4 + a, cc = tx * 4 + c;
-      const int gr = I * DT + r, gc = J * DT + cc;
+      const int cc = tx * 4 + c, gc = J * DT + cc;
       double v = 0.0;
       if (gr < n && gc < n) {
-        v = 0.5 * (P[(size_t)gr * n + gc] + Pt[r][cc]) - 0.5 * (acc[a][c] + acc2[a][c]);
+        const int oj = omega_inv[gc];
+        double q = 0.0;
+        if (oj >= 0) q += Qb[(size_t)gr * 32 + oj];
+        if (oi >= 0) q += Qb[(size_t)gc * 32 + oi];
+        v = 0.5 * (P[(size_t)gr * n + gc] + Pt[r][cc]) - acc[a][c] - 0.5 * q + 0.5 * zy[a][c];
         P[(size_t)gr * n + gc] = v;
       }
       outv[a][c] = v;
     }
+  }
   if (I != J) {
     __syncthreads();
 #pragma unroll
@@ -612,9 +588,9 @@ __global__ void __launch_bounds__(256) k_downdate(double* __restrict__ P, int n,
 }
 
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
-                  const int* tileflag, const double* Zb, const double* Yb) {
+                  const double* Zb, const double* Yb, const double* Qb) {
   const int nt = (n + DT - 1) / DT;
-  k_downdate<<<nt * (nt + 1) / 2, 256, 0, s>>>(P, n, T, m_pad, n_pad, omega_inv, tileflag, Zb, Yb);
+  k_downdate<<<nt * (nt + 1) / 2, 256, 0, s>>>(P, n, T, m_pad, n_pad, omega_inv, Zb, Yb, Qb);
   count_launch();
 }
 

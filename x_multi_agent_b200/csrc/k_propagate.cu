@@ -105,20 +105,31 @@ __global__ void __launch_bounds__(128) k_prop_means(double* __restrict__ xv, int
     for (int e = XV_ARR + t; e < LX; e += blockDim.x) x1[e] = x0[e];
   }
   __syncthreads();
-  if (t == 0) {
+  // the quaternion-integrator matrices depend on the IMU samples and the (static) gyro bias only: one thread per step
+  __shared__ double Dm[128][16];
+  if (t < n_steps) {
+    const double* s0 = xv + (size_t)((start + t) % NS) * LX;
+    const double* s1 = xv + (size_t)((start + t + 1) % NS) * LX;
+    double w1[3], w0[3];
+    for (int e = 0; e < 3; ++e) {  // State::computeUnbiasedImuMeasurements, state.cpp:177-182
+      w1[e] = s1[XV_WM + e] - s1[XV_BW + e];
+      w0[e] = s0[XV_WM + e] - s0[XV_BW + e];
+    }
+    quat_integrator(w0, w1, s1[XV_TIME] - s0[XV_TIME], Dm[t]);
+  }
+  __syncthreads();
+  if (t == 0) {  // the short sequential chain: q, v, p
     for (int k = 1; k <= n_steps; ++k) {
       const double* s0 = xv + (size_t)((start + k - 1) % NS) * LX;
       double* s1 = xv + (size_t)((start + k) % NS) * LX;
-      double w1[3], a1[3], w0[3], a0[3];
-      for (int e = 0; e < 3; ++e) {  // State::computeUnbiasedImuMeasurements, state.cpp:177-182
-        w1[e] = s1[XV_WM + e] - s1[XV_BW + e];
+      double a1[3], a0[3];
+      for (int e = 0; e < 3; ++e) {
         a1[e] = s1[XV_AM + e] - s1[XV_BA + e];
-        w0[e] = s0[XV_WM + e] - s0[XV_BW + e];
         a0[e] = s0[XV_AM + e] - s0[XV_BA + e];
       }
       const double dt = s1[XV_TIME] - s0[XV_TIME];
-      double D[16], q1[4];
-      quat_integrator(w0, w1, dt, D);
+      const double* D = Dm[k - 1];
+      double q1[4];
       for (int r = 0; r < 4; ++r)
         q1[r] = D[r * 4] * s0[XV_Q] + D[r * 4 + 1] * s0[XV_Q + 1] + D[r * 4 + 2] * s0[XV_Q + 2] + D[r * 4 + 3] * s0[XV_Q + 3];
       xb_qnormalize(q1);

@@ -238,35 +238,46 @@ __global__ void __launch_bounds__(1024) k_omega_small(int N, int m_pad, int n_pa
   if (t < NOM) om[NOM * NOM + t] = q[t];
 }
 
-// One warp per state row i:  Y1 = W1_i Vt^T, Y2f (Omega rows use W2), Z1 = Y1 C,
+// Omega tile <- W2_Omega - W1[Omega rows]  (dW: the rows on which W2 differs from W1)
+__global__ void k_omega_delta(int m_pad, int n_pad, const int* __restrict__ omega, double* __restrict__ T) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (c >= m_pad) return;
+  double* dst = T + (size_t)(m_pad + n_pad + 32 + k) * m_pad + c;
+  *dst -= T[(size_t)(m_pad + omega[k]) * m_pad + c];
+}
+// One warp per state row i:  Y1 = W1_i Vt^T, Y2 = W2_i Vt^T, Z1 = Y1 C, Q_i[k] = W1_i . dW_k,
 //   delta_i = W1_i z - Z1 . q - corr_i      (updater.cpp:127-129)
 __global__ void __launch_bounds__(128) k_omega_rowsolve(int N, int m_pad, int n_pad, const double* __restrict__ T,
                                                         const double* __restrict__ om, const int* __restrict__ omega_inv,
                                                         const double* __restrict__ corr, double* __restrict__ delta,
-                                                        double* __restrict__ Zb, double* __restrict__ Yb) {
+                                                        double* __restrict__ Zb, double* __restrict__ Yb,
+                                                        double* __restrict__ Qb) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N) return;
   const double* W1 = T + (size_t)(m_pad + i) * m_pad;
   const int ki = omega_inv[i];
-  const double* W2 = ki >= 0 ? T + (size_t)(m_pad + n_pad + 32 + ki) * m_pad : W1;
+  const double* dWi = ki >= 0 ? T + (size_t)(m_pad + n_pad + 32 + ki) * m_pad : nullptr;
+  const double* dW = T + (size_t)(m_pad + n_pad + 32) * m_pad;
   const double* Vt = T + (size_t)(m_pad + n_pad + 64) * m_pad;
   const double* z = T + (size_t)(m_pad + n_pad) * m_pad;
-  double y1[NOM], y2[NOM], wz = 0.0;
+  double y1[NOM], y2[NOM], qk[NOM], wz = 0.0;
 #pragma unroll
-  for (int k = 0; k < NOM; ++k) { y1[k] = 0.0; y2[k] = 0.0; }
+  for (int k = 0; k < NOM; ++k) { y1[k] = 0.0; y2[k] = 0.0; qk[k] = 0.0; }
   for (int c = lane; c < m_pad; c += 32) {
-    const double a = W1[c], b = W2[c];
+    const double a = W1[c];
+    const double b = dWi ? dWi[c] : 0.0;
     wz = fma(a, z[c], wz);
 #pragma unroll
     for (int k = 0; k < NOM; ++k) {
       const double v = Vt[(size_t)k * m_pad + c];
       y1[k] = fma(a, v, y1[k]);
       y2[k] = fma(b, v, y2[k]);
+      qk[k] = fma(a, dW[(size_t)k * m_pad + c], qk[k]);
     }
   }
   wz = xb_warp_sum(wz);
 #pragma unroll
-  for (int k = 0; k < NOM; ++k) { y1[k] = xb_warp_sum(y1[k]); y2[k] = xb_warp_sum(y2[k]); }
+  for (int k = 0; k < NOM; ++k) { y1[k] = xb_warp_sum(y1[k]); y2[k] = y1[k] + xb_warp_sum(y2[k]); qk[k] = xb_warp_sum(qk[k]); }
   // Z1[l] = sum_k y1[k] C[k][l]   (lane l)
   double zl = 0.0;
   if (lane < NOM)
@@ -274,12 +285,13 @@ __global__ void __launch_bounds__(128) k_omega_rowsolve(int N, int m_pad, int n_
     for (int k = 0; k < NOM; ++k) zl = fma(y1[k], om[k * NOM + lane], zl);
   double zq = (lane < NOM) ? zl * om[NOM * NOM + lane] : 0.0;
   zq = xb_warp_sum(zq);
-  double y2l = 0.0;
+  double y2l = 0.0, ql = 0.0;
 #pragma unroll
   for (int k = 0; k < NOM; ++k)
-    if (lane == k) y2l = y2[k];
+    if (lane == k) { y2l = y2[k]; ql = qk[k]; }
   Zb[(size_t)i * 32 + lane] = (lane < NOM) ? zl : 0.0;
   Yb[(size_t)i * 32 + lane] = (lane < NOM) ? y2l : 0.0;
+  Qb[(size_t)i * 32 + lane] = (lane < NOM) ? ql : 0.0;
   if (lane == 0) delta[i] = wz - zq - (corr ? corr[i] : 0.0);
 }
 
@@ -333,12 +345,17 @@ void launch_sym_lower(cudaStream_t s, double* T, int ld, int m) {
   k_sym_lower<<<g, b, 0, s>>>(T, ld, m);
   count_launch();
 }
-void launch_correct(cudaStream_t s, int M, int F, int N, const double* T, int m_pad, int n_pad, const double* P,
-                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* xv,
+void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
+                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* xv,
                     double* corr_total, double* delta_out) {
   k_omega_small<<<1, 1024, 0, s>>>(N, m_pad, n_pad, T, P, omega, om);
   count_launch();
-  k_omega_rowsolve<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, m_pad, n_pad, T, om, omega_inv, corr_total, delta_out, Zb, Yb);
+  {
+    dim3 g((m_pad + 127) / 128, NOM);
+    k_omega_delta<<<g, 128, 0, s>>>(m_pad, n_pad, omega, T);
+    count_launch();
+  }
+  k_omega_rowsolve<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, m_pad, n_pad, T, om, omega_inv, corr_total, delta_out, Zb, Yb, Qb);
   count_launch();
   launch_apply_delta(s, M, F, N, delta_out, xv, corr_total);
 }

@@ -24,7 +24,7 @@ void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
 void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
               const double* diag0 = nullptr, long long* trace = nullptr);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
-                  const int* tileflag, const double* Zb, const double* Yb);
+                  const double* Zb, const double* Yb, const double* Qb);
 void symmetrise(cudaStream_t s, double* P, int n);
 void gemv(cudaStream_t s, int rows, int cols, const double* A, int lda, const double* x, double* y);
 void transpose(cudaStream_t s, const double* in, double* out, int rows, int cols);
@@ -108,14 +108,14 @@ void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, co
 void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Lg, int ldr, const int* scols,
                        const double* svals, const int* omega, double* T);
 // Woodbury factors, delta = K r - corr_total ; State::correct ; corr_total += delta
-void launch_correct(cudaStream_t s, int M, int F, int N, const double* T, int m_pad, int n_pad, const double* P,
-                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* xv,
+void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
+                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* xv,
                     double* corr_total, double* delta_out);
 void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta, double* xv, double* corr_total);
 void launch_ci_cov(cudaStream_t s, double* P, int N, const double* K, const double* HP, int m);
 // 3xTF32 tcgen05 tensor-core covariance downdate (k_downdate_tc.cu)
 void downdate_tc(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
-                 const int* tileflag, const double* Zb, const double* Yb, void* ws);
+                 const double* Zb, const double* Yb, const double* Qb, void* ws);
 
 // StateManager::manage arithmetic: P' = A P A^T as one gather pass + thin products (k_manage.cu)
 void launch_manage_dev(cudaStream_t s, int M, int F, int N, int n_poses, int n_features, int slide, int n_reanch,
