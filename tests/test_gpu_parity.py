@@ -415,3 +415,36 @@ def test_compressed_ci_payload_exchange_equals_full_state_exchange():
     rp.done()
     for d in (dev0, dev1, twin):
         d.close()
+
+
+@pytest.mark.parametrize("cfg,frames", [(SynthConfig(M=6, F=6, K=12, seed=1), 9), (SynthConfig(M=30, F=40, K=60, seed=0), 33)])
+def test_tensor_core_downdate_is_fp32_accurate(cfg, frames):
+    """Optional tcgen05 (3xTF32, fp32 accumulators in TMEM) covariance downdate vs the default fp64 path.
+    The contraction W W^T is fp32-accurate relative to the PRIOR covariance scale (P+ = P - W W^T cancels):
+    tolerance ||dP||_F/||P||_F <= 2e-5 and |dP_ij| <= 2e-5 sqrt(Pprior_ii Pprior_jj); measured ~7e-6."""
+    ora, m, s = _stage_setup(cfg, frames)
+    sm = ora.upd.sm
+    devs = [make_filter(cfg, downdate_precision=p) for p in (0, 1)]
+    out, prior = [], None
+    for dev in devs:
+        dev.work_set(State.from_oracle(s))
+        dev.sm_set(sm.n_poses, sm.n_features, sm.anchor_idxs, sm.filled_before)
+        dev.set_measurement(m)
+        dev.manage(m.lost_slam_trk_idxs)
+        prior = dev.work_get().cov
+        dev.construct_update(0)
+        dev.reset_correction()
+        dev.apply_constructed(True)
+        out.append(dev.work_get())
+        dev.synchronize()
+    P0, P1 = out[0].cov, out[1].cov
+    rp = Report()
+    rp.check("tc vs fp64 cov (Frobenius)", rel(P1, P0), 2e-5)
+    d = np.sqrt(np.abs(np.diag(prior)))
+    act = d > 0
+    rp.check("tc vs fp64 cov (component-wise, prior scale)", np.abs((P1 - P0)[np.ix_(act, act)] / np.outer(d[act], d[act])).max(), 2e-5)
+    rp.check("tc state identical (correction does not use the downdate)", np.abs(out[0].x - out[1].x).max(), 0.0)
+    rp.check("tc P symmetric", np.abs(P1 - P1.T).max(), 0.0)
+    rp.done()
+    for dev in devs:
+        dev.close()

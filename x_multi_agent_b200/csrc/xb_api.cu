@@ -407,7 +407,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   }
   f->Hdense_doubles = (size_t)m_pad * N + 2 * (size_t)m_pad + 64;
   DA(f->d_Hdense, f->Hdense_doubles, double);
-  DA(f->d_tcws, (size_t)n_pad * m_pad * 3 * 4 + 1024, char);
+  DA(f->d_tcws, downdate_tc_workspace_bytes(N, m_pad), char);
 
   // pinned staging: measurement lists + manage tables
   f->pin_bytes = sizeof(double) * (2 * (size_t)(maxO * 2 + maxO1 * 2 + std::max(1, F) * 4 * M) + (size_t)LX + 4096) +

@@ -114,6 +114,7 @@ void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, i
 void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta, double* xv, double* corr_total);
 void launch_ci_cov(cudaStream_t s, double* P, int N, const double* K, const double* HP, int m);
 // 3xTF32 tcgen05 tensor-core covariance downdate (k_downdate_tc.cu)
+size_t downdate_tc_workspace_bytes(int n, int m_pad);
 void downdate_tc(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                  const double* Zb, const double* Yb, const double* Qb, void* ws);
 
