@@ -275,6 +275,9 @@ def main():
             e2e_s += t1 - t0
     barrier()
     assert np.all(np.isfinite(st.x)), "non-finite state after the benchmark"
+    inl0 = flt.debug_int("inlier0", CFG2["K"])
+    msckf_inlier_frac = float(inl0.mean()) if len(inl0) else None
+    slam_inlier_frac = float(flt.debug_int("slam_inlier", CFG2["F"]).mean())
     # ---- phase C (N > 1): covariance-intersection fusion steps with the compressed payload exchanged over NCCL ----
     ci = None
     if world > 1:
@@ -369,7 +372,8 @@ def main():
                     "h2d_bytes_per_step": int(np.mean([p.h2d_bytes for p in packed])) + 4 * (795 + 16 * 6 + 2 * 200),
                     "d2h_bytes_per_step": flt.LX * 8},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci}
+            "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci,
+            "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac}}
     print(json.dumps(line))
     flt.close()
     if world > 1:

@@ -10,7 +10,7 @@
 //
 // Operands.  With W1 the TRSM'd rows of the tall buffer and Z, Y the rank-21 Woodbury factors (k_update.cu)
 //     K A2^T (symmetrised) = W1 W1^T - (Z Y^T + Y Z^T)/2 + Omega lookups
-//                          = [W1 | (Z+Y)/2 | (Z-Y)/2] [W1 | -(Z+Y)/2 | (Z-Y)/2]^T + Omega lookups
+//                          = [W1 | Z | Y] [W1 | -Y/2 | -Z/2]^T + Omega lookups
 // so one GEMM  C = A B^T  with K' = m_pad + 64 covers everything but the Omega lookups (epilogue).
 // k_tc_stage writes the hi/lo fp32 operand matrices once; k_downdate_tc is one CTA per upper-triangular 128x128
 // tile: operands are staged into shared memory in the canonical K-major SWIZZLE_128B layout (8 rows x 128 B atoms,
@@ -32,7 +32,7 @@ __device__ __forceinline__ float to_tf32(double x) {
   return __uint_as_float(u);
 }
 
-// fp64 -> (hi, lo) TF32 pairs for A = [W1 | (Z+Y)/2 | (Z-Y)/2] and B = [W1 | -(Z+Y)/2 | (Z-Y)/2]; rows >= n are zero.
+// fp64 -> (hi, lo) TF32 pairs for A = [W1 | Z | Y] and B = [W1 | -Y/2 | -Z/2]; rows >= n are zero.
 __global__ void k_tc_stage(int n, int n128, int m_pad, int Kp, const double* __restrict__ W1, const double* __restrict__ Zb,
                            const double* __restrict__ Yb, float* __restrict__ Ahi, float* __restrict__ Alo,
                            float* __restrict__ Bhi, float* __restrict__ Blo) {
@@ -41,8 +41,8 @@ __global__ void k_tc_stage(int n, int n128, int m_pad, int Kp, const double* __r
   double a = 0.0, b = 0.0;
   if (i < n) {
     if (k < m_pad) { a = W1[(size_t)i * m_pad + k]; b = a; }
-    else if (k < m_pad + 32) { const int c = k - m_pad; a = 0.5 * (Zb[(size_t)i * 32 + c] + Yb[(size_t)i * 32 + c]); b = -a; }
-    else { const int c = k - m_pad - 32; a = 0.5 * (Zb[(size_t)i * 32 + c] - Yb[(size_t)i * 32 + c]); b = a; }
+    else if (k < m_pad + 32) { const int c = k - m_pad; a = Zb[(size_t)i * 32 + c]; b = -0.5 * Yb[(size_t)i * 32 + c]; }
+    else { const int c = k - m_pad - 32; a = Yb[(size_t)i * 32 + c]; b = -0.5 * Zb[(size_t)i * 32 + c]; }
   }
   const float ah = to_tf32(a), bh = to_tf32(b);
   const size_t o = (size_t)i * Kp + k;

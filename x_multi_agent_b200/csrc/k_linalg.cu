@@ -14,11 +14,15 @@ namespace xb {
 // 64x64x16 tiles, 256 threads, 4x4 register micro-tile.
 // ------------------------------------------------------------------------------------------------
 template <bool TRANS_B>
-__global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha, const double* __restrict__ A,
+__global__ void __launch_bounds__(256) k_gemm(int M, int N, int Kfull, double alpha, const double* __restrict__ A,
                                               int lda, const double* __restrict__ B, int ldb, double beta,
-                                              double* __restrict__ C, int ldc) {
+                                              double* __restrict__ C, int ldc, int kchunk, size_t strideC) {
   __shared__ double As[16][64 + 4];
   __shared__ double Bs[16][64 + 4];
+  // split-K: blockIdx.z handles k in [z*kchunk, min(K, (z+1)*kchunk)) and writes its own partial C + z*strideC
+  const int kbeg = blockIdx.z * kchunk;
+  const int K = min(Kfull, kbeg + kchunk);
+  C += (size_t)blockIdx.z * strideC;
   const int t = threadIdx.x;
   const int ty = t >> 4, tx = t & 15;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
@@ -27,35 +31,31 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha,
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    {  // A tile: 64 rows x 16 k
-      const int r = t >> 2, kk = (t & 3) * 4;
-      const int gr = m0 + r;
+  // register-prefetched K slabs: the global loads of slab k+1 are in flight while slab k is multiplied
+  double ra[4], rb[4];
+  const int ar = t >> 2, ak = (t & 3) * 4;      // A tile (and B^T tile): row, first k
+  const int bk = t >> 4, bc = (t & 15) * 4;     // B tile (non-transposed): k, first column
+  auto gload = [&](int k0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int gk = k0 + kk + u;
-        As[kk + u][r] = (gr < M && gk < K) ? A[(size_t)gr * lda + gk] : 0.0;
-      }
+    for (int u = 0; u < 4; ++u) {
+      const int gk = k0 + ak + u;
+      ra[u] = (m0 + ar < M && gk < K) ? A[(size_t)(m0 + ar) * lda + gk] : 0.0;
+      if (TRANS_B) rb[u] = (n0 + ar < N && gk < K) ? B[(size_t)(n0 + ar) * ldb + gk] : 0.0;
+      else rb[u] = (k0 + bk < K && n0 + bc + u < N) ? B[(size_t)(k0 + bk) * ldb + n0 + bc + u] : 0.0;
     }
-    if (TRANS_B) {
-      const int r = t >> 2, kk = (t & 3) * 4;
-      const int gr = n0 + r;
+  };
+  auto sstore = [&]() {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int gk = k0 + kk + u;
-        Bs[kk + u][r] = (gr < N && gk < K) ? B[(size_t)gr * ldb + gk] : 0.0;
-      }
-    } else {
-      const int kk = t >> 4, c = (t & 15) * 4;
-      const int gk = k0 + kk;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int gc = n0 + c + u;
-        Bs[kk][c + u] = (gk < K && gc < N) ? B[(size_t)gk * ldb + gc] : 0.0;
-      }
+    for (int u = 0; u < 4; ++u) {
+      As[ak + u][ar] = ra[u];
+      if (TRANS_B) Bs[ak + u][ar] = rb[u]; else Bs[bk][bc + u] = rb[u];
     }
-    __syncthreads();
+  };
+  gload(kbeg);
+  sstore();
+  __syncthreads();
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
+    if (k0 + 16 < K) gload(k0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       double a[4], b[4];
@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha,
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
+    __syncthreads();
+    if (k0 + 16 < K) sstore();
     __syncthreads();
   }
 #pragma unroll
@@ -88,14 +90,22 @@ void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
   dim3 grid((N + 63) / 64, (M + 63) / 64);
-  k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  count_launch();
+}
+// C_z = A[:, kz] B[:, kz]^T for nz K-chunks (partials at C + z*strideC; the consumer sums them in a fixed order)
+void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
+                    int ldc, size_t strideC, int nz) {
+  const int kchunk = ((K + nz - 1) / nz + 15) / 16 * 16;
+  dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
+  k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   count_launch();
 }
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
   dim3 grid((N + 63) / 64, (M + 63) / 64);
-  k_gemm<false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  k_gemm<false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   count_launch();
 }
 

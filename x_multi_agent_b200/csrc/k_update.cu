@@ -22,6 +22,7 @@
 namespace xb {
 
 #define NOM 21  // |Omega| = 15 core + 6 clone states
+#define CBZ 4   // split-K partials of the thin Woodbury GEMM
 
 // PHt[i, ms + 2j + r] = sum_e P[i, col_e] * val[j][r][e]
 __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int* __restrict__ scols,
@@ -166,30 +167,25 @@ __global__ void k_sym_lower(double* __restrict__ T, int ld, int m) {
   if (r < m && c < r) T[(size_t)r * ld + c] = 0.5 * (T[(size_t)r * ld + c] + T[(size_t)c * ld + r]);
 }
 
-// After the tile Cholesky: G = Vt Vt^T, q = Vt z, E from P, C = E (I + G E)^-1.   om = [C 21x21 | q 21]
-__global__ void __launch_bounds__(1024) k_omega_small(int N, int m_pad, int n_pad, const double* __restrict__ T,
+// After the tile Cholesky and the thin GEMM  Cb = [W1 ; aux ; dW ; Vt] [z ; dW ; Vt]^T  (rows n_pad+64+k of Cb hold
+// Vt_k . {z, dW, Vt}):  G = Vt Vt^T, q = Vt z, E from P, C = E (I + G E)^-1.   om = [C 21x21 | q 21]
+__global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const double* __restrict__ Cb,
                                                      const double* __restrict__ P, const int* __restrict__ omega,
                                                      double* __restrict__ om) {
   __shared__ double G[NOM][NOM], E[NOM][NOM], A[NOM][2 * NOM + 1], q[NOM];
   __shared__ int piv;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const double* Vt = T + (size_t)(m_pad + n_pad + 64) * m_pad;
-  const double* z = T + (size_t)(m_pad + n_pad) * m_pad;
-  const int nwarps = blockDim.x >> 5;
-  for (int e = w; e < NOM * NOM + NOM; e += nwarps) {  // one warp per dot product
-    const int k = e / NOM, l = e % NOM;
-    const double* a = Vt + (size_t)(e < NOM * NOM ? k : e - NOM * NOM) * m_pad;
-    const double* b = e < NOM * NOM ? Vt + (size_t)l * m_pad : z;
-    double s = 0.0;
-    for (int c = lane; c < m_pad; c += 32) s = fma(a[c], b[c], s);
-    s = xb_warp_sum(s);
-    if (lane == 0) {
-      if (e < NOM * NOM) G[k][l] = s; else q[e - NOM * NOM] = s;
-    }
-  }
+  const int t = threadIdx.x;
   for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int k = e / NOM, l = e % NOM;
+    double g = 0.0;
+    for (int z = 0; z < CBZ; ++z) g += Cb[(size_t)z * (n_pad + 96) * 96 + (size_t)(n_pad + 64 + k) * 96 + 64 + l];
+    G[k][l] = g;
     E[k][l] = 0.5 * (P[(size_t)omega[k] * N + omega[l]] - P[(size_t)omega[l] * N + omega[k]]);
+  }
+  if (t < NOM) {
+    double g = 0.0;
+    for (int z = 0; z < CBZ; ++z) g += Cb[(size_t)z * (n_pad + 96) * 96 + (size_t)(n_pad + 64 + t) * 96];
+    q[t] = g;
   }
   __syncthreads();
   // A = [I + G E | I]
@@ -245,53 +241,37 @@ __global__ void k_omega_delta(int m_pad, int n_pad, const int* __restrict__ omeg
   double* dst = T + (size_t)(m_pad + n_pad + 32 + k) * m_pad + c;
   *dst -= T[(size_t)(m_pad + omega[k]) * m_pad + c];
 }
-// One warp per state row i:  Y1 = W1_i Vt^T, Y2 = W2_i Vt^T, Z1 = Y1 C, Q_i[k] = W1_i . dW_k,
+// One warp per state row i, fed by Cb:  Y1 = W1_i Vt^T (cols 64..), Q_i = W1_i dW^T (cols 32..), W1_i.z (col 0);
+// Omega rows add dW_k(i) Vt^T (rows n_pad+32+k of Cb):  Y2 = W2_i Vt^T, Z1 = Y1 C,
 //   delta_i = W1_i z - Z1 . q - corr_i      (updater.cpp:127-129)
-__global__ void __launch_bounds__(128) k_omega_rowsolve(int N, int m_pad, int n_pad, const double* __restrict__ T,
-                                                        const double* __restrict__ om, const int* __restrict__ omega_inv,
-                                                        const double* __restrict__ corr, double* __restrict__ delta,
-                                                        double* __restrict__ Zb, double* __restrict__ Yb,
-                                                        double* __restrict__ Qb) {
+__global__ void __launch_bounds__(128) k_omega_finish(int N, int n_pad, const double* __restrict__ Cb,
+                                                      const double* __restrict__ om, const int* __restrict__ omega_inv,
+                                                      const double* __restrict__ corr, double* __restrict__ delta,
+                                                      double* __restrict__ Zb, double* __restrict__ Yb,
+                                                      double* __restrict__ Qb) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N) return;
-  const double* W1 = T + (size_t)(m_pad + i) * m_pad;
+  const size_t zs = (size_t)(n_pad + 96) * 96;
+  const double* ci = Cb + (size_t)i * 96;
   const int ki = omega_inv[i];
-  const double* dWi = ki >= 0 ? T + (size_t)(m_pad + n_pad + 32 + ki) * m_pad : nullptr;
-  const double* dW = T + (size_t)(m_pad + n_pad + 32) * m_pad;
-  const double* Vt = T + (size_t)(m_pad + n_pad + 64) * m_pad;
-  const double* z = T + (size_t)(m_pad + n_pad) * m_pad;
-  double y1[NOM], y2[NOM], qk[NOM], wz = 0.0;
-#pragma unroll
-  for (int k = 0; k < NOM; ++k) { y1[k] = 0.0; y2[k] = 0.0; qk[k] = 0.0; }
-  for (int c = lane; c < m_pad; c += 32) {
-    const double a = W1[c];
-    const double b = dWi ? dWi[c] : 0.0;
-    wz = fma(a, z[c], wz);
-#pragma unroll
-    for (int k = 0; k < NOM; ++k) {
-      const double v = Vt[(size_t)k * m_pad + c];
-      y1[k] = fma(a, v, y1[k]);
-      y2[k] = fma(b, v, y2[k]);
-      qk[k] = fma(a, dW[(size_t)k * m_pad + c], qk[k]);
-    }
+  double y1 = 0.0, ql = 0.0, wz = 0.0, y2 = 0.0;
+  for (int z = 0; z < CBZ; ++z) {  // fixed-order sum of the split-K partials
+    if (lane < NOM) { y1 += ci[z * zs + 64 + lane]; ql += ci[z * zs + 32 + lane]; }
+    wz += ci[z * zs];
+    if (ki >= 0 && lane < NOM) y2 += Cb[z * zs + (size_t)(n_pad + 32 + ki) * 96 + 64 + lane];
   }
-  wz = xb_warp_sum(wz);
-#pragma unroll
-  for (int k = 0; k < NOM; ++k) { y1[k] = xb_warp_sum(y1[k]); y2[k] = y1[k] + xb_warp_sum(y2[k]); qk[k] = xb_warp_sum(qk[k]); }
-  // Z1[l] = sum_k y1[k] C[k][l]   (lane l)
+  y2 += y1;
   double zl = 0.0;
-  if (lane < NOM)
 #pragma unroll
-    for (int k = 0; k < NOM; ++k) zl = fma(y1[k], om[k * NOM + lane], zl);
+  for (int k = 0; k < NOM; ++k) {
+    const double yk = __shfl_sync(0xffffffffu, y1, k);
+    if (lane < NOM) zl = fma(yk, om[k * NOM + lane], zl);
+  }
   double zq = (lane < NOM) ? zl * om[NOM * NOM + lane] : 0.0;
   zq = xb_warp_sum(zq);
-  double y2l = 0.0, ql = 0.0;
-#pragma unroll
-  for (int k = 0; k < NOM; ++k)
-    if (lane == k) { y2l = y2[k]; ql = qk[k]; }
   Zb[(size_t)i * 32 + lane] = (lane < NOM) ? zl : 0.0;
-  Yb[(size_t)i * 32 + lane] = (lane < NOM) ? y2l : 0.0;
-  Qb[(size_t)i * 32 + lane] = (lane < NOM) ? ql : 0.0;
+  Yb[(size_t)i * 32 + lane] = (lane < NOM) ? y2 : 0.0;
+  Qb[(size_t)i * 32 + lane] = ql;
   if (lane == 0) delta[i] = wz - zq - (corr ? corr[i] : 0.0);
 }
 
@@ -346,16 +326,19 @@ void launch_sym_lower(cudaStream_t s, double* T, int ld, int m) {
   count_launch();
 }
 void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
-                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* xv,
-                    double* corr_total, double* delta_out) {
-  k_omega_small<<<1, 1024, 0, s>>>(N, m_pad, n_pad, T, P, omega, om);
-  count_launch();
+                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* Cb,
+                    double* xv, double* corr_total, double* delta_out) {
   {
     dim3 g((m_pad + 127) / 128, NOM);
     k_omega_delta<<<g, 128, 0, s>>>(m_pad, n_pad, omega, T);
     count_launch();
   }
-  k_omega_rowsolve<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, m_pad, n_pad, T, om, omega_inv, corr_total, delta_out, Zb, Yb, Qb);
+  // Cb[(n_pad + 96) x 96] = [W1 ; aux ; dW ; Vt] * [aux ; dW ; Vt]^T : every dot product the Woodbury step needs
+  gemm_nt_splitk(s, n_pad + 96, 96, m_pad, T + (size_t)m_pad * m_pad, m_pad, T + (size_t)(m_pad + n_pad) * m_pad, m_pad, Cb, 96,
+                 (size_t)(n_pad + 96) * 96, CBZ);
+  k_omega_small<<<1, 256, 0, s>>>(N, n_pad, Cb, P, omega, om);
+  count_launch();
+  k_omega_finish<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, n_pad, Cb, om, omega_inv, corr_total, delta_out, Zb, Yb, Qb);
   count_launch();
   launch_apply_delta(s, M, F, N, delta_out, xv, corr_total);
 }

@@ -174,7 +174,7 @@ struct xb_filter {
   void* d_tcws = nullptr;
   // Omega (core + newest clone) bookkeeping for the non-symmetric part of P
   int *d_omega = nullptr, *d_omega_inv = nullptr, *d_tileflag = nullptr;
-  double *d_om = nullptr, *d_Zb = nullptr, *d_Yb = nullptr, *d_Qb = nullptr;
+  double *d_om = nullptr, *d_Zb = nullptr, *d_Yb = nullptr, *d_Qb = nullptr, *d_Cb = nullptr;
   // covariance intersection
   double *d_ci_own = nullptr, *d_ci_gather = nullptr, *d_ci_rec = nullptr, *d_ci_K = nullptr, *d_ci_delta = nullptr, *d_ci_HP = nullptr;
   int *d_ci_matches = nullptr, *d_ci_last = nullptr;
@@ -390,6 +390,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_Zb, (size_t)n_pad * 32, double);
   DA(f->d_Yb, (size_t)n_pad * 32, double);
   DA(f->d_Qb, (size_t)n_pad * 32, double);
+  DA(f->d_Cb, (size_t)4 * (n_pad + 96) * 96, double);
   DA(f->d_err, 4, int);
   if (getenv("XB_CHOL_TRACE")) DA(f->d_trace, 6 * ((size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64), long long);
 
@@ -934,7 +935,7 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
   {
     StageTimer st_(f, ST_CORRECT);
     launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
-                   f->d_Yb, f->d_Qb, f->d_xw, corr_total, f->d_delta);
+                   f->d_Yb, f->d_Qb, f->d_Cb, f->d_xw, corr_total, f->d_delta);
   }
   if (cov_update) {
     StageTimer st_(f, ST_DOWNDATE);

@@ -21,6 +21,8 @@ void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
              double beta, double* C, int ldc);
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc);
+void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
+                    int ldc, size_t strideC, int nz);
 void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
               const double* diag0 = nullptr, long long* trace = nullptr);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
@@ -109,8 +111,8 @@ void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, con
                        const double* svals, const int* omega, double* T);
 // Woodbury factors, delta = K r - corr_total ; State::correct ; corr_total += delta
 void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
-                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* xv,
-                    double* corr_total, double* delta_out);
+                    const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* Cb,
+                    double* xv, double* corr_total, double* delta_out);
 void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta, double* xv, double* corr_total);
 void launch_ci_cov(cudaStream_t s, double* P, int N, const double* K, const double* HP, int m);
 // 3xTF32 tcgen05 tensor-core covariance downdate (k_downdate_tc.cu)
