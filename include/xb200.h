@@ -75,7 +75,8 @@ typedef struct xb_config {
   double sigma_img, sigma_range, rho_0, sigma_rho_0;
   double sigma_landmark, ci_msckf_w, ci_slam_w;
   int downdate_precision; /* 0 = fp64 CUDA cores, 1 = 3xTF32 tcgen05 tensor-core downdate */
-  int reserved;
+  int multi_uav;          /* 1 = Updater::update as compiled with -DMULTI_UAV (updater.cpp:58-97): CI lists of the
+                           * MSCKF-MSCKF matches first, one applyUpdate, no IEKF loop; 0 = single-UAV build */
 } xb_config;
 
 /* One track list in CSR form: track t owns observations [off[t], off[t+1]) of `obs`, each
@@ -119,10 +120,11 @@ typedef struct xb_slam_match {   /* SlamMatch, include/x/vision/types.h:102-116 
 } xb_slam_match;
 
 typedef struct xb_msckf_match {  /* MsckfMatch, include/x/vision/types.h:83-100 */
-  int peer;
-  int id_current_track;          /* index into the msckf / msckf_short list it refers to */
+  int peer;                      /* index into the peers array / slot of the gathered pose payloads */
+  int which;                     /* list the own track is in: 0 = msckf_trks_, 1 = msckf_short_trks_ */
+  int id_current_track;          /* index of the own track in that list (stands for Track::getId) */
   int n_obs;
-  const double* obs;             /* 2*n_obs, the peer's track */
+  const double* obs;             /* 2*n_obs, the peer's track (received_track_ptr), oldest first */
 } xb_msckf_match;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -156,6 +158,17 @@ XB_API int xb_ekf_process_others(xb_filter* f, double timestamp, const xb_peer_s
  * xb_ekf_process_update (VioUpdater::msckf_matches_, vio_updater.cpp:185). */
 XB_API int xb_vio_set_msckf_matches(xb_filter* f, const xb_peer_state* peers, int n_peers,
                              const xb_msckf_match* matches, int n_matches);
+/* Same with the peers given as gathered pose payloads resident on the device (one slot of
+ * xb_ci_pose_payload_len doubles per agent): [8 header | 3M camera positions | 4M attitudes | 6M x 6M pose block
+ * of the covariance] -- all a peer contributes to msckf_update.cpp:175-279. */
+XB_API int xb_vio_set_msckf_matches_packed(xb_filter* f, const double* dev_gathered, int n_agents,
+                                    const xb_msckf_match* matches, int n_matches);
+XB_API int xb_ci_pose_payload_len(const xb_filter* f);
+XB_API int xb_ci_pack_poses(xb_filter* f, int slot, double* dev_payload);
+/* Per consumed match group of the last update: out[3*j..] = (inlier, gamma, chi2); returns the group count. */
+XB_API int xb_mm_last_gates(xb_filter* f, int which, double* out, int max_groups);
+/* Updater::applyCI over the (S, P_j, H, res) lists of the last xb_vio_construct_update (updater.cpp:64-69,88-92). */
+XB_API int xb_updater_apply_ci_lists(xb_filter* f);
 /* State getters on the newest state / on ring slot `slot` (state.h:74-115). slot<0: newest. */
 XB_API int xb_ekf_get_state(xb_filter* f, int slot, double* xvec_out);
 XB_API int xb_ekf_get_covariance(xb_filter* f, int slot, double* cov_out, int cov_layout);

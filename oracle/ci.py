@@ -136,16 +136,30 @@ class MsckfMatch:
     received_track: np.ndarray  # (L_peer, 2)
 
 
-def multi_msckf_one_track(track, track_id, quats, poss, P, n_poses_max, sigma_img, matches, ci_msckf_w,
-                          max_iter=10, term=1e-5):
+def consume_matches(matches, track_id):
+    """The match-collection loop of preProcessOneTrack (msckf_update.cpp:96-139) on the SHARED, mutable list:
+    matches of `track_id` are moved out of `matches`.  The loop bound is re-evaluated while the list shrinks and the
+    index is corrected by the number of erasures, so of several matches sitting at the tail of the list only some are
+    visited (e.g. [a(t), b(t)] consumes a only) -- restated as written."""
+    mine = []
+    corrected = 0
+    i = 0
+    while i < len(matches):
+        if matches[i - corrected].id_current_track == track_id:
+            mine.append(matches.pop(i - corrected))
+            corrected += 1
+        i += 1
+    return mine
+
+
+def multi_msckf_one_track(track, mine, quats, poss, P, n_poses_max, sigma_img, ci_msckf_w, max_iter=10, term=1e-5):
     """Joint multi-agent MSCKF block for ONE own track (msckf_update.cpp:65-281, MULTI_UAV build).
 
-    Returns dict(own=(inlier, gamma), multi=None | (S_j, P_j, h_j, res_pf)).  `matches` is the list of
-    MsckfMatch whose id_current_track == track_id (the reference erases them from the shared list, :137)."""
+    `mine` = the MsckfMatch entries consume_matches() moved out of the shared list for this track.
+    Returns dict(own=(inlier, gamma), jac0, res0, multi=None | (S_j, P_j, h_j, res_pf))."""
     var_img = sigma_img * sigma_img
     track = np.asarray(track, dtype=float)
     L = track.shape[0]
-    mine = [m for m in matches if m.id_current_track == track_id]
     tmp_q, tmp_p, tmp_trk = [], [], []
     sizes = [P.shape[1]]
     for m in mine:  # :96-139 -- peers first, own poses last
@@ -172,13 +186,13 @@ def multi_msckf_one_track(track, track_id, quats, poss, P, n_poses_max, sigma_im
 
     own = project(track, quats, poss, n_poses_max, P.shape[1])
     if own is None:
-        return dict(own=(False, np.nan), multi=None)
+        return dict(own=(False, np.nan), multi=None, ivd=ivd, G_p_f=G_p_fj, n_matched=len(mine))
     jac_j, Hf_j, res_j, A_up, A = own
     res0, jac0 = A.T @ res_j, A.T @ jac_j
     S = jac0 @ P @ jac0.T + var_img * np.eye(2 * L - 3)
     gamma = float(res0 @ np.linalg.inv(S) @ res0)
     inl = gamma < chi2_quantile(0.95, 2.0 * L - 3.0)
-    result = dict(own=(inl, gamma), multi=None, jac0=jac0, res0=res0)
+    result = dict(own=(inl, gamma), multi=None, jac0=jac0, res0=res0, ivd=ivd, G_p_f=G_p_fj, n_matched=len(mine))
     if not (inl and mine):
         return result
     k = len(mine)
@@ -227,6 +241,50 @@ def multi_msckf_one_track(track, track_id, quats, poss, P, n_poses_max, sigma_im
             P_j[c:c + 3, c:c + 3] *= w_result
         result["multi"] = (S_ci, P_j, h_j, res_pf)
     return result
+
+
+class MultiMsckfUpdate:
+    """MsckfUpdate of the MULTI_UAV build (msckf_update.cpp:27-63 with `tracks_matches`): same stacked (jac, res,
+    cov_m_diag) as the single-agent class -- except that matched tracks are triangulated jointly with the peers'
+    observations -- plus the (S, P_j, H, res) lists consumed by Updater::applyCI.  `track_ids[j]` is what
+    MsckfMatch.id_current_track is compared with (Track::getId, :98); `matches` is mutated like the reference's."""
+
+    def __init__(self, trks, track_ids, quats, poss, P, n_poses_max, sigma_img, matches, ci_msckf_w):
+        n_trks = len(trks)
+        n_obs = sum(np.asarray(t).shape[0] for t in trks)
+        rows = 2 * n_obs - 3 * n_trks
+        cols = P.shape[1]
+        self.jac = np.zeros((rows, cols))
+        self.cov_m_diag = np.ones(rows)
+        self.res = np.zeros(rows)
+        self.inlier = np.zeros(n_trks, dtype=bool)
+        self.gamma = np.full(n_trks, np.nan)
+        self.G_p_f = np.full((n_trks, 3), np.nan)
+        self.n_matched = np.zeros(n_trks, dtype=int)
+        self.multi_gate = {}
+        self.S_list, self.P_list, self.H_list, self.res_list = [], [], [], []
+        var_img = sigma_img * sigma_img
+        row_h = 0
+        for j, trk in enumerate(trks):
+            trk = np.asarray(trk, dtype=float)
+            L = trk.shape[0]
+            mine = consume_matches(matches, track_ids[j])
+            out = multi_msckf_one_track(trk, mine, quats, poss, P, n_poses_max, sigma_img, ci_msckf_w)
+            self.G_p_f[j] = out["G_p_f"]
+            self.n_matched[j] = out["n_matched"]
+            inl, gamma = out["own"]
+            self.inlier[j], self.gamma[j] = inl, gamma
+            if inl:
+                self.jac[row_h:row_h + 2 * L - 3] = out["jac0"]
+                self.res[row_h:row_h + 2 * L - 3] = out["res0"]
+                self.cov_m_diag[row_h:row_h + 2 * L - 3] = var_img
+                row_h += 2 * L - 3
+            if "multi_gate" in out:
+                self.multi_gate[j] = out["multi_gate"]
+            if out["multi"] is not None:
+                S_j, P_j, h_j, res_pf = out["multi"]
+                self.S_list.append(S_j); self.P_list.append(P_j); self.H_list.append(h_j); self.res_list.append(res_pf)
+        self.rows_used = row_h
 
 
 # ---- compressed payload (test infrastructure for the multi-agent exchange, SURVEY 8e) ------------------------

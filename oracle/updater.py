@@ -68,7 +68,10 @@ class VisualMeasurement:
 class VioUpdaterOracle:
     """Restates Updater::update (updater.cpp:39-115, single-UAV build) with VioUpdater's overrides."""
 
-    def __init__(self, n_poses_max, n_features_max, sigma_img, rho_0=0.5, sigma_rho_0=0.25, iekf_iter=1):
+    def __init__(self, n_poses_max, n_features_max, sigma_img, rho_0=0.5, sigma_rho_0=0.25, iekf_iter=1,
+                 ci_msckf_w=0.1):
+        self.ci_msckf_w = ci_msckf_w
+        self.msckf_matches = []  # VioUpdater::msckf_matches_ (vio_updater.h:282), consumed by the constructors
         self.sm = StateManager(n_poses_max, n_features_max)
         self.sigma_img = sigma_img
         self.rho_0 = rho_0
@@ -105,6 +108,51 @@ class VioUpdaterOracle:
         r_diag = np.concatenate([msckf.cov_m_diag, msckf_slam.cov_m_diag, slam.cov_m_diag])
         res = np.concatenate([msckf.res, msckf_slam.res, slam.res])
         return apply_qr_decomposition(h, res, r_diag, self.sigma_img)
+
+    # ---- MULTI_UAV build: vio_updater.cpp:217-264 / 266-423 with the four CI lists -------------------------
+    def _construct_multi(self, state, which):
+        from .ci import MultiMsckfUpdate
+        quats = self.sm.camera_attitudes(state)
+        poss = self.sm.camera_positions(state)
+        P = state.cov
+        M = state.n_poses_max()
+        trks = self.meas.msckf_short_trks if which == 1 else self.meas.msckf_trks
+        ids = [(which, j) for j in range(len(trks))]
+        msckf = MultiMsckfUpdate(trks, ids, quats, poss, P, M, self.sigma_img, self.msckf_matches, self.ci_msckf_w)
+        lists = (msckf.S_list, msckf.P_list, msckf.H_list, msckf.res_list)
+        if which == 1:
+            self.last["short"] = msckf
+            return apply_qr_decomposition(msckf.jac, msckf.res, msckf.cov_m_diag, self.sigma_img), lists
+        msckf_slam = MsckfSlamUpdate(self.meas.new_msckf_slam_trks, quats, poss, P, M, self.sigma_img)
+        slam = SlamUpdate(self.meas.slam_trks, quats, poss, state.f_array, self.sm.anchor_idxs, P, M, self.sigma_img)
+        self.last.update(msckf=msckf, msckf_slam=msckf_slam, slam=slam)
+        h = np.vstack([msckf.jac, msckf_slam.jac, slam.jac])
+        r_diag = np.concatenate([msckf.cov_m_diag, msckf_slam.cov_m_diag, slam.cov_m_diag])
+        res = np.concatenate([msckf.res, msckf_slam.res, slam.res])
+        return apply_qr_decomposition(h, res, r_diag, self.sigma_img), lists
+
+    def update_multi_uav(self, state):
+        """Updater::update as compiled with -DMULTI_UAV (updater.cpp:39-115): the short-MSCKF step applies ONLY the
+        CI lists (its stacked h is built and dropped, :58-70); the main step applies the CI lists first, then ONE
+        applyUpdate with the (h, res) linearised BEFORE the CI corrections (:84-97); no IEKF loop."""
+        correction = np.zeros(state.n_error_states())
+        if self.meas.msckf_short_trks:
+            _, (S_l, P_l, H_l, r_l) = self._construct_multi(state, 1)
+            for S_j, P_j, h_j, r_j in zip(S_l, P_l, H_l, r_l):
+                apply_ci(state, P_j, h_j, r_j, S_j)
+        self.sm.manage(state, list(self.meas.lost_slam_trk_idxs))
+        m = self.meas
+        if m.msckf_trks or m.slam_trks or m.new_slam_std_trks or m.new_msckf_slam_trks:
+            correction = np.zeros(state.n_error_states())
+            (h, res, r), (S_l, P_l, H_l, r_l) = self._construct_multi(state, 0)
+            self.last.update(h=h, res=res, r=r, ci_lists=(S_l, P_l, H_l, r_l))
+            for S_j, P_j, h_j, r_j in zip(S_l, P_l, H_l, r_l):
+                apply_ci(state, P_j, h_j, r_j, S_j)
+            if h.size > 0:
+                apply_update(state, h, res, r, correction, True)
+            self.post_update(state, correction)
+        self.last["correction"] = correction
+        return state
 
     # vio_updater.cpp:425-449
     def post_update(self, state, correction):

@@ -417,6 +417,101 @@ def test_compressed_ci_payload_exchange_equals_full_state_exchange():
         d.close()
 
 
+def _peer_snapshot(cfg, seed, frames, phase_shift):
+    """Another agent (oracle only): its newest state after `frames` updates, as SimpleState (oracle) + PeerState (C ABI)."""
+    from oracle.ci import SimpleState
+    from x_multi_agent_b200 import PeerState
+    scn = Scenario(SynthConfig(M=cfg.M, F=cfg.F, K=cfg.K, seed=seed))
+    scn.phase = scn.phase + phase_shift
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    replay(record(scn, frames), ora)
+    s = ora.newest()
+    window = list(range(frames - cfg.M, frames))               # camera frames held by the peer's pose window
+    so = SimpleState(s.dynamic_states(), s.p_array.copy(), s.q_array.copy(), s.f_array.copy(), s.cov.copy(),
+                     list(ora.upd.sm.anchor_idxs))
+    sd = PeerState(s.p_array, s.q_array, s.f_array, list(ora.upd.sm.anchor_idxs), s.cov)
+    return scn, window, so, sd
+
+
+@pytest.mark.parametrize("cfg,frames,min_gated,min_inl", [
+    (SynthConfig(M=6, F=4, K=14, seed=7, n_short=3), 9, 5, 3),
+    (SynthConfig(M=10, F=0, K=50, seed=0), 12, 2, 2),   # cfg-1 shape; the peers' drift turns some matched tracks into outliers
+])
+def test_multi_uav_msckf_msckf_matches_oracle(cfg, frames, min_gated, min_inl):
+    """Updater::update as compiled with -DMULTI_UAV (updater.cpp:39-115): joint triangulation of matched MSCKF tracks,
+    stacked 3-row feature blocks, nullspace projection, gate, k-agent covariance intersection, applyCI over the lists,
+    then the regular applyUpdate (msckf_update.cpp:65-281,494-501; ci.cpp:49-92; updater.cpp:144-161)."""
+    from oracle.ci import MsckfMatch
+    scn = Scenario(cfg)
+    ev = record(scn, frames)
+    last_upd = max(i for i, e in enumerate(ev) if e[0] == "update")
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    replay(ev[:last_upd], ora)
+    m = ev[last_upd][1]
+    s = ora.ekf.buf.states[ora.ekf.buf.closest_idx(m.timestamp)].copy()
+    sm = ora.upd.sm
+    peers = [_peer_snapshot(cfg, 31, frames, 0.25), _peer_snapshot(cfg, 32, frames, -0.2)]
+    lms, short_lms = scn.last_msckf_lms, scn.last_short_lms
+    rng = np.random.Generator(np.random.PCG64(5))
+
+    def peer_track(p, lm, L):
+        pscn, window, _, _ = peers[p]
+        return pscn._project(lm, window[len(window) - L:])
+
+    M = cfg.M
+    spec = []   # (peer, which, own track, landmark, peer track length)
+    spec += [(0, 0, 1, lms[1], M), (1, 0, 1, lms[1], M - 2)]          # two peers on one track (k = 2)
+    spec += [(0, 0, 3, lms[3], 3), (1, 0, 4, lms[4], M), (0, 0, 6, lms[6], M - 1)]
+    spec += [(1, 0, 8, lms[9], M)]                                     # wrong association: the joint gate rejects it
+    if short_lms:
+        spec += [(0, 1, 0, short_lms[0], 4), (1, 1, 2, short_lms[2], M)]
+    spec += [(0, 0, 10, lms[10], M), (1, 0, 10, lms[10], M)]           # tail of the list: the erase loop visits only the first
+    tracks = [peer_track(p, lm, L) for p, _, _, lm, L in spec]
+    o_matches = [MsckfMatch(peers[p][2], (which, trk), z) for (p, which, trk, _, _), z in zip(spec, tracks)]
+    d_matches = [(p, which, trk, z) for (p, which, trk, _, _), z in zip(spec, tracks)]
+
+    w = 0.1
+    dev = make_filter(cfg, multi_uav=1, ci_msckf_w=w)
+    dev.work_set(State.from_oracle(s))
+    dev.sm_set(sm.n_poses, sm.n_features, sm.anchor_idxs, sm.filled_before)
+    dev.set_measurement(m)
+    dev.set_msckf_matches([p[3] for p in peers], d_matches)
+    dev.updater_update()
+
+    ora.upd.ci_msckf_w = w
+    ora.upd.set_measurement(to_oracle_meas(m))
+    ora.upd.msckf_matches = list(o_matches)
+    ora.upd.update_multi_uav(s)
+
+    rp = Report()
+    ms = ora.upd.last["msckf"]
+    exp = [(float(j in ms.multi_gate and ms.multi_gate[j][0] < ms.multi_gate[j][1]), ms.multi_gate.get(j, (np.nan, np.nan)))
+           for j in range(len(m.msckf_trks)) if ms.n_matched[j] > 0]
+    gates = dev.mm_last_gates(0)
+    assert len(gates) == len(exp) == 6
+    own_ok = [i for i, (_, (g, _)) in enumerate(exp) if np.isfinite(g)]
+    rp.check("multi-msckf groups gated", float(len(own_ok) < min_gated), 0.0)
+    rp.check("multi-msckf inlier mask", float(np.abs(gates[:, 0] - np.array([e[0] for e in exp])).sum()), 0.0)
+    rp.check("multi-msckf gamma", rel(gates[own_ok, 1], [exp[i][1][0] for i in own_ok]), 1e-7)
+    rp.check("multi-msckf chi2", rel(gates[own_ok, 2], [exp[i][1][1] for i in own_ok]), 1e-9)
+    n_inl = int(sum(e[0] for e in exp))
+    assert n_inl >= min_inl and n_inl < len(exp), "scenario must contain accepted and rejected joint updates"
+    assert ms.n_matched[10] == 1, "tail-of-list quirk: only the first of the two trailing matches is consumed"
+    assert ms.n_matched[1] == 2
+    n = len(m.msckf_trks)
+    rp.check("msckf gamma (joint triangulation)", rel(dev.debug("gamma0", n), ms.gamma), 1e-7)
+    rp.check("msckf inlier mask", float(np.abs(dev.debug_int("inlier0", n) - ms.inlier.astype(int)).sum()), 0.0)
+    if m.msckf_short_trks:
+        sh = ora.upd.last["short"]
+        gs = dev.mm_last_gates(1)
+        exps = [sh.multi_gate[j] for j in range(len(m.msckf_short_trks)) if sh.n_matched[j] > 0 and j in sh.multi_gate]
+        rp.check("short multi-msckf gamma", rel(gs[np.isfinite(gs[:, 1]), 1], [e[0] for e in exps]), 1e-7)
+    compare_state(rp, "multi-uav update", dev.work_get(), s, cfg.M, cfg.F)
+    assert dev.n_features == sm.n_features and dev.anchor_idxs == list(sm.anchor_idxs)
+    rp.done()
+    dev.close()
+
+
 @pytest.mark.parametrize("cfg,frames", [(SynthConfig(M=6, F=6, K=12, seed=1), 9), (SynthConfig(M=30, F=40, K=60, seed=0), 33)])
 def test_tensor_core_downdate_is_fp32_accurate(cfg, frames):
     """Optional tcgen05 (3xTF32, fp32 accumulators in TMEM) covariance downdate vs the default fp64 path.

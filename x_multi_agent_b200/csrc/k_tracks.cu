@@ -13,53 +13,9 @@
 //   update jac0^T jac0 = J^T J - B^T B,  jac0^T res0 = J^T r - B^T (U^T r),   B = U^T J  (3 x 6M)
 // so the 2L-3 dense rows are never formed: a track emits its sparse J blocks and the 3 dense rows B.
 #include "xb_kernels.h"
+#include "xb_svd4.cuh"
 
 namespace xb {
-
-// ---- 4x4 one-sided Jacobi: right singular vector of the smallest singular value -----------------
-// cv::triangulatePoints (OpenCV calib3d/triangulate.cpp) solves the same 4x4 homogeneous system by SVD.
-__device__ void smallest_right_singular_vector4(double* A /*4x4 row-major, destroyed*/, double* v /*4*/) {
-  double V[16];
-  for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-#pragma unroll 1
-  for (int sweep = 0; sweep < 12; ++sweep) {
-    double off = 0.0;
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-      for (int q = p + 1; q < 4; ++q) {  // static indices keep A and V in registers
-        double al = 0.0, be = 0.0, ga = 0.0;
-        for (int i = 0; i < 4; ++i) {
-          al += A[i * 4 + p] * A[i * 4 + p];
-          be += A[i * 4 + q] * A[i * 4 + q];
-          ga += A[i * 4 + p] * A[i * 4 + q];
-        }
-        const double lim = 1e-14 * sqrt(al * be);
-        if (fabs(ga) <= lim || ga == 0.0) continue;
-        off = fmax(off, fabs(ga) / fmax(sqrt(al * be), 1e-300));
-        const double zeta = (be - al) / (2.0 * ga);
-        const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
-        for (int i = 0; i < 4; ++i) {
-          const double ap = A[i * 4 + p], aq = A[i * 4 + q];
-          A[i * 4 + p] = c * ap - s * aq;
-          A[i * 4 + q] = s * ap + c * aq;
-          const double vp = V[i * 4 + p], vq = V[i * 4 + q];
-          V[i * 4 + p] = c * vp - s * vq;
-          V[i * 4 + q] = s * vp + c * vq;
-        }
-      }
-    if (off == 0.0) break;  // no rotation was needed in this sweep
-  }
-  int best = 0;
-  double bn = 1e300;
-  for (int p = 0; p < 4; ++p) {
-    double n = 0.0;
-    for (int i = 0; i < 4; ++i) n += A[i * 4 + p] * A[i * 4 + p];
-    if (n < bn) { bn = n; best = p; }
-  }
-  for (int i = 0; i < 4; ++i) v[i] = V[i * 4 + best];
-}
 
 __device__ __forceinline__ int tri_idx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
 
@@ -122,7 +78,12 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
   const double* Rl = Rk + 9 * (np - 1);  // last pose = inverse-depth anchor
   const double* pl = pk + 3 * (np - 1);
   double alpha = 0.0, beta = 0.0, rho = 1.0;
-  if (!bad) {
+  // MULTI_UAV: a track matched with other agents' tracks is triangulated jointly with their observations
+  // (msckf_update.cpp:96-166) by k_mm_triangulate; its inverse-depth estimate arrives through mm_ivd.
+  const int mm_g = tp.mm_grp ? tp.mm_grp[trk] : -1;
+  if (!bad && mm_g >= 0) {
+    alpha = tp.mm_ivd[3 * mm_g]; beta = tp.mm_ivd[3 * mm_g + 1]; rho = tp.mm_ivd[3 * mm_g + 2];
+  } else if (!bad) {
     if (lane == 0) {
       // projection matrices [R^T | -R^T p] of the first and last pose (triangulation.cpp:208-216)
       const double* z1 = tp.obs + 2 * (size_t)o0;
@@ -368,6 +329,13 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     }
     if (lane == 0)
       for (int u = 0; u < 3; ++u) Bt[u * W + 6 * M] = ur[u];
+    if (mm_g >= 0) {  // jac_pf_ block of the own agent: A_up^T Hf (msckf_update.cpp:442-443)
+      double f0[9];
+      for (int u = 0; u < 3; ++u)
+        for (int c = 0; c < 3; ++c) f0[u * 3 + c] = wdot(ws.U + u, 3, ws.Hf + c, 3, R2, lane);
+      if (lane == 0)
+        for (int e = 0; e < 9; ++e) tp.mm_F0[9 * (size_t)mm_g + e] = f0[e];
+    }
   }
   __syncwarp();
 

@@ -179,6 +179,16 @@ struct xb_filter {
   double *d_ci_own = nullptr, *d_ci_gather = nullptr, *d_ci_rec = nullptr, *d_ci_K = nullptr, *d_ci_delta = nullptr, *d_ci_HP = nullptr;
   int *d_ci_matches = nullptr, *d_ci_last = nullptr;
   int ci_payload_len = 0, ci_max_matches = 256, ci_max_agents = 16, ci_last_n = 0;
+  // multi-agent MSCKF-MSCKF matches (VioUpdater::msckf_matches_, vio_updater.h:282)
+  struct MmMatch { int peer, which, trk, n_obs; size_t obs_off; };
+  std::vector<MmMatch> mm_matches;
+  std::vector<double> mm_obs_h;
+  const double* mm_gather = nullptr;  // device: pose payload slots (own buffer or the caller's)
+  double *d_mm_gather = nullptr, *d_mm_pobs = nullptr, *d_mm_chi2 = nullptr, *d_mm_ivd = nullptr, *d_mm_F0 = nullptr,
+         *d_mm_rec = nullptr, *d_mm_V = nullptr, *d_mm_D = nullptr, *d_mm_K3 = nullptr, *d_mm_HP3 = nullptr;
+  int *d_mm_grp = nullptr, *d_mm_ent = nullptr, *d_mm_trkgrp = nullptr, *d_mm_last = nullptr;
+  int mm_pp_len = 0, mm_max_groups = 512, mm_max_entries = 1024, mm_G = 0, mm_max_tracks = 0;
+  int mm_last_G[2] = {0, 0};
   int omega_slot = -2;
   bool corr_zero = false;  // correction_total is known to be all-zero (first IEKF iteration)
   std::vector<void*> allocs;
@@ -387,6 +397,22 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_ci_HP, 3 * (size_t)N, double);
   DA(f->d_ci_matches, 3 * (size_t)f->ci_max_matches, int);
   DA(f->d_ci_last, 4, int);
+  f->mm_pp_len = 8 + 7 * M + 36 * M * M;
+  f->mm_max_tracks = maxT;
+  DA(f->d_mm_gather, (size_t)f->ci_max_agents * f->mm_pp_len, double);
+  DA(f->d_mm_pobs, 2 * (size_t)f->mm_max_entries * M, double);
+  DA(f->d_mm_chi2, f->mm_max_groups, double);
+  DA(f->d_mm_ivd, 3 * (size_t)f->mm_max_groups, double);
+  DA(f->d_mm_F0, 9 * (size_t)f->mm_max_groups, double);
+  DA(f->d_mm_rec, (size_t)2 * XB_MM_REC * f->mm_max_groups, double);
+  DA(f->d_mm_V, (size_t)6 * M * f->mm_max_groups, double);
+  DA(f->d_mm_D, (size_t)N * f->mm_max_groups, double);
+  DA(f->d_mm_K3, 3 * (size_t)N, double);
+  DA(f->d_mm_HP3, 3 * (size_t)N, double);
+  DA(f->d_mm_grp, 4 * (size_t)f->mm_max_groups, int);
+  DA(f->d_mm_ent, 3 * (size_t)f->mm_max_entries, int);
+  DA(f->d_mm_trkgrp, maxT, int);
+  DA(f->d_mm_last, 4, int);
   DA(f->d_Zb, (size_t)n_pad * 32, double);
   DA(f->d_Yb, (size_t)n_pad * 32, double);
   DA(f->d_Qb, (size_t)n_pad * 32, double);
@@ -853,6 +879,84 @@ static TrackParams track_params(xb_filter* f, const ListDev& l, int mode) {
   return tp;
 }
 
+// Collects, for every own track of the list in order, the matches the reference's erase-loop would hand to it
+// (msckf_update.cpp:96-139, restated with its shrinking loop bound), and uploads the group tables.
+static int check_ci_weight(double w);
+static MmParams mm_params(xb_filter* f, const ListDev& l0, int which) {
+  MmParams mp{};
+  mp.xv = f->d_xw; mp.M = f->M; mp.n_poses = f->n_poses; mp.N = f->N; mp.P = f->d_Pw;
+  mp.off = l0.d_off; mp.obs = l0.d_obs;
+  mp.grp = f->d_mm_grp; mp.ent = f->d_mm_ent; mp.pobs = f->d_mm_pobs; mp.chi2 = f->d_mm_chi2;
+  mp.n_groups = f->mm_G;
+  mp.gathered = f->mm_gather; mp.pp_len = f->mm_pp_len;
+  mp.var_img = f->cfg.sigma_img * f->cfg.sigma_img; mp.w_other = f->cfg.ci_msckf_w;
+  mp.gn_term = 1e-5; mp.gn_max_iter = 10;
+  mp.B = f->d_B0; mp.inlier = f->d_inl0;
+  mp.ivd = f->d_mm_ivd; mp.F0 = f->d_mm_F0; mp.rec = f->d_mm_rec + (size_t)which * XB_MM_REC * f->mm_max_groups;
+  mp.last = f->d_mm_last;
+  return mp;
+}
+static int mm_prepare(xb_filter* f, int which, const ListDev& l0, MmParams& mp) {
+  auto& ms = f->mm_matches;
+  std::vector<int> cnt(l0.n, 0);
+  bool any = false;
+  for (const auto& m : ms)
+    if (m.which == which && m.trk >= 0 && m.trk < l0.n) { ++cnt[m.trk]; any = true; }
+  if (!any) return 0;
+  std::vector<int> grp, ent, trkgrp(l0.n, -1);
+  std::vector<double> pobs, chi;
+  for (int j = 0; j < l0.n; ++j) {
+    if (!cnt[j]) continue;
+    std::vector<xb_filter::MmMatch> mine;
+    int corrected = 0;
+    for (int i = 0; i < (int)ms.size(); ++i) {  // size() re-evaluated while the list shrinks, like the reference
+      const auto& m = ms[i - corrected];
+      if (m.which == which && m.trk == j) {
+        mine.push_back(m);
+        ms.erase(ms.begin() + (i - corrected));
+        ++corrected;
+      }
+    }
+    if (mine.empty()) continue;
+    if ((int)mine.size() > XB_MM_KMAX) return fail(XB_E_CAPACITY, "more than 7 matched peers for one MSCKF track");
+    const int g = (int)grp.size() / 4;
+    if (g >= f->mm_max_groups || (int)ent.size() / 3 + (int)mine.size() > f->mm_max_entries)
+      return fail(XB_E_CAPACITY, "too many MSCKF-MSCKF matches");
+    int n_tot = l0.h_off[j + 1] - l0.h_off[j];
+    grp.push_back(j); grp.push_back((int)mine.size()); grp.push_back((int)ent.size() / 3);
+    for (const auto& m : mine) {
+      ent.push_back(m.peer); ent.push_back((int)pobs.size() / 2); ent.push_back(m.n_obs);
+      pobs.insert(pobs.end(), f->mm_obs_h.begin() + m.obs_off, f->mm_obs_h.begin() + m.obs_off + 2 * (size_t)m.n_obs);
+      n_tot += m.n_obs;
+    }
+    grp.push_back(n_tot);
+    chi.push_back(xb_chi2_quantile(0.95, 2.0 * n_tot - 3.0));  // msckf_update.cpp:243-247
+    trkgrp[j] = g;
+  }
+  f->mm_G = (int)grp.size() / 4;
+  if (f->mm_G == 0) return 0;
+  int rc = check_ci_weight(f->cfg.ci_msckf_w);  // ci.cpp:59-62
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(f->d_mm_grp, grp.data(), sizeof(int) * grp.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_mm_ent, ent.data(), sizeof(int) * ent.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_mm_trkgrp, trkgrp.data(), sizeof(int) * trkgrp.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_mm_pobs, pobs.data(), sizeof(double) * pobs.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_mm_chi2, chi.data(), sizeof(double) * chi.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaStreamSynchronize(f->stream));  // the staging vectors die with this frame
+  mp = mm_params(f, l0, which);
+  return f->mm_G;
+}
+
+extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
+  if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  if (f->mm_G <= 0) return XB_OK;
+  const ListDev& l0 = f->last_which == 0 ? f->l_msckf : f->l_short;
+  MmParams mp = mm_params(f, l0, f->last_which);
+  launch_mm_apply(f->stream, mp, f->d_Pw, f->d_xw, f->F, f->d_mm_V, f->mm_max_groups, f->d_mm_D, f->d_mm_K3, f->d_mm_HP3);
+  f->mm_G = 0;
+  return XB_OK;
+}
+
 extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   const int M = f->M;
@@ -865,12 +969,26 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   if (!f->constructed_any) return XB_OK;
   if (f->n_poses < 1) return fail(XB_E_INVALID, "empty pose window");
   const size_t gbytes = sizeof(double) * (size_t)f->grows_pad * f->gcols_pad;
+  f->mm_G = 0;
+  MmParams mp{};
+  if (f->cfg.multi_uav && n0 > 0 && !f->mm_matches.empty()) {
+    int rcm = mm_prepare(f, which, l0, mp);
+    if (rcm < 0) return rcm;
+  }
   if (n0 + n1 > 0) {
     {
       StageTimer st_(f, ST_TRACKS);
-      if (n0 > 0 && launch_tracks(f->stream, track_params(f, l0, 0))) return fail(XB_E_CAPACITY, "track kernel shared memory");
+      TrackParams tp0 = track_params(f, l0, 0);
+      if (f->mm_G > 0) {
+        launch_mm_triangulate(f->stream, mp);
+        tp0.mm_grp = f->d_mm_trkgrp; tp0.mm_ivd = f->d_mm_ivd; tp0.mm_F0 = f->d_mm_F0;
+      }
+      if (n0 > 0 && launch_tracks(f->stream, tp0)) return fail(XB_E_CAPACITY, "track kernel shared memory");
+      if (f->mm_G > 0 && launch_mm_construct(f->stream, mp)) return fail(XB_E_CAPACITY, "multi-MSCKF kernel shared memory");
       if (n1 > 0 && launch_tracks(f->stream, track_params(f, f->l_newms, 1))) return fail(XB_E_CAPACITY, "track kernel shared memory");
     }
+    f->mm_last_G[which] = f->mm_G;
+    if (f->cfg.multi_uav && which == 1) return XB_OK;  // the stacked short-MSCKF (h, res) is built and dropped (updater.cpp:58-70)
     GramParams gp{};
     gp.M = M; gp.n_poses = f->n_poses;
     gp.B = f->d_B0; gp.rowsB = 3 * n0; gp.nzB = f->nz; gp.partB = f->d_partB;
@@ -1088,6 +1206,24 @@ extern "C" int xb_vio_post_update(xb_filter* f) {
 extern "C" int xb_updater_update(xb_filter* f) {
   int rc;
   if ((rc = xb_updater_reset_correction(f)) < 0) return rc;
+  if (f->cfg.multi_uav) {  // the -DMULTI_UAV build of the same method (updater.cpp:58-70, 84-97)
+    f->mm_last_G[0] = f->mm_last_G[1] = 0;
+    if (f->l_short.n > 0) {
+      if ((rc = xb_vio_construct_update(f, 1)) < 0) return rc;
+      if ((rc = xb_updater_apply_ci_lists(f)) < 0) return rc;  // only the CI lists: no applyUpdate in this build
+    }
+    if ((rc = xb_sm_manage(f, f->lost.data(), (int)f->lost.size())) < 0) return rc;
+    if (f->l_msckf.n || f->l_slam.n || f->l_newstd.n || f->l_newms.n) {
+      if ((rc = xb_updater_reset_correction(f)) < 0) return rc;
+      if ((rc = xb_vio_construct_update(f, 0)) < 0) return rc;
+      if ((rc = xb_updater_apply_ci_lists(f)) < 0) return rc;
+      if ((rc = xb_updater_apply_constructed(f, 1)) < 0) return rc;
+      if ((rc = xb_vio_post_update(f)) < 0) return rc;
+    }
+    f->mm_matches.clear();  // preProcess replaces msckf_matches_ on every update (vio_updater.cpp:185)
+    f->mm_obs_h.clear();
+    return XB_OK;
+  }
   if (f->l_short.n > 0) {  // preUpdateShortMsckf (vio_updater.cpp:209-215)
     if ((rc = xb_vio_construct_update(f, 1)) < 0) return rc;
     if ((rc = xb_updater_apply_constructed(f, 1)) < 0) return rc;
@@ -1275,9 +1411,81 @@ extern "C" int xb_ci_last_gates(xb_filter* f, double* out, int max_matches) {
   return n;
 }
 
-extern "C" int xb_vio_set_msckf_matches(xb_filter*, const xb_peer_state*, int, const xb_msckf_match*, int n_matches) {
-  if (n_matches <= 0) return XB_OK;
-  return fail(XB_E_UNSUPPORTED, "multi-agent MSCKF-MSCKF matches (msckf_update.cpp:88-279) are not built yet; SLAM-SLAM CI is");
+static int mm_store_matches(xb_filter* f, const xb_msckf_match* matches, int n_matches, int n_agents) {
+  f->mm_matches.clear();
+  f->mm_obs_h.clear();
+  for (int j = 0; j < n_matches; ++j) {
+    const xb_msckf_match& m = matches[j];
+    if (m.peer < 0 || m.peer >= n_agents) return fail(XB_E_INVALID, "match refers to an unknown peer");
+    if (m.n_obs < 1 || m.n_obs > f->M || !m.obs) return fail(XB_E_INVALID, "peer track length must be in [1, n_poses_max]");
+    if (m.which != 0 && m.which != 1) return fail(XB_E_INVALID, "which must be 0 (msckf) or 1 (msckf_short)");
+    f->mm_matches.push_back({m.peer, m.which, m.id_current_track, m.n_obs, f->mm_obs_h.size()});
+    f->mm_obs_h.insert(f->mm_obs_h.end(), m.obs, m.obs + 2 * (size_t)m.n_obs);
+  }
+  return XB_OK;
+}
+
+extern "C" int xb_vio_set_msckf_matches_packed(xb_filter* f, const double* dev_gathered, int n_agents,
+                                               const xb_msckf_match* matches, int n_matches) {
+  if (!f || (n_matches > 0 && (!matches || !dev_gathered))) return fail(XB_E_INVALID, "null argument");
+  if (n_matches > 0 && !f->cfg.multi_uav) return fail(XB_E_INVALID, "MSCKF-MSCKF matches need xb_config.multi_uav = 1");
+  f->mm_gather = dev_gathered;
+  return mm_store_matches(f, matches, std::max(0, n_matches), n_agents);
+}
+
+// Reference-format entry: peers as SimpleState.  The host cuts the pose payload (window + 6M x 6M covariance block)
+// out of each snapshot; camera positions carry SimpleState::translation_ (simple_state.cpp:51-65).
+extern "C" int xb_vio_set_msckf_matches(xb_filter* f, const xb_peer_state* peers, int n_peers,
+                                        const xb_msckf_match* matches, int n_matches) {
+  if (!f) return fail(XB_E_INVALID, "null filter");
+  if (n_matches <= 0) { f->mm_matches.clear(); f->mm_obs_h.clear(); return XB_OK; }
+  if (!peers || !matches) return fail(XB_E_INVALID, "null argument");
+  if (!f->cfg.multi_uav) return fail(XB_E_INVALID, "MSCKF-MSCKF matches need xb_config.multi_uav = 1");
+  if (n_peers > f->ci_max_agents) return fail(XB_E_CAPACITY, "too many peers");
+  const int M = f->M, PL = f->mm_pp_len, n6 = 6 * M;
+  std::vector<double> pay((size_t)n_peers * PL, 0.0);
+  for (int p = 0; p < n_peers; ++p) {
+    const xb_peer_state& ps = peers[p];
+    if (ps.n_poses_max != M) return fail(XB_E_INVALID, "peers must use the same n_poses_max");
+    if (!ps.positions || !ps.orientations || !ps.cov) return fail(XB_E_INVALID, "peer snapshot incomplete");
+    const int Np = XB_NERR(ps.n_poses_max, ps.n_features_max);
+    double* o = pay.data() + (size_t)p * PL;
+    o[0] = 1.0; o[2] = M;
+    for (int i = 0; i < 3 * M; ++i) o[8 + i] = ps.positions[i] + ps.translation[i % 3];
+    for (int i = 0; i < 4 * M; ++i) o[8 + 3 * M + i] = ps.orientations[i];
+    for (int r = 0; r < n6; ++r)
+      for (int c = 0; c < n6; ++c)
+        o[8 + 7 * M + (size_t)r * n6 + c] = ps.cov_layout == XB_COL_MAJOR ? ps.cov[(size_t)(XB_CORE + c) * Np + XB_CORE + r]
+                                                                          : ps.cov[(size_t)(XB_CORE + r) * Np + XB_CORE + c];
+  }
+  CK(cudaMemcpyAsync(f->d_mm_gather, pay.data(), sizeof(double) * pay.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  f->mm_gather = f->d_mm_gather;
+  return mm_store_matches(f, matches, n_matches, n_peers);
+}
+
+extern "C" int xb_ci_pose_payload_len(const xb_filter* f) { return f->mm_pp_len; }
+
+extern "C" int xb_ci_pack_poses(xb_filter* f, int slot, double* dev_payload) {
+  if (!f || !dev_payload) return fail(XB_E_INVALID, "null argument");
+  if (slot < 0) slot = f->tail;
+  if (slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid state");
+  // only pose columns are read, so the generation buffer (P_vv) is the slot's covariance here
+  launch_pack_poses(f->stream, f->d_xv + (size_t)slot * f->LX, f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->N, f->M,
+                    dev_payload);
+  return XB_OK;
+}
+
+extern "C" int xb_mm_last_gates(xb_filter* f, int which, double* out, int max_groups) {
+  if (which < 0 || which > 1) return fail(XB_E_INVALID, "which must be 0 or 1");
+  const int n = std::min(max_groups, f->mm_last_G[which]);
+  if (n <= 0) return 0;
+  std::vector<double> r((size_t)XB_MM_REC * n);
+  CK(cudaStreamSynchronize(f->stream));
+  CK(cudaMemcpy(r.data(), f->d_mm_rec + (size_t)which * XB_MM_REC * f->mm_max_groups, sizeof(double) * r.size(), cudaMemcpyDeviceToHost));
+  for (int j = 0; j < n; ++j)
+    for (int e = 0; e < 3; ++e) out[3 * j + e] = r[(size_t)XB_MM_REC * j + e];
+  return n;
 }
 
 // ---- introspection ----------------------------------------------------------------------------------------------------------

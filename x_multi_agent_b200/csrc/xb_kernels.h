@@ -55,6 +55,11 @@ struct TrackParams {
   double* H1;      // [K][3][6M+1]   mode 1: unmasked U^T [h | r]  (H1 and r1 of Li 2012)
   double* H2;      // [K][9]         mode 1: U^T Hf
   double* D;       // [2*obs][6M+1]  mode 1: Pi [h | r]
+  // MULTI_UAV (mode 0 only; all null otherwise): per-track group index (-1: not matched), the jointly
+  // triangulated inverse-depth estimate per group, and the output A_up^T Hf per group
+  const int* mm_grp;
+  const double* mm_ivd;
+  double* mm_F0;
 };
 int launch_tracks(cudaStream_t s, const TrackParams& tp);
 
@@ -150,5 +155,33 @@ void launch_ci_slam(cudaStream_t s, double* xv, double* P, int N, int M, int F, 
                     const int* anchor, const double* gathered, int payload_len, const int* matches, int n_matches,
                     double var_lm, double w_other, double chi2_90_3, double* rec, int* last_inlier, double* Kall,
                     double* delta, double* HP);
+
+
+// ---- multi-agent MSCKF-MSCKF block (k_multi_msckf.cu; msckf_update.cpp:65-281, MULTI_UAV build) ----------
+#define XB_MM_KMAX 7   // matched peers per own track
+#define XB_MM_REC 32   // doubles per group record
+struct MmParams {
+  const double* xv; int M, n_poses, N;
+  const double* P;            // work covariance (prior of the construct step)
+  const int* off; const double* obs;   // own track list (CSR)
+  const int* grp;             // [G][4]: own track, k peers, first entry, total joint observations
+  const int* ent;             // [E][3]: peer slot in `gathered`, first observation in pobs, n_obs
+  const double* pobs;         // peers' observations, 2 doubles each
+  const double* chi2;         // [G] quantile(0.95, 2 n_tot - 3)
+  int n_groups;
+  const double* gathered; int pp_len;  // peers' pose payloads: [8 hdr | 3M camera positions | 4M quats | 6M x 6M cov]
+  double var_img, w_other, gn_term; int gn_max_iter;
+  const double* B; const int* inlier;  // k_tracks outputs of the own tracks
+  double* ivd;                // [G][3]
+  double* F0;                 // [G][9]
+  double* rec;                // [G][XB_MM_REC]: inlier, gamma, chi2, w_result, a(3), C3(9), trk, i1, L, k
+  int* last;                  // last inlier group (-1: none)
+};
+void launch_mm_triangulate(cudaStream_t s, const MmParams& mp);
+int launch_mm_construct(cudaStream_t s, const MmParams& mp);
+// applyCI over the group list: sequential state corrections, covariance of the last inlier entry (updater.cpp:144-161)
+void launch_mm_apply(cudaStream_t s, const MmParams& mp, double* P, double* xv, int F, double* V, int ldv, double* D,
+                     double* K3, double* HP3);
+void launch_pack_poses(cudaStream_t s, const double* xv, const double* P, int N, int M, double* out);
 
 }  // namespace xb

@@ -187,9 +187,8 @@ class Filter:
             return None
         return State(self.M, self.F, out) if want_state else True
 
-    def process_others_measurement(self, t, peers, matches, want_state=True):
-        """Ekf::processOthersMeasurement (ekf.cpp:143-176) with SLAM-SLAM matches (peer_idx, current_fid, received_fid)."""
-        keep = []
+    @staticmethod
+    def _peers(peers, keep):
         cp = (L.XbPeerState * max(1, len(peers)))()
         for i, p in enumerate(peers):
             pos, ori, fe, cov = L.f64(p.positions), L.f64(p.orientations), L.f64(p.features), L.f64(p.cov)
@@ -200,6 +199,49 @@ class Filter:
             cp[i].anchor_idxs, cp[i].cov, cp[i].cov_layout = L.iptr(an), L.dptr(cov), 0
             for k in range(3):
                 cp[i].translation[k] = p.translation[k]
+        return cp
+
+    @staticmethod
+    def _msckf_matches(matches, keep):
+        """matches: (peer_idx, which, own_track_idx, received_track (L,2)) in list order (vision/types.h:83-100)."""
+        cm = (L.XbMsckfMatch * max(1, len(matches)))()
+        for j, (pi, which, trk, obs) in enumerate(matches):
+            o = np.ascontiguousarray(np.asarray(obs, dtype=np.float64).reshape(-1, 2))
+            keep.append(o)
+            cm[j].peer, cm[j].which, cm[j].id_current_track, cm[j].n_obs, cm[j].obs = pi, which, trk, o.shape[0], L.dptr(o)
+        return cm
+
+    def set_msckf_matches(self, peers, matches):
+        """VioUpdater::msckf_matches_ for the next update (vio_updater.cpp:185), peers as SimpleState snapshots."""
+        keep = []
+        cp = self._peers(peers, keep)
+        cm = self._msckf_matches(matches, keep)
+        L.check(self.lib.xb_vio_set_msckf_matches(self.h, cp, len(peers), cm, len(matches)))
+
+    def set_msckf_matches_packed(self, gathered_dev_ptr, n_agents, matches):
+        keep = []
+        cm = self._msckf_matches(matches, keep)
+        L.check(self.lib.xb_vio_set_msckf_matches_packed(self.h, C.c_void_p(gathered_dev_ptr), n_agents, cm, len(matches)))
+
+    def pose_payload_len(self):
+        return self.lib.xb_ci_pose_payload_len(self.h)
+
+    def pack_poses(self, dev_ptr, slot=-1):
+        """Pack this agent's pose payload (window + 6M x 6M covariance block) into device memory at `dev_ptr`."""
+        L.check(self.lib.xb_ci_pack_poses(self.h, slot, C.c_void_p(dev_ptr)))
+
+    def mm_last_gates(self, which=0, n=512):
+        out = np.zeros(3 * max(1, n))
+        k = L.check(self.lib.xb_mm_last_gates(self.h, which, L.dptr(out), n))
+        return out[:3 * k].reshape(-1, 3)
+
+    def apply_ci_lists(self):
+        L.check(self.lib.xb_updater_apply_ci_lists(self.h))
+
+    def process_others_measurement(self, t, peers, matches, want_state=True):
+        """Ekf::processOthersMeasurement (ekf.cpp:143-176) with SLAM-SLAM matches (peer_idx, current_fid, received_fid)."""
+        keep = []
+        cp = self._peers(peers, keep)
         cm = (L.XbSlamMatch * max(1, len(matches)))()
         for j, (pi, cur, rcv) in enumerate(matches):
             cm[j].peer, cm[j].current_feature_id, cm[j].received_feature_id = pi, cur, rcv

@@ -25,7 +25,7 @@ class XbConfig(C.Structure):
         ("a_m_max", C.c_double), ("time_margin", C.c_double),
         ("sigma_img", C.c_double), ("sigma_range", C.c_double), ("rho_0", C.c_double), ("sigma_rho_0", C.c_double),
         ("sigma_landmark", C.c_double), ("ci_msckf_w", C.c_double), ("ci_slam_w", C.c_double),
-        ("downdate_precision", C.c_int), ("reserved", C.c_int),
+        ("downdate_precision", C.c_int), ("multi_uav", C.c_int),
     ]
 
 
@@ -50,7 +50,8 @@ class XbSlamMatch(C.Structure):
 
 
 class XbMsckfMatch(C.Structure):
-    _fields_ = [("peer", C.c_int), ("id_current_track", C.c_int), ("n_obs", C.c_int), ("obs", c_double_p)]
+    _fields_ = [("peer", C.c_int), ("which", C.c_int), ("id_current_track", C.c_int), ("n_obs", C.c_int),
+                ("obs", c_double_p)]
 
 
 # every exported symbol of include/xb200.h: name -> (restype, argtypes)
@@ -72,6 +73,11 @@ SIGNATURES = {
     "xb_ekf_process_others": (C.c_int, [_VP, C.c_double, C.POINTER(XbPeerState), C.c_int, C.POINTER(XbSlamMatch),
                                         C.c_int, c_double_p]),
     "xb_vio_set_msckf_matches": (C.c_int, [_VP, C.POINTER(XbPeerState), C.c_int, C.POINTER(XbMsckfMatch), C.c_int]),
+    "xb_vio_set_msckf_matches_packed": (C.c_int, [_VP, _VP, C.c_int, C.POINTER(XbMsckfMatch), C.c_int]),
+    "xb_ci_pose_payload_len": (C.c_int, [_VP]),
+    "xb_ci_pack_poses": (C.c_int, [_VP, C.c_int, _VP]),
+    "xb_mm_last_gates": (C.c_int, [_VP, C.c_int, c_double_p, C.c_int]),
+    "xb_updater_apply_ci_lists": (C.c_int, [_VP]),
     "xb_ekf_get_state": (C.c_int, [_VP, C.c_int, c_double_p]),
     "xb_ekf_get_covariance": (C.c_int, [_VP, C.c_int, c_double_p, C.c_int]),
     "xb_ekf_newest_slot": (C.c_int, [_VP]),

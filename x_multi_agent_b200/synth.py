@@ -100,6 +100,8 @@ class Scenario:
         self.feat_obs = []          # observation history per active SLAM feature
         self.imu_seq = 0
         self._cam_cache = {}
+        self._last_lms = np.zeros((0, 3))
+        self.last_msckf_lms, self.last_short_lms = np.zeros((0, 3)), []
 
     # ---- truth ---------------------------------------------------------------------------------------
     def pose(self, t):
@@ -198,6 +200,7 @@ class Scenario:
 
     def _tracks(self, frames, n, outliers=True):
         lms = self._sample_visible(frames, n)
+        self._last_lms = lms
         Z = np.empty((n, len(frames), 2))
         for i, k in enumerate(frames):
             pc, Rc = self.cam_pose(self.frame_time(k))
@@ -216,8 +219,12 @@ class Scenario:
         n = min(k + 1, c.M)
         frames = list(range(k - n + 1, k + 1))
         m = Measurement(timestamp=self.frame_time(k))
+        # landmarks behind the MSCKF / short-MSCKF tracks of the last measurement: lets a multi-agent scenario
+        # generate other agents' observations of the same landmarks (MSCKF-MSCKF matches)
+        self.last_msckf_lms, self.last_short_lms = np.zeros((0, 3)), []
         if n >= 2 and c.K > 0:
             m.msckf_trks = self._tracks(frames, c.K)
+            self.last_msckf_lms = self._last_lms
         if c.n_short > 0 and n >= 3:
             # short tracks are processed BEFORE the window slides / the new clone is added: they end at frame k-1
             nw = min(k, c.M)
@@ -226,6 +233,7 @@ class Scenario:
                 L = min(L, nw)
                 fr = list(range(k - L, k))
                 m.msckf_short_trks += self._tracks(fr, 1, outliers=False)
+                self.last_short_lms.append(self._last_lms[0])
         init_frame = c.slam_init_frame if c.slam_init_frame >= 0 else c.M
         if c.F > 0:
             # existing SLAM features: one track per feature slot (last observation is the one used)
