@@ -220,7 +220,7 @@ def main():
 
     scn, fill = build_scenario(seed=rank)
     flt = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank, downdate_precision=args.precision,
-                 sigma_landmark=1.0, ci_slam_w=0.1)
+                 sigma_landmark=1.0, ci_slam_w=0.1, ci_msckf_w=0.1, multi_uav=int(world > 1))
     stream = torch.cuda.Stream()
     flt.set_stream(stream.cuda_stream)
     replay(fill, flt)
@@ -306,6 +306,54 @@ def main():
         ci = {"ci_fusion_steps_per_sec": world * K / (float(tci[0]) * 1e-3), "ms_per_step": float(tci[0]) / K,
               "matches_per_step": len(matches), "inlier_frac_rank0": inl, "payload_bytes_per_agent": PL * 8,
               "full_simplestate_bytes": 8 * (795 * 795 + 16 + 7 * 30 + 3 * 200), "collective": "all_gather (NCCL)"}
+    # ---- phase D (N > 1): MULTI_UAV visual updates with 32 MSCKF-MSCKF matches per peer; every agent publishes its
+    #      pose payload (window + 6M x 6M covariance block) through one all-gather per update --------------------------
+    mm = None
+    if world > 1:
+        from x_multi_agent_b200.ci import exchange_payloads
+        from x_multi_agent_b200.synth import Scenario, SynthConfig
+        Kd = min(K, 20)
+        peers = [p for p in range(world) if p != rank]
+        peer_scn = {p: Scenario(SynthConfig(M=CFG2["M"], F=CFG2["F"], K=1, seed=p, slam_init_frame=CFG2["M"], slam_lm_seed=4242))
+                    for p in peers}   # analytic truth of the other agents' trajectories (same generator, their seed)
+        k0 = N_FILL + 2 * (W + K)
+        PP = flt.pose_payload_len()
+        local = torch.zeros(PP, dtype=torch.float64, device="cuda")
+        steps_d = []
+        for j in range(W + Kd):
+            imu, m = steady_events(scn, k0 + j, 1)[0]
+            lms = scn.last_msckf_lms
+            win = list(range(k0 + j - CFG2["M"], k0 + j))     # frames held by a peer's window when it packs its payload
+            mt = [(p, 0, a * 32 + q, peer_scn[p]._project(lms[a * 32 + q], win)) for a, p in enumerate(peers) for q in range(32)]
+            steps_d.append((imu, PackedMeasurement(m), mt))
+        d0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
+        d1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
+        acc, gated = [], []
+        barrier()
+        for j, (imu, pm, mt) in enumerate(steps_d):
+            for (t, seq, w, a) in imu:
+                flt.process_imu(t, seq, w, a, want_state=False)
+            flt.set_measurement(pm)
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                d0[j].record(stream)
+                flt.pack_poses(local.data_ptr())
+                gathered = exchange_payloads(local)
+                flt.set_msckf_matches_packed(gathered.data_ptr(), world, mt)
+                flt.process_update_measurement(want_state=False)
+                d1[j].record(stream)
+            stream.synchronize()
+            g = flt.mm_last_gates(0)
+            gated.append(float(np.isfinite(g[:, 1]).mean()) if len(g) else 0.0)
+            acc.append(float(g[:, 0].mean()) if len(g) else 0.0)
+        barrier()
+        mm_ms = sum(d0[j].elapsed_time(d1[j]) for j in range(W, W + Kd))
+        tmm = torch.tensor([mm_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmm, op=dist.ReduceOp.MAX)
+        mm = {"multi_uav_updates_per_sec": world * Kd / (float(tmm[0]) * 1e-3), "ms_per_step": float(tmm[0]) / Kd, "steps": Kd,
+              "msckf_matches_per_step": len(steps_d[0][2]), "own_gate_passed_frac_rank0": float(np.mean(gated[W:])),
+              "joint_gate_accepted_frac_rank0": float(np.mean(acc[W:])), "pose_payload_bytes_per_agent": PP * 8,
+              "collective": "all_gather (NCCL), one per update"}
     tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -372,7 +420,7 @@ def main():
                     "h2d_bytes_per_step": int(np.mean([p.h2d_bytes for p in packed])) + 4 * (795 + 16 * 6 + 2 * 200),
                     "d2h_bytes_per_step": flt.LX * 8},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci,
+            "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci, "multi_uav_msckf": mm,
             "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac}}
     print(json.dumps(line))
     flt.close()

@@ -512,6 +512,57 @@ def test_multi_uav_msckf_msckf_matches_oracle(cfg, frames, min_gated, min_inl):
     dev.close()
 
 
+def test_pose_payload_exchange_equals_full_state_exchange():
+    """for MSCKF-MSCKF matches a peer enters only through its pose window and the 6M x 6M pose block of its
+    covariance.  Shipping that pose payload (packed on the peer's GPU, xb_ci_pack_poses) gives the same update as
+    shipping the whole SimpleState.  Driven through the Ekf-level API (processUpdateMeasurement in a MULTI_UAV build)."""
+    import torch
+    from x_multi_agent_b200 import PeerState
+    cfg = SynthConfig(M=6, F=4, K=12, seed=13)
+    frames = 9
+    scn0, scn1 = Scenario(cfg), Scenario(SynthConfig(M=6, F=4, K=12, seed=14))
+    scn1.phase = scn1.phase + 0.2
+    ev0, ev1 = record(scn0, frames), record(scn1, frames - 1)
+    last_upd = max(i for i, e in enumerate(ev0) if e[0] == "update")
+    kw = dict(multi_uav=1, ci_msckf_w=0.2)
+    full, packed, peer = make_filter(cfg, **kw), make_filter(cfg, **kw), make_filter(cfg)
+    replay(ev1, peer, want_state=False)
+    for flt in (full, packed):
+        replay(ev0[:last_upd], flt, want_state=False)
+    m = ev0[last_upd][1]
+    window1 = list(range(frames - 1 - cfg.M, frames - 1))
+    lms = scn0.last_msckf_lms
+    matches = [(1, 0, j, scn1._project(lms[j], window1[len(window1) - L:])) for j, L in ((0, 6), (2, 4), (5, 6), (7, 3), (9, 5))]
+    PL = peer.pose_payload_len()
+    assert PL == 8 + 7 * cfg.M + 36 * cfg.M * cfg.M
+    gathered = torch.zeros(2, PL, dtype=torch.float64, device="cuda")
+    peer.pack_poses(gathered[1].data_ptr())
+    peer.synchronize()
+    s1 = peer.get_state()
+    ps = PeerState(s1.p_array, s1.q_array, s1.f_array, peer.anchor_idxs, peer.get_covariance())
+    pay = gathered[1].cpu().numpy()
+    n6 = 6 * cfg.M
+    rp = Report()
+    rp.check("payload poses", np.abs(pay[8:8 + 3 * cfg.M] - s1.p_array).max(), 0.0)
+    rp.check("payload pose covariance block", np.abs(pay[8 + 7 * cfg.M:].reshape(n6, n6) - ps.cov[15:15 + n6, 15:15 + n6]).max(), 0.0)
+    full.set_measurement(m)
+    full.set_msckf_matches([ps, ps], matches)           # peer index 1, like the gathered slot
+    packed.set_measurement(m)
+    packed.set_msckf_matches_packed(gathered.data_ptr(), 2, matches)
+    a, b = full.process_update_measurement(), packed.process_update_measurement()
+    assert a is not None and b is not None
+    a.cov, b.cov = full.get_covariance(), packed.get_covariance()
+    compare_state(rp, "packed vs full", b, a, cfg.M, cfg.F, tol_scale=1e-3)
+    g0, g1 = full.mm_last_gates(0), packed.mm_last_gates(0)
+    rp.check("gates equal", float(np.abs(g0 - g1).max()), 1e-9)
+    assert len(g0) == len(matches) and g0[:, 0].sum() >= 2
+    # matches are consumed by the update they were set for (vio_updater.cpp:185)
+    assert full.mm_last_gates(1).size == 0
+    rp.done()
+    for d in (full, packed, peer):
+        d.close()
+
+
 @pytest.mark.parametrize("cfg,frames", [(SynthConfig(M=6, F=6, K=12, seed=1), 9), (SynthConfig(M=30, F=40, K=60, seed=0), 33)])
 def test_tensor_core_downdate_is_fp32_accurate(cfg, frames):
     """Optional tcgen05 (3xTF32, fp32 accumulators in TMEM) covariance downdate vs the default fp64 path.
