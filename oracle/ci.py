@@ -327,3 +327,27 @@ def multi_slam_from_payload(quats, poss, feature_states, anchor_idxs, P, n_poses
                 P_j[c:c + 3, c:c + 3] *= w_res
             out["S"].append(S_j); out["P"].append(P_j); out["H"].append(h_j); out["res"].append(res_j)
     return out
+
+
+def pack_pose_payload(state, n_poses_max):
+    """[8 header | 3M camera positions | 4M attitudes | 6M x 6M pose block of the covariance] -- what xb_ci_pack_poses
+    writes on the device: everything a peer contributes to the MSCKF-MSCKF block (msckf_update.cpp:175-279)."""
+    M = n_poses_max
+    n6 = 6 * M
+    out = np.zeros(8 + 7 * M + n6 * n6)
+    out[0], out[1], out[2] = 1.0, state.time, M
+    out[8:8 + 3 * M] = state.p_array
+    out[8 + 3 * M:8 + 7 * M] = state.q_array
+    out[8 + 7 * M:] = state.cov[K_CORE:K_CORE + n6, K_CORE:K_CORE + n6].ravel()
+    return out
+
+
+def peer_from_pose_payload(payload, n_features_max=0):
+    """SimpleState whose covariance holds only the pose block (all that MultiMsckfUpdate reads of a peer)."""
+    M = int(payload[2])
+    n6 = 6 * M
+    N = K_CORE + n6 + 3 * n_features_max
+    cov = np.zeros((N, N))
+    cov[K_CORE:K_CORE + n6, K_CORE:K_CORE + n6] = payload[8 + 7 * M:].reshape(n6, n6)
+    return SimpleState(np.zeros(16), payload[8:8 + 3 * M].copy(), payload[8 + 3 * M:8 + 7 * M].copy(),
+                       np.zeros(3 * n_features_max), cov, [-1] * n_features_max)

@@ -250,3 +250,52 @@ def test_default_config_matches_reference_defaults(lib):
     assert (cfg.n_poses_max, cfg.n_features_max, cfg.n_slots) == (15, 15, 250)  # vio/types.h:141,146,188
     assert (cfg.n_w, cfg.n_bw, cfg.n_a) == (0.0083, 0.00083, 0.0013)             # common/types.h:69-79
     assert tuple(cfg.g) == (0.0, 0.0, -9.81)
+
+
+def test_match_erase_loop_is_restated_as_written():
+    """msckf_update.cpp:96-139: the loop bound shrinks with every erased match while the index is only corrected by
+    the number of erasures, so trailing matches of the same track are not all visited."""
+    from oracle.ci import MsckfMatch, consume_matches
+    mk = lambda t: MsckfMatch(None, t, np.zeros((2, 2)))
+    ms = [mk(0), mk(1), mk(0), mk(2)]
+    mine = consume_matches(ms, 0)
+    assert len(mine) == 2 and [m.id_current_track for m in ms] == [1, 2]
+    ms = [mk(5), mk(7), mk(7)]
+    mine = consume_matches(ms, 7)
+    assert len(mine) == 1 and [m.id_current_track for m in ms] == [5, 7]
+    ms = [mk(7), mk(7), mk(7), mk(7)]
+    assert len(consume_matches(ms, 7)) == 2 and len(ms) == 2
+
+
+def test_multi_msckf_block_is_invariant_to_the_nullspace_basis():
+    """The device uses U_i = MGS(Hf_i) and its own Householder basis of the stacked nullspace; the reference uses Eigen's
+    householderQ().  K res and (I - K H) P_j do not depend on either choice -- checked here by flipping/rotating bases."""
+    from oracle.ci import fuse_ci_multi
+    rng = np.random.default_rng(3)
+    n, k = 40, 2
+    P = rng.normal(size=(n, n)); P = P @ P.T + n * np.eye(n)
+    Pp = [rng.normal(size=(n, n)) for _ in range(k)]
+    Pp = [x @ x.T + n * np.eye(n) for x in Pp]
+    B = [rng.normal(size=(3, n)) for _ in range(k + 1)]
+    Fs = [rng.normal(size=(3, 3)) for _ in range(k + 1)]
+    bs = [rng.normal(size=3) for _ in range(k + 1)]
+
+    def update(rot):
+        O = [np.linalg.qr(rng.normal(size=(3, 3)))[0] if rot else np.eye(3) for _ in range(k + 1)]
+        F = np.vstack([O[i] @ Fs[i] for i in range(k + 1)])
+        b = np.concatenate([O[i] @ bs[i] for i in range(k + 1)])
+        q = np.linalg.qr(F, mode="complete")[0]
+        A = q[:, 3:]
+        if rot:
+            A = A @ np.linalg.qr(rng.normal(size=(3 * k, 3 * k)))[0]
+        h = A[0:3].T @ (O[0] @ B[0])
+        Hs = [A[3 * (i + 1):3 * (i + 2)].T @ (O[i + 1] @ B[i + 1]) for i in range(k)]
+        S, w = fuse_ci_multi(P, h, Pp, Hs, 0.1)
+        S = S + 1e-3 * np.eye(3 * k)
+        K = P @ h.T @ np.linalg.inv(S)
+        return K @ (A.T @ b), (np.eye(n) - K @ h) @ P
+
+    d0, P0 = update(False)
+    d1, P1 = update(True)
+    assert np.linalg.norm(d0 - d1) < 1e-10 * np.linalg.norm(d0)
+    assert np.linalg.norm(P0 - P1) < 1e-10 * np.linalg.norm(P0)

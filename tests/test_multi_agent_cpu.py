@@ -29,8 +29,18 @@ def _agent(rank, frames=8):
     scn.phase = scn.phase + 0.3 * rank
     scn.rng = np.random.Generator(np.random.PCG64(100 + rank))
     ora = OracleFilter(cfg.M, cfg.F, n_slots=64)
-    replay(record(scn, frames), ora)
-    return cfg, ora
+    ev = record(scn, frames)
+    replay(ev, ora)
+    return cfg, ora, scn, ev[-1][1]
+
+
+def _peer_truth(rank):
+    """Analytic trajectory of another agent (no filter run): used to project this agent's landmarks into its camera."""
+    from x_multi_agent_b200.synth import Scenario, SynthConfig
+    scn = Scenario(SynthConfig(M=6, F=6, K=10, seed=11))
+    scn.phase = scn.phase + 0.3 * rank
+    scn.rng = np.random.Generator(np.random.PCG64(200 + rank))
+    return scn
 
 
 def _worker(rank, world, port, q):
@@ -41,7 +51,7 @@ def _worker(rank, world, port, q):
     from oracle.ci import MultiSlamUpdate, SimpleState, SlamMatch, multi_slam_from_payload, pack_payload
     from oracle.updater import apply_ci
     from x_multi_agent_b200.ci import exchange_payloads, ring_matches
-    cfg, ora = _agent(rank)
+    cfg, ora, scn, last_meas = _agent(rank)
     s, sm = ora.newest(), ora.upd.sm
     local = torch.from_numpy(pack_payload(s, sm, cfg.F))
     gathered = exchange_payloads(local).numpy()
@@ -64,6 +74,26 @@ def _worker(rank, world, port, q):
     ok = (list(msu.inlier) == list(comp["inlier"]) and np.allclose(msu.gamma, comp["gamma"], rtol=1e-10)
           and np.linalg.norm(a.cov - b.cov) <= 1e-12 * np.linalg.norm(a.cov) and np.linalg.norm(a.p - b.p) < 1e-12
           and sum(msu.inlier) >= 2)
+    # MSCKF-MSCKF matches: the pose payload (window + 6M x 6M covariance block) replaces the full SimpleState
+    from oracle.ci import MsckfMatch, MultiMsckfUpdate, pack_pose_payload, peer_from_pose_payload
+    pose_local = torch.from_numpy(pack_pose_payload(s, cfg.M))
+    pose_gathered = exchange_payloads(pose_local).numpy()
+    peer = (rank + 1) % world
+    truth = _peer_truth(peer)
+    window = list(range(8 - cfg.M, 8))
+    trks, lms = last_meas.msckf_trks, scn.last_msckf_lms
+    ptracks = {j: truth._project(lms[j], window[cfg.M - L:]) for j, L in ((0, 6), (3, 4), (7, 5))}
+    lists = []
+    for peer_state in (peers[peer], peer_from_pose_payload(pose_gathered[peer], cfg.F)):
+        mm = [MsckfMatch(peer_state, j, z) for j, z in ptracks.items()]
+        mu = MultiMsckfUpdate(trks, list(range(len(trks))), quats, poss, s.cov, cfg.M, 1.0 / 320.0, mm, 0.1)
+        lists.append(mu)
+    a_, b_ = lists
+    ok_mm = (len(a_.S_list) == len(b_.S_list) and len(a_.multi_gate) == 3
+             and all(np.array_equal(x, y) for x, y in zip(a_.S_list, b_.S_list))
+             and all(np.array_equal(x, y) for x, y in zip(a_.H_list, b_.H_list))
+             and np.array_equal(a_.jac, b_.jac))
+    ok = ok and ok_mm
     payload_bytes, full_bytes = local.numel() * 8, sum(np.asarray(x).nbytes for x in full_states[rank][:5])
     q.put((rank, bool(ok), payload_bytes, full_bytes))
     dist.destroy_process_group()
