@@ -9,6 +9,7 @@
 // x::Matrix below (same element access syntax).
 #pragma once
 #include <cmath>
+#include <memory>
 #include <mutex>
 #include <optional>
 #include <stdexcept>
@@ -89,6 +90,61 @@ inline void xb_throw(int rc) {
   if (rc == XB_E_INVALID) throw std::invalid_argument(msg);
   throw std::runtime_error(msg);
 }
+
+/** x::SimpleState (include/x/ekf/simple_state.h:30-75, src/x/ekf/simple_state.cpp:23-65): another agent's snapshot as
+ *  it arrives from the network -- dynamic state, pose window, features, anchors and the full covariance. */
+class SimpleState {
+ public:
+  SimpleState() = delete;
+  SimpleState(std::vector<double> dynamic_state, std::vector<double> positions_state, std::vector<double> orientations_state,
+              std::vector<double> features_state, Matrix cov, std::vector<int> anchor_idxs)
+      : dynamic_state_(std::move(dynamic_state)), positions_state_(std::move(positions_state)),
+        orientations_state_(std::move(orientations_state)), features_state_(std::move(features_state)),
+        anchor_idxs_(std::move(anchor_idxs)), cov_(std::move(cov)), n_poses_((int)positions_state_.size() / 3) {}
+  int nPosesMax() const { return n_poses_; }
+  int nFeaturesMax() const { return (int)features_state_.size() / 3; }
+  const std::vector<double>& getDynamicState() const { return dynamic_state_; }
+  const std::vector<double>& getPositionState() const { return positions_state_; }
+  const std::vector<double>& getOrientationState() const { return orientations_state_; }
+  const std::vector<double>& getFeatureState() const { return features_state_; }
+  const Matrix& getCovariance() const { return cov_; }
+  const std::vector<int>& getAnchorIdxs() const { return anchor_idxs_; }
+  int getErrorStateSize() const { return (int)cov_.cols(); }
+  Vector3 getTranslation() const { return Vector3(0.0, 0.0, 0.0); }  // simple_state.h:71 (const zero in the reference)
+  /** View for the C ABI (pointers stay valid while *this lives). */
+  xb_peer_state view() const {
+    xb_peer_state ps{};
+    ps.n_poses_max = nPosesMax(); ps.n_features_max = nFeaturesMax();
+    ps.positions = positions_state_.data(); ps.orientations = orientations_state_.data();
+    ps.features = features_state_.data(); ps.anchor_idxs = anchor_idxs_.data();
+    ps.cov = cov_.data(); ps.cov_layout = XB_COL_MAJOR;
+    return ps;
+  }
+ private:
+  std::vector<double> dynamic_state_, positions_state_, orientations_state_, features_state_;
+  std::vector<int> anchor_idxs_;
+  Matrix cov_;
+  int n_poses_ = -1;
+};
+
+/** include/x/vision/types.h:83-100.  The reference identifies the own track by Track::getId(); at the preProcess seam
+ *  a track is identified by the list it sits in (0 = msckf_trks, 1 = msckf_short_trks) and its index there. */
+struct MsckfMatch {
+  std::shared_ptr<SimpleState> state;
+  int uav_id = -1;
+  Track received_track;
+  int current_track_list = 0;
+  int id_current_track = -1;
+};
+using MsckfMatches = std::vector<MsckfMatch>;
+/** include/x/vision/types.h:102-116 */
+struct SlamMatch {
+  std::shared_ptr<SimpleState> state;
+  int uav_id = -1;
+  int current_feature_id = -1;
+  int received_feature_id = -1;
+};
+using SlamMatches = std::vector<SlamMatch>;
 
 /** x::State (include/x/ekf/state.h:36-337): estimates are mirrored on the host; the N x N covariance stays on the
  *  device and is fetched lazily by getCovariance(). */
@@ -184,6 +240,25 @@ class VioUpdater : public Updater {
     iekf_iter_ = iekf_iter;
   }
   void setMeasurement(const VioMeasurement& m) { measurement_ = m; }  // vio_updater.cpp:122-124
+  /** MULTI_UAV build: what Tracker::getMsckfMatches / getSlamMatches hand over (vio_updater.cpp:185,212). */
+  void setMsckfMatches(const MsckfMatches& m) { msckf_matches_ = m; }
+  void setSlamMatches(const SlamMatches& m) { slam_matches_ = m; }
+  /** Updater::collaborativeUpdate (updater.cpp:22-36) through Ekf::processOthersMeasurement. */
+  int collaborate(xb_filter* f, double timestamp, double* xvec_out) {
+    std::vector<const SimpleState*> uniq;
+    std::vector<xb_slam_match> cm;
+    for (const auto& m : slam_matches_) {
+      size_t k = 0;
+      while (k < uniq.size() && uniq[k] != m.state.get()) ++k;
+      if (k == uniq.size()) uniq.push_back(m.state.get());
+      cm.push_back({(int)k, m.current_feature_id, m.received_feature_id});
+    }
+    std::vector<xb_peer_state> ps;
+    for (const auto* u : uniq) ps.push_back(u->view());
+    const int rc = xb_ekf_process_others(f, timestamp, ps.data(), (int)ps.size(), cm.data(), (int)cm.size(), xvec_out);
+    slam_matches_.clear();
+    return rc;
+  }
   double getTime() const override { return measurement_.timestamp; }  // vio_updater.h:60
   void fillConfig(xb_config& c) const {
     c.sigma_img = sigma_img_; c.sigma_range = sigma_range_; c.rho_0 = rho_0_; c.sigma_rho_0 = sigma_rho_0_;
@@ -209,11 +284,31 @@ class VioUpdater : public Updater {
     std::vector<int> lost(measurement_.lost_slam_trk_idxs.begin(), measurement_.lost_slam_trk_idxs.end());
     m.n_lost = (int)lost.size(); m.lost_slam_idxs = lost.data();
     xb_throw(xb_vio_set_measurement(f, &m));
+    if (!msckf_matches_.empty()) {  // consumed by the next Updater::update (msckf_update.cpp:96-139)
+      std::vector<const SimpleState*> uniq;
+      std::vector<xb_msckf_match> cm;
+      std::vector<std::vector<double>> obs;
+      for (const auto& mm : msckf_matches_) {
+        size_t k = 0;
+        while (k < uniq.size() && uniq[k] != mm.state.get()) ++k;
+        if (k == uniq.size()) uniq.push_back(mm.state.get());
+        obs.emplace_back();
+        for (const auto& o : mm.received_track) { obs.back().push_back(o.first); obs.back().push_back(o.second); }
+        cm.push_back({(int)k, mm.current_track_list, mm.id_current_track, (int)mm.received_track.size(), nullptr});
+      }
+      for (size_t j = 0; j < cm.size(); ++j) cm[j].obs = obs[j].data();
+      std::vector<xb_peer_state> ps;
+      for (const auto* u : uniq) ps.push_back(u->view());
+      xb_throw(xb_vio_set_msckf_matches(f, ps.data(), (int)ps.size(), cm.data(), (int)cm.size()));
+      msckf_matches_.clear();  // preProcess replaces the list on every update (vio_updater.cpp:185)
+    }
   }
  protected:
   bool deviceNative() const override { return true; }
  private:
   VioMeasurement measurement_;
+  mutable MsckfMatches msckf_matches_;
+  SlamMatches slam_matches_;
   double sigma_img_, sigma_range_, rho_0_, sigma_rho_0_;
   int min_track_length_;
   double sigma_landmark_, ci_msckf_w_, ci_slam_w_;
@@ -236,6 +331,9 @@ class Ekf {
     c.n_w = noise.n_w; c.n_bw = noise.n_bw; c.n_a = noise.n_a; c.n_ba = noise.n_ba;
     c.a_m_max = a_m_max; c.delta_seq_imu = delta_seq_imu; c.time_margin = time_margin_bfr;
     if (auto* v = dynamic_cast<VioUpdater*>(&updater_)) v->fillConfig(c);
+#ifdef MULTI_UAV
+    c.multi_uav = 1;  // the reference selects this flow at compile time (CMakeLists.txt: -DMULTI_UAV)
+#endif
     if (f_) { xb_destroy(f_); f_ = nullptr; }
     xb_throw(xb_create(&c, &f_));
     M_ = c.n_poses_max; F_ = c.n_features_max;
@@ -265,6 +363,17 @@ class Ekf {
     v->upload(f_);
     State out(M_, F_);
     const int rc = xb_ekf_process_update(f_, out.xvec().data());
+    xb_throw(rc);
+    if (rc == 0) return std::nullopt;
+    return out;
+  }
+  /** ekf.cpp:143-176 (MULTI_UAV): SLAM-SLAM covariance-intersection update against the peers set on the updater. */
+  std::optional<State> processOthersMeasurement(double timestamp) {
+    std::lock_guard<std::mutex> lk(mutex_);
+    auto* v = dynamic_cast<VioUpdater*>(&updater_);
+    if (!v) throw std::logic_error("Ekf::processOthersMeasurement needs a device-native updater");
+    State out(M_, F_);
+    const int rc = v->collaborate(f_, timestamp, out.xvec().data());
     xb_throw(rc);
     if (rc == 0) return std::nullopt;
     return out;

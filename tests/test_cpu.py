@@ -1,6 +1,7 @@
 """CPU-side tests (no GPU): the oracle against the reference's own code / golden vectors, the mathematical
 identities the CUDA formulation relies on, host-side logic, and the C-ABI surface of libxb200.so."""
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -299,3 +300,17 @@ def test_multi_msckf_block_is_invariant_to_the_nullspace_basis():
     d1, P1 = update(True)
     assert np.linalg.norm(d0 - d1) < 1e-10 * np.linalg.norm(d0)
     assert np.linalg.norm(P0 - P1) < 1e-10 * np.linalg.norm(P0)
+
+
+def test_cxx_binding_compiles_in_both_build_flavours():
+    """include/x/xb200_binding.hpp mirrors x::Ekf / x::VioUpdater / x::State (+ SimpleState, MsckfMatch, SlamMatch and
+    Ekf::processOthersMeasurement of the MULTI_UAV build); it must compile with and without -DMULTI_UAV."""
+    import subprocess
+    src = ROOT / "tests" / "cxx" / "multi_uav_syntax.cpp"
+    for flags in ([], ["-DMULTI_UAV"]):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{ROOT / 'include'}", *flags, os.fspath(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{ROOT / 'include'}", os.fspath(ROOT / "tests" / "cxx" / "test_x_api.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
