@@ -185,7 +185,19 @@ def run_reference(args, rank, world):
                                        "per-track and QR stages scaled linearly to 800 tracks (dense reference formulation, "
                                        "numpy/OpenBLAS fp64)", "stages_s": detail},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -197,6 +209,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=int(os.environ.get("XB_DOWNDATE_PRECISION", "0")))
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: native libraries (NCCL version banner, ...) write to fd 1 directly, so fd 1
+    # is pointed at stderr for the whole run and the result goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -422,7 +440,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci, "multi_uav_msckf": mm,
             "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac}}
-    print(json.dumps(line))
+    emit(line)
     flt.close()
     if world > 1:
         dist.destroy_process_group()
