@@ -1,0 +1,10 @@
+set -x
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+for cfg in "XB_NO_OVERLAP=1 XB_TRACK_WARPS=4" "XB_NO_OVERLAP=1 XB_TRACK_WARPS=2" "XB_NO_OVERLAP=0 XB_TRACK_WARPS=2 XB_CHOL_SHARE=4" "XB_NO_OVERLAP=0 XB_TRACK_WARPS=2 XB_CHOL_SHARE=2" "XB_NO_OVERLAP=0 XB_TRACK_WARPS=4 XB_CHOL_SHARE=4"; do
+  echo "== $cfg"
+  env $cfg timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['gate_inlier_frac_last_step'])
+print(d['stage_ms_per_update'])"
+done

@@ -4,6 +4,8 @@
 // is evaluated as   [L ; W ; z^T] = tallchol([S ; P H^T ; r^T])   (W = P H^T L^-T, z = L^-1 r)
 //                   P <- (P + P^T)/2 - W W^T ,  delta = W z
 // which is the same arithmetic with the explicit inverse replaced by a Cholesky factor.
+#include <algorithm>
+
 #include "xb_kernels.h"
 
 namespace xb {
@@ -247,34 +249,88 @@ __device__ __forceinline__ void tile_store(double* g, int ld, double (*S)[TC + 1
 }
 
 #define CP_THREADS 128
-// flags: ready[i*ct + j] (L tile published), pre[rt*ct + j] (partial sums of D_j/E_j over k <= j-2 published)
-__global__ void __launch_bounds__(CP_THREADS) k_tallchol(double* __restrict__ T, int ld, int rt, int ct, int* __restrict__ flags,
-                                                         int* __restrict__ err, double piv_tol, const double* __restrict__ diag0,
-                                                         long long* __restrict__ trace) {
+// Column range / row-skip description of one launch.  A factorisation may be split in two launches so that the first
+// tile columns are factored while the rows of the remaining columns are still being produced (xb_api.cu overlaps
+// the SLAM-row part of the Kalman update with the MSCKF track pipeline this way):
+//   launch 1: columns [0, c1), tile rows [c1, ct) skipped (their entries do not exist yet)
+//   (caller: writes the finished factor tiles L(i, j), i in [c1, ct), j < c1, and sets their ready flags -- for the
+//    Kalman update they are a plain GEMM, k_update.cu:k_wsym)
+//   launch 2: columns [c1, ct) as usual; its first diagonal tile takes all earlier panels through one pre() task.
+// A plain factorisation is {0, ct, 0, 0}.
+struct CholRange {
+  int jstart, jend;    // tile columns factored by this launch
+  int skip0, skip1;    // tile rows excluded from the TRSM work of this launch (skip0 == jend or empty)
+};
+// TRSM tile (i, jcol): left-looking accumulation over k < jcol, then the solve against L(jcol, jcol)
+__device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int ct, int i, int jcol, int* ready, int* err,
+                                            double (*Ds)[TC + 1], double (*Ws)[TC + 1], double (*Ls)[TC + 1], double* rd,
+                                            long long* trace) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const long long tr0 = trace ? gtimer() : 0;
+  double* gC = T + (size_t)i * TC * ld + (size_t)jcol * TC;
+  tile_load(Ds, gC, ld, t, CP_THREADS, false);
+  __syncthreads();
+  for (int k = 0; k < jcol; ++k) {
+    if (t == 0) { flag_spin(&ready[i * ct + k], err); flag_spin(&ready[jcol * ct + k], err); }
+    __syncthreads();
+    tile_load(Ws, T + (size_t)i * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
+    tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
+    __syncthreads();
+    tile_gemm_sub(Ds, Ws, Ls, t, CP_THREADS);
+    __syncthreads();
+  }
+  const long long tr1 = trace ? gtimer() : 0;
+  if (t == 0) flag_spin(&ready[jcol * ct + jcol], err);
+  __syncthreads();
+  tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)jcol * TC, ld, t, CP_THREADS, false);
+  __syncthreads();
+  if (t < TC) { const double d = Ls[t][t]; rd[t] = d != 0.0 ? 1.0 / d : 0.0; }
+  __syncthreads();
+  if (warp == 0) warp_trsm32(Ds, Ls, rd, lane);
+  __syncthreads();
+  const long long tr2 = trace ? gtimer() : 0;
+  tile_store(gC, ld, Ds, t, CP_THREADS);
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    st_release(&ready[i * ct + jcol], 1);
+    if (trace && i < ct + 2 && i >= jcol + 2) {
+      long long* o = trace + 6 * (size_t)(ct + jcol * 2 + (i - jcol - 2) % 2);
+      o[0] = i; o[1] = jcol; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
+    }
+  }
+}
+// flags: ready[i*ct + j] (L tile published), pre[rt*ct + j] (partial sums of D_j/E_j over the earlier panels published)
+__global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__ T, int ld, int rt, int ct, CholRange cr,
+                                                         int* __restrict__ flags, int* __restrict__ err, double piv_tol,
+                                                         const double* __restrict__ diag0, long long* __restrict__ trace) {
   __shared__ double Ds[TC][TC + 1], Es[2][TC][TC + 1], Ws[TC][TC + 1], Ls[TC][TC + 1];
   __shared__ double dorig[TC], rd[TC];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   int* ready = flags;
   int* pre = flags + (size_t)rt * ct;
+  const int jstart = cr.jstart, jend = cr.jend;
 
   if (blockIdx.x == 0) {
     // ------------------------------------------------------------------ critical-path CTA
     int eb = 0;  // Es[eb^1] holds L(j, j-1)^T-major copy from the previous column
-    for (int j = 0; j < ct; ++j) {
+    for (int j = jstart; j < jend; ++j) {
       const long long tr0 = trace ? gtimer() : 0;
-      if (j >= 2) {
+      const bool first = j == jstart;
+      const bool has_e = !(j + 1 >= cr.skip0 && j + 1 < cr.skip1);  // E = (j+1, j) exists in this launch
+      if (first ? jstart >= 1 : j >= 2) {
         if (t == 0) flag_spin(&pre[j], err);
         __syncthreads();
       }
       double* gD = T + (size_t)j * TC * ld + (size_t)j * TC;
       double* gE = T + (size_t)(j + 1) * TC * ld + (size_t)j * TC;
       tile_load(Ds, gD, ld, t, CP_THREADS, false);
-      tile_load(Es[eb], gE, ld, t, CP_THREADS, false);
+      if (has_e) tile_load(Es[eb], gE, ld, t, CP_THREADS, false);
       __syncthreads();
       if (t < TC) dorig[t] = diag0 ? diag0[j * TC + t] : 0.0;
       __syncthreads();
       // previous column's E (= L(j, j-1)) is in Es[eb^1] row-major; k-major copy into Ws for the rank-32 updates
-      if (j >= 1) {
+      if (!first) {
         for (int e = t; e < TC * TC; e += CP_THREADS) { const int r = e >> 5, c = e & 31; Ws[c][r] = Es[eb ^ 1][r][c]; }
         __syncthreads();
         tile_gemm_sub(Ds, Ws, Ws, t, CP_THREADS);  // D -= L(j,j-1) L(j,j-1)^T
@@ -285,7 +341,7 @@ __global__ void __launch_bounds__(CP_THREADS) k_tallchol(double* __restrict__ T,
         warp_potrf32(Ds, Ls, dorig, piv_tol, lane);
         const double d = Ds[lane][lane];
         rd[lane] = d != 0.0 ? 1.0 / d : 0.0;
-      } else if (j >= 1) {
+      } else if (!first && has_e) {
         // meanwhile: E -= L(j+1, j-1) L(j, j-1)^T   (L(j+1,j-1) comes from a worker)
         if (t == 32) flag_spin(&ready[(j + 1) * ct + (j - 1)], err);
         asm volatile("bar.sync 1, 96;" ::: "memory");
@@ -321,18 +377,20 @@ __global__ void __launch_bounds__(CP_THREADS) k_tallchol(double* __restrict__ T,
       const long long tr2 = trace ? gtimer() : 0;
       // publish L(j,j) (warps 1-3) while warp 0 solves E against it
       if (warp == 0) {
-        warp_trsm32(Es[eb], Ds, rd, lane);
+        if (has_e) warp_trsm32(Es[eb], Ds, rd, lane);
       } else {
         tile_store(gD, ld, Ds, t - 32, 96);
         asm volatile("bar.sync 1, 96;" ::: "memory");
         if (t == 32) { __threadfence(); st_release(&ready[j * ct + j], 1); }
       }
       __syncthreads();
-      tile_store(gE, ld, Es[eb], t, CP_THREADS);
+      if (has_e) tile_store(gE, ld, Es[eb], t, CP_THREADS);
       __syncthreads();
       if (t == 0) {
-        __threadfence();
-        st_release(&ready[(j + 1) * ct + j], 1);
+        if (has_e) {
+          __threadfence();
+          st_release(&ready[(j + 1) * ct + j], 1);
+        }
         if (trace) {
           long long* o = trace + 6 * (size_t)j;
           o[0] = j; o[1] = j; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
@@ -344,108 +402,104 @@ __global__ void __launch_bounds__(CP_THREADS) k_tallchol(double* __restrict__ T,
   }
 
   // -------------------------------------------------------------------- workers
-  // task list, dependency-ordered:  for j = 0..ct-1:  [pre(j+2) if j+2 < ct]... see task_decode
+  // task list, dependency-ordered:
+  //   B. pre(jstart), covering the panels k <= jstart-1 (there is no in-CTA hand-over into the first column)
+  //   C. for j = jstart..jend-1: [pre(j+1) if j+1 >= 2 and j+1 < jend; it needs only columns <= j-1],
+  //      then the TRSM tiles (i, j), i = j+2..rt-1 without the skipped rows
   const int nworkers = gridDim.x - 1;
-  // tasks per column j: TRSM tiles i = j+2..rt-1  (rt-j-2 of them), preceded by pre(j+1) when 2 <= j+1 < ct
-  // (pre(j+1) needs only columns <= j-1, so it is scheduled before the TRSM tasks of column j)
+  const int nB = jstart >= 1 ? 1 : 0;
   int task = blockIdx.x - 1;
-  int jcol = 0, base = 0;
+  int jcol = jstart, base = nB;
   while (true) {
-    // advance (jcol, base) so that task falls into column jcol's segment
-    int seg;
-    for (;;) {
-      if (jcol >= ct) return;
-      const int has_pre = (jcol + 1 >= 2 && jcol + 1 < ct) ? 1 : 0;
-      seg = has_pre + (rt - jcol - 2);
-      if (task < base + seg) break;
-      base += seg;
-      ++jcol;
+    int jp = -1, kmax = -1, trsm_i = -1, trsm_j = jcol;
+    if (task < nB) {
+      jp = jstart;
+      kmax = jstart - 1;
+    } else {
+      // advance (jcol, base) so that task falls into column jcol's segment
+      int seg, has_pre, s0, slen;
+      for (;;) {
+        if (jcol >= jend) return;
+        has_pre = (jcol + 1 >= 2 && jcol + 1 < jend) ? 1 : 0;
+        s0 = max(cr.skip0, jcol + 2);
+        slen = max(0, cr.skip1 - s0);
+        seg = has_pre + (rt - jcol - 2) - slen;
+        if (task < base + seg) break;
+        base += seg;
+        ++jcol;
+      }
+      const int local = task - base;
+      if (has_pre && local == 0) {
+        jp = jcol + 1;
+        kmax = jp - 2;
+      } else {
+        trsm_i = jcol + 2 + (local - has_pre);
+        if (trsm_i >= s0) trsm_i += slen;
+        trsm_j = jcol;
+      }
     }
-    const int has_pre = (jcol + 1 >= 2 && jcol + 1 < ct) ? 1 : 0;
-    const int local = task - base;
-    const int ty = (t & 63) >> 3, tx = t & 7;
-    if (has_pre && local == 0) {
-      // ---- pre(jp): D_jp -= sum_{k<=jp-2} L(jp,k) L(jp,k)^T ; E_jp -= sum L(jp+1,k) L(jp,k)^T ; in place
-      const int jp = jcol + 1;
+    if (jp >= 0) {
+      // ---- pre(jp): D_jp -= sum_{k<=kmax} L(jp,k) L(jp,k)^T ; E_jp -= sum L(jp+1,k) L(jp,k)^T ; in place
+      const bool has_e = !(jp + 1 >= cr.skip0 && jp + 1 < cr.skip1);
       double* gD = T + (size_t)jp * TC * ld + (size_t)jp * TC;
       double* gE = T + (size_t)(jp + 1) * TC * ld + (size_t)jp * TC;
       tile_load(Ds, gD, ld, t, CP_THREADS, false);
-      tile_load(Es[0], gE, ld, t, CP_THREADS, false);
+      if (has_e) tile_load(Es[0], gE, ld, t, CP_THREADS, false);
       __syncthreads();
-      for (int k = 0; k <= jp - 2; ++k) {
-        if (t == 0) { flag_spin(&ready[jp * ct + k], err); flag_spin(&ready[(jp + 1) * ct + k], err); }
+      for (int k = 0; k <= kmax; ++k) {
+        if (t == 0) { flag_spin(&ready[jp * ct + k], err); if (has_e) flag_spin(&ready[(jp + 1) * ct + k], err); }
         __syncthreads();
         tile_load(Ws, T + (size_t)jp * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);          // L(jp,k) k-major
-        tile_load(Ls, T + (size_t)(jp + 1) * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);    // L(jp+1,k) k-major
+        if (has_e) tile_load(Ls, T + (size_t)(jp + 1) * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);    // L(jp+1,k) k-major
         __syncthreads();
         if (t < 64) tile_gemm_sub(Ds, Ws, Ws, t, 64);
-        else tile_gemm_sub(Es[0], Ls, Ws, t - 64, 64);
+        else if (has_e) tile_gemm_sub(Es[0], Ls, Ws, t - 64, 64);
         __syncthreads();
       }
       tile_store(gD, ld, Ds, t, CP_THREADS);
-      tile_store(gE, ld, Es[0], t, CP_THREADS);
+      if (has_e) tile_store(gE, ld, Es[0], t, CP_THREADS);
       __syncthreads();
       if (t == 0) { __threadfence(); st_release(&pre[jp], 1); }
     } else {
-      // ---- TRSM tile (i, jcol), i >= jcol+2
-      const int i = jcol + 2 + (local - has_pre);
-      const long long tr0 = trace ? gtimer() : 0;
-      double* gC = T + (size_t)i * TC * ld + (size_t)jcol * TC;
-      tile_load(Ds, gC, ld, t, CP_THREADS, false);
-      __syncthreads();
-      for (int k = 0; k < jcol; ++k) {
-        if (t == 0) { flag_spin(&ready[i * ct + k], err); flag_spin(&ready[jcol * ct + k], err); }
-        __syncthreads();
-        tile_load(Ws, T + (size_t)i * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
-        tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
-        __syncthreads();
-        tile_gemm_sub(Ds, Ws, Ls, t, CP_THREADS);
-        __syncthreads();
-      }
-      const long long tr1 = trace ? gtimer() : 0;
-      if (t == 0) flag_spin(&ready[jcol * ct + jcol], err);
-      __syncthreads();
-      tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)jcol * TC, ld, t, CP_THREADS, false);
-      __syncthreads();
-      if (t < TC) { const double d = Ls[t][t]; rd[t] = d != 0.0 ? 1.0 / d : 0.0; }
-      __syncthreads();
-      if (warp == 0) warp_trsm32(Ds, Ls, rd, lane);
-      __syncthreads();
-      const long long tr2 = trace ? gtimer() : 0;
-      tile_store(gC, ld, Ds, t, CP_THREADS);
-      __syncthreads();
-      if (t == 0) {
-        __threadfence();
-        st_release(&ready[i * ct + jcol], 1);
-        if (trace && i < ct + 2) {
-          long long* o = trace + 6 * (size_t)(ct + jcol * 2 + (i - jcol - 2) % 2);
-          o[0] = i; o[1] = jcol; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
-        }
-      }
-      (void)ty; (void)tx;
+      worker_trsm(T, ld, ct, trsm_i, trsm_j, ready, err, Ds, Ws, Ls, rd, trace);
     }
     __syncthreads();
     task += nworkers;
   }
 }
 
-void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
-              const double* diag0, long long* trace) {
-  const int rt = rows_pad / TC, ct = cols_pad / TC;
-  int ntasks = 0;
-  for (int j = 0; j < ct; ++j) ntasks += ((j + 1 >= 2 && j + 1 < ct) ? 1 : 0) + (rt - j - 2);
-  static int max_workers = 0;
-  if (!max_workers) {
+static int tallchol_max_ctas() {
+  static int max_ctas = 0;
+  if (!max_ctas) {
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tallchol, CP_THREADS, 0);
-    max_workers = sms * (per_sm > 0 ? per_sm : 1) - 1;  // all CTAs must be co-resident (persistent dataflow)
+    max_ctas = sms * (per_sm > 0 ? per_sm : 1);  // all CTAs of a launch must be co-resident (persistent dataflow)
   }
+  return max_ctas;
+}
+// share: fraction denominator of the device this launch may occupy (2 = half of the co-resident CTA slots) so that
+// dataflow launches running concurrently on different streams can always be resident together.
+void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int jstart_cols, int jend_cols,
+                    int phase, int* flags, int* err, double piv_tol, const double* diag0, long long* trace, int share) {
+  const int rt = rows_pad / TC, ct = cols_pad / TC;
+  CholRange cr{jstart_cols / TC, jend_cols / TC, 0, 0};
+  if (phase == 1) { cr.skip0 = cr.jend; cr.skip1 = ct; }
+  int ntasks = cr.jstart >= 1 ? 1 : 0;
+  for (int j = cr.jstart; j < cr.jend; ++j) {
+    const int s0 = std::max(cr.skip0, j + 2), slen = std::max(0, cr.skip1 - s0);
+    ntasks += ((j + 1 >= 2 && j + 1 < cr.jend) ? 1 : 0) + (rt - j - 2) - slen;
+  }
+  const int max_workers = std::max(1, tallchol_max_ctas() / std::max(1, share) - 1);
   const int nworkers = ntasks < max_workers ? (ntasks > 0 ? ntasks : 1) : max_workers;
-  cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)rt * ct + ct + 1), s);
-  k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, flags, err, piv_tol, diag0, trace);
+  if (phase != 2) cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)rt * ct + ct + 1), s);
+  k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace);
   count_launch();
+}
+void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
+              const double* diag0, long long* trace) {
+  tallchol_range(s, T, ld, rows_pad, cols_pad, 0, cols_pad, 0, flags, err, piv_tol, diag0, trace, 1);
 }
 
 // ------------------------------------------------------------------------------------------------

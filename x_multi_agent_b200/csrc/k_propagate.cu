@@ -218,13 +218,21 @@ __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip,
   }
 }
 
-void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,
-                      const ImuSample& in, const PropParams& pp, double* FQ) {
+void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,
+                       const PropParams& pp, double* FQ) {
   if (n_steps <= 0) return;
   k_prop_means<<<1, 128, 0, s>>>(xv, LX, NS, start, n_steps, in, pp, FQ);
   count_launch();
+}
+void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ) {
+  if (n_steps <= 0) return;
   k_prop_strips<<<(N + 127) / 128, 128, 0, s>>>(strip, N, NS, start, n_steps, FQ);
   count_launch();
+}
+void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,
+                      const ImuSample& in, const PropParams& pp, double* FQ) {
+  launch_prop_means(s, xv, LX, NS, start, n_steps, in, pp, FQ);
+  launch_prop_strips(s, strip, N, NS, start, n_steps, FQ);
 }
 
 }  // namespace xb

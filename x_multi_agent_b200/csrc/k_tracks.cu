@@ -12,6 +12,9 @@
 //   gate   gamma = (Pi r)^T (Pi J P J^T Pi + s^2 I)^-1 (Pi r)       (2L x 2L, identical value)
 //   update jac0^T jac0 = J^T J - B^T B,  jac0^T res0 = J^T r - B^T (U^T r),   B = U^T J  (3 x 6M)
 // so the 2L-3 dense rows are never formed: a track emits its sparse J blocks and the 3 dense rows B.
+#include <algorithm>
+#include <cstdlib>
+
 #include "xb_kernels.h"
 #include "xb_svd4.cuh"
 
@@ -609,8 +612,12 @@ size_t tracks_smem_bytes(int M, int Lmax, int warps, int mode) {
 
 int launch_tracks(cudaStream_t s, const TrackParams& tp) {
   if (tp.n_tracks <= 0) return 0;
-  int warps = 4;
-  const size_t cap = 110 * 1024;  // two CTAs per SM
+  // two warps (tracks) per CTA: the CTA's shared memory (<= 55 KB) leaves room on every SM for the dataflow Cholesky CTAs
+  // that xb_api.cu runs concurrently on the side stream
+  static int warps_cfg = 0;
+  if (!warps_cfg) { const char* e = getenv("XB_TRACK_WARPS"); warps_cfg = e ? std::max(1, std::min(4, atoi(e))) : 2; }
+  int warps = warps_cfg;
+  const size_t cap = 110 * 1024;  // two CTAs per SM at four warps
   while (warps > 1 && tracks_smem_bytes(tp.M, tp.Lmax, warps, tp.mode) > cap) --warps;
   const size_t bytes = tracks_smem_bytes(tp.M, tp.Lmax, warps, tp.mode);
   if (bytes > cap) return -1;

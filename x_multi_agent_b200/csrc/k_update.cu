@@ -24,7 +24,12 @@ namespace xb {
 #define NOM 21  // |Omega| = 15 core + 6 clone states
 #define CBZ 4   // split-K partials of the thin Woodbury GEMM
 
-// PHt[i, ms + 2j + r] = sum_e P[i, col_e] * val[j][r][e]
+// Column order of the compressed measurement inside the tall buffer (UpdateDims): the SLAM rows come first,
+//   columns [0, 2 nslam) SLAM rows | padding up to s_pad | columns [ro, ro + 6M) slab rows Rg | padding up to m_pad
+// so that everything belonging to the SLAM columns -- including the first s_pad/32 tile columns of the Cholesky
+// factorisation -- can be computed before Rg exists (xb_api.cu runs it next to the MSCKF track pipeline).
+//
+// PHt[i, 2j + r] = sum_e P[i, col_e] * val[j][r][e]
 __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int* __restrict__ scols,
                            const double* __restrict__ svals, double* __restrict__ T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
@@ -37,15 +42,42 @@ __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int
     a0 = fma(p, svals[30 * j + e], a0);
     a1 = fma(p, svals[30 * j + 15 + e], a1);
   }
-  double* row = T + (size_t)(d.m_pad + i) * d.ld + d.ms + 2 * j;
+  double* row = T + (size_t)(d.m_pad + i) * d.ld + 2 * j;
   row[0] = a0;
   row[1] = a1;
 }
 
-// S[ms + 2j + r, c] = sum_e val[j][r][e] * PHt[col_e, c]
-__global__ void k_s_slam(UpdateDims d, const int* __restrict__ scols, const double* __restrict__ svals, double* __restrict__ T) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-  if (c >= d.m || j >= d.nslam) return;
+// After the SLAM tile columns are factored (S11 = L11 L11^T, W1s = (P Hs^T) L11^-T, W2s on the Omega rows), the
+// sub-diagonal block of the factor needs no triangular solve:
+//   L21 = S21 L11^-T = Rg (sym(P) Hs^T)[pose rows] L11^-T = Rg * Wsym,   Wsym = (W1s + W2s)/2 on the pose rows
+// (W2s differs from W1s on the newest clone's 6 rows only).  This kernel gathers Wsym (6M x s_pad) into Bc, and
+// publishes the dataflow flags of the L21 tiles, which the GEMM of launch_build_slab_part writes.
+__global__ void k_wsym(UpdateDims d, const int* __restrict__ omega_inv, const double* __restrict__ T, double* __restrict__ Bc,
+                       int* __restrict__ ready, int ct) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (b == 0 && c < (ct - d.s_pad / 32) * (d.s_pad / 32)) {
+    const int i = d.s_pad / 32 + c / (d.s_pad / 32), j = c % (d.s_pad / 32);
+    ready[i * ct + j] = 1;
+  }
+  if (c >= d.s_pad || b >= d.ms) return;
+  double v = T[(size_t)(d.m_pad + XB_CORE + b) * d.ld + c];
+  const int k = omega_inv[XB_CORE + b];
+  if (k >= 0) v = 0.5 * (v + T[(size_t)(d.m_pad + d.n_pad + 32 + k) * d.ld + c]);
+  Bc[(size_t)b * d.s_pad + c] = v;
+}
+void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc, int* ready) {
+  if (d.nslam <= 0) return;
+  dim3 g((d.s_pad + 127) / 128, d.ms);
+  k_wsym<<<g, 128, 0, s>>>(d, omega_inv, T, Bc, ready, d.m_pad / 32);
+  count_launch();
+}
+
+// S[2j + r, c] = sum_e val[j][r][e] * PHt[col_e, c]   for the columns c0 + [0, nc)
+__global__ void k_s_slam(UpdateDims d, int c0, int nc, const int* __restrict__ scols, const double* __restrict__ svals,
+                         double* __restrict__ T) {
+  const int cl = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (cl >= nc || j >= d.nslam) return;
+  const int c = c0 + cl;
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
   for (int e = 0; e < 15; ++e) {
@@ -53,30 +85,33 @@ __global__ void k_s_slam(UpdateDims d, const int* __restrict__ scols, const doub
     a0 = fma(svals[30 * j + e], p, a0);
     a1 = fma(svals[30 * j + 15 + e], p, a1);
   }
-  T[(size_t)(d.ms + 2 * j) * d.ld + c] = a0;
-  T[(size_t)(d.ms + 2 * j + 1) * d.ld + c] = a1;
+  T[(size_t)(2 * j) * d.ld + c] = a0;
+  T[(size_t)(2 * j + 1) * d.ld + c] = a1;
 }
 
-// diagonal (+var on real rows, 1 on padding) and the r_eff row
-__global__ void k_s_finish(UpdateDims d, const double* __restrict__ Lg, int ldr, const double* __restrict__ zg,
+// diagonal (+var on real rows, 1 on padding) and the r_eff row, for the rows/columns a in c0 + [0, nc)
+__global__ void k_s_finish(UpdateDims d, int c0, int nc, const double* __restrict__ Lg, int ldr, const double* __restrict__ zg,
                            const int* __restrict__ scols, const double* __restrict__ svals, const double* __restrict__ sres,
                            const double* __restrict__ corr, double var, double* __restrict__ T) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= d.m_pad) return;
+  const int al = blockIdx.x * blockDim.x + threadIdx.x;
+  if (al >= nc) return;
+  const int a = c0 + al;
   double* reff = T + (size_t)(d.m_pad + d.n_pad) * d.ld;
-  if (a >= d.m) {
+  const bool slam = a < d.ns2, slab = a >= d.ro && a < d.ro + d.ms;
+  if (!slam && !slab) {
     T[(size_t)a * d.ld + a] = 1.0;
     reff[a] = 0.0;
     return;
   }
   T[(size_t)a * d.ld + a] += var;
   double r;
-  if (a < d.ms) {
-    r = zg[a];
+  if (slab) {
+    const int ar = a - d.ro;
+    r = zg[ar];
     if (corr)
-      for (int b = 0; b < d.ms; ++b) r = fma(Lg[(size_t)b * ldr + a], corr[XB_CORE + b], r);  // Rg[a][b] = Lg[b][a]
+      for (int b = 0; b < d.ms; ++b) r = fma(Lg[(size_t)b * ldr + ar], corr[XB_CORE + b], r);  // Rg[a][b] = Lg[b][a]
   } else {
-    const int j = (a - d.ms) >> 1, h = (a - d.ms) & 1;
+    const int j = a >> 1, h = a & 1;
     r = sres[2 * j + h];
     if (corr)
       for (int e = 0; e < 15; ++e) r = fma(svals[30 * j + 15 * h + e], corr[scols[15 * j + e]], r);
@@ -84,30 +119,43 @@ __global__ void k_s_finish(UpdateDims d, const double* __restrict__ Lg, int ldr,
   reff[a] = r;
 }
 
-void launch_sym_lower(cudaStream_t s, double* T, int ld, int m);
-void launch_build_pht(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
-                      const double* svals, double* T) {
-  // slab columns: PHt[:, 0:ms] = P[:, pose] * Rg^T
-  gemm_nt(s, d.N, d.ms, d.ms, 1.0, P + XB_CORE, d.N, Rg, ldr, 0.0, T + (size_t)d.m_pad * d.ld, d.ld);
-  if (d.nslam > 0) {
+void launch_sym_lower(cudaStream_t s, double* T, int ld, int r0, int r1, int c0);
+void launch_omega_rows(cudaStream_t s, const UpdateDims& d, int c0, int nc, const double* P, const double* Lg, int ldr,
+                       const int* scols, const double* svals, const int* omega, double* T);
+
+// Everything of the tall buffer that lives on the SLAM columns [0, s_pad): PHt, S[slam, slam], diagonal, r_eff, Omega/V rows.
+void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
+                            const double* sres, const double* corr_total, double var, const int* omega, double* T) {
+  if (d.nslam <= 0) return;
+  {
     dim3 g((d.N + 127) / 128, d.nslam);
     k_pht_slam<<<g, 128, 0, s>>>(d, P, scols, svals, T);
     count_launch();
   }
-}
-
-void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, const double* zg, const int* scols,
-                    const double* svals, const double* sres, const double* corr_total, double var, double* T) {
-  // slab rows: S[0:ms, 0:m] = Rg * PHt[pose rows, 0:m]
-  gemm_nn(s, d.ms, d.m, d.ms, 1.0, Rg, ldr, T + (size_t)(d.m_pad + XB_CORE) * d.ld, d.ld, 0.0, T, d.ld);
-  if (d.nslam > 0) {
-    dim3 g((d.m + 127) / 128, d.nslam);
-    k_s_slam<<<g, 128, 0, s>>>(d, scols, svals, T);
+  {
+    dim3 g((d.ns2 + 127) / 128, d.nslam);
+    k_s_slam<<<g, 128, 0, s>>>(d, 0, d.ns2, scols, svals, T);
     count_launch();
   }
-  launch_sym_lower(s, T, d.ld, d.m);
-  k_s_finish<<<(d.m_pad + 127) / 128, 128, 0, s>>>(d, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
+  launch_sym_lower(s, T, d.ld, 0, d.ns2, 0);
+  k_s_finish<<<(d.s_pad + 127) / 128, 128, 0, s>>>(d, 0, d.s_pad, nullptr, 0, nullptr, scols, svals, sres, corr_total, var, T);
   count_launch();
+  launch_omega_rows(s, d, 0, d.ns2, P, nullptr, 0, scols, svals, omega, T);
+}
+
+// The slab columns [ro, m_pad) once Rg exists: PHt[:, slab] = P[:, pose] Rg^T, S22 = Rg * PHt[pose rows, slab], and the
+// finished factor block L21 = Rg * Wsym on the SLAM columns (k_wsym).
+void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
+                            const double* zg, const int* scols, const double* svals, const double* sres,
+                            const double* corr_total, double var, const int* omega, double* T, const double* Bc) {
+  double* PHt = T + (size_t)d.m_pad * d.ld;
+  if (d.nslam > 0) gemm_nn(s, d.ms, d.ns2, d.ms, 1.0, Rg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
+  gemm_nt(s, d.N, d.ms, d.ms, 1.0, P + XB_CORE, d.N, Rg, ldr, 0.0, PHt + d.ro, d.ld);
+  gemm_nn(s, d.ms, d.ms, d.ms, 1.0, Rg, ldr, PHt + (size_t)XB_CORE * d.ld + d.ro, d.ld, 0.0, T + (size_t)d.ro * d.ld + d.ro, d.ld);
+  launch_sym_lower(s, T, d.ld, d.ro, d.ro + d.ms, d.ro);
+  k_s_finish<<<(d.m_pad - d.ro + 127) / 128, 128, 0, s>>>(d, d.ro, d.m_pad - d.ro, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
+  count_launch();
+  launch_omega_rows(s, d, d.ro, d.ms, P, Lg, ldr, scols, svals, omega, T);
 }
 
 // dense-H path: S += diag(rdiag) (+ identity padding), r_eff = res + H corr
@@ -128,18 +176,20 @@ __global__ void k_dense_finish(int m, int m_pad, int n_pad, int N, const double*
   reff[a] = r;
 }
 // ---- Omega rows for the VIO (structured Hc) path ------------------------------------------------------
-__global__ void k_omega_rows(UpdateDims d, const double* __restrict__ P, const double* __restrict__ Lg, int ldr,
+__global__ void k_omega_rows(UpdateDims d, int c0, int nc, const double* __restrict__ P, const double* __restrict__ Lg, int ldr,
                              const int* __restrict__ scols, const double* __restrict__ svals, const int* __restrict__ omega,
                              double* __restrict__ T) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-  if (a >= d.m) return;
+  const int al = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (al >= nc) return;
+  const int a = c0 + al;
   const int ok = omega[k];
   double v = 0.0, a2 = 0.0;
-  if (a < d.ms) {
-    if (ok >= XB_CORE && ok < XB_CORE + d.ms) v = Lg[(size_t)(ok - XB_CORE) * ldr + a];  // Rg[a][b] = Lg[b][a]
-    for (int b = 0; b < d.ms; ++b) a2 = fma(P[(size_t)(XB_CORE + b) * d.N + ok], Lg[(size_t)b * ldr + a], a2);
+  if (a >= d.ro) {
+    const int ar = a - d.ro;
+    if (ok >= XB_CORE && ok < XB_CORE + d.ms) v = Lg[(size_t)(ok - XB_CORE) * ldr + ar];  // Rg[a][b] = Lg[b][a]
+    for (int b = 0; b < d.ms; ++b) a2 = fma(P[(size_t)(XB_CORE + b) * d.N + ok], Lg[(size_t)b * ldr + ar], a2);
   } else {
-    const int j = (a - d.ms) >> 1, h = (a - d.ms) & 1;
+    const int j = a >> 1, h = a & 1;
     for (int e = 0; e < 15; ++e) {
       const int col = scols[15 * j + e];
       const double hv = svals[30 * j + 15 * h + e];
@@ -161,10 +211,10 @@ __global__ void k_omega_rows_dense(int m, int m_pad, int n_pad, int N, const dou
   T[(size_t)(m_pad + n_pad + 32 + k) * m_pad + a] = a2;
   T[(size_t)(m_pad + n_pad + 64 + k) * m_pad + a] = H[(size_t)a * N + ok];
 }
-// lower(S) <- lower((S + S^T)/2)
-__global__ void k_sym_lower(double* __restrict__ T, int ld, int m) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
-  if (r < m && c < r) T[(size_t)r * ld + c] = 0.5 * (T[(size_t)r * ld + c] + T[(size_t)c * ld + r]);
+// lower(S) <- lower((S + S^T)/2) for the rows [r0, r1), columns >= c0
+__global__ void k_sym_lower(double* __restrict__ T, int ld, int r0, int r1, int c0) {
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x, r = r0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (r < r1 && c < r) T[(size_t)r * ld + c] = 0.5 * (T[(size_t)r * ld + c] + T[(size_t)c * ld + r]);
 }
 
 // After the tile Cholesky and the thin GEMM  Cb = [W1 ; aux ; dW ; Vt] [z ; dW ; Vt]^T  (rows n_pad+64+k of Cb hold
@@ -304,7 +354,7 @@ void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, co
                           const double* res, const double* rdiag, const double* corr_total, const int* omega, double* T) {
   gemm_nt(s, N, m, N, 1.0, P, N, H, N, 0.0, T + (size_t)m_pad * m_pad, m_pad);          // P H^T
   gemm_nn(s, m, m, N, 1.0, H, N, T + (size_t)m_pad * m_pad, m_pad, 0.0, T, m_pad);      // H (P H^T)
-  launch_sym_lower(s, T, m_pad, m);
+  launch_sym_lower(s, T, m_pad, 0, m, 0);
   {
     dim3 g((m + 127) / 128, NOM);
     k_omega_rows_dense<<<g, 128, 0, s>>>(m, m_pad, n_pad, N, P, H, omega, T);
@@ -314,15 +364,17 @@ void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, co
   count_launch();
 }
 
-void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Lg, int ldr, const int* scols,
-                       const double* svals, const int* omega, double* T) {
-  dim3 g((d.m + 127) / 128, NOM);
-  k_omega_rows<<<g, 128, 0, s>>>(d, P, Lg, ldr, scols, svals, omega, T);
+void launch_omega_rows(cudaStream_t s, const UpdateDims& d, int c0, int nc, const double* P, const double* Lg, int ldr,
+                       const int* scols, const double* svals, const int* omega, double* T) {
+  if (nc <= 0) return;
+  dim3 g((nc + 127) / 128, NOM);
+  k_omega_rows<<<g, 128, 0, s>>>(d, c0, nc, P, Lg, ldr, scols, svals, omega, T);
   count_launch();
 }
-void launch_sym_lower(cudaStream_t s, double* T, int ld, int m) {
-  dim3 b(32, 8), g((m + 31) / 32, (m + 7) / 8);
-  k_sym_lower<<<g, b, 0, s>>>(T, ld, m);
+void launch_sym_lower(cudaStream_t s, double* T, int ld, int r0, int r1, int c0) {
+  if (r1 <= r0) return;
+  dim3 b(32, 8), g((r1 - c0 + 31) / 32, (r1 - r0 + 7) / 8);
+  k_sym_lower<<<g, b, 0, s>>>(T, ld, r0, r1, c0);
   count_launch();
 }
 void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,

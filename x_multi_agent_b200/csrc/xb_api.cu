@@ -96,9 +96,11 @@ struct ListDev {
 };
 
 enum { ST_ASSEMBLE, ST_MANAGE, ST_TRACKS, ST_GRAM, ST_CHOLG, ST_SLAMROWS, ST_BUILD, ST_TALLCHOL, ST_CORRECT, ST_DOWNDATE,
-       ST_POST, ST_STORE, ST_PROPAGATE, ST_COUNT };
+       ST_POST, ST_STORE, ST_PROPAGATE, ST_SIDE_SLAM, ST_SIDE_CHOL, ST_SIDE_MEANS, ST_COUNT };
+// the "side_*" stages run on the filter's internal side streams, concurrently with the stages listed before them
 static const char* kStageNames[ST_COUNT] = {"assemble", "manage", "tracks", "gram", "chol_gram", "slam_rows", "build_s_pht",
-                                            "tallchol", "correct", "downdate", "post_update", "store", "propagate"};
+                                            "tallchol", "correct", "downdate", "post_update", "store", "propagate",
+                                            "side_slam_part", "side_tallchol_slam_cols", "side_prop_means"};
 struct ProfSpan { int stage; cudaEvent_t e0, e1; };
 
 struct xb_filter {
@@ -112,6 +114,20 @@ struct xb_filter {
   int M, F, N, LX, NS, NG;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // internal side streams: (a) the SLAM-column part of the Kalman update (rows, P H^T, S block, the first tile columns of
+  // the Cholesky factorisation) runs next to the MSCKF track pipeline; (b) the means of the re-propagation run next to the
+  // covariance downdate.  Joined back into `stream` with events; nothing outside the library sees them.
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_side = nullptr, ev_corr = nullptr, ev_means = nullptr;
+  bool side_pending = false;   // a construct call has forked the SLAM part; apply_constructed joins it
+  bool slam_part_done = false; // the tall buffer already holds the SLAM-column part for the pending update
+  bool side_used_corr = false; // ... and it was built with a non-zero correction_total
+  bool xw_final = false;       // no estimate changed since ev_corr was recorded
+  bool overlap = true;         // XB_NO_OVERLAP=1 runs everything on the one stream
+  int chol_share = 4;          // concurrent dataflow launches each take 1/chol_share of the co-resident CTA slots
+  double* d_Bc = nullptr;      // copy of (P Hs^T)[pose rows] (6M x s_pad)
+  int* d_flags_g = nullptr;    // dataflow flags of the Gram factorisation (may run while the tall buffer is being factored)
+  double* d_FQ2 = nullptr;     // F_d / Q_d of the re-propagation steps
   // ring buffer (state_buffer.cpp)
   double* d_xv = nullptr;      // NS x LX
   double* d_strip = nullptr;   // NS x 15 x N
@@ -139,8 +155,17 @@ struct xb_filter {
   ListDev l_slam, l_msckf, l_short, l_newstd, l_newms;
   std::vector<int> lost;
   double* d_slam_chi2 = nullptr;
-  double* h_pin = nullptr;  // pinned staging
+  // pinned staging rings: a region is reused only after the copies issued from it have completed (event wait, no
+  // stream-wide synchronisation on the hot path)
+  static constexpr int kPinRing = 4;
+  double* h_pin = nullptr;  // kPinRing regions of pin_bytes: measurement lists
   size_t pin_bytes = 0;
+  cudaEvent_t pin_ev[kPinRing] = {nullptr, nullptr, nullptr, nullptr};
+  int pin_cur = 0;
+  size_t ipin_ints = 0;     // kPinRing regions of ipin_ints: manage tables
+  cudaEvent_t ipin_ev[kPinRing] = {nullptr, nullptr, nullptr, nullptr};
+  int ipin_cur = 0;
+  std::vector<double> chi90_cache;  // chi2(0.9, dof) by integer dof (slam_update.cpp:196-197), filled lazily
   // device tables / scratch
   double* d_chi95 = nullptr;
   int chi_len = 0;
@@ -194,22 +219,23 @@ struct xb_filter {
   std::vector<void*> allocs;
 };
 
+static int invalidate_early(xb_filter* f);
 static cudaEvent_t prof_event(xb_filter* f) {
   cudaEvent_t e;
   if (!f->ev_pool.empty()) { e = f->ev_pool.back(); f->ev_pool.pop_back(); }
   else cudaEventCreate(&e);
   return e;
 }
-struct StageTimer {  // RAII: records a CUDA event pair around a stage on the filter's stream when profiling is on
-  xb_filter* f; int idx = -1;
-  StageTimer(xb_filter* f_, int stage) : f(f_) {
+struct StageTimer {  // RAII: records a CUDA event pair around a stage on the given stream when profiling is on
+  xb_filter* f; int idx = -1; cudaStream_t st;
+  StageTimer(xb_filter* f_, int stage, cudaStream_t on = nullptr) : f(f_), st(on ? on : f_->stream) {
     if (!f->prof) return;
     ProfSpan sp{stage, prof_event(f), prof_event(f)};
-    cudaEventRecord(sp.e0, f->stream);
+    cudaEventRecord(sp.e0, st);
     f->spans.push_back(sp);
     idx = (int)f->spans.size() - 1;
   }
-  ~StageTimer() { if (idx >= 0) cudaEventRecord(f->spans[idx].e1, f->stream); }
+  ~StageTimer() { if (idx >= 0) cudaEventRecord(f->spans[idx].e1, st); }
 };
 extern "C" int xb_profile_enable(xb_filter* f, int on) {
   f->prof = on != 0;
@@ -218,6 +244,8 @@ extern "C" int xb_profile_enable(xb_filter* f, int on) {
 // Accumulated device time per stage since the last reset. names: ST_COUNT pointers (may be NULL). Returns stage count.
 extern "C" int xb_profile_read(xb_filter* f, const char** names, double* ms, long long* counts, int reset) {
   cudaStreamSynchronize(f->stream);
+  cudaStreamSynchronize(f->side);
+  cudaStreamSynchronize(f->side2);
   for (auto& sp : f->spans) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) { f->stage_ms[sp.stage] += t; f->stage_n[sp.stage] += 1; }
@@ -315,6 +343,13 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
     return fail(XB_E_CUDA, "cudaStreamCreate failed");
   }
   f->own_stream = true;
+  if (cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&f->side2, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(XB_E_CUDA, "cudaStreamCreate failed");
+  for (cudaEvent_t* e : {&f->ev_fork, &f->ev_side, &f->ev_corr, &f->ev_means})
+    CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  if (const char* e = getenv("XB_NO_OVERLAP")) f->overlap = atoi(e) == 0;
+  if (const char* e = getenv("XB_CHOL_SHARE")) f->chol_share = std::max(1, atoi(e));
   const int W = 6 * M + 1;
   const int maxT = std::max(1, cfg->max_tracks);
   const int maxO = cfg->max_obs > 0 ? cfg->max_obs : maxT * M;
@@ -379,11 +414,14 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_Rg, (size_t)f->gcols_pad * f->gcols_pad, double);
   DA(f->d_diag0, f->gcols_pad, double);
 
-  const int m_max = std::max(6 * M + 2 * F, N);  // dense-H path allows up to N rows
-  const int m_pad = pad32(m_max), n_pad = pad32(N);
+  // structured path: SLAM columns and slab columns are padded separately; dense-H path allows up to N rows
+  const int m_pad = std::max(pad32(2 * F) + pad32(6 * M), pad32(N)), n_pad = pad32(N);
   f->T_doubles = (size_t)(m_pad + n_pad + 96) * m_pad;
   DA(f->d_T, f->T_doubles, double);
   DA(f->d_flags, (size_t)((m_pad + n_pad + 96) / 32 + 2) * (m_pad / 32) + 128, int);
+  DA(f->d_flags_g, (size_t)(f->grows_pad / 32 + 2) * (f->gcols_pad / 32) + 128, int);
+  DA(f->d_Bc, (size_t)6 * M * std::max(32, pad32(2 * F)), double);
+  DA(f->d_FQ2, (size_t)128 * 450, double);
   DA(f->d_omega, 32, int);
   DA(f->d_omega_inv, n_pad, int);
   DA(f->d_tileflag, n_pad / 32 + 4, int);
@@ -439,10 +477,15 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   // pinned staging: measurement lists + manage tables
   f->pin_bytes = sizeof(double) * (2 * (size_t)(maxO * 2 + maxO1 * 2 + std::max(1, F) * 4 * M) + (size_t)LX + 4096) +
                  sizeof(int) * (size_t)(2 * maxT + 2 * maxT1 + 4 * std::max(1, F) + 64);
-  if (cudaMallocHost((void**)&f->h_pin, f->pin_bytes) != cudaSuccess) return fail(XB_E_CUDA, "cudaMallocHost failed");
-  if (cudaMallocHost((void**)&f->h_ipin, sizeof(int) * (size_t)(N + 16 * (6 + 3 * std::max(1, F)) + 2 * std::max(1, F) + 64)) !=
-      cudaSuccess)
+  f->pin_bytes = (f->pin_bytes + 255) / 256 * 256;
+  if (cudaMallocHost((void**)&f->h_pin, f->pin_bytes * xb_filter::kPinRing) != cudaSuccess) return fail(XB_E_CUDA, "cudaMallocHost failed");
+  f->ipin_ints = ((size_t)(N + 16 * (6 + 3 * std::max(1, F)) + 3 * std::max(1, F) + 64) + 63) / 64 * 64;
+  if (cudaMallocHost((void**)&f->h_ipin, sizeof(int) * f->ipin_ints * xb_filter::kPinRing) != cudaSuccess)
     return fail(XB_E_CUDA, "cudaMallocHost failed");
+  for (int i = 0; i < xb_filter::kPinRing; ++i) {
+    CK(cudaEventCreateWithFlags(&f->pin_ev[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&f->ipin_ev[i], cudaEventDisableTiming));
+  }
   CK(cudaDeviceSynchronize());
   *out = f;
   return XB_OK;
@@ -452,9 +495,17 @@ extern "C" int xb_destroy(xb_filter* f) {
   if (!f) return XB_OK;
   cudaSetDevice(f->cfg.device);
   cudaStreamSynchronize(f->stream);
+  if (f->side) { cudaStreamSynchronize(f->side); cudaStreamDestroy(f->side); }
+  if (f->side2) { cudaStreamSynchronize(f->side2); cudaStreamDestroy(f->side2); }
+  for (cudaEvent_t e : {f->ev_fork, f->ev_side, f->ev_corr, f->ev_means})
+    if (e) cudaEventDestroy(e);
   for (void* p : f->allocs) cudaFree(p);
   if (f->h_pin) cudaFreeHost(f->h_pin);
   if (f->h_ipin) cudaFreeHost(f->h_ipin);
+  for (int i = 0; i < xb_filter::kPinRing; ++i) {
+    if (f->pin_ev[i]) cudaEventDestroy(f->pin_ev[i]);
+    if (f->ipin_ev[i]) cudaEventDestroy(f->ipin_ev[i]);
+  }
   if (f->own_stream) cudaStreamDestroy(f->stream);
   delete f;
   return XB_OK;
@@ -470,6 +521,7 @@ extern "C" int xb_set_stream(xb_filter* f, void* s) {
 }
 extern "C" int xb_synchronize(xb_filter* f) {
   CK(cudaStreamSynchronize(f->stream));
+  if (f->side_pending) CK(cudaStreamSynchronize(f->side));
   int err = 0;
   CK(cudaMemcpy(&err, f->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   if (err) {
@@ -667,9 +719,10 @@ static int stage_list(xb_filter* f, ListDev& l, const xb_track_list& in, char*& 
 extern "C" int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m) {
   if (!f || !m) return fail(XB_E_INVALID, "null argument");
   CK(cudaSetDevice(f->cfg.device));
-  CK(cudaStreamSynchronize(f->stream));  // staging buffer reuse
+  f->pin_cur = (f->pin_cur + 1) % xb_filter::kPinRing;
+  CK(cudaEventSynchronize(f->pin_ev[f->pin_cur]));  // staging region reuse: its last copies have landed
   f->meas_time = m->timestamp;
-  char* pin = (char*)f->h_pin;
+  char* pin = (char*)f->h_pin + f->pin_bytes * f->pin_cur;
   int rc;
   if ((rc = stage_list(f, f->l_slam, m->slam, pin, "slam"))) return rc;
   if ((rc = stage_list(f, f->l_msckf, m->msckf, pin, "msckf"))) return rc;
@@ -681,16 +734,22 @@ extern "C" int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m) {
   f->lost.assign(m->lost_slam_idxs, m->lost_slam_idxs + std::max(0, m->n_lost));
   if (f->l_slam.n > 0) {  // chi2(0.9, 2*track_size) per SLAM track (slam_update.cpp:196-197)
     double* pc = (double*)pin;
-    for (int j = 0; j < f->l_slam.n; ++j)
-      pc[j] = xb_chi2_quantile(0.9, 2.0 * (f->l_slam.h_off[j + 1] - f->l_slam.h_off[j]));
+    for (int j = 0; j < f->l_slam.n; ++j) {
+      const size_t dof = 2 * (size_t)(f->l_slam.h_off[j + 1] - f->l_slam.h_off[j]);
+      if (dof >= f->chi90_cache.size()) f->chi90_cache.resize(dof + 1, -1.0);
+      if (f->chi90_cache[dof] < 0.0) f->chi90_cache[dof] = dof ? xb_chi2_quantile(0.9, (double)dof) : NAN;
+      pc[j] = f->chi90_cache[dof];
+    }
     CK(cudaMemcpyAsync(f->d_slam_chi2, pc, sizeof(double) * f->l_slam.n, cudaMemcpyHostToDevice, f->stream));
   }
+  CK(cudaEventRecord(f->pin_ev[f->pin_cur], f->stream));
   return XB_OK;
 }
 
 // ---- work state ---------------------------------------------------------------------------------------------------
 extern "C" int xb_work_load(xb_filter* f, int slot) {
   if (slot < 0 || slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid state");
+  if (invalidate_early(f)) return XB_E_CUDA;
   StageTimer st_(f, ST_ASSEMBLE);
   CK(cudaMemcpyAsync(f->d_xw, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
   launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
@@ -705,7 +764,7 @@ static double* claim_generation(xb_filter* f) {
     if (f->slot_gen[s] == f->cur_gen) { f->slot_gen[s] = -1; }
   return f->d_Pgen + (size_t)f->cur_gen * f->N * f->N;
 }
-extern "C" int xb_work_store(xb_filter* f, int slot) {
+static int work_store_impl(xb_filter* f, int slot, bool copy_estimates) {
   if (slot < 0 || slot >= f->NS) return fail(XB_E_INVALID, "bad slot");
   StageTimer st_(f, ST_STORE);
   const size_t nn = (size_t)f->N * f->N;
@@ -715,13 +774,16 @@ extern "C" int xb_work_store(xb_filter* f, int slot) {
     CK(cudaMemcpyAsync(g, f->d_Pw, sizeof(double) * nn, cudaMemcpyDeviceToDevice, f->stream));
     f->d_Pw = g;
   }
-  CK(cudaMemcpyAsync(f->d_xv + (size_t)slot * f->LX, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
+  if (copy_estimates)
+    CK(cudaMemcpyAsync(f->d_xv + (size_t)slot * f->LX, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
   launch_extract_strip(f->stream, f->N, f->d_Pw, f->d_strip + (size_t)slot * 15 * f->N);
   f->slot_gen[slot] = f->cur_gen;
   return XB_OK;
 }
+extern "C" int xb_work_store(xb_filter* f, int slot) { return work_store_impl(f, slot, true); }
 extern "C" int xb_work_set(xb_filter* f, const double* xvec, const double* cov, int layout) {
   CK(cudaSetDevice(f->cfg.device));
+  if (invalidate_early(f)) return XB_E_CUDA;
   if (xvec) CK(cudaMemcpyAsync(f->d_xw, xvec, sizeof(double) * f->LX, cudaMemcpyHostToDevice, f->stream));
   if (cov) {
     int rc = upload_cov(f, cov, layout, f->d_WA);
@@ -746,12 +808,25 @@ extern "C" int xb_work_get(xb_filter* f, double* xvec_out, double* cov_out, int 
   return XB_OK;
 }
 
+// The SLAM-column part of a constructed update was computed early (side stream) from the P / estimates / correction_total
+// of that moment.  Anything that changes one of them before apply_constructed discards it; apply then rebuilds it in order.
+static int invalidate_early(xb_filter* f) {
+  if (f->side_pending) CK(cudaStreamWaitEvent(f->stream, f->ev_side, 0));
+  f->side_pending = false;
+  f->slam_part_done = false;
+  return 0;
+}
+
 // ---- StateManager::manage (state_manager.cpp:31-149): integer bookkeeping here, arithmetic on the device ----------
 extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
   const int M = f->M, F = f->F, N = f->N;
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  f->xw_final = false;
+  if (invalidate_early(f)) return XB_E_CUDA;
   StageTimer st_(f, ST_MANAGE);
-  int* ip = f->h_ipin;
+  f->ipin_cur = (f->ipin_cur + 1) % xb_filter::kPinRing;
+  CK(cudaEventSynchronize(f->ipin_ev[f->ipin_cur]));  // pinned table region reuse
+  int* ip = f->h_ipin + f->ipin_ints * f->ipin_cur;
   int* rowmap = ip;                       // N
   int* ccols = rowmap + N;                // 15 * n_comp
   // feature removal: compaction map over ALL F slots (state_manager.cpp:52-112)
@@ -827,12 +902,12 @@ extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
   int* ra = fs + F;
   for (int k = 0; k < F; ++k) fs[k] = src[k];
   for (size_t i = 0; i < reanch.size(); ++i) ra[i] = reanch[i];
-  CK(cudaStreamSynchronize(f->stream));  // pinned table reuse
   CK(cudaMemcpyAsync(f->d_rowmap, rowmap, sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
   CK(cudaMemcpyAsync(f->d_ccols, ccols, sizeof(int) * 15 * n_comp, cudaMemcpyHostToDevice, f->stream));
   if (F > 0) CK(cudaMemcpyAsync(f->d_featsrc, fs, sizeof(int) * F, cudaMemcpyHostToDevice, f->stream));
   if (!reanch.empty())
     CK(cudaMemcpyAsync(f->d_reanch, ra, sizeof(int) * reanch.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaEventRecord(f->ipin_ev[f->ipin_cur], f->stream));
   // destination: a fresh generation (or WA when the source already is a generation buffer)
   double* src_P = f->d_Pw;
   double* dst_P = (src_P == f->d_WA) ? claim_generation(f) : f->d_WA;
@@ -950,6 +1025,8 @@ static int mm_prepare(xb_filter* f, int which, const ListDev& l0, MmParams& mp) 
 extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   if (f->mm_G <= 0) return XB_OK;
+  f->xw_final = false;
+  if (invalidate_early(f)) return XB_E_CUDA;
   const ListDev& l0 = f->last_which == 0 ? f->l_msckf : f->l_short;
   MmParams mp = mm_params(f, l0, f->last_which);
   launch_mm_apply(f->stream, mp, f->d_Pw, f->d_xw, f->F, f->d_mm_V, f->mm_max_groups, f->d_mm_D, f->d_mm_K3, f->d_mm_HP3);
@@ -957,12 +1034,44 @@ extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
   return XB_OK;
 }
 
+static UpdateDims update_dims(const xb_filter* f, int nslam);
+static int set_omega(xb_filter* f);
+
+static void launch_slam_rows_on(xb_filter* f, cudaStream_t st, int ns) {
+  SlamParams sp{};
+  sp.xv = f->d_xw; sp.M = f->M; sp.N = f->N; sp.n_poses = f->n_poses; sp.P = f->d_Pw;
+  sp.off = f->l_slam.d_off; sp.obs = f->l_slam.d_obs; sp.anchor = f->d_anchor; sp.chi2 = f->d_slam_chi2;
+  sp.n_tracks = ns; sp.var_img = f->cfg.sigma_img * f->cfg.sigma_img;
+  sp.cols = f->d_scols; sp.vals = f->d_svals; sp.res = f->d_sres; sp.gamma = f->d_sgamma; sp.inlier = f->d_sinl;
+  launch_slam_rows(st, sp);
+}
+// SLAM rows + everything of the tall buffer on their columns + the first s_pad/32 tile columns of its factorisation + Wsym
+static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int stage_build, int stage_chol, int share,
+                       bool with_rows) {
+  {
+    StageTimer st_(f, stage_build, st);
+    if (with_rows) launch_slam_rows_on(f, st, d.nslam);
+    launch_build_slam_part(st, d, f->d_Pw, f->d_scols, f->d_svals, f->d_sres, f->corr_zero ? nullptr : f->d_corr,
+                           f->cfg.sigma_img * f->cfg.sigma_img, f->d_omega, f->d_T);
+  }
+  StageTimer st_(f, stage_chol, st);
+  tallchol_range(st, f->d_T, d.m_pad, d.m_pad + d.n_pad + 96, d.m_pad, 0, d.s_pad, 1, f->d_flags, f->d_err, 0.0, nullptr, nullptr,
+                 share);
+  launch_wsym(st, d, f->d_omega_inv, f->d_T, f->d_Bc, f->d_flags);
+}
+static size_t tall_bytes(const UpdateDims& d) { return sizeof(double) * (size_t)(d.m_pad + d.n_pad + 96) * d.m_pad; }
+
 extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   const int M = f->M;
   const ListDev& l0 = which == 0 ? f->l_msckf : f->l_short;
   const int n0 = l0.n, n1 = which == 0 ? f->l_newms.n : 0, ns = which == 0 ? f->l_slam.n : 0;
   if (ns > f->n_features) return fail(XB_E_INVALID, "more SLAM tracks than SLAM features in the state");
+  if (f->side_pending) {  // a constructed update that was never applied: its side work must not outlive this call
+    CK(cudaStreamWaitEvent(f->stream, f->ev_side, 0));
+    f->side_pending = false;
+  }
+  f->slam_part_done = false;
   f->last_which = which;
   f->last_nslam = ns;
   f->constructed_any = (n0 + n1 + ns) > 0;
@@ -974,6 +1083,30 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   if (f->cfg.multi_uav && n0 > 0 && !f->mm_matches.empty()) {
     int rcm = mm_prepare(f, which, l0, mp);
     if (rcm < 0) return rcm;
+  }
+  if (ns > 0) {
+    // The SLAM rows and everything of the Kalman update that lives on their columns need only P and the estimates: they
+    // are forked onto the side stream here and run next to the MSCKF track pipeline below.  Not with MSCKF-MSCKF matches:
+    // their CI corrections change P between construct and apply (updater.cpp:84-97).
+    const bool early = f->overlap && f->mm_G == 0 && !(f->cfg.multi_uav && which == 1);
+    CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * f->F, cudaMemcpyHostToDevice, f->stream));
+    if (early) {
+      const UpdateDims d = update_dims(f, ns);
+      int rc0 = set_omega(f);
+      if (rc0) return rc0;
+      CK(cudaMemsetAsync(f->d_T, 0, tall_bytes(d), f->stream));
+      CK(cudaEventRecord(f->ev_fork, f->stream));
+      CK(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+      slam_phase(f, f->side, d, ST_SIDE_SLAM, ST_SIDE_CHOL, f->chol_share, true);
+      CK(cudaEventRecord(f->ev_side, f->side));
+      f->side_pending = true;
+      f->slam_part_done = true;
+      f->side_used_corr = !f->corr_zero;
+    } else {
+      // gates are part of constructUpdate (inlier masks are observable right after it); the tall-buffer part follows in apply
+      StageTimer st_(f, ST_SLAMROWS);
+      launch_slam_rows_on(f, f->stream, ns);
+    }
   }
   if (n0 + n1 > 0) {
     {
@@ -998,21 +1131,12 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     gp.T = f->d_Tg; gp.ld = f->gcols_pad; gp.rows_pad = f->grows_pad; gp.cols_pad = f->gcols_pad; gp.diag0 = f->d_diag0;
     { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp); }
     StageTimer st_(f, ST_CHOLG);
-    tallchol(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, f->d_flags, f->d_err, 1e-14, f->d_diag0);
+    tallchol_range(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, 0, f->gcols_pad, 0, f->d_flags_g, f->d_err, 1e-14,
+                   f->d_diag0, nullptr, f->side_pending ? f->chol_share : 1);
     transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
   } else {
     CK(cudaMemsetAsync(f->d_Tg, 0, gbytes, f->stream));
     CK(cudaMemsetAsync(f->d_Rg, 0, sizeof(double) * (size_t)f->gcols_pad * f->gcols_pad, f->stream));
-  }
-  if (ns > 0) {
-    StageTimer st_(f, ST_SLAMROWS);
-    CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * f->F, cudaMemcpyHostToDevice, f->stream));
-    SlamParams sp{};
-    sp.xv = f->d_xw; sp.M = M; sp.N = f->N; sp.n_poses = f->n_poses; sp.P = f->d_Pw;
-    sp.off = f->l_slam.d_off; sp.obs = f->l_slam.d_obs; sp.anchor = f->d_anchor; sp.chi2 = f->d_slam_chi2;
-    sp.n_tracks = ns; sp.var_img = f->cfg.sigma_img * f->cfg.sigma_img;
-    sp.cols = f->d_scols; sp.vals = f->d_svals; sp.res = f->d_sres; sp.gamma = f->d_sgamma; sp.inlier = f->d_sinl;
-    launch_slam_rows(f->stream, sp);
   }
   return XB_OK;
 }
@@ -1022,8 +1146,11 @@ static UpdateDims update_dims(const xb_filter* f, int nslam) {
   d.M = f->M; d.F = f->F; d.N = f->N;
   d.ms = 6 * f->M;
   d.nslam = nslam;
-  d.m = d.ms + 2 * nslam;
-  d.m_pad = pad32(d.m);
+  d.ns2 = 2 * nslam;
+  d.s_pad = pad32(d.ns2);
+  d.ro = d.s_pad;
+  d.m = d.ms + d.ns2;
+  d.m_pad = d.s_pad + pad32(d.ms);
   d.n_pad = pad32(f->N);
   d.ld = d.m_pad;
   return d;
@@ -1046,15 +1173,23 @@ static int set_omega(xb_filter* f) {
   return 0;
 }
 
-static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total) {
+// chol_from > 0: the tile columns [0, chol_from) of the tall buffer are already factored (side stream); finish the rest
+static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total, int chol_from = 0) {
   const int N = f->N;
-  { StageTimer st_(f, ST_TALLCHOL); tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0, nullptr, f->d_trace);
+  { StageTimer st_(f, ST_TALLCHOL);
+    if (chol_from > 0)
+      tallchol_range(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, chol_from, m_pad, 2, f->d_flags, f->d_err, 0.0, nullptr,
+                     nullptr, 1);
+    else
+      tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0, nullptr, f->d_trace);
     f->trace_tiles = (m_pad / 32) * (m_pad / 32 + 1) / 2 + ((n_pad + 96) / 32) * (m_pad / 32); }
   {
     StageTimer st_(f, ST_CORRECT);
     launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
                    f->d_Yb, f->d_Qb, f->d_Cb, f->d_xw, corr_total, f->d_delta);
   }
+  CK(cudaEventRecord(f->ev_corr, f->stream));
+  f->xw_final = true;
   if (cov_update) {
     StageTimer st_(f, ST_DOWNDATE);
     if (f->cfg.downdate_precision == 1)
@@ -1066,6 +1201,7 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
 }
 
 extern "C" int xb_updater_reset_correction(xb_filter* f) {
+  if (f->slam_part_done && f->side_used_corr && invalidate_early(f)) return XB_E_CUDA;
   CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * f->N, f->stream));
   f->corr_zero = true;
   return XB_OK;
@@ -1075,21 +1211,29 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   if (!f->constructed_any) return XB_OK;  // h.size() == 0 (updater.cpp:106)
   const UpdateDims d = update_dims(f, f->last_nslam);
-  const size_t tb = sizeof(double) * (size_t)(d.m_pad + d.n_pad + 96) * d.m_pad;
+  const double var = f->cfg.sigma_img * f->cfg.sigma_img;
+  const double* corr = f->corr_zero ? nullptr : f->d_corr;
   int rc0 = set_omega(f);
   if (rc0) return rc0;
+  int chol_from = 0;
   {
-  StageTimer st_(f, ST_BUILD);
-  CK(cudaMemsetAsync(f->d_T, 0, tb, f->stream));
-  const double* zg = f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad;
-  launch_build_pht(f->stream, d, f->d_Pw, f->d_Rg, f->gcols_pad, f->d_scols, f->d_svals, f->d_T);
-  launch_build_s(f->stream, d, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres,
-                 f->corr_zero ? nullptr : f->d_corr,
-                 f->cfg.sigma_img * f->cfg.sigma_img, f->d_T);
-  launch_omega_rows(f->stream, d, f->d_Pw, f->d_Tg, f->gcols_pad, f->d_scols, f->d_svals, f->d_omega, f->d_T);
+    StageTimer st_(f, ST_BUILD);
+    const double* zg = f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad;
+    if (f->slam_part_done) {
+      // join: SLAM columns of the tall buffer are built and factored by the side stream
+      if (f->side_pending) CK(cudaStreamWaitEvent(f->stream, f->ev_side, 0));
+      f->side_pending = false;
+    } else {
+      CK(cudaMemsetAsync(f->d_T, 0, tall_bytes(d), f->stream));
+      if (d.nslam > 0) slam_phase(f, f->stream, d, ST_SIDE_SLAM, ST_SIDE_CHOL, 1, false);
+    }
+    chol_from = d.s_pad;
+    launch_build_slab_part(f->stream, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var,
+                           f->d_omega, f->d_T, f->d_Bc);
   }
+  f->slam_part_done = false;
   f->corr_zero = false;
-  return apply_from_tall(f, d.m_pad, d.n_pad, cov_update, f->d_corr);
+  return apply_from_tall(f, d.m_pad, d.n_pad, cov_update, f->d_corr, chol_from);
 }
 
 extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const double* res, const double* r_diag, int m,
@@ -1097,6 +1241,7 @@ extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const doub
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   const int N = f->N;
   if (m <= 0) return XB_OK;
+  if (invalidate_early(f)) return XB_E_CUDA;
   const int m_pad = pad32(m), n_pad = pad32(N);
   if ((size_t)(m_pad + n_pad + 96) * m_pad > f->T_doubles || (size_t)m * N + 2 * (size_t)m > f->Hdense_doubles)
     return fail(XB_E_CAPACITY, "dense update has too many rows (max N after QR compression)");
@@ -1127,6 +1272,7 @@ extern "C" int xb_updater_apply_ci(xb_filter* f, const double* H, const double* 
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   const int N = f->N;
   if (m <= 0 || m > 96) return fail(XB_E_INVALID, "applyCI: 0 < rows <= 96");
+  if (invalidate_early(f)) return XB_E_CUDA;
   std::vector<double> A((size_t)m * 2 * m, 0.0);
   for (int r = 0; r < m; ++r) {
     for (int c = 0; c < m; ++c) A[(size_t)r * 2 * m + c] = S[(size_t)r * m + c];
@@ -1181,6 +1327,7 @@ extern "C" int xb_vio_post_update(xb_filter* f) {
   const int M = f->M, F = f->F, N = f->N;
   const double var = f->cfg.sigma_img * f->cfg.sigma_img;
   StageTimer st_(f, ST_POST);
+  if (f->l_newms.n > 0 || f->l_newstd.n > 0) f->xw_final = false;
   if (f->l_newms.n > 0) {
     const int n_new = f->l_newms.n;
     if (f->n_features + n_new > F) return fail(XB_E_CAPACITY, "no free SLAM feature slot (state_manager.cpp:208)");
@@ -1268,9 +1415,33 @@ extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
   if (idx < 0 || f->slot_gen[idx] < 0) return 0;
   int rc;
   if ((rc = xb_work_load(f, idx)) < 0) return rc;
+  f->xw_final = false;
   if ((rc = xb_updater_update(f)) < 0) return rc;
-  if ((rc = xb_work_store(f, idx)) < 0) return rc;
-  repropagate_from(f, idx);
+  int n_re = 0;
+  for (int c = idx; c != f->tail; c = next_idx(f, c)) ++n_re;
+  if (f->overlap && f->xw_final && n_re > 0 && n_re <= 128) {
+    // The estimates have been final since ev_corr (no feature initialisation followed), so the means of the re-propagation
+    // (a serial quaternion/velocity chain on one CTA) run on a side stream next to the covariance downdate; the strips
+    // wait for both.
+    CK(cudaStreamWaitEvent(f->side2, f->ev_corr, 0));
+    {
+      StageTimer st_(f, ST_SIDE_MEANS, f->side2);
+      CK(cudaMemcpyAsync(f->d_xv + (size_t)idx * f->LX, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->side2));
+      ImuSample none{};
+      launch_prop_means(f->side2, f->d_xv, f->LX, f->NS, idx, n_re, none, prop_params(f), f->d_FQ2);
+    }
+    CK(cudaEventRecord(f->ev_means, f->side2));
+    if ((rc = work_store_impl(f, idx, false)) < 0) return rc;
+    CK(cudaStreamWaitEvent(f->stream, f->ev_means, 0));
+    {
+      StageTimer st_(f, ST_PROPAGATE);
+      launch_prop_strips(f->stream, f->d_strip, f->N, f->NS, idx, n_re, f->d_FQ2);
+    }
+    for (int c = idx, k = 0; k < n_re; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; }
+  } else {
+    if ((rc = xb_work_store(f, idx)) < 0) return rc;
+    repropagate_from(f, idx);
+  }
   if (xvec_out) {
     CK(cudaMemcpyAsync(xvec_out, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToHost, f->stream));
     if ((rc = xb_synchronize(f)) < 0) return rc;
@@ -1301,6 +1472,7 @@ static int check_ci_weight(double w) {  // ci.cpp:98-101
 // Updater::collaborativeUpdate (updater.cpp:22-36) on the work state, peers given as gathered payload slots
 static int collaborative_update_packed(xb_filter* f, const double* dev_gathered, const xb_slam_match* matches, int n_matches) {
   if (n_matches <= 0) return XB_OK;  // preUpdateCI (vio_updater.cpp:76-79)
+  if (invalidate_early(f)) return XB_E_CUDA;
   if (n_matches > f->ci_max_matches) return fail(XB_E_CAPACITY, "too many SLAM-SLAM matches");
   int rc = check_ci_weight(f->cfg.ci_slam_w);
   if (rc) return rc;
@@ -1513,6 +1685,7 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
     if (!f->d_trace) return fail(XB_E_INVALID, "set XB_CHOL_TRACE=1 before xb_create");
     std::vector<long long> tr(6 * (size_t)f->trace_tiles);
     CK(cudaStreamSynchronize(f->stream));
+  CK(cudaStreamSynchronize(f->side));
     CK(cudaMemcpy(tr.data(), f->d_trace, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost));
     cnt = std::min((size_t)max_doubles, tr.size());
     for (size_t i = 0; i < cnt; ++i) out[i] = (double)(tr[i] - ((i % 6) >= 2 ? tr[2] : 0));
@@ -1521,6 +1694,7 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
   else return fail(XB_E_INVALID, "unknown debug buffer " + n);
   if ((size_t)max_doubles < cnt) cnt = max_doubles;
   CK(cudaStreamSynchronize(f->stream));
+  CK(cudaStreamSynchronize(f->side));
   CK(cudaMemcpy(out, src, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
   return (int)cnt;
 }
@@ -1539,6 +1713,7 @@ extern "C" int xb_debug_read_int(xb_filter* f, const char* name, int* out, int m
   } else return fail(XB_E_INVALID, "unknown debug buffer " + n);
   if ((size_t)max_ints < cnt) cnt = max_ints;
   CK(cudaStreamSynchronize(f->stream));
+  CK(cudaStreamSynchronize(f->side));
   CK(cudaMemcpy(out, src, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
   return (int)cnt;
 }

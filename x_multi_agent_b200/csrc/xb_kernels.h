@@ -15,6 +15,10 @@ struct ImuSample { int valid; double t, seq, w[3], a[3]; };
 struct PropParams { double g[3]; double n_w, n_bw, n_a, n_ba; };
 void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,
                       const ImuSample& in, const PropParams& pp, double* FQ);
+// the two halves of launch_propagate: estimates + F_d/Q_d per step (one CTA), then the covariance strips
+void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,
+                       const PropParams& pp, double* FQ);
+void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ);
 
 // ---- dense linear algebra -----------------------------------------------------------------------
 void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
@@ -25,6 +29,11 @@ void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int ld
                     int ldc, size_t strideC, int nz);
 void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
               const double* diag0 = nullptr, long long* trace = nullptr);
+// Split factorisation (k_linalg.cu, CholRange): phase 0 = plain over tile columns [jstart, jend); phase 1 = columns
+// [0, jend) with the tile rows [jend, cols_pad) left out; phase 2 = columns [jstart, cols_pad) given finished (and flagged)
+// L tiles in the columns before jstart.
+void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int jstart_cols, int jend_cols, int phase,
+                    int* flags, int* err, double piv_tol, const double* diag0, long long* trace, int share);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                   const double* Zb, const double* Yb, const double* Qb);
 void symmetrise(cudaStream_t s, double* P, int n);
@@ -97,23 +106,25 @@ struct UpdateDims {
   int M, F, N;
   int ms;       // slab rows = 6M
   int nslam;    // SLAM tracks (2 rows each)
-  int m;        // ms + 2*nslam
-  int m_pad;    // m rounded up to 32
+  int ns2;      // 2*nslam
+  int s_pad;    // SLAM columns rounded up to 32 (0 without SLAM rows)
+  int ro;       // first slab column (= s_pad)
+  int m;        // real rows: ms + 2*nslam
+  int m_pad;    // s_pad + ms rounded up to 32
   int n_pad;    // N rounded up to 32
   int ld;       // leading dimension of the tall buffer (= m_pad)
 };
-// PHt[:, 0:6M] = P[:, pose] * Rg^T ; PHt[:, 6M+2j+r] = sum_e P[:, col_e] * val ; written into the tall buffer rows m_pad..
-void launch_build_pht(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, int ldr, const int* scols,
-                      const double* svals, double* T);
-// S = Hc * PHt + var I (rows 0..m-1 of the tall buffer), identity padding and the r_eff row.
-void launch_build_s(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, const double* zg, const int* scols,
-                    const double* svals, const double* sres, const double* corr_total, double var, double* T);
+// Tall-buffer pieces on the SLAM columns (no Rg needed) and on the slab columns (k_update.cu)
+void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
+                            const double* sres, const double* corr_total, double var, const int* omega, double* T);
+// Wsym = (W1s + W2s)/2 on the pose rows -> Bc, and the dataflow flags of the L21 tiles (after the SLAM columns are factored)
+void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc, int* ready);
+void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
+                            const double* zg, const int* scols, const double* svals, const double* sres,
+                            const double* corr_total, double var, const int* omega, double* T, const double* Bc);
 // dense-H variant (Updater::applyUpdate with a caller-supplied H)
 void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, const double* P, const double* H,
                           const double* res, const double* rdiag, const double* corr_total, const int* omega, double* T);
-// Omega tile (A2 rows) and V tile of the structured path
-void launch_omega_rows(cudaStream_t s, const UpdateDims& d, const double* P, const double* Lg, int ldr, const int* scols,
-                       const double* svals, const int* omega, double* T);
 // Woodbury factors, delta = K r - corr_total ; State::correct ; corr_total += delta
 void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
                     const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* Cb,
