@@ -88,26 +88,116 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int Kfull, double al
   }
 }
 
+// Small-problem variant: 32x32 output tile, 128 threads, 2x4 register micro-tile, K in 32-wide slabs.  The GEMMs of this
+// path are tiny (a few hundred rows/columns): with 64x64 tiles most of them occupy 9..54 of the 148 SMs and every CTA
+// walks the whole K loop alone; quarter-size tiles spread the same work over 4x more SMs.
+template <bool TRANS_B>
+__global__ void __launch_bounds__(128) k_gemm32(int M, int N, int Kfull, double alpha, const double* __restrict__ A,
+                                                int lda, const double* __restrict__ B, int ldb, double beta,
+                                                double* __restrict__ C, int ldc, int kchunk, size_t strideC) {
+  __shared__ __align__(16) double As[32][32 + 2];  // [k][row]
+  __shared__ __align__(16) double Bs[32][32 + 4];  // [k][col]
+  const int kbeg = blockIdx.z * kchunk;
+  const int K = min(Kfull, kbeg + kchunk);
+  C += (size_t)blockIdx.z * strideC;
+  const int t = threadIdx.x;
+  const int ty = t >> 3, tx = t & 7;  // rows 2*ty.., cols 4*tx..
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  double acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  double ra[8], rb[8];
+  const int ar = t >> 2, ak = (t & 3) * 8;   // A tile (and B^T tile): row, first k (8 consecutive k)
+  const int bk = t >> 2, bc = (t & 3) * 8;   // B tile (non-transposed): k row, first column (8 consecutive columns)
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int gk = k0 + ak + u;
+      ra[u] = (m0 + ar < M && gk < K) ? A[(size_t)(m0 + ar) * lda + gk] : 0.0;
+      if (TRANS_B) rb[u] = (n0 + ar < N && gk < K) ? B[(size_t)(n0 + ar) * ldb + gk] : 0.0;
+      else rb[u] = (k0 + bk < K && n0 + bc + u < N) ? B[(size_t)(k0 + bk) * ldb + n0 + bc + u] : 0.0;
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      As[ak + u][ar] = ra[u];
+      if (TRANS_B) Bs[ak + u][ar] = rb[u]; else Bs[bk][bc + u] = rb[u];
+    }
+  };
+  gload(kbeg);
+  sstore();
+  __syncthreads();
+  for (int k0 = kbeg; k0 < K; k0 += 32) {
+    if (k0 + 32 < K) gload(k0 + 32);
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
+      acc[0][0] = fma(a01.x, b01.x, acc[0][0]); acc[0][1] = fma(a01.x, b01.y, acc[0][1]);
+      acc[0][2] = fma(a01.x, b23.x, acc[0][2]); acc[0][3] = fma(a01.x, b23.y, acc[0][3]);
+      acc[1][0] = fma(a01.y, b01.x, acc[1][0]); acc[1][1] = fma(a01.y, b01.y, acc[1][1]);
+      acc[1][2] = fma(a01.y, b23.x, acc[1][2]); acc[1][3] = fma(a01.y, b23.y, acc[1][3]);
+    }
+    __syncthreads();
+    if (k0 + 32 < K) sstore();
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int gr = m0 + ty * 2 + i;
+    if (gr >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = n0 + tx * 4 + j;
+      if (gc >= N) continue;
+      double* p = &C[(size_t)gr * ldc + gc];
+      *p = (beta == 0.0) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*p);
+    }
+  }
+}
+
+static bool small_gemm(int M, int N, int nz) { return (size_t)((M + 63) / 64) * ((N + 63) / 64) * nz < 128; }
+
 void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  if (small_gemm(M, N, 1)) {
+    dim3 grid((N + 31) / 32, (M + 31) / 32);
+    k_gemm32<true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  }
   count_launch();
 }
 // C_z = A[:, kz] B[:, kz]^T for nz K-chunks (partials at C + z*strideC; the consumer sums them in a fixed order)
 void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
                     int ldc, size_t strideC, int nz) {
-  const int kchunk = ((K + nz - 1) / nz + 15) / 16 * 16;
-  dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
-  k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+  if (small_gemm(M, N, nz)) {
+    const int kchunk = ((K + nz - 1) / nz + 31) / 32 * 32;
+    dim3 grid((N + 31) / 32, (M + 31) / 32, nz);
+    k_gemm32<true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+  } else {
+    const int kchunk = ((K + nz - 1) / nz + 15) / 16 * 16;
+    dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
+    k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+  }
   count_launch();
 }
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  k_gemm<false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  if (small_gemm(M, N, 1)) {
+    dim3 grid((N + 31) / 32, (M + 31) / 32);
+    k_gemm32<false><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    k_gemm<false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  }
   count_launch();
 }
 
@@ -253,9 +343,9 @@ __device__ __forceinline__ void tile_store(double* g, int ld, double (*S)[TC + 1
 // tile columns are factored while the rows of the remaining columns are still being produced (xb_api.cu overlaps
 // the SLAM-row part of the Kalman update with the MSCKF track pipeline this way):
 //   launch 1: columns [0, c1), tile rows [c1, ct) skipped (their entries do not exist yet)
-//   (caller: writes the finished factor tiles L(i, j), i in [c1, ct), j < c1, and sets their ready flags -- for the
-//    Kalman update they are a plain GEMM, k_update.cu:k_wsym)
-//   launch 2: columns [c1, ct) as usual; its first diagonal tile takes all earlier panels through one pre() task.
+//   caller:   L21 = rows [c1, ct) of the factor on the columns [0, c1) (for the Kalman update a plain GEMM,
+//             k_update.cu:k_wsym), then the Schur complement T[c1:, c1:] -= T[c1:, :c1] L21^T (GEMM)
+//   launch 2: a plain factorisation of the sub-buffer T[c1:, c1:].
 // A plain factorisation is {0, ct, 0, 0}.
 struct CholRange {
   int jstart, jend;    // tile columns factored by this launch
@@ -318,7 +408,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       const long long tr0 = trace ? gtimer() : 0;
       const bool first = j == jstart;
       const bool has_e = !(j + 1 >= cr.skip0 && j + 1 < cr.skip1);  // E = (j+1, j) exists in this launch
-      if (first ? jstart >= 1 : j >= 2) {
+      if (j >= 2) {
         if (t == 0) flag_spin(&pre[j], err);
         __syncthreads();
       }
@@ -402,20 +492,14 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
   }
 
   // -------------------------------------------------------------------- workers
-  // task list, dependency-ordered:
-  //   B. pre(jstart), covering the panels k <= jstart-1 (there is no in-CTA hand-over into the first column)
-  //   C. for j = jstart..jend-1: [pre(j+1) if j+1 >= 2 and j+1 < jend; it needs only columns <= j-1],
-  //      then the TRSM tiles (i, j), i = j+2..rt-1 without the skipped rows
+  // task list, dependency-ordered: for j = jstart..jend-1: [pre(j+1) if j+1 >= 2 and j+1 < jend; it needs only
+  // columns <= j-1], then the TRSM tiles (i, j), i = j+2..rt-1 without the skipped rows
   const int nworkers = gridDim.x - 1;
-  const int nB = jstart >= 1 ? 1 : 0;
   int task = blockIdx.x - 1;
-  int jcol = jstart, base = nB;
+  int jcol = jstart, base = 0;
   while (true) {
     int jp = -1, kmax = -1, trsm_i = -1, trsm_j = jcol;
-    if (task < nB) {
-      jp = jstart;
-      kmax = jstart - 1;
-    } else {
+    {
       // advance (jcol, base) so that task falls into column jcol's segment
       int seg, has_pre, s0, slen;
       for (;;) {
@@ -486,14 +570,14 @@ void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pa
   const int rt = rows_pad / TC, ct = cols_pad / TC;
   CholRange cr{jstart_cols / TC, jend_cols / TC, 0, 0};
   if (phase == 1) { cr.skip0 = cr.jend; cr.skip1 = ct; }
-  int ntasks = cr.jstart >= 1 ? 1 : 0;
+  int ntasks = 0;
   for (int j = cr.jstart; j < cr.jend; ++j) {
     const int s0 = std::max(cr.skip0, j + 2), slen = std::max(0, cr.skip1 - s0);
     ntasks += ((j + 1 >= 2 && j + 1 < cr.jend) ? 1 : 0) + (rt - j - 2) - slen;
   }
   const int max_workers = std::max(1, tallchol_max_ctas() / std::max(1, share) - 1);
   const int nworkers = ntasks < max_workers ? (ntasks > 0 ? ntasks : 1) : max_workers;
-  if (phase != 2) cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)rt * ct + ct + 1), s);
+  cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)rt * ct + ct + 1), s);
   k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace);
   count_launch();
 }

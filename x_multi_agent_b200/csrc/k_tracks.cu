@@ -50,6 +50,68 @@ __device__ __forceinline__ double wdot(const double* a, int sa, const double* b,
   return xb_warp_sum(s);
 }
 
+// advance a packed-lower index (r, c) by n elements (row-major order over the lower triangle)
+__device__ __forceinline__ void tri_advance(int& r, int& c, int n) {
+  c += n;
+  while (c > r) { c -= r + 1; ++r; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky of the packed lower triangle X: R2 factor rows followed by 7 right-hand-side rows R2..R2+6 that are
+// solved along (they become y = L^-1 (Pi r) and Vt = L^-1 V); row q starts at tri_idx(q, 0).  One warp,
+// LEFT-looking: for column c lane l owns the rows c+l, c+l+32, ... and accumulates X[r][c] - sum_k X[r][k] X[c][k] in
+// registers -- the inner loop only loads (the finished row c as a broadcast), so the shared-memory latency pipelines;
+// one store per row and one __syncwarp per column.  Measured per cfg-2 track (R2 = 60): right-looking row-per-lane
+// 182k cycles, right-looking column-per-lane 193k (every iteration waits for its own store), fully unrolled
+// register tiles 128k (instruction-fetch bound: the kernel runs once per warp), this loop: see profiles/.
+// ------------------------------------------------------------------------------------------------
+template <int ROWS>  // rows per lane: ceil((R2 + 7) / 32) <= ROWS
+__device__ __forceinline__ bool gate_chol_packed(double* __restrict__ X, int R2, int lane) {
+  const int Rend = R2 + 6;
+  for (int c = 0; c < R2; ++c) {
+    const double* Lc = X + tri_idx(c, 0);
+    double* pr[ROWS];
+    bool act[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      const int r = c + lane + 32 * u;
+      act[u] = r <= Rend;
+      pr[u] = X + tri_idx(act[u] ? r : c, 0);  // idle slots read row c (harmless) and store nothing
+    }
+    double s0[ROWS], s1[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) { s0[u] = 0.0; s1[u] = 0.0; }
+    int k = 0;
+#pragma unroll 2
+    for (; k + 3 < c; k += 4) {  // loads only: 4 broadcasts of the finished row c + 4 entries of every owned row per step
+      const double l0 = Lc[k], l1 = Lc[k + 1], l2 = Lc[k + 2], l3 = Lc[k + 3];
+#pragma unroll
+      for (int u = 0; u < ROWS; ++u) {
+        const double x0 = pr[u][k], x1 = pr[u][k + 1], x2 = pr[u][k + 2], x3 = pr[u][k + 3];
+        s0[u] = fma(x0, l0, s0[u]); s1[u] = fma(x1, l1, s1[u]);
+        s0[u] = fma(x2, l2, s0[u]); s1[u] = fma(x3, l3, s1[u]);
+      }
+    }
+    for (; k < c; ++k) {
+      const double l0 = Lc[k];
+#pragma unroll
+      for (int u = 0; u < ROWS; ++u) s0[u] = fma(pr[u][k], l0, s0[u]);
+    }
+    double v[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) v[u] = pr[u][c] - (s0[u] + s1[u]);
+    const double piv = __shfl_sync(0xffffffffu, v[0], 0);
+    if (!(piv > 0.0)) return false;
+    const double rs = rsqrt(piv);
+    __syncwarp();  // every lane has read row c's old entries before lane 0 overwrites X[c][c]
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u)
+      if (act[u]) pr[u][c] = (u == 0 && lane == 0) ? piv * rs : v[u] * rs;
+    __syncwarp();
+  }
+  return true;
+}
+
 template <int OPL>  // observations per lane (track length <= 32*OPL)
 __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
   extern __shared__ double smem[];
@@ -70,6 +132,9 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
 
   const int trk = blockIdx.x * nwarp + warp;
   if (trk >= tp.n_tracks) return;
+  long long* pf = tp.prof ? tp.prof + 12 * (size_t)trk : nullptr;
+#define TPROF(k) do { if (pf && lane == 0) pf[k] = clock64(); } while (0)
+  TPROF(0);
   const int o0 = tp.off[trk], L = tp.off[trk + 1] - o0;
   const int W = 6 * M + 1;  // width of a B row: pose columns + residual column
   double* Bt = tp.B + (size_t)trk * 3 * W;
@@ -117,6 +182,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     alpha = __shfl_sync(0xffffffffu, alpha, 0);
     beta = __shfl_sync(0xffffffffu, beta, 0);
     rho = __shfl_sync(0xffffffffu, rho, 0);
+    TPROF(1);
 
     // iteration-invariant relative poses of this lane's observations
     double dR[OPL][9], dp[OPL][3], zz[OPL][2];
@@ -187,6 +253,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       r_norm = sqrt(rr);
     }
   }
+  TPROF(2);
   if (lane == 0) { tp.ivd[3 * trk] = alpha; tp.ivd[3 * trk + 1] = beta; tp.ivd[3 * trk + 2] = rho; }
 
   // ---------------------------------------------------------------- Jacobians
@@ -261,6 +328,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
   nan_flag = __any_sync(0xffffffffu, nan_flag);
   bad = bad || nan_flag;
   __syncwarp();
+  TPROF(3);
 
   // ---------------------------------------------------------------- U = orth(Hf): MGS with re-orthogonalisation
   // (msckf_update.cpp:423: Hf.householderQr().householderQ(); only range(Hf) matters)
@@ -282,6 +350,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     }
   }
 
+  TPROF(4);
   // ---------------------------------------------------------------- B = U^T [J | r]   (3 x (6M+1))
   for (int e = lane; e < 3 * W; e += 32) Bt[e] = 0.0;
   __syncwarp();
@@ -342,6 +411,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
   }
   __syncwarp();
 
+  TPROF(5);
   // ---------------------------------------------------------------- gate: X = J P J^T over block pairs (k <= i)
   double gamma = NAN;
   int inl = 0;
@@ -350,11 +420,9 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     const int ld = tp.ldp;
     const int npairs = L * (L + 1) / 2;
     const int nslot = slam_mode ? 2 : 1;
-    for (int e = lane; e < npairs; e += 32) {
-      int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while (i * (i + 1) / 2 > e) --i;
-      while ((i + 1) * (i + 2) / 2 <= e) ++i;
-      const int k = e - i * (i + 1) / 2;
+    int i = 0, k = 0;
+    tri_advance(i, k, lane);
+    for (int e = lane; e < npairs; e += 32, tri_advance(i, k, 32)) {
       double x00 = 0, x01 = 0, x10 = 0, x11 = 0;
       for (int si = 0; si < nslot; ++si) {
         const int pi_ = si ? np - 1 : i1 + i;
@@ -368,8 +436,10 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
           double T[12];
           const int rp = XB_CORE + 3 * pi_, ra = XB_CORE + 3 * M + 3 * pi_;
           const int cpn = XB_CORE + 3 * pk_, can = XB_CORE + 3 * M + 3 * pk_;
+#pragma unroll
           for (int c = 0; c < 3; ++c) {
             double tp0 = 0, tp1 = 0, ta0 = 0, ta1 = 0;
+#pragma unroll
             for (int a = 0; a < 3; ++a) {
               double ppp = P[(size_t)(rp + a) * ld + cpn + c], pap = P[(size_t)(ra + a) * ld + cpn + c];
               double ppa = P[(size_t)(rp + a) * ld + can + c], paa = P[(size_t)(ra + a) * ld + can + c];
@@ -400,11 +470,23 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       if (k < i) ws.X[tri_idx(2 * i, 2 * k + 1)] = x01;
     }
     __syncwarp();
+    TPROF(6);
     // Y = X U  (2L x 3)
     for (int r = lane; r < R2; r += 32) {
       double y0 = 0, y1 = 0, y2 = 0;
-      for (int c = 0; c < R2; ++c) {
-        const double x = (c <= r) ? ws.X[tri_idx(r, c)] : ws.X[tri_idx(c, r)];
+      const double* xr = ws.X + tri_idx(r, 0);
+#pragma unroll 4
+      for (int c = 0; c <= r; ++c) {  // row part (stored), then the column below the diagonal (symmetric half)
+        const double x = xr[c];
+        y0 = fma(x, ws.U[c * 3], y0);
+        y1 = fma(x, ws.U[c * 3 + 1], y1);
+        y2 = fma(x, ws.U[c * 3 + 2], y2);
+      }
+      int idx = tri_idx(r + 1, r);
+#pragma unroll 4
+      for (int c = r + 1; c < R2; ++c) {
+        const double x = ws.X[idx];
+        idx += c + 1;
         y0 = fma(x, ws.U[c * 3], y0);
         y1 = fma(x, ws.U[c * 3 + 1], y1);
         y2 = fma(x, ws.U[c * 3 + 2], y2);
@@ -415,20 +497,19 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     double Z[9];  // U^T X U
     for (int u = 0; u < 3; ++u)
       for (int v = 0; v < 3; ++v) Z[u * 3 + v] = wdot(ws.U + u, 3, ws.Y + v, 3, R2, lane);
+    // S = Pi X Pi + var I = X - U W^T - W U^T + var I  with  W = Y - U Z / 2  (Z = U^T X U symmetric)
     for (int r = lane; r < R2; r += 32)
       for (int v = 0; v < 3; ++v)
-        ws.V[r * 3 + v] = ws.U[r * 3] * Z[v] + ws.U[r * 3 + 1] * Z[3 + v] + ws.U[r * 3 + 2] * Z[6 + v];
+        ws.V[r * 3 + v] = ws.Y[r * 3 + v] - 0.5 * (ws.U[r * 3] * Z[v] + ws.U[r * 3 + 1] * Z[3 + v] + ws.U[r * 3 + 2] * Z[6 + v]);
     __syncwarp();
-    // S = Pi X Pi + var I (in place, packed), augmented row R2 = (Pi r)^T
+    // (in place, packed), augmented row R2 = (Pi r)^T
     const int nel = R2 * (R2 + 1) / 2;
-    for (int e = lane; e < nel; e += 32) {
-      int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while (r * (r + 1) / 2 > e) --r;
-      while ((r + 1) * (r + 2) / 2 <= e) ++r;
-      const int c = e - r * (r + 1) / 2;
+    int r = 0, c = 0;
+    tri_advance(r, c, lane);
+    for (int e = lane; e < nel; e += 32, tri_advance(r, c, 32)) {
       double s = ws.X[e];
-      for (int u = 0; u < 3; ++u)
-        s += -ws.U[r * 3 + u] * ws.Y[c * 3 + u] - ws.Y[r * 3 + u] * ws.U[c * 3 + u] + ws.V[r * 3 + u] * ws.U[c * 3 + u];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) s -= ws.U[r * 3 + u] * ws.V[c * 3 + u] + ws.V[r * 3 + u] * ws.U[c * 3 + u];
       if (r == c) s += tp.var_img;
       ws.X[e] = s;
     }
@@ -452,32 +533,10 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     __syncwarp();
     // Cholesky of the augmented lower triangle (rows R2..R2+6 are right-hand sides): the last rows become
     // y = L^-1 (Pi r) and Vt = L^-1 V.  Lane-owned rows, 4-wide batches so that loads overlap the FMAs.
-    bool spd = true;
-    const int Rend = R2 + 6;
-    for (int c = 0; c < R2; ++c) {
-      const double piv = ws.X[tri_idx(c, c)];
-      if (!(piv > 0.0)) { spd = false; break; }
-      const double rs = rsqrt(piv);
-      __syncwarp();
-      for (int r = c + 1 + lane; r <= Rend; r += 32) ws.X[tri_idx(r, c)] *= rs;
-      __syncwarp();
-      for (int r = c + 1 + lane; r <= Rend; r += 32) {
-        const double lrc = ws.X[tri_idx(r, c)];
-        double* row = ws.X + tri_idx(r, 0);
-        const int kend = (r < R2) ? r : R2 - 1;  // the augmented rows have no diagonal entries
-        int k = c + 1;
-        int ck = tri_idx(k, c);  // index of X[k][c]; X[k+1][c] is k+1 further
-        for (; k + 3 <= kend; k += 4) {
-          const double l0 = ws.X[ck], l1 = ws.X[ck + k + 1], l2 = ws.X[ck + 2 * k + 3], l3 = ws.X[ck + 3 * k + 6];
-          double r0 = row[k], r1 = row[k + 1], r2 = row[k + 2], r3 = row[k + 3];
-          r0 = fma(-lrc, l0, r0); r1 = fma(-lrc, l1, r1); r2 = fma(-lrc, l2, r2); r3 = fma(-lrc, l3, r3);
-          row[k] = r0; row[k + 1] = r1; row[k + 2] = r2; row[k + 3] = r3;
-          ck += 4 * k + 10;
-        }
-        for (; k <= kend; ++k) { row[k] = fma(-lrc, ws.X[ck], row[k]); ck += k + 1; }
-      }
-      __syncwarp();
-    }
+    TPROF(7);
+    const bool spd = gate_chol_packed<(64 * OPL + 7 + 31) / 32>(ws.X, R2, lane);
+    __syncwarp();
+    TPROF(8);
     if (spd) {
       // gamma = r^T S^-1 r with S = S_s + V E V^T (E = antisymmetric part of the clone block of P):
       //   y^T y - (Vt^T y)^T E (I + G E)^-1 (Vt^T y),  Vt = L^-1 V,  G = Vt^T Vt      (Woodbury)
@@ -496,13 +555,19 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
         double* Gs = ws.scr;            // 36
         double* gvs = ws.scr + 36;      // 6
         double* Am = ws.scr + 42;       // 6 x 13
-        for (int a = 0; a < 6; ++a) {
-          const double gva = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, aug, 1, R2, lane);
-          if (lane == 0) gvs[a] = gva;
-          for (int b = 0; b <= a; ++b) {
-            const double gab = wdot(ws.X + tri_idx(R2 + 1 + a, 0), 1, ws.X + tri_idx(R2 + 1 + b, 0), 1, R2, lane);
-            if (lane == 0) { Gs[a * 6 + b] = gab; Gs[b * 6 + a] = gab; }
-          }
+        // the 21 + 6 dot products G = Vt^T Vt, gv = Vt^T y: one per lane (rows 0..6 of the right-hand-side block: y, Vt_0..5)
+        if (lane < 27) {
+          int a = 0, b = lane;                     // lane < 6: (y, Vt_lane); else the pair (a, b <= a) of G
+          if (lane >= 6) { int e = lane - 6; a = 0; while (e > a) { e -= a + 1; ++a; } b = e; }
+          const double* ra = lane < 6 ? aug : ws.X + tri_idx(R2 + 1 + a, 0);
+          const double* rb = ws.X + tri_idx(R2 + 1 + b, 0);
+          double d0 = 0.0, d1 = 0.0;
+          int i = 0;
+          for (; i + 1 < R2; i += 2) { d0 = fma(ra[i], rb[i], d0); d1 = fma(ra[i + 1], rb[i + 1], d1); }
+          if (i < R2) d0 = fma(ra[i], rb[i], d0);
+          d0 += d1;
+          if (lane < 6) gvs[lane] = d0;
+          else { Gs[a * 6 + b] = d0; Gs[b * 6 + a] = d0; }
         }
         __syncwarp();
         if (lane < 12) {
@@ -560,6 +625,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       inl = gamma < chi;
     }
   }
+  TPROF(9);
   if (lane == 0) {
     tp.gamma[trk] = gamma;
     tp.inlier[trk] = inl;
@@ -604,6 +670,8 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
   __syncwarp();
   if (!inl)
     for (int e = lane; e < 3 * W; e += 32) Bt[e] = 0.0;
+  TPROF(10);
+#undef TPROF
 }
 
 size_t tracks_smem_bytes(int M, int Lmax, int warps, int mode) {

@@ -51,24 +51,19 @@ __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int
 // sub-diagonal block of the factor needs no triangular solve:
 //   L21 = S21 L11^-T = Rg (sym(P) Hs^T)[pose rows] L11^-T = Rg * Wsym,   Wsym = (W1s + W2s)/2 on the pose rows
 // (W2s differs from W1s on the newest clone's 6 rows only).  This kernel gathers Wsym (6M x s_pad) into Bc, and
-// publishes the dataflow flags of the L21 tiles, which the GEMM of launch_build_slab_part writes.
-__global__ void k_wsym(UpdateDims d, const int* __restrict__ omega_inv, const double* __restrict__ T, double* __restrict__ Bc,
-                       int* __restrict__ ready, int ct) {
+// is multiplied by launch_build_slab_part.
+__global__ void k_wsym(UpdateDims d, const int* __restrict__ omega_inv, const double* __restrict__ T, double* __restrict__ Bc) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (b == 0 && c < (ct - d.s_pad / 32) * (d.s_pad / 32)) {
-    const int i = d.s_pad / 32 + c / (d.s_pad / 32), j = c % (d.s_pad / 32);
-    ready[i * ct + j] = 1;
-  }
   if (c >= d.s_pad || b >= d.ms) return;
   double v = T[(size_t)(d.m_pad + XB_CORE + b) * d.ld + c];
   const int k = omega_inv[XB_CORE + b];
   if (k >= 0) v = 0.5 * (v + T[(size_t)(d.m_pad + d.n_pad + 32 + k) * d.ld + c]);
   Bc[(size_t)b * d.s_pad + c] = v;
 }
-void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc, int* ready) {
+void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc) {
   if (d.nslam <= 0) return;
   dim3 g((d.s_pad + 127) / 128, d.ms);
-  k_wsym<<<g, 128, 0, s>>>(d, omega_inv, T, Bc, ready, d.m_pad / 32);
+  k_wsym<<<g, 128, 0, s>>>(d, omega_inv, T, Bc);
   count_launch();
 }
 
@@ -156,6 +151,13 @@ void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P
   k_s_finish<<<(d.m_pad - d.ro + 127) / 128, 128, 0, s>>>(d, d.ro, d.m_pad - d.ro, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
   count_launch();
   launch_omega_rows(s, d, d.ro, d.ms, P, Lg, ldr, scols, svals, omega, T);
+  if (d.nslam > 0) {
+    // Schur complement of the factored SLAM columns on every row from the slab rows down (S22, P H^T, r_eff, Omega, V):
+    //   T[ro:, ro:] -= T[ro:, 0:s_pad] * L21^T     -- after it the slab columns are a plain tall factorisation of their own
+    const int rows = d.m_pad - d.ro + d.n_pad + 96;
+    gemm_nt(s, rows, d.m_pad - d.ro, d.s_pad, -1.0, T + (size_t)d.ro * d.ld, d.ld, T + (size_t)d.ro * d.ld, d.ld, 1.0,
+            T + (size_t)d.ro * d.ld + d.ro, d.ld);
+  }
 }
 
 // dense-H path: S += diag(rdiag) (+ identity padding), r_eff = res + H corr

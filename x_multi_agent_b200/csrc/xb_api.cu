@@ -182,6 +182,7 @@ struct xb_filter {
   int* d_flags = nullptr;
   int* d_err = nullptr;
   long long* d_trace = nullptr;  // optional tile-Cholesky timeline (XB_CHOL_TRACE=1)
+  long long* d_track_prof = nullptr;  // optional per-track phase clocks (XB_TRACK_PROF=1)
   int trace_tiles = 0;
   // kalman tall buffer
   double* d_T = nullptr;
@@ -456,6 +457,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_Qb, (size_t)n_pad * 32, double);
   DA(f->d_Cb, (size_t)4 * (n_pad + 96) * 96, double);
   DA(f->d_err, 4, int);
+  if (getenv("XB_TRACK_PROF")) DA(f->d_track_prof, 12 * (size_t)maxT, long long);
   if (getenv("XB_CHOL_TRACE")) DA(f->d_trace, 6 * ((size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64), long long);
 
   DA(f->d_rowmap, N, int);
@@ -944,6 +946,7 @@ static TrackParams track_params(xb_filter* f, const ListDev& l, int mode) {
   tp.chi2_95 = f->d_chi95;
   tp.gn_term = 1e-5;   // vio_updater.cpp:283-285
   tp.gn_max_iter = 10;
+  tp.prof = mode == 0 ? f->d_track_prof : nullptr;
   if (mode == 0) {
     tp.ivd = f->d_ivd0; tp.gamma = f->d_gamma0; tp.inlier = f->d_inl0; tp.B = f->d_B0; tp.Jout = f->d_J0;
     tp.H1 = nullptr; tp.H2 = nullptr; tp.D = nullptr;
@@ -1057,7 +1060,7 @@ static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int s
   StageTimer st_(f, stage_chol, st);
   tallchol_range(st, f->d_T, d.m_pad, d.m_pad + d.n_pad + 96, d.m_pad, 0, d.s_pad, 1, f->d_flags, f->d_err, 0.0, nullptr, nullptr,
                  share);
-  launch_wsym(st, d, f->d_omega_inv, f->d_T, f->d_Bc, f->d_flags);
+  launch_wsym(st, d, f->d_omega_inv, f->d_T, f->d_Bc);
 }
 static size_t tall_bytes(const UpdateDims& d) { return sizeof(double) * (size_t)(d.m_pad + d.n_pad + 96) * d.m_pad; }
 
@@ -1177,11 +1180,10 @@ static int set_omega(xb_filter* f) {
 static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total, int chol_from = 0) {
   const int N = f->N;
   { StageTimer st_(f, ST_TALLCHOL);
-    if (chol_from > 0)
-      tallchol_range(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, chol_from, m_pad, 2, f->d_flags, f->d_err, 0.0, nullptr,
-                     nullptr, 1);
-    else
-      tallchol(f->stream, f->d_T, m_pad, m_pad + n_pad + 96, m_pad, f->d_flags, f->d_err, 0.0, nullptr, f->d_trace);
+    // chol_from > 0: the leading columns are factored and folded into the rest (Schur complement): the remaining
+    // columns are a plain tall factorisation of the sub-buffer starting at (chol_from, chol_from)
+    tallchol(f->stream, f->d_T + (size_t)chol_from * m_pad + chol_from, m_pad, m_pad - chol_from + n_pad + 96, m_pad - chol_from,
+             f->d_flags, f->d_err, 0.0, nullptr, chol_from ? nullptr : f->d_trace);
     f->trace_tiles = (m_pad / 32) * (m_pad / 32 + 1) / 2 + ((n_pad + 96) / 32) * (m_pad / 32); }
   {
     StageTimer st_(f, ST_CORRECT);
@@ -1681,6 +1683,16 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
   else if (n == "corr") { src = f->d_corr; cnt = f->N; }
   else if (n == "delta") { src = f->d_delta; cnt = f->N; }
   else if (n == "T") { src = f->d_T; cnt = f->T_doubles; }
+  else if (n == "track_prof") {
+    if (!f->d_track_prof) return fail(XB_E_INVALID, "set XB_TRACK_PROF=1 before xb_create");
+    const int nt = f->last_which ? f->l_short.n : f->l_msckf.n;
+    std::vector<long long> tr(12 * (size_t)nt);
+    CK(cudaStreamSynchronize(f->stream));
+    CK(cudaMemcpy(tr.data(), f->d_track_prof, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost));
+    cnt = std::min((size_t)max_doubles, tr.size());
+    for (size_t i = 0; i < cnt; ++i) out[i] = (double)(tr[i] - tr[i / 12 * 12]);
+    return (int)cnt;
+  }
   else if (n == "chol_trace") {
     if (!f->d_trace) return fail(XB_E_INVALID, "set XB_CHOL_TRACE=1 before xb_create");
     std::vector<long long> tr(6 * (size_t)f->trace_tiles);

@@ -29,9 +29,8 @@ void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int ld
                     int ldc, size_t strideC, int nz);
 void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
               const double* diag0 = nullptr, long long* trace = nullptr);
-// Split factorisation (k_linalg.cu, CholRange): phase 0 = plain over tile columns [jstart, jend); phase 1 = columns
-// [0, jend) with the tile rows [jend, cols_pad) left out; phase 2 = columns [jstart, cols_pad) given finished (and flagged)
-// L tiles in the columns before jstart.
+// Partial factorisation (k_linalg.cu, CholRange): phase 0 = plain; phase 1 = tile columns [0, jend) with the tile rows
+// [jend, cols_pad) left out (their entries do not exist yet; the caller finishes with a Schur complement + plain call).
 void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int jstart_cols, int jend_cols, int phase,
                     int* flags, int* err, double piv_tol, const double* diag0, long long* trace, int share);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
@@ -69,6 +68,7 @@ struct TrackParams {
   const int* mm_grp;
   const double* mm_ivd;
   double* mm_F0;
+  long long* prof;   // optional [K][12] clock64 stamps at the phase boundaries (XB_TRACK_PROF=1, tools/track_prof.py)
 };
 int launch_tracks(cudaStream_t s, const TrackParams& tp);
 
@@ -117,8 +117,8 @@ struct UpdateDims {
 // Tall-buffer pieces on the SLAM columns (no Rg needed) and on the slab columns (k_update.cu)
 void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
                             const double* sres, const double* corr_total, double var, const int* omega, double* T);
-// Wsym = (W1s + W2s)/2 on the pose rows -> Bc, and the dataflow flags of the L21 tiles (after the SLAM columns are factored)
-void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc, int* ready);
+// Wsym = (W1s + W2s)/2 on the pose rows -> Bc (after the SLAM columns are factored)
+void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc);
 void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
                             const double* zg, const int* scols, const double* svals, const double* sres,
                             const double* corr_total, double var, const int* omega, double* T, const double* Bc);

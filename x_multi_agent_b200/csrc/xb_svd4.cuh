@@ -23,12 +23,13 @@ static __device__ void smallest_right_singular_vector4(double* A /*4x4 row-major
           be += A[i * 4 + q] * A[i * 4 + q];
           ga += A[i * 4 + p] * A[i * 4 + q];
         }
-        const double lim = 1e-14 * sqrt(al * be);
-        if (fabs(ga) <= lim || ga == 0.0) continue;
-        off = fmax(off, fabs(ga) / fmax(sqrt(al * be), 1e-300));
-        const double zeta = (be - al) / (2.0 * ga);
-        const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+        if (ga * ga <= 1e-28 * (al * be) || ga == 0.0) continue;  // |ga| <= 1e-14 sqrt(al be)
+        off = 1.0;
+        // tan of the rotation angle: t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 ga), written with one
+        // square root and one division:  t = 2 ga / (d + sign(d) sqrt(d^2 + 4 ga^2)),  d = be - al  (sign(0) = +1)
+        const double d = be - al, g2 = 2.0 * ga;
+        const double tt = g2 / (d + copysign(sqrt(fma(d, d, g2 * g2)), d));
+        const double c = rsqrt(fma(tt, tt, 1.0)), s = c * tt;
         for (int i = 0; i < 4; ++i) {
           const double ap = A[i * 4 + p], aq = A[i * 4 + q];
           A[i * 4 + p] = c * ap - s * aq;
