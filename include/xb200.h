@@ -227,7 +227,8 @@ XB_API int xb_ci_last_gates(xb_filter* f, double* out /* 2*n_matches */, int max
 /* ---- introspection for tests / profiling ------------------------------------------------------ */
 XB_API int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles); /* returns count */
 XB_API int xb_debug_read_int(xb_filter* f, const char* name, int* out, int max_ints);
-/* per-stage CUDA-event timers on the filter's stream (bench.py roofline line); names/ms/counts hold 16 entries */
+/* per-stage CUDA-event timers on the filter's stream (bench.py roofline line); names/ms/counts must hold XB_MAX_STAGES entries */
+#define XB_MAX_STAGES 32
 XB_API int xb_profile_enable(xb_filter* f, int on);
 XB_API int xb_profile_read(xb_filter* f, const char** names, double* ms, long long* counts, int reset);
 XB_API long long xb_kernel_launches(const xb_filter* f);                /* kernels launched so far */

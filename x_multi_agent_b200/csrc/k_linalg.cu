@@ -735,9 +735,154 @@ __global__ void __launch_bounds__(256) k_downdate(double* __restrict__ P, int n,
   }
 }
 
+// Small-N variant: 32x32 tile pairs (128 threads, 2x4 micro-tile) so that a 795-state covariance gives 325 CTAs instead
+// of 91, and the K range [kbeg, kend) of the W1 columns is a parameter -- the part of the downdate that belongs to the
+// SLAM columns of the compressed measurement exists long before the rest (xb_api.cu starts it on a side stream):
+//   do_sym : Pout_ij = (Pin_ij + Pin_ji)/2 - ...   (otherwise Pin is already symmetric and only (I,J) is read)
+//   do_tail: also the Woodbury / Omega terms  - (Q_i[k(j)] + Q_j[k(i)])/2 + (Z_i.Y_j + Y_i.Z_j)/2
+#define D3 32
+__global__ void __launch_bounds__(128) k_downdate32(const double* __restrict__ Pin, double* __restrict__ Pout, int n,
+                                                    const double* __restrict__ W1, int ldw, int kbeg, int kend, int do_sym,
+                                                    int do_tail, const int* __restrict__ omega_inv,
+                                                    const double* __restrict__ Zb, const double* __restrict__ Yb,
+                                                    const double* __restrict__ Qb) {
+  const int nt = (n + D3 - 1) / D3;
+  int b = blockIdx.x, I = 0;
+  while (b >= nt - I) { b -= nt - I; ++I; }
+  const int J = I + b;
+  const int t = threadIdx.x, ty = t >> 3, tx = t & 7;  // rows 2*ty.., cols 4*tx.. of tile (I, J)
+  __shared__ __align__(16) double As[32][D3 + 2];  // [k][row of block I]
+  __shared__ __align__(16) double Bs[32][D3 + 4];  // [k][row of block J]
+  __shared__ double Pt[D3][D3 + 1];
+  const int lr = t >> 2, lk8 = (t & 3) * 8;
+  const int gi = I * D3 + lr, gj = J * D3 + lr;
+  const bool vi = gi < n, vj = gj < n;
+  const double* ap = W1 + (size_t)(vi ? gi : 0) * ldw;
+  const double* bp = W1 + (size_t)(vj ? gj : 0) * ldw;
+  double acc[2][4], zy[2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { acc[u][v] = 0.0; zy[u][v] = 0.0; }
+  double ra[8], rb[8];
+  auto gload = [&](int k0) {  // kbeg, kend are multiples of 32 and ldw is a multiple of 32: 16-byte aligned double2 loads
+    const double2* pa = reinterpret_cast<const double2*>(ap + k0 + lk8);
+    const double2* pb = reinterpret_cast<const double2*>(bp + k0 + lk8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double2 va = vi ? pa[u] : make_double2(0.0, 0.0);
+      const double2 vb = vj ? pb[u] : make_double2(0.0, 0.0);
+      ra[2 * u] = va.x; ra[2 * u + 1] = va.y; rb[2 * u] = vb.x; rb[2 * u + 1] = vb.y;
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { As[lk8 + u][lr] = ra[u]; Bs[lk8 + u][lr] = rb[u]; }
+  };
+  auto mma = [&](double (&c)[2][4]) {
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
+      c[0][0] = fma(a01.x, b01.x, c[0][0]); c[0][1] = fma(a01.x, b01.y, c[0][1]);
+      c[0][2] = fma(a01.x, b23.x, c[0][2]); c[0][3] = fma(a01.x, b23.y, c[0][3]);
+      c[1][0] = fma(a01.y, b01.x, c[1][0]); c[1][1] = fma(a01.y, b01.y, c[1][1]);
+      c[1][2] = fma(a01.y, b23.x, c[1][2]); c[1][3] = fma(a01.y, b23.y, c[1][3]);
+    }
+  };
+  if (kbeg < kend) {
+    gload(kbeg);
+    sstore();
+  }
+  __syncthreads();
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
+    if (k0 + 32 < kend) gload(k0 + 32);
+    mma(acc);
+    __syncthreads();
+    if (k0 + 32 < kend) sstore();
+    __syncthreads();
+  }
+  if (do_tail) {
+    // rank-21 Woodbury tail (32-wide): zy = Z_i . Y_j + Y_i . Z_j as two more slabs
+    for (int pass = 0; pass < 2; ++pass) {
+      const double* Ai = pass ? Yb : Zb;
+      const double* Bj = pass ? Zb : Yb;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        As[lk8 + u][lr] = vi ? Ai[(size_t)gi * 32 + lk8 + u] : 0.0;
+        Bs[lk8 + u][lr] = vj ? Bj[(size_t)gj * 32 + lk8 + u] : 0.0;
+      }
+      __syncthreads();
+      mma(zy);
+      __syncthreads();
+    }
+  }
+  // epilogue: the CTA owns (I, J) and (J, I); the transposed tile goes through shared memory
+  if (do_sym) {
+    for (int e = t; e < D3 * D3; e += 128) {
+      const int r = e >> 5, c = e & 31;  // element (r, c) of block (J, I)
+      const int gr = J * D3 + r, gc = I * D3 + c;
+      Pt[c][r] = (gr < n && gc < n) ? Pin[(size_t)gr * n + gc] : 0.0;
+    }
+    __syncthreads();
+  }
+  double outv[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int r = ty * 2 + a, gr = I * D3 + r;
+    const int oi = (do_tail && gr < n) ? omega_inv[gr] : -1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int cc = tx * 4 + c, gc = J * D3 + cc;
+      double v = 0.0;
+      if (gr < n && gc < n) {
+        const double pij = Pin[(size_t)gr * n + gc];
+        v = (do_sym ? 0.5 * (pij + Pt[r][cc]) : pij) - acc[a][c];
+        if (do_tail) {
+          const int oj = omega_inv[gc];
+          double q = 0.0;
+          if (oj >= 0) q += Qb[(size_t)gr * 32 + oj];
+          if (oi >= 0) q += Qb[(size_t)gc * 32 + oi];
+          v += -0.5 * q + 0.5 * zy[a][c];
+        }
+        Pout[(size_t)gr * n + gc] = v;
+      }
+      outv[a][c] = v;
+    }
+  }
+  // mirror: block (J, I) = block (I, J)^T; on a diagonal block the lower half takes the upper half's values so that the
+  // result is symmetric to the bit
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Pt[ty * 2 + a][tx * 4 + c] = outv[a][c];
+  __syncthreads();
+  for (int e = t; e < D3 * D3; e += 128) {
+    const int r = e >> 5, c = e & 31;
+    const int gr = J * D3 + r, gc = I * D3 + c;
+    if (gr < n && gc < n && (I != J || r > c)) Pout[(size_t)gr * n + gc] = Pt[c][r];
+  }
+}
+
+// Pout = [sym](Pin) - W1[:, kbeg:kend] W1[:, kbeg:kend]^T [+ Woodbury/Omega tail]; Pin == Pout allowed.
+void downdate_f64_range(cudaStream_t s, const double* Pin, double* Pout, int n, const double* T, int m_pad, int n_pad, int kbeg,
+                        int kend, int do_sym, int do_tail, const int* omega_inv, const double* Zb, const double* Yb,
+                        const double* Qb) {
+  const int nt = (n + D3 - 1) / D3;
+  k_downdate32<<<nt * (nt + 1) / 2, 128, 0, s>>>(Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
+                                                 omega_inv, Zb, Yb, Qb);
+  count_launch();
+}
+
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                   const double* Zb, const double* Yb, const double* Qb) {
   const int nt = (n + DT - 1) / DT;
+  if (nt * (nt + 1) / 2 < 296) {  // less than one wave of 64x64 tile pairs: quarter-size tiles
+    downdate_f64_range(s, P, P, n, T, m_pad, n_pad, 0, m_pad, 1, 1, omega_inv, Zb, Yb, Qb);
+    return;
+  }
   k_downdate<<<nt * (nt + 1) / 2, 256, 0, s>>>(P, n, T, m_pad, n_pad, omega_inv, Zb, Yb, Qb);
   count_launch();
 }

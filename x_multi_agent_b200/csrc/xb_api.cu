@@ -96,11 +96,12 @@ struct ListDev {
 };
 
 enum { ST_ASSEMBLE, ST_MANAGE, ST_TRACKS, ST_GRAM, ST_CHOLG, ST_SLAMROWS, ST_BUILD, ST_TALLCHOL, ST_CORRECT, ST_DOWNDATE,
-       ST_POST, ST_STORE, ST_PROPAGATE, ST_SIDE_SLAM, ST_SIDE_CHOL, ST_SIDE_MEANS, ST_COUNT };
+       ST_POST, ST_STORE, ST_PROPAGATE, ST_SIDE_SLAM, ST_SIDE_CHOL, ST_SIDE_MEANS, ST_SIDE_DD, ST_COUNT };
 // the "side_*" stages run on the filter's internal side streams, concurrently with the stages listed before them
 static const char* kStageNames[ST_COUNT] = {"assemble", "manage", "tracks", "gram", "chol_gram", "slam_rows", "build_s_pht",
                                             "tallchol", "correct", "downdate", "post_update", "store", "propagate",
-                                            "side_slam_part", "side_tallchol_slam_cols", "side_prop_means"};
+                                            "side_slam_part", "side_tallchol_slam_cols", "side_prop_means", "side_downdate_slam_cols"};
+static_assert(ST_COUNT <= XB_MAX_STAGES, "xb_profile_read callers size their arrays with XB_MAX_STAGES");
 struct ProfSpan { int stage; cudaEvent_t e0, e1; };
 
 struct xb_filter {
@@ -122,6 +123,11 @@ struct xb_filter {
   bool side_pending = false;   // a construct call has forked the SLAM part; apply_constructed joins it
   bool slam_part_done = false; // the tall buffer already holds the SLAM-column part for the pending update
   bool side_used_corr = false; // ... and it was built with a non-zero correction_total
+  // early part of the covariance downdate: sym(P) - W1s W1s^T (the SLAM columns of W1 exist after the side factorisation) is
+  // written into a freshly claimed generation on side2 while the main stream is still busy with the MSCKF pipeline; apply finishes it in place
+  cudaEvent_t ev_dd = nullptr;
+  bool dd_pending = false;
+  int dd_cols = 0;
   bool xw_final = false;       // no estimate changed since ev_corr was recorded
   bool overlap = true;         // XB_NO_OVERLAP=1 runs everything on the one stream
   int chol_share = 4;          // concurrent dataflow launches each take 1/chol_share of the co-resident CTA slots
@@ -143,6 +149,9 @@ struct xb_filter {
   // work state
   double* d_xw = nullptr;   // LX
   double* d_WA = nullptr;   // N x N scratch / assembled covariance
+  double* d_WB = nullptr;   // second scratch: work_load / manage ping-pong between the two, generations are claimed only
+                            // for a covariance that a ring slot is going to reference
+  double* d_dd = nullptr;   // destination of the pending early downdate (a claimed generation)
   double* d_Pw = nullptr;   // points at WA or a generation
   double* d_corr = nullptr; // N correction_total
   double* d_delta = nullptr;
@@ -347,7 +356,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   if (cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&f->side2, cudaStreamNonBlocking) != cudaSuccess)
     return fail(XB_E_CUDA, "cudaStreamCreate failed");
-  for (cudaEvent_t* e : {&f->ev_fork, &f->ev_side, &f->ev_corr, &f->ev_means})
+  for (cudaEvent_t* e : {&f->ev_fork, &f->ev_side, &f->ev_corr, &f->ev_means, &f->ev_dd})
     CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   if (const char* e = getenv("XB_NO_OVERLAP")) f->overlap = atoi(e) == 0;
   if (const char* e = getenv("XB_CHOL_SHARE")) f->chol_share = std::max(1, atoi(e));
@@ -361,6 +370,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_Pgen, (size_t)f->NG * N * N, double);
   DA(f->d_xw, LX, double);
   DA(f->d_WA, (size_t)N * N, double);
+  DA(f->d_WB, (size_t)N * N, double);
   DA(f->d_corr, N, double);
   DA(f->d_delta, N, double);
   DA(f->d_FQ, (size_t)128 * 450, double);
@@ -499,7 +509,7 @@ extern "C" int xb_destroy(xb_filter* f) {
   cudaStreamSynchronize(f->stream);
   if (f->side) { cudaStreamSynchronize(f->side); cudaStreamDestroy(f->side); }
   if (f->side2) { cudaStreamSynchronize(f->side2); cudaStreamDestroy(f->side2); }
-  for (cudaEvent_t e : {f->ev_fork, f->ev_side, f->ev_corr, f->ev_means})
+  for (cudaEvent_t e : {f->ev_fork, f->ev_side, f->ev_corr, f->ev_means, f->ev_dd})
     if (e) cudaEventDestroy(e);
   for (void* p : f->allocs) cudaFree(p);
   if (f->h_pin) cudaFreeHost(f->h_pin);
@@ -755,8 +765,8 @@ extern "C" int xb_work_load(xb_filter* f, int slot) {
   StageTimer st_(f, ST_ASSEMBLE);
   CK(cudaMemcpyAsync(f->d_xw, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
   launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
-                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_WA);
-  f->d_Pw = f->d_WA;
+                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_WB);
+  f->d_Pw = f->d_WB;
   return XB_OK;
 }
 // claim the next covariance generation as destination; slots still pointing at it lose their state
@@ -813,6 +823,8 @@ extern "C" int xb_work_get(xb_filter* f, double* xvec_out, double* cov_out, int 
 // The SLAM-column part of a constructed update was computed early (side stream) from the P / estimates / correction_total
 // of that moment.  Anything that changes one of them before apply_constructed discards it; apply then rebuilds it in order.
 static int invalidate_early(xb_filter* f) {
+  if (f->dd_pending) CK(cudaStreamWaitEvent(f->stream, f->ev_dd, 0));
+  f->dd_pending = false;
   if (f->side_pending) CK(cudaStreamWaitEvent(f->stream, f->ev_side, 0));
   f->side_pending = false;
   f->slam_part_done = false;
@@ -910,9 +922,9 @@ extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
   if (!reanch.empty())
     CK(cudaMemcpyAsync(f->d_reanch, ra, sizeof(int) * reanch.size(), cudaMemcpyHostToDevice, f->stream));
   CK(cudaEventRecord(f->ipin_ev[f->ipin_cur], f->stream));
-  // destination: a fresh generation (or WA when the source already is a generation buffer)
+  // destination: the scratch buffer that is not the source
   double* src_P = f->d_Pw;
-  double* dst_P = (src_P == f->d_WA) ? claim_generation(f) : f->d_WA;
+  double* dst_P = (src_P == f->d_WA) ? f->d_WB : f->d_WA;
   launch_manage_dev(f->stream, M, F, N, f->n_poses, nf, slide, (int)reanch.size(), f->d_featsrc, f->d_reanch, f->d_rowmap,
                     f->d_ccols, f->d_cvals, f->d_mscratch, f->d_xw, src_P, dst_P, f->d_Tm, f->d_T2);
   f->d_Pw = dst_P;
@@ -1070,9 +1082,9 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   const ListDev& l0 = which == 0 ? f->l_msckf : f->l_short;
   const int n0 = l0.n, n1 = which == 0 ? f->l_newms.n : 0, ns = which == 0 ? f->l_slam.n : 0;
   if (ns > f->n_features) return fail(XB_E_INVALID, "more SLAM tracks than SLAM features in the state");
-  if (f->side_pending) {  // a constructed update that was never applied: its side work must not outlive this call
-    CK(cudaStreamWaitEvent(f->stream, f->ev_side, 0));
-    f->side_pending = false;
+  if (f->side_pending || f->dd_pending) {  // a constructed update that was never applied: its side work must not outlive this call
+    int rci = invalidate_early(f);
+    if (rci) return rci;
   }
   f->slam_part_done = false;
   f->last_which = which;
@@ -1102,6 +1114,21 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
       CK(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
       slam_phase(f, f->side, d, ST_SIDE_SLAM, ST_SIDE_CHOL, f->chol_share, true);
       CK(cudaEventRecord(f->ev_side, f->side));
+      {
+        const int nt64 = (f->N + 63) / 64;
+        const bool dd_early = f->cfg.iekf_iter <= 1 && f->cfg.downdate_precision == 0 && nt64 * (nt64 + 1) / 2 < 296 &&
+                              !getenv("XB_NO_EARLY_DOWNDATE");
+        if (dd_early) {
+          f->d_dd = claim_generation(f);
+          CK(cudaStreamWaitEvent(f->side2, f->ev_side, 0));
+          StageTimer st_(f, ST_SIDE_DD, f->side2);
+          downdate_f64_range(f->side2, f->d_Pw, f->d_dd, f->N, f->d_T, d.m_pad, d.n_pad, 0, d.s_pad, 1, 0, f->d_omega_inv, f->d_Zb,
+                             f->d_Yb, f->d_Qb);
+          CK(cudaEventRecord(f->ev_dd, f->side2));
+          f->dd_pending = true;
+          f->dd_cols = d.s_pad;
+        }
+      }
       f->side_pending = true;
       f->slam_part_done = true;
       f->side_used_corr = !f->corr_zero;
@@ -1194,10 +1221,20 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
   f->xw_final = true;
   if (cov_update) {
     StageTimer st_(f, ST_DOWNDATE);
-    if (f->cfg.downdate_precision == 1)
+    if (f->dd_pending && f->dd_cols == chol_from && chol_from > 0) {
+      // the SLAM-column part is already in d_WA (side2): finish with the slab columns and the Woodbury / Omega terms
+      CK(cudaStreamWaitEvent(f->stream, f->ev_dd, 0));
+      downdate_f64_range(f->stream, f->d_dd, f->d_dd, N, f->d_T, m_pad, n_pad, chol_from, m_pad, 0, 1, f->d_omega_inv, f->d_Zb,
+                         f->d_Yb, f->d_Qb);
+      f->d_Pw = f->d_dd;
+    } else if (f->cfg.downdate_precision == 1)
       downdate_tc(f->stream, f->d_Pw, N, f->d_T, m_pad, n_pad, f->d_omega_inv, f->d_Zb, f->d_Yb, f->d_Qb, f->d_tcws);
     else
       downdate_f64(f->stream, f->d_Pw, N, f->d_T, m_pad, n_pad, f->d_omega_inv, f->d_Zb, f->d_Yb, f->d_Qb);
+  }
+  if (f->dd_pending) {  // not consumed (cov_update == 0): later work on the main stream must not overtake side2
+    CK(cudaStreamWaitEvent(f->stream, f->ev_dd, 0));
+    f->dd_pending = false;
   }
   return XB_OK;
 }

@@ -35,6 +35,10 @@ void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pa
                     int* flags, int* err, double piv_tol, const double* diag0, long long* trace, int share);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                   const double* Zb, const double* Yb, const double* Qb);
+// K-range form (small N): Pout = [sym](Pin) - W1[:, kbeg:kend] W1[:, kbeg:kend]^T [+ Woodbury / Omega tail]
+void downdate_f64_range(cudaStream_t s, const double* Pin, double* Pout, int n, const double* T, int m_pad, int n_pad, int kbeg,
+                        int kend, int do_sym, int do_tail, const int* omega_inv, const double* Zb, const double* Yb,
+                        const double* Qb);
 void symmetrise(cudaStream_t s, double* P, int n);
 void gemv(cudaStream_t s, int rows, int cols, const double* A, int lda, const double* x, double* y);
 void transpose(cudaStream_t s, const double* in, double* out, int rows, int cols);

@@ -372,9 +372,9 @@ class Filter:
 
     def profile_read(self, reset=True):
         """{stage: (total_ms, count)} accumulated by the per-stage CUDA-event timers."""
-        names = (C.c_char_p * 16)()
-        ms = np.zeros(16)
-        cnt = (C.c_longlong * 16)()
+        names = (C.c_char_p * 64)()
+        ms = np.zeros(64)
+        cnt = (C.c_longlong * 64)()
         n = L.check(self.lib.xb_profile_read(self.h, names, L.dptr(ms), cnt, int(reset)))
         return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
