@@ -65,49 +65,60 @@ __device__ __forceinline__ void tri_advance(int& r, int& c, int n) {
 // 182k cycles, right-looking column-per-lane 193k (every iteration waits for its own store), fully unrolled
 // register tiles 128k (instruction-fetch bound: the kernel runs once per warp), this loop: see profiles/.
 // ------------------------------------------------------------------------------------------------
+// one column step for the row groups u < NG (rows c + lane + 32 u); returns the pivot, < 0 signals "not positive"
+template <int NG>
+__device__ __forceinline__ bool gate_chol_column(double* __restrict__ X, int c, int Rend, int lane) {
+  const double* Lc = X + tri_idx(c, 0);
+  double* pr[NG];
+  bool act[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) {
+    const int r = c + lane + 32 * u;
+    act[u] = r <= Rend;
+    pr[u] = X + tri_idx(act[u] ? r : c, 0);  // idle slots read row c (harmless) and store nothing
+  }
+  double s0[NG], s1[NG], s2[NG], s3[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) { s0[u] = 0.0; s1[u] = 0.0; s2[u] = 0.0; s3[u] = 0.0; }
+  int k = 0;
+#pragma unroll 2
+  for (; k + 3 < c; k += 4) {  // loads only: 4 broadcasts of the finished row c + 4 entries of every owned row per step
+    const double l0 = Lc[k], l1 = Lc[k + 1], l2 = Lc[k + 2], l3 = Lc[k + 3];
+#pragma unroll
+    for (int u = 0; u < NG; ++u) {
+      s0[u] = fma(pr[u][k], l0, s0[u]); s1[u] = fma(pr[u][k + 1], l1, s1[u]);
+      s2[u] = fma(pr[u][k + 2], l2, s2[u]); s3[u] = fma(pr[u][k + 3], l3, s3[u]);
+    }
+  }
+  for (; k < c; ++k) {
+    const double l0 = Lc[k];
+#pragma unroll
+    for (int u = 0; u < NG; ++u) s0[u] = fma(pr[u][k], l0, s0[u]);
+  }
+  double v[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) v[u] = pr[u][c] - ((s0[u] + s1[u]) + (s2[u] + s3[u]));
+  const double piv = __shfl_sync(0xffffffffu, v[0], 0);
+  if (!(piv > 0.0)) return false;
+  const double rs = rsqrt(piv);
+  __syncwarp();  // every lane has read row c's old entries before lane 0 overwrites X[c][c]
+#pragma unroll
+  for (int u = 0; u < NG; ++u)
+    if (act[u]) pr[u][c] = (u == 0 && lane == 0) ? piv * rs : v[u] * rs;
+  __syncwarp();
+  return true;
+}
 template <int ROWS>  // rows per lane: ceil((R2 + 7) / 32) <= ROWS
 __device__ __forceinline__ bool gate_chol_packed(double* __restrict__ X, int R2, int lane) {
   const int Rend = R2 + 6;
   for (int c = 0; c < R2; ++c) {
-    const double* Lc = X + tri_idx(c, 0);
-    double* pr[ROWS];
-    bool act[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u) {
-      const int r = c + lane + 32 * u;
-      act[u] = r <= Rend;
-      pr[u] = X + tri_idx(act[u] ? r : c, 0);  // idle slots read row c (harmless) and store nothing
-    }
-    double s0[ROWS], s1[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u) { s0[u] = 0.0; s1[u] = 0.0; }
-    int k = 0;
-#pragma unroll 2
-    for (; k + 3 < c; k += 4) {  // loads only: 4 broadcasts of the finished row c + 4 entries of every owned row per step
-      const double l0 = Lc[k], l1 = Lc[k + 1], l2 = Lc[k + 2], l3 = Lc[k + 3];
-#pragma unroll
-      for (int u = 0; u < ROWS; ++u) {
-        const double x0 = pr[u][k], x1 = pr[u][k + 1], x2 = pr[u][k + 2], x3 = pr[u][k + 3];
-        s0[u] = fma(x0, l0, s0[u]); s1[u] = fma(x1, l1, s1[u]);
-        s0[u] = fma(x2, l2, s0[u]); s1[u] = fma(x3, l3, s1[u]);
-      }
-    }
-    for (; k < c; ++k) {
-      const double l0 = Lc[k];
-#pragma unroll
-      for (int u = 0; u < ROWS; ++u) s0[u] = fma(pr[u][k], l0, s0[u]);
-    }
-    double v[ROWS];
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u) v[u] = pr[u][c] - (s0[u] + s1[u]);
-    const double piv = __shfl_sync(0xffffffffu, v[0], 0);
-    if (!(piv > 0.0)) return false;
-    const double rs = rsqrt(piv);
-    __syncwarp();  // every lane has read row c's old entries before lane 0 overwrites X[c][c]
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u)
-      if (act[u]) pr[u][c] = (u == 0 && lane == 0) ? piv * rs : v[u] * rs;
-    __syncwarp();
+    const int ng = (Rend - c) / 32 + 1;  // row groups that still hold a row: shrinks as the factorisation advances
+    bool ok;
+    if (ng <= 1) ok = gate_chol_column<1>(X, c, Rend, lane);
+    else if (ng == 2 || ROWS == 2) ok = gate_chol_column<2>(X, c, Rend, lane);
+    else if (ng == 3 || ROWS == 3) ok = gate_chol_column<3>(X, c, Rend, lane);
+    else ok = gate_chol_column<ROWS>(X, c, Rend, lane);
+    if (!ok) return false;
   }
   return true;
 }
@@ -436,6 +447,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
           double T[12];
           const int rp = XB_CORE + 3 * pi_, ra = XB_CORE + 3 * M + 3 * pi_;
           const int cpn = XB_CORE + 3 * pk_, can = XB_CORE + 3 * M + 3 * pk_;
+          const bool symblk = pi_ == np - 1 && pk_ == np - 1;  // the newest clone's own block is not symmetric: use sym(P)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             double tp0 = 0, tp1 = 0, ta0 = 0, ta1 = 0;
@@ -443,7 +455,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
             for (int a = 0; a < 3; ++a) {
               double ppp = P[(size_t)(rp + a) * ld + cpn + c], pap = P[(size_t)(ra + a) * ld + cpn + c];
               double ppa = P[(size_t)(rp + a) * ld + can + c], paa = P[(size_t)(ra + a) * ld + can + c];
-              if (pi_ == np - 1 && pk_ == np - 1) {  // the newest clone's own block is not symmetric: use sym(P)
+              if (symblk) {
                 ppp = 0.5 * (ppp + P[(size_t)(cpn + c) * ld + rp + a]);
                 pap = 0.5 * (pap + P[(size_t)(cpn + c) * ld + ra + a]);
                 ppa = 0.5 * (ppa + P[(size_t)(can + c) * ld + rp + a]);
