@@ -5,6 +5,7 @@
 //                   P <- (P + P^T)/2 - W W^T ,  delta = W z
 // which is the same arithmetic with the explicit inverse replaced by a Cholesky factor.
 #include <algorithm>
+#include <cstdlib>
 
 #include "xb_kernels.h"
 
@@ -160,12 +161,130 @@ __global__ void __launch_bounds__(128) k_gemm32(int M, int N, int Kfull, double 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp64 tensor-core GEMM: mma.sync.m8n8k4.f64 (DMMA).  Measured on B200 (tools/bench_dmma.cu): DMMA and DFMA share the
+// same 36.9 TFLOP/s peak, but one DMMA retires 256 FMAs from two operand registers per lane, so a warp needs ~7x fewer
+// issue slots and shared-memory loads per flop -- which is what bounds the small, low-occupancy GEMMs of this path
+// (ncu on the DFMA tiles: fp64 pipe 12 % active, 66 % of the stalls on shared-memory operands).
+//   CTA tile 32 x 64, four warps (2 x 2), warp tile 16 x 32 = 2 x 4 DMMA accumulators; K in 16-wide slabs through a
+//   3-stage cp.async ring (8-byte copies: operands such as P + 15 with an odd leading dimension are only 8-byte aligned;
+//   out-of-range elements are zero-filled by the copy itself).
+//   Fragment layout (PTX ISA, m8n8k4 .f64): A row g = lane/4, col t = lane%4; B row(k) t, col(n) g; C row g, cols 2t, 2t+1.
+// Same interface as k_gemm (split-K through blockIdx.z writes partials at C + z*strideC).
+// ------------------------------------------------------------------------------------------------
+#define MG_BM 32
+#define MG_BN 64
+#define MG_BK 16
+#define MG_ST 3
+#define MG_LDK (MG_BK + 4)   // [row][k] tiles: row stride 20 doubles = 4 mod 16 -> conflict-free fragment loads
+#define MG_LDN (MG_BN + 4)   // [k][n] tile of a non-transposed B: row stride 68 doubles = 4 mod 16
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <bool TRANS_B>
+__global__ void __launch_bounds__(128) k_gemm_mma(int M, int N, int Kfull, double alpha, const double* __restrict__ A, int lda,
+                                                  const double* __restrict__ B, int ldb, double beta, double* __restrict__ C,
+                                                  int ldc, int kchunk, size_t strideC) {
+  __shared__ double As[MG_ST][MG_BM * MG_LDK];
+  __shared__ double Bs[MG_ST][TRANS_B ? MG_BN * MG_LDK : MG_BK * MG_LDN];
+  const int kbeg = blockIdx.z * kchunk;
+  const int K = min(Kfull, kbeg + kchunk);
+  C += (size_t)blockIdx.z * strideC;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int m0 = blockIdx.y * MG_BM, n0 = blockIdx.x * MG_BN;
+  const int wm0 = (warp >> 1) * 16, wn0 = (warp & 1) * 32;
+  const int nslab = (K - kbeg + MG_BK - 1) / MG_BK;
+  auto issue = [&](int slab) {
+    if (slab < nslab) {
+      const int k0 = kbeg + slab * MG_BK;
+      double* as = As[slab % MG_ST];
+      double* bs = Bs[slab % MG_ST];
+      // A tile: 32 rows x 16 k = 512 elements, 4 per thread (k fastest: 16 consecutive threads cover one row)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = t + 128 * u, r = e >> 4, k = e & 15;
+        const bool v = m0 + r < M && k0 + k < K;
+        cp_async8(as + r * MG_LDK + k, v ? A + (size_t)(m0 + r) * lda + k0 + k : A, v);
+      }
+      if (TRANS_B) {  // B is [N x K]: 64 rows x 16 k
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = t + 128 * u, r = e >> 4, k = e & 15;
+          const bool v = n0 + r < N && k0 + k < K;
+          cp_async8(bs + r * MG_LDK + k, v ? B + (size_t)(n0 + r) * ldb + k0 + k : B, v);
+        }
+      } else {  // B is [K x N]: 16 k rows x 64 columns (n fastest)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = t + 128 * u, k = e >> 6, c = e & 63;
+          const bool v = k0 + k < K && n0 + c < N;
+          cp_async8(bs + k * MG_LDN + c, v ? B + (size_t)(k0 + k) * ldb + n0 + c : B, v);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll
+  for (int s_ = 0; s_ < MG_ST - 1; ++s_) issue(s_);
+  for (int slab = 0; slab < nslab; ++slab) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(MG_ST - 2) : "memory");
+    __syncthreads();
+    issue(slab + MG_ST - 1);
+    const double* as = As[slab % MG_ST];
+    const double* bs = Bs[slab % MG_ST];
+#pragma unroll
+    for (int kk = 0; kk < MG_BK; kk += 4) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = as[(wm0 + 8 * i + g) * MG_LDK + kk + tg];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        b[j] = TRANS_B ? bs[(wn0 + 8 * j + g) * MG_LDK + kk + tg] : bs[(kk + tg) * MG_LDN + wn0 + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int gr = m0 + wm0 + 8 * i + g;
+    if (gr >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gc = n0 + wn0 + 8 * j + 2 * tg + h;
+        if (gc >= N) continue;
+        double* p = &C[(size_t)gr * ldc + gc];
+        *p = (beta == 0.0) ? alpha * acc[i][j][h] : alpha * acc[i][j][h] + beta * (*p);
+      }
+  }
+}
+
+// XB_GEMM=dfma selects the CUDA-core tiles (k_gemm / k_gemm32) for A/B measurements; default is the DMMA kernel
+static const bool g_use_mma = [] { const char* e = getenv("XB_GEMM"); return !(e && e[0] == 'd'); }();
 static bool small_gemm(int M, int N, int nz) { return (size_t)((M + 63) / 64) * ((N + 63) / 64) * nz < 128; }
 
 void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
-  if (small_gemm(M, N, 1)) {
+  if (g_use_mma) {
+    dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM);
+    k_gemm_mma<true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  } else if (small_gemm(M, N, 1)) {
     dim3 grid((N + 31) / 32, (M + 31) / 32);
     k_gemm32<true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   } else {
@@ -177,7 +296,11 @@ void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
 // C_z = A[:, kz] B[:, kz]^T for nz K-chunks (partials at C + z*strideC; the consumer sums them in a fixed order)
 void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
                     int ldc, size_t strideC, int nz) {
-  if (small_gemm(M, N, nz)) {
+  if (g_use_mma) {
+    const int kchunk = ((K + nz - 1) / nz + MG_BK - 1) / MG_BK * MG_BK;
+    dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM, nz);
+    k_gemm_mma<true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+  } else if (small_gemm(M, N, nz)) {
     const int kchunk = ((K + nz - 1) / nz + 31) / 32 * 32;
     dim3 grid((N + 31) / 32, (M + 31) / 32, nz);
     k_gemm32<true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
@@ -191,7 +314,10 @@ void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int ld
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
-  if (small_gemm(M, N, 1)) {
+  if (g_use_mma) {
+    dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM);
+    k_gemm_mma<false><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  } else if (small_gemm(M, N, 1)) {
     dim3 grid((N + 31) / 32, (M + 31) / 32);
     k_gemm32<false><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   } else {
