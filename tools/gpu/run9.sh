@@ -1,5 +1,5 @@
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | grep -v "^ok" | tail -30
-for cfg in "XB_GEMM=dfma" "XB_GEMM=mma"; do
+for cfg in "XB_GEMM=mma"; do
 echo "== $cfg"
 env $cfg timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
 import sys,json

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(128) k_gemm32(int M, int N, int Kfull, double 
 #define MG_ST 3
 #define MG_LDK (MG_BK + 4)   // [row][k] tiles: row stride 20 doubles = 4 mod 16 -> conflict-free fragment loads
 #define MG_LDN (MG_BN + 4)   // [k][n] tile of a non-transposed B: row stride 68 doubles = 4 mod 16
+#define MG_LDM (MG_BM + 4)   // [k][m] tile of a k-major A: row stride 36 doubles = 4 mod 16
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int n = valid ? 8 : 0;
@@ -186,11 +187,11 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-template <bool TRANS_B>
+template <bool TRANS_B, bool TRANS_A = false>  // TRANS_A: A is given k-major, [K x M] row-major (C = A^T op(B))
 __global__ void __launch_bounds__(128) k_gemm_mma(int M, int N, int Kfull, double alpha, const double* __restrict__ A, int lda,
                                                   const double* __restrict__ B, int ldb, double beta, double* __restrict__ C,
                                                   int ldc, int kchunk, size_t strideC) {
-  __shared__ double As[MG_ST][MG_BM * MG_LDK];
+  __shared__ double As[MG_ST][TRANS_A ? MG_BK * MG_LDM : MG_BM * MG_LDK];
   __shared__ double Bs[MG_ST][TRANS_B ? MG_BN * MG_LDK : MG_BK * MG_LDN];
   const int kbeg = blockIdx.z * kchunk;
   const int K = min(Kfull, kbeg + kchunk);
@@ -208,9 +209,15 @@ __global__ void __launch_bounds__(128) k_gemm_mma(int M, int N, int Kfull, doubl
       // A tile: 32 rows x 16 k = 512 elements, 4 per thread (k fastest: 16 consecutive threads cover one row)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int e = t + 128 * u, r = e >> 4, k = e & 15;
-        const bool v = m0 + r < M && k0 + k < K;
-        cp_async8(as + r * MG_LDK + k, v ? A + (size_t)(m0 + r) * lda + k0 + k : A, v);
+        if (TRANS_A) {
+          const int e = t + 128 * u, k = e >> 5, r = e & 31;
+          const bool v = m0 + r < M && k0 + k < K;
+          cp_async8(as + k * MG_LDM + r, v ? A + (size_t)(k0 + k) * lda + m0 + r : A, v);
+        } else {
+          const int e = t + 128 * u, r = e >> 4, k = e & 15;
+          const bool v = m0 + r < M && k0 + k < K;
+          cp_async8(as + r * MG_LDK + k, v ? A + (size_t)(m0 + r) * lda + k0 + k : A, v);
+        }
       }
       if (TRANS_B) {  // B is [N x K]: 64 rows x 16 k
 #pragma unroll
@@ -247,7 +254,8 @@ __global__ void __launch_bounds__(128) k_gemm_mma(int M, int N, int Kfull, doubl
     for (int kk = 0; kk < MG_BK; kk += 4) {
       double a[2], b[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) a[i] = as[(wm0 + 8 * i + g) * MG_LDK + kk + tg];
+      for (int i = 0; i < 2; ++i)
+        a[i] = TRANS_A ? as[(kk + tg) * MG_LDM + wm0 + 8 * i + g] : as[(wm0 + 8 * i + g) * MG_LDK + kk + tg];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         b[j] = TRANS_B ? bs[(wn0 + 8 * j + g) * MG_LDK + kk + tg] : bs[(kk + tg) * MG_LDN + wn0 + 8 * j + g];
@@ -309,6 +317,14 @@ void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int ld
     dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
     k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   }
+  count_launch();
+}
+// C_z = A[kz, 0:M]^T B[kz, 0:N] for nz K-chunks of row-major [K x M] / [K x N] operands (Gram matrices of tall slabs)
+void gemm_tn_splitk(cudaStream_t s, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                    size_t strideC, int nz) {
+  const int kchunk = ((K + nz - 1) / nz + MG_BK - 1) / MG_BK * MG_BK;
+  dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM, nz);
+  k_gemm_mma<false, true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   count_launch();
 }
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
@@ -992,20 +1008,135 @@ __global__ void __launch_bounds__(128) k_downdate32(const double* __restrict__ P
   }
 }
 
+// fp64 tensor-core (DMMA) form of k_downdate32: same tile pairs, arguments and result; four warps (2 x 2) own 16 x 16
+// quadrants of the 32 x 32 tile = 2 x 2 m8n8k4 accumulators each, operands through the 3-stage cp.async ring.  The
+// Woodbury tail  +(Z_i.Y_j + Y_i.Z_j)/2  enters the same accumulators as four more slabs with the A fragments scaled by -1/2.
+__global__ void __launch_bounds__(128) k_downdate_mma(const double* __restrict__ Pin, double* __restrict__ Pout, int n,
+                                                      const double* __restrict__ W1, int ldw, int kbeg, int kend, int do_sym,
+                                                      int do_tail, const int* __restrict__ omega_inv,
+                                                      const double* __restrict__ Zb, const double* __restrict__ Yb,
+                                                      const double* __restrict__ Qb) {
+  const int nt = (n + D3 - 1) / D3;
+  int b = blockIdx.x, I = 0;
+  while (b >= nt - I) { b -= nt - I; ++I; }
+  const int J = I + b;
+  __shared__ double As[MG_ST][D3 * MG_LDK];
+  __shared__ double Bs[MG_ST][D3 * MG_LDK];
+  __shared__ double Pt[D3][D3 + 1];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int wm0 = (warp >> 1) * 16, wn0 = (warp & 1) * 16;
+  const int nmain = (kend - kbeg) / MG_BK;          // kbeg, kend are multiples of 32
+  const int nslab = nmain + (do_tail ? 4 : 0);      // tail: Z_I.Y_J (2 slabs of 16), then Y_I.Z_J (2 slabs)
+  auto issue = [&](int slab) {
+    if (slab < nslab) {
+      const double *a, *bsrc;
+      int lda_, k0;
+      if (slab < nmain) { a = W1; bsrc = W1; lda_ = ldw; k0 = kbeg + slab * MG_BK; }
+      else {
+        const int ts = slab - nmain;
+        a = ts < 2 ? Zb : Yb; bsrc = ts < 2 ? Yb : Zb; lda_ = 32; k0 = (ts & 1) * MG_BK;
+      }
+      double* as = As[slab % MG_ST];
+      double* bs = Bs[slab % MG_ST];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = t + 128 * u, r = e >> 4, k = e & 15;
+        const bool vi = I * D3 + r < n, vj = J * D3 + r < n;
+        cp_async8(as + r * MG_LDK + k, vi ? a + (size_t)(I * D3 + r) * lda_ + k0 + k : a, vi);
+        cp_async8(bs + r * MG_LDK + k, vj ? bsrc + (size_t)(J * D3 + r) * lda_ + k0 + k : bsrc, vj);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double acc[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll
+  for (int s_ = 0; s_ < MG_ST - 1; ++s_) issue(s_);
+  for (int slab = 0; slab < nslab; ++slab) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(MG_ST - 2) : "memory");
+    __syncthreads();
+    issue(slab + MG_ST - 1);
+    const double* as = As[slab % MG_ST];
+    const double* bs = Bs[slab % MG_ST];
+    const double sc = slab < nmain ? 1.0 : -0.5;
+#pragma unroll
+    for (int kk = 0; kk < MG_BK; kk += 4) {
+      double a[2], bb[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = sc * as[(wm0 + 8 * i + g) * MG_LDK + kk + tg];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bb[j] = bs[(wn0 + 8 * j + g) * MG_LDK + kk + tg];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // epilogue: the CTA owns (I, J) and (J, I); the transposed tile goes through shared memory
+  if (do_sym) {
+    for (int e = t; e < D3 * D3; e += 128) {
+      const int r = e >> 5, c = e & 31;  // element (r, c) of block (J, I)
+      const int gr = J * D3 + r, gc = I * D3 + c;
+      Pt[c][r] = (gr < n && gc < n) ? Pin[(size_t)gr * n + gc] : 0.0;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = wm0 + 8 * i + g, gr = I * D3 + r;
+    const int oi = (do_tail && gr < n) ? omega_inv[gr] : -1;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = wn0 + 8 * j + 2 * tg + h, gc = J * D3 + cc;
+        double v = 0.0;
+        if (gr < n && gc < n) {
+          const double pij = Pin[(size_t)gr * n + gc];
+          v = (do_sym ? 0.5 * (pij + Pt[r][cc]) : pij) - acc[i][j][h];
+          if (do_tail) {
+            const int oj = omega_inv[gc];
+            double q = 0.0;
+            if (oj >= 0) q += Qb[(size_t)gr * 32 + oj];
+            if (oi >= 0) q += Qb[(size_t)gc * 32 + oi];
+            v -= 0.5 * q;
+          }
+          Pout[(size_t)gr * n + gc] = v;
+        }
+        Pt[r][cc] = v;  // this lane was the only reader of Pt[r][cc]
+      }
+  }
+  __syncthreads();
+  for (int e = t; e < D3 * D3; e += 128) {
+    const int r = e >> 5, c = e & 31;
+    const int gr = J * D3 + r, gc = I * D3 + c;
+    if (gr < n && gc < n && (I != J || r > c)) Pout[(size_t)gr * n + gc] = Pt[c][r];
+  }
+}
+
 // Pout = [sym](Pin) - W1[:, kbeg:kend] W1[:, kbeg:kend]^T [+ Woodbury/Omega tail]; Pin == Pout allowed.
 void downdate_f64_range(cudaStream_t s, const double* Pin, double* Pout, int n, const double* T, int m_pad, int n_pad, int kbeg,
                         int kend, int do_sym, int do_tail, const int* omega_inv, const double* Zb, const double* Yb,
                         const double* Qb) {
   const int nt = (n + D3 - 1) / D3;
-  k_downdate32<<<nt * (nt + 1) / 2, 128, 0, s>>>(Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
-                                                 omega_inv, Zb, Yb, Qb);
+  if (g_use_mma)
+    k_downdate_mma<<<nt * (nt + 1) / 2, 128, 0, s>>>(Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
+                                                     omega_inv, Zb, Yb, Qb);
+  else
+    k_downdate32<<<nt * (nt + 1) / 2, 128, 0, s>>>(Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
+                                                   omega_inv, Zb, Yb, Qb);
   count_launch();
 }
 
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                   const double* Zb, const double* Yb, const double* Qb) {
   const int nt = (n + DT - 1) / DT;
-  if (nt * (nt + 1) / 2 < 296) {  // less than one wave of 64x64 tile pairs: quarter-size tiles
+  if (g_use_mma || nt * (nt + 1) / 2 < 296) {  // tensor-core tile pairs; or (DFMA) less than one wave of 64x64 pairs
     downdate_f64_range(s, P, P, n, T, m_pad, n_pad, 0, m_pad, 1, 1, omega_inv, Zb, Yb, Qb);
     return;
   }

@@ -842,6 +842,7 @@ void launch_slam_rows(cudaStream_t s, const SlamParams& sp) {
 //   k_gram_reduce : fixed-order sum of the partials (deterministic), block-diagonal J^T J terms and
 //                   scatter into the tall Cholesky buffer [G ; g^T].
 // ------------------------------------------------------------------------------------------------
+static const bool g_gram_mma = [] { const char* e = getenv("XB_GEMM"); return !(e && e[0] == 'd'); }();  // see k_linalg.cu
 __global__ void __launch_bounds__(256) k_gram_partial(const double* __restrict__ A, int rows, int W, int chunk,
                                                       double* __restrict__ part) {
   __shared__ double As[16][64 + 4];
@@ -964,16 +965,24 @@ void launch_gram(cudaStream_t s, const GramParams& gp) {
   if (gp.rowsB > 0) {
     nzB = gp.nzB;
     const int chunk = ((gp.rowsB + nzB - 1) / nzB + 15) / 16 * 16;
-    dim3 g(tiles, tiles, nzB);
-    k_gram_partial<<<g, 256, 0, s>>>(gp.B, gp.rowsB, W, chunk, gp.partB);
-    count_launch();
+    if (g_gram_mma) {
+      gemm_tn_splitk(s, W, W, gp.rowsB, gp.B, W, gp.B, W, gp.partB, W, (size_t)W * W, nzB);
+    } else {
+      dim3 g(tiles, tiles, nzB);
+      k_gram_partial<<<g, 256, 0, s>>>(gp.B, gp.rowsB, W, chunk, gp.partB);
+      count_launch();
+    }
   }
   if (gp.rowsD > 0) {
     nzD = gp.nzD;
     const int chunk = ((gp.rowsD + nzD - 1) / nzD + 15) / 16 * 16;
-    dim3 g(tiles, tiles, nzD);
-    k_gram_partial<<<g, 256, 0, s>>>(gp.D, gp.rowsD, W, chunk, gp.partD);
-    count_launch();
+    if (g_gram_mma) {
+      gemm_tn_splitk(s, W, W, gp.rowsD, gp.D, W, gp.D, W, gp.partD, W, (size_t)W * W, nzD);
+    } else {
+      dim3 g(tiles, tiles, nzD);
+      k_gram_partial<<<g, 256, 0, s>>>(gp.D, gp.rowsD, W, chunk, gp.partD);
+      count_launch();
+    }
   }
   k_gram_jtj<<<gp.M, 128, 0, s>>>(gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
   count_launch();

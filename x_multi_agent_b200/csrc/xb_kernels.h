@@ -33,6 +33,8 @@ void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int
 // [jend, cols_pad) left out (their entries do not exist yet; the caller finishes with a Schur complement + plain call).
 void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int jstart_cols, int jend_cols, int phase,
                     int* flags, int* err, double piv_tol, const double* diag0, long long* trace, int share);
+void gemm_tn_splitk(cudaStream_t s, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                    size_t strideC, int nz);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
                   const double* Zb, const double* Yb, const double* Qb);
 // K-range form (small N): Pout = [sym](Pin) - W1[:, kbeg:kend] W1[:, kbeg:kend]^T [+ Woodbury / Omega tail]
