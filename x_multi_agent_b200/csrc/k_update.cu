@@ -225,7 +225,6 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
                                                      const double* __restrict__ P, const int* __restrict__ omega,
                                                      double* __restrict__ om) {
   __shared__ double G[NOM][NOM], E[NOM][NOM], A[NOM][2 * NOM + 1], q[NOM];
-  __shared__ int piv;
   const int t = threadIdx.x;
   for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int k = e / NOM, l = e % NOM;
@@ -253,29 +252,44 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
     A[r][c] = v;
   }
   __syncthreads();
-  for (int c = 0; c < NOM; ++c) {  // Gauss-Jordan with partial pivoting
-    if (t == 0) {
-      int best = c;
-      double bv = fabs(A[c][c]);
-      for (int r = c + 1; r < NOM; ++r)
-        if (fabs(A[r][c]) > bv) { bv = fabs(A[r][c]); best = r; }
-      piv = best;
+  // Gauss-Jordan with partial pivoting by ONE warp (the 21 pivots are a serial chain: warp-level synchronisation instead of
+  // 126 block-wide barriers); the other warps wait at the barrier below
+  if (t < 32) {
+    const int lane = t;
+    for (int c = 0; c < NOM; ++c) {
+      // pivot row: arg max |A[r][c]|, r >= c (first maximum wins, like the serial search it replaces)
+      double bv = (lane >= c && lane < NOM) ? fabs(A[lane][c]) : -1.0;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      const int pv = bi;
+      if (pv != c)
+        for (int x = lane; x < 2 * NOM; x += 32) { const double tmp = A[c][x]; A[c][x] = A[pv][x]; A[pv][x] = tmp; }
+      __syncwarp();
+      const double d = A[c][c];
+      __syncwarp();
+      for (int x = lane; x < 2 * NOM; x += 32) A[c][x] /= d;
+      __syncwarp();
+      // elimination: lane <-> column(s) cc = lane, lane + 32; the multipliers A[r][c] are broadcasts
+      const int c1 = lane + 32;
+      const double p0 = A[c][lane], p1 = c1 < 2 * NOM ? A[c][c1] : 0.0;
+#pragma unroll
+      for (int r = 0; r < NOM; ++r) {
+        if (r == c) continue;
+        const double fr = A[r][c];
+        if (lane != c) A[r][lane] = fma(-fr, p0, A[r][lane]);
+        if (c1 < 2 * NOM) A[r][c1] = fma(-fr, p1, A[r][c1]);
+      }
+      __syncwarp();
+      if (lane < NOM && lane != c) A[lane][c] = 0.0;
+      __syncwarp();
     }
-    __syncthreads();
-    if (piv != c && t < 2 * NOM) { const double tmp = A[c][t]; A[c][t] = A[piv][t]; A[piv][t] = tmp; }
-    __syncthreads();
-    const double d = A[c][c];
-    __syncthreads();
-    if (t < 2 * NOM) A[c][t] /= d;
-    __syncthreads();
-    for (int e = t; e < NOM * 2 * NOM; e += blockDim.x) {
-      const int r = e / (2 * NOM), cc = e % (2 * NOM);
-      if (r != c && cc != c) A[r][cc] = fma(-A[r][c], A[c][cc], A[r][cc]);
-    }
-    __syncthreads();
-    if (t < NOM && t != c) A[t][c] = 0.0;
-    __syncthreads();
   }
+  __syncthreads();
   // C = E * inv
   for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int r = e / NOM, c = e % NOM;
