@@ -138,11 +138,23 @@ void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P
   launch_omega_rows(s, d, 0, d.ns2, P, nullptr, 0, scols, svals, omega, T);
 }
 
+// Gp[k][b] = P[15 + b, Omega_k] (32 x 6M, row-major) and the V tile on the slab columns: V^T[k][ro + a] = Rg[a][Omega_k - 15]
+__global__ void k_omega_gather(UpdateDims d, const double* __restrict__ P, const double* __restrict__ Lg, int ldr,
+                               const int* __restrict__ omega, double* __restrict__ Gp, double* __restrict__ T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (b >= d.ms) return;
+  const int ok = omega[k];
+  Gp[(size_t)k * d.ms + b] = P[(size_t)(XB_CORE + b) * d.N + ok];
+  double v = 0.0;
+  if (ok >= XB_CORE && ok < XB_CORE + d.ms) v = Lg[(size_t)(ok - XB_CORE) * ldr + b];  // Rg[a][b'] = Lg[b'][a]
+  T[(size_t)(d.m_pad + d.n_pad + 64 + k) * d.ld + d.ro + b] = v;
+}
+
 // The slab columns [ro, m_pad) once Rg exists: PHt[:, slab] = P[:, pose] Rg^T, S22 = Rg * PHt[pose rows, slab], and the
 // finished factor block L21 = Rg * Wsym on the SLAM columns (k_wsym).
 void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
                             const double* zg, const int* scols, const double* svals, const double* sres,
-                            const double* corr_total, double var, const int* omega, double* T, const double* Bc) {
+                            const double* corr_total, double var, const int* omega, double* T, const double* Bc, double* Gp) {
   double* PHt = T + (size_t)d.m_pad * d.ld;
   if (d.nslam > 0) gemm_nn(s, d.ms, d.ns2, d.ms, 1.0, Rg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
   gemm_nt(s, d.N, d.ms, d.ms, 1.0, P + XB_CORE, d.N, Rg, ldr, 0.0, PHt + d.ro, d.ld);
@@ -150,7 +162,14 @@ void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P
   launch_sym_lower(s, T, d.ld, d.ro, d.ro + d.ms, d.ro);
   k_s_finish<<<(d.m_pad - d.ro + 127) / 128, 128, 0, s>>>(d, d.ro, d.m_pad - d.ro, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
   count_launch();
-  launch_omega_rows(s, d, d.ro, d.ms, P, Lg, ldr, scols, svals, omega, T);
+  // Omega tile on the slab columns: A2[Omega_k, a] = sum_b P[15+b, Omega_k] Rg[a][b] = (Gp Rg^T)[k][a] with the gathered
+  // Gp[k][b] = P[15+b, Omega_k] (k_omega_gather, which also writes the V rows Rg[:, Omega_k]^T); a 21 x 6M x 6M tensor-core GEMM
+  {
+    dim3 g((d.ms + 127) / 128, NOM);
+    k_omega_gather<<<g, 128, 0, s>>>(d, P, Lg, ldr, omega, Gp, T);
+    count_launch();
+    gemm_nt(s, NOM, d.ms, d.ms, 1.0, Gp, d.ms, Rg, ldr, 0.0, T + (size_t)(d.m_pad + d.n_pad + 32) * d.ld + d.ro, d.ld);
+  }
   if (d.nslam > 0) {
     // Schur complement of the factored SLAM columns on every row from the slab rows down (S22, P H^T, r_eff, Omega, V):
     //   T[ro:, ro:] -= T[ro:, 0:s_pad] * L21^T     -- after it the slab columns are a plain tall factorisation of their own
@@ -253,7 +272,9 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
   }
   __syncthreads();
   // Gauss-Jordan with partial pivoting by ONE warp (the 21 pivots are a serial chain: warp-level synchronisation instead of
-  // 126 block-wide barriers); the other warps wait at the barrier below
+  // 126 block-wide barriers); the other warps wait at the barrier below.  A fully unrolled register-resident variant
+  // (row per lane, pivot row by shuffle) was measured 30 us SLOWER: ~3500 straight-line instructions executed once are
+  // instruction-fetch bound, like the unrolled per-track Cholesky.
   if (t < 32) {
     const int lane = t;
     for (int c = 0; c < NOM; ++c) {

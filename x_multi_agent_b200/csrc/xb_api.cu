@@ -131,7 +131,8 @@ struct xb_filter {
   bool xw_final = false;       // no estimate changed since ev_corr was recorded
   bool overlap = true;         // XB_NO_OVERLAP=1 runs everything on the one stream
   int chol_share = 4;          // concurrent dataflow launches each take 1/chol_share of the co-resident CTA slots
-  double* d_Bc = nullptr;      // copy of (P Hs^T)[pose rows] (6M x s_pad)
+  double* d_Bc = nullptr;      // Wsym = (W1s + W2s)/2 on the pose rows (6M x s_pad)
+  double* d_Gp = nullptr;      // gathered P[pose rows, Omega]^T (32 x 6M)
   int* d_flags_g = nullptr;    // dataflow flags of the Gram factorisation (may run while the tall buffer is being factored)
   double* d_FQ2 = nullptr;     // F_d / Q_d of the re-propagation steps
   // ring buffer (state_buffer.cpp)
@@ -433,6 +434,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_flags_g, (size_t)(f->grows_pad / 32 + 2) * (f->gcols_pad / 32) + 128, int);
   DA(f->d_Bc, (size_t)6 * M * std::max(32, pad32(2 * F)), double);
   DA(f->d_FQ2, (size_t)128 * 450, double);
+  DA(f->d_Gp, (size_t)32 * 6 * M, double);
   DA(f->d_omega, 32, int);
   DA(f->d_omega_inv, n_pad, int);
   DA(f->d_tileflag, n_pad / 32 + 4, int);
@@ -1268,7 +1270,7 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
     }
     chol_from = d.s_pad;
     launch_build_slab_part(f->stream, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var,
-                           f->d_omega, f->d_T, f->d_Bc);
+                           f->d_omega, f->d_T, f->d_Bc, f->d_Gp);
   }
   f->slam_part_done = false;
   f->corr_zero = false;

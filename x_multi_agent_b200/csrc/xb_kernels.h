@@ -127,7 +127,7 @@ void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P
 void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc);
 void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
                             const double* zg, const int* scols, const double* svals, const double* sres,
-                            const double* corr_total, double var, const int* omega, double* T, const double* Bc);
+                            const double* corr_total, double var, const int* omega, double* T, const double* Bc, double* Gp);
 // dense-H variant (Updater::applyUpdate with a caller-supplied H)
 void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, const double* P, const double* H,
                           const double* res, const double* rdiag, const double* corr_total, const int* omega, double* T);
