@@ -364,6 +364,9 @@ void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
 //   Tiles are handed over through global memory + release/acquire flags; all tile reads bypass L1 (ld.cg).
 // ------------------------------------------------------------------------------------------------
 #define TC 32
+__device__ __forceinline__ void dmma884_t(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -393,6 +396,9 @@ __device__ __forceinline__ void flag_spin(const int* flag, int* err) {
 
 // 32x32 lower Cholesky by one warp: lane r keeps row r in registers, finished rows of L are mirrored in
 // shared memory (Ls) and read back as broadcasts (left-looking).  Cs: in = tile, out = L (upper part zero).
+// Measured alternative (rejected): right-looking in registers with the multipliers exchanged by shuffle and the bulk
+// update software-pipelined around the pivot chain -- 1100 64-bit shuffles per tile make it 2x SLOWER (tile column
+// 12 -> 24 us) than the 500 broadcast shared-memory loads of this version.
 __device__ __forceinline__ void warp_potrf32(double (*Cs)[TC + 1], double (*Ls)[TC + 1], const double* dorig,
                                              double piv_tol, int lane) {
   double a[TC];
@@ -438,32 +444,43 @@ __device__ __forceinline__ void warp_trsm32(double (*Cs)[TC + 1], double (*Ls)[T
 #pragma unroll
   for (int k = 0; k < TC; ++k) Cs[lane][k] = a[k];
 }
-// C(32x32, smem) -= A(32x32) * B(32x32)^T with A, B stored k-major (At[k][r], Bt[k][c]); nthreads >= 64
+// C(32x32, smem) -= A(32x32) * B(32x32)^T with A, B stored k-major (At[k][r], Bt[k][c]), on the fp64 tensor cores:
+// the calling group of nthreads = 64 or 128 threads (t = index within the group) splits C into 16x16 quadrants, one or two
+// per warp, 2x2 m8n8k4 accumulators each: 32 DMMAs per quadrant (~0.3 us) instead of 512 DFMAs + 256 shared loads per
+// thread (~1.3 us) -- this product sits between two pivots of the critical-path CTA and inside every worker task.
 __device__ __forceinline__ void tile_gemm_sub(double (*Cs)[TC + 1], double (*At)[TC + 1], double (*Bt)[TC + 1], int t,
                                               int nthreads) {
-  for (int e = t; e < 64; e += nthreads) {  // 64 micro-tiles of 4x4
-    const int ty = e >> 3, tx = e & 7;
-    double acc[4][4];
+  const int lane = t & 31, w = t >> 5, nw = nthreads >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  for (int q = w; q < 4; q += nw) {
+    const int r0 = (q >> 1) * 16, c0 = (q & 1) * 16;
+    double acc[2][2][2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int v = 0; v < 4; ++v) acc[u][v] = Cs[ty * 4 + u][tx * 4 + v];
-#pragma unroll 8
-    for (int kk = 0; kk < TC; ++kk) {
-      double a[4], b[4];
+      for (int j = 0; j < 2; ++j) {
+        acc[i][j][0] = Cs[r0 + 8 * i + g][c0 + 8 * j + 2 * tg];
+        acc[i][j][1] = Cs[r0 + 8 * i + g][c0 + 8 * j + 2 * tg + 1];
+      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = At[kk][ty * 4 + u];
+    for (int kk = 0; kk < TC; kk += 4) {
+      double a[2], b[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) b[u] = Bt[kk][tx * 4 + u];
+      for (int i = 0; i < 2; ++i) a[i] = -At[kk + tg][r0 + 8 * i + g];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int j = 0; j < 2; ++j) b[j] = Bt[kk + tg][c0 + 8 * j + g];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(-a[u], b[v], acc[u][v]);
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884_t(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int v = 0; v < 4; ++v) Cs[ty * 4 + u][tx * 4 + v] = acc[u][v];
+      for (int j = 0; j < 2; ++j) {
+        Cs[r0 + 8 * i + g][c0 + 8 * j + 2 * tg] = acc[i][j][0];
+        Cs[r0 + 8 * i + g][c0 + 8 * j + 2 * tg + 1] = acc[i][j][1];
+      }
   }
 }
 __device__ __forceinline__ void tile_load(double (*S)[TC + 1], const double* g, int ld, int t, int nthreads, bool transpose) {

@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libxb200.so"
+LIB_PATH = Path(os.environ["XB200_LIB"]) if os.environ.get("XB200_LIB") else _HERE / "libxb200.so"  # override: A/B builds
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
