@@ -958,8 +958,17 @@ __global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const d
   T[(size_t)r * ld + c] = v;
 }
 
-void launch_gram(cudaStream_t s, const GramParams& gp) {
+void launch_gram(cudaStream_t s, const GramParams& gp, cudaStream_t s_jtj, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   const int W = 6 * gp.M + 1;
+  // the block-diagonal J^T J terms (one CTA per pose) are independent of the B^T B partials: optional second stream
+  const bool fork = s_jtj != nullptr && s_jtj != s;
+  if (fork) {
+    cudaEventRecord(ev_fork, s);
+    cudaStreamWaitEvent(s_jtj, ev_fork, 0);
+    k_gram_jtj<<<gp.M, 128, 0, s_jtj>>>(gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
+    count_launch();
+    cudaEventRecord(ev_join, s_jtj);
+  }
   const int tiles = (W + 63) / 64;
   int nzB = 0, nzD = 0;
   if (gp.rowsB > 0) {
@@ -984,8 +993,12 @@ void launch_gram(cudaStream_t s, const GramParams& gp) {
       count_launch();
     }
   }
-  k_gram_jtj<<<gp.M, 128, 0, s>>>(gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
-  count_launch();
+  if (fork) {
+    cudaStreamWaitEvent(s, ev_join, 0);
+  } else {
+    k_gram_jtj<<<gp.M, 128, 0, s>>>(gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
+    count_launch();
+  }
   dim3 b(16, 16), g((gp.cols_pad + 15) / 16, (gp.rows_pad + 15) / 16);
   k_gram_reduce<<<g, b, 0, s>>>(gp.partB, nzB, gp.partD, nzD, gp.blocks, gp.M, gp.n_poses, gp.T, gp.ld, gp.rows_pad,
                                 gp.cols_pad, gp.diag0);

@@ -152,31 +152,45 @@ __global__ void k_omega_gather(UpdateDims d, const double* __restrict__ P, const
 
 // The slab columns [ro, m_pad) once Rg exists: PHt[:, slab] = P[:, pose] Rg^T, S22 = Rg * PHt[pose rows, slab], and the
 // finished factor block L21 = Rg * Wsym on the SLAM columns (k_wsym).
-void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
-                            const double* zg, const int* scols, const double* svals, const double* sres,
-                            const double* corr_total, double var, const int* omega, double* T, const double* Bc, double* Gp) {
-  double* PHt = T + (size_t)d.m_pad * d.ld;
+// The four pieces are independent up to the Schur complement, which needs all of them: xb_api.cu runs L21 and the Omega
+// tile on side streams next to the P H_R^T -> S22 chain.
+void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, int ldr, double* T, const double* Bc) {
   if (d.nslam > 0) gemm_nn(s, d.ms, d.ns2, d.ms, 1.0, Rg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
+}
+void launch_slab_omega(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
+                       const int* omega, double* T, double* Gp) {
+  // Omega tile on the slab columns: A2[Omega_k, a] = sum_b P[15+b, Omega_k] Rg[a][b] = (Gp Rg^T)[k][a] with the gathered
+  // Gp[k][b] = P[15+b, Omega_k] (k_omega_gather, which also writes the V rows Rg[:, Omega_k]^T); a 21 x 6M x 6M tensor-core GEMM
+  dim3 g((d.ms + 127) / 128, NOM);
+  k_omega_gather<<<g, 128, 0, s>>>(d, P, Lg, ldr, omega, Gp, T);
+  count_launch();
+  gemm_nt(s, NOM, d.ms, d.ms, 1.0, Gp, d.ms, Rg, ldr, 0.0, T + (size_t)(d.m_pad + d.n_pad + 32) * d.ld + d.ro, d.ld);
+}
+void launch_slab_s22(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
+                     const double* zg, const int* scols, const double* svals, const double* sres, const double* corr_total,
+                     double var, double* T) {
+  double* PHt = T + (size_t)d.m_pad * d.ld;
   gemm_nt(s, d.N, d.ms, d.ms, 1.0, P + XB_CORE, d.N, Rg, ldr, 0.0, PHt + d.ro, d.ld);
   gemm_nn(s, d.ms, d.ms, d.ms, 1.0, Rg, ldr, PHt + (size_t)XB_CORE * d.ld + d.ro, d.ld, 0.0, T + (size_t)d.ro * d.ld + d.ro, d.ld);
   launch_sym_lower(s, T, d.ld, d.ro, d.ro + d.ms, d.ro);
   k_s_finish<<<(d.m_pad - d.ro + 127) / 128, 128, 0, s>>>(d, d.ro, d.m_pad - d.ro, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
   count_launch();
-  // Omega tile on the slab columns: A2[Omega_k, a] = sum_b P[15+b, Omega_k] Rg[a][b] = (Gp Rg^T)[k][a] with the gathered
-  // Gp[k][b] = P[15+b, Omega_k] (k_omega_gather, which also writes the V rows Rg[:, Omega_k]^T); a 21 x 6M x 6M tensor-core GEMM
-  {
-    dim3 g((d.ms + 127) / 128, NOM);
-    k_omega_gather<<<g, 128, 0, s>>>(d, P, Lg, ldr, omega, Gp, T);
-    count_launch();
-    gemm_nt(s, NOM, d.ms, d.ms, 1.0, Gp, d.ms, Rg, ldr, 0.0, T + (size_t)(d.m_pad + d.n_pad + 32) * d.ld + d.ro, d.ld);
-  }
-  if (d.nslam > 0) {
-    // Schur complement of the factored SLAM columns on every row from the slab rows down (S22, P H^T, r_eff, Omega, V):
-    //   T[ro:, ro:] -= T[ro:, 0:s_pad] * L21^T     -- after it the slab columns are a plain tall factorisation of their own
-    const int rows = d.m_pad - d.ro + d.n_pad + 96;
-    gemm_nt(s, rows, d.m_pad - d.ro, d.s_pad, -1.0, T + (size_t)d.ro * d.ld, d.ld, T + (size_t)d.ro * d.ld, d.ld, 1.0,
-            T + (size_t)d.ro * d.ld + d.ro, d.ld);
-  }
+}
+void launch_slab_schur(cudaStream_t s, const UpdateDims& d, double* T) {
+  if (d.nslam <= 0) return;
+  // Schur complement of the factored SLAM columns on every row from the slab rows down (S22, P H^T, r_eff, Omega, V):
+  //   T[ro:, ro:] -= T[ro:, 0:s_pad] * L21^T     -- after it the slab columns are a plain tall factorisation of their own
+  const int rows = d.m_pad - d.ro + d.n_pad + 96;
+  gemm_nt(s, rows, d.m_pad - d.ro, d.s_pad, -1.0, T + (size_t)d.ro * d.ld, d.ld, T + (size_t)d.ro * d.ld, d.ld, 1.0,
+          T + (size_t)d.ro * d.ld + d.ro, d.ld);
+}
+void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
+                            const double* zg, const int* scols, const double* svals, const double* sres,
+                            const double* corr_total, double var, const int* omega, double* T, const double* Bc, double* Gp) {
+  launch_slab_l21(s, d, Rg, ldr, T, Bc);
+  launch_slab_s22(s, d, P, Rg, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
+  launch_slab_omega(s, d, P, Rg, Lg, ldr, omega, T, Gp);
+  launch_slab_schur(s, d, T);
 }
 
 // dense-H path: S += diag(rdiag) (+ identity padding), r_eff = res + H corr
@@ -295,15 +309,22 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
       __syncwarp();
       for (int x = lane; x < 2 * NOM; x += 32) A[c][x] /= d;
       __syncwarp();
-      // elimination: lane <-> column(s) cc = lane, lane + 32; the multipliers A[r][c] are broadcasts
+      // elimination: lane <-> column(s) cc = lane, lane + 32; the multipliers A[r][c] are broadcasts.  All loads first,
+      // then the FMAs, then the stores (the compiler cannot move a load of A above a store to A on its own)
       const int c1 = lane + 32;
-      const double p0 = A[c][lane], p1 = c1 < 2 * NOM ? A[c][c1] : 0.0;
+      const bool has1 = c1 < 2 * NOM;
+      const double p0 = A[c][lane], p1 = has1 ? A[c][c1] : 0.0;
+      double fr[NOM], v0[NOM], v1[NOM];
+#pragma unroll
+      for (int r = 0; r < NOM; ++r) { fr[r] = A[r][c]; v0[r] = A[r][lane]; v1[r] = has1 ? A[r][c1] : 0.0; }
+#pragma unroll
+      for (int r = 0; r < NOM; ++r) { v0[r] = fma(-fr[r], p0, v0[r]); v1[r] = fma(-fr[r], p1, v1[r]); }
+      __syncwarp();
 #pragma unroll
       for (int r = 0; r < NOM; ++r) {
         if (r == c) continue;
-        const double fr = A[r][c];
-        if (lane != c) A[r][lane] = fma(-fr, p0, A[r][lane]);
-        if (c1 < 2 * NOM) A[r][c1] = fma(-fr, p1, A[r][c1]);
+        if (lane != c) A[r][lane] = v0[r];
+        if (has1) A[r][c1] = v1[r];
       }
       __syncwarp();
       if (lane < NOM && lane != c) A[lane][c] = 0.0;

@@ -118,7 +118,8 @@ struct xb_filter {
   // internal side streams: (a) the SLAM-column part of the Kalman update (rows, P H^T, S block, the first tile columns of
   // the Cholesky factorisation) runs next to the MSCKF track pipeline; (b) the means of the re-propagation run next to the
   // covariance downdate.  Joined back into `stream` with events; nothing outside the library sees them.
-  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;
+  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_b2 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_side = nullptr, ev_corr = nullptr, ev_means = nullptr;
   bool side_pending = false;   // a construct call has forked the SLAM part; apply_constructed joins it
   bool slam_part_done = false; // the tall buffer already holds the SLAM-column part for the pending update
@@ -257,6 +258,7 @@ extern "C" int xb_profile_read(xb_filter* f, const char** names, double* ms, lon
   cudaStreamSynchronize(f->stream);
   cudaStreamSynchronize(f->side);
   cudaStreamSynchronize(f->side2);
+  cudaStreamSynchronize(f->side3);
   for (auto& sp : f->spans) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) { f->stage_ms[sp.stage] += t; f->stage_n[sp.stage] += 1; }
@@ -355,9 +357,11 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   }
   f->own_stream = true;
   if (cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&f->side2, cudaStreamNonBlocking) != cudaSuccess)
+      cudaStreamCreateWithFlags(&f->side2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&f->side3, cudaStreamNonBlocking) != cudaSuccess)
     return fail(XB_E_CUDA, "cudaStreamCreate failed");
-  for (cudaEvent_t* e : {&f->ev_fork, &f->ev_side, &f->ev_corr, &f->ev_means, &f->ev_dd})
+  for (cudaEvent_t* e : {&f->ev_fork, &f->ev_side, &f->ev_corr, &f->ev_means, &f->ev_dd, &f->ev_b0, &f->ev_b1, &f->ev_b2,
+                         &f->ev_g0, &f->ev_g1})
     CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   if (const char* e = getenv("XB_NO_OVERLAP")) f->overlap = atoi(e) == 0;
   if (const char* e = getenv("XB_CHOL_SHARE")) f->chol_share = std::max(1, atoi(e));
@@ -472,11 +476,16 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   if (getenv("XB_TRACK_PROF")) DA(f->d_track_prof, 12 * (size_t)maxT, long long);
   if (getenv("XB_CHOL_TRACE")) DA(f->d_trace, 6 * ((size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64), long long);
 
-  DA(f->d_rowmap, N, int);
-  DA(f->d_ccols, 15 * (size_t)(6 + 3 * std::max(1, F)), int);
+  {  // the manage tables travel as ONE host-to-device copy: [rowmap N | ccols 15 (6 + 3F) | featsrc F | reanch F]
+    const size_t nc = 15 * (size_t)(6 + 3 * std::max(1, F));
+    int* tab;
+    DA(tab, (size_t)N + nc + 2 * (size_t)std::max(1, F), int);
+    f->d_rowmap = tab;
+    f->d_ccols = tab + N;
+    f->d_featsrc = f->d_ccols + nc;
+    f->d_reanch = f->d_featsrc + std::max(1, F);
+  }
   DA(f->d_cvals, 15 * (size_t)(6 + 3 * std::max(1, F)), double);
-  DA(f->d_featsrc, std::max(1, F), int);
-  DA(f->d_reanch, std::max(1, F), int);
   DA(f->d_mscratch, 7 * (size_t)M + 3 * (size_t)F + 8, double);
   DA(f->d_Tm, (size_t)(6 + 3 * std::max(1, F)) * N, double);
   DA(f->d_T2, (size_t)(6 + 3 * std::max(1, F)) * 15, double);
@@ -493,7 +502,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
                  sizeof(int) * (size_t)(2 * maxT + 2 * maxT1 + 4 * std::max(1, F) + 64);
   f->pin_bytes = (f->pin_bytes + 255) / 256 * 256;
   if (cudaMallocHost((void**)&f->h_pin, f->pin_bytes * xb_filter::kPinRing) != cudaSuccess) return fail(XB_E_CUDA, "cudaMallocHost failed");
-  f->ipin_ints = ((size_t)(N + 16 * (6 + 3 * std::max(1, F)) + 3 * std::max(1, F) + 64) + 63) / 64 * 64;
+  f->ipin_ints = ((size_t)(N + 15 * (6 + 3 * std::max(1, F)) + 2 * std::max(1, F) + 64) + 63) / 64 * 64;
   if (cudaMallocHost((void**)&f->h_ipin, sizeof(int) * f->ipin_ints * xb_filter::kPinRing) != cudaSuccess)
     return fail(XB_E_CUDA, "cudaMallocHost failed");
   for (int i = 0; i < xb_filter::kPinRing; ++i) {
@@ -511,7 +520,8 @@ extern "C" int xb_destroy(xb_filter* f) {
   cudaStreamSynchronize(f->stream);
   if (f->side) { cudaStreamSynchronize(f->side); cudaStreamDestroy(f->side); }
   if (f->side2) { cudaStreamSynchronize(f->side2); cudaStreamDestroy(f->side2); }
-  for (cudaEvent_t e : {f->ev_fork, f->ev_side, f->ev_corr, f->ev_means, f->ev_dd})
+  if (f->side3) { cudaStreamSynchronize(f->side3); cudaStreamDestroy(f->side3); }
+  for (cudaEvent_t e : {f->ev_fork, f->ev_side, f->ev_corr, f->ev_means, f->ev_dd, f->ev_b0, f->ev_b1, f->ev_b2, f->ev_g0, f->ev_g1})
     if (e) cudaEventDestroy(e);
   for (void* p : f->allocs) cudaFree(p);
   if (f->h_pin) cudaFreeHost(f->h_pin);
@@ -914,15 +924,13 @@ extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
       rowmap[F0 + 3 * k + r] = -2 - (6 + 3 * (int)i + r);
     }
   }
-  int* fs = ccols + 15 * n_comp;
-  int* ra = fs + F;
+  const size_t nc_cap = 15 * (size_t)(6 + 3 * std::max(1, F));
+  int* fs = ccols + nc_cap;   // fixed layout: mirrors the device table
+  int* ra = fs + std::max(1, F);
   for (int k = 0; k < F; ++k) fs[k] = src[k];
   for (size_t i = 0; i < reanch.size(); ++i) ra[i] = reanch[i];
-  CK(cudaMemcpyAsync(f->d_rowmap, rowmap, sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
-  CK(cudaMemcpyAsync(f->d_ccols, ccols, sizeof(int) * 15 * n_comp, cudaMemcpyHostToDevice, f->stream));
-  if (F > 0) CK(cudaMemcpyAsync(f->d_featsrc, fs, sizeof(int) * F, cudaMemcpyHostToDevice, f->stream));
-  if (!reanch.empty())
-    CK(cudaMemcpyAsync(f->d_reanch, ra, sizeof(int) * reanch.size(), cudaMemcpyHostToDevice, f->stream));
+  CK(cudaMemcpyAsync(f->d_rowmap, rowmap, sizeof(int) * ((size_t)N + nc_cap + 2 * (size_t)std::max(1, F)), cudaMemcpyHostToDevice,
+                     f->stream));
   CK(cudaEventRecord(f->ipin_ev[f->ipin_cur], f->stream));
   // destination: the scratch buffer that is not the source
   double* src_P = f->d_Pw;
@@ -1161,7 +1169,7 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     gp.off = l0.d_off; gp.inlier = f->d_inl0; gp.n_tracks_msckf = n0; gp.Jout = f->d_J0;
     gp.blocks = f->d_blocks;
     gp.T = f->d_Tg; gp.ld = f->gcols_pad; gp.rows_pad = f->grows_pad; gp.cols_pad = f->gcols_pad; gp.diag0 = f->d_diag0;
-    { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp); }
+    { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp, f->overlap ? f->side3 : nullptr, f->ev_g0, f->ev_g1); }
     StageTimer st_(f, ST_CHOLG);
     tallchol_range(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, 0, f->gcols_pad, 0, f->d_flags_g, f->d_err, 1e-14,
                    f->d_diag0, nullptr, f->side_pending ? f->chol_share : 1);
@@ -1269,8 +1277,23 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
       if (d.nslam > 0) slam_phase(f, f->stream, d, ST_SIDE_SLAM, ST_SIDE_CHOL, 1, false);
     }
     chol_from = d.s_pad;
-    launch_build_slab_part(f->stream, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var,
-                           f->d_omega, f->d_T, f->d_Bc, f->d_Gp);
+    if (f->overlap) {
+      // L21 and the Omega tile are independent of the P H_R^T -> S22 chain: side streams (idle by now), joined before Schur
+      CK(cudaEventRecord(f->ev_b0, f->stream));
+      CK(cudaStreamWaitEvent(f->side, f->ev_b0, 0));
+      CK(cudaStreamWaitEvent(f->side3, f->ev_b0, 0));
+      launch_slab_l21(f->side, d, f->d_Rg, f->gcols_pad, f->d_T, f->d_Bc);
+      CK(cudaEventRecord(f->ev_b1, f->side));
+      launch_slab_omega(f->side3, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, f->d_omega, f->d_T, f->d_Gp);
+      CK(cudaEventRecord(f->ev_b2, f->side3));
+      launch_slab_s22(f->stream, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var, f->d_T);
+      CK(cudaStreamWaitEvent(f->stream, f->ev_b1, 0));
+      CK(cudaStreamWaitEvent(f->stream, f->ev_b2, 0));
+      launch_slab_schur(f->stream, d, f->d_T);
+    } else {
+      launch_build_slab_part(f->stream, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var,
+                             f->d_omega, f->d_T, f->d_Bc, f->d_Gp);
+    }
   }
   f->slam_part_done = false;
   f->corr_zero = false;

@@ -105,7 +105,8 @@ struct GramParams {
   double* T; int ld, rows_pad, cols_pad;
   double* diag0;   // [cols_pad] original diagonal of G (relative pivot test of the semi-definite factorisation)
 };
-void launch_gram(cudaStream_t s, const GramParams& gp);
+void launch_gram(cudaStream_t s, const GramParams& gp, cudaStream_t s_jtj = nullptr, cudaEvent_t ev_fork = nullptr,
+                 cudaEvent_t ev_join = nullptr);
 
 // ---- update assembly / state correction / state management (k_update.cu, k_manage.cu) -----------
 struct UpdateDims {
@@ -123,6 +124,13 @@ struct UpdateDims {
 // Tall-buffer pieces on the SLAM columns (no Rg needed) and on the slab columns (k_update.cu)
 void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
                             const double* sres, const double* corr_total, double var, const int* omega, double* T);
+void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, int ldr, double* T, const double* Bc);
+void launch_slab_omega(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
+                       const int* omega, double* T, double* Gp);
+void launch_slab_s22(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
+                     const double* zg, const int* scols, const double* svals, const double* sres, const double* corr_total,
+                     double var, double* T);
+void launch_slab_schur(cudaStream_t s, const UpdateDims& d, double* T);
 // Wsym = (W1s + W2s)/2 on the pose rows -> Bc (after the SLAM columns are factored)
 void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc);
 void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
