@@ -594,3 +594,69 @@ def test_tensor_core_downdate_is_fp32_accurate(cfg, frames):
     rp.done()
     for dev in devs:
         dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,frames", [
+    (SynthConfig(M=6, F=6, K=12, seed=2, n_short=2, churn=1), 24),
+    (SynthConfig(M=30, F=40, K=60, seed=0, slam_init_frame=30), 40),
+])
+def test_side_stream_schedule_equals_single_stream(cfg, frames, monkeypatch):
+    """The overlapped schedule (SLAM-column half of the update, K-split downdate, build pieces and re-propagation means on
+    library-internal side streams) is a re-ordering of independent work: it must give the same states
+    and covariance as everything in order on the caller's stream (XB_NO_OVERLAP=1, read at xb_create), update after
+    update, also when updates are issued back to back without host synchronisation in between (races would show here)."""
+    ev = record(Scenario(cfg), frames)
+    results = []
+    for no_overlap in ("0", "1"):
+        monkeypatch.setenv("XB_NO_OVERLAP", no_overlap)
+        dev = make_filter(cfg)
+        states = []
+        replay(ev, dev, lambda k, m, st: states.append(st))
+        P = dev.get_covariance()
+        results.append((states, P, dev.get_state()))
+        dev.synchronize()
+        dev.close()
+    monkeypatch.delenv("XB_NO_OVERLAP")
+    (s_a, P_a, n_a), (s_b, P_b, n_b) = results
+    rp = Report()
+    assert len(s_a) == len(s_b) and len(s_a) > 0
+    worst = max(np.abs(a.x - b.x).max() for a, b in zip(s_a, s_b))
+    rp.check("states, all updates (abs)", worst, 1e-11)
+    rp.check("newest state", np.abs(n_a.x - n_b.x).max(), 1e-11)
+    rp.check("newest covariance", rel(P_a, P_b), 1e-11)
+    rp.done()
+
+
+@pytest.mark.gpu
+def test_constructed_update_survives_calls_between_construct_and_apply():
+    """The C ABI allows xb_updater_reset_correction / xb_sm_manage-style calls between constructUpdate and applyUpdate (the
+    reference's Updater::update does its own sequencing, updater.cpp:39-115).  The early side-stream part of a constructed
+    update must then be discarded and rebuilt (invalidate_early): same result as the plain sequence."""
+    cfg = SynthConfig(M=6, F=6, K=12, seed=1, churn=1)
+    ora, m, s = _stage_setup(cfg, 13)
+    out = []
+    for variant in range(2):
+        dev = make_filter(cfg)
+        dev.work_set(State.from_oracle(s))
+        sm = ora.upd.sm
+        dev.sm_set(sm.n_poses, sm.n_features, sm.anchor_idxs, sm.filled_before)
+        dev.set_measurement(m)
+        dev.manage(m.lost_slam_trk_idxs)
+        dev.reset_correction()
+        dev.construct_update(0)
+        dev.apply_constructed(False)          # IEKF-style first pass: correction_total becomes non-zero, covariance untouched
+        dev.construct_update(0)               # second pass: the early part is built with that correction_total ...
+        if variant == 1:
+            dev.reset_correction()            # ... which the caller now resets before applying
+        else:
+            dev.reset_correction()
+            dev.construct_update(0)           # reference sequence: reset first, then construct
+        dev.apply_constructed(True)
+        out.append(dev.work_get())
+        dev.synchronize()
+        dev.close()
+    rp = Report()
+    rp.check("state", np.abs(out[0].x - out[1].x).max(), 1e-12)
+    rp.check("covariance", rel(out[0].cov, out[1].cov), 1e-12)
+    rp.done()
