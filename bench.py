@@ -253,7 +253,7 @@ def main():
     assert flt.n_poses == CFG2["M"] and flt.n_features == CFG2["F"], "warm-up did not reach steady state"
     W, K = max(args.warmup, 3), args.steps
     events = steady_events(scn, N_FILL, 2 * (W + K))
-    packed = [PackedMeasurement(m) for _, m in events]
+    packed = [PackedMeasurement(m, pinned=True) for _, m in events]   # inputs in pinned host memory (bench contract)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def feed(i):

@@ -27,6 +27,7 @@
 #ifndef XB200_H_
 #define XB200_H_
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -145,8 +146,14 @@ XB_API int xb_ekf_initialize_from_state(xb_filter* f, const double* xvec, const 
 XB_API int xb_ekf_process_imu(xb_filter* f, double timestamp, unsigned seq, const double w_m[3],
                        const double a_m[3], double* xvec_out);
 /* VioUpdater::setMeasurement (vio_updater.cpp:122-124) at the preProcess seam: copies the track lists
- * to the device (the only host->device traffic of an update). */
+ * to the device (the only host->device traffic of an update).  Observation arrays that live in page-locked host
+ * memory (xb_host_alloc, or the caller's own cudaHostRegister) are copied asynchronously straight from the caller's
+ * buffer -- they must then stay unchanged until the update that uses them has completed (xb_synchronize or a returned
+ * state); pageable buffers are staged through the library's pinned ring and may be reused at once. */
 XB_API int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m);
+/* cudaMallocHost / cudaFreeHost for measurement buffers (no reference counterpart: VioMeasurement is host memory). */
+XB_API void* xb_host_alloc(size_t bytes);
+XB_API void xb_host_free(void* p);
 /* Ekf::processUpdateMeasurement (ekf.cpp:179-213): closest state, Updater::update, re-propagation.
  * 1 = updated state written to xvec_out (may be NULL: no device->host copy), 0 = nullopt. */
 XB_API int xb_ekf_process_update(xb_filter* f, double* xvec_out);

@@ -660,3 +660,32 @@ def test_constructed_update_survives_calls_between_construct_and_apply():
     rp.check("state", np.abs(out[0].x - out[1].x).max(), 1e-12)
     rp.check("covariance", rel(out[0].cov, out[1].cov), 1e-12)
     rp.done()
+
+
+@pytest.mark.gpu
+def test_pinned_measurement_buffers_take_the_direct_copy_path():
+    """xb_vio_set_measurement copies observation arrays in page-locked memory (xb_host_alloc) without staging; results
+    are identical to the staged path."""
+    from x_multi_agent_b200 import PackedMeasurement
+    cfg = SynthConfig(M=10, F=8, K=200, seed=4)
+    ev = record(Scenario(cfg), 14)
+    out = []
+    for pinned in (False, True):
+        dev = make_filter(cfg)
+        keep = []
+        for e in ev:
+            if e[0] == "init":
+                dev.initialize_from_state(e[1])
+            elif e[0] == "imu":
+                dev.process_imu(*e[1:], want_state=False)
+            else:
+                pm = PackedMeasurement(e[1], pinned=pinned)
+                keep.append(pm)           # pinned buffers must outlive the update that reads them
+                dev.set_measurement(pm)
+                dev.process_update_measurement(want_state=False)
+        st = dev.get_state()
+        st.cov = dev.get_covariance()
+        out.append(st)
+        dev.synchronize()
+        dev.close()
+    assert np.array_equal(out[0].x, out[1].x) and np.array_equal(out[0].cov, out[1].cov)

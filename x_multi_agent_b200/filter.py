@@ -101,16 +101,28 @@ def _csr(tracks):
 
 
 class PackedMeasurement:
-    """A Measurement marshalled once into the CSR buffers the C ABI takes (keeps them alive)."""
+    """A Measurement marshalled once into the CSR buffers the C ABI takes (keeps them alive).  pinned=True places the
+    observation arrays in page-locked host memory (xb_host_alloc): xb_vio_set_measurement then copies them to the device
+    straight from these buffers, without the staging pass."""
 
-    def __init__(self, m: Measurement):
+    def __init__(self, m: Measurement, pinned=False):
         self.keep = []
+        self._pinned = []
         self.c = L.XbMeasurement()
         self.c.timestamp = m.timestamp
         self.h2d_bytes = 0
+        lib = L.load() if pinned else None
         for name, trks in (("slam", m.slam_trks), ("msckf", m.msckf_trks), ("msckf_short", m.msckf_short_trks),
                            ("new_slam_std", m.new_slam_std_trks), ("new_msckf_slam", m.new_msckf_slam_trks)):
             off, obs = _csr(trks)
+            if pinned and obs.size:
+                ptr = lib.xb_host_alloc(obs.nbytes)
+                if not ptr:
+                    raise MemoryError("xb_host_alloc failed")
+                self._pinned.append((lib, ptr))
+                buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(obs.size,)).reshape(obs.shape)
+                buf[...] = obs
+                obs = buf
             self.keep += [off, obs]
             tl = L.XbTrackList(len(trks), L.iptr(off), L.dptr(obs))
             setattr(self.c, name, tl)
@@ -120,6 +132,14 @@ class PackedMeasurement:
         self.keep.append(lost)
         self.c.n_lost = len(lost)
         self.c.lost_slam_idxs = L.iptr(lost)
+
+    def __del__(self):
+        for lib, ptr in getattr(self, "_pinned", []):
+            try:
+                lib.xb_host_free(ptr)
+            except Exception:
+                pass
+        self._pinned = []
 
 
 class Filter:

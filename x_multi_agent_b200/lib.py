@@ -69,6 +69,8 @@ SIGNATURES = {
     "xb_ekf_initialize_from_state": (C.c_int, [_VP, c_double_p, c_double_p, C.c_int]),
     "xb_ekf_process_imu": (C.c_int, [_VP, C.c_double, C.c_uint, c_double_p, c_double_p, c_double_p]),
     "xb_vio_set_measurement": (C.c_int, [_VP, C.POINTER(XbMeasurement)]),
+    "xb_host_alloc": (_VP, [C.c_size_t]),
+    "xb_host_free": (None, [_VP]),
     "xb_ekf_process_update": (C.c_int, [_VP, c_double_p]),
     "xb_ekf_process_others": (C.c_int, [_VP, C.c_double, C.POINTER(XbPeerState), C.c_int, C.POINTER(XbSlamMatch),
                                         C.c_int, c_double_p]),
