@@ -225,11 +225,16 @@ __global__ void k_omega_rows(UpdateDims d, int c0, int nc, const double* __restr
     for (int b = 0; b < d.ms; ++b) a2 = fma(P[(size_t)(XB_CORE + b) * d.N + ok], Lg[(size_t)b * ldr + ar], a2);
   } else {
     const int j = a >> 1, h = a & 1;
+    int col[15];
+    double hv[15], pv[15];
+#pragma unroll
+    for (int e = 0; e < 15; ++e) { col[e] = scols[15 * j + e]; hv[e] = svals[30 * j + 15 * h + e]; }
+#pragma unroll
+    for (int e = 0; e < 15; ++e) pv[e] = P[(size_t)col[e] * d.N + ok];  // 15 independent loads in flight
+#pragma unroll
     for (int e = 0; e < 15; ++e) {
-      const int col = scols[15 * j + e];
-      const double hv = svals[30 * j + 15 * h + e];
-      if (col == ok) v += hv;
-      a2 = fma(P[(size_t)col * d.N + ok], hv, a2);
+      if (col[e] == ok) v += hv[e];
+      a2 = fma(pv[e], hv[e], a2);
     }
   }
   T[(size_t)(d.m_pad + d.n_pad + 32 + k) * d.ld + a] = a2;
