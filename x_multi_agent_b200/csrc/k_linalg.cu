@@ -5,6 +5,7 @@
 //                   P <- (P + P^T)/2 - W W^T ,  delta = W z
 // which is the same arithmetic with the explicit inverse replaced by a Cholesky factor.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "xb_kernels.h"
@@ -327,6 +328,15 @@ void gemm_tn_splitk(cudaStream_t s, int M, int N, int K, const double* A, int ld
   k_gemm_mma<false, true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   count_launch();
 }
+bool gemm_uses_tensor_cores() { return g_use_mma; }
+// C = alpha * A^T * B + beta * C with A given k-major ([K x M] row-major) -- tensor-core kernel only
+void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+             double* C, int ldc) {
+  if (M <= 0 || N <= 0) return;
+  dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM);
+  k_gemm_mma<false, true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  count_launch();
+}
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
@@ -386,9 +396,11 @@ __device__ __forceinline__ long long gtimer() {
   return t;
 }
 // one thread polls (relaxed), then a single acquire orders the tile reads that follow
-__device__ __forceinline__ void flag_spin(const int* flag, int* err) {
+// A flag is "set" when it holds the epoch of the current launch (a process-wide launch counter): no memset between
+// launches, stale values of earlier launches never match.
+__device__ __forceinline__ void flag_spin(const int* flag, int* err, int epoch) {
   long long spins = 0;
-  while (ld_relaxed(flag) == 0) {
+  while (ld_relaxed(flag) != epoch) {
     if (++spins > (1ll << 22)) { atomicExch(err, 1); break; }
   }
   (void)ld_acquire(flag);
@@ -513,14 +525,14 @@ struct CholRange {
 // TRSM tile (i, jcol): left-looking accumulation over k < jcol, then the solve against L(jcol, jcol)
 __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int ct, int i, int jcol, int* ready, int* err,
                                             double (*Ds)[TC + 1], double (*Ws)[TC + 1], double (*Ls)[TC + 1], double* rd,
-                                            long long* trace) {
+                                            long long* trace, int epoch) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const long long tr0 = trace ? gtimer() : 0;
   double* gC = T + (size_t)i * TC * ld + (size_t)jcol * TC;
   tile_load(Ds, gC, ld, t, CP_THREADS, false);
   __syncthreads();
   for (int k = 0; k < jcol; ++k) {
-    if (t == 0) { flag_spin(&ready[i * ct + k], err); flag_spin(&ready[jcol * ct + k], err); }
+    if (t == 0) { flag_spin(&ready[i * ct + k], err, epoch); flag_spin(&ready[jcol * ct + k], err, epoch); }
     __syncthreads();
     tile_load(Ws, T + (size_t)i * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
     tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
@@ -529,7 +541,7 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
     __syncthreads();
   }
   const long long tr1 = trace ? gtimer() : 0;
-  if (t == 0) flag_spin(&ready[jcol * ct + jcol], err);
+  if (t == 0) flag_spin(&ready[jcol * ct + jcol], err, epoch);
   __syncthreads();
   tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)jcol * TC, ld, t, CP_THREADS, false);
   __syncthreads();
@@ -542,7 +554,7 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
   __syncthreads();
   if (t == 0) {
     __threadfence();
-    st_release(&ready[i * ct + jcol], 1);
+    st_release(&ready[i * ct + jcol], epoch);
     if (trace && i < ct + 2 && i >= jcol + 2) {
       long long* o = trace + 6 * (size_t)(ct + jcol * 2 + (i - jcol - 2) % 2);
       o[0] = i; o[1] = jcol; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
@@ -552,7 +564,8 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
 // flags: ready[i*ct + j] (L tile published), pre[rt*ct + j] (partial sums of D_j/E_j over the earlier panels published)
 __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__ T, int ld, int rt, int ct, CholRange cr,
                                                          int* __restrict__ flags, int* __restrict__ err, double piv_tol,
-                                                         const double* __restrict__ diag0, long long* __restrict__ trace) {
+                                                         const double* __restrict__ diag0, long long* __restrict__ trace,
+                                                         int epoch) {
   __shared__ double Ds[TC][TC + 1], Es[2][TC][TC + 1], Ws[TC][TC + 1], Ls[TC][TC + 1];
   __shared__ double dorig[TC], rd[TC];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -568,7 +581,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       const bool first = j == jstart;
       const bool has_e = !(j + 1 >= cr.skip0 && j + 1 < cr.skip1);  // E = (j+1, j) exists in this launch
       if (j >= 2) {
-        if (t == 0) flag_spin(&pre[j], err);
+        if (t == 0) flag_spin(&pre[j], err, epoch);
         __syncthreads();
       }
       double* gD = T + (size_t)j * TC * ld + (size_t)j * TC;
@@ -592,7 +605,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
         rd[lane] = d != 0.0 ? 1.0 / d : 0.0;
       } else if (!first && has_e) {
         // meanwhile: E -= L(j+1, j-1) L(j, j-1)^T   (L(j+1,j-1) comes from a worker)
-        if (t == 32) flag_spin(&ready[(j + 1) * ct + (j - 1)], err);
+        if (t == 32) flag_spin(&ready[(j + 1) * ct + (j - 1)], err, epoch);
         asm volatile("bar.sync 1, 96;" ::: "memory");
         // k-major copy of L(j+1,j-1) into Ls is not possible (warp 0 uses Ls): accumulate straight from global
         const double* gW = T + (size_t)(j + 1) * TC * ld + (size_t)(j - 1) * TC;
@@ -630,7 +643,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       } else {
         tile_store(gD, ld, Ds, t - 32, 96);
         asm volatile("bar.sync 1, 96;" ::: "memory");
-        if (t == 32) { __threadfence(); st_release(&ready[j * ct + j], 1); }
+        if (t == 32) { __threadfence(); st_release(&ready[j * ct + j], epoch); }
       }
       __syncthreads();
       if (has_e) tile_store(gE, ld, Es[eb], t, CP_THREADS);
@@ -638,7 +651,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       if (t == 0) {
         if (has_e) {
           __threadfence();
-          st_release(&ready[(j + 1) * ct + j], 1);
+          st_release(&ready[(j + 1) * ct + j], epoch);
         }
         if (trace) {
           long long* o = trace + 6 * (size_t)j;
@@ -690,7 +703,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       if (has_e) tile_load(Es[0], gE, ld, t, CP_THREADS, false);
       __syncthreads();
       for (int k = 0; k <= kmax; ++k) {
-        if (t == 0) { flag_spin(&ready[jp * ct + k], err); if (has_e) flag_spin(&ready[(jp + 1) * ct + k], err); }
+        if (t == 0) { flag_spin(&ready[jp * ct + k], err, epoch); if (has_e) flag_spin(&ready[(jp + 1) * ct + k], err, epoch); }
         __syncthreads();
         tile_load(Ws, T + (size_t)jp * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);          // L(jp,k) k-major
         if (has_e) tile_load(Ls, T + (size_t)(jp + 1) * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);    // L(jp+1,k) k-major
@@ -702,9 +715,9 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       tile_store(gD, ld, Ds, t, CP_THREADS);
       if (has_e) tile_store(gE, ld, Es[0], t, CP_THREADS);
       __syncthreads();
-      if (t == 0) { __threadfence(); st_release(&pre[jp], 1); }
+      if (t == 0) { __threadfence(); st_release(&pre[jp], epoch); }
     } else {
-      worker_trsm(T, ld, ct, trsm_i, trsm_j, ready, err, Ds, Ws, Ls, rd, trace);
+      worker_trsm(T, ld, ct, trsm_i, trsm_j, ready, err, Ds, Ws, Ls, rd, trace, epoch);
     }
     __syncthreads();
     task += nworkers;
@@ -736,8 +749,10 @@ void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pa
   }
   const int max_workers = std::max(1, tallchol_max_ctas() / std::max(1, share) - 1);
   const int nworkers = ntasks < max_workers ? (ntasks > 0 ? ntasks : 1) : max_workers;
-  cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)rt * ct + ct + 1), s);
-  k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace);
+  static std::atomic<unsigned> g_epoch{0};
+  unsigned ep = ++g_epoch;
+  if ((int)ep == 0) ep = ++g_epoch;  // 0 is the value of a freshly allocated flag buffer
+  k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace, (int)ep);
   count_launch();
 }
 void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,

@@ -138,6 +138,30 @@ void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P
   launch_omega_rows(s, d, 0, d.ns2, P, nullptr, 0, scols, svals, omega, T);
 }
 
+// lower(S22) <- sym, diagonal (+var on real rows, 1 on padding) and r_eff of the slab block (k_sym_lower + k_s_finish fused)
+__global__ void k_slab_sym_finish(UpdateDims d, const double* __restrict__ Lg, int ldr, const double* __restrict__ zg,
+                                  const double* __restrict__ corr, double var, double* __restrict__ T) {
+  const int c = d.ro + blockIdx.x * blockDim.x + threadIdx.x, r = d.ro + blockIdx.y * blockDim.y + threadIdx.y;
+  if (r >= d.m_pad || c > r) return;
+  const bool real = r < d.ro + d.ms;
+  if (c < r) {
+    if (real) T[(size_t)r * d.ld + c] = 0.5 * (T[(size_t)r * d.ld + c] + T[(size_t)c * d.ld + r]);
+    return;
+  }
+  double* reff = T + (size_t)(d.m_pad + d.n_pad) * d.ld;
+  if (!real) {
+    T[(size_t)r * d.ld + r] = 1.0;
+    reff[r] = 0.0;
+    return;
+  }
+  T[(size_t)r * d.ld + r] += var;
+  const int ar = r - d.ro;
+  double rr = zg[ar];
+  if (corr)
+    for (int b = 0; b < d.ms; ++b) rr = fma(Lg[(size_t)b * ldr + ar], corr[XB_CORE + b], rr);  // Rg[a][b] = Lg[b][a]
+  reff[r] = rr;
+}
+
 // Gp[k][b] = P[15 + b, Omega_k] (32 x 6M, row-major) and the V tile on the slab columns: V^T[k][ro + a] = Rg[a][Omega_k - 15]
 __global__ void k_omega_gather(UpdateDims d, const double* __restrict__ P, const double* __restrict__ Lg, int ldr,
                                const int* __restrict__ omega, double* __restrict__ Gp, double* __restrict__ T) {
@@ -154,8 +178,12 @@ __global__ void k_omega_gather(UpdateDims d, const double* __restrict__ P, const
 // finished factor block L21 = Rg * Wsym on the SLAM columns (k_wsym).
 // The four pieces are independent up to the Schur complement, which needs all of them: xb_api.cu runs L21 and the Omega
 // tile on side streams next to the P H_R^T -> S22 chain.
-void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, int ldr, double* T, const double* Bc) {
-  if (d.nslam > 0) gemm_nn(s, d.ms, d.ns2, d.ms, 1.0, Rg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
+// Rg (the transposed Gram factor) is only materialised for the CUDA-core GEMM fallback; the tensor-core kernel takes the
+// factor Lg = Rg^T as a k-major / [K x N] operand directly (Rg == nullptr).
+void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, double* T, const double* Bc) {
+  if (d.nslam <= 0) return;
+  if (Rg) gemm_nn(s, d.ms, d.ns2, d.ms, 1.0, Rg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
+  else gemm_tn(s, d.ms, d.ns2, d.ms, 1.0, Lg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
 }
 void launch_slab_omega(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
                        const int* omega, double* T, double* Gp) {
@@ -164,17 +192,26 @@ void launch_slab_omega(cudaStream_t s, const UpdateDims& d, const double* P, con
   dim3 g((d.ms + 127) / 128, NOM);
   k_omega_gather<<<g, 128, 0, s>>>(d, P, Lg, ldr, omega, Gp, T);
   count_launch();
-  gemm_nt(s, NOM, d.ms, d.ms, 1.0, Gp, d.ms, Rg, ldr, 0.0, T + (size_t)(d.m_pad + d.n_pad + 32) * d.ld + d.ro, d.ld);
+  double* dst = T + (size_t)(d.m_pad + d.n_pad + 32) * d.ld + d.ro;
+  if (Rg) gemm_nt(s, NOM, d.ms, d.ms, 1.0, Gp, d.ms, Rg, ldr, 0.0, dst, d.ld);
+  else gemm_nn(s, NOM, d.ms, d.ms, 1.0, Gp, d.ms, Lg, ldr, 0.0, dst, d.ld);
 }
 void launch_slab_s22(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
-                     const double* zg, const int* scols, const double* svals, const double* sres, const double* corr_total,
-                     double var, double* T) {
+                     const double* zg, const double* corr_total, double var, double* T) {
   double* PHt = T + (size_t)d.m_pad * d.ld;
-  gemm_nt(s, d.N, d.ms, d.ms, 1.0, P + XB_CORE, d.N, Rg, ldr, 0.0, PHt + d.ro, d.ld);
-  gemm_nn(s, d.ms, d.ms, d.ms, 1.0, Rg, ldr, PHt + (size_t)XB_CORE * d.ld + d.ro, d.ld, 0.0, T + (size_t)d.ro * d.ld + d.ro, d.ld);
-  launch_sym_lower(s, T, d.ld, d.ro, d.ro + d.ms, d.ro);
-  k_s_finish<<<(d.m_pad - d.ro + 127) / 128, 128, 0, s>>>(d, d.ro, d.m_pad - d.ro, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
-  count_launch();
+  double* S22 = T + (size_t)d.ro * d.ld + d.ro;
+  if (Rg) {
+    gemm_nt(s, d.N, d.ms, d.ms, 1.0, P + XB_CORE, d.N, Rg, ldr, 0.0, PHt + d.ro, d.ld);
+    gemm_nn(s, d.ms, d.ms, d.ms, 1.0, Rg, ldr, PHt + (size_t)XB_CORE * d.ld + d.ro, d.ld, 0.0, S22, d.ld);
+  } else {
+    gemm_nn(s, d.N, d.ms, d.ms, 1.0, P + XB_CORE, d.N, Lg, ldr, 0.0, PHt + d.ro, d.ld);
+    gemm_tn(s, d.ms, d.ms, d.ms, 1.0, Lg, ldr, PHt + (size_t)XB_CORE * d.ld + d.ro, d.ld, 0.0, S22, d.ld);
+  }
+  {  // symmetrise the slab block, add the measurement variance, identity on the padding, r_eff: one launch
+    dim3 b(32, 8), g((d.m_pad - d.ro + 31) / 32, (d.m_pad - d.ro + 7) / 8);
+    k_slab_sym_finish<<<g, b, 0, s>>>(d, Lg, ldr, zg, corr_total, var, T);
+    count_launch();
+  }
 }
 void launch_slab_schur(cudaStream_t s, const UpdateDims& d, double* T) {
   if (d.nslam <= 0) return;
@@ -187,8 +224,8 @@ void launch_slab_schur(cudaStream_t s, const UpdateDims& d, double* T) {
 void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
                             const double* zg, const int* scols, const double* svals, const double* sres,
                             const double* corr_total, double var, const int* omega, double* T, const double* Bc, double* Gp) {
-  launch_slab_l21(s, d, Rg, ldr, T, Bc);
-  launch_slab_s22(s, d, P, Rg, Lg, ldr, zg, scols, svals, sres, corr_total, var, T);
+  launch_slab_l21(s, d, Rg, Lg, ldr, T, Bc);
+  launch_slab_s22(s, d, P, Rg, Lg, ldr, zg, corr_total, var, T);
   launch_slab_omega(s, d, P, Rg, Lg, ldr, omega, T, Gp);
   launch_slab_schur(s, d, T);
 }

@@ -1193,10 +1193,12 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     StageTimer st_(f, ST_CHOLG);
     tallchol_range(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, 0, f->gcols_pad, 0, f->d_flags_g, f->d_err, 1e-14,
                    f->d_diag0, nullptr, f->side_pending ? f->chol_share : 1);
-    transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
+    // Rg = L_G^T is only materialised for the CUDA-core GEMM fallback (and on demand for xb_debug_read("Rg"))
+    if (!gemm_uses_tensor_cores()) transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
   } else {
     CK(cudaMemsetAsync(f->d_Tg, 0, gbytes, f->stream));
-    CK(cudaMemsetAsync(f->d_Rg, 0, sizeof(double) * (size_t)f->gcols_pad * f->gcols_pad, f->stream));
+    if (!gemm_uses_tensor_cores())
+      CK(cudaMemsetAsync(f->d_Rg, 0, sizeof(double) * (size_t)f->gcols_pad * f->gcols_pad, f->stream));
   }
   return XB_OK;
 }
@@ -1288,6 +1290,7 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   {
     StageTimer st_(f, ST_BUILD);
     const double* zg = f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad;
+    const double* Rg = gemm_uses_tensor_cores() ? nullptr : f->d_Rg;
     if (f->slam_part_done) {
       // join: SLAM columns of the tall buffer are built and factored by the side stream
       if (f->side_pending) CK(cudaStreamWaitEvent(f->stream, f->ev_side, 0));
@@ -1302,16 +1305,16 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
       CK(cudaEventRecord(f->ev_b0, f->stream));
       CK(cudaStreamWaitEvent(f->side, f->ev_b0, 0));
       CK(cudaStreamWaitEvent(f->side3, f->ev_b0, 0));
-      launch_slab_l21(f->side, d, f->d_Rg, f->gcols_pad, f->d_T, f->d_Bc);
+      launch_slab_l21(f->side, d, Rg, f->d_Tg, f->gcols_pad, f->d_T, f->d_Bc);
       CK(cudaEventRecord(f->ev_b1, f->side));
-      launch_slab_omega(f->side3, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, f->d_omega, f->d_T, f->d_Gp);
+      launch_slab_omega(f->side3, d, f->d_Pw, Rg, f->d_Tg, f->gcols_pad, f->d_omega, f->d_T, f->d_Gp);
       CK(cudaEventRecord(f->ev_b2, f->side3));
-      launch_slab_s22(f->stream, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var, f->d_T);
+      launch_slab_s22(f->stream, d, f->d_Pw, Rg, f->d_Tg, f->gcols_pad, zg, corr, var, f->d_T);
       CK(cudaStreamWaitEvent(f->stream, f->ev_b1, 0));
       CK(cudaStreamWaitEvent(f->stream, f->ev_b2, 0));
       launch_slab_schur(f->stream, d, f->d_T);
     } else {
-      launch_build_slab_part(f->stream, d, f->d_Pw, f->d_Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var,
+      launch_build_slab_part(f->stream, d, f->d_Pw, Rg, f->d_Tg, f->gcols_pad, zg, f->d_scols, f->d_svals, f->d_sres, corr, var,
                              f->d_omega, f->d_T, f->d_Bc, f->d_Gp);
     }
   }
@@ -1761,7 +1764,10 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
   else if (n == "slam_vals") { src = f->d_svals; cnt = 30 * (size_t)f->l_slam.n; }
   else if (n == "slam_res") { src = f->d_sres; cnt = 2 * (size_t)f->l_slam.n; }
   else if (n == "Tg") { src = f->d_Tg; cnt = (size_t)f->grows_pad * f->gcols_pad; }
-  else if (n == "Rg") { src = f->d_Rg; cnt = (size_t)f->gcols_pad * f->gcols_pad; }
+  else if (n == "Rg") {
+    if (gemm_uses_tensor_cores()) transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);  // not kept otherwise
+    src = f->d_Rg; cnt = (size_t)f->gcols_pad * f->gcols_pad;
+  }
   else if (n == "corr") { src = f->d_corr; cnt = f->N; }
   else if (n == "delta") { src = f->d_delta; cnt = f->N; }
   else if (n == "T") { src = f->d_T; cnt = f->T_doubles; }

@@ -33,6 +33,9 @@ void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int
 // [jend, cols_pad) left out (their entries do not exist yet; the caller finishes with a Schur complement + plain call).
 void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int jstart_cols, int jend_cols, int phase,
                     int* flags, int* err, double piv_tol, const double* diag0, long long* trace, int share);
+bool gemm_uses_tensor_cores();
+void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+             double* C, int ldc);
 void gemm_tn_splitk(cudaStream_t s, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                     size_t strideC, int nz);
 void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, int n_pad, const int* omega_inv,
@@ -124,12 +127,11 @@ struct UpdateDims {
 // Tall-buffer pieces on the SLAM columns (no Rg needed) and on the slab columns (k_update.cu)
 void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
                             const double* sres, const double* corr_total, double var, const int* omega, double* T);
-void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, int ldr, double* T, const double* Bc);
+void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, double* T, const double* Bc);
 void launch_slab_omega(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
                        const int* omega, double* T, double* Gp);
 void launch_slab_s22(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
-                     const double* zg, const int* scols, const double* svals, const double* sres, const double* corr_total,
-                     double var, double* T);
+                     const double* zg, const double* corr_total, double var, double* T);
 void launch_slab_schur(cudaStream_t s, const UpdateDims& d, double* T);
 // Wsym = (W1s + W2s)/2 on the pose rows -> Bc (after the SLAM columns are factored)
 void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc);
