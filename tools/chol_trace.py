@@ -16,7 +16,7 @@ for imu, m in ev:
         flt.process_imu(t, i, w, a, want_state=False)
     flt.set_measurement(m)
     flt.process_update_measurement()
-tr = flt.debug("chol_trace", 6 * 19).reshape(-1, 6)
+tr = flt.debug("chol_trace", 6 * 6).reshape(-1, 6)   # the slab-column launch of the update: 6 tile columns
 t0 = tr[0, 2]
 print("critical-path CTA, per tile column (us since start): col_start  potrf_start  potrf_done  E_published")
 for r in tr:

@@ -410,7 +410,10 @@ __device__ __forceinline__ void flag_spin(const int* flag, int* err, int epoch) 
 // shared memory (Ls) and read back as broadcasts (left-looking).  Cs: in = tile, out = L (upper part zero).
 // Measured alternative (rejected): right-looking in registers with the multipliers exchanged by shuffle and the bulk
 // update software-pipelined around the pivot chain -- 1100 64-bit shuffles per tile make it 2x SLOWER (tile column
-// 12 -> 24 us) than the 500 broadcast shared-memory loads of this version.
+// 12 -> 24 us) than the 500 broadcast shared-memory loads of this version.  A left-looking variant with one column of
+// look-ahead (partial dot product of column c+1 issued under the rsqrt of pivot c, last term by one shuffle) measured
+// the same 5.7 us per tile as this one (tools/chol_trace.py): the tile is issue-bound on its ~2300 instructions executed
+// by a single warp, not bound by the pivot chain alone.
 __device__ __forceinline__ void warp_potrf32(double (*Cs)[TC + 1], double (*Ls)[TC + 1], const double* dorig,
                                              double piv_tol, int lane) {
   double a[TC];

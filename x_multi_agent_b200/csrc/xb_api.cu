@@ -1242,7 +1242,7 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
     // chol_from > 0: the leading columns are factored and folded into the rest (Schur complement): the remaining
     // columns are a plain tall factorisation of the sub-buffer starting at (chol_from, chol_from)
     tallchol(f->stream, f->d_T + (size_t)chol_from * m_pad + chol_from, m_pad, m_pad - chol_from + n_pad + 96, m_pad - chol_from,
-             f->d_flags, f->d_err, 0.0, nullptr, chol_from ? nullptr : f->d_trace);
+             f->d_flags, f->d_err, 0.0, nullptr, f->d_trace);
     f->trace_tiles = (m_pad / 32) * (m_pad / 32 + 1) / 2 + ((n_pad + 96) / 32) * (m_pad / 32); }
   {
     StageTimer st_(f, ST_CORRECT);
