@@ -73,28 +73,49 @@ def steady_events(scn, k0, n):
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.uuid, self.rows, self.stop_flag = index, uuid, [], False
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:   # one nvidia-smi process in loop mode (a fresh process per sample costs 0.1-0.5 s each)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index),
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                if line.strip():
-                    self.rows.append([x.strip() for x in line.split(",")])
+        # NVML directly (nvidia_ml_py): a sample costs microseconds; nvidia-smi (0.1-0.5 s per query) only as a fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active"
+                                                       for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                                 "sw_power_cap")])
+                time.sleep(0.01)
+            return
         except Exception:
             pass
-        finally:
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
             try:
-                self.proc.kill()
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
@@ -263,7 +284,11 @@ def main():
     # ---- phase A: device-timed throughput, inputs resident in HBM ------------------------------------------
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     launches0 = 0
     barrier()
     sampler.start()   # nvidia-smi takes ~0.1 s per query: start with the warm-up so that the timed region is covered

@@ -192,6 +192,7 @@ struct xb_filter {
   int gcols_pad = 0, grows_pad = 0, nz = 1;
   int* d_flags = nullptr;
   int* d_err = nullptr;
+  int* h_err = nullptr;  // pinned mirror of d_err
   long long* d_trace = nullptr;  // optional tile-Cholesky timeline (XB_CHOL_TRACE=1)
   long long* d_track_prof = nullptr;  // optional per-track phase clocks (XB_TRACK_PROF=1)
   int trace_tiles = 0;
@@ -505,6 +506,8 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   f->ipin_ints = ((size_t)(N + 15 * (6 + 3 * std::max(1, F)) + 2 * std::max(1, F) + 64) + 63) / 64 * 64;
   if (cudaMallocHost((void**)&f->h_ipin, sizeof(int) * f->ipin_ints * xb_filter::kPinRing) != cudaSuccess)
     return fail(XB_E_CUDA, "cudaMallocHost failed");
+  if (cudaMallocHost((void**)&f->h_err, sizeof(int)) != cudaSuccess) return fail(XB_E_CUDA, "cudaMallocHost failed");
+  *f->h_err = 0;
   for (int i = 0; i < xb_filter::kPinRing; ++i) {
     CK(cudaEventCreateWithFlags(&f->pin_ev[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&f->ipin_ev[i], cudaEventDisableTiming));
@@ -526,6 +529,7 @@ extern "C" int xb_destroy(xb_filter* f) {
   for (void* p : f->allocs) cudaFree(p);
   if (f->h_pin) cudaFreeHost(f->h_pin);
   if (f->h_ipin) cudaFreeHost(f->h_ipin);
+  if (f->h_err) cudaFreeHost(f->h_err);
   for (int i = 0; i < xb_filter::kPinRing; ++i) {
     if (f->pin_ev[i]) cudaEventDestroy(f->pin_ev[i]);
     if (f->ipin_ev[i]) cudaEventDestroy(f->ipin_ev[i]);
@@ -555,11 +559,11 @@ extern "C" int xb_set_stream(xb_filter* f, void* s) {
   return XB_OK;
 }
 extern "C" int xb_synchronize(xb_filter* f) {
+  // the dataflow-timeout flag rides on the same synchronisation (pinned word, no second blocking copy)
+  CK(cudaMemcpyAsync(f->h_err, f->d_err, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
   CK(cudaStreamSynchronize(f->stream));
   if (f->side_pending) CK(cudaStreamSynchronize(f->side));
-  int err = 0;
-  CK(cudaMemcpy(&err, f->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err) {
+  if (*f->h_err) {
     cudaMemset(f->d_err, 0, sizeof(int));
     return fail(XB_E_RUNTIME, "tile Cholesky dependency wait timed out");
   }
