@@ -1,0 +1,6 @@
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 600 python bench.py 2>gpurun_out/final_bench.err | tee gpurun_out/final_bench.json | cut -c1-400
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tee gpurun_out/final_ref.json | cut -c1-300
+bash tools/gpu/prof_all.sh r01_s2 > /dev/null 2>&1
+ls gpurun_out | head -30
