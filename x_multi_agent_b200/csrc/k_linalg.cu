@@ -513,6 +513,16 @@ __device__ __forceinline__ void tile_store(double* g, int ld, double (*S)[TC + 1
 }
 
 #define CP_THREADS 128
+// Register-staged tile: 128 threads x 8 elements.  fetch = ld.cg from global (row-major tile), stash = store into a shared
+// tile, transposed (k-major) -- the global-load latency of panel k+1 is hidden behind the tensor-core update with panel k.
+__device__ __forceinline__ void tile_fetch(double (&r)[8], const double* g, int ld, int t) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { const int e = t + CP_THREADS * u; r[u] = __ldcg(&g[(size_t)(e >> 5) * ld + (e & 31)]); }
+}
+__device__ __forceinline__ void tile_stash_t(double (*S)[TC + 1], const double (&r)[8], int t) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { const int e = t + CP_THREADS * u; S[e & 31][e >> 5] = r[u]; }
+}
 // Column range / row-skip description of one launch.  A factorisation may be split in two launches so that the first
 // tile columns are factored while the rows of the remaining columns are still being produced (xb_api.cu overlaps
 // the SLAM-row part of the Kalman update with the MSCKF track pipeline this way):
@@ -534,14 +544,32 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
   double* gC = T + (size_t)i * TC * ld + (size_t)jcol * TC;
   tile_load(Ds, gC, ld, t, CP_THREADS, false);
   __syncthreads();
-  for (int k = 0; k < jcol; ++k) {
-    if (t == 0) { flag_spin(&ready[i * ct + k], err, epoch); flag_spin(&ready[jcol * ct + k], err, epoch); }
-    __syncthreads();
-    tile_load(Ws, T + (size_t)i * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
-    tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);
-    __syncthreads();
-    tile_gemm_sub(Ds, Ws, Ls, t, CP_THREADS);
-    __syncthreads();
+  if (jcol > 0) {
+    // left-looking accumulation over the panels k < jcol, software-pipelined: while panel k is multiplied, the tiles of
+    // panel k+1 are already on their way into registers if their flags are set (they almost always are: only the last
+    // panel is fresh); otherwise the fetch falls back to the blocking wait after the product.
+    double ra[8], rb[8];
+    auto fetch_blocking = [&](int k) {
+      if (t == 0) { flag_spin(&ready[i * ct + k], err, epoch); flag_spin(&ready[jcol * ct + k], err, epoch); }
+      __syncthreads();
+      tile_fetch(ra, T + (size_t)i * TC * ld + (size_t)k * TC, ld, t);
+      tile_fetch(rb, T + (size_t)jcol * TC * ld + (size_t)k * TC, ld, t);
+    };
+    fetch_blocking(0);
+    for (int k = 0; k < jcol; ++k) {
+      tile_stash_t(Ws, ra, t);
+      tile_stash_t(Ls, rb, t);
+      int rdy = 0;
+      if (k + 1 < jcol) rdy = ld_acquire(&ready[i * ct + k + 1]) == epoch && ld_acquire(&ready[jcol * ct + k + 1]) == epoch;
+      const int all = __syncthreads_and(rdy);
+      if (all) {
+        tile_fetch(ra, T + (size_t)i * TC * ld + (size_t)(k + 1) * TC, ld, t);
+        tile_fetch(rb, T + (size_t)jcol * TC * ld + (size_t)(k + 1) * TC, ld, t);
+      }
+      tile_gemm_sub(Ds, Ws, Ls, t, CP_THREADS);
+      __syncthreads();
+      if (!all && k + 1 < jcol) fetch_blocking(k + 1);
+    }
   }
   const long long tr1 = trace ? gtimer() : 0;
   if (t == 0) flag_spin(&ready[jcol * ct + jcol], err, epoch);
@@ -705,15 +733,31 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       tile_load(Ds, gD, ld, t, CP_THREADS, false);
       if (has_e) tile_load(Es[0], gE, ld, t, CP_THREADS, false);
       __syncthreads();
-      for (int k = 0; k <= kmax; ++k) {
-        if (t == 0) { flag_spin(&ready[jp * ct + k], err, epoch); if (has_e) flag_spin(&ready[(jp + 1) * ct + k], err, epoch); }
-        __syncthreads();
-        tile_load(Ws, T + (size_t)jp * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);          // L(jp,k) k-major
-        if (has_e) tile_load(Ls, T + (size_t)(jp + 1) * TC * ld + (size_t)k * TC, ld, t, CP_THREADS, true);    // L(jp+1,k) k-major
-        __syncthreads();
-        if (t < 64) tile_gemm_sub(Ds, Ws, Ws, t, 64);
-        else if (has_e) tile_gemm_sub(Es[0], Ls, Ws, t - 64, 64);
-        __syncthreads();
+      if (kmax >= 0) {  // same software pipeline as worker_trsm: panel k+1 in flight while panel k is multiplied
+        double ra[8], rb[8];
+        auto fetch_blocking = [&](int k) {
+          if (t == 0) { flag_spin(&ready[jp * ct + k], err, epoch); if (has_e) flag_spin(&ready[(jp + 1) * ct + k], err, epoch); }
+          __syncthreads();
+          tile_fetch(ra, T + (size_t)jp * TC * ld + (size_t)k * TC, ld, t);
+          if (has_e) tile_fetch(rb, T + (size_t)(jp + 1) * TC * ld + (size_t)k * TC, ld, t);
+        };
+        fetch_blocking(0);
+        for (int k = 0; k <= kmax; ++k) {
+          tile_stash_t(Ws, ra, t);                 // L(jp,k) k-major
+          if (has_e) tile_stash_t(Ls, rb, t);      // L(jp+1,k) k-major
+          int rdy = 0;
+          if (k + 1 <= kmax)
+            rdy = ld_acquire(&ready[jp * ct + k + 1]) == epoch && (!has_e || ld_acquire(&ready[(jp + 1) * ct + k + 1]) == epoch);
+          const int all = __syncthreads_and(rdy);
+          if (all) {
+            tile_fetch(ra, T + (size_t)jp * TC * ld + (size_t)(k + 1) * TC, ld, t);
+            if (has_e) tile_fetch(rb, T + (size_t)(jp + 1) * TC * ld + (size_t)(k + 1) * TC, ld, t);
+          }
+          if (t < 64) tile_gemm_sub(Ds, Ws, Ws, t, 64);
+          else if (has_e) tile_gemm_sub(Es[0], Ls, Ws, t - 64, 64);
+          __syncthreads();
+          if (!all && k + 1 <= kmax) fetch_blocking(k + 1);
+        }
       }
       tile_store(gD, ld, Ds, t, CP_THREADS);
       if (has_e) tile_store(gE, ld, Es[0], t, CP_THREADS);

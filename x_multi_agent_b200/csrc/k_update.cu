@@ -31,16 +31,24 @@ namespace xb {
 //
 // PHt[i, 2j + r] = sum_e P[i, col_e] * val[j][r][e]
 __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int* __restrict__ scols,
-                           const double* __restrict__ svals, double* __restrict__ T) {
+                           const double* __restrict__ svals, const int* __restrict__ omega_inv, double* __restrict__ T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= d.N || j >= d.nslam) return;
+  // P[i][col] is read as P[col][i] (consecutive threads -> consecutive addresses; the row-wise form is a stride-N gather
+  // that costs 4x the sectors, 1.6 ms at cfg-5) wherever P is symmetric, i.e. everywhere except Omega x Omega
+  const bool i_om = omega_inv[i] >= 0;
+  int col[15];
+  double pv[15];
+#pragma unroll
+  for (int e = 0; e < 15; ++e) col[e] = scols[15 * j + e];
+#pragma unroll
+  for (int e = 0; e < 15; ++e)
+    pv[e] = (i_om && omega_inv[col[e]] >= 0) ? P[(size_t)i * d.N + col[e]] : P[(size_t)col[e] * d.N + i];
   double a0 = 0.0, a1 = 0.0;
-  const double* Pi = P + (size_t)i * d.N;
 #pragma unroll
   for (int e = 0; e < 15; ++e) {
-    const double p = Pi[scols[15 * j + e]];
-    a0 = fma(p, svals[30 * j + e], a0);
-    a1 = fma(p, svals[30 * j + 15 + e], a1);
+    a0 = fma(pv[e], svals[30 * j + e], a0);
+    a1 = fma(pv[e], svals[30 * j + 15 + e], a1);
   }
   double* row = T + (size_t)(d.m_pad + i) * d.ld + 2 * j;
   row[0] = a0;
@@ -120,11 +128,12 @@ void launch_omega_rows(cudaStream_t s, const UpdateDims& d, int c0, int nc, cons
 
 // Everything of the tall buffer that lives on the SLAM columns [0, s_pad): PHt, S[slam, slam], diagonal, r_eff, Omega/V rows.
 void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
-                            const double* sres, const double* corr_total, double var, const int* omega, double* T) {
+                            const double* sres, const double* corr_total, double var, const int* omega, const int* omega_inv,
+                            double* T) {
   if (d.nslam <= 0) return;
   {
     dim3 g((d.N + 127) / 128, d.nslam);
-    k_pht_slam<<<g, 128, 0, s>>>(d, P, scols, svals, T);
+    k_pht_slam<<<g, 128, 0, s>>>(d, P, scols, svals, omega_inv, T);
     count_launch();
   }
   {

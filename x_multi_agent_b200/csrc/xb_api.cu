@@ -1101,7 +1101,7 @@ static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int s
     StageTimer st_(f, stage_build, st);
     if (with_rows) launch_slam_rows_on(f, st, d.nslam);
     launch_build_slam_part(st, d, f->d_Pw, f->d_scols, f->d_svals, f->d_sres, f->corr_zero ? nullptr : f->d_corr,
-                           f->cfg.sigma_img * f->cfg.sigma_img, f->d_omega, f->d_T);
+                           f->cfg.sigma_img * f->cfg.sigma_img, f->d_omega, f->d_omega_inv, f->d_T);
   }
   StageTimer st_(f, stage_chol, st);
   tallchol_range(st, f->d_T, d.m_pad, d.m_pad + d.n_pad + 96, d.m_pad, 0, d.s_pad, 1, f->d_flags, f->d_err, 0.0, nullptr, nullptr,

@@ -126,7 +126,8 @@ struct UpdateDims {
 };
 // Tall-buffer pieces on the SLAM columns (no Rg needed) and on the slab columns (k_update.cu)
 void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
-                            const double* sres, const double* corr_total, double var, const int* omega, double* T);
+                            const double* sres, const double* corr_total, double var, const int* omega, const int* omega_inv,
+                            double* T);
 void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, double* T, const double* Bc);
 void launch_slab_omega(cudaStream_t s, const UpdateDims& d, const double* P, const double* Rg, const double* Lg, int ldr,
                        const int* omega, double* T, double* Gp);
