@@ -116,6 +116,7 @@ def _stage_setup(cfg, n_frames):
     (SynthConfig(M=10, F=0, K=50, seed=0), 12),                     # BASELINE cfg-1 shape
     (SynthConfig(M=5, F=4, K=20, seed=5, n_short=3, churn=1), 11),  # short-MSCKF pre-update
     (SynthConfig(M=34, F=4, K=16, seed=3), 37),                     # window > 32 poses: two observations per lane
+    (SynthConfig(M=6, F=6, K=0, seed=1, churn=1), 9),               # SLAM-only update (no MSCKF rows at all) with feature loss
 ])
 def test_update_stage_by_stage(cfg, frames):
     """Updater::update (updater.cpp:39-115) split into its stages, each compared with the oracle."""
@@ -689,3 +690,36 @@ def test_pinned_measurement_buffers_take_the_direct_copy_path():
         dev.synchronize()
         dev.close()
     assert np.array_equal(out[0].x, out[1].x) and np.array_equal(out[0].cov, out[1].cov)
+
+
+@pytest.mark.gpu
+def test_consecutive_empty_updates_stay_within_the_documented_deviation():
+    """KNOWN DEVIATION ('asymmetric support'): an update without measurement rows runs
+    StateManager::manage but no applyUpdate (updater.cpp:106), so the reference's covariance is not symmetrised and the
+    asymmetry of its Q_d (propagator.cpp:207-840) spreads from the core block into every clone added meanwhile.  The
+    device represents the antisymmetric part on Omega = core + newest clone only (exact whenever each update applies a
+    covariance update).  Six consecutive empty updates (window filling without any track), then feature initialisation
+    and SLAM-only updates: the device must stay finite, symmetric-consistent and within 5e-2 of the oracle; the observed
+    deviation is 6e-3 m in position, 7e-4 in the quaternions, 2e-3 relative in the covariance."""
+    cfg = SynthConfig(M=6, F=6, K=0, seed=1, churn=1)
+    ev = record(Scenario(cfg), 14)
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    dev = make_filter(cfg)
+    o_states, d_states = [], []
+    replay(ev, ora, lambda k, m, st: o_states.append(st.copy()))
+    replay(ev, dev, lambda k, m, st: d_states.append(st))
+    rp = Report()
+    # the empty updates themselves only run manage on the estimates: exact
+    for k in range(6):
+        rp.check(f"empty update {k} state", np.abs(d_states[k].x[:16] - np.concatenate([o_states[k].p, o_states[k].v, o_states[k].q,
+                 o_states[k].b_w, o_states[k].b_a])).max(), 1e-12)
+    worst_p = max(np.abs(d.p - o.p).max() for d, o in zip(d_states[6:], o_states[6:]))
+    worst_q = max(np.abs(d.q - o.q).max() for d, o in zip(d_states[6:], o_states[6:]))
+    P_d, P_o = dev.get_covariance(), ora.newest().cov
+    rp.check("position after the first real updates (known deviation)", worst_p, 5e-2)
+    rp.check("quaternion (known deviation)", worst_q, 5e-2)
+    rp.check("covariance (known deviation)", rel(P_d, P_o), 5e-2)
+    assert np.isfinite(P_d).all()
+    dev.synchronize()
+    rp.done()
+    dev.close()

@@ -125,6 +125,8 @@ def load():
                            "(x_multi_agent_b200 has no CPU fallback)")
     lib = C.CDLL(os.fspath(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("XB200_LIB") and not hasattr(lib, name):
+            continue   # an older A/B build may lack newer entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
