@@ -314,3 +314,52 @@ def test_cxx_binding_compiles_in_both_build_flavours():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{ROOT / 'include'}", os.fspath(ROOT / "tests" / "cxx" / "test_x_api.cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_split_schedule_of_the_kalman_update_equals_the_one_shot_update():
+    """The device orders the compressed measurement as Hc = [H_slam ; R] and splits the tall factorisation (DESIGN.md
+    section 2): SLAM columns first (side stream), then L21 = R * Wsym as a plain GEMM, one Schur-complement GEMM over every
+    row from the R rows down, and a plain factorisation of the remaining columns; the covariance downdate is split by
+    the same column ranges.  numpy restatement of exactly that schedule against the reference algebra
+    K = P H^T (H P H^T + R)^-1, P <- (I - K H) P, symmetrise (updater.cpp:117-141), for a symmetric P."""
+    rng = np.random.default_rng(7)
+    N, ns, nr, pose0, npose = 60, 14, 18, 15, 18          # nr slab rows living on the pose columns [pose0, pose0 + npose)
+    A = rng.normal(size=(N, N))
+    P = A @ A.T / N + np.eye(N) * 0.1
+    Hs = np.zeros((ns, N))
+    for r in range(ns):                                   # sparse SLAM rows: a few pose and feature columns each
+        cols = rng.choice(N, size=9, replace=False)
+        Hs[r, cols] = rng.normal(size=9)
+    Rg = np.triu(rng.normal(size=(nr, npose)))            # compressed MSCKF block (upper-triangular factor of the Gram matrix)
+    Hr = np.zeros((nr, N)); Hr[:, pose0:pose0 + npose] = Rg
+    res_s, res_r = rng.normal(size=ns), rng.normal(size=nr)
+    var = 0.3
+    # reference: one shot, rows in the reference's order [R ; H_slam]
+    H = np.vstack([Hr, Hs]); res = np.concatenate([res_r, res_s])
+    S = H @ P @ H.T + var * np.eye(ns + nr)
+    K = P @ H.T @ np.linalg.inv(S)
+    P_ref = (np.eye(N) - K @ H) @ P
+    P_ref = 0.5 * (P_ref + P_ref.T)
+    d_ref = K @ res
+    # device schedule
+    A1s = P @ Hs.T                                        # side stream: P Hs^T, S11, first tile columns of the factorisation
+    L11 = np.linalg.cholesky(Hs @ A1s + var * np.eye(ns))
+    W1s = sla.solve_triangular(L11, A1s.T, lower=True).T  # (P Hs^T) L11^-T
+    z_s = sla.solve_triangular(L11, res_s, lower=True)
+    L21 = Rg @ W1s[pose0:pose0 + npose]                   # no triangular solve: L21 = S21 L11^-T = Rg (P Hs^T)[pose rows] L11^-T
+    assert np.allclose(L21, sla.solve_triangular(L11, (Hr @ A1s).T, lower=True).T, atol=1e-12)
+    A1r = P[:, pose0:pose0 + npose] @ Rg.T                # P H_R^T
+    S22 = Rg @ A1r[pose0:pose0 + npose] + var * np.eye(nr)
+    S22s, A1rs, res_rs = S22 - L21 @ L21.T, A1r - W1s @ L21.T, res_r - L21 @ z_s   # ONE Schur-complement GEMM over all rows
+    L22 = np.linalg.cholesky(S22s)                        # plain factorisation of the remaining columns
+    W1r = sla.solve_triangular(L22, A1rs.T, lower=True).T
+    z_r = sla.solve_triangular(L22, res_rs, lower=True)
+    P_early = 0.5 * (P + P.T) - W1s @ W1s.T               # K-split downdate: SLAM columns early (side stream) ...
+    P_dev = P_early - W1r @ W1r.T                         # ... slab columns after the correction
+    d_dev = W1s @ z_s + W1r @ z_r
+    assert np.abs(P_dev - P_ref).max() < 1e-12 * np.abs(P_ref).max() * 100
+    assert np.abs(d_dev - d_ref).max() < 1e-11
+    # the full one-shot factor has exactly these blocks
+    Hc = np.vstack([Hs, Hr])
+    Lfull = np.linalg.cholesky(Hc @ P @ Hc.T + var * np.eye(ns + nr))
+    assert np.allclose(Lfull[:ns, :ns], L11) and np.allclose(Lfull[ns:, :ns], L21) and np.allclose(Lfull[ns:, ns:], L22)
