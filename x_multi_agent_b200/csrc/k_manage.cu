@@ -126,9 +126,25 @@ __global__ void __launch_bounds__(128) k_manage_prep(ManageDev md, double* __res
   }
 }
 
+// Source covariance of manage: either a materialised N x N matrix, or the "virtual" form a ring slot is stored in -- the
+// 15 x N strip [P_ii | P_iv] of the slot plus the covariance generation that holds P_vv (P_vi = P_iv^T).  Reading the
+// virtual form directly saves the assemble pass (one 5 MB read + write at cfg-2) at the head of every update.
+struct PSrc {
+  const double* P;      // materialised matrix, or nullptr
+  const double* strip;  // 15 x N
+  const double* gen;    // N x N (only rows/cols >= 15 are read)
+  int N;
+  __device__ __forceinline__ double at(int r, int c) const {
+    if (P) return P[(size_t)r * N + c];
+    if (r < XB_CORE) return strip[(size_t)r * N + c];
+    if (c < XB_CORE) return strip[(size_t)c * N + r];
+    return gen[(size_t)r * N + c];
+  }
+};
+
 // T[ci][b] = sum_e val_e * P[col_e][b]   and   T2[ci][r] = sum_e P[r][col_e] * val_e  (r < 15)
-__global__ void k_manage_T(int N, int n_comp, const int* __restrict__ ccols, const double* __restrict__ cvals,
-                           const double* __restrict__ P, double* __restrict__ T, double* __restrict__ T2) {
+__global__ void k_manage_T(int N, int n_comp, const int* __restrict__ ccols, const double* __restrict__ cvals, PSrc P,
+                           double* __restrict__ T, double* __restrict__ T2) {
   const int ci = blockIdx.y;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= n_comp || b >= N) return;
@@ -136,17 +152,16 @@ __global__ void k_manage_T(int N, int n_comp, const int* __restrict__ ccols, con
   for (int e = 0; e < 15; ++e) {
     const int col = ccols[ci * 15 + e];
     const double v = cvals[ci * 15 + e];
-    s = fma(v, P[(size_t)col * N + b], s);
-    if (b < XB_CORE) s2 = fma(P[(size_t)b * N + col], v, s2);
+    s = fma(v, P.at(col, b), s);
+    if (b < XB_CORE) s2 = fma(P.at(b, col), v, s2);
   }
   T[(size_t)ci * N + b] = s;
   if (b < XB_CORE) T2[ci * XB_CORE + b] = s2;
 }
 
 __global__ void __launch_bounds__(256) k_manage_apply(int N, const int* __restrict__ rowmap, const int* __restrict__ ccols,
-                                                       const double* __restrict__ cvals, const double* __restrict__ P,
-                                                       const double* __restrict__ T, const double* __restrict__ T2,
-                                                       double* __restrict__ Pn) {
+                                                       const double* __restrict__ cvals, PSrc P, const double* __restrict__ T,
+                                                       const double* __restrict__ T2, double* __restrict__ Pn) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
   if (j >= N) return;
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(256) k_manage_apply(int N, const int* __restri
     if (mi == -1 || mj == -1) {
       v = 0.0;
     } else if (mi >= 0 && mj >= 0) {
-      v = P[(size_t)mi * N + mj];
+      v = P.at(mi, mj);
     } else if (mi <= -2 && mj >= 0) {
       v = T[(size_t)(-2 - mi) * N + mj];
     } else if (mi >= 0 && mj <= -2) {
@@ -176,16 +191,17 @@ __global__ void __launch_bounds__(256) k_manage_apply(int N, const int* __restri
 void launch_manage_dev(cudaStream_t s, int M, int F, int N, int n_poses, int n_features, int slide, int n_reanch,
                        const int* d_feat_src, const int* d_reanch, const int* d_rowmap, const int* d_ccols,
                        double* d_cvals, double* d_scratch, double* xv, const double* Pold, double* Pnew, double* Tm,
-                       double* T2) {
+                       double* T2, const double* strip, const double* gen) {
   ManageDev md{M, F, N, n_poses, n_features, slide, n_reanch, d_feat_src, d_reanch, d_cvals, d_scratch};
   k_manage_prep<<<1, 128, 0, s>>>(md, xv);
   count_launch();
+  const PSrc src{Pold, strip, gen, N};  // Pold == nullptr: read the slot's strip + generation directly
   const int n_comp = 6 + 3 * n_reanch;
   dim3 gt((N + 127) / 128, n_comp);
-  k_manage_T<<<gt, 128, 0, s>>>(N, n_comp, d_ccols, d_cvals, Pold, Tm, T2);
+  k_manage_T<<<gt, 128, 0, s>>>(N, n_comp, d_ccols, d_cvals, src, Tm, T2);
   count_launch();
   dim3 ga((N + 31) / 32, (N + 31) / 32);
-  k_manage_apply<<<ga, 256, 0, s>>>(N, d_rowmap, d_ccols, d_cvals, Pold, Tm, T2, Pnew);
+  k_manage_apply<<<ga, 256, 0, s>>>(N, d_rowmap, d_ccols, d_cvals, src, Tm, T2, Pnew);
   count_launch();
 }
 

@@ -154,6 +154,11 @@ struct xb_filter {
   double* d_WB = nullptr;   // second scratch: work_load / manage ping-pong between the two, generations are claimed only
                             // for a covariance that a ring slot is going to reference
   double* d_dd = nullptr;   // destination of the pending early downdate (a claimed generation)
+  // The work covariance right after xb_work_load is "virtual": d_Pw names d_WB, but its content is still the slot's strip +
+  // generation.  xb_sm_manage (the first consumer in Ekf::processUpdateMeasurement unless a short-MSCKF update precedes it)
+  // reads that form directly; every other consumer materialises it first (one assemble pass).
+  bool virt = false;
+  const double *virt_strip = nullptr, *virt_gen = nullptr;
   double* d_Pw = nullptr;   // points at WA or a generation
   double* d_corr = nullptr; // N correction_total
   double* d_delta = nullptr;
@@ -233,6 +238,9 @@ struct xb_filter {
 };
 
 static int invalidate_early(xb_filter* f);
+static cudaEvent_t prof_event(xb_filter* f);
+struct StageTimer;
+static void materialize(xb_filter* f);
 static cudaEvent_t prof_event(xb_filter* f) {
   cudaEvent_t e;
   if (!f->ev_pool.empty()) { e = f->ev_pool.back(); f->ev_pool.pop_back(); }
@@ -800,10 +808,17 @@ extern "C" int xb_work_load(xb_filter* f, int slot) {
   if (invalidate_early(f)) return XB_E_CUDA;
   StageTimer st_(f, ST_ASSEMBLE);
   CK(cudaMemcpyAsync(f->d_xw, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
-  launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
-                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_WB);
+  f->virt_strip = f->d_strip + (size_t)slot * 15 * f->N;
+  f->virt_gen = f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N;
   f->d_Pw = f->d_WB;
+  f->virt = true;
+  if (!f->overlap) materialize(f);   // XB_NO_OVERLAP=1 also switches this shortcut off (plain, ordered reference schedule)
   return XB_OK;
+}
+static void materialize(xb_filter* f) {
+  if (!f->virt) return;
+  launch_assemble(f->stream, f->N, f->virt_strip, f->virt_gen, f->d_WB);
+  f->virt = false;
 }
 // claim the next covariance generation as destination; slots still pointing at it lose their state
 static double* claim_generation(xb_filter* f) {
@@ -814,6 +829,7 @@ static double* claim_generation(xb_filter* f) {
 }
 static int work_store_impl(xb_filter* f, int slot, bool copy_estimates) {
   if (slot < 0 || slot >= f->NS) return fail(XB_E_INVALID, "bad slot");
+  materialize(f);
   StageTimer st_(f, ST_STORE);
   const size_t nn = (size_t)f->N * f->N;
   bool in_gen = f->d_Pw >= f->d_Pgen && f->d_Pw < f->d_Pgen + (size_t)f->NG * nn;
@@ -832,6 +848,7 @@ extern "C" int xb_work_store(xb_filter* f, int slot) { return work_store_impl(f,
 extern "C" int xb_work_set(xb_filter* f, const double* xvec, const double* cov, int layout) {
   CK(cudaSetDevice(f->cfg.device));
   if (invalidate_early(f)) return XB_E_CUDA;
+  if (cov) f->virt = false; else materialize(f);
   if (xvec) CK(cudaMemcpyAsync(f->d_xw, xvec, sizeof(double) * f->LX, cudaMemcpyHostToDevice, f->stream));
   if (cov) {
     int rc = upload_cov(f, cov, layout, f->d_WA);
@@ -842,6 +859,7 @@ extern "C" int xb_work_set(xb_filter* f, const double* xvec, const double* cov, 
   return XB_OK;
 }
 extern "C" int xb_work_get(xb_filter* f, double* xvec_out, double* cov_out, int layout) {
+  if (cov_out) materialize(f);
   if (xvec_out) CK(cudaMemcpyAsync(xvec_out, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToHost, f->stream));
   if (cov_out) {
     if (!f->d_Pw) return fail(XB_E_INVALID, "no work covariance");
@@ -959,8 +977,11 @@ extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
   // destination: the scratch buffer that is not the source
   double* src_P = f->d_Pw;
   double* dst_P = (src_P == f->d_WA) ? f->d_WB : f->d_WA;
+  // a work covariance that is still in its ring-slot form (strip + generation) is read as such: no assemble pass
   launch_manage_dev(f->stream, M, F, N, f->n_poses, nf, slide, (int)reanch.size(), f->d_featsrc, f->d_reanch, f->d_rowmap,
-                    f->d_ccols, f->d_cvals, f->d_mscratch, f->d_xw, src_P, dst_P, f->d_Tm, f->d_T2);
+                    f->d_ccols, f->d_cvals, f->d_mscratch, f->d_xw, f->virt ? nullptr : src_P, dst_P, f->d_Tm, f->d_T2,
+                    f->virt_strip, f->virt_gen);
+  f->virt = false;
   f->d_Pw = dst_P;
   // bookkeeping after the call
   for (int k = 0; k < F; ++k) f->anchor[k] = anc[k];
@@ -1073,6 +1094,7 @@ static int mm_prepare(xb_filter* f, int which, const ListDev& l0, MmParams& mp) 
 
 extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  materialize(f);
   if (f->mm_G <= 0) return XB_OK;
   f->xw_final = false;
   if (invalidate_early(f)) return XB_E_CUDA;
@@ -1112,6 +1134,7 @@ static size_t tall_bytes(const UpdateDims& d) { return sizeof(double) * (size_t)
 
 extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  materialize(f);
   const int M = f->M;
   const ListDev& l0 = which == 0 ? f->l_msckf : f->l_short;
   const int n0 = l0.n, n1 = which == 0 ? f->l_newms.n : 0, ns = which == 0 ? f->l_slam.n : 0;
@@ -1284,6 +1307,7 @@ extern "C" int xb_updater_reset_correction(xb_filter* f) {
 
 extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  materialize(f);
   if (!f->constructed_any) return XB_OK;  // h.size() == 0 (updater.cpp:106)
   const UpdateDims d = update_dims(f, f->last_nslam);
   const double var = f->cfg.sigma_img * f->cfg.sigma_img;
@@ -1330,6 +1354,7 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
 extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const double* res, const double* r_diag, int m,
                                        double* correction_total, int cov_update) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  materialize(f);
   const int N = f->N;
   if (m <= 0) return XB_OK;
   if (invalidate_early(f)) return XB_E_CUDA;
@@ -1361,6 +1386,7 @@ extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const doub
 extern "C" int xb_updater_apply_ci(xb_filter* f, const double* H, const double* res, const double* S, int m,
                                    const int* scaled_block_cols, int n_blocks, double w_result) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  materialize(f);
   const int N = f->N;
   if (m <= 0 || m > 96) return fail(XB_E_INVALID, "applyCI: 0 < rows <= 96");
   if (invalidate_early(f)) return XB_E_CUDA;
@@ -1417,6 +1443,7 @@ extern "C" int xb_updater_apply_ci(xb_filter* f, const double* H, const double* 
 extern "C" int xb_vio_post_update(xb_filter* f) {
   const int M = f->M, F = f->F, N = f->N;
   const double var = f->cfg.sigma_img * f->cfg.sigma_img;
+  materialize(f);
   StageTimer st_(f, ST_POST);
   if (f->l_newms.n > 0 || f->l_newstd.n > 0) f->xw_final = false;
   if (f->l_newms.n > 0) {
@@ -1564,6 +1591,7 @@ static int check_ci_weight(double w) {  // ci.cpp:98-101
 static int collaborative_update_packed(xb_filter* f, const double* dev_gathered, const xb_slam_match* matches, int n_matches) {
   if (n_matches <= 0) return XB_OK;  // preUpdateCI (vio_updater.cpp:76-79)
   if (invalidate_early(f)) return XB_E_CUDA;
+  materialize(f);
   if (n_matches > f->ci_max_matches) return fail(XB_E_CAPACITY, "too many SLAM-SLAM matches");
   int rc = check_ci_weight(f->cfg.ci_slam_w);
   if (rc) return rc;

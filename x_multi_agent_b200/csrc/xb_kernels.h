@@ -157,7 +157,8 @@ void downdate_tc(cudaStream_t s, double* P, int n, const double* T, int m_pad, i
 void launch_manage_dev(cudaStream_t s, int M, int F, int N, int n_poses, int n_features, int slide, int n_reanch,
                        const int* d_feat_src, const int* d_reanch, const int* d_rowmap, const int* d_ccols,
                        double* d_cvals, double* d_scratch, double* xv, const double* Pold, double* Pnew, double* Tm,
-                       double* T2);
+                       double* T2,
+                       const double* strip = nullptr, const double* gen = nullptr);
 // P(full) <- strip rows/cols + P_vv of a generation buffer
 void launch_assemble(cudaStream_t s, int N, const double* strip, const double* Pgen, double* Pwork);
 void launch_extract_strip(cudaStream_t s, int N, const double* Pwork, double* strip);
