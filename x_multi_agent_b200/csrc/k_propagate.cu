@@ -118,52 +118,34 @@ __global__ void __launch_bounds__(128) k_prop_means(double* __restrict__ xv, int
     quat_integrator(w0, w1, s1[XV_TIME] - s0[XV_TIME], Dm[t]);
   }
   __syncthreads();
-  // The sequential part is split so that only what is inherently serial runs on one thread, out of registers / shared
-  // memory (the chain used to re-read every slot from global memory): (1) quaternion chain q_k = normalise(D_k q_{k-1});
-  // (2) in parallel over k: rotated specific force C(q_k) (a_m - b_a)_k and dt_k; (3) velocity / position chain;
-  // (4) parallel write-back.  Same operations in the same order as Propagator::propagateState (propagator.cpp:30-51).
-  __shared__ double qs[129][4], ras[129][3], dts[129], vs[129][3], ps[129][3];
-  if (t == 0) {
-    double q[4] = {x0[XV_Q], x0[XV_Q + 1], x0[XV_Q + 2], x0[XV_Q + 3]};
-    for (int e = 0; e < 4; ++e) qs[0][e] = q[e];
+  if (t == 0) {  // the short sequential chain: q, v, p
     for (int k = 1; k <= n_steps; ++k) {
+      const double* s0 = xv + (size_t)((start + k - 1) % NS) * LX;
+      double* s1 = xv + (size_t)((start + k) % NS) * LX;
+      double a1[3], a0[3];
+      for (int e = 0; e < 3; ++e) {
+        a1[e] = s1[XV_AM + e] - s1[XV_BA + e];
+        a0[e] = s0[XV_AM + e] - s0[XV_BA + e];
+      }
+      const double dt = s1[XV_TIME] - s0[XV_TIME];
       const double* D = Dm[k - 1];
       double q1[4];
-      for (int r = 0; r < 4; ++r) q1[r] = D[r * 4] * q[0] + D[r * 4 + 1] * q[1] + D[r * 4 + 2] * q[2] + D[r * 4 + 3] * q[3];
+      for (int r = 0; r < 4; ++r)
+        q1[r] = D[r * 4] * s0[XV_Q] + D[r * 4 + 1] * s0[XV_Q + 1] + D[r * 4 + 2] * s0[XV_Q + 2] + D[r * 4 + 3] * s0[XV_Q + 3];
       xb_qnormalize(q1);
-      for (int e = 0; e < 4; ++e) { q[e] = q1[e]; qs[k][e] = q1[e]; }
-    }
-  }
-  __syncthreads();
-  for (int k = t; k <= n_steps; k += blockDim.x) {
-    const double* sk = xv + (size_t)((start + k) % NS) * LX;
-    double a[3], R[9], ra[3];
-    for (int e = 0; e < 3; ++e) a[e] = sk[XV_AM + e] - sk[XV_BA + e];
-    xb_rot_raw(qs[k], R);
-    xb_mv33(R, a, ra);
-    for (int e = 0; e < 3; ++e) ras[k][e] = ra[e];
-    dts[k] = k >= 1 ? sk[XV_TIME] - xv[(size_t)((start + k - 1) % NS) * LX + XV_TIME] : 0.0;
-  }
-  __syncthreads();
-  if (t == 0) {
-    double v[3] = {x0[XV_V], x0[XV_V + 1], x0[XV_V + 2]}, p[3] = {x0[XV_P], x0[XV_P + 1], x0[XV_P + 2]};
-    for (int k = 1; k <= n_steps; ++k) {
-      const double dt = dts[k];
+      double R1[9], R0[9], ra1[3], ra0[3];
+      xb_rot_raw(q1, R1);
+      xb_rot_raw(&s0[XV_Q], R0);
+      xb_mv33(R1, a1, ra1);
+      xb_mv33(R0, a0, ra0);
       for (int e = 0; e < 3; ++e) {
-        const double dv = (ras[k][e] + ras[k - 1][e]) / 2.0;
-        const double v1 = v[e] + (dv + pp.g[e]) * dt;
-        p[e] = p[e] + (v1 + v[e]) / 2.0 * dt;
-        v[e] = v1;
-        vs[k][e] = v1;
-        ps[k][e] = p[e];
+        const double dv = (ra1[e] + ra0[e]) / 2.0;
+        const double v1 = s0[XV_V + e] + (dv + pp.g[e]) * dt;
+        s1[XV_V + e] = v1;
+        s1[XV_P + e] = s0[XV_P + e] + (v1 + s0[XV_V + e]) / 2.0 * dt;
       }
+      for (int e = 0; e < 4; ++e) s1[XV_Q + e] = q1[e];
     }
-  }
-  __syncthreads();
-  for (int k = 1 + t; k <= n_steps; k += blockDim.x) {
-    double* s1 = xv + (size_t)((start + k) % NS) * LX;
-    for (int e = 0; e < 3; ++e) { s1[XV_V + e] = vs[k][e]; s1[XV_P + e] = ps[k][e]; }
-    for (int e = 0; e < 4; ++e) s1[XV_Q + e] = qs[k][e];
   }
   __syncthreads();
   if (t < n_steps) {
