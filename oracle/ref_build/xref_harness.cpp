@@ -270,6 +270,31 @@ int xref_sm_info(void* h, int* n_poses, int* n_features, int* anchors) {
   return 0;
 }
 
+// StateManager bookkeeping (n_poses_, n_features_, anchor_idxs_, stateHasBeenFilledBefore_) set directly, so that an
+// update can start from a prior produced elsewhere (e.g. downloaded from the device).
+int xref_sm_set(void* h, int n_poses, int n_features, const int* anchors, int filled_before) {
+  VIO& v = *static_cast<VIO*>(h);
+  StateManager& sm = v.sm();
+  sm.n_poses_ = n_poses;
+  sm.n_features_ = size_t(n_features);
+  for (size_t i = 0; i < sm.anchor_idxs_.size(); ++i) sm.anchor_idxs_[i] = anchors[i];
+  sm.stateHasBeenFilledBefore_ = filled_before != 0;
+  return 0;
+}
+
+// Updater::update (updater.cpp:39-115) on a caller-provided state with the measurement set by xref_set_measurement.
+int xref_updater_update(void* h, double* xvec, double* cov_rm, double* seconds) {
+  VIO& v = *static_cast<VIO*>(h);
+  State s = state_from(xvec, cov_rm, v.M, v.F);
+  const auto t0 = std::chrono::steady_clock::now();
+  v.updater.update(s);
+  const auto t1 = std::chrono::steady_clock::now();
+  if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+  state_to(s, xvec, v.M, v.F);
+  cov_to(s.getCovariance(), cov_rm);
+  return 0;
+}
+
 // ---- stage-level entry points (methods VioUpdater / Updater keep protected; VIO is a friend) ----------------
 
 // Updater::applyUpdate (updater.cpp:117-141) on a caller-provided state: H (m x N), res (m), R diagonal (m),

@@ -57,6 +57,8 @@ def load(flavour="single"):
     lib.xref_qr_compress.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, _dp, _dp]
     lib.xref_manage.argtypes = [C.c_void_p, _dp, _dp, _ip, C.c_int]
     lib.xref_propagate.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp]
+    lib.xref_sm_set.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, C.c_int]
+    lib.xref_updater_update.argtypes = [C.c_void_p, _dp, _dp, _dp]
     lib.xref_msckf_rows.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, _ip, _dp, _dp, _dp, C.c_int]
     _LIBS[flavour] = lib
     return lib
@@ -201,6 +203,20 @@ class RefFilter:
         self.lib.xref_sm_info(self.h, C.byref(n_p), C.byref(n_f), an.ctypes.data_as(_ip))
         return n_p.value, n_f.value, an[:self.F].tolist()
 
+    def sm_set(self, n_poses, n_features, anchor_idxs, filled_before):
+        a = np.full(max(self.F, 1), -1, dtype=np.int32)
+        a[:len(anchor_idxs)] = anchor_idxs
+        self.lib.xref_sm_set(self.h, int(n_poses), int(n_features), a.ctypes.data_as(_ip), int(filled_before))
+
+    def updater_update(self, xs):
+        """Updater::update (updater.cpp:39-115) on a copy of `xs` with the measurement set by set_measurement()."""
+        x = np.ascontiguousarray(xs.x, dtype=np.float64).copy()
+        cov = np.ascontiguousarray(xs.cov, dtype=np.float64).copy()
+        sec = C.c_double(0.0)
+        self.lib.xref_updater_update(self.h, _d(x), _d(cov), C.cast(C.byref(sec), _dp))
+        self.last_seconds = sec.value
+        return RefState(self.M, self.F, x, cov)
+
     # ---- stage level ---------------------------------------------------------------------------------------
     def apply_update(self, xs, H, res, r_diag, correction_total, cov_update=True):
         """Updater::applyUpdate (updater.cpp:117-141) on a copy of `xs`; returns (state, correction_total)."""
@@ -252,3 +268,72 @@ class RefFilter:
         if rows < 0:
             raise RuntimeError(f"xref_msckf_rows failed ({rows})")
         return J[:rows].copy(), r[:rows].copy()
+
+
+# ---- MULTI_UAV flavour (libxref_multi.so) ----------------------------------------------------------------------
+class _XrefPeer(C.Structure):
+    _fields_ = [("M", C.c_int), ("F", C.c_int), ("dynamic", _dp), ("positions", _dp), ("orientations", _dp),
+                ("features", _dp), ("anchors", _ip), ("cov_rm", _dp)]
+
+
+def _peers(peers, keep):
+    """peers: objects with positions (3M), orientations (4M), features (3F), anchor_idxs, cov (x::SimpleState)."""
+    arr = (_XrefPeer * max(1, len(peers)))()
+    for i, p in enumerate(peers):
+        pos = np.ascontiguousarray(p.positions, dtype=np.float64)
+        ori = np.ascontiguousarray(p.orientations, dtype=np.float64)
+        fe = np.ascontiguousarray(p.features, dtype=np.float64)
+        cov = np.ascontiguousarray(p.cov, dtype=np.float64)
+        an = np.ascontiguousarray(list(p.anchor_idxs) + [0], dtype=np.int32)
+        dyn = np.zeros(16)
+        keep += [pos, ori, fe, cov, an, dyn]
+        arr[i].M, arr[i].F = pos.size // 3, fe.size // 3
+        arr[i].dynamic, arr[i].positions, arr[i].orientations = _d(dyn), _d(pos), _d(ori)
+        arr[i].features, arr[i].anchors, arr[i].cov_rm = _d(fe), an.ctypes.data_as(_ip), _d(cov)
+    return arr
+
+
+MSCKF_ID0, SHORT_ID0 = 1000001, 2000001   # Track ids RefFilter.set_measurement(ids={}) gives the two MSCKF lists
+
+
+class RefFilterMulti(RefFilter):
+    """The -DMULTI_UAV build of the reference (Updater::update with CI lists, Ekf::processOthersMeasurement)."""
+
+    def __init__(self, M, F, **kw):
+        kw.setdefault("flavour", "multi")
+        super().__init__(M, F, **kw)
+        lib = self.lib
+        lib.xref_set_msckf_matches.argtypes = [C.c_void_p, C.POINTER(_XrefPeer), C.c_int, C.c_int, _ip, _up, _ip, _dp,
+                                               C.c_double]
+        lib.xref_process_others.argtypes = [C.c_void_p, C.c_double, C.POINTER(_XrefPeer), C.c_int, C.c_int, _ip, _ip,
+                                            _ip, _dp]
+
+    def set_measurement(self, m, ids=None):
+        super().set_measurement(m, ids={} if ids is None else ids)
+
+    def set_msckf_matches(self, peers, matches, timestamp=0.0):
+        """matches: (peer_idx, which, own_track_idx, received_track (L,2)) in list order (vision/types.h:83-100);
+        which = 0 -> msckf_trks, 1 -> msckf_short_trks of the measurement set with set_measurement()."""
+        keep = []
+        cp = _peers(peers, keep)
+        peer_of = np.ascontiguousarray([m[0] for m in matches], dtype=np.int32)
+        own = np.ascontiguousarray([(MSCKF_ID0 if m[1] == 0 else SHORT_ID0) + m[2] for m in matches], dtype=np.uint64)
+        off, obs = _csr([m[3] for m in matches])
+        self.lib.xref_set_msckf_matches(self.h, cp, len(peers), len(matches), peer_of.ctypes.data_as(_ip),
+                                        own.ctypes.data_as(_up), off.ctypes.data_as(_ip), _d(obs), float(timestamp))
+
+    def process_others_measurement(self, t, peers, matches, want_state=True):
+        """Ekf::processOthersMeasurement (ekf.cpp:143-176); matches: (peer_idx, current_feature_id, received_id)."""
+        keep = []
+        cp = _peers(peers, keep)
+        pe = np.ascontiguousarray([m[0] for m in matches], dtype=np.int32)
+        cu = np.ascontiguousarray([m[1] for m in matches], dtype=np.int32)
+        rc_ = np.ascontiguousarray([m[2] for m in matches], dtype=np.int32)
+        out = np.empty(self.LX)
+        rc = self.lib.xref_process_others(self.h, float(t), cp, len(peers), len(matches), pe.ctypes.data_as(_ip),
+                                          cu.ctypes.data_as(_ip), rc_.ctypes.data_as(_ip), _d(out))
+        if rc < 0:
+            raise RuntimeError("Ekf::processOthersMeasurement threw")
+        if rc == 0:
+            return None
+        return RefState(self.M, self.F, out) if want_state else True

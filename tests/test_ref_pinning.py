@@ -1,0 +1,294 @@
+"""Pins the numpy oracle (oracle/) to the reference ITSELF.
+
+The reference ships no tests or vectors, so the pin is its own code run here: the unmodified sources
+under /root/reference/src/x/{ekf,vio,vision} are compiled in place against stand-in headers for Eigen / OpenCV /
+Boost / NLopt (oracle/ref_build/) into oracle/_ref/libxref*.so.  Two layers:
+  * golden vectors (tests/golden/ref_sequences.npz, written by oracle/tools/make_ref_golden.py from that binary):
+    always checked, also where neither /root/reference nor oracle/_ref exists;
+  * the live binary, when present: sequences in both build flavours and the stage-level methods
+    (applyUpdate, applyQRDecomposition, StateManager::manage, Propagator, MsckfUpdate).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import refcpp
+from oracle.updater import apply_qr_decomposition, apply_update
+from oracle_driver import OracleFilter, to_oracle_meas, to_oracle_state
+from ref_scenarios import SCENARIOS, events, oracle_xvec
+from x_multi_agent_b200.filter import State
+from x_multi_agent_b200.synth import Scenario, SynthConfig, record, replay
+
+GOLD = Path(__file__).resolve().parent / "golden" / "ref_sequences.npz"
+TOL_X, TOL_P = 1e-10, 1e-10     # fp64 round-off only: summation order of numpy/LAPACK vs the compiled loops
+
+need_ref = pytest.mark.skipif(not refcpp.available("single"), reason="oracle/_ref/libxref.so not built")
+need_ref_multi = pytest.mark.skipif(not refcpp.available("multi"), reason="oracle/_ref/libxref_multi.so not built")
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def _run_oracle(name):
+    cfg, ev, iekf = events(name)
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64, iekf_iter=iekf)
+    xs = []
+    replay(ev, ora, lambda k, m, st: xs.append(oracle_xvec(st, cfg.M, cfg.F)))
+    return cfg, ora, np.vstack(xs)
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_oracle_matches_reference_golden_sequences(name):
+    """Every update's returned state and the final re-propagated state + covariance of the numpy oracle equal what
+    the compiled reference produced (Ekf::processImu / processUpdateMeasurement, ekf.cpp:66-255)."""
+    g = np.load(GOLD)
+    cfg, ora, xs = _run_oracle(name)
+    ref_xs = g[f"{name}/updates"]
+    assert xs.shape == ref_xs.shape
+    assert np.abs(xs - ref_xs).max() < TOL_X
+    n = ora.newest()
+    assert np.abs(oracle_xvec(n, cfg.M, cfg.F) - g[f"{name}/newest_x"]).max() < TOL_X
+    P = g[f"{name}/newest_cov"]
+    assert _rel(n.cov, P) < TOL_P
+    # the asymmetry of the reference's covariance (not symmetrised between updates) is reproduced, not averaged away
+    A_ref, A_ora = P - P.T, n.cov - n.cov.T
+    assert np.abs(A_ref).max() > 1e-6 and np.abs(A_ref - A_ora).max() < 1e-12
+    sm = g[f"{name}/sm"]
+    assert (ora.upd.sm.n_poses, ora.upd.sm.n_features) == (sm[0], sm[1])
+    assert list(ora.upd.sm.anchor_idxs) == list(sm[2:])
+
+
+@need_ref
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_compiled_reference_reproduces_its_golden_vectors(name):
+    g = np.load(GOLD)
+    cfg, ev, iekf = events(name)
+    ref = refcpp.RefFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64, iekf_iter=iekf)
+    xs = []
+    replay(ev, ref, lambda k, m, st: xs.append(st.x.copy()))
+    assert np.abs(np.vstack(xs) - g[f"{name}/updates"]).max() < 1e-12
+    assert _rel(ref.newest().cov, g[f"{name}/newest_cov"]) < 1e-12
+
+
+@need_ref
+def test_oracle_matches_compiled_reference_on_a_fresh_seed():
+    """Not in the golden file: a seed drawn here, so the oracle cannot have been tuned to the fixture."""
+    cfg = SynthConfig(M=7, F=5, K=9, seed=12345, n_short=2, churn=1)
+    ev = record(Scenario(cfg), 15)
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    ref = refcpp.RefFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    xo, xr = [], []
+    replay(ev, ora, lambda k, m, st: xo.append(oracle_xvec(st, cfg.M, cfg.F)))
+    replay(ev, ref, lambda k, m, st: xr.append(st.x.copy()))
+    assert np.abs(np.vstack(xo) - np.vstack(xr)).max() < TOL_X
+    assert _rel(ora.newest().cov, ref.newest().cov) < TOL_P
+    assert ref.sm_info()[2] == list(ora.upd.sm.anchor_idxs)
+
+
+def _prior(cfg, frames):
+    """A mid-sequence update state (window full, features initialised) from the oracle."""
+    ev = record(Scenario(cfg), frames)
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    replay(ev, ora)
+    return ora, State.from_oracle(ora.newest())
+
+
+@need_ref
+def test_apply_update_and_qr_compression_match_compiled_reference():
+    """Updater::applyUpdate (updater.cpp:117-141) and VioUpdater::applyQRDecomposition (vio_updater.cpp:487-512)."""
+    cfg = SynthConfig(M=6, F=6, K=12, seed=4)
+    ora, xs = _prior(cfg, 9)
+    N = xs.n_error_states()
+    rng = np.random.default_rng(0)
+    ref = refcpp.RefFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img)
+    m = 2 * N + 7
+    H = rng.normal(size=(m, N)) * (rng.uniform(size=(m, N)) < 0.3)
+    res = rng.normal(size=m) * 1e-2
+    rd = np.full(m, cfg.sigma_img ** 2)
+    # QR compression: R and Q^T r are unique up to row signs -> compare the invariants R^T R, R^T z and |R| itself
+    Hq_r, rq_r = ref.qr_compress(H, res)
+    Hq_o, rq_o, Rq_o = apply_qr_decomposition(H.copy(), res.copy(), rd.copy(), cfg.sigma_img)
+    assert Hq_r.shape == Hq_o.shape == (N, N)
+    assert _rel(Hq_r.T @ Hq_r, Hq_o.T @ Hq_o) < 1e-12 and _rel(Hq_r.T @ rq_r, Hq_o.T @ rq_o) < 1e-12
+    assert _rel(np.abs(Hq_r), np.abs(Hq_o)) < 1e-10
+    # dense update with an unsymmetric prior (as left by propagation), IEKF-style correction_total; a measurement
+    # with a well-conditioned innovation covariance (the explicit S.inverse() of updater.cpp:125 amplifies round-off
+    # by cond(S), identically in both implementations but not bit for bit)
+    mu = 40
+    Hu = rng.normal(size=(mu, N)) * (rng.uniform(size=(mu, N)) < 0.3)
+    ru = rng.normal(size=mu) * 1e-2
+    Ru = np.full(mu, 1e-3)
+    so = to_oracle_state(xs)
+    ct = rng.normal(size=N) * 1e-3
+    ct_o = ct.copy()
+    apply_update(so, Hu, ru, np.diag(Ru), ct_o, True)
+    sr, ct_r = ref.apply_update(xs, Hu, ru, Ru, ct, True)
+    assert np.abs(oracle_xvec(so, cfg.M, cfg.F)[:16] - sr.x[:16]).max() < 1e-10
+    assert np.abs(ct_o - ct_r).max() < 1e-10
+    assert _rel(so.cov, sr.cov) < 1e-10
+    assert np.abs(sr.cov - sr.cov.T).max() == 0.0      # applyUpdate symmetrises (updater.cpp:133)
+
+
+@need_ref
+def test_propagation_and_manage_match_compiled_reference():
+    """Propagator (propagator.cpp:30-205) and StateManager::manage (state_manager.cpp:31-149), incl. the
+    unsymmetric P_ii and P_vi != P_iv^T the reference carries between updates."""
+    cfg = SynthConfig(M=6, F=6, K=12, seed=6, churn=1)
+    ora, xs = _prior(cfg, 10)
+    ref = refcpp.RefFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img)
+    so = to_oracle_state(xs)
+    prop = oracle.Propagator()
+    w1, a1 = np.array([0.02, -0.01, 0.03]), np.array([0.1, -0.2, 9.7])
+    s1 = so.copy()
+    s1.set_imu(so.time + 0.005, so.seq + 1, w1, a1)
+    prop.propagate_state(so, s1)
+    prop.propagate_covariance(so, s1)
+    r1 = ref.propagate(xs, so.time + 0.005, w1, a1)
+    assert np.abs(oracle_xvec(s1, cfg.M, cfg.F)[:16] - r1.x[:16]).max() < 1e-13
+    assert _rel(s1.cov, r1.cov) < 1e-13
+    assert np.abs(r1.cov - r1.cov.T).max() > 0.0
+    # manage from the propagated (unsymmetric) state: window full -> re-anchor + slide + clone, one lost feature
+    sm = ora.upd.sm
+    ref.sm_set(sm.n_poses, sm.n_features, sm.anchor_idxs, sm.filled_before)
+    x1 = State(cfg.M, cfg.F, oracle_xvec(s1, cfg.M, cfg.F))
+    x1.cov = s1.cov.copy()
+    rm = ref.manage(x1, lost=[1])
+    sm.manage(s1, [1])
+    assert np.abs(oracle_xvec(s1, cfg.M, cfg.F) - rm.x)[32:].max() < 1e-12
+    assert _rel(s1.cov, rm.cov) < 1e-12
+    assert ref.sm_info() == (sm.n_poses, sm.n_features, list(sm.anchor_idxs))
+
+
+@need_ref
+def test_msckf_rows_match_compiled_reference():
+    """MsckfUpdate (msckf_update.cpp:27-63,306-492): same inlier rows up to the nullspace basis -> J^T J and J^T r."""
+    cfg = SynthConfig(M=6, F=6, K=20, seed=8)
+    scn = Scenario(cfg)
+    ev = record(scn, 9)
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    replay(ev[:-1], ora)
+    m = ev[-1][1]
+    s = ora.ekf.buf.states[ora.ekf.buf.closest_idx(m.timestamp)].copy()
+    sm = ora.upd.sm
+    sm.manage(s, list(m.lost_slam_trk_idxs))
+    ref = refcpp.RefFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img)
+    ref.sm_set(sm.n_poses, sm.n_features, sm.anchor_idxs, sm.filled_before)
+    xs = State.from_oracle(s)
+    Jr, rr = ref.msckf_rows(xs, m.msckf_trks, m.timestamp)
+    mo = oracle.MsckfUpdate(m.msckf_trks, sm.camera_attitudes(s), sm.camera_positions(s), s.cov, cfg.M, cfg.sigma_img)
+    rows = int(mo.inlier.sum()) * (2 * cfg.M - 3)
+    assert Jr.shape[0] == rows and 0 < mo.inlier.sum() < len(m.msckf_trks)
+    Jo, ro = mo.jac[:rows], mo.res[:rows]
+    assert _rel(Jr.T @ Jr, Jo.T @ Jo) < 1e-9 and _rel(Jr.T @ rr, Jo.T @ ro) < 1e-9
+
+
+# ---- MULTI_UAV build flavour ------------------------------------------------------------------------------------
+def _peer_snapshot(cfg, seed, frames, phase_shift):
+    from oracle.ci import SimpleState
+    from x_multi_agent_b200 import PeerState
+    scn = Scenario(SynthConfig(M=cfg.M, F=cfg.F, K=cfg.K, seed=seed))
+    scn.phase = scn.phase + phase_shift
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    replay(record(scn, frames), ora)
+    s = ora.newest()
+    window = list(range(frames - cfg.M, frames))
+    so = SimpleState(s.dynamic_states(), s.p_array.copy(), s.q_array.copy(), s.f_array.copy(), s.cov.copy(),
+                     list(ora.upd.sm.anchor_idxs))
+    sd = PeerState(s.p_array, s.q_array, s.f_array, list(ora.upd.sm.anchor_idxs), s.cov)
+    return scn, window, so, sd
+
+
+@need_ref_multi
+def test_multi_uav_update_matches_compiled_reference():
+    """Updater::update as compiled with -DMULTI_UAV (updater.cpp:39-115) incl. the multi-agent MSCKF block and its
+    match-erase loop (msckf_update.cpp:88-139,175-279), k-agent fuseCI (ci.cpp:49-92) and applyCI (updater.cpp:144-161),
+    through Ekf::processUpdateMeasurement."""
+    from oracle.ci import MsckfMatch
+    cfg, frames, w = SynthConfig(M=6, F=4, K=14, seed=7, n_short=3), 9, 0.1
+    scn = Scenario(cfg)
+    ev = record(scn, frames)
+    last_upd = max(i for i, e in enumerate(ev) if e[0] == "update")
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    ora.upd.update = ora.upd.update_multi_uav
+    ora.upd.ci_msckf_w = w
+    ref = refcpp.RefFilterMulti(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64, ci_msckf_w=w, ci_slam_w=w,
+                                sigma_landmark=0.3)
+    replay(ev[:last_upd], ora)
+    replay(ev[:last_upd], ref)
+    assert _rel(ora.newest().cov, ref.newest().cov) < TOL_P
+    m = ev[last_upd][1]
+    peers = [_peer_snapshot(cfg, 31, frames, 0.25), _peer_snapshot(cfg, 32, frames, -0.2)]
+    lms, short_lms = scn.last_msckf_lms, scn.last_short_lms
+
+    def peer_track(p, lm, L):
+        pscn, window, _, _ = peers[p]
+        return pscn._project(lm, window[len(window) - L:])
+
+    M = cfg.M
+    spec = [(0, 0, 1, lms[1], M), (1, 0, 1, lms[1], M - 2), (0, 0, 3, lms[3], 3), (1, 0, 4, lms[4], M),
+            (0, 0, 6, lms[6], M - 1), (1, 0, 8, lms[9], M), (0, 1, 0, short_lms[0], 4), (1, 1, 2, short_lms[2], M),
+            (0, 0, 10, lms[10], M), (1, 0, 10, lms[10], M)]
+    tracks = [peer_track(p, lm, L) for p, _, _, lm, L in spec]
+    ora.upd.set_measurement(to_oracle_meas(m))
+    ora.upd.msckf_matches = [MsckfMatch(peers[p][2], (which, trk), z) for (p, which, trk, _, _), z in zip(spec, tracks)]
+    so = ora.ekf.process_update_measurement()
+    ref.set_measurement(m)
+    ref.set_msckf_matches([p[3] for p in peers], [(p, which, trk, z) for (p, which, trk, _, _), z in zip(spec, tracks)],
+                          m.timestamp)
+    sr = ref.process_update_measurement()
+    ms = ora.upd.last["msckf"]
+    n_inl = sum(1 for j in ms.multi_gate if ms.multi_gate[j][0] < ms.multi_gate[j][1])
+    assert 0 < n_inl < len(ms.multi_gate), "scenario must contain accepted and rejected joint updates"
+    assert ms.n_matched[10] == 1, "tail-of-list quirk of the erase loop"
+    assert np.abs(oracle_xvec(so, cfg.M, cfg.F) - sr.x).max() < TOL_X
+    assert _rel(so.cov, ref.get_state(-2).cov) < TOL_P
+    assert _rel(ora.newest().cov, ref.newest().cov) < TOL_P
+
+
+@need_ref_multi
+def test_slam_slam_ci_matches_compiled_reference():
+    """Ekf::processOthersMeasurement -> Updater::collaborativeUpdate -> MultiSlamUpdate + pair fuseCI + applyCI
+    (ekf.cpp:143-176, updater.cpp:22-36,144-161, multi_slam_update.cpp:61-246, ci.cpp:94-127), fixed weight."""
+    from oracle.ci import MultiSlamUpdate, SimpleState, SlamMatch
+    from oracle.updater import apply_ci
+    from x_multi_agent_b200 import PeerState
+    agents = []
+    for a in range(2):
+        cfg = SynthConfig(M=6, F=6, K=10, seed=11)
+        scn = Scenario(cfg)
+        scn.phase = scn.phase + 0.3 * a
+        scn.rng = np.random.Generator(np.random.PCG64(100 + a))
+        ev = record(scn, 8)
+        ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+        ora.upd.update = ora.upd.update_multi_uav
+        replay(ev, ora)
+        agents.append((cfg, ev, ora))
+    (cfg, ev0, ora0), (_, _, ora1) = agents
+    sigma_lm, w = 0.3, 0.1
+    ref0 = refcpp.RefFilterMulti(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64, ci_msckf_w=w, ci_slam_w=w,
+                                 sigma_landmark=sigma_lm)
+    replay(ev0, ref0)
+    s1 = ora1.newest()
+    peer_o = SimpleState(s1.dynamic_states(), s1.p_array.copy(), s1.q_array.copy(), s1.f_array.copy(), s1.cov.copy(),
+                         list(ora1.upd.sm.anchor_idxs))
+    peer_d = PeerState(s1.p_array, s1.q_array, s1.f_array, list(ora1.upd.sm.anchor_idxs), s1.cov)
+    matches = [(0, f, f) for f in range(cfg.F)] + [(0, 2, 4)]
+    t = ora0.newest().time - 0.02
+    info = {}
+
+    def collab(state):
+        sm = ora0.upd.sm
+        msu = MultiSlamUpdate(sm.camera_attitudes(state), sm.camera_positions(state), state.f_array, sm.anchor_idxs,
+                              state.cov, cfg.M, sigma_lm, [SlamMatch(peer_o, c, r) for _, c, r in matches], w)
+        info["inl"] = list(msu.inlier)
+        for Pj, H, res, S in zip(msu.P_list, msu.H_list, msu.res_list, msu.S_list):
+            apply_ci(state, Pj, H, res, S)
+
+    so = ora0.ekf.process_others_measurement(t, collab)
+    sr = ref0.process_others_measurement(t, [peer_d], matches)
+    assert sum(info["inl"]) >= 3 and not info["inl"][-1]
+    assert np.abs(oracle_xvec(so, cfg.M, cfg.F) - sr.x).max() < TOL_X
+    assert _rel(ora0.newest().cov, ref0.newest().cov) < TOL_P
