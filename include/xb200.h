@@ -78,6 +78,13 @@ typedef struct xb_config {
   int downdate_precision; /* 0 = fp64 CUDA cores, 1 = 3xTF32 tcgen05 tensor-core downdate */
   int multi_uav;          /* 1 = Updater::update as compiled with -DMULTI_UAV (updater.cpp:58-97): CI lists of the
                            * MSCKF-MSCKF matches first, one applyUpdate, no IEKF loop; 0 = single-UAV build */
+  int oc_projection;      /* 1 (default) = the reference's observability-constrained projection of the MSCKF pose
+                           * Jacobians exactly as written (msckf_update.cpp:393-406); 0 = plain Jacobians.  Not a
+                           * reference option: as written the projection removes real information (u_pos = C(q) g
+                           * nulls the vertical position column of every observation) and the filter loses
+                           * consistency within seconds on synthetic data (tests/test_cpu.py,
+                           * test_oc_projection_as_written_breaks_consistency); 0 exists so that a benchmark can run
+                           * the path on a consistent filter.  The oracle has the same switch. */
 } xb_config;
 
 /* One track list in CSR form: track t owns observations [off[t], off[t+1]) of `obs`, each

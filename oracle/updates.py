@@ -13,6 +13,10 @@ from .state_manager import _mat_ivd
 from .triangulation import Triangulation
 
 G_OC = np.array([0.0, 0.0, -9.81])  # hard-coded in the OC projection, msckf_update.cpp:393
+# Mirror of xb_config.oc_projection (include/xb200.h).  True = the reference as written.  False is NOT a reference
+# option: it exists so that the benchmark can run the path on a consistent filter; the device has the
+# same switch and the two are always set together.
+OC_PROJECTION = True
 
 
 def chi2_quantile(p, dof):
@@ -55,10 +59,11 @@ def msckf_track_jacobians(track, quats, poss, n_poses_max, n_cols, G_p_fj):
         J_pos = -J_i @ R.T
         J_att = J_i @ skew(cp)
         # Observability-constrained projection (Hesch 2012), msckf_update.cpp:393-406
-        u_pos = (R @ G_OC)[:, None]
-        J_pos = J_pos - J_pos @ u_pos @ np.linalg.inv(u_pos.T @ u_pos) @ u_pos.T
-        u_att = (skew(G_p_fj - p_c) @ G_OC)[:, None]
-        J_att = J_att - J_att @ u_att @ np.linalg.inv(u_att.T @ u_att) @ u_att.T
+        if OC_PROJECTION:
+            u_pos = (R @ G_OC)[:, None]
+            J_pos = J_pos - J_pos @ u_pos @ np.linalg.inv(u_pos.T @ u_pos) @ u_pos.T
+            u_att = (skew(G_p_fj - p_c) @ G_OC)[:, None]
+            J_att = J_att - J_att @ u_att @ np.linalg.inv(u_att.T @ u_att) @ u_att.T
         Hf[2 * i:2 * i + 2] = -J_pos
         c = K_CORE + pos * 3
         jac[2 * i:2 * i + 2, c:c + 3] = J_pos

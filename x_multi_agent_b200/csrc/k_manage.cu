@@ -131,37 +131,43 @@ __global__ void __launch_bounds__(128) k_manage_prep(ManageDev md, double* __res
 // virtual form directly saves the assemble pass (one 5 MB read + write at cfg-2) at the head of every update.
 struct PSrc {
   const double* P;      // materialised matrix, or nullptr
-  const double* strip;  // 15 x N
+  const double* strip;  // 15 x N: [P_ii | P_iv]
+  const double* strip2; // 15 x N: P_vi^T; == strip for a slot whose P_vi equals P_iv^T (every slot written by an update
+                        // that symmetrised); differs after updates without measurement rows (propagator.cpp:197-203)
   const double* gen;    // N x N (only rows/cols >= 15 are read)
   int N;
   __device__ __forceinline__ double at(int r, int c) const {
     if (P) return P[(size_t)r * N + c];
     if (r < XB_CORE) return strip[(size_t)r * N + c];
-    if (c < XB_CORE) return strip[(size_t)c * N + r];
+    if (c < XB_CORE) return strip2[(size_t)c * N + r];
     return gen[(size_t)r * N + c];
   }
 };
 
-// T[ci][b] = sum_e val_e * P[col_e][b]   and   T2[ci][r] = sum_e P[r][col_e] * val_e  (r < 15)
+// T[ci][b] = sum_e val_e * P[col_e][b]   and   T2[ci][r] = sum_e P[r][col_e] * val_e
+// The column-side products T2 are needed wherever P[r][col] != P[col][r]: for the core rows (r < 15) always, for every
+// row when the source covariance is unsymmetric beyond the core block (`general`: the previous updates applied no
+// measurement, state_manager.cpp:273-349 then copies unsymmetric blocks from clone to clone).
 __global__ void k_manage_T(int N, int n_comp, const int* __restrict__ ccols, const double* __restrict__ cvals, PSrc P,
-                           double* __restrict__ T, double* __restrict__ T2) {
+                           double* __restrict__ T, double* __restrict__ T2, int general) {
   const int ci = blockIdx.y;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= n_comp || b >= N) return;
+  const bool col_side = general || b < XB_CORE;
   double s = 0.0, s2 = 0.0;
   for (int e = 0; e < 15; ++e) {
     const int col = ccols[ci * 15 + e];
     const double v = cvals[ci * 15 + e];
     s = fma(v, P.at(col, b), s);
-    if (b < XB_CORE) s2 = fma(P.at(b, col), v, s2);
+    if (col_side) s2 = fma(P.at(b, col), v, s2);
   }
   T[(size_t)ci * N + b] = s;
-  if (b < XB_CORE) T2[ci * XB_CORE + b] = s2;
+  if (col_side) T2[(size_t)ci * N + b] = s2;
 }
 
 __global__ void __launch_bounds__(256) k_manage_apply(int N, const int* __restrict__ rowmap, const int* __restrict__ ccols,
                                                        const double* __restrict__ cvals, PSrc P, const double* __restrict__ T,
-                                                       const double* __restrict__ T2, double* __restrict__ Pn) {
+                                                       const double* __restrict__ T2, double* __restrict__ Pn, int general) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
   if (j >= N) return;
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(256) k_manage_apply(int N, const int* __restri
     } else if (mi <= -2 && mj >= 0) {
       v = T[(size_t)(-2 - mi) * N + mj];
     } else if (mi >= 0 && mj <= -2) {
-      v = (mi < XB_CORE) ? T2[(-2 - mj) * XB_CORE + mi] : T[(size_t)(-2 - mj) * N + mi];
+      v = (general || mi < XB_CORE) ? T2[(size_t)(-2 - mj) * N + mi] : T[(size_t)(-2 - mj) * N + mi];
     } else {
       const int ci = -2 - mi, cj = -2 - mj;
       for (int e = 0; e < 15; ++e) v = fma(T[(size_t)ci * N + ccols[cj * 15 + e]], cvals[cj * 15 + e], v);
@@ -191,33 +197,44 @@ __global__ void __launch_bounds__(256) k_manage_apply(int N, const int* __restri
 void launch_manage_dev(cudaStream_t s, int M, int F, int N, int n_poses, int n_features, int slide, int n_reanch,
                        const int* d_feat_src, const int* d_reanch, const int* d_rowmap, const int* d_ccols,
                        double* d_cvals, double* d_scratch, double* xv, const double* Pold, double* Pnew, double* Tm,
-                       double* T2, const double* strip, const double* gen) {
+                       double* T2, const double* strip, const double* gen, const double* strip2, int general) {
   ManageDev md{M, F, N, n_poses, n_features, slide, n_reanch, d_feat_src, d_reanch, d_cvals, d_scratch};
   k_manage_prep<<<1, 128, 0, s>>>(md, xv);
   count_launch();
-  const PSrc src{Pold, strip, gen, N};  // Pold == nullptr: read the slot's strip + generation directly
+  const PSrc src{Pold, strip, strip2 ? strip2 : strip, gen, N};  // Pold == nullptr: read the slot's strips + generation directly
   const int n_comp = 6 + 3 * n_reanch;
   dim3 gt((N + 127) / 128, n_comp);
-  k_manage_T<<<gt, 128, 0, s>>>(N, n_comp, d_ccols, d_cvals, src, Tm, T2);
+  k_manage_T<<<gt, 128, 0, s>>>(N, n_comp, d_ccols, d_cvals, src, Tm, T2, general);
   count_launch();
   dim3 ga((N + 31) / 32, (N + 31) / 32);
-  k_manage_apply<<<ga, 256, 0, s>>>(N, d_rowmap, d_ccols, d_cvals, src, Tm, T2, Pnew);
+  k_manage_apply<<<ga, 256, 0, s>>>(N, d_rowmap, d_ccols, d_cvals, src, Tm, T2, Pnew, general);
   count_launch();
 }
 
 // ---- assemble / extract: strip <-> full covariance ------------------------------------------------
-__global__ void k_assemble(int N, const double* __restrict__ strip, const double* __restrict__ Pg, double* __restrict__ Pw) {
+__global__ void k_assemble(int N, const double* __restrict__ strip, const double* __restrict__ strip2,
+                           const double* __restrict__ Pg, double* __restrict__ Pw) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (j >= N) return;
   double v;
   if (i < XB_CORE) v = strip[(size_t)i * N + j];
-  else if (j < XB_CORE) v = strip[(size_t)j * N + i];  // P_vi = P_iv^T
+  else if (j < XB_CORE) v = strip2[(size_t)j * N + i];  // P_vi (strip2 == strip when P_vi = P_iv^T)
   else v = Pg[(size_t)i * N + j];
   Pw[(size_t)i * N + j] = v;
 }
-void launch_assemble(cudaStream_t s, int N, const double* strip, const double* Pgen, double* Pwork) {
+void launch_assemble(cudaStream_t s, int N, const double* strip, const double* Pgen, double* Pwork, const double* strip2) {
   dim3 g((N + 255) / 256, N);
-  k_assemble<<<g, 256, 0, s>>>(N, strip, Pgen, Pwork);
+  k_assemble<<<g, 256, 0, s>>>(N, strip, strip2 ? strip2 : strip, Pgen, Pwork);
+  count_launch();
+}
+// strip2[r][j] = Pwork[j][r]: the first 15 columns of the work covariance, stored like the row strip
+__global__ void k_extract_cols(int N, const double* __restrict__ Pw, double* __restrict__ strip2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (j < N) strip2[(size_t)r * N + j] = Pw[(size_t)j * N + r];
+}
+void launch_extract_strip2(cudaStream_t s, int N, const double* Pwork, double* strip2) {
+  dim3 g((N + 255) / 256, XB_CORE);
+  k_extract_cols<<<g, 256, 0, s>>>(N, Pwork, strip2);
   count_launch();
 }
 void launch_extract_strip(cudaStream_t s, int N, const double* Pwork, double* strip) {

@@ -293,20 +293,22 @@ __global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
       xb_skew(cp, sk);
       xb_mm23(Ji, sk, Jatt);
       // observability-constrained projection (msckf_update.cpp:393-406), g hard-coded
-      const double gv[3] = {0.0, 0.0, -9.81};
-      double u[3], t2[2];
-      xb_mv33(R, gv, u);
-      double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
-      for (int r = 0; r < 2; ++r) t2[r] = (Jpos[r * 3] * u[0] + Jpos[r * 3 + 1] * u[1] + Jpos[r * 3 + 2] * u[2]) * (1.0 / uu);
-      for (int r = 0; r < 2; ++r)
-        for (int c = 0; c < 3; ++c) Jpos[r * 3 + c] -= t2[r] * u[c];
-      double skd[9];
-      xb_skew(dG, skd);
-      xb_mv33(skd, gv, u);
-      uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
-      for (int r = 0; r < 2; ++r) t2[r] = (Jatt[r * 3] * u[0] + Jatt[r * 3 + 1] * u[1] + Jatt[r * 3 + 2] * u[2]) * (1.0 / uu);
-      for (int r = 0; r < 2; ++r)
-        for (int c = 0; c < 3; ++c) Jatt[r * 3 + c] -= t2[r] * u[c];
+      if (mp.oc) {
+        const double gv[3] = {0.0, 0.0, -9.81};
+        double u[3], t2[2];
+        xb_mv33(R, gv, u);
+        double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+        for (int r = 0; r < 2; ++r) t2[r] = (Jpos[r * 3] * u[0] + Jpos[r * 3 + 1] * u[1] + Jpos[r * 3 + 2] * u[2]) * (1.0 / uu);
+        for (int r = 0; r < 2; ++r)
+          for (int c = 0; c < 3; ++c) Jpos[r * 3 + c] -= t2[r] * u[c];
+        double skd[9];
+        xb_skew(dG, skd);
+        xb_mv33(skd, gv, u);
+        uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+        for (int r = 0; r < 2; ++r) t2[r] = (Jatt[r * 3] * u[0] + Jatt[r * 3 + 1] * u[1] + Jatt[r * 3 + 2] * u[2]) * (1.0 / uu);
+        for (int r = 0; r < 2; ++r)
+          for (int c = 0; c < 3; ++c) Jatt[r * 3 + c] -= t2[r] * u[c];
+      }
       for (int q = 0; q < 6; ++q) { Jp[6 * i + q] = Jpos[q]; Ja[6 * i + q] = Jatt[q]; Hf[6 * i + q] = -Jpos[q]; U[6 * i + q] = -Jpos[q]; }
     }
     __syncwarp();

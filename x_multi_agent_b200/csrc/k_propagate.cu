@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(128) k_prop_means(double* __restrict__ xv, int
 }
 
 // Strip propagation: for every step k,  strip_k = [F P_ii F^T + Q | F P_iv]  (propagator.cpp:195-203).
+// second != 0: the same recurrence on the column strips P_vi^T (P_vi' = P_vi F^T, propagator.cpp:203), whose core block
+// is the transpose of P_ii and therefore takes Q_d^T.
 __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip, int N, int NS, int start, int n_steps,
-                                                     const double* __restrict__ FQ) {
+                                                     const double* __restrict__ FQ, int second) {
   __shared__ double Fs[225], Qs[225], Pii[225], Tm[225];
   const int t = threadIdx.x;
   const int j = blockIdx.x * blockDim.x + t;  // column
@@ -183,7 +185,10 @@ __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip,
     for (int e = t; e < 225; e += blockDim.x) Pii[e] = s0[(size_t)(e / 15) * N + (e % 15)];
   for (int k = 0; k < n_steps; ++k) {
     __syncthreads();
-    for (int e = t; e < 225; e += blockDim.x) { Fs[e] = FQ[(size_t)k * 450 + e]; Qs[e] = FQ[(size_t)k * 450 + 225 + e]; }
+    for (int e = t; e < 225; e += blockDim.x) {
+      Fs[e] = FQ[(size_t)k * 450 + e];
+      Qs[e] = FQ[(size_t)k * 450 + 225 + (second ? (e % 15) * 15 + e / 15 : e)];
+    }
     __syncthreads();
     double* s1 = strip + (size_t)((start + k + 1) % NS) * SS;
     if (j >= XB_CORE && j < N) {
@@ -224,9 +229,9 @@ void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, in
   k_prop_means<<<1, 128, 0, s>>>(xv, LX, NS, start, n_steps, in, pp, FQ);
   count_launch();
 }
-void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ) {
+void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ, int second) {
   if (n_steps <= 0) return;
-  k_prop_strips<<<(N + 127) / 128, 128, 0, s>>>(strip, N, NS, start, n_steps, FQ);
+  k_prop_strips<<<(N + 127) / 128, 128, 0, s>>>(strip, N, NS, start, n_steps, FQ, second);
   count_launch();
 }
 void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,

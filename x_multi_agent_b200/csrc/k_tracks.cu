@@ -302,7 +302,9 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     double* Jap = ws.Jap + 6 * i;
     double* Jaa = ws.Jaa + 6 * i;
     double* Hf = ws.Hf + 6 * i;
-    if (!slam_mode) {
+    if (!slam_mode && !tp.oc) {
+      for (int e = 0; e < 6; ++e) { Jp[e] = Jpos[e]; Ja[e] = Jatt[e]; Hf[e] = -Jpos[e]; }
+    } else if (!slam_mode) {
       // observability-constrained projection (msckf_update.cpp:393-406), g hard-coded
       const double g[3] = {0.0, 0.0, -9.81};
       double u[3], t2[2];
@@ -447,7 +449,9 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
           double T[12];
           const int rp = XB_CORE + 3 * pi_, ra = XB_CORE + 3 * M + 3 * pi_;
           const int cpn = XB_CORE + 3 * pk_, can = XB_CORE + 3 * M + 3 * pk_;
-          const bool symblk = pi_ == np - 1 && pk_ == np - 1;  // the newest clone's own block is not symmetric: use sym(P)
+          // blocks among the newest clones are not symmetric (one clone in the regular case, more after updates without
+          // measurement rows): use sym(P) there
+          const bool symblk = pi_ >= np - tp.asym_clones && pk_ >= np - tp.asym_clones;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             double tp0 = 0, tp1 = 0, ta0 = 0, ta1 = 0;

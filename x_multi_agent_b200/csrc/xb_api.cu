@@ -138,7 +138,14 @@ struct xb_filter {
   double* d_FQ2 = nullptr;     // F_d / Q_d of the re-propagation steps
   // ring buffer (state_buffer.cpp)
   double* d_xv = nullptr;      // NS x LX
-  double* d_strip = nullptr;   // NS x 15 x N
+  double* d_strip = nullptr;   // NS x 15 x N: [P_ii | P_iv]
+  double* d_strip2 = nullptr;  // NS x 15 x N: P_vi^T, maintained only for slots with slot_asym > 0
+  // Number of newest clones whose covariance blocks are unsymmetric in a slot (0: core block only, P_vi = P_iv^T).
+  // > 0 only after updates WITHOUT measurement rows: the reference then never symmetrises (updater.cpp:106) and carries
+  // P_vi != P_iv^T through propagation (propagator.cpp:197-203).
+  std::vector<int> slot_asym;
+  int asym_clones = 0;         // the same count for the work covariance
+  double* d_getcov = nullptr;  // scratch of xb_ekf_get_covariance (never a work buffer)
   std::vector<double> h_time;  // mirror of State::time_
   std::vector<double> h_am;    // mirror of a_m (accel-spike substitution, ekf.cpp:119-128)
   std::vector<int> slot_gen;
@@ -158,7 +165,7 @@ struct xb_filter {
   // generation.  xb_sm_manage (the first consumer in Ekf::processUpdateMeasurement unless a short-MSCKF update precedes it)
   // reads that form directly; every other consumer materialises it first (one assemble pass).
   bool virt = false;
-  const double *virt_strip = nullptr, *virt_gen = nullptr;
+  const double *virt_strip = nullptr, *virt_gen = nullptr, *virt_strip2 = nullptr;
   double* d_Pw = nullptr;   // points at WA or a generation
   double* d_corr = nullptr; // N correction_total
   double* d_delta = nullptr;
@@ -324,6 +331,7 @@ extern "C" void xb_default_config(xb_config* c) {
   c->ci_msckf_w = -1.0;
   c->ci_slam_w = -1.0;
   c->downdate_precision = 0;
+  c->oc_projection = 1;     // msckf_update.cpp:393-406 as written
 }
 
 extern "C" const char* xb_last_error(void) { return g_err.c_str(); }
@@ -381,6 +389,9 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
 
   DA(f->d_xv, (size_t)NS * LX, double);
   DA(f->d_strip, (size_t)NS * 15 * N, double);
+  DA(f->d_strip2, (size_t)NS * 15 * N, double);
+  DA(f->d_getcov, (size_t)N * N, double);
+  f->slot_asym.assign(NS, 0);
   DA(f->d_Pgen, (size_t)f->NG * N * N, double);
   DA(f->d_xw, LX, double);
   DA(f->d_WA, (size_t)N * N, double);
@@ -497,7 +508,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_cvals, 15 * (size_t)(6 + 3 * std::max(1, F)), double);
   DA(f->d_mscratch, 7 * (size_t)M + 3 * (size_t)F + 8, double);
   DA(f->d_Tm, (size_t)(6 + 3 * std::max(1, F)) * N, double);
-  DA(f->d_T2, (size_t)(6 + 3 * std::max(1, F)) * 15, double);
+  DA(f->d_T2, (size_t)(6 + 3 * std::max(1, F)) * N, double);
   {
     const size_t n3 = 3 * (size_t)maxT1;
     DA(f->d_fscratch, n3 * 6 * M + 9 * (size_t)maxT1 + n3 * N + n3 * n3, double);
@@ -636,6 +647,23 @@ extern "C" int xb_sm_set(xb_filter* f, int n_poses, int n_features, const int* a
   return XB_OK;
 }
 
+// Number of pose slots whose rows/columns of a host covariance are unsymmetric (the unsymmetric clones are always the
+// newest ones of the window, so the count is all the device needs)
+static int count_asym_clones(const xb_filter* f, const double* cov) {
+  const int N = f->N, M = f->M;
+  int n = 0;
+  for (int s = 0; s < M; ++s) {
+    bool asym = false;
+    for (int c = 0; c < 6 && !asym; ++c) {
+      const int r = XB_CORE + (c < 3 ? 3 * s + c : 3 * M + 3 * s + c - 3);
+      for (int j = 0; j < N; ++j)
+        if (cov[(size_t)r * N + j] != cov[(size_t)j * N + r]) { asym = true; break; }
+    }
+    n += asym;
+  }
+  return n;
+}
+
 // ---- Ekf::initializeFromState (ekf.cpp:43-64) -------------------------------------------------------------
 extern "C" int xb_ekf_initialize_from_state(xb_filter* f, const double* xvec, const double* cov, int layout) {
   if (!f || !xvec || !cov) return fail(XB_E_INVALID, "null argument");
@@ -650,6 +678,9 @@ extern "C" int xb_ekf_initialize_from_state(xb_filter* f, const double* xvec, co
   int rc = upload_cov(f, cov, layout, f->d_Pgen);
   if (rc) return rc;
   launch_extract_strip(f->stream, f->N, f->d_Pgen, f->d_strip);
+  std::fill(f->slot_asym.begin(), f->slot_asym.end(), 0);
+  f->slot_asym[0] = count_asym_clones(f, cov);
+  if (f->slot_asym[0] > 0) launch_extract_strip2(f->stream, f->N, f->d_Pgen, f->d_strip2);
   CK(cudaStreamSynchronize(f->stream));
   f->h_time[0] = xvec[XV_TIME];
   for (int e = 0; e < 3; ++e) f->h_am[e] = xvec[XV_AM + e];
@@ -678,6 +709,8 @@ static void propagate_chain(xb_filter* f, int start, int n_steps, const ImuSampl
     const bool last = done + n == n_steps;
     launch_propagate(f->stream, f->d_xv, f->LX, f->d_strip, f->N, f->NS, (start + done) % f->NS, n, last ? in : none,
                      prop_params(f), f->d_FQ);
+    if (f->slot_asym[start] > 0)  // P_vi' = P_vi F^T next to P_iv' = F P_iv (propagator.cpp:197-203)
+      launch_prop_strips(f->stream, f->d_strip2, f->N, f->NS, (start + done) % f->NS, n, f->d_FQ, 1);
     done += n;
   }
 }
@@ -719,6 +752,7 @@ extern "C" int xb_ekf_process_imu(xb_filter* f, double t, unsigned seq, const do
   f->h_time[f->tail] = t;
   for (int e = 0; e < 3; ++e) f->h_am[3 * f->tail + e] = as[e];
   f->slot_gen[f->tail] = f->slot_gen[last];
+  f->slot_asym[f->tail] = f->slot_asym[last];
   if (xvec_out) return xb_ekf_get_state(f, f->tail, xvec_out) < 0 ? XB_E_CUDA : 1;
   return 1;
 }
@@ -733,9 +767,11 @@ extern "C" int xb_ekf_get_state(xb_filter* f, int slot, double* xvec_out) {
 extern "C" int xb_ekf_get_covariance(xb_filter* f, int slot, double* cov_out, int layout) {
   if (slot < 0) slot = f->tail;
   if (slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid covariance");
+  // assembled into its own scratch: d_WA / d_WB may hold the work covariance of an update in flight
   launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
-                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_WA);
-  return download_cov(f, f->d_WA, cov_out, layout);
+                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_getcov,
+                  f->slot_asym[slot] > 0 ? f->d_strip2 + (size_t)slot * 15 * f->N : nullptr);
+  return download_cov(f, f->d_getcov, cov_out, layout);
 }
 
 // ---- measurement upload ---------------------------------------------------------------------------------------
@@ -810,6 +846,8 @@ extern "C" int xb_work_load(xb_filter* f, int slot) {
   CK(cudaMemcpyAsync(f->d_xw, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
   f->virt_strip = f->d_strip + (size_t)slot * 15 * f->N;
   f->virt_gen = f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N;
+  f->virt_strip2 = f->slot_asym[slot] > 0 ? f->d_strip2 + (size_t)slot * 15 * f->N : nullptr;
+  f->asym_clones = f->slot_asym[slot];
   f->d_Pw = f->d_WB;
   f->virt = true;
   if (!f->overlap) materialize(f);   // XB_NO_OVERLAP=1 also switches this shortcut off (plain, ordered reference schedule)
@@ -817,7 +855,7 @@ extern "C" int xb_work_load(xb_filter* f, int slot) {
 }
 static void materialize(xb_filter* f) {
   if (!f->virt) return;
-  launch_assemble(f->stream, f->N, f->virt_strip, f->virt_gen, f->d_WB);
+  launch_assemble(f->stream, f->N, f->virt_strip, f->virt_gen, f->d_WB, f->virt_strip2);
   f->virt = false;
 }
 // claim the next covariance generation as destination; slots still pointing at it lose their state
@@ -841,6 +879,8 @@ static int work_store_impl(xb_filter* f, int slot, bool copy_estimates) {
   if (copy_estimates)
     CK(cudaMemcpyAsync(f->d_xv + (size_t)slot * f->LX, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
   launch_extract_strip(f->stream, f->N, f->d_Pw, f->d_strip + (size_t)slot * 15 * f->N);
+  if (f->asym_clones > 0) launch_extract_strip2(f->stream, f->N, f->d_Pw, f->d_strip2 + (size_t)slot * 15 * f->N);
+  f->slot_asym[slot] = f->asym_clones;
   f->slot_gen[slot] = f->cur_gen;
   return XB_OK;
 }
@@ -854,6 +894,7 @@ extern "C" int xb_work_set(xb_filter* f, const double* xvec, const double* cov, 
     int rc = upload_cov(f, cov, layout, f->d_WA);
     if (rc) return rc;
     f->d_Pw = f->d_WA;
+    f->asym_clones = count_asym_clones(f, cov);
   }
   CK(cudaStreamSynchronize(f->stream));
   return XB_OK;
@@ -980,9 +1021,10 @@ extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
   // a work covariance that is still in its ring-slot form (strip + generation) is read as such: no assemble pass
   launch_manage_dev(f->stream, M, F, N, f->n_poses, nf, slide, (int)reanch.size(), f->d_featsrc, f->d_reanch, f->d_rowmap,
                     f->d_ccols, f->d_cvals, f->d_mscratch, f->d_xw, f->virt ? nullptr : src_P, dst_P, f->d_Tm, f->d_T2,
-                    f->virt_strip, f->virt_gen);
+                    f->virt_strip, f->virt_gen, f->virt_strip2, f->asym_clones > 0);
   f->virt = false;
   f->d_Pw = dst_P;
+  f->asym_clones = std::min(f->asym_clones + 1, M);  // the new clone inherits the unsymmetric core block
   // bookkeeping after the call
   for (int k = 0; k < F; ++k) f->anchor[k] = anc[k];
   f->n_features = nf;
@@ -1014,6 +1056,8 @@ static TrackParams track_params(xb_filter* f, const ListDev& l, int mode) {
   tp.gn_term = 1e-5;   // vio_updater.cpp:283-285
   tp.gn_max_iter = 10;
   tp.prof = mode == 0 ? f->d_track_prof : nullptr;
+  tp.asym_clones = std::max(1, f->asym_clones);
+  tp.oc = f->cfg.oc_projection;
   if (mode == 0) {
     tp.ivd = f->d_ivd0; tp.gamma = f->d_gamma0; tp.inlier = f->d_inl0; tp.B = f->d_B0; tp.Jout = f->d_J0;
     tp.H1 = nullptr; tp.H2 = nullptr; tp.D = nullptr;
@@ -1036,6 +1080,7 @@ static MmParams mm_params(xb_filter* f, const ListDev& l0, int which) {
   mp.gathered = f->mm_gather; mp.pp_len = f->mm_pp_len;
   mp.var_img = f->cfg.sigma_img * f->cfg.sigma_img; mp.w_other = f->cfg.ci_msckf_w;
   mp.gn_term = 1e-5; mp.gn_max_iter = 10;
+  mp.oc = f->cfg.oc_projection;
   mp.B = f->d_B0; mp.inlier = f->d_inl0;
   mp.ivd = f->d_mm_ivd; mp.F0 = f->d_mm_F0; mp.rec = f->d_mm_rec + (size_t)which * XB_MM_REC * f->mm_max_groups;
   mp.last = f->d_mm_last;
@@ -1160,7 +1205,7 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     // The SLAM rows and everything of the Kalman update that lives on their columns need only P and the estimates: they
     // are forked onto the side stream here and run next to the MSCKF track pipeline below.  Not with MSCKF-MSCKF matches:
     // their CI corrections change P between construct and apply (updater.cpp:84-97).
-    const bool early = f->overlap && f->mm_G == 0 && !(f->cfg.multi_uav && which == 1);
+    const bool early = f->overlap && f->mm_G == 0 && !(f->cfg.multi_uav && which == 1) && f->asym_clones <= 1;
     CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * f->F, cudaMemcpyHostToDevice, f->stream));
     if (early) {
       const UpdateDims d = update_dims(f, ns);
@@ -1262,6 +1307,28 @@ static int set_omega(xb_filter* f) {
   return 0;
 }
 
+// Exact applyUpdate for a work covariance that is unsymmetric beyond core + newest clone (k_general.cu): only reachable
+// after updates without measurement rows.  Hd (m x N), res (m) and rdiag (m, or nullptr for sigma_img^2) on the device.
+static int apply_general(xb_filter* f, int m, const double* Hd, const double* res, const double* rdiag, int cov_update,
+                         const double* corr) {
+  const int N = f->N;
+  if ((size_t)m * (m + N + 1) > f->T_doubles || m > N) return fail(XB_E_CAPACITY, "general update: too many rows");
+  double* X = (f->d_Pw == f->d_WA) ? f->d_WB : f->d_WA;
+  {
+    StageTimer st_(f, ST_TALLCHOL);
+    general_update(f->stream, N, m, Hd, res, rdiag, f->cfg.sigma_img * f->cfg.sigma_img, corr, f->d_Pw, X, f->d_T, f->d_delta,
+                   cov_update);
+  }
+  {
+    StageTimer st_(f, ST_CORRECT);
+    launch_apply_delta(f->stream, f->M, f->F, N, f->d_delta, f->d_xw, f->d_corr);
+  }
+  CK(cudaEventRecord(f->ev_corr, f->stream));
+  f->xw_final = true;
+  if (cov_update) f->asym_clones = 0;
+  return XB_OK;
+}
+
 // chol_from > 0: the tile columns [0, chol_from) of the tall buffer are already factored (side stream); finish the rest
 static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, double* corr_total, int chol_from = 0) {
   const int N = f->N;
@@ -1295,6 +1362,7 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
     CK(cudaStreamWaitEvent(f->stream, f->ev_dd, 0));
     f->dd_pending = false;
   }
+  if (cov_update) f->asym_clones = 0;  // P = (P + P^T)/2 (updater.cpp:133)
   return XB_OK;
 }
 
@@ -1312,6 +1380,17 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   const UpdateDims d = update_dims(f, f->last_nslam);
   const double var = f->cfg.sigma_img * f->cfg.sigma_img;
   const double* corr = f->corr_zero ? nullptr : f->d_corr;
+  if (f->asym_clones > 1) {
+    // unsymmetric beyond core + newest clone (the previous updates applied no measurement): exact dense path
+    if (invalidate_early(f)) return XB_E_CUDA;
+    double* Hd = f->d_Hdense;
+    double* res = Hd + (size_t)d.m * f->N;
+    launch_gen_densify(f->stream, d, f->d_scols, f->d_svals, f->d_sres, f->d_Tg, f->gcols_pad,
+                       f->d_Tg + (size_t)f->gcols_pad * f->gcols_pad, Hd, res);
+    f->slam_part_done = false;
+    f->corr_zero = false;
+    return apply_general(f, d.m, Hd, res, nullptr, cov_update, corr);
+  }
   int rc0 = set_omega(f);
   if (rc0) return rc0;
   int chol_from = 0;
@@ -1369,11 +1448,16 @@ extern "C" int xb_updater_apply_update(xb_filter* f, const double* H, const doub
   CK(cudaMemcpyAsync(drd, r_diag, sizeof(double) * m, cudaMemcpyHostToDevice, f->stream));
   if (correction_total) CK(cudaMemcpyAsync(f->d_corr, correction_total, sizeof(double) * N, cudaMemcpyHostToDevice, f->stream));
   else CK(cudaMemsetAsync(f->d_corr, 0, sizeof(double) * N, f->stream));
-  int rc0 = set_omega(f);
-  if (rc0) return rc0;
-  CK(cudaMemsetAsync(f->d_T, 0, sizeof(double) * (size_t)(m_pad + n_pad + 96) * m_pad, f->stream));
-  launch_dense_prepare(f->stream, m, m_pad, N, n_pad, f->d_Pw, dH, dres, drd, f->d_corr, f->d_omega, f->d_T);
-  int rc = apply_from_tall(f, m_pad, n_pad, cov_update, f->d_corr);
+  int rc;
+  if (f->asym_clones > 1) {
+    rc = apply_general(f, m, dH, dres, drd, cov_update, f->d_corr);
+  } else {
+    int rc0 = set_omega(f);
+    if (rc0) return rc0;
+    CK(cudaMemsetAsync(f->d_T, 0, sizeof(double) * (size_t)(m_pad + n_pad + 96) * m_pad, f->stream));
+    launch_dense_prepare(f->stream, m, m_pad, N, n_pad, f->d_Pw, dH, dres, drd, f->d_corr, f->d_omega, f->d_T);
+    rc = apply_from_tall(f, m_pad, n_pad, cov_update, f->d_corr);
+  }
   if (rc) return rc;
   if (correction_total) CK(cudaMemcpyAsync(correction_total, f->d_corr, sizeof(double) * N, cudaMemcpyDeviceToHost, f->stream));
   CK(cudaStreamSynchronize(f->stream));
@@ -1512,6 +1596,7 @@ extern "C" int xb_propagate(xb_filter* f, int slot_from, int slot_to) {
   ImuSample none{};
   propagate_chain(f, slot_from, 1, none);
   f->slot_gen[slot_to] = f->slot_gen[slot_from];
+  f->slot_asym[slot_to] = f->slot_asym[slot_from];
   return XB_OK;
 }
 
@@ -1521,7 +1606,7 @@ static int repropagate_from(xb_filter* f, int idx) {  // ekf.cpp:227-255
   StageTimer st_(f, ST_PROPAGATE);
   ImuSample none{};
   propagate_chain(f, idx, n, none);
-  for (int c = idx, k = 0; k < n; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; }
+  for (int c = idx, k = 0; k < n; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; f->slot_asym[c] = f->slot_asym[idx]; }
   return n;
 }
 
@@ -1554,8 +1639,9 @@ extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
     {
       StageTimer st_(f, ST_PROPAGATE);
       launch_prop_strips(f->stream, f->d_strip, f->N, f->NS, idx, n_re, f->d_FQ2);
+      if (f->slot_asym[idx] > 0) launch_prop_strips(f->stream, f->d_strip2, f->N, f->NS, idx, n_re, f->d_FQ2, 1);
     }
-    for (int c = idx, k = 0; k < n_re; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; }
+    for (int c = idx, k = 0; k < n_re; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; f->slot_asym[c] = f->slot_asym[idx]; }
   } else {
     if ((rc = xb_work_store(f, idx)) < 0) return rc;
     repropagate_from(f, idx);

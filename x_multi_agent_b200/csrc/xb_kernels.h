@@ -18,7 +18,8 @@ void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, 
 // the two halves of launch_propagate: estimates + F_d/Q_d per step (one CTA), then the covariance strips
 void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,
                        const PropParams& pp, double* FQ);
-void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ);
+// second = 1: the column strips P_vi^T (same recurrence; their core block carries Q_d^T)
+void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ, int second = 0);
 
 // ---- dense linear algebra -----------------------------------------------------------------------
 void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
@@ -77,6 +78,8 @@ struct TrackParams {
   const int* mm_grp;
   const double* mm_ivd;
   double* mm_F0;
+  int asym_clones;   // the newest `asym_clones` clones carry unsymmetric covariance blocks (1 in the regular case)
+  int oc;            // apply the reference's OC projection (xb_config.oc_projection)
   long long* prof;   // optional [K][12] clock64 stamps at the phase boundaries (XB_TRACK_PROF=1, tools/track_prof.py)
 };
 int launch_tracks(cudaStream_t s, const TrackParams& tp);
@@ -158,10 +161,18 @@ void launch_manage_dev(cudaStream_t s, int M, int F, int N, int n_poses, int n_f
                        const int* d_feat_src, const int* d_reanch, const int* d_rowmap, const int* d_ccols,
                        double* d_cvals, double* d_scratch, double* xv, const double* Pold, double* Pnew, double* Tm,
                        double* T2,
-                       const double* strip = nullptr, const double* gen = nullptr);
-// P(full) <- strip rows/cols + P_vv of a generation buffer
-void launch_assemble(cudaStream_t s, int N, const double* strip, const double* Pgen, double* Pwork);
+                       const double* strip = nullptr, const double* gen = nullptr, const double* strip2 = nullptr,
+                       int general = 0);
+// P(full) <- strip rows/cols + P_vv of a generation buffer (strip2: the column strip P_vi^T when it differs from strip)
+void launch_assemble(cudaStream_t s, int N, const double* strip, const double* Pgen, double* Pwork,
+                     const double* strip2 = nullptr);
 void launch_extract_strip(cudaStream_t s, int N, const double* Pwork, double* strip);
+void launch_extract_strip2(cudaStream_t s, int N, const double* Pwork, double* strip2);
+// general (unsymmetric-prior) Updater::applyUpdate (k_general.cu)
+void launch_gen_densify(cudaStream_t s, const UpdateDims& d, const int* scols, const double* svals, const double* sres,
+                        const double* Lg, int ldr, const double* zg, double* Hd, double* res);
+void general_update(cudaStream_t s, int N, int m, const double* Hd, const double* res, const double* rdiag, double var,
+                    const double* corr_total, double* P, double* X, double* A, double* delta, int cov_update);
 // MSCKF-SLAM / standard SLAM feature initialisation (state_manager.cpp:151-227)
 struct FeatInitParams {
   int M, F, N, n_poses, n_features, n_new;
@@ -200,6 +211,7 @@ struct MmParams {
   int n_groups;
   const double* gathered; int pp_len;  // peers' pose payloads: [8 hdr | 3M camera positions | 4M quats | 6M x 6M cov]
   double var_img, w_other, gn_term; int gn_max_iter;
+  int oc;                     // apply the reference's OC projection (xb_config.oc_projection)
   const double* B; const int* inlier;  // k_tracks outputs of the own tracks
   double* ivd;                // [G][3]
   double* F0;                 // [G][9]

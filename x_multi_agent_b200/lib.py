@@ -25,7 +25,7 @@ class XbConfig(C.Structure):
         ("a_m_max", C.c_double), ("time_margin", C.c_double),
         ("sigma_img", C.c_double), ("sigma_range", C.c_double), ("rho_0", C.c_double), ("sigma_rho_0", C.c_double),
         ("sigma_landmark", C.c_double), ("ci_msckf_w", C.c_double), ("ci_slam_w", C.c_double),
-        ("downdate_precision", C.c_int), ("multi_uav", C.c_int),
+        ("downdate_precision", C.c_int), ("multi_uav", C.c_int), ("oc_projection", C.c_int),
     ]
 
 

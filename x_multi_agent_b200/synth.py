@@ -75,6 +75,7 @@ class SynthConfig:
     n_bw: float = 0.00083
     n_a: float = 0.0013
     n_ba: float = 0.00013
+    init_err_scale: float = 0.5  # initial estimation error = N(0,1) * sigma * init_err_scale (sigma = initial P)
 
 
 class Scenario:
@@ -151,7 +152,7 @@ class Scenario:
         sp, sv, sth, sbw, sba = sigmas
         sig = np.concatenate([np.full(3, sp), np.full(3, sv), np.full(3, np.deg2rad(sth)), np.full(3, np.deg2rad(sbw)),
                               np.full(3, sba)])
-        err = self.rng.normal(0, 1, 15) * sig * 0.5
+        err = self.rng.normal(0, 1, 15) * sig * c.init_err_scale
         s.x[0:3] = p + err[0:3]
         s.x[3:6] = v + err[3:6]
         dth = err[6:9]
