@@ -2,7 +2,8 @@
 """EKF visual updates/sec on BASELINE cfg-2 (30-pose window, 200 SLAM + 800 MSCKF features), one agent per GPU.
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                     (the fp64 CPU port of the reference, host cores)
+  python bench.py --impl reference ...                     (the reference's own C++ filter back end compiled in place,
+                                                            oracle/_ref/libxref_release.so, on the host cores)
 
 A step = one Ekf::processUpdateMeasurement()-equivalent (SURVEY.md 8d): manage + constructUpdate (MSCKF,
 SLAM) + compression + applyUpdate + postUpdate + re-propagation of the 10 buffered IMU states.  Inputs are
@@ -34,6 +35,11 @@ N_FILL = 33          # frames until the window is full and all 200 SLAM features
 def workload_config(n_gpus, extra=None):
     c = {"workload": "cfg-2: single-agent 30-pose window, 200 SLAM + 800 MSCKF (30-obs) tracks per update, "
                      "10 IMU states re-propagated per update, ring buffer 250",
+         "oc_projection": "off on the device arm (xb_config.oc_projection = 0: plain MSCKF pose Jacobians, so that the "
+                          "synthetic filter stays statistically consistent and the gates accept; the reference's "
+                          "projection as written loses consistency within seconds, tests/test_cpu.py::"
+                          "test_oc_projection_as_written_breaks_consistency); same arithmetic cost either way; "
+                          "`reference_semantics` in the line is the same run with the projection on",
          "window": 30, "slam_features": 200, "msckf_tracks": 800, "n_error_states": 795,
          "agents": n_gpus, "parallelism": f"one agent per GPU x{n_gpus}, no data-path collective",
          "l2": "flushed between steps (256 MiB write)",
@@ -47,7 +53,8 @@ def workload_config(n_gpus, extra=None):
 
 def build_scenario(seed):
     from x_multi_agent_b200.synth import Scenario, SynthConfig, record
-    cfg = SynthConfig(M=CFG2["M"], F=CFG2["F"], K=FILL_K, seed=seed, slam_init_frame=CFG2["M"], slam_lm_seed=4242)
+    cfg = SynthConfig(M=CFG2["M"], F=CFG2["F"], K=FILL_K, seed=seed, slam_init_frame=CFG2["M"], slam_lm_seed=4242,
+                      slam_msckf_init_frac=1.0)
     scn = Scenario(cfg)
     fill = record(scn, N_FILL)
     scn.c.K = CFG2["K"]
@@ -127,92 +134,75 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def oracle_one_update(prior_state, sm_state, meas, sigma_img, k_sample=None):
-    """Time the fp64 CPU port of the reference (oracle/) on one update; returns (seconds_per_update, detail).
-    With k_sample < K the per-track stage runs on a sample of the MSCKF tracks and the row-proportional stages
-    are extrapolated to the full update (the dense formulation is linear in the number of tracks)."""
-    sys.path.insert(0, os.fspath(ROOT / "tests"))
-    import oracle
-    from oracle.updater import apply_qr_decomposition, apply_update
-    from oracle.updates import MsckfSlamUpdate, MsckfUpdate, SlamUpdate
-    from oracle_driver import to_oracle_state
-    s = to_oracle_state(prior_state)
-    M, F = prior_state.M, prior_state.F
-    upd = oracle.VioUpdaterOracle(M, F, sigma_img)
-    upd.sm.n_poses, upd.sm.n_features, upd.sm.anchor_idxs, upd.sm.filled_before = sm_state
-    upd.sm.anchor_idxs = list(upd.sm.anchor_idxs)
-    K = len(meas.msckf_trks)
-    ks = K if not k_sample else min(k_sample, K)
-    t = {}
-    t0 = time.perf_counter()
-    upd.sm.manage(s, list(meas.lost_slam_trk_idxs))
-    t["manage"] = time.perf_counter() - t0
-    quats, poss = upd.sm.camera_attitudes(s), upd.sm.camera_positions(s)
-    t0 = time.perf_counter()
-    ms = MsckfUpdate(meas.msckf_trks[:ks], quats, poss, s.cov, M, sigma_img)
-    t["msckf"] = (time.perf_counter() - t0) * K / ks
-    t0 = time.perf_counter()
-    mss = MsckfSlamUpdate(meas.new_msckf_slam_trks, quats, poss, s.cov, M, sigma_img)
-    sl = SlamUpdate(meas.slam_trks, quats, poss, s.f_array, upd.sm.anchor_idxs, s.cov, M, sigma_img)
-    t["slam"] = time.perf_counter() - t0
-    h = np.vstack([ms.jac, mss.jac, sl.jac])
-    res = np.concatenate([ms.res, mss.res, sl.res])
-    rd = np.concatenate([ms.cov_m_diag, mss.cov_m_diag, sl.cov_m_diag])
-    t0 = time.perf_counter()
-    hq, rq, Rq = apply_qr_decomposition(h, res, rd, sigma_img)
-    rows_full = h.shape[0] + (K - ks) * (2 * M - 3)
-    t["qr"] = (time.perf_counter() - t0) * rows_full / max(h.shape[0], 1)
-    corr = np.zeros(s.n_error_states())
-    t0 = time.perf_counter()
-    apply_update(s, hq, rq, Rq, corr, True)
-    t["apply"] = time.perf_counter() - t0
-    # re-propagation of the 10 buffered IMU states (ekf.cpp:227-255)
-    prop = oracle.Propagator()
-    a, b = s.copy(), s.copy()
-    t0 = time.perf_counter()
-    for i in range(10):
-        b.set_imu(a.time + 0.005, 0, a.w_m, a.a_m)
-        prop.propagate_state(a, b)
-        prop.propagate_covariance(a, b)
-        a, b = b, a
-    t["repropagate"] = time.perf_counter() - t0
-    return sum(t.values()), {k: round(v, 4) for k, v in t.items()}
+def reference_binary(threads):
+    """The reference's own filter back end compiled in place (oracle/ref_build/build_ref.sh): Release-flag build when
+    present, its large GEMM / QR / LU routed to the OpenBLAS that ships with numpy on `threads` host threads."""
+    from oracle import refcpp
+    flavour = "release" if refcpp.available("release") else "single"
+    if not refcpp.available(flavour):
+        raise RuntimeError("oracle/_ref/libxref*.so missing: run oracle/ref_build/build_ref.sh where /root/reference exists")
+    blas = refcpp.bind_blas(flavour, threads)
+    desc = ("reference C++ sources compiled in place (oracle/_ref/libxref_%s.so: src/x/{ekf,vio,vision}/*.cpp unmodified, "
+            "%s; Eigen/OpenCV/Boost stand-in headers, dense products / QR / LU through %s)"
+            % ("release" if flavour == "release" else "single", "reference Release flags CMakeLists.txt:185,194"
+               if flavour == "release" else "-O2", "OpenBLAS 0.3.30 on %d threads" % threads if blas else
+               "the stand-in's own loops (OpenBLAS not found)"))
+    return refcpp, flavour, desc
+
+
+def reference_one_update(prior_state, sm_state, meas, sigma_img, threads):
+    """One full Updater::update of the compiled reference (all 800 tracks) from the given prior: seconds."""
+    refcpp, flavour, desc = reference_binary(threads)
+    ref = refcpp.RefFilter(prior_state.M, prior_state.F, sigma_img=sigma_img, n_slots=2, flavour=flavour)
+    ref.sm_set(*sm_state)
+    ref.set_measurement(meas)
+    ref.updater_update(prior_state)
+    sec = ref.last_seconds
+    ref.close()
+    return sec, desc
+
+
+def host_threads():
+    """Host threads for the CPU arm: all of them.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, so
+    the count is taken from the affinity mask and handed to OpenBLAS explicitly."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the fp64 CPU port of the reference (numpy + OpenBLAS, all host threads), rank 0 only."""
+    """--impl reference: the reference's own C++ update path on the host cores, rank 0 only.  Every step is one FULL
+    Ekf::processUpdateMeasurement of cfg-2 (800 MSCKF tracks + 200 SLAM features, N = 795, incl. the re-propagation of
+    the 10 buffered IMU states), on the same synthetic stream as the GPU arm; nothing is sampled or extrapolated."""
     if rank != 0:
         return
-    sys.path.insert(0, os.fspath(ROOT / "tests"))
-    from oracle_driver import OracleFilter
-    from x_multi_agent_b200.filter import State
     from x_multi_agent_b200.synth import replay
+    threads = host_threads()
+    refcpp, flavour, desc = reference_binary(threads)
     scn, fill = build_scenario(seed=0)
-    ora = OracleFilter(CFG2["M"], CFG2["F"], n_slots=64)
-    replay(fill, ora)
-    ev = steady_events(scn, N_FILL, 1)
-    for (t, i, w, a) in ev[0][0]:
-        ora.process_imu(t, i, w, a)
-    meas = ev[0][1]
-    idx = ora.ekf.buf.closest_idx(meas.timestamp)
-    prior = State.from_oracle(ora.ekf.buf.states[idx])
-    smst = (ora.upd.sm.n_poses, ora.upd.sm.n_features, list(ora.upd.sm.anchor_idxs), ora.upd.sm.filled_before)
-    ks = 50  # bounded sample: 50 of the 800 MSCKF tracks per step, row-proportional stages extrapolated
+    ref = refcpp.RefFilter(CFG2["M"], CFG2["F"], n_slots=250, flavour=flavour)
+    replay(fill, ref)
+    W, K = max(args.warmup, 1), args.steps
+    events = steady_events(scn, N_FILL, W + K)
     times = []
-    for i in range(args.warmup + args.steps):
-        sec, detail = oracle_one_update(prior, smst, meas, scn.c.sigma_img, k_sample=ks)
-        if i >= args.warmup:
-            times.append(sec)
+    for i, (imu, m) in enumerate(events):
+        for (t, seq, w, a) in imu:
+            ref.process_imu(t, seq, w, a, want_state=False)
+        ref.set_measurement(m)
+        st = ref.process_update_measurement()
+        assert st is not None and np.all(np.isfinite(st.x))
+        if i >= W:
+            times.append(ref.last_seconds)
     sec = float(np.mean(times))
     val = 1.0 / sec
-    cores = os.cpu_count()
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"one cfg-2 update per step on {ks}/800 MSCKF tracks + all 200 SLAM rows at full N=795; "
-                                       "per-track and QR stages scaled linearly to 800 tracks (dense reference formulation, "
-                                       "numpy/OpenBLAS fp64)", "stages_s": detail},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": "every step is one full cfg-2 Ekf::processUpdateMeasurement (800 MSCKF tracks + 200 "
+                                       "SLAM features, N = 795, 10 IMU states re-propagated): " + desc,
+                             "ms_per_step_min_max": [round(min(times) * 1e3, 1), round(max(times) * 1e3, 1)]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -257,7 +247,9 @@ def main():
     from x_multi_agent_b200.synth import replay
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+        # NCCL's INFO lines (communicator ranks, transport, NVLS) go to stderr: fd 1 already points there
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -265,57 +257,74 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    scn, fill = build_scenario(seed=rank)
-    flt = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank, downdate_precision=args.precision,
-                 sigma_landmark=1.0, ci_slam_w=0.1, ci_msckf_w=0.1, multi_uav=int(world > 1))
-    stream = torch.cuda.Stream()
-    flt.set_stream(stream.cuda_stream)
-    replay(fill, flt)
-    assert flt.n_poses == CFG2["M"] and flt.n_features == CFG2["F"], "warm-up did not reach steady state"
     W, K = max(args.warmup, 3), args.steps
-    events = steady_events(scn, N_FILL, 2 * (W + K))
-    packed = [PackedMeasurement(m, pinned=True) for _, m in events]   # inputs in pinned host memory (bench contract)
+    stream = torch.cuda.Stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    def feed(i):
-        for (t, seq, w, a) in events[i][0]:
-            flt.process_imu(t, seq, w, a, want_state=False)
+    def make_agent(oc, n_steady):
+        """One agent: filter + warm-up to steady state + the next `n_steady` frames (IMU + pinned measurement)."""
+        scn_, fill_ = build_scenario(seed=rank)
+        f_ = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank,
+                    downdate_precision=args.precision, sigma_landmark=0.1, ci_slam_w=0.1, ci_msckf_w=0.1,
+                    multi_uav=int(world > 1), oc_projection=oc)
+        f_.set_stream(stream.cuda_stream)
+        replay(fill_, f_)
+        assert f_.n_poses == CFG2["M"] and f_.n_features == CFG2["F"], "warm-up did not reach steady state"
+        ev_ = steady_events(scn_, N_FILL, n_steady)
+        pk_ = [PackedMeasurement(m, pinned=True) for _, m in ev_]   # inputs in pinned host memory (bench contract)
+        return scn_, f_, ev_, pk_
+
+    def device_timed(f_, ev_, pk_, first, n_warm, n_timed, profile):
+        """n_warm + n_timed updates starting at event `first`, CUDA events on the filter's stream around each
+        Ekf::processUpdateMeasurement, L2 flushed before each; returns (ms over the timed ones, launches, stage times)."""
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_warm + n_timed)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_warm + n_timed)]
+        l0, stage_ = 0, None
+        for i in range(n_warm + n_timed):
+            if i == n_warm:
+                barrier()
+                if profile:
+                    f_.profile(True)
+                l0 = f_.kernel_launches()
+            for (t, seq, w, a) in ev_[first + i][0]:
+                f_.process_imu(t, seq, w, a, want_state=False)
+            f_.set_measurement(pk_[first + i])
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                e0[i].record(stream)
+            f_.process_update_measurement(want_state=False)
+            e1[i].record(stream)
+        barrier()
+        n_l = f_.kernel_launches() - l0
+        if profile:
+            stage_ = f_.profile_read()
+            f_.profile(False)
+        return sum(e0[i].elapsed_time(e1[i]) for i in range(n_warm, n_warm + n_timed)), n_l, stage_
+
+    nC = nR = 4 + min(K, 12)                       # fusion steps of phase C (all-gather / request-response variant)
+    n_extra = (nC + nR) if world > 1 else 0        # frames consumed by the multi-agent phases
+    scn, flt, events, packed = make_agent(0, 2 * (W + K) + n_extra)
 
     # ---- phase A: device-timed throughput, inputs resident in HBM ------------------------------------------
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
     try:
         dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         dev_uuid = None
     sampler = ClockSampler(local_rank, dev_uuid)
-    launches0 = 0
     barrier()
-    sampler.start()   # nvidia-smi takes ~0.1 s per query: start with the warm-up so that the timed region is covered
-    for i in range(W + K):
-        if i == W:
-            barrier()
-            flt.profile(True)
-            launches0 = flt.kernel_launches()
-        feed(i)
-        flt.set_measurement(packed[i])
-        with torch.cuda.stream(stream):
-            flush.zero_()
-            ev0[i].record(stream)
-        flt.process_update_measurement(want_state=False)
-        ev1[i].record(stream)
-    barrier()
+    sampler.start()   # started with the warm-up so that the timed region is covered
+    dev_ms, launches, stage = device_timed(flt, events, packed, 0, W, K, True)
     sampler.stop_flag = True
-    launches = flt.kernel_launches() - launches0
-    stage = flt.profile_read()
-    flt.profile(False)
-    dev_ms = sum(ev0[i].elapsed_time(ev1[i]) for i in range(W, W + K))
+    inl0 = flt.debug_int("inlier0", CFG2["K"])
+    msckf_inlier_frac = float(inl0.mean()) if len(inl0) else None
+    slam_inlier_frac = float(flt.debug_int("slam_inlier", CFG2["F"]).mean())
     # ---- phase B: end to end through the C ABI with host buffers ---------------------------------------------
     e2e_s = 0.0
     barrier()
     for j in range(W + K):
         i = W + K + j
-        feed(i)
+        for (t, seq, w, a) in events[i][0]:
+            flt.process_imu(t, seq, w, a, want_state=False)
         flt.synchronize()
         t0 = time.perf_counter()
         flt.set_measurement(packed[i])                      # host -> device: track lists
@@ -326,24 +335,42 @@ def main():
             e2e_s += t1 - t0
     barrier()
     assert np.all(np.isfinite(st.x)), "non-finite state after the benchmark"
-    inl0 = flt.debug_int("inlier0", CFG2["K"])
-    msckf_inlier_frac = float(inl0.mean()) if len(inl0) else None
-    slam_inlier_frac = float(flt.debug_int("slam_inlier", CFG2["F"]).mean())
+    next_ev = 2 * (W + K)
+    # ---- the same device-timed run with the reference's OC projection as written (N = 1 only) ------------------
+    ref_sem = None
+    if world == 1:
+        Kr = min(K, 20)
+        scn_r, flt_r, ev_r, pk_r = make_agent(1, W + Kr)
+        ms_r, _, _ = device_timed(flt_r, ev_r, pk_r, 0, W, Kr, False)
+        inl_r = flt_r.debug_int("inlier0", CFG2["K"])
+        ref_sem = {"value": Kr / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r / Kr, "steps": Kr,
+                   "msckf_inlier_frac_last_step": float(inl_r.mean()) if len(inl_r) else None,
+                   "note": "xb_config.oc_projection = 1 (msckf_update.cpp:393-406 as written): bit-parity setting of the "
+                           "tests; the filter has lost consistency by this point of the sequence, so fewer tracks pass the gate"}
+        flt_r.close()
     # ---- phase C (N > 1): covariance-intersection fusion steps with the compressed payload exchanged over NCCL ----
     ci = None
     if world > 1:
         from x_multi_agent_b200.ci import exchange_payloads, ring_matches
+        from x_multi_agent_b200.request_comm import (VLAD_LEN, Keyframe, KeyframeDatabase, exchange_request_response)
         PL = flt.ci_payload_len()
         local = torch.zeros(PL, dtype=torch.float64, device="cuda")
         matches = ring_matches(rank, world, CFG2["F"])
-        c0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-        c1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-        inl = 0.0
-        inl_first = None   # the loop fuses the SAME matches W+K times (a timing loop): acceptance of the first step is the
-                           # meaningful one, later steps double-count the peers' information and the gates close
+        c0 = [torch.cuda.Event(enable_timing=True) for _ in range(nC)]
+        c1 = [torch.cuda.Event(enable_timing=True) for _ in range(nC)]
+        inl = []
         barrier()
-        for i in range(W + K):
+        for i in range(nC):
+            # (untimed) the filters keep running between fusion steps: one regular visual update per step, so that
+            # every fusion step sees fresh, independently evolved estimates
+            for (t, seq, w, a) in events[next_ev][0]:
+                flt.process_imu(t, seq, w, a, want_state=False)
+            flt.set_measurement(packed[next_ev])
+            stt = flt.process_update_measurement(want_state=True)
+            t_last = stt.time
+            next_ev += 1
             flt.synchronize()
+            barrier()
             with torch.cuda.stream(stream):
                 c0[i].record(stream)
                 flt.ci_pack(local.data_ptr())
@@ -351,28 +378,84 @@ def main():
                 flt.process_others_packed(t_last, gathered.data_ptr(), world, matches, want_state=False)
                 c1[i].record(stream)
             stream.synchronize()
-            inl = float(flt.ci_last_gates(len(matches))[:, 0].mean())
-            if inl_first is None:
-                inl_first = inl
+            inl.append(float(flt.ci_last_gates(len(matches))[:, 0].mean()))
         barrier()
-        ci_ms = sum(c0[i].elapsed_time(c1[i]) for i in range(W, W + K))
+        ci_ms = sum(c0[i].elapsed_time(c1[i]) for i in range(4, nC))
         tci = torch.tensor([ci_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tci, op=dist.ReduceOp.MAX)
-        ci = {"ci_fusion_steps_per_sec": world * K / (float(tci[0]) * 1e-3), "ms_per_step": float(tci[0]) / K,
-              "matches_per_step": len(matches), "inlier_frac_rank0": inl, "inlier_frac_first_step_rank0": inl_first,
-              "payload_bytes_per_agent": PL * 8,
-              "full_simplestate_bytes": 8 * (795 * 795 + 16 + 7 * 30 + 3 * 200), "collective": "all_gather (NCCL)"}
+        ci = {"ci_fusion_steps_per_sec": world * (nC - 4) / (float(tci[0]) * 1e-3), "ms_per_step": float(tci[0]) / (nC - 4),
+              "steps": nC - 4, "matches_per_step": len(matches), "inlier_frac_first_step_rank0": inl[0],
+              "inlier_frac_mean_rank0": float(np.mean(inl[4:])), "payload_bytes_per_agent": PL * 8,
+              "full_simplestate_bytes": 8 * (795 * 795 + 16 + 7 * 30 + 3 * 200), "collective": "all_gather (NCCL)",
+              "note": "one regular visual update per agent between fusion steps (untimed); every timed step = pack + "
+                      "all-gather + gate + CI fusion + applyCI + re-propagation"}
+        # REQUEST_COMM variant (vio.cpp:455-496): 2592-byte VLAD request all-gather, then point-to-point answers only
+        # between the pairs whose request scored above the threshold against a stored keyframe
+        db = KeyframeDatabase(pr_score_thr=0.9)
+        rng_v = np.random.Generator(np.random.PCG64(777))
+        scene = rng_v.integers(0, 256, VLAD_LEN, dtype=np.uint8)   # all agents look at the same landmark patch ...
+
+        def view_descriptor(seed):                                  # ... through their own noisy descriptors (3 % bits)
+            r = np.random.Generator(np.random.PCG64(seed))
+            flip = np.packbits(r.uniform(size=8 * VLAD_LEN) < 0.03)
+            return np.bitwise_xor(scene, flip)
+        r0 = [torch.cuda.Event(enable_timing=True) for _ in range(nR)]
+        r1 = [torch.cuda.Event(enable_timing=True) for _ in range(nR)]
+        sent = recv = 0
+        inl_r = []
+        barrier()
+        for i in range(nR):
+            for (t, seq, w, a) in events[next_ev][0]:
+                flt.process_imu(t, seq, w, a, want_state=False)
+            flt.set_measurement(packed[next_ev])
+            stt = flt.process_update_measurement(want_state=True)
+            t_last = stt.time
+            next_ev += 1
+            # keyframe selection is the caller's policy (vio_updater.cpp:451-484): here every second frame
+            if i % 2 == 0:
+                snap = torch.empty(PL, dtype=torch.float64, device="cuda")
+                with torch.cuda.stream(stream):
+                    flt.ci_pack(snap.data_ptr())
+                stream.synchronize()
+                db.add(Keyframe(view_descriptor(1000 * rank + i), snap, t_last))
+            req = torch.from_numpy(view_descriptor(5000 * rank + i)).cuda()
+            flt.synchronize()
+            barrier()
+            with torch.cuda.stream(stream):
+                r0[i].record(stream)
+                got, stats = exchange_request_response(req, db, PL)
+                for peer, payload in got.items():
+                    slots = torch.zeros((world, PL), dtype=torch.float64, device="cuda")
+                    slots[peer].copy_(payload)
+                    pm = [(peer, f, f) for f in range(CFG2["F"])]
+                    flt.process_others_packed(t_last, slots.data_ptr(), world, pm, want_state=False)
+                r1[i].record(stream)
+            stream.synchronize()
+            if i >= 4:
+                sent += stats["answers_sent"]
+                recv += stats["answers_received"]
+                if got:
+                    inl_r.append(float(flt.ci_last_gates(CFG2["F"])[:, 0].mean()))
+        barrier()
+        rc_ms = sum(r0[i].elapsed_time(r1[i]) for i in range(4, nR))
+        trc = torch.tensor([rc_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(trc, op=dist.ReduceOp.MAX)
+        ci["request_comm"] = {"ms_per_step": float(trc[0]) / (nR - 4), "steps": nR - 4,
+                              "request_bytes_per_agent": VLAD_LEN, "answers_sent_rank0": sent, "answers_received_rank0": recv,
+                              "answer_bytes": PL * 8, "inlier_frac_mean_rank0": float(np.mean(inl_r)) if inl_r else None,
+                              "transport": "all_gather of the 2592-byte requests + NCCL send/recv of the answers "
+                                           "(accepted pairs only; a keyframe is sent to a peer at most once)"}
     # ---- phase D (N > 1): MULTI_UAV visual updates with 32 MSCKF-MSCKF matches per peer; every agent publishes its
     #      pose payload (window + 6M x 6M covariance block) through one all-gather per update --------------------------
     mm = None
     if world > 1:
         from x_multi_agent_b200.ci import exchange_payloads
         from x_multi_agent_b200.synth import Scenario, SynthConfig
-        Kd = min(K, 20)
+        Kd = min(K, 12)
         peers = [p for p in range(world) if p != rank]
         peer_scn = {p: Scenario(SynthConfig(M=CFG2["M"], F=CFG2["F"], K=1, seed=p, slam_init_frame=CFG2["M"], slam_lm_seed=4242))
                     for p in peers}   # analytic truth of the other agents' trajectories (same generator, their seed)
-        k0 = N_FILL + 2 * (W + K)
+        k0 = N_FILL + next_ev
         PP = flt.pose_payload_len()
         local = torch.zeros(PP, dtype=torch.float64, device="cuda")
         steps_d = []
@@ -475,8 +558,8 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        # bounded sample of the same workload on the host cores: the fp64 port of the reference's dense formulation
-        slot = (flt.newest_slot() - scn.c.latency_imu) % 250
+        # the reference's own C++ update path on the host cores: ONE full cfg-2 update (all 800 tracks) from the device's
+        # own prior, on all host threads and on one (the reference's update path is single-threaded)
         more = steady_events(scn, N_FILL + 2 * (W + K), 1)
         for (t, seq, w, a) in more[0][0]:
             flt.process_imu(t, seq, w, a, want_state=False)
@@ -484,11 +567,14 @@ def main():
         prior = flt.get_state(slot)
         prior.cov = flt.get_covariance(slot)
         smst = (flt.n_poses, flt.n_features, list(flt.anchor_idxs), True)
-        sec, detail = oracle_one_update(prior, smst, more[0][1], scn.c.sigma_img, k_sample=100)
-        cpu_baseline = {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                        "sample": "one cfg-2 update from the device's own prior: 100/800 MSCKF tracks + 200 SLAM rows at N=795, "
-                                  "per-track and QR stages scaled linearly to 800 tracks (numpy/OpenBLAS fp64 port of the dense "
-                                  "reference formulation)", "stages_s": detail}
+        threads = host_threads()
+        sec_all, desc = reference_one_update(prior, smst, more[0][1], scn.c.sigma_img, threads)
+        sec_one, _ = reference_one_update(prior, smst, more[0][1], scn.c.sigma_img, 1)
+        cpu_baseline = {"value": 1.0 / sec_all, "unit": UNIT, "cores": threads, "kind": "reference",
+                        "sample": "one full cfg-2 Updater::update (800 MSCKF tracks + 200 SLAM features, N = 795) from the "
+                                  "device's own prior: " + desc,
+                        "seconds_per_update": round(sec_all, 3),
+                        "one_core": {"value": 1.0 / sec_one, "seconds_per_update": round(sec_one, 3), "cores": 1}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -499,7 +585,8 @@ def main():
                     "d2h_bytes_per_step": flt.LX * 8},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci, "multi_uav_msckf": mm,
-            "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac}}
+            "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac},
+            "reference_semantics": ref_sem}
     emit(line)
     flt.close()
     if world > 1:

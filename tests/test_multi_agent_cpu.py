@@ -112,3 +112,66 @@ def test_two_rank_gloo_payload_exchange_and_ci_equivalence():
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res), res
     assert all(pb * 10 < fb for _, _, pb, fb in res)   # the compressed slot is >10x smaller than the SimpleState
+
+
+# ---- request / response exchange (the reference's -DREQUEST_COMM build, vio.cpp:455-496) ------------------------
+def _rc_worker(rank, world, port, q):
+    sys.path.insert(0, os.fspath(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from x_multi_agent_b200.request_comm import (VLAD_LEN, Keyframe, KeyframeDatabase, exchange_request_response, vlad_score)
+    rng = np.random.Generator(np.random.PCG64(5))
+    scene_a = rng.integers(0, 256, VLAD_LEN, dtype=np.uint8)
+    scene_b = rng.integers(0, 256, VLAD_LEN, dtype=np.uint8)      # an unrelated place: ~50 % of the bits differ
+
+    def noisy(v, seed):
+        r = np.random.Generator(np.random.PCG64(seed))
+        return np.bitwise_xor(v, np.packbits(r.uniform(size=8 * VLAD_LEN) < 0.03))
+
+    PL = 21
+    db = KeyframeDatabase(pr_score_thr=0.9)
+    # rank 0 has seen place A, rank 1 has seen place B and place A
+    db.add(Keyframe(noisy(scene_a, 10 + rank), torch.full((PL,), 100.0 + rank, dtype=torch.float64)))
+    if rank == 1:
+        db.add(Keyframe(noisy(scene_b, 20), torch.full((PL,), 200.0, dtype=torch.float64)))
+    ok = abs(vlad_score(scene_a, scene_a) - 1.0) < 1e-15 and 0.4 < vlad_score(scene_a, scene_b) < 0.6
+    ok = ok and vlad_score(scene_a, noisy(scene_a, 1)) > 0.95
+    # round 1: rank 0 asks about place A, rank 1 asks about place B (which rank 0 never saw)
+    req = torch.from_numpy(noisy(scene_a if rank == 0 else scene_b, 30 + rank))
+    got, st = exchange_request_response(req, db, PL)
+    if rank == 0:
+        ok = ok and list(got) == [1] and float(got[1][0]) == 101.0 and st["answers_sent"] == 0
+    else:
+        ok = ok and got == {} and st["answers_sent"] == 1
+    # round 2: the same request again -- the keyframe was already sent to that agent (database.cpp:33-36)
+    got2, st2 = exchange_request_response(req, db, PL)
+    ok = ok and got2 == {} and st2["answers_sent"] == 0 and st2["answers_received"] == 0
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_request_response_policy():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
+
+
+def test_keyframe_selector_follows_the_reference_rule():
+    """vio_updater.cpp:451-484: no keyframe during the first 10 frames, then one whenever the agent moved by more than
+    15 % of the mean feature depth with more than 10 live tracks."""
+    from x_multi_agent_b200.request_comm import KeyframeSelector
+    sel = KeyframeSelector()
+    ivd = np.tile([0.0, 0.0, 0.1], 20)          # 20 features at 10 m
+    taken = [sel.step(np.array([0.2 * k, 0.0, 0.0]), ivd, n_tracks=50) for k in range(40)]
+    assert not any(taken[:11]) and taken[11]
+    nxt = taken.index(True, 12)
+    assert nxt - 11 == 11                       # the frame counter restarts at every keyframe
+    assert not any(sel.step(np.array([100.0 + k, 0, 0]), ivd, n_tracks=5) for k in range(30))   # not "worthy"
