@@ -51,7 +51,9 @@ enum {
   XB_E_RUNTIME = -3,      /* std::runtime_error sites (ekf.cpp:46, ci.cpp:59-62, multi_slam_update.cpp:83-88) */
   XB_E_MISMATCH = -4,     /* init_bfr_mismatch (ekf.h:202, ekf.cpp:50-59) */
   XB_E_CAPACITY = -5,     /* more tracks/observations/features than the filter was created for */
-  XB_E_UNSUPPORTED = -6   /* NLopt-optimised CI weights (w<0), out of scope */
+  XB_E_UNSUPPORTED = -6,  /* reserved (no entry point returns it any more) */
+  XB_E_STALE = -7         /* the addressed ring-buffer state exists but its covariance generation was recycled
+                           * (measurement older than xb_config.n_generations - 1 covariance updates) */
 };
 
 typedef struct xb_filter xb_filter; /* one agent's sliding-window filter, resident on one GPU */
@@ -62,7 +64,7 @@ typedef struct xb_config {
   int n_poses_max;        /* M */
   int n_features_max;     /* F */
   int n_slots;            /* state_buffer_sz (include/x/vio/types.h:188), default 250 */
-  int n_generations;      /* P_vv generations kept on device (>=2); see DESIGN.md */
+  int n_generations;      /* covariance generations kept on the device; 0 = automatic (32); see DESIGN.md */
   int device;             /* CUDA device ordinal */
   int max_tracks;         /* capacity: MSCKF + short + MSCKF-SLAM tracks per update */
   int max_obs;            /* capacity: total observations over those tracks */

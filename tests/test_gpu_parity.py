@@ -716,3 +716,110 @@ def test_consecutive_empty_updates_match_the_oracle():
     dev.synchronize()
     rp.done()
     dev.close()
+
+
+@pytest.mark.gpu
+def test_late_peer_message_is_applied_to_an_older_buffered_state():
+    """Ekf::processOthersMeasurement with a timestamp several visual updates back (ekf.cpp:143-176): the reference
+    applies any timestamp inside its state buffer and re-propagates everything after it.  The device keeps a buffered
+    state usable for n_generations - 1 later covariance updates (default 31) and answers XB_E_STALE -- not a silent
+    nullopt -- beyond that."""
+    from oracle.ci import MultiSlamUpdate, SimpleState, SlamMatch
+    from x_multi_agent_b200 import PeerState
+    from x_multi_agent_b200.lib import XbError
+    (cfg, ev0, ora0, dev0), (_, ev1, ora1, dev1) = _two_agents(frames=12)
+    sigma_lm, w = 0.3, 0.1
+    s1 = ora1.newest()
+    peer_o = SimpleState(s1.dynamic_states(), s1.p_array.copy(), s1.q_array.copy(), s1.f_array.copy(), s1.cov.copy(),
+                         list(ora1.upd.sm.anchor_idxs))
+    peer_d = PeerState(s1.p_array, s1.q_array, s1.f_array, list(ora1.upd.sm.anchor_idxs), s1.cov)
+    matches = [(0, f, f) for f in range(cfg.F)]
+    t = ora0.newest().time - 0.17          # 34 IMU states / three visual updates back
+
+    def collab(state):
+        sm = ora0.upd.sm
+        msu = MultiSlamUpdate(sm.camera_attitudes(state), sm.camera_positions(state), state.f_array, sm.anchor_idxs, state.cov,
+                              cfg.M, sigma_lm, [SlamMatch(peer_o, c, r) for _, c, r in matches], w)
+        for Pj, H, res, S in zip(msu.P_list, msu.H_list, msu.res_list, msu.S_list):
+            apply_ci(state, Pj, H, res, S)
+    so = ora0.ekf.process_others_measurement(t, collab)
+    sd = dev0.process_others_measurement(t, [peer_d], matches)
+    assert so is not None and sd is not None and abs(sd.time - so.time) < 1e-12 and so.time < ora0.newest().time - 0.15
+    rp = Report()
+    compare_state(rp, "late ci state", sd, so, cfg.M, cfg.F, cov=False)
+    dn = dev0.get_state()
+    dn.cov = dev0.get_covariance()
+    compare_state(rp, "late ci newest", dn, ora0.newest(), cfg.M, cfg.F)
+    rp.done()
+    dev0.close()
+    dev1.close()
+    # a filter with only three generations: the same late message now addresses a recycled generation
+    cfg3 = SynthConfig(M=6, F=6, K=10, seed=11)
+    dev = make_filter(cfg3, sigma_landmark=0.3, ci_slam_w=0.1, n_generations=3)
+    replay(ev0, dev)
+    with pytest.raises(XbError) as ei:
+        dev.process_others_measurement(t, [peer_d], matches)
+    assert ei.value.code == -7
+    dev.close()
+
+
+@pytest.mark.gpu
+def test_ci_fusion_at_cfg2_size_with_four_peers():
+    """BASELINE cfg-3 shape: SLAM-SLAM covariance-intersection fusion at cfg-2 dimensions (30-pose window, 200 SLAM
+    features, N = 795) with four peers and 16 matches per peer, plus one wrong association per peer.
+    Peers and prior come from device filters that ran the fill sequence; the fusion itself (MultiSlamUpdate, pair
+    fuseCI, applyCI in list order, "last match wins" covariance: multi_slam_update.cpp:61-246, ci.cpp:94-127,
+    updater.cpp:22-36,144-161) is compared with the oracle on the same inputs."""
+    from oracle.ci import MultiSlamUpdate, SimpleState, SlamMatch
+    from x_multi_agent_b200 import PeerState
+    M, F, n_peers, per_peer = 30, 200, 4, 16
+    sigma_lm, w = 0.1, 0.1
+    agents = []
+    for a in range(n_peers + 1):
+        cfg = SynthConfig(M=M, F=F, K=12, seed=40 + a, slam_init_frame=M, slam_lm_seed=4242, slam_msckf_init_frac=1.0)
+        dev = Filter(M, F, max_tracks=16, sigma_img=cfg.sigma_img, n_slots=64, sigma_landmark=sigma_lm, ci_slam_w=w,
+                     oc_projection=0)
+        replay(record(Scenario(cfg), 36), dev)
+        assert dev.n_features == F
+        agents.append((cfg, dev))
+    cfg, own = agents[0]
+    peers_d, peers_o = [], []
+    for _, dev in agents[1:]:
+        s = dev.get_state()
+        P = dev.get_covariance()
+        peers_d.append(PeerState(s.p_array.copy(), s.q_array.copy(), s.f_array.copy(), dev.anchor_idxs, P))
+        peers_o.append(SimpleState(s.x[0:16].copy(), s.p_array.copy(), s.q_array.copy(), s.f_array.copy(), P.copy(),
+                                   list(dev.anchor_idxs)))
+    # every peer matches a different block of 16 features; the last entry of each block is a wrong association
+    matches = []
+    for p in range(n_peers):
+        for q in range(per_peer):
+            f = p * per_peer + q
+            matches.append((p, f, f if q < per_peer - 1 else (f + 97) % F))
+    slot = own.newest_slot()
+    prior = own.get_state(slot)
+    prior.cov = own.get_covariance(slot)
+    so = to_oracle_state(prior)
+    sm_anchor = list(own.anchor_idxs)
+    quats = [so.q_array[4 * i:4 * i + 4] for i in range(own.n_poses)]
+    poss = [so.p_array[3 * i:3 * i + 3] for i in range(own.n_poses)]
+    msu = MultiSlamUpdate(quats, poss, so.f_array, sm_anchor, so.cov, M, sigma_lm,
+                          [SlamMatch(peers_o[p], c, r) for p, c, r in matches], w)
+    for Pj, H, res, S in zip(msu.P_list, msu.H_list, msu.res_list, msu.S_list):
+        apply_ci(so, Pj, H, res, S)
+    sd = own.process_others_measurement(prior.time, peers_d, matches)
+    assert sd is not None
+    rp = Report()
+    gates = own.ci_last_gates(len(matches))
+    rp.check("ci inlier mask", float(np.abs(gates[:, 0] - np.array(msu.inlier, float)).sum()), 0.0)
+    rp.check("ci gamma", rel(gates[:, 1], msu.gamma), 1e-8)
+    n_inl = int(sum(msu.inlier))
+    print(f"cfg-2-size CI: {n_inl}/{len(matches)} matches fused")
+    assert n_inl >= len(matches) // 2, "the fusion arithmetic must actually run on accepted matches"
+    assert not any(msu.inlier[p * per_peer + per_peer - 1] for p in range(n_peers)), "wrong associations must be gated out"
+    compare_state(rp, "ci state", sd, so, M, F, cov=False)
+    sd.cov = own.get_covariance(slot)
+    rp.check("ci covariance", rel(sd.cov, so.cov), 1e-8)
+    rp.done()
+    for _, dev in agents:
+        dev.close()

@@ -307,7 +307,7 @@ __global__ void k_sym_lower(double* __restrict__ T, int ld, int r0, int r1, int 
 // Vt_k . {z, dW, Vt}):  G = Vt Vt^T, q = Vt z, E from P, C = E (I + G E)^-1.   om = [C 21x21 | q 21]
 __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const double* __restrict__ Cb,
                                                      const double* __restrict__ P, const int* __restrict__ omega,
-                                                     double* __restrict__ om) {
+                                                     double* __restrict__ om, int* __restrict__ err) {
   __shared__ double G[NOM][NOM], E[NOM][NOM], A[NOM][2 * NOM + 1], q[NOM];
   const int t = threadIdx.x;
   for (int e = t; e < NOM * NOM; e += blockDim.x) {
@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      const int pv = bi;
+      // a non-finite column (the factorisation met a non-positive pivot: S was not positive definite) must not
+      // select a row outside the matrix; the error word makes xb_synchronize report it
+      const int pv = (bi >= c && bi < NOM && bv == bv) ? bi : c;
+      if (lane == 0 && !(bv > 0.0) && err) atomicOr(err, 2);
       if (pv != c)
         for (int x = lane; x < 2 * NOM; x += 32) { const double tmp = A[c][x]; A[c][x] = A[pv][x]; A[pv][x] = tmp; }
       __syncwarp();
@@ -488,7 +491,7 @@ void launch_sym_lower(cudaStream_t s, double* T, int ld, int r0, int r1, int c0)
 }
 void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
                     const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* Cb,
-                    double* xv, double* corr_total, double* delta_out) {
+                    double* xv, double* corr_total, double* delta_out, int* err) {
   {
     dim3 g((m_pad + 127) / 128, NOM);
     k_omega_delta<<<g, 128, 0, s>>>(m_pad, n_pad, omega, T);
@@ -497,7 +500,7 @@ void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, i
   // Cb[(n_pad + 96) x 96] = [W1 ; aux ; dW ; Vt] * [aux ; dW ; Vt]^T : every dot product the Woodbury step needs
   gemm_nt_splitk(s, n_pad + 96, 96, m_pad, T + (size_t)m_pad * m_pad, m_pad, T + (size_t)(m_pad + n_pad) * m_pad, m_pad, Cb, 96,
                  (size_t)(n_pad + 96) * 96, CBZ);
-  k_omega_small<<<1, 256, 0, s>>>(N, n_pad, Cb, P, omega, om);
+  k_omega_small<<<1, 256, 0, s>>>(N, n_pad, Cb, P, omega, om, err);
   count_launch();
   k_omega_finish<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, n_pad, Cb, om, omega_inv, corr_total, delta_out, Zb, Yb, Qb);
   count_launch();

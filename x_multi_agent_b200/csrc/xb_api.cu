@@ -153,7 +153,11 @@ struct xb_filter {
   int status = 0;  // 0 not initialised, 1 stand-by, 2 initialised
   unsigned last_seq = 0;
   // covariance generations
-  double* d_Pgen = nullptr;  // NG x N x N
+  // NG generation slots, each naming one N x N buffer of a pool of NG + 3 (generations + the two work buffers + the
+  // early-downdate destination).  Storing a work covariance SWAPS its buffer into the generation table (no copy);
+  // the buffer that falls out becomes the new scratch.
+  std::vector<double*> gen_buf;
+  double* d_spare = nullptr; // destination of the early downdate; enters the table only when the update is stored
   int cur_gen = 0;
   // work state
   double* d_xw = nullptr;   // LX
@@ -312,7 +316,7 @@ extern "C" void xb_default_config(xb_config* c) {
   c->n_poses_max = 15;      // vio/types.h:141
   c->n_features_max = 15;   // vio/types.h:146
   c->n_slots = 250;         // vio/types.h:188
-  c->n_generations = 4;
+  c->n_generations = 0;     // 0 = automatic (32): a buffered state stays usable for 31 later covariance updates
   c->device = 0;
   c->max_tracks = 1024;
   c->max_obs = 0;
@@ -366,7 +370,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   f->N = XB_NERR(f->M, f->F);
   f->LX = XB_XVEC_LEN(f->M, f->F);
   f->NS = cfg->n_slots;
-  f->NG = std::max(2, cfg->n_generations);
+  f->NG = cfg->n_generations > 0 ? std::max(3, cfg->n_generations) : 32;
   const int M = f->M, F = f->F, N = f->N, LX = f->LX, NS = f->NS;
   if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete f;
@@ -392,7 +396,9 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_strip2, (size_t)NS * 15 * N, double);
   DA(f->d_getcov, (size_t)N * N, double);
   f->slot_asym.assign(NS, 0);
-  DA(f->d_Pgen, (size_t)f->NG * N * N, double);
+  f->gen_buf.assign(f->NG, nullptr);
+  for (int g = 0; g < f->NG; ++g) DA(f->gen_buf[g], (size_t)N * N, double);
+  DA(f->d_spare, (size_t)N * N, double);
   DA(f->d_xw, LX, double);
   DA(f->d_WA, (size_t)N * N, double);
   DA(f->d_WB, (size_t)N * N, double);
@@ -583,7 +589,10 @@ extern "C" int xb_synchronize(xb_filter* f) {
   CK(cudaStreamSynchronize(f->stream));
   if (f->side_pending) CK(cudaStreamSynchronize(f->side));
   if (*f->h_err) {
+    const int e = *f->h_err;
     cudaMemset(f->d_err, 0, sizeof(int));
+    if (e & 2)
+      return fail(XB_E_RUNTIME, "innovation covariance not positive definite (the covariance has lost definiteness)");
     return fail(XB_E_RUNTIME, "tile Cholesky dependency wait timed out");
   }
   return XB_OK;
@@ -675,12 +684,12 @@ extern "C" int xb_ekf_initialize_from_state(xb_filter* f, const double* xvec, co
   f->n_valid = 1;
   f->cur_gen = 0;
   CK(cudaMemcpyAsync(f->d_xv, xvec, sizeof(double) * f->LX, cudaMemcpyHostToDevice, f->stream));
-  int rc = upload_cov(f, cov, layout, f->d_Pgen);
+  int rc = upload_cov(f, cov, layout, f->gen_buf[0]);
   if (rc) return rc;
-  launch_extract_strip(f->stream, f->N, f->d_Pgen, f->d_strip);
+  launch_extract_strip(f->stream, f->N, f->gen_buf[0], f->d_strip);
   std::fill(f->slot_asym.begin(), f->slot_asym.end(), 0);
   f->slot_asym[0] = count_asym_clones(f, cov);
-  if (f->slot_asym[0] > 0) launch_extract_strip2(f->stream, f->N, f->d_Pgen, f->d_strip2);
+  if (f->slot_asym[0] > 0) launch_extract_strip2(f->stream, f->N, f->gen_buf[0], f->d_strip2);
   CK(cudaStreamSynchronize(f->stream));
   f->h_time[0] = xvec[XV_TIME];
   for (int e = 0; e < 3; ++e) f->h_am[e] = xvec[XV_AM + e];
@@ -769,7 +778,7 @@ extern "C" int xb_ekf_get_covariance(xb_filter* f, int slot, double* cov_out, in
   if (slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid covariance");
   // assembled into its own scratch: d_WA / d_WB may hold the work covariance of an update in flight
   launch_assemble(f->stream, f->N, f->d_strip + (size_t)slot * 15 * f->N,
-                  f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->d_getcov,
+                  f->gen_buf[f->slot_gen[slot]], f->d_getcov,
                   f->slot_asym[slot] > 0 ? f->d_strip2 + (size_t)slot * 15 * f->N : nullptr);
   return download_cov(f, f->d_getcov, cov_out, layout);
 }
@@ -845,7 +854,7 @@ extern "C" int xb_work_load(xb_filter* f, int slot) {
   StageTimer st_(f, ST_ASSEMBLE);
   CK(cudaMemcpyAsync(f->d_xw, f->d_xv + (size_t)slot * f->LX, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
   f->virt_strip = f->d_strip + (size_t)slot * 15 * f->N;
-  f->virt_gen = f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N;
+  f->virt_gen = f->gen_buf[f->slot_gen[slot]];
   f->virt_strip2 = f->slot_asym[slot] > 0 ? f->d_strip2 + (size_t)slot * 15 * f->N : nullptr;
   f->asym_clones = f->slot_asym[slot];
   f->d_Pw = f->d_WB;
@@ -859,22 +868,25 @@ static void materialize(xb_filter* f) {
   f->virt = false;
 }
 // claim the next covariance generation as destination; slots still pointing at it lose their state
-static double* claim_generation(xb_filter* f) {
+static int claim_generation(xb_filter* f) {
   f->cur_gen = (f->cur_gen + 1) % f->NG;
   for (int s = 0; s < f->NS; ++s)
     if (f->slot_gen[s] == f->cur_gen) { f->slot_gen[s] = -1; }
-  return f->d_Pgen + (size_t)f->cur_gen * f->N * f->N;
+  return f->cur_gen;
 }
 static int work_store_impl(xb_filter* f, int slot, bool copy_estimates) {
   if (slot < 0 || slot >= f->NS) return fail(XB_E_INVALID, "bad slot");
   materialize(f);
   StageTimer st_(f, ST_STORE);
-  const size_t nn = (size_t)f->N * f->N;
-  bool in_gen = f->d_Pw >= f->d_Pgen && f->d_Pw < f->d_Pgen + (size_t)f->NG * nn;
-  if (!in_gen) {
-    double* g = claim_generation(f);
-    CK(cudaMemcpyAsync(g, f->d_Pw, sizeof(double) * nn, cudaMemcpyDeviceToDevice, f->stream));
-    f->d_Pw = g;
+  {
+    // the work buffer becomes the claimed generation; the buffer it replaces becomes scratch (no copy)
+    const int g = claim_generation(f);
+    double* old = f->gen_buf[g];
+    f->gen_buf[g] = f->d_Pw;
+    if (f->d_Pw == f->d_WA) f->d_WA = old;
+    else if (f->d_Pw == f->d_WB) f->d_WB = old;
+    else if (f->d_Pw == f->d_spare) f->d_spare = old;
+    else return fail(XB_E_RUNTIME, "work covariance is not a pool buffer");
   }
   if (copy_estimates)
     CK(cudaMemcpyAsync(f->d_xv + (size_t)slot * f->LX, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToDevice, f->stream));
@@ -946,7 +958,8 @@ extern "C" int xb_sm_manage(xb_filter* f, const int* lost_idxs, int n_lost) {
   int nf = f->n_features;
   for (size_t i = del.size(); i > 0; --i) {
     const int idx = (int)del[i - 1];
-    if (idx < 0 || idx >= F) return fail(XB_E_INVALID, "lost SLAM feature index out of range");
+    if (idx < 0 || idx >= f->n_features) return fail(XB_E_INVALID, "lost SLAM feature index out of range");
+    if (i > 1 && del[i - 2] == del[i - 1]) return fail(XB_E_INVALID, "duplicate lost SLAM feature index");
     src.erase(src.begin() + idx);
     src.push_back(-1);
     anc.erase(anc.begin() + idx);
@@ -1221,7 +1234,7 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
         const bool dd_early = f->cfg.iekf_iter <= 1 && f->cfg.downdate_precision == 0 && nt64 * (nt64 + 1) / 2 < 296 &&
                               !getenv("XB_NO_EARLY_DOWNDATE");
         if (dd_early) {
-          f->d_dd = claim_generation(f);
+          f->d_dd = f->d_spare;
           CK(cudaStreamWaitEvent(f->side2, f->ev_side, 0));
           StageTimer st_(f, ST_SIDE_DD, f->side2);
           downdate_f64_range(f->side2, f->d_Pw, f->d_dd, f->N, f->d_T, d.m_pad, d.n_pad, 0, d.s_pad, 1, 0, f->d_omega_inv, f->d_Zb,
@@ -1341,7 +1354,7 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
   {
     StageTimer st_(f, ST_CORRECT);
     launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
-                   f->d_Yb, f->d_Qb, f->d_Cb, f->d_xw, corr_total, f->d_delta);
+                   f->d_Yb, f->d_Qb, f->d_Cb, f->d_xw, corr_total, f->d_delta, f->d_err);
   }
   CK(cudaEventRecord(f->ev_corr, f->stream));
   f->xw_final = true;
@@ -1581,7 +1594,7 @@ extern "C" int xb_updater_update(xb_filter* f) {
   const bool requested = f->l_msckf.n || f->l_slam.n || f->l_newstd.n || f->l_newms.n;
   if (requested) {
     if ((rc = xb_updater_reset_correction(f)) < 0) return rc;
-    const int iters = std::max(1, f->cfg.iekf_iter);
+    const int iters = f->cfg.iekf_iter;  // zero iterations when iekf_iter_ = 0, like the reference's loop (updater.cpp:99)
     for (int i = 0; i < iters; ++i) {
       if ((rc = xb_vio_construct_update(f, 0)) < 0) return rc;
       if ((rc = xb_updater_apply_constructed(f, i == iters - 1)) < 0) return rc;
@@ -1615,7 +1628,8 @@ extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
   if (!f) return fail(XB_E_INVALID, "null filter");
   if (f->status == 0) return 0;
   const int idx = closest_idx(f, f->meas_time);
-  if (idx < 0 || f->slot_gen[idx] < 0) return 0;
+  if (idx < 0) return 0;
+  if (f->slot_gen[idx] < 0) return fail(XB_E_STALE, "the buffered state's covariance generation was recycled: raise xb_config.n_generations");
   int rc;
   if ((rc = xb_work_load(f, idx)) < 0) return rc;
   f->xw_final = false;
@@ -1662,19 +1676,22 @@ extern "C" int xb_ci_pack(xb_filter* f, int slot, double* dev_payload) {
   if (slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid state");
   CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * std::max(1, f->F), cudaMemcpyHostToDevice, f->stream));
   // only pose / feature columns are read, so the generation buffer (P_vv) is the slot's covariance here
-  launch_ci_pack(f->stream, f->d_xv + (size_t)slot * f->LX, f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->N, f->M,
+  launch_ci_pack(f->stream, f->d_xv + (size_t)slot * f->LX, f->gen_buf[f->slot_gen[slot]], f->N, f->M,
                  f->F, f->n_poses, f->n_features, f->d_anchor, dev_payload);
   return XB_OK;
 }
 
 static int check_ci_weight(double w) {  // ci.cpp:98-101
   if (w > 1.0 || w == 0.0 || w < -1.0) return fail(XB_E_RUNTIME, "The CI weights must be lower than 1.0 and larger than 0.0");
-  if (w < 0.0) return fail(XB_E_UNSUPPORTED, "NLopt-optimised CI weights (ci_slam_w < 0) are out of scope");
+  // w in [-1, 0) asks the reference for NLopt-optimised weights (ci.cpp:64-75,103-116).  There is no optimiser here:
+  // the weights are the ones the reference itself falls back to when its optimiser fails -- the pair form uses -w
+  // (ci.cpp:112-113), the k-agent form keeps w as written (ci.cpp:70-75) -- see ci_pair_weight / k_mm_construct.
   return 0;
 }
 
 // Updater::collaborativeUpdate (updater.cpp:22-36) on the work state, peers given as gathered payload slots
-static int collaborative_update_packed(xb_filter* f, const double* dev_gathered, const xb_slam_match* matches, int n_matches) {
+static int collaborative_update_packed(xb_filter* f, const double* dev_gathered, int n_agents, const xb_slam_match* matches,
+                                       int n_matches) {
   if (n_matches <= 0) return XB_OK;  // preUpdateCI (vio_updater.cpp:76-79)
   if (invalidate_early(f)) return XB_E_CUDA;
   materialize(f);
@@ -1686,7 +1703,7 @@ static int collaborative_update_packed(xb_filter* f, const double* dev_gathered,
     hm[3 * j] = matches[j].peer;
     hm[3 * j + 1] = matches[j].current_feature_id;
     hm[3 * j + 2] = matches[j].received_feature_id;
-    if (matches[j].peer < 0 || matches[j].peer >= f->ci_max_agents || matches[j].received_feature_id < 0 ||
+    if (matches[j].peer < 0 || matches[j].peer >= n_agents || matches[j].received_feature_id < 0 ||
         matches[j].received_feature_id >= f->F)
       return fail(XB_E_INVALID, "bad SLAM match");
     if (matches[j].current_feature_id < 0 || matches[j].current_feature_id >= f->n_features || f->anchor[matches[j].current_feature_id] < 0)
@@ -1696,7 +1713,8 @@ static int collaborative_update_packed(xb_filter* f, const double* dev_gathered,
   CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * std::max(1, f->F), cudaMemcpyHostToDevice, f->stream));
   const double var_lm = f->cfg.sigma_landmark * f->cfg.sigma_landmark;
   launch_ci_slam(f->stream, f->d_xw, f->d_Pw, f->N, f->M, f->F, f->n_poses, f->n_features, f->d_anchor, dev_gathered,
-                 f->ci_payload_len, f->d_ci_matches, n_matches, var_lm, f->cfg.ci_slam_w, xb_chi2_quantile(0.9, 3.0),
+                 f->ci_payload_len, f->d_ci_matches, n_matches, var_lm, f->cfg.ci_slam_w < 0.0 ? -f->cfg.ci_slam_w : f->cfg.ci_slam_w,
+                 xb_chi2_quantile(0.9, 3.0),
                  f->d_ci_rec, f->d_ci_last, f->d_ci_K, f->d_ci_delta, f->d_ci_HP);
   f->ci_last_n = n_matches;
   CK(cudaStreamSynchronize(f->stream));  // hm lifetime
@@ -1709,10 +1727,11 @@ extern "C" int xb_ekf_process_others_packed(xb_filter* f, double t, const double
   if (f->status == 0) return 0;
   if (n_agents > f->ci_max_agents) return fail(XB_E_CAPACITY, "too many agents");
   const int idx = closest_idx(f, t);
-  if (idx < 0 || f->slot_gen[idx] < 0) return 0;
+  if (idx < 0) return 0;
+  if (f->slot_gen[idx] < 0) return fail(XB_E_STALE, "the buffered state's covariance generation was recycled: raise xb_config.n_generations");
   int rc;
   if ((rc = xb_work_load(f, idx)) < 0) return rc;
-  if ((rc = collaborative_update_packed(f, dev_gathered, matches, n_matches)) < 0) return rc;
+  if ((rc = collaborative_update_packed(f, dev_gathered, n_agents, matches, n_matches)) < 0) return rc;
   if ((rc = xb_work_store(f, idx)) < 0) return rc;
   repropagate_from(f, idx);
   if (xvec_out) {
@@ -1738,6 +1757,7 @@ extern "C" int xb_ekf_process_others(xb_filter* f, double t, const xb_peer_state
     const int Mp = ps.n_poses_max, Np = XB_NERR(Mp, ps.n_features_max);
     const int an = ps.anchor_idxs[rf];
     if (an < 0) return fail(XB_E_RUNTIME, "anchor_idx < 0");
+    if (an >= Mp) return fail(XB_E_INVALID, "peer anchor index outside its pose window");
     const double a = ps.features[3 * rf], b = ps.features[3 * rf + 1], r = ps.features[3 * rf + 2];
     if (r == 0.0) return fail(XB_E_RUNTIME, "rho = 0");
     double Ra[9], sk[9], m3[9], t3[3], A1[9], A2[9], h9[27];
@@ -1848,7 +1868,7 @@ extern "C" int xb_ci_pack_poses(xb_filter* f, int slot, double* dev_payload) {
   if (slot < 0) slot = f->tail;
   if (slot >= f->NS || f->slot_gen[slot] < 0) return fail(XB_E_INVALID, "slot has no valid state");
   // only pose columns are read, so the generation buffer (P_vv) is the slot's covariance here
-  launch_pack_poses(f->stream, f->d_xv + (size_t)slot * f->LX, f->d_Pgen + (size_t)f->slot_gen[slot] * f->N * f->N, f->N, f->M,
+  launch_pack_poses(f->stream, f->d_xv + (size_t)slot * f->LX, f->gen_buf[f->slot_gen[slot]], f->N, f->M,
                     dev_payload);
   return XB_OK;
 }
