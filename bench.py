@@ -28,6 +28,12 @@ sys.path.insert(0, os.fspath(ROOT))
 METRIC = "ekf_visual_updates_per_sec"
 UNIT = "updates/s"
 CFG2 = dict(M=30, F=200, K=800)
+# IMU of the synthetic agent AND of the filter's noise model: a MEMS-grade gyro (noise density 2e-4 rad/s/sqrt(Hz), bias
+# random walk 2e-5) instead of the reference's default 0.0083 / 0.00083 (include/x/common/types.h:65-79).  With the default
+# the reference's own Q_d polynomial -- which is not symmetric and, at that gyro density, not positive semi-definite
+# (propagator.cpp:207-840) -- drives the covariance of a well-observed filter indefinite within ~20 updates of this size
+# (oracle-only measurement): lambda_min(P) = -3e-6 after the first steady-state update, doubling every step.
+IMU_NOISE = dict(n_w=2e-4, n_bw=2e-5, n_a=0.0013, n_ba=0.00013)
 FILL_K = 40          # MSCKF tracks per update while the window fills (warm-up to steady state, untimed)
 N_FILL = 33          # frames until the window is full and all 200 SLAM features are initialised
 
@@ -40,6 +46,10 @@ def workload_config(n_gpus, extra=None):
                           "projection as written loses consistency within seconds, tests/test_cpu.py::"
                           "test_oc_projection_as_written_breaks_consistency); same arithmetic cost either way; "
                           "`reference_semantics` in the line is the same run with the projection on",
+         "imu_noise": dict(IMU_NOISE, note="MEMS-grade gyro instead of the reference default 0.0083 / 0.00083, used for the "
+                                                "synthetic data and for the filter's noise model on both arms: with the default "
+                                                "the reference's Q_d polynomial is not positive semi-definite and the covariance of "
+                                                "a well-observed filter loses definiteness within ~20 updates (DESIGN.md)"),
          "window": 30, "slam_features": 200, "msckf_tracks": 800, "n_error_states": 795,
          "agents": n_gpus, "parallelism": f"one agent per GPU x{n_gpus}, no data-path collective",
          "l2": "flushed between steps (256 MiB write)",
@@ -54,7 +64,7 @@ def workload_config(n_gpus, extra=None):
 def build_scenario(seed):
     from x_multi_agent_b200.synth import Scenario, SynthConfig, record
     cfg = SynthConfig(M=CFG2["M"], F=CFG2["F"], K=FILL_K, seed=seed, slam_init_frame=CFG2["M"], slam_lm_seed=4242,
-                      slam_msckf_init_frac=1.0)
+                      slam_msckf_init_frac=1.0, **IMU_NOISE)
     scn = Scenario(cfg)
     fill = record(scn, N_FILL)
     scn.c.K = CFG2["K"]
@@ -153,7 +163,8 @@ def reference_binary(threads):
 def reference_one_update(prior_state, sm_state, meas, sigma_img, threads):
     """One full Updater::update of the compiled reference (all 800 tracks) from the given prior: seconds."""
     refcpp, flavour, desc = reference_binary(threads)
-    ref = refcpp.RefFilter(prior_state.M, prior_state.F, sigma_img=sigma_img, n_slots=2, flavour=flavour)
+    ref = refcpp.RefFilter(prior_state.M, prior_state.F, sigma_img=sigma_img, n_slots=2, flavour=flavour,
+                           noise=tuple(IMU_NOISE[k] for k in ("n_w", "n_bw", "n_a", "n_ba")))
     ref.sm_set(*sm_state)
     ref.set_measurement(meas)
     ref.updater_update(prior_state)
@@ -181,7 +192,8 @@ def run_reference(args, rank, world):
     threads = host_threads()
     refcpp, flavour, desc = reference_binary(threads)
     scn, fill = build_scenario(seed=0)
-    ref = refcpp.RefFilter(CFG2["M"], CFG2["F"], n_slots=250, flavour=flavour)
+    ref = refcpp.RefFilter(CFG2["M"], CFG2["F"], n_slots=250, flavour=flavour,
+                           noise=tuple(IMU_NOISE[k] for k in ("n_w", "n_bw", "n_a", "n_ba")))
     replay(fill, ref)
     W, K = max(args.warmup, 1), args.steps
     events = steady_events(scn, N_FILL, W + K)
@@ -266,7 +278,7 @@ def main():
         scn_, fill_ = build_scenario(seed=rank)
         f_ = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank,
                     downdate_precision=args.precision, sigma_landmark=0.1, ci_slam_w=0.1, ci_msckf_w=0.1,
-                    multi_uav=int(world > 1), oc_projection=oc)
+                    multi_uav=int(world > 1), oc_projection=oc, **IMU_NOISE)
         f_.set_stream(stream.cuda_stream)
         replay(fill_, f_)
         assert f_.n_poses == CFG2["M"] and f_.n_features == CFG2["F"], "warm-up did not reach steady state"
@@ -279,6 +291,8 @@ def main():
         Ekf::processUpdateMeasurement, L2 flushed before each; returns (ms over the timed ones, launches, stage times)."""
         e0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_warm + n_timed)]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_warm + n_timed)]
+        i0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_warm + n_timed)]
+        i1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_warm + n_timed)]
         l0, stage_ = 0, None
         for i in range(n_warm + n_timed):
             if i == n_warm:
@@ -286,8 +300,11 @@ def main():
                 if profile:
                     f_.profile(True)
                 l0 = f_.kernel_launches()
+            i0[i].record(stream)
             for (t, seq, w, a) in ev_[first + i][0]:
-                f_.process_imu(t, seq, w, a, want_state=False)
+                f_.process_imu(t, seq, w, a, want_state=False)     # Ekf::processImu: one fused launch per sample
+            i1[i].record(stream)
+            n_imu = len(ev_[first + i][0])
             f_.set_measurement(pk_[first + i])
             with torch.cuda.stream(stream):
                 flush.zero_()
@@ -299,7 +316,8 @@ def main():
         if profile:
             stage_ = f_.profile_read()
             f_.profile(False)
-        return sum(e0[i].elapsed_time(e1[i]) for i in range(n_warm, n_warm + n_timed)), n_l, stage_
+        imu_us = 1e3 * sum(i0[i].elapsed_time(i1[i]) for i in range(n_warm, n_warm + n_timed)) / (n_timed * max(n_imu, 1))
+        return sum(e0[i].elapsed_time(e1[i]) for i in range(n_warm, n_warm + n_timed)), n_l, (stage_, imu_us)
 
     nC = nR = 4 + min(K, 12)                       # fusion steps of phase C (all-gather / request-response variant)
     n_extra = (nC + nR) if world > 1 else 0        # frames consumed by the multi-agent phases
@@ -313,7 +331,7 @@ def main():
     sampler = ClockSampler(local_rank, dev_uuid)
     barrier()
     sampler.start()   # started with the warm-up so that the timed region is covered
-    dev_ms, launches, stage = device_timed(flt, events, packed, 0, W, K, True)
+    dev_ms, launches, (stage, imu_us) = device_timed(flt, events, packed, 0, W, K, True)
     sampler.stop_flag = True
     inl0 = flt.debug_int("inlier0", CFG2["K"])
     msckf_inlier_frac = float(inl0.mean()) if len(inl0) else None
@@ -586,7 +604,10 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci, "multi_uav_msckf": mm,
             "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac},
-            "reference_semantics": ref_sem}
+            "reference_semantics": ref_sem,
+            "imu_us_per_sample": {"value": round(imu_us, 2), "note": "Ekf::processImu (propagateState + propagateCovariance, "
+                                  "ekf.cpp:66-140) between updates: device time per IMU sample over the untimed feed of the "
+                                  "steady-state phase (10 samples per frame, one fused launch each, issued back to back)"}}
     emit(line)
     flt.close()
     if world > 1:

@@ -137,6 +137,41 @@ def main():
     out.mkdir(parents=True, exist_ok=True)
     (out / "qd_poly.cuh").write_text("\n".join(cu) + "\n")
 
+    # ---- partitioned form: the entries are split into NPART groups of similar cost, each with its own CSE, so that
+    #      NPART warps evaluate the polynomial concurrently (k_prop_step); shared sub-expressions are recomputed
+    NPART = 7
+    cost = [sp.count_ops(Q[r, c]) + 1 for r, c in nz]
+    order = sorted(range(len(nz)), key=lambda i: -cost[i])
+    groups, load = [[] for _ in range(NPART)], [0] * NPART
+    for i in order:
+        g = load.index(min(load))
+        groups[g].append(i)
+        load[g] += cost[i]
+
+    def mul_pow(code):
+        return re.sub(r"pow\(([A-Za-z0-9_]+), (\d)\)", lambda m: "(" + "*".join([m.group(1)] * int(m.group(2))) + ")", code)
+
+    cp = [f"// {hdr}", "// Partitioned form: xb_qd_poly_part(part, ...) writes the entries of group `part` (0..XB_QD_NPART-1).",
+          "#pragma once", f"#define XB_QD_NPART {NPART}",
+          "__device__ __noinline__ void xb_qd_poly_part(int part, double dt, const double* C, const double* w, const double* a,",
+          "                                             double n_w, double n_bw, double n_a, double n_ba, double* Q) {",
+          "  const double C00 = C[0], C01 = C[1], C02 = C[2], C10 = C[3], C11 = C[4], C12 = C[5], C20 = C[6], C21 = C[7], C22 = C[8];",
+          "  const double w0 = w[0], w1 = w[1], w2 = w[2], a0 = a[0], a1 = a[1], a2 = a[2];",
+          "  switch (part) {"]
+    for g, idxs in enumerate(groups):
+        rg, eg = sp.cse([Q[nz[i][0], nz[i][1]] for i in idxs], symbols=sp.numbered_symbols("s"), optimizations="basic")
+        cp.append(f"    case {g}: {{")
+        for sym, e in rg:
+            cp.append(f"      const double {sym} = {mul_pow(sp.ccode(e))};")
+        for i, e in zip(idxs, eg):
+            r, c = nz[i]
+            cp.append(f"      Q[{r * 15 + c}] = {mul_pow(sp.ccode(e))};")
+        cp.append("      break;")
+        cp.append("    }")
+        print(f"part {g}: {len(idxs)} entries, {len(rg)} temporaries", file=sys.stderr)
+    cp += ["    default: break;", "  }", "}"]
+    (out / "qd_poly_parts.cuh").write_text("\n".join(cp) + "\n")
+
 
 if __name__ == "__main__":
     main()

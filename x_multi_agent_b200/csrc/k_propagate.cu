@@ -8,6 +8,7 @@
 // P_iv (the reference computes both with the same products, propagator.cpp:195-203).
 #include "xb_kernels.h"
 #include "qd_poly.cuh"
+#include "qd_poly_parts.cuh"
 
 namespace xb {
 
@@ -221,6 +222,189 @@ __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip,
       }
     }
   }
+}
+
+__device__ __noinline__ void state_transition_call(double dt, const double* w, const double* a, const double* q, double* F) {
+  state_transition(dt, w, a, q, F);
+}
+
+// ---- one IMU step in ONE launch (Ekf::processImu, ekf.cpp:66-140: hot loop #1) -------------------------------------
+// Every CTA recomputes the step's small quantities itself -- quaternion integrator across 16 lanes, the q/v/p update,
+// F_d on one warp and the Q_d polynomial split over XB_QD_NPART warps (qd_poly_parts.cuh) -- and then propagates its
+// 256 columns of the covariance strip(s); CTA 0 also writes the estimates of the new slot.  No grid-wide dependency,
+// so means and strips need no second launch, and the serial Q_d evaluation (the whole cost of the two-kernel form on a
+// single sample) is cut to its longest partition.
+__global__ void __launch_bounds__(256) k_prop_step(double* __restrict__ xv, int LX, double* __restrict__ strip, int N, int NS,
+                                                   int start, ImuSample in, PropParams pp, double* __restrict__ FQ) {
+  __shared__ double x0s[32], x1s[32], O1[16], O0[16], A[16], Ak[16], Tm4[16], Dm[16], w1s[3], a1s[3], Cs[9];
+  __shared__ double Fs[225], Qs[225], Pii[225], Tm[225];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const double* x0 = xv + (size_t)start * LX;
+  double* x1 = xv + (size_t)((start + 1) % NS) * LX;
+#ifdef XB_PROP_PROF
+  long long ck[6];
+  ck[0] = clock64();
+#define PCK(i) if (blockIdx.x == 0 && t == 0) ck[i] = clock64();
+#else
+#define PCK(i)
+#endif
+  if (t < 32) {
+    x0s[t] = x0[t];
+    x1s[t] = (t >= XV_WM && t < XV_ARR) ? x1[t] : x0[t];   // biases, extrinsics: State::setStaticStatesFrom (state.cpp:153-161)
+  }
+  for (int e = t; e < 225; e += blockDim.x) Qs[e] = 0.0;
+  __syncthreads();
+  if (t == 0 && in.valid) {                                   // State::setImu (state.cpp:145-151)
+    x1s[XV_WM] = in.w[0]; x1s[XV_WM + 1] = in.w[1]; x1s[XV_WM + 2] = in.w[2];
+    x1s[XV_AM] = in.a[0]; x1s[XV_AM + 1] = in.a[1]; x1s[XV_AM + 2] = in.a[2];
+    x1s[XV_TIME] = in.t;
+    x1s[XV_SEQ] = in.seq;
+  }
+  __syncthreads();
+  PCK(1)
+  const double dt = x1s[XV_TIME] - x0s[XV_TIME];
+  if (warp == 0) {
+    // quaternionIntegrator (propagator.cpp:74-98), element (r, c) per lane, same operation order as quat_integrator()
+    const int r = (lane & 15) >> 2, c = lane & 3;
+    if (lane < 16) {
+      // Omega(v)[r][c] (eigen_matrix_base_plugin.h:43-52): +-v[k] with k, sign from the (r, c) pattern
+      //   [ 0  z -y  x ; -z  0  x  y ;  y -x  0  z ; -x -y -z  0 ]
+      const int kk[16] = {-1, 2, 1, 0, 2, -1, 0, 1, 1, 0, -1, 2, 0, 1, 2, -1};
+      const double sg[16] = {0, 1, -1, 1, -1, 0, 1, 1, 1, -1, 0, 1, -1, -1, -1, 0};
+      const int k = kk[lane];
+      double o1 = 0.0, o0 = 0.0, om = 0.0;
+      if (k >= 0) {
+        const double w1 = x1s[XV_WM + k] - x1s[XV_BW + k], w0 = x0s[XV_WM + k] - x0s[XV_BW + k];
+        o1 = sg[lane] * w1;
+        o0 = sg[lane] * w0;
+        om = sg[lane] * ((w1 + w0) / 2.0);
+      }
+      O1[lane] = o1;
+      O0[lane] = o0;
+      const double a = om * 0.5 * dt;
+      A[lane] = a;
+      Ak[lane] = a;
+      Dm[lane] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    int fac = 1;
+#pragma unroll 1
+    for (int k = 1; k < 5; ++k) {
+      fac *= k;
+      if (lane < 16) {
+        Dm[lane] = Dm[lane] + Ak[lane] / fac;
+        double s = 0.0;
+        for (int e = 0; e < 4; ++e) s += Ak[r * 4 + e] * A[e * 4 + c];
+        Tm4[lane] = s;
+      }
+      __syncwarp();
+      if (lane < 16) Ak[lane] = Tm4[lane];
+      __syncwarp();
+    }
+    if (lane < 16) {
+      double s10 = 0.0, s01 = 0.0;
+      for (int e = 0; e < 4; ++e) {
+        s10 += O1[r * 4 + e] * O0[e * 4 + c];
+        s01 += O0[r * 4 + e] * O1[e * 4 + c];
+      }
+      Dm[lane] += 1.0 / 48.0 * (s10 - s01) * dt * dt;
+    }
+    __syncwarp();
+    if (lane == 0) {   // propagateState (propagator.cpp:30-51)
+      double q1[4], a1[3], a0[3];
+      for (int e = 0; e < 3; ++e) {
+        a1[e] = x1s[XV_AM + e] - x1s[XV_BA + e];
+        a0[e] = x0s[XV_AM + e] - x0s[XV_BA + e];
+      }
+      for (int rr = 0; rr < 4; ++rr)
+        q1[rr] = Dm[rr * 4] * x0s[XV_Q] + Dm[rr * 4 + 1] * x0s[XV_Q + 1] + Dm[rr * 4 + 2] * x0s[XV_Q + 2] + Dm[rr * 4 + 3] * x0s[XV_Q + 3];
+      xb_qnormalize(q1);
+      double R1[9], R0[9], ra1[3], ra0[3];
+      xb_rot_raw(q1, R1);
+      xb_rot_raw(&x0s[XV_Q], R0);
+      xb_mv33(R1, a1, ra1);
+      xb_mv33(R0, a0, ra0);
+      const double gv[3] = {pp.g[0], pp.g[1], pp.g[2]};
+      for (int e = 0; e < 3; ++e) {
+        const double dv = (ra1[e] + ra0[e]) / 2.0;
+        const double v1 = x0s[XV_V + e] + (dv + gv[e]) * dt;
+        x1s[XV_V + e] = v1;
+        x1s[XV_P + e] = x0s[XV_P + e] + (v1 + x0s[XV_V + e]) / 2.0 * dt;
+      }
+      for (int e = 0; e < 4; ++e) x1s[XV_Q + e] = q1[e];
+      // operands of F_d / Q_d, staged in shared memory for the warps below
+      for (int e = 0; e < 3; ++e) {
+        w1s[e] = x1s[XV_WM + e] - x1s[XV_BW + e];
+        a1s[e] = a1[e];
+      }
+      for (int e = 0; e < 9; ++e) Cs[e] = R1[e];
+    }
+  }
+  __syncthreads();
+  PCK(2)
+  // F_d on warp 0, the Q_d partitions on warps 1..XB_QD_NPART (one lane each: the polynomial is a scalar DAG)
+  if (lane == 0) {
+    if (warp == 0) state_transition_call(dt, w1s, a1s, &x1s[XV_Q], Fs);
+    else if (warp <= XB_QD_NPART) xb_qd_poly_part(warp - 1, dt, Cs, w1s, a1s, pp.n_w, pp.n_bw, pp.n_a, pp.n_ba, Qs);
+  }
+  __syncthreads();
+  PCK(3)
+  // strip columns of this thread: P_iv' = F P_iv (propagator.cpp:197); compact loops (the kernel runs once per launch on
+  // cold instruction caches: code size is latency)
+  // CTA 0: core block + estimates; CTAs 1..: 256 strip columns each (they run side by side on different SMs)
+  const bool core_block = blockIdx.x == 0;
+  const int j = XB_CORE + ((int)blockIdx.x - 1) * (int)blockDim.x + t;
+  const size_t SS = (size_t)15 * N;
+  const double* s0 = strip + (size_t)start * SS;
+  double* s1 = strip + (size_t)((start + 1) % NS) * SS;
+  if (!core_block && j < N) {
+    double v[15];
+#pragma unroll
+    for (int r = 0; r < 15; ++r) v[r] = s0[(size_t)r * N + j];
+#pragma unroll 1
+    for (int r0 = 0; r0 < 15; r0 += 5) {   // five independent accumulation chains per pass
+      double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int e = 0; e < 15; ++e)
+#pragma unroll
+        for (int u = 0; u < 5; ++u) s[u] = fma(Fs[(r0 + u) * 15 + e], v[e], s[u]);
+#pragma unroll
+      for (int u = 0; u < 5; ++u) s1[(size_t)(r0 + u) * N + j] = s[u];
+    }
+  }
+  if (core_block) {
+    if (t < 225) Pii[t] = s0[(size_t)(t / 15) * N + (t % 15)];
+    __syncthreads();
+    if (t < 225) {  // Tm = F * P_ii
+      const int r = t / 15, c = t % 15;
+      double s = 0.0;
+      for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], Pii[a * 15 + c], s);
+      Tm[t] = s;
+    }
+    __syncthreads();
+    if (t < 225) {  // P_ii' = Tm * F^T + Q
+      const int r = t / 15, c = t % 15;
+      double s = 0.0;
+      for (int a = 0; a < 15; ++a) s = fma(Tm[r * 15 + a], Fs[c * 15 + a], s);
+      s1[(size_t)r * N + c] = s + Qs[t];
+      FQ[t] = Fs[t];            // F_d / Q_d of the step where the two-kernel form leaves them
+      FQ[225 + t] = Qs[t];
+    }
+    // estimates of the new slot
+    if (t < 32) x1[t] = x1s[t];
+    for (int e = XV_ARR + t; e < LX; e += blockDim.x) x1[e] = x0[e];
+  }
+#ifdef XB_PROP_PROF
+  PCK(4)
+  if (blockIdx.x == 0 && t == 0)
+    for (int i = 0; i < 5; ++i) FQ[460 + i] = (double)(ck[i] - ck[0]);
+#endif
+}
+
+void launch_prop_step(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, const ImuSample& in,
+                      const PropParams& pp, double* FQ) {
+  k_prop_step<<<1 + (N - XB_CORE + 255) / 256, 256, 0, s>>>(xv, LX, strip, N, NS, start, in, pp, FQ);
+  count_launch();
 }
 
 void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,

@@ -712,6 +712,12 @@ static PropParams prop_params(const xb_filter* f) {
 
 static void propagate_chain(xb_filter* f, int start, int n_steps, const ImuSample& in) {
   ImuSample none{};
+  if (n_steps == 1 && !getenv("XB_NO_FUSED_IMU")) {   // the processImu case: one fused launch
+    launch_prop_step(f->stream, f->d_xv, f->LX, f->d_strip, f->N, f->NS, start, in, prop_params(f), f->d_FQ);
+    if (f->slot_asym[start] > 0)  // P_vi' = P_vi F^T next to P_iv' = F P_iv (propagator.cpp:197-203): rare, second launch
+      launch_prop_strips(f->stream, f->d_strip2, f->N, f->NS, start, 1, f->d_FQ, 1);
+    return;
+  }
   int done = 0;
   while (done < n_steps) {
     const int n = std::min(128, n_steps - done);
@@ -1907,6 +1913,7 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
     src = f->d_Rg; cnt = (size_t)f->gcols_pad * f->gcols_pad;
   }
   else if (n == "corr") { src = f->d_corr; cnt = f->N; }
+  else if (n == "FQ") { src = f->d_FQ; cnt = 470; }
   else if (n == "delta") { src = f->d_delta; cnt = f->N; }
   else if (n == "T") { src = f->d_T; cnt = f->T_doubles; }
   else if (n == "track_prof") {

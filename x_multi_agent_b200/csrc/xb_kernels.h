@@ -15,6 +15,9 @@ struct ImuSample { int valid; double t, seq, w[3], a[3]; };
 struct PropParams { double g[3]; double n_w, n_bw, n_a, n_ba; };
 void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,
                       const ImuSample& in, const PropParams& pp, double* FQ);
+// one IMU step (means + row strips) in a single launch
+void launch_prop_step(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, const ImuSample& in,
+                      const PropParams& pp, double* FQ);
 // the two halves of launch_propagate: estimates + F_d/Q_d per step (one CTA), then the covariance strips
 void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,
                        const PropParams& pp, double* FQ);
