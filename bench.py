@@ -34,6 +34,11 @@ CFG2 = dict(M=30, F=200, K=800)
 # (propagator.cpp:207-840) -- drives the covariance of a well-observed filter indefinite within ~20 updates of this size
 # (oracle-only measurement): lambda_min(P) = -3e-6 after the first steady-state update, doubling every step.
 IMU_NOISE = dict(n_w=2e-4, n_bw=2e-5, n_a=0.0013, n_ba=0.00013)
+# Fixed covariance-intersection weights of the fusion phases.  The reference applies the correction of EVERY accepted
+# match from the same prior, one after the other (updater.cpp:22-36,84-97): for the states the matches have in common the
+# gain of a fusion step is n_matches x K with K ~ w, so the weights are chosen such that n_matches x w = 0.5 (a
+# contraction); with w = 0.1 and 32 matches per peer the loop overshoots and every later gate closes.
+CI_SLAM_W = 0.5 / 16
 FILL_K = 40          # MSCKF tracks per update while the window fills (warm-up to steady state, untimed)
 N_FILL = 33          # frames until the window is full and all 200 SLAM features are initialised
 
@@ -277,7 +282,8 @@ def main():
         """One agent: filter + warm-up to steady state + the next `n_steady` frames (IMU + pinned measurement)."""
         scn_, fill_ = build_scenario(seed=rank)
         f_ = Filter(CFG2["M"], CFG2["F"], max_tracks=CFG2["K"], n_slots=250, device=local_rank,
-                    downdate_precision=args.precision, sigma_landmark=0.1, ci_slam_w=0.1, ci_msckf_w=0.1,
+                    downdate_precision=args.precision, sigma_landmark=0.1, ci_slam_w=CI_SLAM_W,
+                    ci_msckf_w=0.5 / (32 * max(1, world - 1)),
                     multi_uav=int(world > 1), oc_projection=oc, **IMU_NOISE)
         f_.set_stream(stream.cuda_stream)
         replay(fill_, f_)
@@ -320,8 +326,7 @@ def main():
         return sum(e0[i].elapsed_time(e1[i]) for i in range(n_warm, n_warm + n_timed)), n_l, (stage_, imu_us)
 
     nC = nR = 4 + min(K, 12)                       # fusion steps of phase C (all-gather / request-response variant)
-    n_extra = (nC + nR) if world > 1 else 0        # frames consumed by the multi-agent phases
-    scn, flt, events, packed = make_agent(0, 2 * (W + K) + n_extra)
+    scn, flt, events, packed = make_agent(0, 2 * (W + K))
 
     # ---- phase A: device-timed throughput, inputs resident in HBM ------------------------------------------
     try:
@@ -353,7 +358,6 @@ def main():
             e2e_s += t1 - t0
     barrier()
     assert np.all(np.isfinite(st.x)), "non-finite state after the benchmark"
-    next_ev = 2 * (W + K)
     # ---- the same device-timed run with the reference's OC projection as written (N = 1 only) ------------------
     ref_sem = None
     if world == 1:
@@ -366,14 +370,82 @@ def main():
                    "note": "xb_config.oc_projection = 1 (msckf_update.cpp:393-406 as written): bit-parity setting of the "
                            "tests; the filter has lost consistency by this point of the sequence, so fewer tracks pass the gate"}
         flt_r.close()
-    # ---- phase C (N > 1): covariance-intersection fusion steps with the compressed payload exchanged over NCCL ----
+    frame_cursor = [N_FILL + 2 * (W + K)]          # next camera frame of this agent's scenario
+
+    def next_frame():
+        """IMU samples + pinned measurement of the next frame, generated on demand (multi-agent phases)."""
+        imu_, m_ = steady_events(scn, frame_cursor[0], 1)[0]
+        frame_cursor[0] += 1
+        return imu_, PackedMeasurement(m_, pinned=True)
+
+    # ---- phase C (N > 1): MULTI_UAV visual updates with 32 MSCKF-MSCKF matches per peer; every agent publishes its
+    #      pose payload (window + 6M x 6M covariance block) through one all-gather per update --------------------------
+    mm = None
+    if world > 1:
+        from x_multi_agent_b200.ci import exchange_payloads
+        from x_multi_agent_b200.synth import Scenario, SynthConfig
+        Kd = min(K, 12)
+        peers = [p for p in range(world) if p != rank]
+        peer_scn = {p: Scenario(SynthConfig(M=CFG2["M"], F=CFG2["F"], K=1, seed=p, slam_init_frame=CFG2["M"], slam_lm_seed=4242))
+                    for p in peers}   # analytic truth of the other agents' trajectories (same generator, their seed)
+        k0 = frame_cursor[0]
+        PP = flt.pose_payload_len()
+        local = torch.zeros(PP, dtype=torch.float64, device="cuda")
+        steps_d = []
+        for j in range(W + Kd):
+            imu, m = steady_events(scn, k0 + j, 1)[0]
+            lms = scn.last_msckf_lms
+            win = list(range(k0 + j - CFG2["M"], k0 + j))     # frames held by a peer's window when it packs its payload
+            mt = [(p, 0, a * 32 + q, peer_scn[p]._project(lms[a * 32 + q], win)) for a, p in enumerate(peers) for q in range(32)]
+            steps_d.append((imu, PackedMeasurement(m), mt))
+        d0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
+        d1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
+        acc, gated = [], []
+        barrier()
+        for j, (imu, pm, mt) in enumerate(steps_d):
+            for (t, seq, w, a) in imu:
+                flt.process_imu(t, seq, w, a, want_state=False)
+            flt.set_measurement(pm)
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                d0[j].record(stream)
+                flt.pack_poses(local.data_ptr())
+                gathered = exchange_payloads(local)
+                flt.set_msckf_matches_packed(gathered.data_ptr(), world, mt)
+                flt.process_update_measurement(want_state=False)
+                d1[j].record(stream)
+            stream.synchronize()
+            g = flt.mm_last_gates(0)
+            if os.environ.get("BENCH_DEBUG") and rank == 0 and j < 3:
+                print("mm gates step", j, "gamma/chi2 quantiles", np.nanquantile(g[:, 1] / g[:, 2], [0.1, 0.5, 0.9]) if len(g) else None,
+                      "n", len(g), file=sys.stderr, flush=True)
+            gated.append(float(np.isfinite(g[:, 1]).mean()) if len(g) else 0.0)
+            acc.append(float(g[:, 0].mean()) if len(g) else 0.0)
+        barrier()
+        frame_cursor[0] = k0 + W + Kd
+        mm_ms = sum(d0[j].elapsed_time(d1[j]) for j in range(W, W + Kd))
+        tmm = torch.tensor([mm_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmm, op=dist.ReduceOp.MAX)
+        mm = {"multi_uav_updates_per_sec": world * Kd / (float(tmm[0]) * 1e-3), "ms_per_step": float(tmm[0]) / Kd, "steps": Kd,
+              "msckf_matches_per_step": len(steps_d[0][2]), "own_gate_passed_frac_rank0": float(np.mean(gated[W:])),
+              "joint_gate_accepted_frac_rank0": float(np.mean(acc[W:])), "pose_payload_bytes_per_agent": PP * 8,
+              "collective": "all_gather (NCCL), one per update"}
+    # ---- phase D (N > 1): covariance-intersection fusion steps with the compressed payload exchanged over NCCL ----
     ci = None
     if world > 1:
         from x_multi_agent_b200.ci import exchange_payloads, ring_matches
         from x_multi_agent_b200.request_comm import (VLAD_LEN, Keyframe, KeyframeDatabase, exchange_request_response)
         PL = flt.ci_payload_len()
         local = torch.zeros(PL, dtype=torch.float64, device="cuda")
-        matches = ring_matches(rank, world, CFG2["F"])
+        # 16 SLAM-SLAM matches with one peer per fusion step (SURVEY.md 8d), the peer and the feature block rotating from
+        # step to step.  The reference applies every match's correction from the same prior, one after the other
+        # (updater.cpp:22-36): the common-mode gain of a step is n_matches x K, so a step that fuses hundreds of matches
+        # at once overshoots and the gates close for good -- 16 keeps the loop a contraction (16 x ~0.09 with w = 0.1).
+        def step_matches(i):
+            peer = (rank + 1 + i % (world - 1)) % world
+            f0 = (16 * i) % CFG2["F"]
+            return [(peer, (f0 + q) % CFG2["F"], (f0 + q) % CFG2["F"]) for q in range(16)]
+        matches = step_matches(0)
         c0 = [torch.cuda.Event(enable_timing=True) for _ in range(nC)]
         c1 = [torch.cuda.Event(enable_timing=True) for _ in range(nC)]
         inl = []
@@ -381,14 +453,15 @@ def main():
         for i in range(nC):
             # (untimed) the filters keep running between fusion steps: one regular visual update per step, so that
             # every fusion step sees fresh, independently evolved estimates
-            for (t, seq, w, a) in events[next_ev][0]:
+            imu_c, pm_c = next_frame()
+            for (t, seq, w, a) in imu_c:
                 flt.process_imu(t, seq, w, a, want_state=False)
-            flt.set_measurement(packed[next_ev])
+            flt.set_measurement(pm_c)
             stt = flt.process_update_measurement(want_state=True)
             t_last = stt.time
-            next_ev += 1
             flt.synchronize()
             barrier()
+            matches = step_matches(i)
             with torch.cuda.stream(stream):
                 c0[i].record(stream)
                 flt.ci_pack(local.data_ptr())
@@ -423,12 +496,12 @@ def main():
         inl_r = []
         barrier()
         for i in range(nR):
-            for (t, seq, w, a) in events[next_ev][0]:
+            imu_c, pm_c = next_frame()
+            for (t, seq, w, a) in imu_c:
                 flt.process_imu(t, seq, w, a, want_state=False)
-            flt.set_measurement(packed[next_ev])
+            flt.set_measurement(pm_c)
             stt = flt.process_update_measurement(want_state=True)
             t_last = stt.time
-            next_ev += 1
             # keyframe selection is the caller's policy (vio_updater.cpp:451-484): here every second frame
             if i % 2 == 0:
                 snap = torch.empty(PL, dtype=torch.float64, device="cuda")
@@ -445,7 +518,8 @@ def main():
                 for peer, payload in got.items():
                     slots = torch.zeros((world, PL), dtype=torch.float64, device="cuda")
                     slots[peer].copy_(payload)
-                    pm = [(peer, f, f) for f in range(CFG2["F"])]
+                    f0 = (16 * (i + 7 * peer)) % CFG2["F"]
+                    pm = [(peer, (f0 + q) % CFG2["F"], (f0 + q) % CFG2["F"]) for q in range(16)]
                     flt.process_others_packed(t_last, slots.data_ptr(), world, pm, want_state=False)
                 r1[i].record(stream)
             stream.synchronize()
@@ -453,7 +527,7 @@ def main():
                 sent += stats["answers_sent"]
                 recv += stats["answers_received"]
                 if got:
-                    inl_r.append(float(flt.ci_last_gates(CFG2["F"])[:, 0].mean()))
+                    inl_r.append(float(flt.ci_last_gates(16)[:, 0].mean()))
         barrier()
         rc_ms = sum(r0[i].elapsed_time(r1[i]) for i in range(4, nR))
         trc = torch.tensor([rc_ms], dtype=torch.float64, device="cuda")
@@ -463,54 +537,6 @@ def main():
                               "answer_bytes": PL * 8, "inlier_frac_mean_rank0": float(np.mean(inl_r)) if inl_r else None,
                               "transport": "all_gather of the 2592-byte requests + NCCL send/recv of the answers "
                                            "(accepted pairs only; a keyframe is sent to a peer at most once)"}
-    # ---- phase D (N > 1): MULTI_UAV visual updates with 32 MSCKF-MSCKF matches per peer; every agent publishes its
-    #      pose payload (window + 6M x 6M covariance block) through one all-gather per update --------------------------
-    mm = None
-    if world > 1:
-        from x_multi_agent_b200.ci import exchange_payloads
-        from x_multi_agent_b200.synth import Scenario, SynthConfig
-        Kd = min(K, 12)
-        peers = [p for p in range(world) if p != rank]
-        peer_scn = {p: Scenario(SynthConfig(M=CFG2["M"], F=CFG2["F"], K=1, seed=p, slam_init_frame=CFG2["M"], slam_lm_seed=4242))
-                    for p in peers}   # analytic truth of the other agents' trajectories (same generator, their seed)
-        k0 = N_FILL + next_ev
-        PP = flt.pose_payload_len()
-        local = torch.zeros(PP, dtype=torch.float64, device="cuda")
-        steps_d = []
-        for j in range(W + Kd):
-            imu, m = steady_events(scn, k0 + j, 1)[0]
-            lms = scn.last_msckf_lms
-            win = list(range(k0 + j - CFG2["M"], k0 + j))     # frames held by a peer's window when it packs its payload
-            mt = [(p, 0, a * 32 + q, peer_scn[p]._project(lms[a * 32 + q], win)) for a, p in enumerate(peers) for q in range(32)]
-            steps_d.append((imu, PackedMeasurement(m), mt))
-        d0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
-        d1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
-        acc, gated = [], []
-        barrier()
-        for j, (imu, pm, mt) in enumerate(steps_d):
-            for (t, seq, w, a) in imu:
-                flt.process_imu(t, seq, w, a, want_state=False)
-            flt.set_measurement(pm)
-            with torch.cuda.stream(stream):
-                flush.zero_()
-                d0[j].record(stream)
-                flt.pack_poses(local.data_ptr())
-                gathered = exchange_payloads(local)
-                flt.set_msckf_matches_packed(gathered.data_ptr(), world, mt)
-                flt.process_update_measurement(want_state=False)
-                d1[j].record(stream)
-            stream.synchronize()
-            g = flt.mm_last_gates(0)
-            gated.append(float(np.isfinite(g[:, 1]).mean()) if len(g) else 0.0)
-            acc.append(float(g[:, 0].mean()) if len(g) else 0.0)
-        barrier()
-        mm_ms = sum(d0[j].elapsed_time(d1[j]) for j in range(W, W + Kd))
-        tmm = torch.tensor([mm_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmm, op=dist.ReduceOp.MAX)
-        mm = {"multi_uav_updates_per_sec": world * Kd / (float(tmm[0]) * 1e-3), "ms_per_step": float(tmm[0]) / Kd, "steps": Kd,
-              "msckf_matches_per_step": len(steps_d[0][2]), "own_gate_passed_frac_rank0": float(np.mean(gated[W:])),
-              "joint_gate_accepted_frac_rank0": float(np.mean(acc[W:])), "pose_payload_bytes_per_agent": PP * 8,
-              "collective": "all_gather (NCCL), one per update"}
     tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
