@@ -239,6 +239,19 @@ XB_API int xb_ekf_process_others_packed(xb_filter* f, double timestamp, const do
                                         const xb_slam_match* matches, int n_matches, double* xvec_out);
 /* introspection: per match [inlier, gamma] of the last CI step */
 XB_API int xb_ci_last_gates(xb_filter* f, double* out /* 2*n_matches */, int max_matches);
+/* Updater::collaborativeUpdate (src/x/ekf/updater.cpp:22-36) on the work state: stage-level twin of
+ * xb_ekf_process_others. */
+XB_API int xb_updater_collaborative_update(xb_filter* f, const xb_peer_state* peers, int n_peers,
+                                           const xb_slam_match* matches, int n_matches);
+/* The two halves of Ekf::processUpdateMeasurement (src/x/ekf/ekf.cpp:179-213) around Updater::update, for a host-side
+ * template method that drives the stages itself: begin = StateBuffer::closestIdx + copy of the buffered state into the
+ * work state (returns 1, 0 for std::nullopt), end = write-back + repropagateFromStateAtIdx (ekf.cpp:227-255). */
+XB_API int xb_ekf_update_begin(xb_filter* f, double timestamp, double* xvec_out /* may be NULL */);
+XB_API int xb_ekf_update_end(xb_filter* f, double* xvec_out);
+/* Bookkeeping a host-side x::State needs to refer to a buffered covariance: time stamp of a ring slot and the serial
+ * number of the covariance it holds (-1: gone); the slot the last update was applied to. */
+XB_API int xb_ekf_slot_info(const xb_filter* f, int slot, double* time_out, int* serial_out);
+XB_API int xb_ekf_last_update_slot(const xb_filter* f);
 
 /* ---- introspection for tests / profiling ------------------------------------------------------ */
 XB_API int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles); /* returns count */

@@ -41,7 +41,9 @@ def test_cxx_binding_replays_identically(tmp_path):
     ev = record(Scenario(cfg), 12)
     exe = tmp_path / "test_x_api"
     libdir = ROOT / "x_multi_agent_b200"
-    subprocess.run(["g++", "-std=c++17", "-O2", f"-I{ROOT / 'include'}", "-o", os.fspath(exe),
+    # Eigen is not installed here: the binding is compiled against the stand-in of the test infrastructure
+    subprocess.run(["g++", "-std=c++17", "-O2", f"-I{ROOT / 'include'}", f"-I{ROOT / 'oracle' / 'ref_build' / 'shim'}", "-o",
+                    os.fspath(exe),
                     os.fspath(ROOT / "tests" / "cxx" / "test_x_api.cpp"), f"-L{libdir}", "-lxb200", f"-Wl,-rpath,{libdir}"],
                    check=True)
     _serialise(cfg, ev, 16).tofile(tmp_path / "events.bin")

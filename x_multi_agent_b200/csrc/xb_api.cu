@@ -149,6 +149,8 @@ struct xb_filter {
   std::vector<double> h_time;  // mirror of State::time_
   std::vector<double> h_am;    // mirror of a_m (accel-spike substitution, ekf.cpp:119-128)
   std::vector<int> slot_gen;
+  std::vector<int> slot_serial;   // stamp of the covariance a slot refers to (changes whenever the slot is rewritten)
+  int serial = 0, last_update_slot = -1;
   int tail = 0, head = 0, n_valid = 0;
   int status = 0;  // 0 not initialised, 1 stand-by, 2 initialised
   unsigned last_seq = 0;
@@ -408,6 +410,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   f->h_time.assign(NS, -1.0);
   f->h_am.assign(3 * (size_t)NS, 0.0);
   f->slot_gen.assign(NS, -1);
+  f->slot_serial.assign(NS, 0);
   f->anchor.assign(std::max(F, 1), -1);
 
   int rc;
@@ -768,6 +771,7 @@ extern "C" int xb_ekf_process_imu(xb_filter* f, double t, unsigned seq, const do
   for (int e = 0; e < 3; ++e) f->h_am[3 * f->tail + e] = as[e];
   f->slot_gen[f->tail] = f->slot_gen[last];
   f->slot_asym[f->tail] = f->slot_asym[last];
+  f->slot_serial[f->tail] = ++f->serial;
   if (xvec_out) return xb_ekf_get_state(f, f->tail, xvec_out) < 0 ? XB_E_CUDA : 1;
   return 1;
 }
@@ -900,6 +904,7 @@ static int work_store_impl(xb_filter* f, int slot, bool copy_estimates) {
   if (f->asym_clones > 0) launch_extract_strip2(f->stream, f->N, f->d_Pw, f->d_strip2 + (size_t)slot * 15 * f->N);
   f->slot_asym[slot] = f->asym_clones;
   f->slot_gen[slot] = f->cur_gen;
+  f->slot_serial[slot] = ++f->serial;
   return XB_OK;
 }
 extern "C" int xb_work_store(xb_filter* f, int slot) { return work_store_impl(f, slot, true); }
@@ -1625,21 +1630,48 @@ static int repropagate_from(xb_filter* f, int idx) {  // ekf.cpp:227-255
   StageTimer st_(f, ST_PROPAGATE);
   ImuSample none{};
   propagate_chain(f, idx, n, none);
-  for (int c = idx, k = 0; k < n; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; f->slot_asym[c] = f->slot_asym[idx]; }
+  for (int c = idx, k = 0; k < n; ++k) {
+    c = next_idx(f, c);
+    f->slot_gen[c] = f->slot_gen[idx];
+    f->slot_asym[c] = f->slot_asym[idx];
+    f->slot_serial[c] = ++f->serial;
+  }
   return n;
 }
 
 // ---- Ekf::processUpdateMeasurement (ekf.cpp:179-213) ---------------------------------------------------------------------
-extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
+// The two halves of Ekf::processUpdateMeasurement around Updater::update, for a host-side template method that drives
+// the stages itself (include/x/xb200_binding.hpp): begin = closestIdx + copy of the buffered state into the work state
+// (ekf.cpp:184-196), end = write-back + re-propagation of the newer states (ekf.cpp:201-205, 227-255).
+extern "C" int xb_ekf_update_begin(xb_filter* f, double timestamp, double* xvec_out) {
   if (!f) return fail(XB_E_INVALID, "null filter");
   if (f->status == 0) return 0;
-  const int idx = closest_idx(f, f->meas_time);
+  const int idx = closest_idx(f, timestamp);
   if (idx < 0) return 0;
   if (f->slot_gen[idx] < 0) return fail(XB_E_STALE, "the buffered state's covariance generation was recycled: raise xb_config.n_generations");
   int rc;
   if ((rc = xb_work_load(f, idx)) < 0) return rc;
+  f->last_update_slot = idx;
   f->xw_final = false;
+  if (xvec_out) {
+    CK(cudaMemcpyAsync(xvec_out, f->d_xw, sizeof(double) * f->LX, cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+  }
+  return 1;
+}
+static int update_end(xb_filter* f, int idx, double* xvec_out);
+extern "C" int xb_ekf_update_end(xb_filter* f, double* xvec_out) {
+  if (!f || f->last_update_slot < 0) return fail(XB_E_INVALID, "no update in progress");
+  return update_end(f, f->last_update_slot, xvec_out);
+}
+extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
+  int rc = xb_ekf_update_begin(f, f ? f->meas_time : 0.0, nullptr);
+  if (rc <= 0) return rc;
   if ((rc = xb_updater_update(f)) < 0) return rc;
+  return update_end(f, f->last_update_slot, xvec_out);
+}
+static int update_end(xb_filter* f, int idx, double* xvec_out) {
+  int rc;
   int n_re = 0;
   for (int c = idx; c != f->tail; c = next_idx(f, c)) ++n_re;
   if (f->overlap && f->xw_final && n_re > 0 && n_re <= 128) {
@@ -1661,7 +1693,12 @@ extern "C" int xb_ekf_process_update(xb_filter* f, double* xvec_out) {
       launch_prop_strips(f->stream, f->d_strip, f->N, f->NS, idx, n_re, f->d_FQ2);
       if (f->slot_asym[idx] > 0) launch_prop_strips(f->stream, f->d_strip2, f->N, f->NS, idx, n_re, f->d_FQ2, 1);
     }
-    for (int c = idx, k = 0; k < n_re; ++k) { c = next_idx(f, c); f->slot_gen[c] = f->slot_gen[idx]; f->slot_asym[c] = f->slot_asym[idx]; }
+    for (int c = idx, k = 0; k < n_re; ++k) {
+      c = next_idx(f, c);
+      f->slot_gen[c] = f->slot_gen[idx];
+      f->slot_asym[c] = f->slot_asym[idx];
+      f->slot_serial[c] = ++f->serial;
+    }
   } else {
     if ((rc = xb_work_store(f, idx)) < 0) return rc;
     repropagate_from(f, idx);
@@ -1737,6 +1774,7 @@ extern "C" int xb_ekf_process_others_packed(xb_filter* f, double t, const double
   if (f->slot_gen[idx] < 0) return fail(XB_E_STALE, "the buffered state's covariance generation was recycled: raise xb_config.n_generations");
   int rc;
   if ((rc = xb_work_load(f, idx)) < 0) return rc;
+  f->last_update_slot = idx;
   if ((rc = collaborative_update_packed(f, dev_gathered, n_agents, matches, n_matches)) < 0) return rc;
   if ((rc = xb_work_store(f, idx)) < 0) return rc;
   repropagate_from(f, idx);
@@ -1749,8 +1787,7 @@ extern "C" int xb_ekf_process_others_packed(xb_filter* f, double t, const double
 
 // Reference-format entry: peers as SimpleState (full covariance).  The host only gathers, per match, the peer's 9x9
 // covariance block and forms the 13-double payload entry; everything N-sized runs on the device.
-extern "C" int xb_ekf_process_others(xb_filter* f, double t, const xb_peer_state* peers, int n_peers,
-                                     const xb_slam_match* matches, int n_matches, double* xvec_out) {
+static int peers_to_payload(xb_filter* f, const xb_peer_state* peers, int n_peers, const xb_slam_match* matches, int n_matches) {
   if (!f || (n_peers > 0 && !peers)) return fail(XB_E_INVALID, "null argument");
   if (n_peers > f->ci_max_agents) return fail(XB_E_CAPACITY, "too many peers");
   const int PL = f->ci_payload_len;
@@ -1802,8 +1839,31 @@ extern "C" int xb_ekf_process_others(xb_filter* f, double t, const xb_peer_state
   }
   CK(cudaMemcpyAsync(f->d_ci_gather, pay.data(), sizeof(double) * pay.size(), cudaMemcpyHostToDevice, f->stream));
   CK(cudaStreamSynchronize(f->stream));
+  return XB_OK;
+}
+extern "C" int xb_ekf_process_others(xb_filter* f, double t, const xb_peer_state* peers, int n_peers,
+                                     const xb_slam_match* matches, int n_matches, double* xvec_out) {
+  int rc = peers_to_payload(f, peers, n_peers, matches, n_matches);
+  if (rc < 0) return rc;
   return xb_ekf_process_others_packed(f, t, f->d_ci_gather, std::max(1, n_peers), matches, n_matches, xvec_out);
 }
+// Updater::collaborativeUpdate (updater.cpp:22-36) on the WORK state (stage-level twin of xb_ekf_process_others)
+extern "C" int xb_updater_collaborative_update(xb_filter* f, const xb_peer_state* peers, int n_peers,
+                                               const xb_slam_match* matches, int n_matches) {
+  if (!f || !f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
+  int rc = peers_to_payload(f, peers, n_peers, matches, n_matches);
+  if (rc < 0) return rc;
+  return collaborative_update_packed(f, f->d_ci_gather, std::max(1, n_peers), matches, n_matches);
+}
+// Ring-buffer bookkeeping a host-side x::State needs to refer to a buffered covariance safely: time stamp and
+// covariance generation of a slot (-1: the slot's covariance is gone), and the slot the last update was stored in.
+extern "C" int xb_ekf_slot_info(const xb_filter* f, int slot, double* time_out, int* generation_out) {
+  if (!f || slot < 0 || slot >= f->NS) return fail(XB_E_INVALID, "bad slot");
+  if (time_out) *time_out = f->h_time[slot];
+  if (generation_out) *generation_out = f->slot_gen[slot] < 0 ? -1 : f->slot_serial[slot];
+  return XB_OK;
+}
+extern "C" int xb_ekf_last_update_slot(const xb_filter* f) { return f ? f->last_update_slot : -1; }
 
 extern "C" int xb_ci_last_gates(xb_filter* f, double* out, int max_matches) {
   const int n = std::min(max_matches, f->ci_last_n);

@@ -110,6 +110,11 @@ SIGNATURES = {
     "xb_profile_read": (C.c_int, [_VP, C.POINTER(C.c_char_p), c_double_p, C.POINTER(C.c_longlong), C.c_int]),
     "xb_kernel_launches": (C.c_longlong, [_VP]),
     "xb_chi2_quantile": (C.c_double, [C.c_double, C.c_double]),
+    "xb_updater_collaborative_update": (C.c_int, [_VP, C.POINTER(XbPeerState), C.c_int, C.POINTER(XbSlamMatch), C.c_int]),
+    "xb_ekf_update_begin": (C.c_int, [_VP, C.c_double, c_double_p]),
+    "xb_ekf_update_end": (C.c_int, [_VP, c_double_p]),
+    "xb_ekf_slot_info": (C.c_int, [_VP, C.c_int, c_double_p, c_int_p]),
+    "xb_ekf_last_update_slot": (C.c_int, [_VP]),
 }
 
 _lib = None
