@@ -823,3 +823,34 @@ def test_ci_fusion_at_cfg2_size_with_four_peers():
     rp.done()
     for _, dev in agents:
         dev.close()
+
+
+@pytest.mark.gpu
+def test_two_filters_on_one_gpu_run_concurrently():
+    """Two agents' filters on ONE GPU, driven from two host threads at the same time (ctypes releases the GIL): their
+    tile-Cholesky dataflow launches are cooperative (all CTAs of a launch resident or none), so neither can starve the
+    other.  Both must reproduce their single-filter results bit for bit."""
+    import threading
+    cfgs = [SynthConfig(M=30, F=40, K=60, seed=21 + a, slam_init_frame=30) for a in range(2)]
+    evs = [record(Scenario(c), 40) for c in cfgs]
+
+    def run(c, ev, out):
+        dev = Filter(c.M, c.F, max_tracks=c.K, sigma_img=c.sigma_img, n_slots=64)
+        xs = []
+        replay(ev, dev, lambda k, m, st: xs.append(st.x.copy()))
+        dev.synchronize()
+        out.append(np.vstack(xs))
+        dev.close()
+
+    alone = [[], []]
+    for a in range(2):
+        run(cfgs[a], evs[a], alone[a])
+    both = [[], []]
+    th = [threading.Thread(target=run, args=(cfgs[a], evs[a], both[a])) for a in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+        assert not t.is_alive(), "a filter hung while the other one was running"
+    for a in range(2):
+        assert np.array_equal(alone[a][0], both[a][0])

@@ -8,6 +8,9 @@
 #include <atomic>
 #include <cstdlib>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "xb_kernels.h"
 
 namespace xb {
@@ -799,7 +802,22 @@ void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pa
   static std::atomic<unsigned> g_epoch{0};
   unsigned ep = ++g_epoch;
   if ((int)ep == 0) ep = ++g_epoch;  // 0 is the value of a freshly allocated flag buffer
-  k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace, (int)ep);
+  // Cooperative launch: the CTAs of this kernel wait on one another (release/acquire flags), so they must all be
+  // resident at once.  The grid is sized from the occupancy query above; the cooperative launch makes the scheduler
+  // place it all-or-nothing, which also covers dataflow launches of OTHER filters on the same GPU (two partially
+  // resident grids could otherwise wait for each other until the spin limit).  XB_NO_COOP=1: plain launch (A/B).
+  static const bool coop = !getenv("XB_NO_COOP");
+  int epi = (int)ep;
+  if (coop) {
+    void* args[] = {&T, &ld, (void*)&rt, (void*)&ct, &cr, &flags, &err, &piv_tol, &diag0, &trace, &epi};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tallchol, dim3(1 + nworkers), dim3(CP_THREADS), args, 0, s);
+    if (e != cudaSuccess) {   // too large to be co-resident: must not happen (grid sized from the occupancy query)
+      fprintf(stderr, "xb200: cooperative launch of k_tallchol failed: %s\n", cudaGetErrorString(e));
+      cudaMemsetAsync(err, 0xff, sizeof(int), s);
+    }
+  } else {
+    k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace, epi);
+  }
   count_launch();
 }
 void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int* flags, int* err, double piv_tol,
