@@ -66,13 +66,17 @@ def workload_config(n_gpus, extra=None):
     return c
 
 
-def build_scenario(seed):
+CFG5 = dict(M=50, F=800, K=3200)   # BASELINE configs[4] per agent (800 SLAM + 3200 MSCKF of 4k features)
+
+
+def build_scenario(seed, dims=None, n_fill=None):
     from x_multi_agent_b200.synth import Scenario, SynthConfig, record
-    cfg = SynthConfig(M=CFG2["M"], F=CFG2["F"], K=FILL_K, seed=seed, slam_init_frame=CFG2["M"], slam_lm_seed=4242,
+    dims = dims or CFG2
+    cfg = SynthConfig(M=dims["M"], F=dims["F"], K=FILL_K, seed=seed, slam_init_frame=dims["M"], slam_lm_seed=4242,
                       slam_msckf_init_frac=1.0, **IMU_NOISE)
     scn = Scenario(cfg)
-    fill = record(scn, N_FILL)
-    scn.c.K = CFG2["K"]
+    fill = record(scn, n_fill or N_FILL)
+    scn.c.K = dims["K"]
     return scn, fill
 
 
@@ -243,6 +247,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-semantics", action="store_true", help="skip the extra oc_projection = 1 run (profiling)")
     ap.add_argument("--precision", type=int, default=int(os.environ.get("XB_DOWNDATE_PRECISION", "0")))
     args = ap.parse_args()
     # stdout carries exactly one JSON line: native libraries (NCCL version banner, ...) write to fd 1 directly, so fd 1
@@ -341,6 +346,28 @@ def main():
     inl0 = flt.debug_int("inlier0", CFG2["K"])
     msckf_inlier_frac = float(inl0.mean()) if len(inl0) else None
     slam_inlier_frac = float(flt.debug_int("slam_inlier", CFG2["F"]).mean())
+    # ---- cfg-5 dimensions (N = 2715: the covariance kernels become throughput kernels), N = 1 only ----------------
+    cfg5 = None
+    if world == 1 and not args.no_reference_semantics:
+        n_fill5 = CFG5["M"] + 3
+        scn5, fill5 = build_scenario(seed=5, dims=CFG5, n_fill=n_fill5)
+        f5 = Filter(CFG5["M"], CFG5["F"], max_tracks=CFG5["K"], n_slots=250, device=local_rank, oc_projection=0, n_generations=8,
+                    **IMU_NOISE)
+        f5.set_stream(stream.cuda_stream)
+        replay(fill5, f5)
+        assert f5.n_poses == CFG5["M"] and f5.n_features == CFG5["F"]
+        ev5 = steady_events(scn5, n_fill5, 3 + 8)
+        pk5 = [PackedMeasurement(m, pinned=True) for _, m in ev5]
+        ms5, _, (st5, _) = device_timed(f5, ev5, pk5, 0, 3, 8, True)
+        inl5 = f5.debug_int("inlier0", CFG5["K"])
+        N5 = 15 + 6 * CFG5["M"] + 3 * CFG5["F"]
+        top5 = sorted(((k, v[0] / max(v[1], 1)) for k, v in st5.items() if v[1] > 0), key=lambda kv: -kv[1])[:6]
+        cfg5 = {"workload": "cfg-5 dimensions per agent: 50-pose window, 800 SLAM + 3200 MSCKF (50-obs) tracks per update, "
+                            "N = %d" % N5, "updates_per_sec": 8 / (ms5 * 1e-3), "ms_per_update": ms5 / 8, "steps": 8,
+                "msckf_inlier_frac_last_step": float(inl5.mean()),
+                "top_stages_ms": {k: round(v, 3) for k, v in top5},
+                "covariance_bytes": 8 * N5 * N5}
+        f5.close()
     # ---- phase B: end to end through the C ABI with host buffers ---------------------------------------------
     e2e_s = 0.0
     barrier()
@@ -360,7 +387,7 @@ def main():
     assert np.all(np.isfinite(st.x)), "non-finite state after the benchmark"
     # ---- the same device-timed run with the reference's OC projection as written (N = 1 only) ------------------
     ref_sem = None
-    if world == 1:
+    if world == 1 and not args.no_reference_semantics:
         Kr = min(K, 20)
         scn_r, flt_r, ev_r, pk_r = make_agent(1, W + Kr)
         ms_r, _, _ = device_timed(flt_r, ev_r, pk_r, 0, W, Kr, False)
@@ -630,7 +657,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci, "multi_uav_msckf": mm,
             "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac},
-            "reference_semantics": ref_sem,
+            "reference_semantics": ref_sem, "cfg5": cfg5,
             "imu_us_per_sample": {"value": round(imu_us, 2), "note": "Ekf::processImu (propagateState + propagateCovariance, "
                                   "ekf.cpp:66-140) between updates: device time per IMU sample over the untimed feed of the "
                                   "steady-state phase (10 samples per frame, one fused launch each, issued back to back)"}}

@@ -1,9 +1,11 @@
 # one launch list + full captures of the top kernels of a steady-state cfg-2 update (outputs under gpurun_out/)
-B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
-T=${1:-r01_s2}
-ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/${T}_launches.csv $B > /dev/null 2>&1
+B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-reference-semantics"
+T=${1:-r02}
+ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/${T}_launches.csv $B > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_tracks -s 36 -c 1 -o gpurun_out/${T}_tracks $B > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_tallchol -s 110 -c 3 -o gpurun_out/${T}_tallchol $B > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_downdate_mma -s 45 -c 2 -o gpurun_out/${T}_downdate_mma $B > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_gemm_mma -s 150 -c 7 -o gpurun_out/${T}_gemm_mma $B > /dev/null 2>&1
-ls -la gpurun_out/
+ncu --set full --clock-control none --import-source on -k regex:k_tallchol -s 75 -c 3 -o gpurun_out/${T}_tallchol $B > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_downdate_mma -s 40 -c 2 -o gpurun_out/${T}_downdate_mma $B > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_gemm_mma -s 250 -c 7 -o gpurun_out/${T}_gemm_mma $B > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_prop_step -s 400 -c 1 -o gpurun_out/${T}_prop_step $B > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_omega_small -s 40 -c 1 -o gpurun_out/${T}_omega_small $B > /dev/null 2>&1
+ls -la gpurun_out/ | grep ${T}

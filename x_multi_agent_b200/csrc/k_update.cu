@@ -336,56 +336,55 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
     A[r][c] = v;
   }
   __syncthreads();
-  // Gauss-Jordan with partial pivoting by ONE warp (the 21 pivots are a serial chain: warp-level synchronisation instead of
-  // 126 block-wide barriers); the other warps wait at the barrier below.  A fully unrolled register-resident variant
-  // (row per lane, pivot row by shuffle) was measured 30 us SLOWER: ~3500 straight-line instructions executed once are
-  // instruction-fetch bound, like the unrolled per-track Cholesky.
-  if (t < 32) {
-    const int lane = t;
-    for (int c = 0; c < NOM; ++c) {
-      // pivot row: arg max |A[r][c]|, r >= c (first maximum wins, like the serial search it replaces)
-      double bv = (lane >= c && lane < NOM) ? fabs(A[lane][c]) : -1.0;
-      int bi = lane;
+  // Gauss-Jordan with partial pivoting, all 256 threads: the 21 pivots are a serial chain, but everything inside one
+  // pivot step (swap, scaling, the 21 x 42 elimination) is element-parallel; four block barriers per step (~0.3 us)
+  // instead of a single warp that holds three 21-element register arrays per lane (measured 30 us for the kernel).
+  // Same operations on the same operands as the serial form: scale the pivot row, then v <- fma(-A[r][c], A[c][x], v).
+  __shared__ double fcol[NOM];
+  __shared__ int pvs;
+  // element (r, x) of the 21 x 42 elimination owned by this thread in pass u (fixed over the pivot steps)
+  int er[4], ex[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = t + u * 256;
+    er[u] = e < NOM * 2 * NOM ? e / (2 * NOM) : -1;
+    ex[u] = e % (2 * NOM);
+  }
+  for (int c = 0; c < NOM; ++c) {
+    if (t < 32) {
+      // pivot row: arg max |A[r][c]|, r >= c (first maximum wins)
+      double bv = (t >= c && t < NOM) ? fabs(A[t][c]) : -1.0;
+      int bi = t;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      // a non-finite column (the factorisation met a non-positive pivot: S was not positive definite) must not
-      // select a row outside the matrix; the error word makes xb_synchronize report it
-      const int pv = (bi >= c && bi < NOM && bv == bv) ? bi : c;
-      if (lane == 0 && !(bv > 0.0) && err) atomicOr(err, 2);
-      if (pv != c)
-        for (int x = lane; x < 2 * NOM; x += 32) { const double tmp = A[c][x]; A[c][x] = A[pv][x]; A[pv][x] = tmp; }
-      __syncwarp();
-      const double d = A[c][c];
-      __syncwarp();
-      for (int x = lane; x < 2 * NOM; x += 32) A[c][x] /= d;
-      __syncwarp();
-      // elimination: lane <-> column(s) cc = lane, lane + 32; the multipliers A[r][c] are broadcasts.  All loads first,
-      // then the FMAs, then the stores (the compiler cannot move a load of A above a store to A on its own)
-      const int c1 = lane + 32;
-      const bool has1 = c1 < 2 * NOM;
-      const double p0 = A[c][lane], p1 = has1 ? A[c][c1] : 0.0;
-      double fr[NOM], v0[NOM], v1[NOM];
-#pragma unroll
-      for (int r = 0; r < NOM; ++r) { fr[r] = A[r][c]; v0[r] = A[r][lane]; v1[r] = has1 ? A[r][c1] : 0.0; }
-#pragma unroll
-      for (int r = 0; r < NOM; ++r) { v0[r] = fma(-fr[r], p0, v0[r]); v1[r] = fma(-fr[r], p1, v1[r]); }
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < NOM; ++r) {
-        if (r == c) continue;
-        if (lane != c) A[r][lane] = v0[r];
-        if (has1) A[r][c1] = v1[r];
+      if (t == 0) {
+        // a non-finite column (the factorisation met a non-positive pivot: S was not positive definite) must not
+        // select a row outside the matrix; the error word makes xb_synchronize report it
+        pvs = (bi >= c && bi < NOM && bv == bv) ? bi : c;
+        if (!(bv > 0.0) && err) atomicOr(err, 2);
       }
-      __syncwarp();
-      if (lane < NOM && lane != c) A[lane][c] = 0.0;
-      __syncwarp();
     }
+    __syncthreads();
+    const int pv = pvs;
+    if (pv != c && t < 2 * NOM) { const double tmp = A[c][t]; A[c][t] = A[pv][t]; A[pv][t] = tmp; }
+    __syncthreads();
+    const double d = A[c][c];
+    if (t < NOM) fcol[t] = A[t][c];          // multipliers of this step (row c's entry is the pivot itself)
+    __syncthreads();
+    if (t < 2 * NOM) A[c][t] /= d;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = er[u], x = ex[u];
+      if (r < 0 || r == c) continue;
+      A[r][x] = (x == c) ? 0.0 : fma(-fcol[r], A[c][x], A[r][x]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // C = E * inv
   for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int r = e / NOM, c = e % NOM;
