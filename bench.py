@@ -608,7 +608,7 @@ def main():
     avg_ms = per_stage[dom][0]
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this kernel
-        traffic = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text()).get(dom)
+        traffic = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text()).get(dom)
     except Exception:
         pass
     fp64_peak = 36.9  # TFLOP/s, DFMA = DMMA peak measured with tools/bench_dmma.cu on this pool's B200

@@ -9,7 +9,7 @@ from x_multi_agent_b200 import Filter
 from x_multi_agent_b200.synth import replay
 
 scn, fill = bench.build_scenario(0)
-flt = Filter(30, 200, max_tracks=800, n_slots=250)
+flt = Filter(30, 200, max_tracks=800, n_slots=250, oc_projection=0, **bench.IMU_NOISE)
 replay(fill, flt)
 ev = bench.steady_events(scn, bench.N_FILL, 3)
 for imu, m in ev:

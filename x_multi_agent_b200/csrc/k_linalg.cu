@@ -590,7 +590,7 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
     __threadfence();
     st_release(&ready[i * ct + jcol], epoch);
     if (trace && i < ct + 2 && i >= jcol + 2) {
-      long long* o = trace + 6 * (size_t)(ct + jcol * 2 + (i - jcol - 2) % 2);
+      long long* o = trace + 10 * (size_t)(ct + jcol * 2 + (i - jcol - 2) % 2);
       o[0] = i; o[1] = jcol; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
     }
   }
@@ -623,6 +623,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       tile_load(Ds, gD, ld, t, CP_THREADS, false);
       if (has_e) tile_load(Es[eb], gE, ld, t, CP_THREADS, false);
       __syncthreads();
+      if (trace && t == 0) trace[10 * (size_t)j + 9] = gtimer();
       if (t < TC) dorig[t] = diag0 ? diag0[j * TC + t] : 0.0;
       __syncthreads();
       // previous column's E (= L(j, j-1)) is in Es[eb^1] row-major; k-major copy into Ws for the rank-32 updates
@@ -637,6 +638,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
         warp_potrf32(Ds, Ls, dorig, piv_tol, lane);
         const double d = Ds[lane][lane];
         rd[lane] = d != 0.0 ? 1.0 / d : 0.0;
+        if (trace && lane == 0) trace[10 * (size_t)j + 6] = gtimer();
       } else if (!first && has_e) {
         // meanwhile: E -= L(j+1, j-1) L(j, j-1)^T   (L(j+1,j-1) comes from a worker)
         if (t == 32) flag_spin(&ready[(j + 1) * ct + (j - 1)], err, epoch);
@@ -668,12 +670,14 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
 #pragma unroll
             for (int v = 0; v < 4; ++v) Es[eb][ty * 4 + u][tx * 4 + v] = acc[u][v];
         }
+        if (trace && t == 32) trace[10 * (size_t)j + 7] = gtimer();
       }
       __syncthreads();
       const long long tr2 = trace ? gtimer() : 0;
       // publish L(j,j) (warps 1-3) while warp 0 solves E against it
       if (warp == 0) {
         if (has_e) warp_trsm32(Es[eb], Ds, rd, lane);
+        if (trace && lane == 0) trace[10 * (size_t)j + 8] = gtimer();
       } else {
         tile_store(gD, ld, Ds, t - 32, 96);
         asm volatile("bar.sync 1, 96;" ::: "memory");
@@ -688,7 +692,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
           st_release(&ready[(j + 1) * ct + j], epoch);
         }
         if (trace) {
-          long long* o = trace + 6 * (size_t)j;
+          long long* o = trace + 10 * (size_t)j;
           o[0] = j; o[1] = j; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
         }
       }

@@ -503,7 +503,7 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_Cb, (size_t)4 * (n_pad + 96) * 96, double);
   DA(f->d_err, 4, int);
   if (getenv("XB_TRACK_PROF")) DA(f->d_track_prof, 12 * (size_t)maxT, long long);
-  if (getenv("XB_CHOL_TRACE")) DA(f->d_trace, 6 * ((size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64), long long);
+  if (getenv("XB_CHOL_TRACE")) DA(f->d_trace, 10 * ((size_t)((m_pad + n_pad + 96) / 32) * (m_pad / 32) + 64), long long);
 
   {  // the manage tables travel as ONE host-to-device copy: [rowmap N | ccols 15 (6 + 3F) | featsrc F | reanch F]
     const size_t nc = 15 * (size_t)(6 + 3 * std::max(1, F));
@@ -1988,12 +1988,12 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
   }
   else if (n == "chol_trace") {
     if (!f->d_trace) return fail(XB_E_INVALID, "set XB_CHOL_TRACE=1 before xb_create");
-    std::vector<long long> tr(6 * (size_t)f->trace_tiles);
+    std::vector<long long> tr(10 * (size_t)f->trace_tiles);
     CK(cudaStreamSynchronize(f->stream));
   CK(cudaStreamSynchronize(f->side));
     CK(cudaMemcpy(tr.data(), f->d_trace, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost));
     cnt = std::min((size_t)max_doubles, tr.size());
-    for (size_t i = 0; i < cnt; ++i) out[i] = (double)(tr[i] - ((i % 6) >= 2 ? tr[2] : 0));
+    for (size_t i = 0; i < cnt; ++i) out[i] = (double)(tr[i] - ((i % 10) >= 2 ? tr[2] : 0));
     return (int)cnt;
   }
   else return fail(XB_E_INVALID, "unknown debug buffer " + n);
