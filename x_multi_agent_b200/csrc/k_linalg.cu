@@ -398,55 +398,20 @@ __device__ __forceinline__ long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// one thread polls (relaxed), then a single acquire orders the tile reads that follow
+// one thread polls with acquire loads; the CTA / group barrier that follows extends the ordering to the other threads.
+// Publishing side: tile stores by all threads, barrier, then ONE st.release by one thread (release is cumulative over the
+// barrier: no separate __threadfence, which costs a second ~0.5 us round trip per hand-over).
 // A flag is "set" when it holds the epoch of the current launch (a process-wide launch counter): no memset between
 // launches, stale values of earlier launches never match.
+template <bool BACKOFF = false>
 __device__ __forceinline__ void flag_spin(const int* flag, int* err, int epoch) {
   long long spins = 0;
-  while (ld_relaxed(flag) != epoch) {
+  while (ld_acquire(flag) != epoch) {   // every poll is an acquire: no second round trip once the flag has flipped
+    if (BACKOFF) __nanosleep(40);       // workers: leave the issue slots of the SM to whoever shares it (the chain CTA)
     if (++spins > (1ll << 22)) { atomicExch(err, 1); break; }
   }
-  (void)ld_acquire(flag);
 }
 
-// 32x32 lower Cholesky by one warp: lane r keeps row r in registers, finished rows of L are mirrored in
-// shared memory (Ls) and read back as broadcasts (left-looking).  Cs: in = tile, out = L (upper part zero).
-// Measured alternative (rejected): right-looking in registers with the multipliers exchanged by shuffle and the bulk
-// update software-pipelined around the pivot chain -- 1100 64-bit shuffles per tile make it 2x SLOWER (tile column
-// 12 -> 24 us) than the 500 broadcast shared-memory loads of this version.  A left-looking variant with one column of
-// look-ahead (partial dot product of column c+1 issued under the rsqrt of pivot c, last term by one shuffle) measured
-// the same 5.7 us per tile as this one (tools/chol_trace.py): the tile is issue-bound on its ~2300 instructions executed
-// by a single warp, not bound by the pivot chain alone.
-__device__ __forceinline__ void warp_potrf32(double (*Cs)[TC + 1], double (*Ls)[TC + 1], const double* dorig,
-                                             double piv_tol, int lane) {
-  double a[TC];
-#pragma unroll
-  for (int k = 0; k < TC; ++k) a[k] = Cs[lane][k];
-#pragma unroll
-  for (int c = 0; c < TC; ++c) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int k = 0; k < c; ++k) {
-      const double lc = Ls[c][k];
-      if ((k & 3) == 0) s0 = fma(a[k], lc, s0);
-      else if ((k & 3) == 1) s1 = fma(a[k], lc, s1);
-      else if ((k & 3) == 2) s2 = fma(a[k], lc, s2);
-      else s3 = fma(a[k], lc, s3);
-    }
-    const double v = a[c] - ((s0 + s1) + (s2 + s3));
-    const double piv = __shfl_sync(0xffffffffu, v, c);
-    const bool ok = piv > piv_tol * fabs(dorig[c]) && piv > 0.0;
-    const double rs = ok ? rsqrt(piv) : 0.0;
-    double l = 0.0;
-    if (lane == c) l = piv * rs;
-    else if (lane > c) l = v * rs;
-    a[c] = l;
-    Ls[lane][c] = l;
-    __syncwarp();
-  }
-#pragma unroll
-  for (int k = 0; k < TC; ++k) Cs[lane][k] = a[k];
-}
 // X L^T = C for the 32 rows of C (lane = row, registers), L and its reciprocal diagonal in shared memory.
 __device__ __forceinline__ void warp_trsm32(double (*Cs)[TC + 1], double (*Ls)[TC + 1], const double* rd, int lane) {
   double a[TC];
@@ -461,6 +426,82 @@ __device__ __forceinline__ void warp_trsm32(double (*Cs)[TC + 1], double (*Ls)[T
   }
 #pragma unroll
   for (int k = 0; k < TC; ++k) Cs[lane][k] = a[k];
+}
+// same solve, the result is also stored k-major (Wt[k][row]) for the tensor-core products that consume it next
+__device__ __forceinline__ void warp_trsm32_t(double (*Cs)[TC + 1], double (*Ls)[TC + 1], const double* rd, double (*Wt)[TC + 1],
+                                              int lane) {
+  double a[TC];
+#pragma unroll
+  for (int k = 0; k < TC; ++k) a[k] = Cs[lane][k];
+#pragma unroll
+  for (int c = 0; c < TC; ++c) {
+    const double x = a[c] * rd[c];
+    a[c] = x;
+#pragma unroll
+    for (int k = c + 1; k < TC; ++k) a[k] = fma(-x, Ls[k][c], a[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < TC; ++k) { Cs[lane][k] = a[k]; Wt[k][lane] = a[k]; }
+}
+__device__ __forceinline__ void bar_group(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// 32x32 lower Cholesky by one warp, LEFT-looking and blocked by 4 columns, in place: lane r keeps row r in registers and
+// mirrors its finished entries in Cs (read back by the other lanes as broadcasts).  Per block step: the four dot
+// products of the row against the finished rows c0..c0+3 (8 independent chains), ten shuffles fetch the updated 4x4
+// diagonal block, every lane factors it redundantly (the serial part: 4 dependent rsqrt), then solves its own four
+// entries.  One shuffle round / one __syncwarp / one shared-memory round trip per FOUR pivots instead of per pivot:
+// tools/bench_potrf4.cu measures it against warp_potrf32 (same pivot guard; rd = reciprocal diagonal, 0 if skipped).
+__device__ __forceinline__ void warp_potrf32_b4(double (*Cs)[TC + 1], const double* dorig, double piv_tol, double* rd, int lane) {
+  // fully unrolled with the row in registers; a compact-loop variant with the row in shared memory measured 8.9k cycles
+  // against 6.9k for this one in isolation (tools/bench_potrf4.cu) and 60 against 55 us per 6-column launch in the kernel
+  double a[TC];
+#pragma unroll
+  for (int k = 0; k < TC; ++k) a[k] = Cs[lane][k];
+#pragma unroll
+  for (int c0 = 0; c0 < TC; c0 += 4) {
+    double v0 = a[c0], v1 = a[c0 + 1], v2 = a[c0 + 2], v3 = a[c0 + 3], w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < c0; k += 2) {
+      const double ak = a[k], ak1 = a[k + 1];
+      v0 = fma(-ak, Cs[c0][k], v0); v1 = fma(-ak, Cs[c0 + 1][k], v1); v2 = fma(-ak, Cs[c0 + 2][k], v2); v3 = fma(-ak, Cs[c0 + 3][k], v3);
+      w0 = fma(-ak1, Cs[c0][k + 1], w0); w1 = fma(-ak1, Cs[c0 + 1][k + 1], w1); w2 = fma(-ak1, Cs[c0 + 2][k + 1], w2);
+      w3 = fma(-ak1, Cs[c0 + 3][k + 1], w3);
+    }
+    v0 += w0; v1 += w1; v2 += w2; v3 += w3;
+    const unsigned FULL = 0xffffffffu;
+    const double a00 = __shfl_sync(FULL, v0, c0), a10 = __shfl_sync(FULL, v0, c0 + 1), a11 = __shfl_sync(FULL, v1, c0 + 1),
+                 a20 = __shfl_sync(FULL, v0, c0 + 2), a21 = __shfl_sync(FULL, v1, c0 + 2), a22 = __shfl_sync(FULL, v2, c0 + 2),
+                 a30 = __shfl_sync(FULL, v0, c0 + 3), a31 = __shfl_sync(FULL, v1, c0 + 3), a32 = __shfl_sync(FULL, v2, c0 + 3),
+                 a33 = __shfl_sync(FULL, v3, c0 + 3);
+    const double t0 = piv_tol * fabs(dorig[c0]), t1 = piv_tol * fabs(dorig[c0 + 1]), t2 = piv_tol * fabs(dorig[c0 + 2]),
+                 t3 = piv_tol * fabs(dorig[c0 + 3]);
+    const double q0 = rsqrt(a00);
+    const double r0 = (a00 > t0 && a00 > 0.0) ? q0 : 0.0;
+    const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+    const double p1 = fma(-l10, l10, a11);
+    const double q1 = rsqrt(p1);
+    const double r1 = (p1 > t1 && p1 > 0.0) ? q1 : 0.0;
+    const double l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
+    const double p2 = fma(-l21, l21, fma(-l20, l20, a22));
+    const double q2 = rsqrt(p2);
+    const double r2 = (p2 > t2 && p2 > 0.0) ? q2 : 0.0;
+    const double l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
+    const double p3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
+    const double q3 = rsqrt(p3);
+    const double r3 = (p3 > t3 && p3 > 0.0) ? q3 : 0.0;
+    // own row: for the lanes of the block itself the same formulas reproduce l_ij (j < i) and l_ii = p_i r_i
+    double x0 = v0 * r0;
+    double x1 = fma(-x0, l10, v1) * r1;
+    double x2 = fma(-x1, l21, fma(-x0, l20, v2)) * r2;
+    double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, v3))) * r3;
+    if (lane < c0) x0 = 0.0;
+    if (lane < c0 + 1) x1 = 0.0;
+    if (lane < c0 + 2) x2 = 0.0;
+    if (lane < c0 + 3) x3 = 0.0;
+    a[c0] = x0; a[c0 + 1] = x1; a[c0 + 2] = x2; a[c0 + 3] = x3;
+    Cs[lane][c0] = x0; Cs[lane][c0 + 1] = x1; Cs[lane][c0 + 2] = x2; Cs[lane][c0 + 3] = x3;
+    if (lane == 0) { rd[c0] = r0; rd[c0 + 1] = r1; rd[c0 + 2] = r2; rd[c0 + 3] = r3; }
+    __syncwarp();
+  }
 }
 // C(32x32, smem) -= A(32x32) * B(32x32)^T with A, B stored k-major (At[k][r], Bt[k][c]), on the fp64 tensor cores:
 // the calling group of nthreads = 64 or 128 threads (t = index within the group) splits C into 16x16 quadrants, one or two
@@ -553,7 +594,7 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
     // panel is fresh); otherwise the fetch falls back to the blocking wait after the product.
     double ra[8], rb[8];
     auto fetch_blocking = [&](int k) {
-      if (t == 0) { flag_spin(&ready[i * ct + k], err, epoch); flag_spin(&ready[jcol * ct + k], err, epoch); }
+      if (t == 0) { flag_spin<true>(&ready[i * ct + k], err, epoch); flag_spin<true>(&ready[jcol * ct + k], err, epoch); }
       __syncthreads();
       tile_fetch(ra, T + (size_t)i * TC * ld + (size_t)k * TC, ld, t);
       tile_fetch(rb, T + (size_t)jcol * TC * ld + (size_t)k * TC, ld, t);
@@ -575,7 +616,7 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
     }
   }
   const long long tr1 = trace ? gtimer() : 0;
-  if (t == 0) flag_spin(&ready[jcol * ct + jcol], err, epoch);
+  if (t == 0) flag_spin<true>(&ready[jcol * ct + jcol], err, epoch);
   __syncthreads();
   tile_load(Ls, T + (size_t)jcol * TC * ld + (size_t)jcol * TC, ld, t, CP_THREADS, false);
   __syncthreads();
@@ -587,7 +628,6 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
   tile_store(gC, ld, Ds, t, CP_THREADS);
   __syncthreads();
   if (t == 0) {
-    __threadfence();
     st_release(&ready[i * ct + jcol], epoch);
     if (trace && i < ct + 2 && i >= jcol + 2) {
       long long* o = trace + 10 * (size_t)(ct + jcol * 2 + (i - jcol - 2) % 2);
@@ -596,12 +636,39 @@ __device__ __forceinline__ void worker_trsm(double* __restrict__ T, int ld, int 
   }
 }
 // flags: ready[i*ct + j] (L tile published), pre[rt*ct + j] (partial sums of D_j/E_j over the earlier panels published)
+//
+// Critical-path CTA, per tile column j (warp 0 = the chain, warps 1-3 = what can be taken off it):
+//   (a)  all   : wait for pre(j) (partial sums over k <= j-2, done by a worker a whole column ago); D_j, E_j = (j+1, j)
+//                into shared memory through registers (all loads of a thread in flight at once);
+//                D -= Wt Wt^T on the tensor cores (Wt = L(j, j-1), the k-major copy the previous solve left behind)
+//   (b)  warp 0: potrf(D)             | warps 1-3: wait for L(j+1, j-1) from a worker, E -= L(j+1, j-1) Wt^T (tensor cores)
+//   (c)  warp 0: E <- E L_jj^-T, also stored k-major into Wt
+//                                     | warps 1-3: publish L_jj
+//   (d)  all   : publish E
+// Measured alternatives (tools/chol_trace.py): prefetching D_{j+1}/E_{j+1} during (b) with the pre tasks moved one column
+// earlier makes the chain wait for tiles the workers have only just been able to start (a TRSM tile reaches the consumer
+// ~5-7 us after its diagonal tile is published: flag, tile load, solve, store, flag, tile load are six dependent L2 round
+// trips): 8.9 and 14 us per column against 10 us before and the figure in DESIGN.md for this schedule.
+typedef double (*Tile)[TC + 1];
+#define TC_TILE_DOUBLES (TC * (TC + 1))
+#define TC_SMEM_BYTES ((5 * TC_TILE_DOUBLES + 2 * TC) * sizeof(double))
+__device__ __forceinline__ void tile_fetch96(double (&r)[11], const double* g, int ld, int t) {  // t = 0..95
+#pragma unroll
+  for (int u = 0; u < 11; ++u) { const int e = t + 96 * u; r[u] = e < TC * TC ? __ldcg(&g[(size_t)(e >> 5) * ld + (e & 31)]) : 0.0; }
+}
+__device__ __forceinline__ void tile_stash(double (*S)[TC + 1], const double (&r)[8], int t) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { const int e = t + CP_THREADS * u; S[e >> 5][e & 31] = r[u]; }
+}
 __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__ T, int ld, int rt, int ct, CholRange cr,
                                                          int* __restrict__ flags, int* __restrict__ err, double piv_tol,
                                                          const double* __restrict__ diag0, long long* __restrict__ trace,
                                                          int epoch) {
-  __shared__ double Ds[TC][TC + 1], Es[2][TC][TC + 1], Ws[TC][TC + 1], Ls[TC][TC + 1];
-  __shared__ double dorig[TC], rd[TC];
+  extern __shared__ double tc_smem[];
+  Tile Ds = (Tile)tc_smem, Ws = (Tile)(tc_smem + 2 * TC_TILE_DOUBLES), Ls = (Tile)(tc_smem + 3 * TC_TILE_DOUBLES);
+  Tile Es[2] = {(Tile)(tc_smem + 1 * TC_TILE_DOUBLES), (Tile)(tc_smem + 4 * TC_TILE_DOUBLES)};
+  double* dorig = tc_smem + 5 * TC_TILE_DOUBLES;
+  double* rd = dorig + TC;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   int* ready = flags;
   int* pre = flags + (size_t)rt * ct;
@@ -609,92 +676,70 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
 
   if (blockIdx.x == 0) {
     // ------------------------------------------------------------------ critical-path CTA
-    int eb = 0;  // Es[eb^1] holds L(j, j-1)^T-major copy from the previous column
+    int eb = 0;
     for (int j = jstart; j < jend; ++j) {
       const long long tr0 = trace ? gtimer() : 0;
       const bool first = j == jstart;
       const bool has_e = !(j + 1 >= cr.skip0 && j + 1 < cr.skip1);  // E = (j+1, j) exists in this launch
+      double* gD = T + (size_t)j * TC * ld + (size_t)j * TC;
+      double* gE = T + (size_t)(j + 1) * TC * ld + (size_t)j * TC;
+      // ---- (a)
       if (j >= 2) {
         if (t == 0) flag_spin(&pre[j], err, epoch);
         __syncthreads();
       }
-      double* gD = T + (size_t)j * TC * ld + (size_t)j * TC;
-      double* gE = T + (size_t)(j + 1) * TC * ld + (size_t)j * TC;
-      tile_load(Ds, gD, ld, t, CP_THREADS, false);
-      if (has_e) tile_load(Es[eb], gE, ld, t, CP_THREADS, false);
+      {
+        double ra[8], rb[8];
+        tile_fetch(ra, gD, ld, t);
+        if (has_e) tile_fetch(rb, gE, ld, t);
+        if (t < TC) dorig[t] = diag0 ? diag0[j * TC + t] : 0.0;
+        tile_stash(Ds, ra, t);
+        if (has_e) tile_stash(Es[eb], rb, t);
+      }
       __syncthreads();
       if (trace && t == 0) trace[10 * (size_t)j + 9] = gtimer();
-      if (t < TC) dorig[t] = diag0 ? diag0[j * TC + t] : 0.0;
-      __syncthreads();
-      // previous column's E (= L(j, j-1)) is in Es[eb^1] row-major; k-major copy into Ws for the rank-32 updates
       if (!first) {
-        for (int e = t; e < TC * TC; e += CP_THREADS) { const int r = e >> 5, c = e & 31; Ws[c][r] = Es[eb ^ 1][r][c]; }
-        __syncthreads();
-        tile_gemm_sub(Ds, Ws, Ws, t, CP_THREADS);  // D -= L(j,j-1) L(j,j-1)^T
+        tile_gemm_sub(Ds, Ws, Ws, t, CP_THREADS);  // D -= L(j, j-1) L(j, j-1)^T
         __syncthreads();
       }
-      const long long tr1 = trace ? gtimer() : 0;
+      if (trace && t == 0) trace[10 * (size_t)j + 3] = gtimer();
+      // ---- (b)
       if (warp == 0) {
-        warp_potrf32(Ds, Ls, dorig, piv_tol, lane);
-        const double d = Ds[lane][lane];
-        rd[lane] = d != 0.0 ? 1.0 / d : 0.0;
+        warp_potrf32_b4(Ds, dorig, piv_tol, rd, lane);
         if (trace && lane == 0) trace[10 * (size_t)j + 6] = gtimer();
       } else if (!first && has_e) {
-        // meanwhile: E -= L(j+1, j-1) L(j, j-1)^T   (L(j+1,j-1) comes from a worker)
-        if (t == 32) flag_spin(&ready[(j + 1) * ct + (j - 1)], err, epoch);
-        asm volatile("bar.sync 1, 96;" ::: "memory");
-        // k-major copy of L(j+1,j-1) into Ls is not possible (warp 0 uses Ls): accumulate straight from global
-        const double* gW = T + (size_t)(j + 1) * TC * ld + (size_t)(j - 1) * TC;
-        for (int e = t - 32; e < 64; e += 96) {
-          const int ty = e >> 3, tx = e & 7;
-          double acc[4][4];
+        const int tb = t - 32;
+        if (tb == 0) flag_spin(&ready[(j + 1) * ct + (j - 1)], err, epoch);
+        bar_group(1, 96);
+        double rg[11];
+        tile_fetch96(rg, T + (size_t)(j + 1) * TC * ld + (size_t)(j - 1) * TC, ld, tb);
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[u][v] = Es[eb][ty * 4 + u][tx * 4 + v];
-          for (int kk = 0; kk < TC; kk += 4) {
-            double a[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int q = 0; q < 4; ++q) a[u][q] = __ldcg(&gW[(size_t)(ty * 4 + u) * ld + kk + q]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = fma(-a[u][q], Ws[kk + q][tx * 4 + v], acc[u][v]);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) Es[eb][ty * 4 + u][tx * 4 + v] = acc[u][v];
-        }
-        if (trace && t == 32) trace[10 * (size_t)j + 7] = gtimer();
+        for (int u = 0; u < 11; ++u) { const int e = tb + 96 * u; if (e < TC * TC) Ls[e & 31][e >> 5] = rg[u]; }
+        bar_group(1, 96);
+        tile_gemm_sub(Es[eb], Ls, Ws, tb, 96);   // E -= L(j+1, j-1) L(j, j-1)^T
+        if (trace && tb == 0) trace[10 * (size_t)j + 7] = gtimer();
       }
       __syncthreads();
-      const long long tr2 = trace ? gtimer() : 0;
-      // publish L(j,j) (warps 1-3) while warp 0 solves E against it
+      // ---- (c)
       if (warp == 0) {
-        if (has_e) warp_trsm32(Es[eb], Ds, rd, lane);
+        if (has_e) warp_trsm32_t(Es[eb], Ds, rd, Ws, lane);
         if (trace && lane == 0) trace[10 * (size_t)j + 8] = gtimer();
       } else {
-        tile_store(gD, ld, Ds, t - 32, 96);
-        asm volatile("bar.sync 1, 96;" ::: "memory");
-        if (t == 32) { __threadfence(); st_release(&ready[j * ct + j], epoch); }
+        const int tb = t - 32;
+        tile_store(gD, ld, Ds, tb, 96);
+        bar_group(1, 96);
+        if (tb == 0) { st_release(&ready[j * ct + j], epoch); if (trace) trace[10 * (size_t)j + 4] = gtimer(); }
       }
       __syncthreads();
-      if (has_e) tile_store(gE, ld, Es[eb], t, CP_THREADS);
-      __syncthreads();
-      if (t == 0) {
-        if (has_e) {
-          __threadfence();
-          st_release(&ready[(j + 1) * ct + j], epoch);
-        }
-        if (trace) {
-          long long* o = trace + 10 * (size_t)j;
-          o[0] = j; o[1] = j; o[2] = tr0; o[3] = tr1; o[4] = tr2; o[5] = gtimer();
-        }
+      // ---- (d)
+      if (has_e) {
+        tile_store(gE, ld, Es[eb], t, CP_THREADS);
+        __syncthreads();
+        if (t == 0) st_release(&ready[(j + 1) * ct + j], epoch);
+      }
+      if (trace && t == 0) {
+        long long* o = trace + 10 * (size_t)j;
+        o[0] = j; o[1] = j; o[2] = tr0; o[5] = gtimer();
       }
       eb ^= 1;
     }
@@ -743,7 +788,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       if (kmax >= 0) {  // same software pipeline as worker_trsm: panel k+1 in flight while panel k is multiplied
         double ra[8], rb[8];
         auto fetch_blocking = [&](int k) {
-          if (t == 0) { flag_spin(&ready[jp * ct + k], err, epoch); if (has_e) flag_spin(&ready[(jp + 1) * ct + k], err, epoch); }
+          if (t == 0) { flag_spin<true>(&ready[jp * ct + k], err, epoch); if (has_e) flag_spin<true>(&ready[(jp + 1) * ct + k], err, epoch); }
           __syncthreads();
           tile_fetch(ra, T + (size_t)jp * TC * ld + (size_t)k * TC, ld, t);
           if (has_e) tile_fetch(rb, T + (size_t)(jp + 1) * TC * ld + (size_t)k * TC, ld, t);
@@ -769,7 +814,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
       tile_store(gD, ld, Ds, t, CP_THREADS);
       if (has_e) tile_store(gE, ld, Es[0], t, CP_THREADS);
       __syncthreads();
-      if (t == 0) { __threadfence(); st_release(&pre[jp], epoch); }
+      if (t == 0) { st_release(&pre[jp], epoch); }
     } else {
       worker_trsm(T, ld, ct, trsm_i, trsm_j, ready, err, Ds, Ws, Ls, rd, trace, epoch);
     }
@@ -784,7 +829,8 @@ static int tallchol_max_ctas() {
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tallchol, CP_THREADS, 0);
+    cudaFuncSetAttribute(k_tallchol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tallchol, CP_THREADS, TC_SMEM_BYTES);
     max_ctas = sms * (per_sm > 0 ? per_sm : 1);  // all CTAs of a launch must be co-resident (persistent dataflow)
   }
   return max_ctas;
@@ -814,13 +860,13 @@ void tallchol_range(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pa
   int epi = (int)ep;
   if (coop) {
     void* args[] = {&T, &ld, (void*)&rt, (void*)&ct, &cr, &flags, &err, &piv_tol, &diag0, &trace, &epi};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tallchol, dim3(1 + nworkers), dim3(CP_THREADS), args, 0, s);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_tallchol, dim3(1 + nworkers), dim3(CP_THREADS), args, TC_SMEM_BYTES, s);
     if (e != cudaSuccess) {   // too large to be co-resident: must not happen (grid sized from the occupancy query)
       fprintf(stderr, "xb200: cooperative launch of k_tallchol failed: %s\n", cudaGetErrorString(e));
       cudaMemsetAsync(err, 0xff, sizeof(int), s);
     }
   } else {
-    k_tallchol<<<1 + nworkers, CP_THREADS, 0, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace, epi);
+    k_tallchol<<<1 + nworkers, CP_THREADS, TC_SMEM_BYTES, s>>>(T, ld, rt, ct, cr, flags, err, piv_tol, diag0, trace, epi);
   }
   count_launch();
 }

@@ -529,4 +529,27 @@ void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta
   count_launch();
 }
 
+// Omega = 15 core states + the 6 states of the newest clone: index table, inverse table and the flags of the 32-row
+// tiles that contain an Omega row -- written on the stream (no host staging, no synchronisation).
+__global__ void k_set_omega(int* __restrict__ omega, int* __restrict__ omega_inv, int* __restrict__ tileflag, int slot, int M,
+                            int n_pad, int nflag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  auto om = [&](int k) { return k < 15 ? k : (k < 18 ? XB_CORE + 3 * slot + (k - 15) : XB_CORE + 3 * M + 3 * slot + (k - 18)); };
+  if (i < 32) omega[i] = i < 21 ? om(i) : 0;
+  if (i < n_pad) {
+    int inv = -1;
+    for (int k = 0; k < 21; ++k) if (om(k) == i) inv = k;
+    omega_inv[i] = inv;
+  }
+  if (i < nflag) {
+    int fl = 0;
+    for (int k = 0; k < 21; ++k) if (om(k) / 32 == i) fl = 1;
+    tileflag[i] = fl;
+  }
+}
+void launch_set_omega(cudaStream_t s, int* omega, int* omega_inv, int* tileflag, int slot, int M, int n_pad, int nflag) {
+  k_set_omega<<<(n_pad + 255) / 256, 256, 0, s>>>(omega, omega_inv, tileflag, slot, M, n_pad, nflag);
+  count_launch();
+}
+
 }  // namespace xb

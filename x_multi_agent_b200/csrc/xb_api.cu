@@ -1318,15 +1318,8 @@ static UpdateDims update_dims(const xb_filter* f, int nslam) {
 static int set_omega(xb_filter* f) {
   const int slot = std::max(0, f->n_poses - 1);
   if (slot == f->omega_slot) return 0;
-  const int N = f->N, M = f->M, n_pad = pad32(N);
-  std::vector<int> om(32, 0), inv(n_pad, -1), flag(n_pad / 32 + 4, 0);
-  for (int k = 0; k < 15; ++k) om[k] = k;
-  for (int c = 0; c < 3; ++c) { om[15 + c] = XB_CORE + 3 * slot + c; om[18 + c] = XB_CORE + 3 * M + 3 * slot + c; }
-  for (int k = 0; k < 21; ++k) { inv[om[k]] = k; flag[om[k] / 32] = 1; }
-  CK(cudaMemcpyAsync(f->d_omega, om.data(), sizeof(int) * 32, cudaMemcpyHostToDevice, f->stream));
-  CK(cudaMemcpyAsync(f->d_omega_inv, inv.data(), sizeof(int) * n_pad, cudaMemcpyHostToDevice, f->stream));
-  CK(cudaMemcpyAsync(f->d_tileflag, flag.data(), sizeof(int) * flag.size(), cudaMemcpyHostToDevice, f->stream));
-  CK(cudaStreamSynchronize(f->stream));
+  const int n_pad = pad32(f->N);
+  launch_set_omega(f->stream, f->d_omega, f->d_omega_inv, f->d_tileflag, slot, f->M, n_pad, n_pad / 32 + 4);
   f->omega_slot = slot;
   return 0;
 }

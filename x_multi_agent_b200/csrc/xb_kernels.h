@@ -152,6 +152,7 @@ void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, co
 void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
                     const int* omega, const int* omega_inv, double* om, double* Zb, double* Yb, double* Qb, double* Cb,
                     double* xv, double* corr_total, double* delta_out, int* err = nullptr);
+void launch_set_omega(cudaStream_t s, int* omega, int* omega_inv, int* tileflag, int slot, int M, int n_pad, int nflag);
 void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta, double* xv, double* corr_total);
 void launch_ci_cov(cudaStream_t s, double* P, int N, const double* K, const double* HP, int m);
 // 3xTF32 tcgen05 tensor-core covariance downdate (k_downdate_tc.cu)
