@@ -1,5 +1,5 @@
 // Per-track MSCKF / MSCKF-SLAM measurement construction: triangulation, reprojection Jacobians,
-// left-nullspace projection and chi-square gating -- one CTA (four warps) per track.
+// left-nullspace projection and chi-square gating -- one warp per track.
 //
 // reference: src/x/vision/triangulation.cpp:48-206 (DLT + Gauss-Newton),
 //            src/x/vio/msckf_update.cpp:283-492 (Jacobians, OC projection, nullspace, gate),
@@ -22,7 +22,7 @@ namespace xb {
 
 __device__ __forceinline__ int tri_idx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
 
-// Per-track shared-memory carve-up (doubles), Lm = max track length handled by the launch.
+// Per-warp shared-memory carve-up (doubles), Lm = max track length handled by the launch.
 // Y overlays Hf (Hf is dead once U and H2 exist); the anchor blocks exist only in MSCKF-SLAM mode.
 struct WarpSmem {
   double *Jp, *Ja, *Jap, *Jaa, *Hf, *U, *Y, *V, *res, *X, *scr;
@@ -57,126 +57,94 @@ __device__ __forceinline__ void tri_advance(int& r, int& c, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cholesky of the packed lower triangle X by the whole CTA, blocked by 4 columns, LEFT-looking: R2 factor rows followed by
-// 7 right-hand-side rows R2..R2+6 that are solved along (they become y = L^-1 (Pi r) and Vt = L^-1 V); row q starts at
-// tri_idx(q, 0).  Thread t owns the rows t, t + NT, ...  Per block step: every thread forms the four dot products of its
-// rows against the finished rows c0..c0+3 (the bulk of the flops, spread over all rows at once), the owners of the rows
-// c0..c0+3 put the updated 4x4 diagonal block into shared memory, every thread factors it redundantly in registers (the
-// only serial part: 4 dependent rsqrt) and solves the four entries of its rows.  Two CTA barriers per FOUR pivots.
-// Measured history of this stage per cfg-2 track (R2 = 60), one warp per track: right-looking row-per-lane 182k cycles,
-// column-per-lane 193k, fully unrolled register tiles 128k (instruction-fetch bound), left-looking column by column
-// 84-99k; this version: see DESIGN.md.
+// Cholesky of the packed lower triangle X: R2 factor rows followed by 7 right-hand-side rows R2..R2+6 that are
+// solved along (they become y = L^-1 (Pi r) and Vt = L^-1 V); row q starts at tri_idx(q, 0).  One warp,
+// LEFT-looking: for column c lane l owns the rows c+l, c+l+32, ... and accumulates X[r][c] - sum_k X[r][k] X[c][k] in
+// registers -- the inner loop only loads (the finished row c as a broadcast), so the shared-memory latency pipelines;
+// one store per row and one __syncwarp per column.  Measured per cfg-2 track (R2 = 60): right-looking row-per-lane
+// 182k cycles, right-looking column-per-lane 193k (every iteration waits for its own store), fully unrolled
+// register tiles 128k (instruction-fetch bound: the kernel runs once per warp), this loop: see profiles/.
 // ------------------------------------------------------------------------------------------------
-#define TRK_NT 128
-template <int NR>  // rows per thread: ceil((R2 + 7) / TRK_NT) <= NR
-__device__ __forceinline__ bool gate_chol_blocked(double* __restrict__ X, int R2, double* __restrict__ blk, int t) {
+// one column step for the row groups u < NG (rows c + lane + 32 u); returns the pivot, < 0 signals "not positive"
+template <int NG>
+__device__ __forceinline__ bool gate_chol_column(double* __restrict__ X, int c, int Rend, int lane) {
+  const double* Lc = X + tri_idx(c, 0);
+  double* pr[NG];
+  bool act[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) {
+    const int r = c + lane + 32 * u;
+    act[u] = r <= Rend;
+    pr[u] = X + tri_idx(act[u] ? r : c, 0);  // idle slots read row c (harmless) and store nothing
+  }
+  double s0[NG], s1[NG], s2[NG], s3[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) { s0[u] = 0.0; s1[u] = 0.0; s2[u] = 0.0; s3[u] = 0.0; }
+  int k = 0;
+#pragma unroll 2
+  for (; k + 3 < c; k += 4) {  // loads only: 4 broadcasts of the finished row c + 4 entries of every owned row per step
+    const double l0 = Lc[k], l1 = Lc[k + 1], l2 = Lc[k + 2], l3 = Lc[k + 3];
+#pragma unroll
+    for (int u = 0; u < NG; ++u) {
+      s0[u] = fma(pr[u][k], l0, s0[u]); s1[u] = fma(pr[u][k + 1], l1, s1[u]);
+      s2[u] = fma(pr[u][k + 2], l2, s2[u]); s3[u] = fma(pr[u][k + 3], l3, s3[u]);
+    }
+  }
+  for (; k < c; ++k) {
+    const double l0 = Lc[k];
+#pragma unroll
+    for (int u = 0; u < NG; ++u) s0[u] = fma(pr[u][k], l0, s0[u]);
+  }
+  double v[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) v[u] = pr[u][c] - ((s0[u] + s1[u]) + (s2[u] + s3[u]));
+  const double piv = __shfl_sync(0xffffffffu, v[0], 0);
+  if (!(piv > 0.0)) return false;
+  const double rs = rsqrt(piv);
+  __syncwarp();  // every lane has read row c's old entries before lane 0 overwrites X[c][c]
+#pragma unroll
+  for (int u = 0; u < NG; ++u)
+    if (act[u]) pr[u][c] = (u == 0 && lane == 0) ? piv * rs : v[u] * rs;
+  __syncwarp();
+  return true;
+}
+template <int ROWS>  // rows per lane: ceil((R2 + 7) / 32) <= ROWS
+__device__ __forceinline__ bool gate_chol_packed(double* __restrict__ X, int R2, int lane) {
   const int Rend = R2 + 6;
-  for (int c0 = 0; c0 < R2; c0 += 4) {
-    const int nb = min(4, R2 - c0);  // R2 = 2 L is even: the last block may have 2 columns
-    double v[NR][4];
-    const double* L0 = X + tri_idx(c0, 0);
-    const double* L1 = X + tri_idx(c0 + 1, 0);
-    const double* L2 = nb > 2 ? X + tri_idx(c0 + 2, 0) : L0;
-    const double* L3 = nb > 2 ? X + tri_idx(c0 + 3, 0) : L0;
-#pragma unroll
-    for (int u = 0; u < NR; ++u) {
-      const int r = t + TRK_NT * u;
-      const bool act = r >= c0 && r <= Rend;
-      const double* row = X + tri_idx(act ? r : c0, 0);
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-      int k = 0;
-      for (; k + 1 < c0; k += 2) {
-        const double a0 = row[k], a1 = row[k + 1];
-        s0 = fma(a0, L0[k], s0); s1 = fma(a0, L1[k], s1); s2 = fma(a0, L2[k], s2); s3 = fma(a0, L3[k], s3);
-        q0 = fma(a1, L0[k + 1], q0); q1 = fma(a1, L1[k + 1], q1); q2 = fma(a1, L2[k + 1], q2); q3 = fma(a1, L3[k + 1], q3);
-      }
-      // entries (r, c0 + j) exist only for c0 + j <= r (packed lower triangle)
-      v[u][0] = act ? row[c0] - (s0 + q0) : 0.0;
-      v[u][1] = (act && r >= c0 + 1) ? row[c0 + 1] - (s1 + q1) : 0.0;
-      v[u][2] = (act && nb > 2 && r >= c0 + 2) ? row[c0 + 2] - (s2 + q2) : 0.0;
-      v[u][3] = (act && nb > 2 && r >= c0 + 3) ? row[c0 + 3] - (s3 + q3) : 0.0;
-      if (act && r < c0 + nb) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) blk[(r - c0) * 4 + j] = v[u][j];
-      }
-    }
-    __syncthreads();
-    const double a00 = blk[0], a10 = blk[4], a11 = blk[5];
-    double a20 = 0.0, a21 = 0.0, a22 = 1.0, a30 = 0.0, a31 = 0.0, a32 = 0.0, a33 = 1.0;
-    if (nb > 2) { a20 = blk[8]; a21 = blk[9]; a22 = blk[10]; a30 = blk[12]; a31 = blk[13]; a32 = blk[14]; a33 = blk[15]; }
-    const double r0 = rsqrt(a00);
-    const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
-    const double p1 = fma(-l10, l10, a11);
-    const double r1 = rsqrt(p1);
-    const double l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
-    const double p2 = fma(-l21, l21, fma(-l20, l20, a22));
-    const double r2 = rsqrt(p2);
-    const double l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
-    const double p3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
-    const double r3 = rsqrt(p3);
-    if (!(a00 > 0.0) || !(p1 > 0.0) || !(p2 > 0.0) || !(p3 > 0.0)) return false;  // same values in every thread
-#pragma unroll
-    for (int u = 0; u < NR; ++u) {
-      const int r = t + TRK_NT * u;
-      if (r >= c0 && r <= Rend) {
-        double* row = X + tri_idx(r, 0);
-        // for the rows of the block itself the same formulas give l_ij (j < i) and l_ii = p_i r_i
-        const double x0 = v[u][0] * r0;
-        const double x1 = fma(-x0, l10, v[u][1]) * r1;
-        const double x2 = fma(-x1, l21, fma(-x0, l20, v[u][2])) * r2;
-        const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, v[u][3]))) * r3;
-        row[c0] = x0;
-        if (r >= c0 + 1) row[c0 + 1] = x1;
-        if (nb > 2 && r >= c0 + 2) row[c0 + 2] = x2;
-        if (nb > 2 && r >= c0 + 3) row[c0 + 3] = x3;
-      }
-    }
-    __syncthreads();
+  for (int c = 0; c < R2; ++c) {
+    const int ng = (Rend - c) / 32 + 1;  // row groups that still hold a row: shrinks as the factorisation advances
+    bool ok;
+    if (ng <= 1) ok = gate_chol_column<1>(X, c, Rend, lane);
+    else if (ng == 2 || ROWS == 2) ok = gate_chol_column<2>(X, c, Rend, lane);
+    else if (ng == 3 || ROWS == 3) ok = gate_chol_column<3>(X, c, Rend, lane);
+    else ok = gate_chol_column<ROWS>(X, c, Rend, lane);
+    if (!ok) return false;
   }
   return true;
 }
 
-// sum of NV per-thread values over the CTA (all threads get the result); red: >= 4 * NV doubles of scratch
-template <int NV>
-__device__ __forceinline__ void cta_sum(double (&v)[NV], double* red, int t) {
-  const int lane = t & 31, warp = t >> 5;
-#pragma unroll
-  for (int e = 0; e < NV; ++e) v[e] = xb_warp_sum(v[e]);
-  __syncthreads();  // red may still be read from a previous use
-  if (lane == 0)
-#pragma unroll
-    for (int e = 0; e < NV; ++e) red[warp * NV + e] = v[e];
-  __syncthreads();
-#pragma unroll
-  for (int e = 0; e < NV; ++e) v[e] = (red[e] + red[NV + e]) + (red[2 * NV + e] + red[3 * NV + e]);
-}
-
-// One CTA (four warps) per track.  The serial parts (DLT on one lane, Gauss-Newton and the small per-observation algebra on
-// warp 0, the 4-pivot chains of the gate factorisation) are what is left of the per-track latency; everything with
-// row / block-pair parallelism (X = J P J^T over L (L+1) / 2 block pairs, Y = X U, the projection of X, the factor's dot
-// products, the Woodbury dot products, the dense output rows) is spread over the 128 threads.  Round 1 ran one warp per
-// track (800 warps on 592 schedulers: every dependent instruction exposed): 240k cycles per cfg-2 track.
-template <int OPL>  // observations per lane of warp 0 (track length <= 32*OPL)
-__global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
+template <int OPL>  // observations per lane (track length <= 32*OPL)
+__global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
   extern __shared__ double smem[];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int M = tp.M, np = tp.n_poses;
   double* Rk = smem;            // [M][9]  rot(q_k) (body -> global), normalised
   double* pk = Rk + 9 * M;      // [M][3]
-  double* red = pk + 3 * M;     // 128 doubles of CTA scratch (reductions, the 4x4 diagonal block, broadcasts)
-  WarpSmem ws(red + 128, tp.Lmax, tp.mode);
+  double* wbase = pk + 3 * M + warp * WarpSmem::doubles(tp.Lmax, tp.mode);
+  WarpSmem ws(wbase, tp.Lmax, tp.mode);
 
   const double* parr = tp.xv + XV_ARR;
   const double* qarr = tp.xv + XV_ARR + 3 * M;
-  for (int k = t; k < np; k += TRK_NT) {
+  for (int k = threadIdx.x; k < np; k += blockDim.x) {
     xb_rot(qarr + 4 * k, Rk + 9 * k);
     pk[3 * k] = parr[3 * k]; pk[3 * k + 1] = parr[3 * k + 1]; pk[3 * k + 2] = parr[3 * k + 2];
   }
   __syncthreads();
 
-  const int trk = blockIdx.x;
+  const int trk = blockIdx.x * nwarp + warp;
+  if (trk >= tp.n_tracks) return;
   long long* pf = tp.prof ? tp.prof + 12 * (size_t)trk : nullptr;
-#define TPROF(k) do { if (pf && t == 0) pf[k] = clock64(); } while (0)
+#define TPROF(k) do { if (pf && lane == 0) pf[k] = clock64(); } while (0)
   TPROF(0);
   const int o0 = tp.off[trk], L = tp.off[trk + 1] - o0;
   const int W = 6 * M + 1;  // width of a B row: pose columns + residual column
@@ -185,128 +153,121 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
   const bool slam_mode = tp.mode == 1;
   bool bad = (L < 2) || (i1 < 0) || (L > 32 * OPL);
 
-  // ---------------------------------------------------------------- triangulation (triangulation.cpp:102-206), warp 0
+  // ---------------------------------------------------------------- triangulation (triangulation.cpp:102-206)
   const double* Rl = Rk + 9 * (np - 1);  // last pose = inverse-depth anchor
   const double* pl = pk + 3 * (np - 1);
+  double alpha = 0.0, beta = 0.0, rho = 1.0;
+  // MULTI_UAV: a track matched with other agents' tracks is triangulated jointly with their observations
+  // (msckf_update.cpp:96-166) by k_mm_triangulate; its inverse-depth estimate arrives through mm_ivd.
   const int mm_g = tp.mm_grp ? tp.mm_grp[trk] : -1;
-  if (warp == 0) {
-    double alpha = 0.0, beta = 0.0, rho = 1.0;
-    // MULTI_UAV: a track matched with other agents' tracks is triangulated jointly with their observations
-    // (msckf_update.cpp:96-166) by k_mm_triangulate; its inverse-depth estimate arrives through mm_ivd.
-    if (!bad && mm_g >= 0) {
-      alpha = tp.mm_ivd[3 * mm_g]; beta = tp.mm_ivd[3 * mm_g + 1]; rho = tp.mm_ivd[3 * mm_g + 2];
-    } else if (!bad) {
-      if (lane == 0) {
-        // projection matrices [R^T | -R^T p] of the first and last pose (triangulation.cpp:208-216)
-        const double* z1 = tp.obs + 2 * (size_t)o0;
-        const double* z2 = tp.obs + 2 * (size_t)(o0 + L - 1);
-        const double* R1 = Rk + 9 * i1;
-        const double* p1 = pk + 3 * i1;
-        double A[16], P1[12], P2[12];
-        for (int r = 0; r < 3; ++r) {
-          for (int c = 0; c < 3; ++c) { P1[r * 4 + c] = R1[c * 3 + r]; P2[r * 4 + c] = Rl[c * 3 + r]; }
-          P1[r * 4 + 3] = -(R1[0 * 3 + r] * p1[0] + R1[1 * 3 + r] * p1[1] + R1[2 * 3 + r] * p1[2]);
-          P2[r * 4 + 3] = -(Rl[0 * 3 + r] * pl[0] + Rl[1 * 3 + r] * pl[1] + Rl[2 * 3 + r] * pl[2]);
-        }
-        for (int c = 0; c < 4; ++c) {
-          A[0 + c] = z1[0] * P1[8 + c] - P1[0 + c];
-          A[4 + c] = z1[1] * P1[8 + c] - P1[4 + c];
-          A[8 + c] = z2[0] * P2[8 + c] - P2[0 + c];
-          A[12 + c] = z2[1] * P2[8 + c] - P2[4 + c];
-        }
-        double vh[4];
-        smallest_right_singular_vector4(A, vh);
-        const double x = vh[0] / vh[3], y = vh[1] / vh[3], z = vh[2] / vh[3];
-        double c2[3];
-        for (int r = 0; r < 3; ++r) c2[r] = P2[r * 4] * x + P2[r * 4 + 1] * y + P2[r * 4 + 2] * z + P2[r * 4 + 3];
-        alpha = c2[0] / c2[2];
-        beta = c2[1] / c2[2];
-        rho = 1.0 / c2[2];
+  if (!bad && mm_g >= 0) {
+    alpha = tp.mm_ivd[3 * mm_g]; beta = tp.mm_ivd[3 * mm_g + 1]; rho = tp.mm_ivd[3 * mm_g + 2];
+  } else if (!bad) {
+    if (lane == 0) {
+      // projection matrices [R^T | -R^T p] of the first and last pose (triangulation.cpp:208-216)
+      const double* z1 = tp.obs + 2 * (size_t)o0;
+      const double* z2 = tp.obs + 2 * (size_t)(o0 + L - 1);
+      const double* R1 = Rk + 9 * i1;
+      const double* p1 = pk + 3 * i1;
+      double A[16], P1[12], P2[12];
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) { P1[r * 4 + c] = R1[c * 3 + r]; P2[r * 4 + c] = Rl[c * 3 + r]; }
+        P1[r * 4 + 3] = -(R1[0 * 3 + r] * p1[0] + R1[1 * 3 + r] * p1[1] + R1[2 * 3 + r] * p1[2]);
+        P2[r * 4 + 3] = -(Rl[0 * 3 + r] * pl[0] + Rl[1 * 3 + r] * pl[1] + Rl[2 * 3 + r] * pl[2]);
       }
-      alpha = __shfl_sync(0xffffffffu, alpha, 0);
-      beta = __shfl_sync(0xffffffffu, beta, 0);
-      rho = __shfl_sync(0xffffffffu, rho, 0);
-      TPROF(1);
+      for (int c = 0; c < 4; ++c) {
+        A[0 + c] = z1[0] * P1[8 + c] - P1[0 + c];
+        A[4 + c] = z1[1] * P1[8 + c] - P1[4 + c];
+        A[8 + c] = z2[0] * P2[8 + c] - P2[0 + c];
+        A[12 + c] = z2[1] * P2[8 + c] - P2[4 + c];
+      }
+      double vh[4];
+      smallest_right_singular_vector4(A, vh);
+      const double x = vh[0] / vh[3], y = vh[1] / vh[3], z = vh[2] / vh[3];
+      double c2[3];
+      for (int r = 0; r < 3; ++r) c2[r] = P2[r * 4] * x + P2[r * 4 + 1] * y + P2[r * 4 + 2] * z + P2[r * 4 + 3];
+      alpha = c2[0] / c2[2];
+      beta = c2[1] / c2[2];
+      rho = 1.0 / c2[2];
+    }
+    alpha = __shfl_sync(0xffffffffu, alpha, 0);
+    beta = __shfl_sync(0xffffffffu, beta, 0);
+    rho = __shfl_sync(0xffffffffu, rho, 0);
+    TPROF(1);
 
-      // iteration-invariant relative poses of this lane's observations
-      double dR[OPL][9], dp[OPL][3], zz[OPL][2];
+    // iteration-invariant relative poses of this lane's observations
+    double dR[OPL][9], dp[OPL][3], zz[OPL][2];
+#pragma unroll
+    for (int o = 0; o < OPL; ++o) {
+      const int i = lane + 32 * o;
+      if (i < L) {
+        const double* Ri = Rk + 9 * (i1 + i);
+        const double* pi = pk + 3 * (i1 + i);
+        // rot = R_i^T ; delta_rot = rot * rot_a^T = R_i^T R_l ; delta_pos = rot p_a - rot p_i
+        for (int r = 0; r < 3; ++r) {
+          for (int c = 0; c < 3; ++c)
+            dR[o][r * 3 + c] = Ri[0 * 3 + r] * Rl[0 * 3 + c] + Ri[1 * 3 + r] * Rl[1 * 3 + c] + Ri[2 * 3 + r] * Rl[2 * 3 + c];
+          const double a = Ri[0 * 3 + r] * pl[0] + Ri[1 * 3 + r] * pl[1] + Ri[2 * 3 + r] * pl[2];
+          const double b = Ri[0 * 3 + r] * pi[0] + Ri[1 * 3 + r] * pi[1] + Ri[2 * 3 + r] * pi[2];
+          dp[o][r] = a - b;
+        }
+        zz[o][0] = tp.obs[2 * (size_t)(o0 + i)];
+        zz[o][1] = tp.obs[2 * (size_t)(o0 + i) + 1];
+      }
+    }
+    double r_norm_last = 1000.0, r_norm = 100.0;
+    int iter = 0;
+    while (r_norm_last - r_norm > tp.gn_term) {
+      ++iter;
+      if (iter > tp.gn_max_iter) break;
+      double jtj[6] = {0, 0, 0, 0, 0, 0}, jtr[3] = {0, 0, 0}, rr = 0.0;
 #pragma unroll
       for (int o = 0; o < OPL; ++o) {
         const int i = lane + 32 * o;
         if (i < L) {
-          const double* Ri = Rk + 9 * (i1 + i);
-          const double* pi = pk + 3 * (i1 + i);
-          // rot = R_i^T ; delta_rot = rot * rot_a^T = R_i^T R_l ; delta_pos = rot p_a - rot p_i
-          for (int r = 0; r < 3; ++r) {
-            for (int c = 0; c < 3; ++c)
-              dR[o][r * 3 + c] = Ri[0 * 3 + r] * Rl[0 * 3 + c] + Ri[1 * 3 + r] * Rl[1 * 3 + c] + Ri[2 * 3 + r] * Rl[2 * 3 + c];
-            const double a = Ri[0 * 3 + r] * pl[0] + Ri[1 * 3 + r] * pl[1] + Ri[2 * 3 + r] * pl[2];
-            const double b = Ri[0 * 3 + r] * pi[0] + Ri[1 * 3 + r] * pi[1] + Ri[2 * 3 + r] * pi[2];
-            dp[o][r] = a - b;
-          }
-          zz[o][0] = tp.obs[2 * (size_t)(o0 + i)];
-          zz[o][1] = tp.obs[2 * (size_t)(o0 + i) + 1];
+          double h[3];
+          for (int r = 0; r < 3; ++r)
+            h[r] = dR[o][r * 3] * alpha + dR[o][r * 3 + 1] * beta + dR[o][r * 3 + 2] + rho * dp[o][r];
+          const double r0 = zz[o][0] - h[0] / h[2], r1 = zz[o][1] - h[1] / h[2];
+          const double j1a = -1.0 / h[2], j1b = h[0] / (h[2] * h[2]), j1c = h[1] / (h[2] * h[2]);
+          // J = j1 * j0, j0 = [dR(:,0) dR(:,1) dp]
+          double J0[3], J1[3];
+          const double c0[3] = {dR[o][0], dR[o][3], dR[o][6]}, c1[3] = {dR[o][1], dR[o][4], dR[o][7]};
+          J0[0] = j1a * c0[0] + j1b * c0[2]; J0[1] = j1a * c1[0] + j1b * c1[2]; J0[2] = j1a * dp[o][0] + j1b * dp[o][2];
+          J1[0] = j1a * c0[1] + j1c * c0[2]; J1[1] = j1a * c1[1] + j1c * c1[2]; J1[2] = j1a * dp[o][1] + j1c * dp[o][2];
+          jtj[0] += J0[0] * J0[0] + J1[0] * J1[0];
+          jtj[1] += J0[0] * J0[1] + J1[0] * J1[1];
+          jtj[2] += J0[0] * J0[2] + J1[0] * J1[2];
+          jtj[3] += J0[1] * J0[1] + J1[1] * J1[1];
+          jtj[4] += J0[1] * J0[2] + J1[1] * J1[2];
+          jtj[5] += J0[2] * J0[2] + J1[2] * J1[2];
+          jtr[0] += J0[0] * r0 + J1[0] * r1;
+          jtr[1] += J0[1] * r0 + J1[1] * r1;
+          jtr[2] += J0[2] * r0 + J1[2] * r1;
+          rr += r0 * r0 + r1 * r1;
         }
       }
-      double r_norm_last = 1000.0, r_norm = 100.0;
-      int iter = 0;
-      while (r_norm_last - r_norm > tp.gn_term) {
-        ++iter;
-        if (iter > tp.gn_max_iter) break;
-        double jtj[6] = {0, 0, 0, 0, 0, 0}, jtr[3] = {0, 0, 0}, rr = 0.0;
 #pragma unroll
-        for (int o = 0; o < OPL; ++o) {
-          const int i = lane + 32 * o;
-          if (i < L) {
-            double h[3];
-            for (int r = 0; r < 3; ++r)
-              h[r] = dR[o][r * 3] * alpha + dR[o][r * 3 + 1] * beta + dR[o][r * 3 + 2] + rho * dp[o][r];
-            const double r0 = zz[o][0] - h[0] / h[2], r1 = zz[o][1] - h[1] / h[2];
-            const double j1a = -1.0 / h[2], j1b = h[0] / (h[2] * h[2]), j1c = h[1] / (h[2] * h[2]);
-            // J = j1 * j0, j0 = [dR(:,0) dR(:,1) dp]
-            double J0[3], J1[3];
-            const double c0[3] = {dR[o][0], dR[o][3], dR[o][6]}, c1[3] = {dR[o][1], dR[o][4], dR[o][7]};
-            J0[0] = j1a * c0[0] + j1b * c0[2]; J0[1] = j1a * c1[0] + j1b * c1[2]; J0[2] = j1a * dp[o][0] + j1b * dp[o][2];
-            J1[0] = j1a * c0[1] + j1c * c0[2]; J1[1] = j1a * c1[1] + j1c * c1[2]; J1[2] = j1a * dp[o][1] + j1c * dp[o][2];
-            jtj[0] += J0[0] * J0[0] + J1[0] * J1[0];
-            jtj[1] += J0[0] * J0[1] + J1[0] * J1[1];
-            jtj[2] += J0[0] * J0[2] + J1[0] * J1[2];
-            jtj[3] += J0[1] * J0[1] + J1[1] * J1[1];
-            jtj[4] += J0[1] * J0[2] + J1[1] * J1[2];
-            jtj[5] += J0[2] * J0[2] + J1[2] * J1[2];
-            jtr[0] += J0[0] * r0 + J1[0] * r1;
-            jtr[1] += J0[1] * r0 + J1[1] * r1;
-            jtr[2] += J0[2] * r0 + J1[2] * r1;
-            rr += r0 * r0 + r1 * r1;
-          }
-        }
+      for (int e = 0; e < 6; ++e) jtj[e] = xb_warp_sum(jtj[e]);
 #pragma unroll
-        for (int e = 0; e < 6; ++e) jtj[e] = xb_warp_sum(jtj[e]);
-#pragma unroll
-        for (int e = 0; e < 3; ++e) jtr[e] = xb_warp_sum(jtr[e]);
-        rr = xb_warp_sum(rr);
-        const double Am[9] = {jtj[0], jtj[1], jtj[2], jtj[1], jtj[3], jtj[4], jtj[2], jtj[4], jtj[5]};
-        double Ai[9];
-        xb_inv33(Am, Ai);
-        double d[3];
-        xb_mv33(Ai, jtr, d);
-        alpha -= d[0];
-        beta -= d[1];
-        rho -= d[2];
-        r_norm_last = r_norm;
-        r_norm = sqrt(rr);
-      }
-    }
-    if (lane == 0) {
-      red[0] = alpha; red[1] = beta; red[2] = rho;
-      tp.ivd[3 * trk] = alpha; tp.ivd[3 * trk + 1] = beta; tp.ivd[3 * trk + 2] = rho;
+      for (int e = 0; e < 3; ++e) jtr[e] = xb_warp_sum(jtr[e]);
+      rr = xb_warp_sum(rr);
+      const double Am[9] = {jtj[0], jtj[1], jtj[2], jtj[1], jtj[3], jtj[4], jtj[2], jtj[4], jtj[5]};
+      double Ai[9];
+      xb_inv33(Am, Ai);
+      double d[3];
+      xb_mv33(Ai, jtr, d);
+      alpha -= d[0];
+      beta -= d[1];
+      rho -= d[2];
+      r_norm_last = r_norm;
+      r_norm = sqrt(rr);
     }
   }
-  __syncthreads();
-  const double alpha = red[0], beta = red[1], rho = red[2];
   TPROF(2);
+  if (lane == 0) { tp.ivd[3 * trk] = alpha; tp.ivd[3 * trk + 1] = beta; tp.ivd[3 * trk + 2] = rho; }
 
-  // ---------------------------------------------------------------- Jacobians (one thread per observation)
+  // ---------------------------------------------------------------- Jacobians
   // global feature position (msckf_update.cpp:283-304): 1/rho * R_l (alpha,beta,1) + p_l
   double Gf[3];
   {
@@ -316,7 +277,7 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
     for (int e = 0; e < 3; ++e) Gf[e] = 1.0 / rho * t3[e] + pl[e];
   }
   int nan_flag = 0;
-  for (int i = t; i < L && !bad; i += TRK_NT) {
+  for (int i = lane; i < L && !bad; i += 32) {
     const int pos = i1 + i;
     const double* R = Rk + 9 * pos;
     const double* pc = pk + 3 * pos;
@@ -377,52 +338,40 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
       for (int e = 0; e < 6; ++e) Hf[e] = 1.0 / rho * tmp[e];
     }
   }
-  bad = bad || __syncthreads_or(nan_flag);
+  nan_flag = __any_sync(0xffffffffu, nan_flag);
+  bad = bad || nan_flag;
+  __syncwarp();
   TPROF(3);
 
-  // ---------------------------------------------------------------- U = orth(Hf)
-  // (msckf_update.cpp:423: Hf.householderQr().householderQ(); only range(Hf) matters.)  Cholesky-QR applied twice
-  // (U = Hf R^-1 with R^T R = Hf^T Hf, then once more on the result): the six Gram sums of a pass are ONE reduction round
-  // instead of the nine dependent dot products of Gram-Schmidt with re-orthogonalisation; orthonormal to rounding for
-  // cond(Hf) < 1e7 (Hf is 2L x 3).  A non-positive pivot zeroes its column, as the zero-norm guard of Gram-Schmidt did.
+  // ---------------------------------------------------------------- U = orth(Hf): MGS with re-orthogonalisation
+  // (msckf_update.cpp:423: Hf.householderQr().householderQ(); only range(Hf) matters)
   const int R2 = 2 * L;
   if (!bad) {
-    for (int pass = 0; pass < 2; ++pass) {
-      const double* src = pass ? ws.U : ws.Hf;
-      double g[6] = {0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
-      const bool own = t < R2;  // R2 <= 128: one row per thread
-      if (own) {
-        h[0] = src[t * 3]; h[1] = src[t * 3 + 1]; h[2] = src[t * 3 + 2];
-        g[0] = h[0] * h[0]; g[1] = h[0] * h[1]; g[2] = h[0] * h[2]; g[3] = h[1] * h[1]; g[4] = h[1] * h[2]; g[5] = h[2] * h[2];
-      }
-      cta_sum<6>(g, red, t);
-      // R (upper triangular, R^T R = G): r00 r01 r02 / r11 r12 / r22 ; i0, i1, i2 = reciprocal diagonal
-      const double i0 = g[0] > 0.0 ? rsqrt(g[0]) : 0.0;
-      const double r01 = g[1] * i0, r02 = g[2] * i0;
-      const double d1 = g[3] - r01 * r01;
-      const double i1_ = d1 > 0.0 ? rsqrt(d1) : 0.0;
-      const double r12 = (g[4] - r01 * r02) * i1_;
-      const double d2 = g[5] - r02 * r02 - r12 * r12;
-      const double i2 = d2 > 0.0 ? rsqrt(d2) : 0.0;
-      if (own) {
-        const double u0 = h[0] * i0;
-        const double u1 = (h[1] - u0 * r01) * i1_;
-        const double u2 = (h[2] - u0 * r02 - u1 * r12) * i2;
-        ws.U[t * 3] = u0; ws.U[t * 3 + 1] = u1; ws.U[t * 3 + 2] = u2;
-      }
-      __syncthreads();
+    for (int i = lane; i < R2 * 3; i += 32) ws.U[i] = ws.Hf[i];
+    __syncwarp();
+    for (int c = 0; c < 3; ++c) {
+      for (int pass = 0; pass < 2; ++pass)
+        for (int p = 0; p < c; ++p) {
+          const double d = wdot(ws.U + p, 3, ws.U + c, 3, R2, lane);
+          for (int i = lane; i < R2; i += 32) ws.U[i * 3 + c] -= d * ws.U[i * 3 + p];
+          __syncwarp();
+        }
+      const double n2 = wdot(ws.U + c, 3, ws.U + c, 3, R2, lane);
+      const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+      for (int i = lane; i < R2; i += 32) ws.U[i * 3 + c] *= inv;
+      __syncwarp();
     }
   }
 
   TPROF(4);
   // ---------------------------------------------------------------- B = U^T [J | r]   (3 x (6M+1))
-  for (int e = t; e < 3 * W; e += TRK_NT) Bt[e] = 0.0;
-  __syncthreads();
+  for (int e = lane; e < 3 * W; e += 32) Bt[e] = 0.0;
+  __syncwarp();
   double ur[3] = {0, 0, 0};
   if (!bad) {
     double anc[18];
     for (int e = 0; e < 18; ++e) anc[e] = 0.0;
-    for (int i = t; i < L; i += TRK_NT) {
+    for (int i = lane; i < L; i += 32) {
       const int pos = i1 + i;
       const double* U0 = ws.U + 6 * i;  // rows 2i, 2i+1 (3 each)
       const double* Jp = ws.Jp + 6 * i;
@@ -444,15 +393,11 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
           }
       }
     }
-    cta_sum<3>(ur, red, t);
+    for (int u = 0; u < 3; ++u) ur[u] = xb_warp_sum(ur[u]);
+    __syncwarp();
     if (slam_mode) {
-      double a9[9];
-      for (int half = 0; half < 2; ++half) {
-        for (int e = 0; e < 9; ++e) a9[e] = anc[half * 9 + e];
-        cta_sum<9>(a9, red, t);
-        for (int e = 0; e < 9; ++e) anc[half * 9 + e] = a9[e];
-      }
-      if (t == 0) {
+      for (int e = 0; e < 18; ++e) anc[e] = xb_warp_sum(anc[e]);
+      if (lane == 0) {
         const int pos = np - 1;  // own block of the last observation is zero, so plain stores are exact
         for (int u = 0; u < 3; ++u)
           for (int c = 0; c < 3; ++c) {
@@ -460,27 +405,24 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
             Bt[u * W + 3 * M + 3 * pos + c] = anc[u * 6 + 3 + c];
           }
       }
-    }
-    if (slam_mode || mm_g >= 0) {
-      // H2 = U^T Hf (3x3), msckf_slam_update.cpp:225; for a matched track the same product is the jac_pf_ block of the own
-      // agent, A_up^T Hf (msckf_update.cpp:442-443)
+      // H2 = U^T Hf (3x3), msckf_slam_update.cpp:225
       double h2[9];
-      for (int e = 0; e < 9; ++e) h2[e] = 0.0;
-      if (t < R2)
-        for (int u = 0; u < 3; ++u)
-          for (int c = 0; c < 3; ++c) h2[u * 3 + c] = ws.U[t * 3 + u] * ws.Hf[t * 3 + c];
-      cta_sum<9>(h2, red, t);
-      if (t == 0) {
-        if (slam_mode)
-          for (int e = 0; e < 9; ++e) tp.H2[9 * (size_t)trk + e] = h2[e];
-        if (mm_g >= 0)
-          for (int e = 0; e < 9; ++e) tp.mm_F0[9 * (size_t)mm_g + e] = h2[e];
-      }
+      for (int u = 0; u < 3; ++u)
+        for (int c = 0; c < 3; ++c) h2[u * 3 + c] = wdot(ws.U + u, 3, ws.Hf + c, 3, R2, lane);
+      if (lane == 0)
+        for (int e = 0; e < 9; ++e) tp.H2[9 * (size_t)trk + e] = h2[e];
     }
-    if (t == 0)
+    if (lane == 0)
       for (int u = 0; u < 3; ++u) Bt[u * W + 6 * M] = ur[u];
+    if (mm_g >= 0) {  // jac_pf_ block of the own agent: A_up^T Hf (msckf_update.cpp:442-443)
+      double f0[9];
+      for (int u = 0; u < 3; ++u)
+        for (int c = 0; c < 3; ++c) f0[u * 3 + c] = wdot(ws.U + u, 3, ws.Hf + c, 3, R2, lane);
+      if (lane == 0)
+        for (int e = 0; e < 9; ++e) tp.mm_F0[9 * (size_t)mm_g + e] = f0[e];
+    }
   }
-  __syncthreads();
+  __syncwarp();
 
   TPROF(5);
   // ---------------------------------------------------------------- gate: X = J P J^T over block pairs (k <= i)
@@ -492,8 +434,8 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
     const int npairs = L * (L + 1) / 2;
     const int nslot = slam_mode ? 2 : 1;
     int i = 0, k = 0;
-    tri_advance(i, k, t);
-    for (int e = t; e < npairs; e += TRK_NT, tri_advance(i, k, TRK_NT)) {
+    tri_advance(i, k, lane);
+    for (int e = lane; e < npairs; e += 32, tri_advance(i, k, 32)) {
       double x00 = 0, x01 = 0, x10 = 0, x11 = 0;
       for (int si = 0; si < nslot; ++si) {
         const int pi_ = si ? np - 1 : i1 + i;
@@ -543,13 +485,10 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
       ws.X[tri_idx(2 * i + 1, 2 * k + 1)] = x11;
       if (k < i) ws.X[tri_idx(2 * i, 2 * k + 1)] = x01;
     }
-    __syncthreads();
+    __syncwarp();
     TPROF(6);
-    // Y = X U  (2L x 3), one row per thread
-    double zp[9];
-    for (int e = 0; e < 9; ++e) zp[e] = 0.0;
-    if (t < R2) {
-      const int r = t;
+    // Y = X U  (2L x 3)
+    for (int r = lane; r < R2; r += 32) {
       double y0 = 0, y1 = 0, y2 = 0;
       const double* xr = ws.X + tri_idx(r, 0);
 #pragma unroll 4
@@ -569,21 +508,21 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
         y2 = fma(x, ws.U[c * 3 + 2], y2);
       }
       ws.Y[r * 3] = y0; ws.Y[r * 3 + 1] = y1; ws.Y[r * 3 + 2] = y2;
-      const double yv[3] = {y0, y1, y2};
-      for (int u = 0; u < 3; ++u)
-        for (int v = 0; v < 3; ++v) zp[u * 3 + v] = ws.U[r * 3 + u] * yv[v];
     }
-    cta_sum<9>(zp, red, t);  // Z = U^T X U (the barriers inside also publish Y)
+    __syncwarp();
+    double Z[9];  // U^T X U
+    for (int u = 0; u < 3; ++u)
+      for (int v = 0; v < 3; ++v) Z[u * 3 + v] = wdot(ws.U + u, 3, ws.Y + v, 3, R2, lane);
     // S = Pi X Pi + var I = X - U W^T - W U^T + var I  with  W = Y - U Z / 2  (Z = U^T X U symmetric)
-    if (t < R2)
+    for (int r = lane; r < R2; r += 32)
       for (int v = 0; v < 3; ++v)
-        ws.V[t * 3 + v] = ws.Y[t * 3 + v] - 0.5 * (ws.U[t * 3] * zp[v] + ws.U[t * 3 + 1] * zp[3 + v] + ws.U[t * 3 + 2] * zp[6 + v]);
-    __syncthreads();
+        ws.V[r * 3 + v] = ws.Y[r * 3 + v] - 0.5 * (ws.U[r * 3] * Z[v] + ws.U[r * 3 + 1] * Z[3 + v] + ws.U[r * 3 + 2] * Z[6 + v]);
+    __syncwarp();
     // (in place, packed), augmented row R2 = (Pi r)^T
     const int nel = R2 * (R2 + 1) / 2;
     int r = 0, c = 0;
-    tri_advance(r, c, t);
-    for (int e = t; e < nel; e += TRK_NT, tri_advance(r, c, TRK_NT)) {
+    tri_advance(r, c, lane);
+    for (int e = lane; e < nel; e += 32, tri_advance(r, c, 32)) {
       double s = ws.X[e];
 #pragma unroll
       for (int u = 0; u < 3; ++u) s -= ws.U[r * 3 + u] * ws.V[c * 3 + u] + ws.V[r * 3 + u] * ws.U[c * 3 + u];
@@ -591,140 +530,124 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
       ws.X[e] = s;
     }
     double* aug = ws.X + tri_idx(R2, 0);
-    if (t < R2) aug[t] = ws.res[t] - (ws.U[t * 3] * ur[0] + ws.U[t * 3 + 1] * ur[1] + ws.U[t * 3 + 2] * ur[2]);
+    for (int r = lane; r < R2; r += 32)
+      aug[r] = ws.res[r] - (ws.U[r * 3] * ur[0] + ws.U[r * 3 + 1] * ur[1] + ws.U[r * 3 + 2] * ur[2]);
     // rows R2+1+k: V^T, V = Pi J_c with J_c = J[:, 6 columns of the newest clone]  (antisymmetric part of P lives there)
     const int ccol[6] = {3 * (np - 1), 3 * (np - 1) + 1, 3 * (np - 1) + 2, 3 * M + 3 * (np - 1), 3 * M + 3 * (np - 1) + 1,
                          3 * M + 3 * (np - 1) + 2};
-    for (int e = t; e < 6 * R2; e += TRK_NT) {
-      const int kk = e / R2, rr = e - kk * R2;
-      double* vr = ws.X + tri_idx(R2 + 1 + kk, 0);
-      const double b0 = Bt[ccol[kk]], b1 = Bt[W + ccol[kk]], b2 = Bt[2 * W + ccol[kk]];
-      const int ii = rr >> 1, hh = rr & 1;
-      double jc = 0.0;
-      if (i1 + ii == np - 1) jc += (kk < 3 ? ws.Jp : ws.Ja)[6 * ii + 3 * hh + (kk % 3)];
-      if (slam_mode) jc += (kk < 3 ? ws.Jap : ws.Jaa)[6 * ii + 3 * hh + (kk % 3)];
-      vr[rr] = jc - (ws.U[rr * 3] * b0 + ws.U[rr * 3 + 1] * b1 + ws.U[rr * 3 + 2] * b2);
+    for (int k = 0; k < 6; ++k) {
+      double* vr = ws.X + tri_idx(R2 + 1 + k, 0);
+      const double b0 = Bt[ccol[k]], b1 = Bt[W + ccol[k]], b2 = Bt[2 * W + ccol[k]];
+      for (int r = lane; r < R2; r += 32) {
+        const int i = r >> 1, h = r & 1;
+        double jc = 0.0;
+        if (i1 + i == np - 1) jc += (k < 3 ? ws.Jp : ws.Ja)[6 * i + 3 * h + (k % 3)];
+        if (slam_mode) jc += (k < 3 ? ws.Jap : ws.Jaa)[6 * i + 3 * h + (k % 3)];
+        vr[r] = jc - (ws.U[r * 3] * b0 + ws.U[r * 3 + 1] * b1 + ws.U[r * 3 + 2] * b2);
+      }
     }
-    __syncthreads();
+    __syncwarp();
     // Cholesky of the augmented lower triangle (rows R2..R2+6 are right-hand sides): the last rows become
-    // y = L^-1 (Pi r) and Vt = L^-1 V.
+    // y = L^-1 (Pi r) and Vt = L^-1 V.  Lane-owned rows, 4-wide batches so that loads overlap the FMAs.
     TPROF(7);
-    const bool spd = gate_chol_blocked<(64 * OPL + 7 + TRK_NT - 1) / TRK_NT>(ws.X, R2, red, t);
-    __syncthreads();
+    const bool spd = gate_chol_packed<(64 * OPL + 7 + 31) / 32>(ws.X, R2, lane);
+    __syncwarp();
     TPROF(8);
     if (spd) {
       // gamma = r^T S^-1 r with S = S_s + V E V^T (E = antisymmetric part of the clone block of P):
       //   y^T y - (Vt^T y)^T E (I + G E)^-1 (Vt^T y),  Vt = L^-1 V,  G = Vt^T Vt      (Woodbury)
-      // the 1 + 6 + 21 dot products y.y, Vt_b.y, Vt_a.Vt_b over the R2 rows: four threads per dot product
-      double* Gs = ws.scr;            // 36
-      double* gvs = ws.scr + 36;      // 6
-      double* Am = ws.scr + 42;       // 6 x 13
-      {
-        const int d = t >> 2, q = t & 3;
-        double part = 0.0;
-        int a = 0, b = 0;
-        if (d < 28) {
-          // d = 0: (y, y); 1..6: (y, Vt_{d-1}); 7..27: the pair (a, b <= a) of G
-          const double* ra = aug;
-          const double* rb = aug;
-          if (d >= 1 && d < 7) rb = ws.X + tri_idx(R2 + d, 0);
-          if (d >= 7) {
-            int e = d - 7;
-            while (e > a) { e -= a + 1; ++a; }
-            b = e;
-            ra = ws.X + tri_idx(R2 + 1 + a, 0);
-            rb = ws.X + tri_idx(R2 + 1 + b, 0);
-          }
-          for (int i2 = q; i2 < R2; i2 += 4) part = fma(ra[i2], rb[i2], part);
-        }
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        if (q == 0 && d < 28) {
-          if (d == 0) red[64] = part;
-          else if (d < 7) gvs[d - 1] = part;
-          else { Gs[a * 6 + b] = part; Gs[b * 6 + a] = part; }
-        }
-      }
-      __syncthreads();
-      gamma = red[64];
-      if (warp == 0) {
-        double Em[36], emax = 0.0;
+      gamma = wdot(aug, 1, aug, 1, R2, lane);
+      double Em[36], emax = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+      for (int a = 0; a < 6; ++a)
 #pragma unroll
-          for (int b = 0; b < 6; ++b) {
-            Em[a * 6 + b] = 0.5 * (P[(size_t)(XB_CORE + ccol[a]) * ld + XB_CORE + ccol[b]] -
-                                   P[(size_t)(XB_CORE + ccol[b]) * ld + XB_CORE + ccol[a]]);
-            emax = fmax(emax, fabs(Em[a * 6 + b]));
+        for (int b = 0; b < 6; ++b) {
+          Em[a * 6 + b] = 0.5 * (P[(size_t)(XB_CORE + ccol[a]) * ld + XB_CORE + ccol[b]] -
+                                 P[(size_t)(XB_CORE + ccol[b]) * ld + XB_CORE + ccol[a]]);
+          emax = fmax(emax, fabs(Em[a * 6 + b]));
+        }
+      if (emax > 0.0) {
+        // small dense algebra cooperatively in shared memory: Am = [I + G E | I] (6 x 12), lane b owns column b
+        double* Gs = ws.scr;            // 36
+        double* gvs = ws.scr + 36;      // 6
+        double* Am = ws.scr + 42;       // 6 x 13
+        // the 21 + 6 dot products G = Vt^T Vt, gv = Vt^T y: one per lane (rows 0..6 of the right-hand-side block: y, Vt_0..5)
+        if (lane < 27) {
+          int a = 0, b = lane;                     // lane < 6: (y, Vt_lane); else the pair (a, b <= a) of G
+          if (lane >= 6) { int e = lane - 6; a = 0; while (e > a) { e -= a + 1; ++a; } b = e; }
+          const double* ra = lane < 6 ? aug : ws.X + tri_idx(R2 + 1 + a, 0);
+          const double* rb = ws.X + tri_idx(R2 + 1 + b, 0);
+          double d0 = 0.0, d1 = 0.0;
+          int i = 0;
+          for (; i + 1 < R2; i += 2) { d0 = fma(ra[i], rb[i], d0); d1 = fma(ra[i + 1], rb[i + 1], d1); }
+          if (i < R2) d0 = fma(ra[i], rb[i], d0);
+          d0 += d1;
+          if (lane < 6) gvs[lane] = d0;
+          else { Gs[a * 6 + b] = d0; Gs[b * 6 + a] = d0; }
+        }
+        __syncwarp();
+        if (lane < 12) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            double v;
+            if (lane < 6) {
+              v = (a == lane) ? 1.0 : 0.0;
+#pragma unroll
+              for (int x = 0; x < 6; ++x) v = fma(Gs[a * 6 + x], Em[x * 6 + lane], v);
+            } else {
+              v = (lane - 6 == a) ? 1.0 : 0.0;
+            }
+            Am[a * 13 + lane] = v;
           }
-        if (emax > 0.0) {
-          // small dense algebra cooperatively in shared memory: Am = [I + G E | I] (6 x 12), lane b owns column b
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {  // Gauss-Jordan with partial pivoting
+          int best = c;
+          double bv = fabs(Am[c * 13 + c]);
+          for (int r = c + 1; r < 6; ++r) { const double x = fabs(Am[r * 13 + c]); if (x > bv) { bv = x; best = r; } }
+          __syncwarp();
+          if (lane < 12 && best != c) { const double tmp = Am[c * 13 + lane]; Am[c * 13 + lane] = Am[best * 13 + lane]; Am[best * 13 + lane] = tmp; }
+          __syncwarp();
+          double f6[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) f6[r] = Am[r * 13 + c];
+          __syncwarp();
           if (lane < 12) {
+            const double pr = Am[c * 13 + lane] / f6[c];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
-              double v;
-              if (lane < 6) {
-                v = (a == lane) ? 1.0 : 0.0;
-#pragma unroll
-                for (int x = 0; x < 6; ++x) v = fma(Gs[a * 6 + x], Em[x * 6 + lane], v);
-              } else {
-                v = (lane - 6 == a) ? 1.0 : 0.0;
-              }
-              Am[a * 13 + lane] = v;
+            for (int r = 0; r < 6; ++r) {
+              if (r == c) Am[r * 13 + lane] = pr;
+              else Am[r * 13 + lane] = fma(-f6[r], pr, Am[r * 13 + lane]);
             }
           }
           __syncwarp();
-#pragma unroll 1
-          for (int c2 = 0; c2 < 6; ++c2) {  // Gauss-Jordan with partial pivoting
-            int best = c2;
-            double bv = fabs(Am[c2 * 13 + c2]);
-            for (int r2 = c2 + 1; r2 < 6; ++r2) { const double x = fabs(Am[r2 * 13 + c2]); if (x > bv) { bv = x; best = r2; } }
-            __syncwarp();
-            if (lane < 12 && best != c2) { const double tmp = Am[c2 * 13 + lane]; Am[c2 * 13 + lane] = Am[best * 13 + lane]; Am[best * 13 + lane] = tmp; }
-            __syncwarp();
-            double f6[6];
-#pragma unroll
-            for (int r2 = 0; r2 < 6; ++r2) f6[r2] = Am[r2 * 13 + c2];
-            __syncwarp();
-            if (lane < 12) {
-              const double pr = Am[c2 * 13 + lane] / f6[c2];
-#pragma unroll
-              for (int r2 = 0; r2 < 6; ++r2) {
-                if (r2 == c2) Am[r2 * 13 + lane] = pr;
-                else Am[r2 * 13 + lane] = fma(-f6[r2], pr, Am[r2 * 13 + lane]);
-              }
-            }
-            __syncwarp();
-          }
-          double t6[6];
-#pragma unroll
-          for (int a = 0; a < 6; ++a) {
-            t6[a] = 0.0;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) t6[a] = fma(Am[a * 13 + 6 + b], gvs[b], t6[a]);  // (I+GE)^-1 g
-          }
-          double corr = 0.0;
-#pragma unroll
-          for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = 0; b < 6; ++b) corr = fma(gvs[a] * Em[a * 6 + b], t6[b], corr);
-          gamma -= corr;
         }
-        if (lane == 0) red[65] = gamma;
+        double t6[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          t6[a] = 0.0;
+#pragma unroll
+          for (int b = 0; b < 6; ++b) t6[a] = fma(Am[a * 13 + 6 + b], gvs[b], t6[a]);  // (I+GE)^-1 g
+        }
+        double corr = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = 0; b < 6; ++b) corr = fma(gvs[a] * Em[a * 6 + b], t6[b], corr);
+        gamma -= corr;
       }
-      __syncthreads();
-      gamma = red[65];
       const double chi = tp.chi2_95[2 * L - 3];
       inl = gamma < chi;
     }
   }
   TPROF(9);
-  if (t == 0) {
+  if (lane == 0) {
     tp.gamma[trk] = gamma;
     tp.inlier[trk] = inl;
   }
   // emit the sparse J blocks + residuals of the track (used by the Gram stage)
-  for (int i = t; i < L; i += TRK_NT) {
+  for (int i = lane; i < L; i += 32) {
     double* o = tp.Jout + 14 * (size_t)(o0 + i);
     for (int e = 0; e < 6; ++e) { o[e] = bad ? 0.0 : ws.Jp[6 * i + e]; o[6 + e] = bad ? 0.0 : ws.Ja[6 * i + e]; }
     o[12] = bad ? 0.0 : ws.res[2 * i];
@@ -732,11 +655,12 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
   }
   if (slam_mode && (bad || !inl)) {
     double* D = tp.D + (size_t)2 * o0 * W;
-    for (int e = t; e < 2 * L * W; e += TRK_NT) D[e] = 0.0;
+    for (int e = lane; e < 2 * L * W; e += 32) D[e] = 0.0;
   } else if (slam_mode) {
     // dense rows D = Pi J (2L x W) for the Gram stage: D = J - U B   (mode-1 tracks are few)
     double* D = tp.D + (size_t)2 * o0 * W;
-    for (int e = t; e < R2 * W; e += TRK_NT) {
+    __syncwarp();
+    for (int e = lane; e < R2 * W; e += 32) {
       const int r = e / W, c = e % W;
       double v = -(ws.U[r * 3] * Bt[c] + ws.U[r * 3 + 1] * Bt[W + c] + ws.U[r * 3 + 2] * Bt[2 * W + c]);
       const int i = r >> 1, h = r & 1;
@@ -755,34 +679,39 @@ __global__ void __launch_bounds__(TRK_NT, 4) k_tracks(TrackParams tp) {
   // outliers contribute nothing downstream: B is kept only for inliers in MSCKF mode.  In MSCKF-SLAM
   // mode B (= H1) and U^T r (= r1) also feed the feature initialisation of *every* new track
   // (vio_updater.cpp:430-437), so they are copied out before B is masked.
-  __syncthreads();  // D above read Bt
   if (slam_mode) {
     double* h1 = tp.H1 + (size_t)trk * 3 * W;
-    for (int e = t; e < 3 * W; e += TRK_NT) h1[e] = Bt[e];
+    for (int e = lane; e < 3 * W; e += 32) h1[e] = Bt[e];
   }
-  __syncthreads();
+  __syncwarp();
   if (!inl)
-    for (int e = t; e < 3 * W; e += TRK_NT) Bt[e] = 0.0;
+    for (int e = lane; e < 3 * W; e += 32) Bt[e] = 0.0;
   TPROF(10);
 #undef TPROF
 }
 
-size_t tracks_smem_bytes(int M, int Lmax, int mode) {
-  return sizeof(double) * ((size_t)12 * M + 128 + WarpSmem::doubles(Lmax, mode));
+size_t tracks_smem_bytes(int M, int Lmax, int warps, int mode) {
+  return sizeof(double) * ((size_t)12 * M + (size_t)warps * WarpSmem::doubles(Lmax, mode));
 }
 
 int launch_tracks(cudaStream_t s, const TrackParams& tp) {
   if (tp.n_tracks <= 0) return 0;
-  // one CTA of four warps per track; at cfg-2 a CTA needs 31 KB of shared memory, so that four of them and a dataflow
-  // Cholesky CTA of the side stream (43 KB, k_linalg.cu) fit on an SM together
-  const size_t bytes = tracks_smem_bytes(tp.M, tp.Lmax, tp.mode);
-  if (bytes > 200 * 1024) return -1;
+  // two warps (tracks) per CTA: the CTA's shared memory (<= 55 KB) leaves room on every SM for the dataflow Cholesky CTAs
+  // that xb_api.cu runs concurrently on the side stream
+  static int warps_cfg = 0;
+  if (!warps_cfg) { const char* e = getenv("XB_TRACK_WARPS"); warps_cfg = e ? std::max(1, std::min(4, atoi(e))) : 2; }
+  int warps = warps_cfg;
+  const size_t cap = 110 * 1024;  // two CTAs per SM at four warps
+  while (warps > 1 && tracks_smem_bytes(tp.M, tp.Lmax, warps, tp.mode) > cap) --warps;
+  const size_t bytes = tracks_smem_bytes(tp.M, tp.Lmax, warps, tp.mode);
+  if (bytes > cap) return -1;
+  const int grid = (tp.n_tracks + warps - 1) / warps;
   if (tp.Lmax <= 32) {
     cudaFuncSetAttribute(k_tracks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    k_tracks<1><<<tp.n_tracks, TRK_NT, bytes, s>>>(tp);
+    k_tracks<1><<<grid, warps * 32, bytes, s>>>(tp);
   } else if (tp.Lmax <= 64) {
     cudaFuncSetAttribute(k_tracks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    k_tracks<2><<<tp.n_tracks, TRK_NT, bytes, s>>>(tp);
+    k_tracks<2><<<grid, warps * 32, bytes, s>>>(tp);
   } else {
     return -1;
   }
