@@ -137,21 +137,45 @@ def main():
     out.mkdir(parents=True, exist_ok=True)
     (out / "qd_poly.cuh").write_text("\n".join(cu) + "\n")
 
-    # ---- partitioned form: the entries are split into NPART groups of similar cost, each with its own CSE, so that
-    #      NPART warps evaluate the polynomial concurrently (k_prop_step); shared sub-expressions are recomputed
+    # ---- partitioned form: the entries are split into NPART groups of similar cost so that NPART warps evaluate the
+    #      polynomial concurrently (k_prop_step, k_prop_means).  Every group evaluates the statements of the ONE global CSE
+    #      above that its entries depend on, in the same order and with the same text: bit-identical to xb_qd_poly (a CSE per
+    #      group re-associates the cancelling terms of the polynomial, which showed up as 1e-10 relative differences in the
+    #      small entries and, through one ill-conditioned update, as 1e-7 in a 65-update parity sequence); temporaries
+    #      shared between groups are recomputed.
     NPART = 7
-    cost = [sp.count_ops(Q[r, c]) + 1 for r, c in nz]
-    order = sorted(range(len(nz)), key=lambda i: -cost[i])
-    groups, load = [[] for _ in range(NPART)], [0] * NPART
+    syms = [sym for sym, _ in repl]
+    pos = {sym: i for i, sym in enumerate(syms)}
+    ops = [sp.count_ops(e) + 1 for _, e in repl]
+    deps = []
+    for i, (sym, e) in enumerate(repl):
+        d = set()
+        for fs in e.free_symbols:
+            if fs in pos:
+                d |= {pos[fs]} | deps[pos[fs]]
+        deps.append(d)
+    need = []
+    for e in red:
+        d = set()
+        for fs in e.free_symbols:
+            if fs in pos:
+                d |= {pos[fs]} | deps[pos[fs]]
+        need.append(d)
+    ecost = [sp.count_ops(e) + 1 for e in red]
+    order = sorted(range(len(nz)), key=lambda i: -(ecost[i] + sum(ops[j] for j in need[i])))
+    groups, have, load = [[] for _ in range(NPART)], [set() for _ in range(NPART)], [0] * NPART
     for i in order:
-        g = load.index(min(load))
-        groups[g].append(i)
-        load[g] += cost[i]
+        best, bl = 0, None
+        for g in range(NPART):
+            l = load[g] + ecost[i] + sum(ops[j] for j in need[i] - have[g])
+            if bl is None or l < bl:
+                best, bl = g, l
+        groups[best].append(i)
+        have[best] |= need[i]
+        load[best] = bl
 
-    def mul_pow(code):
-        return re.sub(r"pow\(([A-Za-z0-9_]+), (\d)\)", lambda m: "(" + "*".join([m.group(1)] * int(m.group(2))) + ")", code)
-
-    cp = [f"// {hdr}", "// Partitioned form: xb_qd_poly_part(part, ...) writes the entries of group `part` (0..XB_QD_NPART-1).",
+    cp = [f"// {hdr}", "// Partitioned form: xb_qd_poly_part(part, ...) writes the entries of group `part` (0..XB_QD_NPART-1); the statements",
+          "// are those of xb_qd_poly (qd_poly.cuh), each group keeps the ones its entries need.",
           "#pragma once", f"#define XB_QD_NPART {NPART}",
           "__device__ __noinline__ void xb_qd_poly_part(int part, double dt, const double* C, const double* w, const double* a,",
           "                                             double n_w, double n_bw, double n_a, double n_ba, double* Q) {",
@@ -159,16 +183,16 @@ def main():
           "  const double w0 = w[0], w1 = w[1], w2 = w[2], a0 = a[0], a1 = a[1], a2 = a[2];",
           "  switch (part) {"]
     for g, idxs in enumerate(groups):
-        rg, eg = sp.cse([Q[nz[i][0], nz[i][1]] for i in idxs], symbols=sp.numbered_symbols("s"), optimizations="basic")
         cp.append(f"    case {g}: {{")
-        for sym, e in rg:
-            cp.append(f"      const double {sym} = {mul_pow(sp.ccode(e))};")
-        for i, e in zip(idxs, eg):
+        for j in sorted(have[g]):
+            sym, e = repl[j]
+            cp.append(f"      const double {sym} = {sp.ccode(e)};")
+        for i in sorted(idxs):
             r, c = nz[i]
-            cp.append(f"      Q[{r * 15 + c}] = {mul_pow(sp.ccode(e))};")
+            cp.append(f"      Q[{r * 15 + c}] = {sp.ccode(red[i])};")
         cp.append("      break;")
         cp.append("    }")
-        print(f"part {g}: {len(idxs)} entries, {len(rg)} temporaries", file=sys.stderr)
+        print(f"part {g}: {len(idxs)} entries, {len(have[g])} temporaries, cost {load[g]}", file=sys.stderr)
     cp += ["    default: break;", "  }", "}"]
     (out / "qd_poly_parts.cuh").write_text("\n".join(cp) + "\n")
 

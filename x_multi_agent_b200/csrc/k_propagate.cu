@@ -6,6 +6,7 @@
 // (N-15)^2 block P_vv is NOT copied per IMU step (the reference does, propagator.cpp:204): slots
 // propagated from one another share a P_vv generation.  P_vi is the transpose of
 // P_iv (the reference computes both with the same products, propagator.cpp:195-203).
+#include <cstdlib>
 #include "xb_kernels.h"
 #include "qd_poly.cuh"
 #include "qd_poly_parts.cuh"
@@ -86,140 +87,236 @@ __device__ void state_transition(double dt, const double* w, const double* a, co
     }
 }
 
-// One launch propagates the estimates of `n_steps` consecutive slots starting after `start`
-// and emits F_d / Q_d of every step into FQ (n_steps x 450).
-__global__ void __launch_bounds__(128) k_prop_means(double* __restrict__ xv, int LX, int NS, int start, int n_steps,
+__device__ __noinline__ void state_transition_call(double dt, const double* w, const double* a, const double* q, double* F);
+
+// One launch propagates the estimates of `n_steps` consecutive slots starting after `start` and emits F_d / Q_d of every
+// step into FQ (n_steps x 450): the re-propagation over the buffered IMU tail (Ekf::repropagateFromStateAtIdx,
+// ekf.cpp:227-255) and processImu chains longer than one step.
+// One CTA per step.  The only true dependency between steps is the q / v / p recurrence (a few hundred cycles per step
+// once its operands sit in shared memory), so CTA k simply redoes that recurrence from the start slot up to its own
+// step -- no grid-wide dependency -- and then spends its warps on what is expensive: F_d on one warp and the Q_d
+// polynomial split over XB_QD_NPART warps.  Round 1 evaluated the polynomial of every step on ONE thread each
+// (47 us for 10 steps, the longest item next to the covariance downdate).
+__global__ void __launch_bounds__(256) k_prop_means(double* __restrict__ xv, int LX, int NS, int start, int n_steps,
                                                     ImuSample in, PropParams pp, double* __restrict__ FQ) {
-  const int t = threadIdx.x;
+  __shared__ double imu[129][8];  // slots start .. start + k: w_m[3], a_m[3], time
+  __shared__ double Dm[128][16];  // quaternion-integrator matrices of the steps 1 .. k
+  __shared__ double wsc[8][80];   // per-warp scratch of the integrator: O1, O0, A, Ak, Tm4
+  __shared__ double x0s[32], x1s[32], w1s[3], a1s[3], Cs[9], dts[1], Fs[225], Qs[225];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int k = blockIdx.x + 1;  // this CTA produces slot start + k
   const double* x0 = xv + (size_t)start * LX;
-  // the new IMU sample of a processImu call goes into the last slot of the chain (State::setImu, state.cpp:145-151)
-  if (in.valid && t == 0) {
-    double* xl = xv + (size_t)((start + n_steps) % NS) * LX;
-    xl[XV_TIME] = in.t;
-    xl[XV_SEQ] = in.seq;
-    for (int e = 0; e < 3; ++e) { xl[XV_WM + e] = in.w[e]; xl[XV_AM + e] = in.a[e]; }
-  }
-  // State::setStaticStatesFrom (state.cpp:153-161): biases, extrinsics, window and feature arrays
-  for (int k = 1; k <= n_steps; ++k) {
-    double* x1 = xv + (size_t)((start + k) % NS) * LX;
-    for (int e = XV_BW + t; e < XV_WM; e += blockDim.x) x1[e] = x0[e];
-    for (int e = XV_ARR + t; e < LX; e += blockDim.x) x1[e] = x0[e];
-  }
-  __syncthreads();
-  // the quaternion-integrator matrices depend on the IMU samples and the (static) gyro bias only: one thread per step
-  __shared__ double Dm[128][16];
-  if (t < n_steps) {
-    const double* s0 = xv + (size_t)((start + t) % NS) * LX;
-    const double* s1 = xv + (size_t)((start + t + 1) % NS) * LX;
-    double w1[3], w0[3];
-    for (int e = 0; e < 3; ++e) {  // State::computeUnbiasedImuMeasurements, state.cpp:177-182
-      w1[e] = s1[XV_WM + e] - s1[XV_BW + e];
-      w0[e] = s0[XV_WM + e] - s0[XV_BW + e];
+  double* xk = xv + (size_t)((start + k) % NS) * LX;
+  for (int e = t; e < (k + 1) * 8; e += blockDim.x) {
+    const int j = e >> 3, c = e & 7;
+    const double* xj = xv + (size_t)((start + j) % NS) * LX;
+    double v = 0.0;
+    if (c < 3) v = xj[XV_WM + c];
+    else if (c < 6) v = xj[XV_AM + c - 3];
+    else if (c == 6) v = xj[XV_TIME];
+    // the new IMU sample of a processImu call goes into the last slot of the chain (State::setImu, state.cpp:145-151)
+    if (in.valid && j == n_steps) {
+      if (c < 3) v = in.w[c];
+      else if (c < 6) v = in.a[c - 3];
+      else if (c == 6) v = in.t;
     }
-    quat_integrator(w0, w1, s1[XV_TIME] - s0[XV_TIME], Dm[t]);
+    imu[j][c] = v;
+  }
+  if (t < 32) {
+    x0s[t] = x0[t];
+    x1s[t] = (t >= XV_WM && t < XV_ARR) ? xk[t] : x0[t];  // State::setStaticStatesFrom (state.cpp:153-161)
+  }
+  for (int e = t; e < 225; e += blockDim.x) Qs[e] = 0.0;
+  __syncthreads();
+  if (t == 0 && in.valid && k == n_steps) {
+    x1s[XV_WM] = in.w[0]; x1s[XV_WM + 1] = in.w[1]; x1s[XV_WM + 2] = in.w[2];
+    x1s[XV_AM] = in.a[0]; x1s[XV_AM + 1] = in.a[1]; x1s[XV_AM + 2] = in.a[2];
+    x1s[XV_TIME] = in.t;
+    x1s[XV_SEQ] = in.seq;
+  }
+  // quaternionIntegrator (propagator.cpp:74-98) of the steps 1..k: one warp per step, element (r, c) per lane, same
+  // operation order as quat_integrator()
+  for (int j = warp + 1; j <= k; j += 8) {
+    double* O1 = wsc[warp];
+    double* O0 = O1 + 16;
+    double* A = O1 + 32;
+    double* Ak = O1 + 48;
+    double* Tm4 = O1 + 64;
+    double* D = Dm[j - 1];
+    const double dt = imu[j][6] - imu[j - 1][6];
+    const int r = (lane & 15) >> 2, c = lane & 3;
+    if (lane < 16) {
+      const int kk[16] = {-1, 2, 1, 0, 2, -1, 0, 1, 1, 0, -1, 2, 0, 1, 2, -1};
+      const double sg[16] = {0, 1, -1, 1, -1, 0, 1, 1, 1, -1, 0, 1, -1, -1, -1, 0};
+      const int q = kk[lane];
+      double o1 = 0.0, o0 = 0.0, om = 0.0;
+      if (q >= 0) {
+        const double w1 = imu[j][q] - x0s[XV_BW + q], w0 = imu[j - 1][q] - x0s[XV_BW + q];
+        o1 = sg[lane] * w1;
+        o0 = sg[lane] * w0;
+        om = sg[lane] * ((w1 + w0) / 2.0);
+      }
+      O1[lane] = o1;
+      O0[lane] = o0;
+      const double a = om * 0.5 * dt;
+      A[lane] = a;
+      Ak[lane] = a;
+      D[lane] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    int fac = 1;
+#pragma unroll 1
+    for (int it = 1; it < 5; ++it) {
+      fac *= it;
+      if (lane < 16) {
+        D[lane] = D[lane] + Ak[lane] / fac;
+        double s = 0.0;
+        for (int e = 0; e < 4; ++e) s += Ak[r * 4 + e] * A[e * 4 + c];
+        Tm4[lane] = s;
+      }
+      __syncwarp();
+      if (lane < 16) Ak[lane] = Tm4[lane];
+      __syncwarp();
+    }
+    if (lane < 16) {
+      double s10 = 0.0, s01 = 0.0;
+      for (int e = 0; e < 4; ++e) {
+        s10 += O1[r * 4 + e] * O0[e * 4 + c];
+        s01 += O0[r * 4 + e] * O1[e * 4 + c];
+      }
+      D[lane] += 1.0 / 48.0 * (s10 - s01) * dt * dt;
+    }
+    __syncwarp();
   }
   __syncthreads();
-  if (t == 0) {  // the short sequential chain: q, v, p
-    for (int k = 1; k <= n_steps; ++k) {
-      const double* s0 = xv + (size_t)((start + k - 1) % NS) * LX;
-      double* s1 = xv + (size_t)((start + k) % NS) * LX;
+  if (t == 0) {  // propagateState (propagator.cpp:30-51) for the steps 1..k, operands in shared memory
+    double q0[4], v0[3], p0[3], R0[9];
+    for (int e = 0; e < 4; ++e) q0[e] = x0s[XV_Q + e];
+    for (int e = 0; e < 3; ++e) { v0[e] = x0s[XV_V + e]; p0[e] = x0s[XV_P + e]; }
+    xb_rot_raw(q0, R0);
+    const double gv[3] = {pp.g[0], pp.g[1], pp.g[2]};
+    for (int j = 1; j <= k; ++j) {
+      const double* D = Dm[j - 1];
       double a1[3], a0[3];
       for (int e = 0; e < 3; ++e) {
-        a1[e] = s1[XV_AM + e] - s1[XV_BA + e];
-        a0[e] = s0[XV_AM + e] - s0[XV_BA + e];
+        a1[e] = imu[j][3 + e] - x0s[XV_BA + e];
+        a0[e] = imu[j - 1][3 + e] - x0s[XV_BA + e];
       }
-      const double dt = s1[XV_TIME] - s0[XV_TIME];
-      const double* D = Dm[k - 1];
+      const double dt = imu[j][6] - imu[j - 1][6];
       double q1[4];
-      for (int r = 0; r < 4; ++r)
-        q1[r] = D[r * 4] * s0[XV_Q] + D[r * 4 + 1] * s0[XV_Q + 1] + D[r * 4 + 2] * s0[XV_Q + 2] + D[r * 4 + 3] * s0[XV_Q + 3];
+      for (int r = 0; r < 4; ++r) q1[r] = D[r * 4] * q0[0] + D[r * 4 + 1] * q0[1] + D[r * 4 + 2] * q0[2] + D[r * 4 + 3] * q0[3];
       xb_qnormalize(q1);
-      double R1[9], R0[9], ra1[3], ra0[3];
+      double R1[9], ra1[3], ra0[3];
       xb_rot_raw(q1, R1);
-      xb_rot_raw(&s0[XV_Q], R0);
       xb_mv33(R1, a1, ra1);
       xb_mv33(R0, a0, ra0);
       for (int e = 0; e < 3; ++e) {
         const double dv = (ra1[e] + ra0[e]) / 2.0;
-        const double v1 = s0[XV_V + e] + (dv + pp.g[e]) * dt;
-        s1[XV_V + e] = v1;
-        s1[XV_P + e] = s0[XV_P + e] + (v1 + s0[XV_V + e]) / 2.0 * dt;
+        const double v1 = v0[e] + (dv + gv[e]) * dt;
+        p0[e] = p0[e] + (v1 + v0[e]) / 2.0 * dt;
+        v0[e] = v1;
       }
-      for (int e = 0; e < 4; ++e) s1[XV_Q + e] = q1[e];
+      for (int e = 0; e < 4; ++e) q0[e] = q1[e];
+      for (int e = 0; e < 9; ++e) R0[e] = R1[e];
+      if (j == k) {
+        for (int e = 0; e < 3; ++e) { w1s[e] = imu[j][e] - x0s[XV_BW + e]; a1s[e] = a1[e]; }
+        dts[0] = dt;
+      }
     }
+    for (int e = 0; e < 4; ++e) x1s[XV_Q + e] = q0[e];
+    for (int e = 0; e < 3; ++e) { x1s[XV_V + e] = v0[e]; x1s[XV_P + e] = p0[e]; }
+    for (int e = 0; e < 9; ++e) Cs[e] = R0[e];
   }
   __syncthreads();
-  if (t < n_steps) {
-    const double* s0 = xv + (size_t)((start + t) % NS) * LX;
-    const double* s1 = xv + (size_t)((start + t + 1) % NS) * LX;
-    double w1[3], a1[3];
-    for (int e = 0; e < 3; ++e) {
-      w1[e] = s1[XV_WM + e] - s1[XV_BW + e];
-      a1[e] = s1[XV_AM + e] - s1[XV_BA + e];
-    }
-    const double dt = s1[XV_TIME] - s0[XV_TIME];
-    double* F = FQ + (size_t)t * 450;
-    double* Q = F + 225;
-    state_transition(dt, w1, a1, &s1[XV_Q], F);
-    double C[9];
-    xb_rot_raw(&s1[XV_Q], C);
-    for (int e = 0; e < 225; ++e) Q[e] = 0.0;
-    xb_qd_poly(dt, C, w1, a1, pp.n_w, pp.n_bw, pp.n_a, pp.n_ba, Q);
+  // F_d on warp 0, the Q_d partitions on warps 1..XB_QD_NPART (one lane each: the polynomial is a scalar DAG)
+  if (lane == 0) {
+    if (warp == 0) state_transition_call(dts[0], w1s, a1s, &x1s[XV_Q], Fs);
+    else if (warp <= XB_QD_NPART) xb_qd_poly_part(warp - 1, dts[0], Cs, w1s, a1s, pp.n_w, pp.n_bw, pp.n_a, pp.n_ba, Qs);
   }
+  // estimates of slot start + k (window and feature arrays: State::setStaticStatesFrom)
+  if (t >= 32 && t < 64) xk[t - 32] = x1s[t - 32];
+  for (int e = XV_ARR + t; e < LX; e += blockDim.x) xk[e] = x0[e];
+  __syncthreads();
+  double* Fo = FQ + (size_t)(k - 1) * 450;
+  if (t < 225) { Fo[t] = Fs[t]; Fo[225 + t] = Qs[t]; }
 }
 
 // Strip propagation: for every step k,  strip_k = [F P_ii F^T + Q | F P_iv]  (propagator.cpp:195-203).
+// The steps of a chain are NOT processed one after the other: slot k's off-diagonal strip is Phi_k P_iv(start) with the
+// prefix product Phi_k = F_k ... F_1 (15x15), so blockIdx.y = k-1 picks the step, every CTA forms the prefix product it needs
+// itself (k-1 products of 15x15 matrices, a few hundred cycles each) and all slots are written side by side; the core
+// block P_ii needs the true recurrence (Q_d enters every step) and is chained inside the CTAs with blockIdx.x == 0.
+// The serial form took 2.8 us per step (28 us for the 10-step re-propagation of an update).  (F_k (F_k-1 v)) and
+// ((F_k F_k-1) v) differ in rounding only.
 // second != 0: the same recurrence on the column strips P_vi^T (P_vi' = P_vi F^T, propagator.cpp:203), whose core block
 // is the transpose of P_ii and therefore takes Q_d^T.
 __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip, int N, int NS, int start, int n_steps,
                                                      const double* __restrict__ FQ, int second) {
-  __shared__ double Fs[225], Qs[225], Pii[225], Tm[225];
+  __shared__ double Fs[225], Qs[225], Pa[225], Pb[225];
   const int t = threadIdx.x;
-  const int j = blockIdx.x * blockDim.x + t;  // column
-  const bool core_block = blockIdx.x == 0;
+  const int k = blockIdx.y + 1;
   const size_t SS = (size_t)15 * N;
   const double* s0 = strip + (size_t)start * SS;
-  double v[15];
-  if (j >= XB_CORE && j < N)
-    for (int r = 0; r < 15; ++r) v[r] = s0[(size_t)r * N + j];
-  if (core_block)
-    for (int e = t; e < 225; e += blockDim.x) Pii[e] = s0[(size_t)(e / 15) * N + (e % 15)];
-  for (int k = 0; k < n_steps; ++k) {
-    __syncthreads();
-    for (int e = t; e < 225; e += blockDim.x) {
-      Fs[e] = FQ[(size_t)k * 450 + e];
-      Qs[e] = FQ[(size_t)k * 450 + 225 + (second ? (e % 15) * 15 + e / 15 : e)];
-    }
-    __syncthreads();
-    double* s1 = strip + (size_t)((start + k + 1) % NS) * SS;
-    if (j >= XB_CORE && j < N) {
-      double u[15];
-#pragma unroll
-      for (int r = 0; r < 15; ++r) {
-        double s = 0.0;
-#pragma unroll
-        for (int e = 0; e < 15; ++e) s = fma(Fs[r * 15 + e], v[e], s);
-        u[r] = s;
-      }
-#pragma unroll
-      for (int r = 0; r < 15; ++r) { v[r] = u[r]; s1[(size_t)r * N + j] = u[r]; }
-    }
-    if (core_block) {
-      for (int e = t; e < 225; e += blockDim.x) {  // Tm = F * P_ii
-        const int r = e / 15, c = e % 15;
-        double s = 0.0;
-        for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], Pii[a * 15 + c], s);
-        Tm[e] = s;
+  double* s1 = strip + (size_t)((start + k) % NS) * SS;
+  if (blockIdx.x == 0) {
+    // core block: P_ii <- F P_ii F^T + Q over the steps 1..k
+    for (int e = t; e < 225; e += blockDim.x) Pa[e] = s0[(size_t)(e / 15) * N + (e % 15)];
+    for (int j = 0; j < k; ++j) {
+      __syncthreads();
+      for (int e = t; e < 225; e += blockDim.x) {
+        Fs[e] = FQ[(size_t)j * 450 + e];
+        Qs[e] = FQ[(size_t)j * 450 + 225 + (second ? (e % 15) * 15 + e / 15 : e)];
       }
       __syncthreads();
-      for (int e = t; e < 225; e += blockDim.x) {  // P_ii' = Tm * F^T + Q
+      for (int e = t; e < 225; e += blockDim.x) {  // Pb = F * P_ii
         const int r = e / 15, c = e % 15;
         double s = 0.0;
-        for (int a = 0; a < 15; ++a) s = fma(Tm[r * 15 + a], Fs[c * 15 + a], s);
-        s += Qs[e];
-        s1[(size_t)r * N + c] = s;
-        Pii[e] = s;  // each thread rewrites only the entries it owns; Tm already holds F*P_ii
+        for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], Pa[a * 15 + c], s);
+        Pb[e] = s;
       }
+      __syncthreads();
+      for (int e = t; e < 225; e += blockDim.x) {  // P_ii' = Pb * F^T + Q
+        const int r = e / 15, c = e % 15;
+        double s = 0.0;
+        for (int a = 0; a < 15; ++a) s = fma(Pb[r * 15 + a], Fs[c * 15 + a], s);
+        Pa[e] = s + Qs[e];
+      }
+    }
+    __syncthreads();
+    for (int e = t; e < 225; e += blockDim.x) s1[(size_t)(e / 15) * N + (e % 15)] = Pa[e];
+    return;
+  }
+  // prefix product Phi_k in Pa
+  for (int e = t; e < 225; e += blockDim.x) Pa[e] = FQ[e];
+  double* cur = Pa;
+  double* nxt = Pb;
+  for (int j = 1; j < k; ++j) {
+    __syncthreads();
+    for (int e = t; e < 225; e += blockDim.x) Fs[e] = FQ[(size_t)j * 450 + e];
+    __syncthreads();
+    for (int e = t; e < 225; e += blockDim.x) {
+      const int r = e / 15, c = e % 15;
+      double s = 0.0;
+      for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], cur[a * 15 + c], s);
+      nxt[e] = s;
+    }
+    double* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  __syncthreads();
+  const int j = XB_CORE + ((int)blockIdx.x - 1) * (int)blockDim.x + t;  // column
+  if (j < N) {
+    double v[15];
+#pragma unroll
+    for (int r = 0; r < 15; ++r) v[r] = s0[(size_t)r * N + j];
+#pragma unroll 1
+    for (int r0 = 0; r0 < 15; r0 += 5) {   // five independent accumulation chains per pass
+      double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int e = 0; e < 15; ++e)
+#pragma unroll
+        for (int u = 0; u < 5; ++u) s[u] = fma(cur[(r0 + u) * 15 + e], v[e], s[u]);
+#pragma unroll
+      for (int u = 0; u < 5; ++u) s1[(size_t)(r0 + u) * N + j] = s[u];
     }
   }
 }
@@ -410,12 +507,13 @@ void launch_prop_step(cudaStream_t s, double* xv, int LX, double* strip, int N, 
 void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,
                        const PropParams& pp, double* FQ) {
   if (n_steps <= 0) return;
-  k_prop_means<<<1, 128, 0, s>>>(xv, LX, NS, start, n_steps, in, pp, FQ);
+  k_prop_means<<<n_steps, 256, 0, s>>>(xv, LX, NS, start, n_steps, in, pp, FQ);
   count_launch();
 }
 void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ, int second) {
   if (n_steps <= 0) return;
-  k_prop_strips<<<(N + 127) / 128, 128, 0, s>>>(strip, N, NS, start, n_steps, FQ, second);
+  dim3 grid(1 + (N - XB_CORE + 127) / 128, n_steps);
+  k_prop_strips<<<grid, 128, 0, s>>>(strip, N, NS, start, n_steps, FQ, second);
   count_launch();
 }
 void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,

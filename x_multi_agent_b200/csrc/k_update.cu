@@ -308,8 +308,9 @@ __global__ void k_sym_lower(double* __restrict__ T, int ld, int r0, int r1, int 
 __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const double* __restrict__ Cb,
                                                      const double* __restrict__ P, const int* __restrict__ omega,
                                                      double* __restrict__ om, int* __restrict__ err) {
-  __shared__ double G[NOM][NOM], E[NOM][NOM], A[NOM][2 * NOM + 1], q[NOM];
-  const int t = threadIdx.x;
+  __shared__ double G[NOM][NOM], E[NOM][NOM], A[2][NOM][2 * NOM + 1], q[NOM];
+  __shared__ int perm[NOM];
+  const int t = threadIdx.x, lane = t & 31;
   for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int k = e / NOM, l = e % NOM;
     double g = 0.0;
@@ -323,7 +324,8 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
     q[t] = g;
   }
   __syncthreads();
-  // A = [I + G E | I]
+  // A = [I + G E | I]   (G E is of order one: the antisymmetric part of the covariance is as large as the covariance itself
+  // in the velocity/attitude cross blocks, so there is no series shortcut -- measured max |G E| = 0.6 at cfg-2)
   for (int e = t; e < NOM * 2 * NOM; e += blockDim.x) {
     const int r = e / (2 * NOM), c = e % (2 * NOM);
     double v;
@@ -333,16 +335,13 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
     } else {
       v = (c - NOM == r) ? 1.0 : 0.0;
     }
-    A[r][c] = v;
+    A[0][r][c] = v;
   }
-  __syncthreads();
-  // Gauss-Jordan with partial pivoting, all 256 threads: the 21 pivots are a serial chain, but everything inside one
-  // pivot step (swap, scaling, the 21 x 42 elimination) is element-parallel; four block barriers per step (~0.3 us)
-  // instead of a single warp that holds three 21-element register arrays per lane (measured 30 us for the kernel).
-  // Same operations on the same operands as the serial form: scale the pivot row, then v <- fma(-A[r][c], A[c][x], v).
-  __shared__ double fcol[NOM];
-  __shared__ int pvs;
-  // element (r, x) of the 21 x 42 elimination owned by this thread in pass u (fixed over the pivot steps)
+  // Gauss-Jordan with (implicit) partial pivoting, all 256 threads, ONE barrier per pivot: the pivot row stays where it is
+  // (perm[c] remembers it, rows already used are masked out of the search), every warp finds the pivot redundantly from
+  // shared memory, and the elimination writes into the other copy of the matrix, so no element is read after it has been
+  // overwritten.  The pivot row is normalised at the end.  Same pivots as the explicit row-swapping form (first maximum of
+  // |A[r][c]| over the unused rows); that form needed five barriers per pivot (23 us for the kernel).
   int er[4], ex[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -350,46 +349,51 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
     er[u] = e < NOM * 2 * NOM ? e / (2 * NOM) : -1;
     ex[u] = e % (2 * NOM);
   }
+  unsigned used = 0;  // same value in every thread
+  int cur = 0;
+  __syncthreads();
   for (int c = 0; c < NOM; ++c) {
-    if (t < 32) {
-      // pivot row: arg max |A[r][c]|, r >= c (first maximum wins)
-      double bv = (t >= c && t < NOM) ? fabs(A[t][c]) : -1.0;
-      int bi = t;
+    double bv = (lane < NOM && !((used >> lane) & 1u)) ? fabs(A[cur][lane][c]) : -1.0;
+    int bi = lane;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (t == 0) {
-        // a non-finite column (the factorisation met a non-positive pivot: S was not positive definite) must not
-        // select a row outside the matrix; the error word makes xb_synchronize report it
-        pvs = (bi >= c && bi < NOM && bv == bv) ? bi : c;
-        if (!(bv > 0.0) && err) atomicOr(err, 2);
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    __syncthreads();
-    const int pv = pvs;
-    if (pv != c && t < 2 * NOM) { const double tmp = A[c][t]; A[c][t] = A[pv][t]; A[pv][t] = tmp; }
-    __syncthreads();
-    const double d = A[c][c];
-    if (t < NOM) fcol[t] = A[t][c];          // multipliers of this step (row c's entry is the pivot itself)
-    __syncthreads();
-    if (t < 2 * NOM) A[c][t] /= d;
-    __syncthreads();
+    // a non-finite column (the factorisation met a non-positive pivot: S was not positive definite) must not select a
+    // row outside the matrix; the error word makes xb_synchronize report it
+    int pv = bi;
+    if (!(bv == bv) || pv < 0 || pv >= NOM || ((used >> pv) & 1u)) {
+      pv = 0;
+      while (pv < NOM - 1 && ((used >> pv) & 1u)) ++pv;
+    }
+    if (t == 0) {
+      perm[c] = pv;
+      if (!(bv > 0.0) && err) atomicOr(err, 2);
+    }
+    used |= 1u << pv;
+    const double rp = 1.0 / A[cur][pv][c];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = er[u], x = ex[u];
-      if (r < 0 || r == c) continue;
-      A[r][x] = (x == c) ? 0.0 : fma(-fcol[r], A[c][x], A[r][x]);
+      if (r < 0) continue;
+      const double a = A[cur][r][x];
+      A[cur ^ 1][r][x] = (r == pv) ? a : ((x == c) ? 0.0 : fma(-(A[cur][r][c] * rp), A[cur][pv][x], a));
     }
+    cur ^= 1;
     __syncthreads();
   }
-  // C = E * inv
+  // inv row x = (pivot row perm[x]) / pivot, then C = E * inv
+  for (int e = t; e < NOM * NOM; e += blockDim.x) {
+    const int x = e / NOM, c = e % NOM, px = perm[x];
+    A[cur ^ 1][x][c] = A[cur][px][NOM + c] / A[cur][px][x];
+  }
+  __syncthreads();
   for (int e = t; e < NOM * NOM; e += blockDim.x) {
     const int r = e / NOM, c = e % NOM;
     double v = 0.0;
-    for (int x = 0; x < NOM; ++x) v = fma(E[r][x], A[x][NOM + c], v);
+    for (int x = 0; x < NOM; ++x) v = fma(E[r][x], A[cur ^ 1][x][c], v);
     om[e] = v;
   }
   if (t < NOM) om[NOM * NOM + t] = q[t];

@@ -1968,6 +1968,7 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
   else if (n == "corr") { src = f->d_corr; cnt = f->N; }
   else if (n == "FQ") { src = f->d_FQ; cnt = 470; }
   else if (n == "delta") { src = f->d_delta; cnt = f->N; }
+  else if (n == "om") { src = f->d_om; cnt = 21 * 21 + 32; }
   else if (n == "T") { src = f->d_T; cnt = f->T_doubles; }
   else if (n == "track_prof") {
     if (!f->d_track_prof) return fail(XB_E_INVALID, "set XB_TRACK_PROF=1 before xb_create");
