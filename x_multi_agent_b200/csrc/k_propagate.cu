@@ -252,7 +252,9 @@ __global__ void __launch_bounds__(256) k_prop_means(double* __restrict__ xv, int
 // is the transpose of P_ii and therefore takes Q_d^T.
 __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip, int N, int NS, int start, int n_steps,
                                                      const double* __restrict__ FQ, int second) {
-  __shared__ double Fs[225], Qs[225], Pa[225], Pb[225];
+  // F_d (and Q_d for the core block) of several steps are brought into shared memory at once: one global-memory latency
+  // per 8 / 16 steps of the chain instead of one per step
+  __shared__ double buf[3600], Pa[225], Pb[225];
   const int t = threadIdx.x;
   const int k = blockIdx.y + 1;
   const size_t SS = (size_t)15 * N;
@@ -261,48 +263,60 @@ __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip,
   if (blockIdx.x == 0) {
     // core block: P_ii <- F P_ii F^T + Q over the steps 1..k
     for (int e = t; e < 225; e += blockDim.x) Pa[e] = s0[(size_t)(e / 15) * N + (e % 15)];
-    for (int j = 0; j < k; ++j) {
+    for (int j0 = 0; j0 < k; j0 += 8) {
+      const int nj = min(8, k - j0);
       __syncthreads();
-      for (int e = t; e < 225; e += blockDim.x) {
-        Fs[e] = FQ[(size_t)j * 450 + e];
-        Qs[e] = FQ[(size_t)j * 450 + 225 + (second ? (e % 15) * 15 + e / 15 : e)];
+      for (int e = t; e < nj * 450; e += blockDim.x) {
+        const int jj = e / 450, r = e % 450;
+        buf[e] = FQ[(size_t)(j0 + jj) * 450 + ((r >= 225 && second) ? 225 + ((r - 225) % 15) * 15 + (r - 225) / 15 : r)];
       }
-      __syncthreads();
-      for (int e = t; e < 225; e += blockDim.x) {  // Pb = F * P_ii
-        const int r = e / 15, c = e % 15;
-        double s = 0.0;
-        for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], Pa[a * 15 + c], s);
-        Pb[e] = s;
-      }
-      __syncthreads();
-      for (int e = t; e < 225; e += blockDim.x) {  // P_ii' = Pb * F^T + Q
-        const int r = e / 15, c = e % 15;
-        double s = 0.0;
-        for (int a = 0; a < 15; ++a) s = fma(Pb[r * 15 + a], Fs[c * 15 + a], s);
-        Pa[e] = s + Qs[e];
+      for (int jj = 0; jj < nj; ++jj) {
+        const double* Fs = buf + jj * 450;
+        const double* Qs = Fs + 225;
+        __syncthreads();
+        for (int e = t; e < 225; e += blockDim.x) {  // Pb = F * P_ii
+          const int r = e / 15, c = e % 15;
+          double s = 0.0;
+          for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], Pa[a * 15 + c], s);
+          Pb[e] = s;
+        }
+        __syncthreads();
+        for (int e = t; e < 225; e += blockDim.x) {  // P_ii' = Pb * F^T + Q
+          const int r = e / 15, c = e % 15;
+          double s = 0.0;
+          for (int a = 0; a < 15; ++a) s = fma(Pb[r * 15 + a], Fs[c * 15 + a], s);
+          Pa[e] = s + Qs[e];
+        }
       }
     }
     __syncthreads();
     for (int e = t; e < 225; e += blockDim.x) s1[(size_t)(e / 15) * N + (e % 15)] = Pa[e];
     return;
   }
-  // prefix product Phi_k in Pa
-  for (int e = t; e < 225; e += blockDim.x) Pa[e] = FQ[e];
+  // prefix product Phi_k = F_k ... F_1
   double* cur = Pa;
   double* nxt = Pb;
-  for (int j = 1; j < k; ++j) {
+  for (int j0 = 0; j0 < k; j0 += 16) {
+    const int nj = min(16, k - j0);
     __syncthreads();
-    for (int e = t; e < 225; e += blockDim.x) Fs[e] = FQ[(size_t)j * 450 + e];
+    for (int e = t; e < nj * 225; e += blockDim.x) buf[e] = FQ[(size_t)(j0 + e / 225) * 450 + e % 225];
     __syncthreads();
-    for (int e = t; e < 225; e += blockDim.x) {
-      const int r = e / 15, c = e % 15;
-      double s = 0.0;
-      for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], cur[a * 15 + c], s);
-      nxt[e] = s;
+    for (int jj = 0; jj < nj; ++jj) {
+      const double* Fs = buf + jj * 225;
+      if (j0 + jj == 0) {
+        for (int e = t; e < 225; e += blockDim.x) cur[e] = Fs[e];
+      } else {
+        for (int e = t; e < 225; e += blockDim.x) {
+          const int r = e / 15, c = e % 15;
+          double s = 0.0;
+          for (int a = 0; a < 15; ++a) s = fma(Fs[r * 15 + a], cur[a * 15 + c], s);
+          nxt[e] = s;
+        }
+        double* tmp = cur; cur = nxt; nxt = tmp;
+      }
+      __syncthreads();
     }
-    double* tmp = cur; cur = nxt; nxt = tmp;
   }
-  __syncthreads();
   const int j = XB_CORE + ((int)blockIdx.x - 1) * (int)blockDim.x + t;  // column
   if (j < N) {
     double v[15];

@@ -58,67 +58,83 @@ __device__ __forceinline__ void tri_advance(int& r, int& c, int n) {
 
 // ------------------------------------------------------------------------------------------------
 // Cholesky of the packed lower triangle X: R2 factor rows followed by 7 right-hand-side rows R2..R2+6 that are
-// solved along (they become y = L^-1 (Pi r) and Vt = L^-1 V); row q starts at tri_idx(q, 0).  One warp,
-// LEFT-looking: for column c lane l owns the rows c+l, c+l+32, ... and accumulates X[r][c] - sum_k X[r][k] X[c][k] in
-// registers -- the inner loop only loads (the finished row c as a broadcast), so the shared-memory latency pipelines;
-// one store per row and one __syncwarp per column.  Measured per cfg-2 track (R2 = 60): right-looking row-per-lane
-// 182k cycles, right-looking column-per-lane 193k (every iteration waits for its own store), fully unrolled
-// register tiles 128k (instruction-fetch bound: the kernel runs once per warp), this loop: see profiles/.
+// solved along (they become y = L^-1 (Pi r) and Vt = L^-1 V); row q starts at tri_idx(q, 0).  One warp, LEFT-looking.
+// Measured per cfg-2 track (R2 = 60): right-looking row-per-lane 182k cycles, right-looking column-per-lane 193k (every
+// iteration waits for its own store), fully unrolled register tiles 128k (instruction-fetch bound: the kernel runs once
+// per warp), left-looking column by column with shrinking row groups 84-99k, blocked by 4 columns (below) 66k.
 // ------------------------------------------------------------------------------------------------
-// one column step for the row groups u < NG (rows c + lane + 32 u); returns the pivot, < 0 signals "not positive"
-template <int NG>
-__device__ __forceinline__ bool gate_chol_column(double* __restrict__ X, int c, int Rend, int lane) {
-  const double* Lc = X + tri_idx(c, 0);
-  double* pr[NG];
-  bool act[NG];
-#pragma unroll
-  for (int u = 0; u < NG; ++u) {
-    const int r = c + lane + 32 * u;
-    act[u] = r <= Rend;
-    pr[u] = X + tri_idx(act[u] ? r : c, 0);  // idle slots read row c (harmless) and store nothing
-  }
-  double s0[NG], s1[NG], s2[NG], s3[NG];
-#pragma unroll
-  for (int u = 0; u < NG; ++u) { s0[u] = 0.0; s1[u] = 0.0; s2[u] = 0.0; s3[u] = 0.0; }
-  int k = 0;
-#pragma unroll 2
-  for (; k + 3 < c; k += 4) {  // loads only: 4 broadcasts of the finished row c + 4 entries of every owned row per step
-    const double l0 = Lc[k], l1 = Lc[k + 1], l2 = Lc[k + 2], l3 = Lc[k + 3];
-#pragma unroll
-    for (int u = 0; u < NG; ++u) {
-      s0[u] = fma(pr[u][k], l0, s0[u]); s1[u] = fma(pr[u][k + 1], l1, s1[u]);
-      s2[u] = fma(pr[u][k + 2], l2, s2[u]); s3[u] = fma(pr[u][k + 3], l3, s3[u]);
-    }
-  }
-  for (; k < c; ++k) {
-    const double l0 = Lc[k];
-#pragma unroll
-    for (int u = 0; u < NG; ++u) s0[u] = fma(pr[u][k], l0, s0[u]);
-  }
-  double v[NG];
-#pragma unroll
-  for (int u = 0; u < NG; ++u) v[u] = pr[u][c] - ((s0[u] + s1[u]) + (s2[u] + s3[u]));
-  const double piv = __shfl_sync(0xffffffffu, v[0], 0);
-  if (!(piv > 0.0)) return false;
-  const double rs = rsqrt(piv);
-  __syncwarp();  // every lane has read row c's old entries before lane 0 overwrites X[c][c]
-#pragma unroll
-  for (int u = 0; u < NG; ++u)
-    if (act[u]) pr[u][c] = (u == 0 && lane == 0) ? piv * rs : v[u] * rs;
-  __syncwarp();
-  return true;
-}
-template <int ROWS>  // rows per lane: ceil((R2 + 7) / 32) <= ROWS
-__device__ __forceinline__ bool gate_chol_packed(double* __restrict__ X, int R2, int lane) {
+// Blocked by 4 columns (round 2): per block step every lane forms the four dot products of each of its rows against the
+// finished rows c0..c0+3 (the own-row entries are loaded once for the four columns), the owners of the rows c0..c0+3 put
+// the updated 4x4 diagonal block into shared memory, every lane factors it redundantly in registers (4 dependent rsqrt:
+// the serial part) and solves the four entries of its rows: one shuffle-free hand-over, two __syncwarp and one rsqrt chain
+// per FOUR pivots instead of per pivot.  Row r belongs to lane r % 32.
+template <int NR>  // rows per lane: ceil((R2 + 7) / 32) <= NR
+__device__ __forceinline__ bool gate_chol_blocked(double* __restrict__ X, int R2, double* __restrict__ blk, int lane) {
   const int Rend = R2 + 6;
-  for (int c = 0; c < R2; ++c) {
-    const int ng = (Rend - c) / 32 + 1;  // row groups that still hold a row: shrinks as the factorisation advances
-    bool ok;
-    if (ng <= 1) ok = gate_chol_column<1>(X, c, Rend, lane);
-    else if (ng == 2 || ROWS == 2) ok = gate_chol_column<2>(X, c, Rend, lane);
-    else if (ng == 3 || ROWS == 3) ok = gate_chol_column<3>(X, c, Rend, lane);
-    else ok = gate_chol_column<ROWS>(X, c, Rend, lane);
-    if (!ok) return false;
+  for (int c0 = 0; c0 < R2; c0 += 4) {
+    const int nb = min(4, R2 - c0);  // R2 = 2 L is even: the last block may have 2 columns
+    double v[NR][4];
+    const double* L0 = X + tri_idx(c0, 0);
+    const double* L1 = X + tri_idx(c0 + 1, 0);
+    const double* L2 = nb > 2 ? X + tri_idx(c0 + 2, 0) : L0;
+    const double* L3 = nb > 2 ? X + tri_idx(c0 + 3, 0) : L0;
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      const int r = lane + 32 * u;
+      const bool act = r >= c0 && r <= Rend;
+      v[u][0] = 0.0; v[u][1] = 0.0; v[u][2] = 0.0; v[u][3] = 0.0;
+      if (act) {
+        const double* row = X + tri_idx(r, 0);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll 2
+        for (int k = 0; k + 1 < c0; k += 2) {
+          const double a0 = row[k], a1 = row[k + 1];
+          s0 = fma(a0, L0[k], s0); s1 = fma(a0, L1[k], s1); s2 = fma(a0, L2[k], s2); s3 = fma(a0, L3[k], s3);
+          q0 = fma(a1, L0[k + 1], q0); q1 = fma(a1, L1[k + 1], q1); q2 = fma(a1, L2[k + 1], q2); q3 = fma(a1, L3[k + 1], q3);
+        }
+        // entries (r, c0 + j) exist only for c0 + j <= r (packed lower triangle)
+        v[u][0] = row[c0] - (s0 + q0);
+        if (r >= c0 + 1) v[u][1] = row[c0 + 1] - (s1 + q1);
+        if (nb > 2 && r >= c0 + 2) v[u][2] = row[c0 + 2] - (s2 + q2);
+        if (nb > 2 && r >= c0 + 3) v[u][3] = row[c0 + 3] - (s3 + q3);
+        if (r < c0 + nb) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) blk[(r - c0) * 4 + j] = v[u][j];
+        }
+      }
+    }
+    __syncwarp();
+    const double a00 = blk[0], a10 = blk[4], a11 = blk[5];
+    double a20 = 0.0, a21 = 0.0, a22 = 1.0, a30 = 0.0, a31 = 0.0, a32 = 0.0, a33 = 1.0;
+    if (nb > 2) { a20 = blk[8]; a21 = blk[9]; a22 = blk[10]; a30 = blk[12]; a31 = blk[13]; a32 = blk[14]; a33 = blk[15]; }
+    const double r0 = rsqrt(a00);
+    const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+    const double p1 = fma(-l10, l10, a11);
+    const double r1 = rsqrt(p1);
+    const double l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
+    const double p2 = fma(-l21, l21, fma(-l20, l20, a22));
+    const double r2 = rsqrt(p2);
+    const double l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
+    const double p3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
+    const double r3 = rsqrt(p3);
+    if (!(a00 > 0.0) || !(p1 > 0.0) || !(p2 > 0.0) || !(p3 > 0.0)) return false;  // same values in every lane
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      const int r = lane + 32 * u;
+      if (r >= c0 && r <= Rend) {
+        double* row = X + tri_idx(r, 0);
+        // for the rows of the block itself the same formulas give l_ij (j < i) and l_ii = p_i r_i
+        const double x0 = v[u][0] * r0;
+        const double x1 = fma(-x0, l10, v[u][1]) * r1;
+        const double x2 = fma(-x1, l21, fma(-x0, l20, v[u][2])) * r2;
+        const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, v[u][3]))) * r3;
+        row[c0] = x0;
+        if (r >= c0 + 1) row[c0 + 1] = x1;
+        if (nb > 2 && r >= c0 + 2) row[c0 + 2] = x2;
+        if (nb > 2 && r >= c0 + 3) row[c0 + 3] = x3;
+      }
+    }
+    __syncwarp();
   }
   return true;
 }
@@ -550,7 +566,7 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
     // Cholesky of the augmented lower triangle (rows R2..R2+6 are right-hand sides): the last rows become
     // y = L^-1 (Pi r) and Vt = L^-1 V.  Lane-owned rows, 4-wide batches so that loads overlap the FMAs.
     TPROF(7);
-    const bool spd = gate_chol_packed<(64 * OPL + 7 + 31) / 32>(ws.X, R2, lane);
+    const bool spd = gate_chol_blocked<(64 * OPL + 7 + 31) / 32>(ws.X, R2, ws.scr, lane);
     __syncwarp();
     TPROF(8);
     if (spd) {
