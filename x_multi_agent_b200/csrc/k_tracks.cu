@@ -140,7 +140,7 @@ __device__ __forceinline__ bool gate_chol_blocked(double* __restrict__ X, int R2
 }
 
 template <int OPL>  // observations per lane (track length <= 32*OPL)
-__global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
+__global__ void __launch_bounds__(128, 3) k_tracks(TrackParams tp) {  // <= 168 registers: leaves the register file room for the side-stream kernels
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int M = tp.M, np = tp.n_poses;
@@ -461,26 +461,41 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
           const int pk_ = sk ? np - 1 : i1 + k;
           const double* Jk_p = (sk ? ws.Jap : ws.Jp) + 6 * k;
           const double* Jk_a = (sk ? ws.Jaa : ws.Ja) + 6 * k;
-          // T (2x6) = [Ji_p Ji_a] * P[pose pi_, pose pk_]
+          // T (2x6) = [Ji_p Ji_a] * P[pose pi_, pose pk_]: the 36 entries of the 6x6 block are loaded first (one L2
+          // latency per block pair instead of one per column)
           double T[12];
           const int rp = XB_CORE + 3 * pi_, ra = XB_CORE + 3 * M + 3 * pi_;
           const int cpn = XB_CORE + 3 * pk_, can = XB_CORE + 3 * M + 3 * pk_;
+          double pb[6][6];  // rows: pos a, att a of pose pi_; columns: pos c, att c of pose pk_
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              pb[a][c] = P[(size_t)(rp + a) * ld + cpn + c];
+              pb[a][3 + c] = P[(size_t)(rp + a) * ld + can + c];
+              pb[3 + a][c] = P[(size_t)(ra + a) * ld + cpn + c];
+              pb[3 + a][3 + c] = P[(size_t)(ra + a) * ld + can + c];
+            }
           // blocks among the newest clones are not symmetric (one clone in the regular case, more after updates without
           // measurement rows): use sym(P) there
           const bool symblk = pi_ >= np - tp.asym_clones && pk_ >= np - tp.asym_clones;
+          if (symblk) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                pb[a][c] = 0.5 * (pb[a][c] + P[(size_t)(cpn + c) * ld + rp + a]);
+                pb[a][3 + c] = 0.5 * (pb[a][3 + c] + P[(size_t)(can + c) * ld + rp + a]);
+                pb[3 + a][c] = 0.5 * (pb[3 + a][c] + P[(size_t)(cpn + c) * ld + ra + a]);
+                pb[3 + a][3 + c] = 0.5 * (pb[3 + a][3 + c] + P[(size_t)(can + c) * ld + ra + a]);
+              }
+          }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             double tp0 = 0, tp1 = 0, ta0 = 0, ta1 = 0;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-              double ppp = P[(size_t)(rp + a) * ld + cpn + c], pap = P[(size_t)(ra + a) * ld + cpn + c];
-              double ppa = P[(size_t)(rp + a) * ld + can + c], paa = P[(size_t)(ra + a) * ld + can + c];
-              if (symblk) {
-                ppp = 0.5 * (ppp + P[(size_t)(cpn + c) * ld + rp + a]);
-                pap = 0.5 * (pap + P[(size_t)(cpn + c) * ld + ra + a]);
-                ppa = 0.5 * (ppa + P[(size_t)(can + c) * ld + rp + a]);
-                paa = 0.5 * (paa + P[(size_t)(can + c) * ld + ra + a]);
-              }
+              const double ppp = pb[a][c], pap = pb[3 + a][c], ppa = pb[a][3 + c], paa = pb[3 + a][3 + c];
               tp0 = fma(Ji_p[a], ppp, tp0); tp0 = fma(Ji_a[a], pap, tp0);
               tp1 = fma(Ji_p[3 + a], ppp, tp1); tp1 = fma(Ji_a[3 + a], pap, tp1);
               ta0 = fma(Ji_p[a], ppa, ta0); ta0 = fma(Ji_a[a], paa, ta0);
@@ -534,16 +549,27 @@ __global__ void __launch_bounds__(128) k_tracks(TrackParams tp) {
       for (int v = 0; v < 3; ++v)
         ws.V[r * 3 + v] = ws.Y[r * 3 + v] - 0.5 * (ws.U[r * 3] * Z[v] + ws.U[r * 3 + 1] * Z[3 + v] + ws.U[r * 3 + 2] * Z[6 + v]);
     __syncwarp();
-    // (in place, packed), augmented row R2 = (Pi r)^T
-    const int nel = R2 * (R2 + 1) / 2;
-    int r = 0, c = 0;
-    tri_advance(r, c, lane);
-    for (int e = lane; e < nel; e += 32, tri_advance(r, c, 32)) {
-      double s = ws.X[e];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) s -= ws.U[r * 3 + u] * ws.V[c * 3 + u] + ws.V[r * 3 + u] * ws.U[c * 3 + u];
-      if (r == c) s += tp.var_img;
-      ws.X[e] = s;
+    // (in place, packed), augmented row R2 = (Pi r)^T.  Row-wise: a lane takes the rows r and R2-1-r (R2 + 1 elements
+    // together, so the lanes are balanced), keeps U_r, V_r in registers and walks the columns; all lanes read U_c, V_c of
+    // the same column at the same time (broadcasts).
+    for (int h = lane; h < (R2 + 1) / 2; h += 32) {
+#pragma unroll 1
+      for (int side = 0; side < 2; ++side) {
+        const int r = side ? R2 - 1 - h : h;
+        if (side && r == h) break;
+        const double u0 = ws.U[r * 3], u1 = ws.U[r * 3 + 1], u2 = ws.U[r * 3 + 2];
+        const double v0 = ws.V[r * 3], v1 = ws.V[r * 3 + 1], v2 = ws.V[r * 3 + 2];
+        double* xr = ws.X + tri_idx(r, 0);
+#pragma unroll 4
+        for (int c = 0; c <= r; ++c) {
+          double sv = xr[c];
+          sv -= u0 * ws.V[c * 3] + v0 * ws.U[c * 3];
+          sv -= u1 * ws.V[c * 3 + 1] + v1 * ws.U[c * 3 + 1];
+          sv -= u2 * ws.V[c * 3 + 2] + v2 * ws.U[c * 3 + 2];
+          if (c == r) sv += tp.var_img;
+          xr[c] = sv;
+        }
+      }
     }
     double* aug = ws.X + tri_idx(R2, 0);
     for (int r = lane; r < R2; r += 32)
