@@ -64,16 +64,30 @@ class Feature {
   Feature() = default;
   Feature(const double& timestamp, double x, double y, double intensity = -1.0)
       : timestamp_(timestamp), x_(x), y_(y), intensity_(intensity) {}
+  Feature(const double& timestamp, unsigned int frame_number, double x, double y, double x_dist, double y_dist,
+          double intensity = -1.0)
+      : timestamp_(timestamp), x_(x), y_(y), intensity_(intensity), x_dist_(x_dist), y_dist_(y_dist), frame_number_(frame_number) {}
   void setX(const double x) { x_ = x; }
   void setY(const double y) { y_ = y; }
+  void setXDist(const double x_dist) { x_dist_ = x_dist; }
+  void setYDist(const double y_dist) { y_dist_ = y_dist; }
+  [[nodiscard]] double getXDist() const { return x_dist_; }   // distorted (measured) pixel coordinates
+  [[nodiscard]] double getYDist() const { return y_dist_; }
   [[nodiscard]] double getTimestamp() const { return timestamp_; }
   [[nodiscard]] double getX() const { return x_; }   // normalised image coordinates
   [[nodiscard]] double getY() const { return y_; }
   [[nodiscard]] double getIntensity() const { return intensity_; }
 
  private:
-  double timestamp_{0}, x_{0}, y_{0}, intensity_{-1};
+  double timestamp_{0}, x_{0}, y_{0}, intensity_{-1}, x_dist_{0}, y_dist_{0};
+  unsigned int frame_number_{0};
 };
+/** include/x/vision/types.h:39-42 */
+struct Match {
+  Feature previous;
+  Feature current;
+};
+using MatchList = std::vector<Match>;
 class Track : public std::vector<Feature> {
  public:
   Track() : std::vector<Feature>() { id_ = ++counter(); }
@@ -385,24 +399,134 @@ class Tracker {};
 /** Carries what VioUpdater::preProcess reads from the reference's TrackManager (vio_updater.cpp:172-179): the five
  *  normalised track lists and the lost SLAM feature indexes.  Sorting matches into these lists
  *  (TrackManager::manageTracks) is the step before the hot path. */
+/** x::Camera (include/x/vision/camera.h): the intrinsics the track manager needs (FOV distortion model). */
+class Camera {
+ public:
+  Camera() = default;
+  Camera(double fx, double fy, double cx, double cy, double s, unsigned int img_width, unsigned int img_height)
+      : fx_(fx), fy_(fy), cx_(cx), cy_(cy), s_(s), img_width_(img_width), img_height_(img_height) {}
+  [[nodiscard]] unsigned int getWidth() const { return img_width_; }
+  [[nodiscard]] unsigned int getHeight() const { return img_height_; }
+  double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0, s_ = 0;  // as given: fractions of the image size (camera.cpp:27-35)
+  unsigned int img_width_ = 0, img_height_ = 0;
+};
+/** x::TiledImage (include/x/vision/tiled_image.h) without the pixels: the tile grid manageTracks balances over. */
+class TiledImage {
+ public:
+  TiledImage() = default;
+  TiledImage(unsigned int n_tiles_h, unsigned int n_tiles_w) : n_tiles_h_(n_tiles_h), n_tiles_w_(n_tiles_w) {}
+  [[nodiscard]] unsigned int getNTilesH() const { return n_tiles_h_; }
+  [[nodiscard]] unsigned int getNTilesW() const { return n_tiles_w_; }
+ private:
+  unsigned int n_tiles_h_ = 1, n_tiles_w_ = 1;
+};
+
+/** x::TrackManager (include/x/vio/track_manager.h).  manageTracks (track_manager.cpp:115-436) runs in libxb200.so
+ *  (xb_tm_*, host code); the lists can also be injected directly (setTracks) when the caller has its own front end. */
 class TrackManager {
  public:
+  TrackManager() = default;
+  TrackManager(const Camera& camera, const double min_baseline_x_n, const double min_baseline_y_n)
+      : camera_(camera), min_baseline_x_n_(min_baseline_x_n), min_baseline_y_n_(min_baseline_y_n) {}
+  TrackManager(const TrackManager& o) { *this = o; }
+  TrackManager& operator=(const TrackManager& o) {
+    if (this == &o) return *this;
+    release();
+    camera_ = o.camera_; min_baseline_x_n_ = o.min_baseline_x_n_; min_baseline_y_n_ = o.min_baseline_y_n_;
+    slam_ = o.slam_; msckf_ = o.msckf_; short_ = o.short_; new_std_ = o.new_std_; new_msckf_ = o.new_msckf_; lost_ = o.lost_;
+    injected_ = o.injected_; tiles_h_ = o.tiles_h_; tiles_w_ = o.tiles_w_;
+    tm_ = o.tm_; refs_ = o.refs_;
+    if (refs_) ++*refs_;
+    return *this;
+  }
+  ~TrackManager() { release(); }
+  void setCamera(Camera camera) { camera_ = camera; }
   void setTracks(TrackList slam, TrackList msckf, TrackList msckf_short, TrackList new_slam_std, TrackList new_slam_msckf,
                  std::vector<unsigned int> lost_slam_idxs) {
     slam_ = std::move(slam); msckf_ = std::move(msckf); short_ = std::move(msckf_short);
     new_std_ = std::move(new_slam_std); new_msckf_ = std::move(new_slam_msckf); lost_ = std::move(lost_slam_idxs);
+    injected_ = true;
   }
-  TrackList normalizeSlamTracks(const int) const { return slam_; }
-  TrackList getMsckfTracks() const { return msckf_; }
-  TrackList getShortMsckfTracks() const { return short_; }
-  TrackList getNewSlamStdTracks() const { return new_std_; }
-  TrackList getNewSlamMsckfTracks() const { return new_msckf_; }
-  std::vector<unsigned int> getLostSlamTrackIndexes() const { return lost_; }
-  void clear() { *this = TrackManager(); }
+  /** track_manager.cpp:115-436; matches carry distorted pixel coordinates (getXDist / getYDist), as after
+   *  VIO::importMatches before undistortion -- the undistortion of vio.cpp:399-405 is part of the call. */
+  void manageTracks(MatchList& matches, const AttitudeList cam_rots, const size_t n_poses_max, const size_t n_slam_features_max,
+                    const size_t min_track_length, TiledImage& img) {
+    if (!tm_ || tiles_h_ != img.getNTilesH() || tiles_w_ != img.getNTilesW()) {
+      release();
+      xb_tm_config c{};
+      c.fx = camera_.fx_; c.fy = camera_.fy_; c.cx = camera_.cx_; c.cy = camera_.cy_; c.s = camera_.s_;
+      c.img_width = camera_.img_width_; c.img_height = camera_.img_height_;
+      c.min_baseline_x_n = min_baseline_x_n_; c.min_baseline_y_n = min_baseline_y_n_;
+      c.n_tiles_h = tiles_h_ = img.getNTilesH(); c.n_tiles_w = tiles_w_ = img.getNTilesW();
+      tm_ = xb_tm_create(&c);
+      if (!tm_) throw std::invalid_argument("TrackManager: invalid camera / tile configuration");
+      refs_ = new int(1);
+    }
+    std::vector<double> mv(10 * matches.size(), 0.0), rots(4 * cam_rots.size());
+    for (size_t i = 0; i < matches.size(); ++i) {
+      mv[10 * i + 1] = matches[i].previous.getTimestamp(); mv[10 * i + 2] = matches[i].previous.getXDist();
+      mv[10 * i + 3] = matches[i].previous.getYDist(); mv[10 * i + 4] = matches[i].current.getTimestamp();
+      mv[10 * i + 5] = matches[i].current.getXDist(); mv[10 * i + 6] = matches[i].current.getYDist();
+    }
+    for (size_t i = 0; i < cam_rots.size(); ++i) {
+      rots[4 * i] = cam_rots[i].ax; rots[4 * i + 1] = cam_rots[i].ay; rots[4 * i + 2] = cam_rots[i].az; rots[4 * i + 3] = cam_rots[i].aw;
+    }
+    detail_check(xb_tm_manage_tracks(tm_, mv.data(), static_cast<int>(matches.size()), rots.data(), static_cast<int>(cam_rots.size()),
+                                     static_cast<int>(n_poses_max), static_cast<int>(n_slam_features_max),
+                                     static_cast<int>(min_track_length)));
+    matches.clear();  // the reference consumes the matched entries (track_manager.cpp:167)
+    injected_ = false;
+  }
+  TrackList normalizeSlamTracks(const int size_out) const { return injected_ || !tm_ ? slam_ : fetch(XB_TM_SLAM, size_out); }
+  TrackList getMsckfTracks() const { return injected_ || !tm_ ? msckf_ : fetch(XB_TM_MSCKF, 0); }
+  TrackList getShortMsckfTracks() const { return injected_ || !tm_ ? short_ : fetch(XB_TM_MSCKF_SHORT, 0); }
+  TrackList getNewSlamStdTracks() const { return injected_ || !tm_ ? new_std_ : fetch(XB_TM_NEW_SLAM_STD, 0); }
+  TrackList getNewSlamMsckfTracks() const { return injected_ || !tm_ ? new_msckf_ : fetch(XB_TM_NEW_SLAM_MSCKF, 0); }
+  TrackList getOppTracks() const { return tm_ ? fetch(XB_TM_OPP, 0) : TrackList(); }
+  std::vector<unsigned int> getLostSlamTrackIndexes() const {
+    if (injected_ || !tm_) return lost_;
+    std::vector<int> tmp(static_cast<size_t>(std::max(1, xb_tm_lost_slam_idxs(tm_, nullptr, 0))));
+    const int n = xb_tm_lost_slam_idxs(tm_, tmp.data(), static_cast<int>(tmp.size()));
+    return std::vector<unsigned int>(tmp.begin(), tmp.begin() + n);
+  }
+  void removePersistentTracksAtIndex(const unsigned int idx) { if (tm_) detail_check(xb_tm_remove_persistent_track(tm_, idx)); }
+  void removeNewPersistentTracksAtIndexes(const std::vector<unsigned int> invalid_tracks_idx) {
+    if (tm_) detail_check(xb_tm_remove_new_persistent_tracks(tm_, invalid_tracks_idx.data(), static_cast<int>(invalid_tracks_idx.size())));
+  }
+  void clear() {
+    slam_.clear(); msckf_.clear(); short_.clear(); new_std_.clear(); new_msckf_.clear(); lost_.clear();
+    if (tm_) xb_tm_clear(tm_);
+  }
 
  private:
+  static void detail_check(int rc) { if (rc < 0) throw std::invalid_argument("TrackManager: xb_tm call failed"); }
+  TrackList fetch(int which, int size_out) const {
+    int nt = 0, no = 0;
+    detail_check(xb_tm_list_size(tm_, which, size_out, &nt, &no));
+    std::vector<int> off(static_cast<size_t>(nt) + 1);
+    std::vector<double> xy(2 * static_cast<size_t>(std::max(1, no)));
+    std::vector<unsigned long long> ids(static_cast<size_t>(std::max(1, nt)));
+    detail_check(xb_tm_get_list(tm_, which, size_out, off.data(), xy.data(), ids.data()));
+    TrackList out;
+    for (int i = 0; i < nt; ++i) {
+      Track t(static_cast<size_t>(off[i + 1] - off[i]), Feature(), ids[static_cast<size_t>(i)]);
+      for (int j = off[i]; j < off[i + 1]; ++j) { t[static_cast<size_t>(j - off[i])].setX(xy[2 * j]); t[static_cast<size_t>(j - off[i])].setY(xy[2 * j + 1]); }
+      out.push_back(t);
+    }
+    return out;
+  }
+  void release() {
+    if (refs_ && --*refs_ == 0) { xb_tm_destroy(tm_); delete refs_; }
+    tm_ = nullptr; refs_ = nullptr;
+  }
+  Camera camera_;
+  double min_baseline_x_n_ = 0.0, min_baseline_y_n_ = 0.0;
   TrackList slam_, msckf_, short_, new_std_, new_msckf_;
   std::vector<unsigned int> lost_;
+  bool injected_ = false;
+  xb_track_manager* tm_ = nullptr;   // shared between copies (VioUpdater keeps a copy of the manager it is given)
+  int* refs_ = nullptr;
+  unsigned int tiles_h_ = 0, tiles_w_ = 0;
 };
 
 /** x::StateManager (include/x/vio/state_manager.h): the window / feature bookkeeping lives in the device filter; this

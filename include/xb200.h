@@ -263,6 +263,39 @@ XB_API int xb_profile_read(xb_filter* f, const char** names, double* ms, long lo
 XB_API long long xb_kernel_launches(const xb_filter* f);                /* kernels launched so far */
 XB_API double xb_chi2_quantile(double p, double dof);                   /* boost::math::quantile(chi_squared) */
 
+/* ---- track management and match import (part of f-1): the step in front of the hot path ---------------
+ * Host-side list logic (no device work): TrackManager::manageTracks + checkBaseline (src/x/vio/track_manager.cpp:
+ * 115-436, 576-636) fed by the 10-double match vector of VIO::importMatches (src/x/vio/vio.cpp:372-434).  The lists it
+ * returns are in the CSR form xb_vio_set_measurement takes (normalised image coordinates). */
+typedef struct xb_track_manager xb_track_manager;
+typedef struct xb_tm_config {
+  double fx, fy, cx, cy;          /* Camera (camera.cpp:27-48): fractions of the image width / height */
+  double s;                       /* FOV distortion parameter (0: none) */
+  unsigned img_width, img_height;
+  double min_baseline_x_n, min_baseline_y_n;  /* TrackManager ctor (track_manager.cpp:27-32) */
+  unsigned n_tiles_h, n_tiles_w;  /* TiledImage (tiled_image.cpp:38-52) */
+  int multi_uav;                  /* 1: the -DMULTI_UAV flavour of the short-track rule (track_manager.cpp:239-262) */
+} xb_tm_config;
+enum { XB_TM_MSCKF = 0, XB_TM_MSCKF_SHORT = 1, XB_TM_NEW_SLAM_STD = 2, XB_TM_NEW_SLAM_MSCKF = 3, XB_TM_SLAM = 4, XB_TM_OPP = 5 };
+XB_API xb_track_manager* xb_tm_create(const xb_tm_config* cfg);
+XB_API void xb_tm_destroy(xb_track_manager* tm);
+XB_API void xb_tm_clear(xb_track_manager* tm);                                   /* TrackManager::clear, :74-81 */
+/* VIO::importMatches + TrackManager::manageTracks.  match_vector: 10 doubles per match [cam_id, t_prev, x_prev, y_prev,
+ * t_cur, x_cur, y_cur, landmark xyz] (distorted pixel coordinates); cam_rots: n_rots x 4 (Attitude ax, ay, az, aw), the
+ * window's camera attitudes followed by the current one (vio_updater.cpp:150-153). */
+XB_API int xb_tm_manage_tracks(xb_track_manager* tm, const double* match_vector, int n_matches, const double* cam_rots,
+                               int n_rots, int n_poses_max, int n_slam_features_max, int min_track_length);
+/* TrackManager::get*Tracks / normalizeSlamTracks(size_out) (:36-61): sizes, then offsets[n_tracks + 1] + xy[2 * n_obs]
+ * (+ optional track ids).  xb_tm_get_list returns the number of tracks. */
+XB_API int xb_tm_list_size(const xb_track_manager* tm, int which, int size_out, int* n_tracks, int* n_obs);
+XB_API int xb_tm_get_list(const xb_track_manager* tm, int which, int size_out, int* offsets, double* xy,
+                          unsigned long long* ids);
+XB_API int xb_tm_lost_slam_idxs(const xb_track_manager* tm, int* idxs, int cap);  /* getLostSlamTrackIndexes, :99-101 */
+XB_API int xb_tm_remove_persistent_track(xb_track_manager* tm, unsigned idx);     /* removePersistentTracksAtIndex, :83-85 */
+XB_API int xb_tm_remove_new_persistent_tracks(xb_track_manager* tm, const unsigned* idxs, int n);  /* :87-97 */
+XB_API int xb_tm_set_opp_ids(xb_track_manager* tm, const unsigned long long* ids, int n);  /* setOppUpgradesMSCKF (MULTI_UAV) */
+XB_API int xb_tm_counts(const xb_track_manager* tm, int* n_slam, int* n_new_slam, int* n_opp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,9 @@
 #                       tiled_image,triangulation}.cpp, unmodified) against the stand-in headers of shim/ (Eigen,
 #                       OpenCV, Boost, NLopt are not installed here) + xref_harness.cpp; strict IEEE arithmetic (-O2)
 #  libxref_multi.so     the same with -DMULTI_UAV (+ ci.cpp, simple_state.cpp, multi_slam_update.cpp)
+#  libxref_tm.so        the reference's own TrackManager (src/x/vio/track_manager.cpp + src/x/vision/{camera,feature,track,
+#                       tiled_image}.cpp, unmodified; the front-end stubs of shim_stubs/ are NOT on its include path) +
+#                       xref_tm_harness.cpp: pins oracle/track_manager.py and the product's xb_tm_* 
 #  libxref_release.so   single-agent flavour with the reference's Release flags (CMakeLists.txt:185,194): the binary
 #                       bench.py times as the CPU reference
 set -euo pipefail
@@ -15,6 +18,8 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${XREF_ROOT:-/root/reference}"
 OUT="$HERE/../_ref"
 mkdir -p "$OUT"
+# std::sort helper of oracle/track_manager.py (no reference source involved)
+g++ -O2 -fPIC -shared -o "$OUT/libxsort.so" "$HERE/xsort.cpp"
 if [ ! -d "$REF/src/x/ekf" ]; then
   echo "build_ref: $REF not present; keeping prebuilt oracle/_ref" >&2
   exit 0
@@ -32,7 +37,7 @@ TUS="ekf/state ekf/propagator ekf/state_buffer ekf/updater ekf/ekf vision/featur
      vio/range_update vio/solar_update"
 TUS_MULTI="ekf/ci ekf/simple_state vio/multi_slam_update"
 RELEASE="-O3 -funsafe-loop-optimizations -fsee -funroll-loops -fno-math-errno -funsafe-math-optimizations -ffinite-math-only -fno-signed-zeros -DNDEBUG"
-COMMON="-std=c++17 -fPIC -w -DMULTI_THREAD -DEIGEN_MATRIXBASE_PLUGIN=<x/common/eigen_matrix_base_plugin.h> -I$HERE/shim -I$REF/include"
+COMMON="-std=c++17 -fPIC -w -DMULTI_THREAD -DEIGEN_MATRIXBASE_PLUGIN=<x/common/eigen_matrix_base_plugin.h> -I$HERE/shim_stubs -I$HERE/shim -I$REF/include"
 
 build_flavour() {  # name, extra flags, extra TUs
   local name="$1" flags="$2" extra="$3" dir="$OUT/obj_$1"
@@ -57,3 +62,17 @@ build_flavour() {  # name, extra flags, extra TUs
 build_flavour libxref "-O2" ""
 build_flavour libxref_multi "-O2 -DMULTI_UAV" "$TUS_MULTI"
 build_flavour libxref_release "$RELEASE" ""
+
+# ---- the reference's TrackManager (real header, no front-end stubs)
+TMDIR="$OUT/obj_tm"
+mkdir -p "$TMDIR"
+TMOBJS=""
+for tu in vio/track_manager vision/camera vision/feature vision/track vision/tiled_image; do
+  o="$TMDIR/$(echo "$tu" | tr / _).o"
+  TMOBJS="$TMOBJS $o"
+  g++ -std=c++17 -fPIC -w -O2 "-DEIGEN_MATRIXBASE_PLUGIN=<x/common/eigen_matrix_base_plugin.h>" -I"$HERE/shim" -I"$REF/include" -c "$REF/src/x/$tu.cpp" -o "$o" &
+done
+g++ -std=c++17 -fPIC -w -O2 "-DEIGEN_MATRIXBASE_PLUGIN=<x/common/eigen_matrix_base_plugin.h>" -I"$HERE/shim" -I"$REF/include" -c "$HERE/xref_tm_harness.cpp" -o "$TMDIR/harness.o" &
+wait
+g++ -shared -Wl,-Bsymbolic -o "$OUT/libxref_tm.so" $TMOBJS "$TMDIR/harness.o"
+echo "build_ref: built $OUT/libxref_tm.so from $REF/src/x/vio/track_manager.cpp"

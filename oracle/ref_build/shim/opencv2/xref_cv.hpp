@@ -103,11 +103,42 @@ template <typename T> class MatCommaInitializer_ {
 };
 template <typename T> MatCommaInitializer_<T> Mat_<T>::operator<<(T v) { return MatCommaInitializer_<T>(*this, v); }
 
+// Delaunay lookup of TrackManager::featureTriangleAtPoint (range-finder facet, out of scope): the type exists so that the
+// reference's track_manager.cpp compiles unmodified; locate() reports "outside", so the caller gets no facet.
+struct Rect {
+  int x = 0, y = 0, width = 0, height = 0;
+  Rect() {}
+  Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {}
+  template <typename T> bool contains(const Point_<T>& p) const { return p.x >= x && p.y >= y && p.x < x + width && p.y < y + height; }
+};
+template <typename T, int N> struct Vec {
+  T v[N] = {};
+  T& operator[](int i) { return v[i]; }
+  const T& operator[](int i) const { return v[i]; }
+};
+typedef Vec<float, 6> Vec6f;
+typedef Vec<float, 4> Vec4f;
+class Subdiv2D {
+ public:
+  enum { PTLOC_ERROR = -2, PTLOC_OUTSIDE_RECT = -1, PTLOC_INSIDE = 0, PTLOC_VERTEX = 1, PTLOC_ON_EDGE = 2 };
+  Subdiv2D() {}
+  explicit Subdiv2D(Rect) {}
+  template <typename T> int insert(const Point_<T>&) { return 0; }
+  template <typename T> int locate(const Point_<T>&, int& edge, int& vertex) { edge = 0; vertex = 0; return PTLOC_OUTSIDE_RECT; }
+  int edgeOrg(int, Point2f* = nullptr) const { return 0; }
+  int edgeDst(int, Point2f* = nullptr) const { return 0; }
+  int nextEdge(int) const { return 0; }
+  Point2f getVertex(int, int* first_edge = nullptr) const { if (first_edge) *first_edge = 0; return Point2f(); }
+  void getTriangleList(std::vector<Vec6f>& t) const { t.clear(); }
+};
+
 // drawing: no-ops
 template <typename... A> inline void rectangle(A&&...) {}
 template <typename... A> inline void line(A&&...) {}
 template <typename... A> inline void circle(A&&...) {}
 template <typename... A> inline void putText(A&&...) {}
+template <typename... A> inline void cvtColor(A&&...) {}
+template <typename... A> inline Size getTextSize(A&&...) { return Size(); }
 enum { FONT_HERSHEY_SIMPLEX = 0, FONT_HERSHEY_PLAIN = 1, LINE_AA = 16, LINE_8 = 8 };
 
 // Two-view linear triangulation (the DLT cv::triangulatePoints documents): for every point the homogeneous
@@ -169,4 +200,11 @@ inline void triangulatePoints(const Mat& P1, const Mat& P2, const Mat& x1, const
   }
 }
 }  // namespace cv
+inline int cvRound(double x) { return (int)std::lround(x); }
+#ifndef CV_AA
+#define CV_AA 16
+#endif
+#ifndef CV_GRAY2BGR
+#define CV_GRAY2BGR 8
+#endif
 #endif

@@ -56,7 +56,26 @@ class XbMsckfMatch(C.Structure):
 
 # every exported symbol of include/xb200.h: name -> (restype, argtypes)
 _VP = C.c_void_p
+
+class XbTmConfig(C.Structure):
+    """xb_tm_config (include/xb200.h)."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("s", C.c_double),
+                ("img_width", C.c_uint), ("img_height", C.c_uint), ("min_baseline_x_n", C.c_double),
+                ("min_baseline_y_n", C.c_double), ("n_tiles_h", C.c_uint), ("n_tiles_w", C.c_uint), ("multi_uav", C.c_int)]
+
+
 SIGNATURES = {
+    "xb_tm_create": (_VP, [C.POINTER(XbTmConfig)]),
+    "xb_tm_destroy": (None, [_VP]),
+    "xb_tm_clear": (None, [_VP]),
+    "xb_tm_manage_tracks": (C.c_int, [_VP, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "xb_tm_list_size": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "xb_tm_get_list": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "xb_tm_lost_slam_idxs": (C.c_int, [_VP, C.POINTER(C.c_int), C.c_int]),
+    "xb_tm_remove_persistent_track": (C.c_int, [_VP, C.c_uint]),
+    "xb_tm_remove_new_persistent_tracks": (C.c_int, [_VP, C.POINTER(C.c_uint), C.c_int]),
+    "xb_tm_set_opp_ids": (C.c_int, [_VP, C.POINTER(C.c_ulonglong), C.c_int]),
+    "xb_tm_counts": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "xb_default_config": (None, [C.POINTER(XbConfig)]),
     "xb_create": (C.c_int, [C.POINTER(XbConfig), C.POINTER(_VP)]),
     "xb_destroy": (C.c_int, [_VP]),
