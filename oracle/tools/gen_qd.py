@@ -137,64 +137,66 @@ def main():
     out.mkdir(parents=True, exist_ok=True)
     (out / "qd_poly.cuh").write_text("\n".join(cu) + "\n")
 
-    # ---- partitioned form: the entries are split into NPART groups of similar cost so that NPART warps evaluate the
-    #      polynomial concurrently (k_prop_step, k_prop_means).  Every group evaluates the statements of the ONE global CSE
-    #      above that its entries depend on, in the same order and with the same text: bit-identical to xb_qd_poly (a CSE per
-    #      group re-associates the cancelling terms of the polynomial, which showed up as 1e-10 relative differences in the
-    #      small entries and, through one ill-conditioned update, as 1e-7 in a 65-update parity sequence); temporaries
-    #      shared between groups are recomputed.
-    NPART = 7
-    syms = [sym for sym, _ in repl]
-    pos = {sym: i for i, sym in enumerate(syms)}
+    pos = {sym: i for i, (sym, _) in enumerate(repl)}
     ops = [sp.count_ops(e) + 1 for _, e in repl]
-    deps = []
-    for i, (sym, e) in enumerate(repl):
-        d = set()
-        for fs in e.free_symbols:
-            if fs in pos:
-                d |= {pos[fs]} | deps[pos[fs]]
-        deps.append(d)
-    need = []
-    for e in red:
-        d = set()
-        for fs in e.free_symbols:
-            if fs in pos:
-                d |= {pos[fs]} | deps[pos[fs]]
-        need.append(d)
     ecost = [sp.count_ops(e) + 1 for e in red]
-    order = sorted(range(len(nz)), key=lambda i: -(ecost[i] + sum(ops[j] for j in need[i])))
-    groups, have, load = [[] for _ in range(NPART)], [set() for _ in range(NPART)], [0] * NPART
-    for i in order:
-        best, bl = 0, None
-        for g in range(NPART):
-            l = load[g] + ecost[i] + sum(ops[j] for j in need[i] - have[g])
-            if bl is None or l < bl:
-                best, bl = g, l
-        groups[best].append(i)
-        have[best] |= need[i]
-        load[best] = bl
+    # ---- level-scheduled form: every statement of the global CSE exactly once (bit-identical to xb_qd_poly), temporaries in
+    #      shared memory S[], statements of one dependency level spread over NWARP warps (one lane each); the caller puts a
+    #      block barrier between levels.  Per warp this is ~1/5 of the instructions of a partition above: the kernels run
+    #      this code once per launch on cold instruction caches, where the instruction count IS the latency.  (An earlier
+    #      form split the ENTRIES into 7 groups with a CSE per group: faster still, but a CSE per group re-associates
+    #      cancelling terms -- 1e-10 relative differences in the small entries, amplified to 1e-7 by one ill-conditioned
+    #      update of the 65-update parity sequence; with the global CSE per group every group recomputes ~95 of the 224
+    #      temporaries.)
+    NWARP = 15
+    lvl_t = []
+    for i, (sym, e) in enumerate(repl):
+        d = [pos[fs] for fs in e.free_symbols if fs in pos]
+        lvl_t.append(1 + max([lvl_t[j] for j in d], default=-1))
+    lvl_e = [1 + max([lvl_t[pos[fs]] for fs in e.free_symbols if fs in pos], default=-1) for e in red]
+    nlev = max(max(lvl_t), max(lvl_e)) + 1
+    sched = [[[] for _ in range(NWARP)] for _ in range(nlev)]
+    loadw = [[0] * NWARP for _ in range(nlev)]
 
-    cp = [f"// {hdr}", "// Partitioned form: xb_qd_poly_part(part, ...) writes the entries of group `part` (0..XB_QD_NPART-1); the statements",
-          "// are those of xb_qd_poly (qd_poly.cuh), each group keeps the ones its entries need.",
-          "#pragma once", f"#define XB_QD_NPART {NPART}",
-          "__device__ __noinline__ void xb_qd_poly_part(int part, double dt, const double* C, const double* w, const double* a,",
-          "                                             double n_w, double n_bw, double n_a, double n_ba, double* Q) {",
+    def to_s(code):
+        return re.sub(r"\bs(\d+)\b", r"S[\1]", code)
+
+    def place(level, cost, text):
+        w = loadw[level].index(min(loadw[level]))
+        sched[level][w].append(text)
+        loadw[level][w] += cost
+
+    for i in sorted(range(len(repl)), key=lambda i: -ops[i]):
+        place(lvl_t[i], ops[i], f"S[{i}] = {to_s(sp.ccode(repl[i][1]))};")
+    # entries have no dependants: an entry goes to the least loaded level at or after its own
+    for i in sorted(range(len(nz)), key=lambda i: -ecost[i]):
+        r, c = nz[i]
+        best = min(range(lvl_e[i], nlev), key=lambda L: min(loadw[L]))
+        place(best, ecost[i], f"Q[{r * 15 + c}] = {to_s(sp.ccode(red[i]))};")
+    assert all(str(sym) == f"s{i}" for i, (sym, _) in enumerate(repl))
+    cl = [f"// {hdr}", "// Level-scheduled form: xb_qd_poly_warp(w, ...) is executed by ALL lanes of warp w (0..XB_QD_NWARP-1) of a CTA, redundantly",
+          "// (the polynomial is scalar); it runs that warp's statements of every dependency level in turn, with a named barrier",
+          "// over the XB_QD_NWARP warps between levels (bar.sync 1).  Temporaries live in S[XB_QD_NTEMP] (shared memory).  Every",
+          "// statement of xb_qd_poly (qd_poly.cuh) appears exactly once, with the same text: bit-identical results.  A warp's",
+          "// statements are contiguous in the code (sequential instruction fetch: the kernels run this once per launch).",
+          "#pragma once", f"#define XB_QD_NLEVEL {nlev}", f"#define XB_QD_NWARP {NWARP}", f"#define XB_QD_NTEMP {len(repl)}",
+          f'#define XB_QD_BAR() asm volatile("bar.sync 1, {32 * NWARP};" ::: "memory")',
+          "__device__ __noinline__ void xb_qd_poly_warp(int w, double dt, const double* C, const double* wv, const double* a,",
+          "                                             double n_w, double n_bw, double n_a, double n_ba, double* S, double* Q) {",
           "  const double C00 = C[0], C01 = C[1], C02 = C[2], C10 = C[3], C11 = C[4], C12 = C[5], C20 = C[6], C21 = C[7], C22 = C[8];",
-          "  const double w0 = w[0], w1 = w[1], w2 = w[2], a0 = a[0], a1 = a[1], a2 = a[2];",
-          "  switch (part) {"]
-    for g, idxs in enumerate(groups):
-        cp.append(f"    case {g}: {{")
-        for j in sorted(have[g]):
-            sym, e = repl[j]
-            cp.append(f"      const double {sym} = {sp.ccode(e)};")
-        for i in sorted(idxs):
-            r, c = nz[i]
-            cp.append(f"      Q[{r * 15 + c}] = {sp.ccode(red[i])};")
-        cp.append("      break;")
-        cp.append("    }")
-        print(f"part {g}: {len(idxs)} entries, {len(have[g])} temporaries, cost {load[g]}", file=sys.stderr)
-    cp += ["    default: break;", "  }", "}"]
-    (out / "qd_poly_parts.cuh").write_text("\n".join(cp) + "\n")
+          "  const double w0 = wv[0], w1 = wv[1], w2 = wv[2], a0 = a[0], a1 = a[1], a2 = a[2];",
+          "  switch (w) {"]
+    for w in range(NWARP):
+        cl.append(f"    case {w}: {{")
+        for L in range(nlev):
+            cl += ["      " + t for t in sched[L][w]]
+            if L + 1 < nlev:
+                cl.append("      XB_QD_BAR();")
+        cl += ["      break;", "    }"]
+    for L in range(nlev):
+        print(f"level {L}: {sum(len(x) for x in sched[L])} statements, max warp cost {max(loadw[L])}", file=sys.stderr)
+    cl += ["    default: break;", "  }", "}"]
+    (out / "qd_poly_levels.cuh").write_text("\n".join(cl) + "\n")
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@
 #include <cstdlib>
 #include "xb_kernels.h"
 #include "qd_poly.cuh"
-#include "qd_poly_parts.cuh"
+#include "qd_poly_levels.cuh"
 
 namespace xb {
 
@@ -95,14 +95,14 @@ __device__ __noinline__ void state_transition_call(double dt, const double* w, c
 // One CTA per step.  The only true dependency between steps is the q / v / p recurrence (a few hundred cycles per step
 // once its operands sit in shared memory), so CTA k simply redoes that recurrence from the start slot up to its own
 // step -- no grid-wide dependency -- and then spends its warps on what is expensive: F_d on one warp and the Q_d
-// polynomial split over XB_QD_NPART warps.  Round 1 evaluated the polynomial of every step on ONE thread each
+// polynomial level by level over XB_QD_NWARP warps.  Round 1 evaluated the polynomial of every step on ONE thread each
 // (47 us for 10 steps, the longest item next to the covariance downdate).
-__global__ void __launch_bounds__(256) k_prop_means(double* __restrict__ xv, int LX, int NS, int start, int n_steps,
+__global__ void __launch_bounds__(512) k_prop_means(double* __restrict__ xv, int LX, int NS, int start, int n_steps,
                                                     ImuSample in, PropParams pp, double* __restrict__ FQ) {
   __shared__ double imu[129][8];  // slots start .. start + k: w_m[3], a_m[3], time
   __shared__ double Dm[128][16];  // quaternion-integrator matrices of the steps 1 .. k
-  __shared__ double wsc[8][80];   // per-warp scratch of the integrator: O1, O0, A, Ak, Tm4
-  __shared__ double x0s[32], x1s[32], w1s[3], a1s[3], Cs[9], dts[1], Fs[225], Qs[225];
+  __shared__ double wsc[16][80];  // per-warp scratch of the integrator: O1, O0, A, Ak, Tm4
+  __shared__ double x0s[32], x1s[32], w1s[3], a1s[3], Cs[9], dts[1], Fs[225], Qs[225], Sq[XB_QD_NTEMP];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int k = blockIdx.x + 1;  // this CTA produces slot start + k
   const double* x0 = xv + (size_t)start * LX;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_prop_means(double* __restrict__ xv, int
   }
   // quaternionIntegrator (propagator.cpp:74-98) of the steps 1..k: one warp per step, element (r, c) per lane, same
   // operation order as quat_integrator()
-  for (int j = warp + 1; j <= k; j += 8) {
+  for (int j = warp + 1; j <= k; j += 16) {
     double* O1 = wsc[warp];
     double* O0 = O1 + 16;
     double* A = O1 + 32;
@@ -228,11 +228,14 @@ __global__ void __launch_bounds__(256) k_prop_means(double* __restrict__ xv, int
     for (int e = 0; e < 9; ++e) Cs[e] = R0[e];
   }
   __syncthreads();
-  // F_d on warp 0, the Q_d partitions on warps 1..XB_QD_NPART (one lane each: the polynomial is a scalar DAG)
-  if (lane == 0) {
-    if (warp == 0) state_transition_call(dts[0], w1s, a1s, &x1s[XV_Q], Fs);
-    else if (warp <= XB_QD_NPART) xb_qd_poly_part(warp - 1, dts[0], Cs, w1s, a1s, pp.n_w, pp.n_bw, pp.n_a, pp.n_ba, Qs);
+  // F_d on warp 0 (one lane); the Q_d polynomial on warps 1..XB_QD_NWARP, each executing its statements of every
+  // dependency level with a named barrier among those warps between levels (qd_poly_levels.cuh)
+  if (warp == 0) {
+    if (lane == 0) state_transition_call(dts[0], w1s, a1s, &x1s[XV_Q], Fs);
+  } else if (warp <= XB_QD_NWARP) {
+    xb_qd_poly_warp(warp - 1, dts[0], Cs, w1s, a1s, pp.n_w, pp.n_bw, pp.n_a, pp.n_ba, Sq, Qs);
   }
+  __syncthreads();
   // estimates of slot start + k (window and feature arrays: State::setStaticStatesFrom)
   if (t >= 32 && t < 64) xk[t - 32] = x1s[t - 32];
   for (int e = XV_ARR + t; e < LX; e += blockDim.x) xk[e] = x0[e];
@@ -341,14 +344,14 @@ __device__ __noinline__ void state_transition_call(double dt, const double* w, c
 
 // ---- one IMU step in ONE launch (Ekf::processImu, ekf.cpp:66-140: hot loop #1) -------------------------------------
 // Every CTA recomputes the step's small quantities itself -- quaternion integrator across 16 lanes, the q/v/p update,
-// F_d on one warp and the Q_d polynomial split over XB_QD_NPART warps (qd_poly_parts.cuh) -- and then propagates its
-// 256 columns of the covariance strip(s); CTA 0 also writes the estimates of the new slot.  No grid-wide dependency,
+// F_d on one warp and (CTA 0) the Q_d polynomial level by level over XB_QD_NWARP warps (qd_poly_levels.cuh) -- and then
+// propagates its 512 columns of the covariance strip(s); CTA 0 also writes the estimates of the new slot.  No grid-wide dependency,
 // so means and strips need no second launch, and the serial Q_d evaluation (the whole cost of the two-kernel form on a
 // single sample) is cut to its longest partition.
-__global__ void __launch_bounds__(256) k_prop_step(double* __restrict__ xv, int LX, double* __restrict__ strip, int N, int NS,
+__global__ void __launch_bounds__(512) k_prop_step(double* __restrict__ xv, int LX, double* __restrict__ strip, int N, int NS,
                                                    int start, ImuSample in, PropParams pp, double* __restrict__ FQ) {
   __shared__ double x0s[32], x1s[32], O1[16], O0[16], A[16], Ak[16], Tm4[16], Dm[16], w1s[3], a1s[3], Cs[9];
-  __shared__ double Fs[225], Qs[225], Pii[225], Tm[225];
+  __shared__ double Fs[225], Qs[225], Pii[225], Tm[225], Sq[XB_QD_NTEMP];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const double* x0 = xv + (size_t)start * LX;
   double* x1 = xv + (size_t)((start + 1) % NS) * LX;
@@ -453,16 +456,19 @@ __global__ void __launch_bounds__(256) k_prop_step(double* __restrict__ xv, int 
   }
   __syncthreads();
   PCK(2)
-  // F_d on warp 0, the Q_d partitions on warps 1..XB_QD_NPART (one lane each: the polynomial is a scalar DAG)
-  if (lane == 0) {
-    if (warp == 0) state_transition_call(dt, w1s, a1s, &x1s[XV_Q], Fs);
-    else if (warp <= XB_QD_NPART) xb_qd_poly_part(warp - 1, dt, Cs, w1s, a1s, pp.n_w, pp.n_bw, pp.n_a, pp.n_ba, Qs);
+  // F_d on warp 0 (one lane); CTA 0 (the only one that needs Q_d: it owns the core block) evaluates the polynomial on warps
+  // 1..XB_QD_NWARP, each executing its statements of every dependency level with a named barrier among those warps between
+  // levels (qd_poly_levels.cuh); the strip CTAs go straight to their columns
+  if (warp == 0) {
+    if (lane == 0) state_transition_call(dt, w1s, a1s, &x1s[XV_Q], Fs);
+  } else if (blockIdx.x == 0 && warp <= XB_QD_NWARP) {
+    xb_qd_poly_warp(warp - 1, dt, Cs, w1s, a1s, pp.n_w, pp.n_bw, pp.n_a, pp.n_ba, Sq, Qs);
   }
   __syncthreads();
   PCK(3)
   // strip columns of this thread: P_iv' = F P_iv (propagator.cpp:197); compact loops (the kernel runs once per launch on
   // cold instruction caches: code size is latency)
-  // CTA 0: core block + estimates; CTAs 1..: 256 strip columns each (they run side by side on different SMs)
+  // CTA 0: core block + estimates; CTAs 1..: 512 strip columns each (they run side by side on different SMs)
   const bool core_block = blockIdx.x == 0;
   const int j = XB_CORE + ((int)blockIdx.x - 1) * (int)blockDim.x + t;
   const size_t SS = (size_t)15 * N;
@@ -514,14 +520,14 @@ __global__ void __launch_bounds__(256) k_prop_step(double* __restrict__ xv, int 
 
 void launch_prop_step(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, const ImuSample& in,
                       const PropParams& pp, double* FQ) {
-  k_prop_step<<<1 + (N - XB_CORE + 255) / 256, 256, 0, s>>>(xv, LX, strip, N, NS, start, in, pp, FQ);
+  k_prop_step<<<1 + (N - XB_CORE + 511) / 512, 512, 0, s>>>(xv, LX, strip, N, NS, start, in, pp, FQ);
   count_launch();
 }
 
 void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,
                        const PropParams& pp, double* FQ) {
   if (n_steps <= 0) return;
-  k_prop_means<<<n_steps, 256, 0, s>>>(xv, LX, NS, start, n_steps, in, pp, FQ);
+  k_prop_means<<<n_steps, 512, 0, s>>>(xv, LX, NS, start, n_steps, in, pp, FQ);
   count_launch();
 }
 void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ, int second) {
