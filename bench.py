@@ -646,6 +646,49 @@ def main():
                                   "device's own prior: " + desc,
                         "seconds_per_update": round(sec_all, 3),
                         "one_core": {"value": 1.0 / sec_one, "seconds_per_update": round(sec_one, 3), "cores": 1}}
+        # the STRUCTURED formulation (what the device computes) on the same host cores: vectorised numpy
+        # + its BLAS/LAPACK (oracle/structured.py), from the post-manage state of the same update; splits the GPU-vs-reference
+        # ratio into "algorithm" (reference C++ / this) and "hardware + implementation" (this / GPU)
+        try:
+            from oracle.structured import structured_update
+            from oracle.updates import chi2_quantile
+            meas = more[0][1]
+            flt.work_set(prior)
+            flt.set_measurement(meas)
+            flt.manage(meas.lost_slam_trk_idxs)
+            st = flt.work_get()
+            Z = np.array([np.asarray(t_) for t_ in meas.msckf_trks])
+            slam_obs = np.array([np.asarray(t_)[-1] for t_ in meas.slam_trks])
+            slam_len = np.array([len(t_) for t_ in meas.slam_trks])
+            chi95 = np.array([0.0] + [chi2_quantile(0.95, d) for d in range(1, 2 * CFG2["M"] + 1)])
+            chi90 = np.array([0.0] + [chi2_quantile(0.90, d) for d in range(1, 2 * CFG2["M"] + 4)])
+            args_s = (st.p_array, st.q_array, st.f_array, list(flt.anchor_idxs), st.cov, Z, slam_obs, slam_len, flt.n_poses,
+                      CFG2["M"], CFG2["F"], scn.c.sigma_img, chi95, chi90)
+            structured_update(*args_s)                      # warm-up (BLAS threads, page faults)
+            t0 = time.perf_counter()
+            d_cpu, info = structured_update(*args_s)
+            sec_s = time.perf_counter() - t0
+            flt.reset_correction()                          # Updater::update starts from a zero correction_total (updater.cpp:44)
+            flt.construct_update(0)
+            flt.apply_constructed()
+            d_dev = flt.debug("delta", 15 + 6 * CFG2["M"] + 3 * CFG2["F"])
+            # same gates on both sides for the comparison of the correction (the device gates with the exact unsymmetrised
+            # covariance, this leg with sym(P): a handful of borderline tracks can differ)
+            masks = (flt.debug_int("inlier0", CFG2["K"]) != 0, flt.debug_int("slam_inlier", CFG2["F"]) != 0)
+            d_cpu, info_f = structured_update(*args_s, force_inliers=masks)
+            info["gates_equal_to_device"] = bool(np.array_equal(info["inlier"], masks[0]) and np.array_equal(info["slam_inlier"], masks[1]))
+            cpu_baseline["structured"] = {
+                "value": 1.0 / sec_s, "unit": UNIT, "seconds_per_update": round(sec_s, 4), "cores": threads,
+                "what": "the device's structured formulation (projector gate, Gram compression, sparse SLAM rows, Cholesky "
+                        "update) as vectorised numpy + OpenBLAS/LAPACK on the host, stages after StateManager::manage "
+                        "(oracle/structured.py; equals the dense formulation: tests/test_structured_cpu.py)",
+                "stage_seconds": {k_: round(v_, 4) for k_, v_ in info["seconds"].items()},
+                "state_correction_rel_diff_vs_device": float(np.linalg.norm(d_cpu - d_dev) / np.linalg.norm(d_dev)),
+                "msckf_inliers": int(info["inlier"].sum()), "gates_equal_to_device": info["gates_equal_to_device"],
+                "compressed_rows": int(info["rows"]),
+                "algorithm_factor_vs_reference_all_cores": round(sec_all / sec_s, 1)}
+        except Exception as exc:   # the structured leg is an explanation, never a reason to lose the bench line
+            cpu_baseline["structured"] = {"error": repr(exc)[:300]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
