@@ -453,3 +453,16 @@ def test_oc_projection_as_written_breaks_consistency():
     assert as_written[-1, 0] > 1.0 and as_written[-1, 0] > 3.0 * as_written[-1, 1]
     assert np.all(plain[10:, 0] < 3.0 * plain[10:, 1]) and plain[-1, 0] < 0.5
     assert plain[40:, 2].mean() > 0.9
+
+
+def test_vio_params_from_yaml(tmp_path):
+    """VIO::loadParamsFromYaml (vio.cpp:576-707): the reference's keys, OpenCV's %YAML directive skipped, defaults kept."""
+    from x_multi_agent_b200.vio import load_params_from_yaml
+    f = tmp_path / "params.yaml"
+    f.write_text("%YAML:1.0\nn_poses_max: 12\nsigma_img: 0.004\ncam1_q_ic: [0.0, 1.0, 0.0, 0.0]\np: [1.0, 2.0, 3.0]\n")
+    p = load_params_from_yaml(f)
+    assert p["n_poses_max"] == 12 and p["sigma_img"] == 0.004 and p["p"] == [1.0, 2.0, 3.0] and p["n_slam_features_max"] == 15
+    f.write_text("p: [1.0, 2.0]\n")
+    import pytest
+    with pytest.raises(ValueError):
+        load_params_from_yaml(f)

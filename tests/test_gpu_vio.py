@@ -1,0 +1,131 @@
+"""End to end from feature MATCHES (SURVEY 8 rows f-1 / f-2 in front of the hot path): x_multi_agent_b200.VIO
+(YAML-style parameters -> camera + track manager on the host -> device filter) against the same pipeline assembled from
+the oracle pieces (oracle.track_manager + the fp64 oracle filter), on one synthetic stream of 10-double match vectors
+(VIO::importMatches format, vio.cpp:372-434) and IMU samples."""
+import numpy as np
+import pytest
+
+from x_multi_agent_b200.synth import Scenario, SynthConfig
+
+pytestmark = pytest.mark.gpu
+
+NL = 700   # landmarks on the ground patch under the trajectory
+PARAMS = dict(cam1_fx=0.46, cam1_fy=0.61, cam1_cx=0.5, cam1_cy=0.5, cam1_s=0.0, cam1_img_width=640, cam1_img_height=480,
+              sigma_img=0.6 / 294.4, n_tiles_h=2, n_tiles_w=2, msckf_baseline=12.0, min_track_length=5, rho_0=0.3, sigma_rho_0=0.3,
+              iekf_iter=1, n_poses_max=8, n_slam_features_max=6, state_buffer_size=120,
+              sigma_dp=[0.1, 0.1, 0.1], sigma_dv=[0.1, 0.1, 0.1], sigma_dtheta=[2, 2, 2], sigma_dbw=[0.5, 0.5, 0.5],
+              sigma_dba=[0.05, 0.05, 0.05], n_w=0.0083, n_bw=0.00083, n_a=0.0013, n_ba=0.00013)   # the scenario's IMU
+
+
+def _stream(seed, frames):
+    """IMU samples and match vectors of a camera looking down at a patch of landmarks."""
+    scn = Scenario(SynthConfig(M=8, F=6, K=0, seed=seed, height=4.0))
+    rng = np.random.default_rng(seed + 7)
+    lms = np.column_stack([rng.uniform(-8, 8, NL), rng.uniform(-6, 6, NL), rng.uniform(-0.6, 0.6, NL)])
+    fx, fy, cx, cy = 0.46 * 640, 0.61 * 480, 320.0, 240.0
+    last_px = {}
+    events = []
+    fed = 0
+    for k in range(frames):
+        upto = k * scn.c.imu_per_frame + scn.c.latency_imu
+        for i in range(fed + 1, upto + 1):
+            t = i * scn.dt_imu
+            events.append(("imu", t, i, *scn.imu_sample(t)))
+        fed = max(fed, upto)
+        tk = scn.frame_time(k)
+        pc, Rc = scn.cam_pose(tk)
+        x = (lms - pc) @ Rc
+        px = np.column_stack([x[:, 0] / x[:, 2] * fx + cx, x[:, 1] / x[:, 2] * fy + cy]) + rng.normal(0, 0.3, (len(lms), 2))
+        vis = (x[:, 2] > 1.0) & (px[:, 0] > 8) & (px[:, 0] < 632) & (px[:, 1] > 8) & (px[:, 1] < 472) & (rng.random(len(lms)) > 0.03)
+        rows = []
+        cur = {}
+        for j in np.flatnonzero(vis):
+            cur[j] = px[j]
+            if j in last_px:
+                rows.append([0, scn.frame_time(k - 1), *last_px[j], tk, *px[j], 0, 0, 0])
+        last_px = cur
+        order = rng.permutation(len(rows))
+        events.append(("matches", tk, k, np.array(rows, dtype=float).reshape(-1, 10)[order]))
+    return scn, events
+
+
+class _OracleVIO:
+    """The same facade assembled from the oracle pieces (test infrastructure)."""
+
+    def __init__(self, vio):
+        from oracle.track_manager import TrackManagerOracle
+        from oracle_driver import OracleFilter
+        import oracle
+        p = vio.params
+        self.p = p
+        bx = p["msckf_baseline"] / (p["cam1_img_width"] * p["cam1_fx"])
+        by = p["msckf_baseline"] / (p["cam1_img_height"] * p["cam1_fy"])
+        self.tm = TrackManagerOracle(p["cam1_fx"], p["cam1_fy"], p["cam1_cx"], p["cam1_cy"], p["cam1_s"], p["cam1_img_width"],
+                                     p["cam1_img_height"], bx, by, p["n_tiles_h"], p["n_tiles_w"])
+        noise = oracle.ImuNoise()
+        noise.n_w, noise.n_bw, noise.n_a, noise.n_ba = p["n_w"], p["n_bw"], p["n_a"], p["n_ba"]
+        self.f = OracleFilter(p["n_poses_max"], p["n_slam_features_max"], sigma_img=p["sigma_img"], rho_0=p["rho_0"],
+                              sigma_rho_0=p["sigma_rho_0"], iekf_iter=p["iekf_iter"], n_slots=p["state_buffer_size"],
+                              g=tuple(p["g"]), noise=noise)
+        self.vio = vio
+
+    def process_matches(self, t, mv):
+        from x_multi_agent_b200.filter import Measurement
+        p, ekf = self.p, self.f.ekf
+        n_poses = self.f.upd.sm.n_poses
+        if n_poses == 0:
+            mv = mv[:0]
+        idx = ekf.buf.closest_idx(t)
+        s = ekf.buf.states[idx]
+        M = p["n_poses_max"]
+        qa = np.asarray(s.q_array).reshape(M, 4)[:n_poses]
+        size_out = min(M - 1, n_poses)
+        from x_multi_agent_b200.vio import _qmul
+        rots = np.vstack([qa[n_poses - size_out:], _qmul(s.q / np.linalg.norm(s.q), s.q_ic / np.linalg.norm(s.q_ic))[None]])
+        self.tm.manage_tracks(mv, rots, M, p["n_slam_features_max"], p["min_track_length"])
+
+        def tl(which, so=0):
+            off, xy = self.tm.get_list(which, so)
+            return [xy[off[i]:off[i + 1]].copy() for i in range(len(off) - 1)]
+        self.f.set_measurement(Measurement(t, tl(4, M), tl(0), tl(1), tl(2), tl(3), [int(i) for i in self.tm.lost]))
+        return self.f.process_update_measurement()
+
+
+def test_vio_facade_from_match_vectors_matches_the_oracle_pipeline():
+    from x_multi_agent_b200 import VIO
+    from test_gpu_parity import Report, compare_state
+    scn, events = _stream(11, 40)
+    vio = VIO()
+    params = dict(PARAMS)
+    s0 = scn.initial_state()
+    params.update(p=list(s0.p), v=list(s0.v), q=[s0.q[3], s0.q[0], s0.q[1], s0.q[2]], b_w=list(s0.b_w), b_a=list(s0.b_a),
+                  cam1_p_ic=list(scn.p_ic), cam1_q_ic=[scn.q_ic[3], scn.q_ic[0], scn.q_ic[1], scn.q_ic[2]])
+    vio.set_up(params, max_tracks=256)
+    vio.init_at_time(0.0)
+    ora = _OracleVIO(vio)
+    ora.f.initialize_from_state(vio.initial_state(0.0))
+    n_upd, n_msckf, n_feat = 0, 0, 0
+    rp = Report()
+    last_d = last_o = None
+    for ev in events:
+        if ev[0] == "imu":
+            vio.process_imu(*ev[1:])
+            ora.f.process_imu(*ev[1:])
+        else:
+            _, t, k, mv = ev
+            d = vio.process_matches_measurement(t, k, mv)
+            o = ora.process_matches(t, mv)
+            assert (d is None) == (o is None)
+            if d is not None:
+                n_upd += 1
+                last_d, last_o = d, o
+                n_msckf += len(vio.track_manager.get_list(0)[0]) - 1
+                n_feat = vio.filter.n_features
+    assert n_upd >= 35 and n_msckf > 20 and n_feat == params["n_slam_features_max"], (n_upd, n_msckf, n_feat)
+    compare_state(rp, "last update", last_d, last_o, params["n_poses_max"], params["n_slam_features_max"], tol_scale=100.0,
+                  cov=False)
+    rp.done()
+    # the estimate follows the truth (sanity of the whole chain, not a parity statement)
+    p_true = scn.pose(events[-1][1])[0]
+    assert np.linalg.norm(last_d.p - p_true) < 0.5
+    vio.close()

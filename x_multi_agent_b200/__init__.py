@@ -9,3 +9,4 @@ VioUpdater::preProcess seam).  There is no CPU fallback.
 from .filter import Filter, Measurement, PackedMeasurement, PeerState, State  # noqa: F401
 from .lib import LIB_PATH, XbError, load  # noqa: F401
 from .track_manager import TrackManager  # noqa: F401
+from .vio import VIO, load_params_from_yaml  # noqa: F401

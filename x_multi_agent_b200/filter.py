@@ -377,6 +377,21 @@ class Filter:
     def updater_update(self):
         L.check(self.lib.xb_updater_update(self.h))
 
+    def update_begin(self, timestamp):
+        """First half of Ekf::processUpdateMeasurement (ekf.cpp:183-199): the buffered state closest to `timestamp` becomes
+        the work state and is returned (None = std::nullopt)."""
+        out = np.empty(self.LX)
+        rc = L.check(self.lib.xb_ekf_update_begin(self.h, float(timestamp), L.dptr(out)))
+        return State(self.M, self.F, out) if rc else None
+
+    def update_end(self, want_state=True):
+        """Second half (ekf.cpp:200-211): write-back and re-propagation; returns the updated state."""
+        out = np.empty(self.LX) if want_state else None
+        rc = L.check(self.lib.xb_ekf_update_end(self.h, L.dptr(out)))
+        if rc == 0:
+            return None
+        return State(self.M, self.F, out) if want_state else True
+
     def debug(self, name, count):
         out = np.zeros(int(count))
         n = L.check(self.lib.xb_debug_read(self.h, name.encode(), L.dptr(out), int(count)))
