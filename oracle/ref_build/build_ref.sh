@@ -47,7 +47,8 @@ build_flavour() {  # name, extra flags, extra TUs
     local o="$dir/$(echo "$tu" | tr / _).o"
     objs="$objs $o"
     if [ ! -f "$o" ] || [ "$REF/src/x/$tu.cpp" -nt "$o" ] || [ "$HERE/shim/Eigen/Core" -nt "$o" ] \
-       || [ "$HERE/shim/opencv2/xref_cv.hpp" -nt "$o" ] || [ "$HERE/build_ref.sh" -nt "$o" ]; then
+       || [ "$HERE/shim/opencv2/xref_cv.hpp" -nt "$o" ] || [ "$HERE/build_ref.sh" -nt "$o" ] \
+       || [ "$HERE/shim_stubs/x/vio/track_manager.h" -nt "$o" ] || [ "$HERE/shim_stubs/x/vision/tracker.h" -nt "$o" ]; then
       g++ $COMMON $flags -c "$REF/src/x/$tu.cpp" -o "$o" &
       pids="$pids $!"
     fi

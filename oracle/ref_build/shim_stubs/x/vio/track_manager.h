@@ -16,6 +16,7 @@ class TrackManager {
   struct Lists {
     TrackList slam, msckf, msckf_short, new_slam_std, new_slam_msckf, opp;
     std::vector<unsigned int> lost;
+    std::vector<int> tri;  // the facet featureTriangleAtPoint() reports (3 SLAM feature ids, or empty)
   };
   std::shared_ptr<Lists> lists = std::make_shared<Lists>();  // shared by the copy VioUpdater keeps
 
@@ -29,7 +30,7 @@ class TrackManager {
   void clear() { *lists = Lists(); }
   std::vector<unsigned int> getLostSlamTrackIndexes() const { return lists->lost; }
   void manageTracks(MatchList&, const AttitudeList, const size_t, const size_t, const size_t, TiledImage&) {}
-  std::vector<int> featureTriangleAtPoint(const Feature&, TiledImage&) const { return {}; }
+  std::vector<int> featureTriangleAtPoint(const Feature&, TiledImage&) const { return lists->tri; }
 };
 }  // namespace x
 #endif

@@ -42,6 +42,8 @@
 #include "x/ekf/ekf.h"
 #include "x/vio/msckf_update.h"
 #include "x/vio/vio_updater.h"
+#include "x/vio/range_update.h"
+#include "x/vio/solar_update.h"
 #undef private
 #undef protected
 
@@ -229,6 +231,24 @@ int xref_set_measurement(void* h, double ts, const int* n, const int* const* off
   return 0;
 }
 
+// VioMeasurement::range / sun_angle (include/x/vio/types.h:223-254, 300-305) of the measurement set by the last
+// xref_set_measurement, and the facet TrackManager::featureTriangleAtPoint reports for the LRF beam (vio_updater.cpp:
+// 365-366; the Delaunay lookup itself is front-end code).  range_ts <= 0.1 / sun_ts <= -1 leave the sensor unused.
+int xref_set_sensors(void* h, double range_ts, double range, double img_x_n, double img_y_n, const int* tri, int n_tri,
+                     double sun_ts, double sun_x, double sun_y) {
+  VIO& v = *static_cast<VIO*>(h);
+  VioMeasurement& m = v.updater.measurement_;
+  m.range.timestamp = range_ts;
+  m.range.range = range;
+  m.range.img_pt_n.setX(img_x_n);
+  m.range.img_pt_n.setY(img_y_n);
+  v.lists().tri.assign(tri, tri + n_tri);
+  m.sun_angle.timestamp = sun_ts;
+  m.sun_angle.x_angle = sun_x;
+  m.sun_angle.y_angle = sun_y;
+  return 0;
+}
+
 // Ekf::processUpdateMeasurement; returns 1 and the updated state, 0 for std::nullopt.  seconds (optional) receives
 // the wall time of the call.
 int xref_process_update(void* h, double* xvec_out, double* seconds) {
@@ -390,6 +410,66 @@ int xref_msckf_rows(void* h, const double* xvec, const double* cov_rm, double ts
   for (int i = 0; i < rows; ++i) {
     for (int j = 0; j < N; ++j) jac_rm[size_t(i) * N + j] = J(i, j);
     res[i] = r(i, 0);
+  }
+  return rows;
+#endif
+}
+
+// RangeUpdate (range_update.cpp:24-265) and SolarUpdate (solar_update.cpp:25-94) on a caller-provided state: the
+// Jacobian rows (1 x N, 2 x N), residuals and noise variances as the classes leave them.  sm bookkeeping (n_poses,
+// anchors) is the harness filter's own (xref_sm_set).
+int xref_sensor_rows(void* h, const double* xvec, const double* cov_rm, double range, double img_x_n, double img_y_n,
+                     const int* tri, double sun_x, double sun_y, double* jac_rm, double* res, double* r_diag) {
+  VIO& v = *static_cast<VIO*>(h);
+  const int N = 15 + 6 * v.M + 3 * v.F;
+  State s = state_from(xvec, cov_rm, v.M, v.F);
+  const TranslationList G_p_C = v.sm().convertCameraPositionsToList(s);
+  const AttitudeList C_q_G = v.sm().convertCameraAttitudesToList(s);
+  RangeMeasurement rm;
+  rm.timestamp = 1.0;
+  rm.range = range;
+  rm.img_pt_n.setX(img_x_n);
+  rm.img_pt_n.setY(img_y_n);
+  const std::vector<int> ids(tri, tri + 3);
+  const RangeUpdate ru(rm, ids, C_q_G, G_p_C, s.getFeatureArray(), v.sm().getAnchorIdxs(), s.getCovariance(),
+                       s.nPosesMax(), v.updater.sigma_range_);
+  SunAngleMeasurement sa;
+  sa.timestamp = 1.0;
+  sa.x_angle = sun_x;
+  sa.y_angle = sun_y;
+  const SolarUpdate su(sa, s.getOrientation(), s.getCovariance());
+  for (int j = 0; j < N; ++j) {
+    jac_rm[j] = ru.getJacobian()(0, j);
+    jac_rm[N + j] = su.getJacobian()(0, j);
+    jac_rm[2 * N + j] = su.getJacobian()(1, j);
+  }
+  res[0] = ru.getResidual()(0, 0), res[1] = su.getResidual()(0, 0), res[2] = su.getResidual()(1, 0);
+  r_diag[0] = ru.getCovDiag()(0), r_diag[1] = su.getCovDiag()(0), r_diag[2] = su.getCovDiag()(1);
+  return 0;
+}
+
+// VioUpdater::preProcess + constructUpdate (vio_updater.cpp:126-198, 266-423; single-UAV build) on a caller-provided
+// state AFTER StateManager::manage: the stacked (and, when rows > N + 1, QR-compressed) h, res and diag(R).
+int xref_construct_update(void* h, const double* xvec, const double* cov_rm, double* H_rm, double* res, double* r_diag,
+                          int max_rows) {
+#ifdef MULTI_UAV
+  (void)h, (void)xvec, (void)cov_rm, (void)H_rm, (void)res, (void)r_diag, (void)max_rows;
+  return -1;
+#else
+  VIO& v = *static_cast<VIO*>(h);
+  const int N = 15 + 6 * v.M + 3 * v.F;
+  State s = state_from(xvec, cov_rm, v.M, v.F);
+  const VioMeasurement keep = v.updater.measurement_;
+  v.updater.preProcess(s);
+  v.updater.measurement_ = keep;
+  Matrix H, r, R;
+  v.updater.constructUpdate(s, H, r, R);
+  const int rows = int(H.rows());
+  if (rows > max_rows) return -2;
+  for (int i = 0; i < rows; ++i) {
+    for (int j = 0; j < N; ++j) H_rm[size_t(i) * N + j] = H(i, j);
+    res[i] = r(i, 0);
+    r_diag[i] = R(i, i);
   }
   return rows;
 #endif

@@ -51,6 +51,12 @@ def load(flavour="single"):
     lib.xref_set_measurement.argtypes = [C.c_void_p, C.c_double, _ip, C.POINTER(_ip), C.POINTER(_dp), C.POINTER(_up),
                                          _ip, C.c_int]
     lib.xref_process_update.argtypes = [C.c_void_p, _dp, _dp]
+    lib.xref_sensor_rows.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double, _ip, C.c_double,
+                                     C.c_double, _dp, _dp, _dp]
+    lib.xref_construct_update.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_int]
+    if hasattr(lib, "xref_set_sensors"):
+        lib.xref_set_sensors.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, _ip, C.c_int,
+                                         C.c_double, C.c_double, C.c_double]
     lib.xref_get_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     lib.xref_sm_info.argtypes = [C.c_void_p, _ip, _ip, _ip]
     lib.xref_apply_update.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_int]
@@ -174,6 +180,17 @@ class RefFilter:
         self._keep = (n, csr, offs, obs, id_arrs, idp, lost)
         self.lib.xref_set_measurement(self.h, float(m.timestamp), n.ctypes.data_as(_ip), offs, obs, idp,
                                       lost.ctypes.data_as(_ip), len(lost))
+        rng, sun = getattr(m, "range", None), getattr(m, "sun_angle", None)
+        if rng is not None or sun is not None:  # VioMeasurement::range / sun_angle (vio/types.h:300-305)
+            tri = np.ascontiguousarray(list(rng.tr_feat_ids) if rng is not None else [], dtype=np.int32)
+            self.lib.xref_set_sensors(self.h, float(rng.timestamp) if rng is not None else -1.0,
+                                      float(rng.range) if rng is not None else 0.0,
+                                      float(rng.img_pt_n[0]) if rng is not None else 0.0,
+                                      float(rng.img_pt_n[1]) if rng is not None else 0.0,
+                                      tri.ctypes.data_as(_ip), len(tri),
+                                      float(sun.timestamp) if sun is not None else -1.0,
+                                      float(sun.x_angle) if sun is not None else 0.0,
+                                      float(sun.y_angle) if sun is not None else 0.0)
 
     def process_update_measurement(self, want_state=True):
         out = np.empty(self.LX)
@@ -255,6 +272,28 @@ class RefFilter:
         x1, c1 = np.empty(self.LX), np.empty((self.N, self.N))
         self.lib.xref_propagate(self.h, _d(x0), _d(c0), float(t1), _d(w), _d(a), _d(x1), _d(c1))
         return RefState(self.M, self.F, x1, c1)
+
+    def sensor_rows(self, xs, rng, sun):
+        """RangeUpdate (range_update.cpp:24-265) + SolarUpdate (solar_update.cpp:25-94) on `xs`: (jac 3 x N, res 3,
+        r_diag 3), row 0 the range row, rows 1-2 the sun-sensor rows."""
+        x = np.ascontiguousarray(xs.x, dtype=np.float64)
+        cov = np.ascontiguousarray(xs.cov, dtype=np.float64)
+        tri = np.ascontiguousarray(list(rng.tr_feat_ids), dtype=np.int32)
+        J, r, d = np.zeros((3, self.N)), np.zeros(3), np.zeros(3)
+        self.lib.xref_sensor_rows(self.h, _d(x), _d(cov), float(rng.range), float(rng.img_pt_n[0]), float(rng.img_pt_n[1]),
+                                  tri.ctypes.data_as(_ip), float(sun.x_angle), float(sun.y_angle), _d(J), _d(r), _d(d))
+        return J, r, d
+
+    def construct_update(self, xs, max_rows=4096):
+        """VioUpdater::constructUpdate (vio_updater.cpp:266-423, single-UAV build) for the measurement set with
+        set_measurement() on the post-manage state `xs`: (h, res, diag R)."""
+        x = np.ascontiguousarray(xs.x, dtype=np.float64)
+        cov = np.ascontiguousarray(xs.cov, dtype=np.float64)
+        H, r, d = np.zeros((max_rows, self.N)), np.zeros(max_rows), np.zeros(max_rows)
+        rows = self.lib.xref_construct_update(self.h, _d(x), _d(cov), _d(H), _d(r), _d(d), max_rows)
+        if rows < 0:
+            raise RuntimeError(f"xref_construct_update failed ({rows})")
+        return H[:rows].copy(), r[:rows].copy(), d[:rows].copy()
 
     def msckf_rows(self, xs, tracks, timestamp=0.0):
         """MsckfUpdate (msckf_update.cpp:27-63) on `xs`: stacked inlier Jacobian rows and residual."""

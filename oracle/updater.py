@@ -8,6 +8,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from .sensors import RangeMeasurement, RangeUpdate, SolarUpdate, SunAngleMeasurement
 from .state_manager import StateManager
 from .updates import MsckfSlamUpdate, MsckfUpdate, SlamUpdate
 
@@ -63,14 +64,17 @@ class VisualMeasurement:
     new_slam_std_trks: list = field(default_factory=list)
     new_msckf_slam_trks: list = field(default_factory=list)
     lost_slam_trk_idxs: list = field(default_factory=list)
+    range: RangeMeasurement = field(default_factory=RangeMeasurement)      # VioMeasurement::range (vio/types.h:300)
+    sun_angle: SunAngleMeasurement = field(default_factory=SunAngleMeasurement)  # VioMeasurement::sun_angle (:305)
 
 
 class VioUpdaterOracle:
     """Restates Updater::update (updater.cpp:39-115, single-UAV build) with VioUpdater's overrides."""
 
     def __init__(self, n_poses_max, n_features_max, sigma_img, rho_0=0.5, sigma_rho_0=0.25, iekf_iter=1,
-                 ci_msckf_w=0.1):
+                 ci_msckf_w=0.1, sigma_range=0.05):
         self.ci_msckf_w = ci_msckf_w
+        self.sigma_range = sigma_range
         self.msckf_matches = []  # VioUpdater::msckf_matches_ (vio_updater.h:282), consumed by the constructors
         self.sm = StateManager(n_poses_max, n_features_max)
         self.sigma_img = sigma_img
@@ -94,7 +98,28 @@ class VioUpdaterOracle:
         self.last["short"] = msckf
         return apply_qr_decomposition(msckf.jac, msckf.res, msckf.cov_m_diag, self.sigma_img)
 
-    # vio_updater.cpp:266-423 (range / sun-sensor rows out of scope: absent from every BASELINE config)
+    # vio_updater.cpp:352-403: the range row (one, gated) and the two sun-sensor rows; each measurement is used once
+    def _sensor_rows(self, state, quats, poss):
+        P = state.cov
+        cols = P.shape[1]
+        h_l, res_l, r_l = np.zeros((0, cols)), np.zeros(0), np.zeros(0)
+        rng, sun = self.meas.range, self.meas.sun_angle
+        self.last.pop("range", None)
+        self.last.pop("solar", None)
+        if rng.timestamp > 0.1 and self.meas.slam_trks and len(rng.tr_feat_ids) > 0:
+            ru = RangeUpdate(rng, quats, poss, state.f_array, self.sm.anchor_idxs, P, state.n_poses_max(), self.sigma_range)
+            self.last["range"] = ru
+            h_l, res_l, r_l = ru.jac, ru.res, ru.cov_m_diag
+            rng.timestamp = -1.0
+        h_s, res_s, r_s = np.zeros((0, cols)), np.zeros(0), np.zeros(0)
+        if sun.timestamp > -1:
+            su = SolarUpdate(sun, state.q, cols)
+            self.last["solar"] = su
+            h_s, res_s, r_s = su.jac, su.res, su.cov_m_diag
+            sun.timestamp = -1.0
+        return np.vstack([h_l, h_s]), np.concatenate([res_l, res_s]), np.concatenate([r_l, r_s])
+
+    # vio_updater.cpp:266-423
     def construct_update(self, state):
         quats = self.sm.camera_attitudes(state)
         poss = self.sm.camera_positions(state)
@@ -104,9 +129,10 @@ class VioUpdaterOracle:
         msckf_slam = MsckfSlamUpdate(self.meas.new_msckf_slam_trks, quats, poss, P, M, self.sigma_img)
         slam = SlamUpdate(self.meas.slam_trks, quats, poss, state.f_array, self.sm.anchor_idxs, P, M, self.sigma_img)
         self.last.update(msckf=msckf, msckf_slam=msckf_slam, slam=slam)
-        h = np.vstack([msckf.jac, msckf_slam.jac, slam.jac])
-        r_diag = np.concatenate([msckf.cov_m_diag, msckf_slam.cov_m_diag, slam.cov_m_diag])
-        res = np.concatenate([msckf.res, msckf_slam.res, slam.res])
+        h_x, res_x, r_x = self._sensor_rows(state, quats, poss)
+        h = np.vstack([msckf.jac, msckf_slam.jac, slam.jac, h_x])
+        r_diag = np.concatenate([msckf.cov_m_diag, msckf_slam.cov_m_diag, slam.cov_m_diag, r_x])
+        res = np.concatenate([msckf.res, msckf_slam.res, slam.res, res_x])
         return apply_qr_decomposition(h, res, r_diag, self.sigma_img)
 
     # ---- MULTI_UAV build: vio_updater.cpp:217-264 / 266-423 with the four CI lists -------------------------
@@ -126,9 +152,10 @@ class VioUpdaterOracle:
         msckf_slam = MsckfSlamUpdate(self.meas.new_msckf_slam_trks, quats, poss, P, M, self.sigma_img)
         slam = SlamUpdate(self.meas.slam_trks, quats, poss, state.f_array, self.sm.anchor_idxs, P, M, self.sigma_img)
         self.last.update(msckf=msckf, msckf_slam=msckf_slam, slam=slam)
-        h = np.vstack([msckf.jac, msckf_slam.jac, slam.jac])
-        r_diag = np.concatenate([msckf.cov_m_diag, msckf_slam.cov_m_diag, slam.cov_m_diag])
-        res = np.concatenate([msckf.res, msckf_slam.res, slam.res])
+        h_x, res_x, r_x = self._sensor_rows(state, quats, poss)
+        h = np.vstack([msckf.jac, msckf_slam.jac, slam.jac, h_x])
+        r_diag = np.concatenate([msckf.cov_m_diag, msckf_slam.cov_m_diag, slam.cov_m_diag, r_x])
+        res = np.concatenate([msckf.res, msckf_slam.res, slam.res, res_x])
         return apply_qr_decomposition(h, res, r_diag, self.sigma_img), lists
 
     def update_multi_uav(self, state):

@@ -292,3 +292,51 @@ def test_slam_slam_ci_matches_compiled_reference():
     assert sum(info["inl"]) >= 3 and not info["inl"][-1]
     assert np.abs(oracle_xvec(so, cfg.M, cfg.F) - sr.x).max() < TOL_X
     assert _rel(ora0.newest().cov, ref0.newest().cov) < TOL_P
+
+
+# ---- range (laser range finder) and sun-sensor rows ---------------------------------------------------
+SENSOR_CASES = {
+    # rows <= N + 1: no QR compression, the sensor rows keep their own variances (vio_updater.cpp:405-419, 487-512)
+    "slam_only_no_qr": dict(M=5, F=6, K=0, seed=5, churn=1, range_every=1, sun_every=3),
+    # rows > N + 1: [H | r] is QR-compressed and EVERY row, the sensor rows included, is then weighted sigma_img^2
+    "msckf_slam_qr": dict(M=6, F=6, K=14, seed=11, n_short=2, churn=1, range_every=1, sun_every=2),
+}
+
+
+@need_ref
+@pytest.mark.parametrize("case", sorted(SENSOR_CASES))
+def test_range_and_sun_rows_match_compiled_reference(case):
+    """RangeUpdate (range_update.cpp:24-265) and SolarUpdate (solar_update.cpp:25-94) stacked by
+    VioUpdater::constructUpdate (vio_updater.cpp:352-403): oracle == the reference's own sources over a sequence."""
+    cfg = SynthConfig(**SENSOR_CASES[case])
+    ev = record(Scenario(cfg), 16)
+    n_range = sum(1 for e in ev if e[0] == "update" and e[1].range is not None)
+    n_sun = sum(1 for e in ev if e[0] == "update" and e[1].sun_angle is not None)
+    assert n_range >= 3 and n_sun >= 3
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64, sigma_range=cfg.sigma_range)
+    ref = refcpp.RefFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64, sigma_range=cfg.sigma_range)
+    xo, xr, gates = [], [], []
+
+    def on_oracle(k, m, st):
+        xo.append(oracle_xvec(st, cfg.M, cfg.F))
+        if "range" in ora.upd.last:
+            gates.append(ora.upd.last["range"].inlier)
+
+    replay(ev, ora, on_oracle)
+    replay(ev, ref, lambda k, m, st: xr.append(st.x.copy()))
+    assert any(gates), "no range row passed its gate: the case does not exercise the Jacobian"
+    # round-off only, but amplified in the QR case: there the 5 cm range row is weighted like a 1-pixel image row
+    # (R <- sigma_img^2 I, vio_updater.cpp:507-508), which makes the later updates ill-conditioned (1e-13 after the first
+    # range inlier, x10 per update afterwards -- in the reference binary and in the oracle alike)
+    tol = 1e-9 if case == "slam_only_no_qr" else 1e-6
+    d = np.abs(np.vstack(xo) - np.vstack(xr)).max(axis=1)
+    assert d[:10].max() < 1e-10 and d.max() < tol
+    assert _rel(ora.newest().cov, ref.newest().cov) < tol
+
+    # the sensors matter: the same sequence without them ends somewhere else
+    for e in ev:
+        if e[0] == "update":
+            e[1].range, e[1].sun_angle = None, None
+    ora0 = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64)
+    replay(ev, ora0)
+    assert np.abs(ora0.newest().p - ora.newest().p).max() > 1e-6

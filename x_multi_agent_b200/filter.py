@@ -68,6 +68,24 @@ class State:
 
 
 @dataclass
+class RangeMeasurement:
+    """x::RangeMeasurement (include/x/vio/types.h:223-243) + the SLAM-feature facet the LRF beam hits
+    (TrackManager::featureTriangleAtPoint, vio_updater.cpp:365-366).  Used when timestamp > 0.1."""
+    timestamp: float = -1.0
+    range: float = 0.0
+    img_pt_n: tuple = (0.0, 0.0)
+    tr_feat_ids: list = field(default_factory=list)
+
+
+@dataclass
+class SunAngleMeasurement:
+    """x::SunAngleMeasurement (include/x/vio/types.h:250-254); used when timestamp > -1."""
+    timestamp: float = -1.0
+    x_angle: float = 0.0
+    y_angle: float = 0.0
+
+
+@dataclass
 class Measurement:
     """Output of VioUpdater::preProcess (vio_updater.cpp:172-179); tracks are (L,2) arrays, oldest first."""
     timestamp: float = 0.0
@@ -77,6 +95,8 @@ class Measurement:
     new_slam_std_trks: list = field(default_factory=list)
     new_msckf_slam_trks: list = field(default_factory=list)
     lost_slam_trk_idxs: list = field(default_factory=list)
+    range: RangeMeasurement = None         # VioMeasurement::range (vio/types.h:300)
+    sun_angle: SunAngleMeasurement = None  # VioMeasurement::sun_angle (vio/types.h:305)
 
 
 @dataclass

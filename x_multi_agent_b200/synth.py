@@ -9,7 +9,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .filter import Measurement, State, K_CORE
+from .filter import Measurement, RangeMeasurement, State, SunAngleMeasurement, K_CORE
 
 
 def _rx(a):
@@ -76,6 +76,10 @@ class SynthConfig:
     n_a: float = 0.0013
     n_ba: float = 0.00013
     init_err_scale: float = 0.5  # initial estimation error = N(0,1) * sigma * init_err_scale (sigma = initial P)
+    range_every: int = 0        # > 0: a laser-range measurement on every range_every-th frame with >= 3 SLAM tracks
+    sigma_range: float = 0.05
+    sun_every: int = 0          # > 0: a sun-sensor measurement on every sun_every-th frame
+    sun_noise_deg: float = 1.0
 
 
 class Scenario:
@@ -266,7 +270,38 @@ class Scenario:
                 m.new_msckf_slam_trks = [z for _, z in new_ms]
                 m.new_slam_std_trks = [z for _, z in new_std]
                 assert n_std == len(new_std)
+        t = self.frame_time(k)
+        if c.range_every > 0 and k % c.range_every == 0 and len(m.slam_trks) >= 3 and t > 0.1:
+            m.range = self._range_measurement(k, len(m.slam_trks))
+        if c.sun_every > 0 and k % c.sun_every == 0:
+            m.sun_angle = self._sun_measurement(k)
         return m
+
+    # Laser range finder (range_update.cpp:61-139): the beam leaves the camera centre through the normalised image point
+    # `pt` and hits the facet spanned by three SLAM landmarks; range = ((f1 - p_c) . n) / (pt . R_c^T n).
+    def _range_measurement(self, k, n_tracked):
+        c = self.c
+        ids = sorted(self.rng.choice(n_tracked, 3, replace=False).tolist())  # slots initialised in earlier frames
+        f = [self.slam_lm[self.feat_lm[j]] for j in ids]
+        pc, Rc = self.cam_pose(self.frame_time(k))
+        z = np.array([(Rc.T @ (fj - pc))[:2] / (Rc.T @ (fj - pc))[2] for fj in f])
+        pt = np.array([*z.mean(axis=0), 1.0])
+        n = np.cross(f[0] - f[1], f[2] - f[1])
+        rng_true = float((f[1] - pc) @ n) / float(pt @ (Rc.T @ n))
+        return RangeMeasurement(timestamp=self.frame_time(k), range=rng_true + self.rng.normal(0, c.sigma_range),
+                                img_pt_n=(float(pt[0]), float(pt[1])), tr_feat_ids=ids)
+
+    # Sun sensor (solar_update.cpp:44-70): angles of the sun vector in the sensor frame, in degrees; the sensor
+    # orientation and the world-frame sun vector are the constants hard-coded there.
+    S_Q_I = np.array([-0.063338979194957, 0.007502445522018, 0.930635612981541, 0.360346005598587])  # (x,y,z,w)
+    G_SUN = np.array([-0.29385515271891938, -0.55080445540063927, 0.78119370269565391])
+
+    def _sun_measurement(self, k):
+        t = self.frame_time(k)
+        _, R, *_ = self.pose(t)
+        s = quat_to_rot(self.S_Q_I).T @ (R.T @ (self.G_SUN / np.linalg.norm(self.G_SUN)))
+        ang = np.degrees([np.arctan2(s[0], s[2]), np.arctan2(s[1], s[2])]) + self.rng.normal(0, self.c.sun_noise_deg, 2)
+        return SunAngleMeasurement(timestamp=t, x_angle=float(ang[0]), y_angle=float(ang[1]))
 
     def imu_between(self, k0, k1, extra=0):
         """IMU samples with timestamps in (t_k0, t_k1 + extra*dt_imu]: list of (t, seq, w_m, a_m)."""
