@@ -115,12 +115,29 @@ struct Translation {
 using AttitudeList = std::vector<Attitude>;
 using TranslationList = std::vector<Translation>;
 
-/** include/x/vio/types.h:264-324 without the image front end's members (matches, image, range, sun angle). */
+/** include/x/vio/types.h:223-243: laser range finder. */
+struct RangeMeasurement {
+  double timestamp{-1.0};   // kInvalid
+  double range{0.0};
+  Feature img_pt{Feature()};
+  Feature img_pt_n{Feature()};
+};
+/** include/x/vio/types.h:250-254: sun sensor. */
+struct SunAngleMeasurement {
+  double timestamp{-1.0};
+  double x_angle{0.0};
+  double y_angle{0.0};
+};
+/** include/x/vio/types.h:264-324 without the image front end's members (matches, image). */
 struct VioMeasurement {
   double timestamp{0};
   unsigned int seq{0};
+  RangeMeasurement range;
+  SunAngleMeasurement sun_angle;
   VioMeasurement() = default;
   VioMeasurement(const double& timestamp, const unsigned int seq) : timestamp{timestamp}, seq{seq} {}
+  VioMeasurement(const double& timestamp, const unsigned int seq, RangeMeasurement range, const SunAngleMeasurement& sun_angle)
+      : timestamp{timestamp}, seq{seq}, range{std::move(range)}, sun_angle{sun_angle} {}
 };
 
 /** x::SimpleState (include/x/ekf/simple_state.h:30-75): another agent's snapshot as it arrives from the network. */
@@ -434,7 +451,7 @@ class TrackManager {
     release();
     camera_ = o.camera_; min_baseline_x_n_ = o.min_baseline_x_n_; min_baseline_y_n_ = o.min_baseline_y_n_;
     slam_ = o.slam_; msckf_ = o.msckf_; short_ = o.short_; new_std_ = o.new_std_; new_msckf_ = o.new_msckf_; lost_ = o.lost_;
-    injected_ = o.injected_; tiles_h_ = o.tiles_h_; tiles_w_ = o.tiles_w_;
+    injected_ = o.injected_; tiles_h_ = o.tiles_h_; tiles_w_ = o.tiles_w_; facet_ = o.facet_;
     tm_ = o.tm_; refs_ = o.refs_;
     if (refs_) ++*refs_;
     return *this;
@@ -483,6 +500,16 @@ class TrackManager {
   TrackList getNewSlamStdTracks() const { return injected_ || !tm_ ? new_std_ : fetch(XB_TM_NEW_SLAM_STD, 0); }
   TrackList getNewSlamMsckfTracks() const { return injected_ || !tm_ ? new_msckf_ : fetch(XB_TM_NEW_SLAM_MSCKF, 0); }
   TrackList getOppTracks() const { return tm_ ? fetch(XB_TM_OPP, 0) : TrackList(); }
+  /** track_manager.cpp:443-560: the Delaunay facet of SLAM features around the LRF image point (distorted pixels).  With
+   *  injected track lists (setTracks) the facet is the one given to setFacet(). */
+  std::vector<int> featureTriangleAtPoint(const Feature& lrf_img_pt, TiledImage&) const {
+    if (injected_ || !tm_) return facet_;
+    int ids[3] = {0, 0, 0};
+    const int n = xb_tm_feature_triangle_at_point(tm_, lrf_img_pt.getXDist(), lrf_img_pt.getYDist(), ids);
+    detail_check(n);
+    return n == 3 ? std::vector<int>(ids, ids + 3) : std::vector<int>();
+  }
+  void setFacet(std::vector<int> ids) { facet_ = std::move(ids); }
   std::vector<unsigned int> getLostSlamTrackIndexes() const {
     if (injected_ || !tm_) return lost_;
     std::vector<int> tmp(static_cast<size_t>(std::max(1, xb_tm_lost_slam_idxs(tm_, nullptr, 0))));
@@ -524,6 +551,7 @@ class TrackManager {
   TrackList slam_, msckf_, short_, new_std_, new_msckf_;
   std::vector<unsigned int> lost_;
   bool injected_ = false;
+  std::vector<int> facet_;
   xb_track_manager* tm_ = nullptr;   // shared between copies (VioUpdater keeps a copy of the manager it is given)
   int* refs_ = nullptr;
   unsigned int tiles_h_ = 0, tiles_w_ = 0;
@@ -794,6 +822,28 @@ class VioUpdater : public Updater {
     m.n_lost = static_cast<int>(lost.size());
     m.lost_slam_idxs = lost.data();
     xb_throw(xb_vio_set_measurement(f, &m));
+    {  // range / sun-sensor measurements (vio_updater.cpp:352-403; the facet lookup uses the hard-coded image point of :360-363)
+      xb_range_measurement rm{};
+      xb_sun_angle_measurement sm{};
+      const bool with_range = measurement_.range.timestamp > 0.1 && !slam_trks_.empty();
+      if (with_range) {
+        Feature lrf_img_pt;
+        lrf_img_pt.setXDist(320.5);
+        lrf_img_pt.setYDist(240.5);
+        TiledImage img;
+        const std::vector<int> ids = track_manager_.featureTriangleAtPoint(lrf_img_pt, img);
+        rm.timestamp = measurement_.range.timestamp;
+        rm.range = measurement_.range.range;
+        rm.img_pt_n[0] = measurement_.range.img_pt_n.getX();
+        rm.img_pt_n[1] = measurement_.range.img_pt_n.getY();
+        rm.n_tr_feat_ids = static_cast<int>(ids.size());
+        for (size_t j = 0; j < ids.size() && j < 3; ++j) rm.tr_feat_ids[j] = ids[j];
+      }
+      sm.timestamp = measurement_.sun_angle.timestamp;
+      sm.x_angle = measurement_.sun_angle.x_angle;
+      sm.y_angle = measurement_.sun_angle.y_angle;
+      xb_throw(xb_vio_set_sensors(f, with_range ? &rm : nullptr, &sm));
+    }
     xb_throw(xb_updater_reset_correction(f));
 #ifdef MULTI_UAV
     std::vector<const SimpleState*> uniq;

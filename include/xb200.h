@@ -110,6 +110,23 @@ typedef struct xb_measurement {
   const int* lost_slam_idxs;     /* lost_slam_trk_idxs_ */
 } xb_measurement;
 
+/* RangeMeasurement (include/x/vio/types.h:223-243) + the facet of SLAM features its beam hits, as
+ * TrackManager::featureTriangleAtPoint reports it to VioUpdater::constructUpdate (src/x/vio/vio_updater.cpp:358-369).
+ * Used when timestamp > 0.1 and n_tr_feat_ids == 3 (0: no facet found -> no range row). */
+typedef struct xb_range_measurement {
+  double timestamp;
+  double range;          /* [m] */
+  double img_pt_n[2];    /* normalised image coordinates of the LRF beam */
+  int n_tr_feat_ids;
+  int tr_feat_ids[3];    /* indexes of the facet's SLAM features (slam_trks_ order) */
+} xb_range_measurement;
+
+/* SunAngleMeasurement (include/x/vio/types.h:250-254); used when timestamp > -1. */
+typedef struct xb_sun_angle_measurement {
+  double timestamp;
+  double x_angle, y_angle;  /* [deg] */
+} xb_sun_angle_measurement;
+
 /* Another agent's snapshot: SimpleState (include/x/ekf/simple_state.h:30-75) + the match lists of
  * include/x/vision/types.h:83-116.  cov is N_peer x N_peer (layout as given). */
 typedef struct xb_peer_state {
@@ -160,6 +177,12 @@ XB_API int xb_ekf_process_imu(xb_filter* f, double timestamp, unsigned seq, cons
  * buffer -- they must then stay unchanged until the update that uses them has completed (xb_synchronize or a returned
  * state); pageable buffers are staged through the library's pinned ring and may be reused at once. */
 XB_API int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m);
+/* VioMeasurement::range / sun_angle of the measurement set last (either may be NULL): the range row (RangeUpdate,
+ * src/x/vio/range_update.cpp:61-265) and the two sun-sensor rows (SolarUpdate, src/x/vio/solar_update.cpp:39-94) that
+ * VioUpdater::constructUpdate stacks under the visual rows (vio_updater.cpp:352-403).  Call after
+ * xb_vio_set_measurement (which, like VioUpdater::setMeasurement, replaces the whole measurement); each sensor
+ * measurement is used by one constructUpdate only (vio_updater.cpp:381, 402). */
+XB_API int xb_vio_set_sensors(xb_filter* f, const xb_range_measurement* range, const xb_sun_angle_measurement* sun);
 /* cudaMallocHost / cudaFreeHost for measurement buffers (no reference counterpart: VioMeasurement is host memory). */
 XB_API void* xb_host_alloc(size_t bytes);
 XB_API void xb_host_free(void* p);
@@ -295,6 +318,15 @@ XB_API int xb_tm_remove_persistent_track(xb_track_manager* tm, unsigned idx);   
 XB_API int xb_tm_remove_new_persistent_tracks(xb_track_manager* tm, const unsigned* idxs, int n);  /* :87-97 */
 XB_API int xb_tm_set_opp_ids(xb_track_manager* tm, const unsigned long long* ids, int n);  /* setOppUpgradesMSCKF (MULTI_UAV) */
 XB_API int xb_tm_counts(const xb_track_manager* tm, int* n_slam, int* n_new_slam, int* n_opp);
+/* TrackManager::featureTriangleAtPoint (:443-560): the Delaunay facet of the SLAM features' last image positions that
+ * contains the LRF image point (distorted pixel coordinates).  Returns 3 and the feature indexes (slam_trks_ order) for
+ * xb_range_measurement::tr_feat_ids, 0 when the point lies in no facet of features.  xb_tm_delaunay_facet is the same
+ * lookup on a caller-provided point set xy (n x 2). */
+XB_API int xb_tm_feature_triangle_at_point(const xb_track_manager* tm, double x_dist, double y_dist, int* ids);
+/* Camera::undistort + Camera::normalize of one image point (src/x/vision/camera.cpp:69-101), e.g. the LRF beam's image
+ * point -> RangeMeasurement::img_pt_n (src/x/vio/vio.cpp:288-294).  out: normalised (x, y). */
+XB_API int xb_tm_normalize_point(const xb_track_manager* tm, double x_dist, double y_dist, double* out);
+XB_API int xb_tm_delaunay_facet(const double* xy, int n, int img_width, int img_height, double qx, double qy, int* ids);
 
 #ifdef __cplusplus
 }

@@ -104,8 +104,6 @@ class VioUpdaterOracle:
         cols = P.shape[1]
         h_l, res_l, r_l = np.zeros((0, cols)), np.zeros(0), np.zeros(0)
         rng, sun = self.meas.range, self.meas.sun_angle
-        self.last.pop("range", None)
-        self.last.pop("solar", None)
         if rng.timestamp > 0.1 and self.meas.slam_trks and len(rng.tr_feat_ids) > 0:
             ru = RangeUpdate(rng, quats, poss, state.f_array, self.sm.anchor_idxs, P, state.n_poses_max(), self.sigma_range)
             self.last["range"] = ru
@@ -162,6 +160,8 @@ class VioUpdaterOracle:
         """Updater::update as compiled with -DMULTI_UAV (updater.cpp:39-115): the short-MSCKF step applies ONLY the
         CI lists (its stacked h is built and dropped, :58-70); the main step applies the CI lists first, then ONE
         applyUpdate with the (h, res) linearised BEFORE the CI corrections (:84-97); no IEKF loop."""
+        self.last.pop("range", None)
+        self.last.pop("solar", None)
         correction = np.zeros(state.n_error_states())
         if self.meas.msckf_short_trks:
             _, (S_l, P_l, H_l, r_l) = self._construct_multi(state, 1)
@@ -192,6 +192,8 @@ class VioUpdaterOracle:
 
     # updater.cpp:39-115
     def update(self, state):
+        self.last.pop("range", None)
+        self.last.pop("solar", None)
         correction = np.zeros(state.n_error_states())
         if self.meas.msckf_short_trks:  # preUpdateShortMsckf, vio_updater.cpp:209-215
             h, res, r = self.construct_short_msckf_update(state)

@@ -71,6 +71,19 @@ int main(int argc, char** argv) {
       const int nl = (int)ev[p++];
       for (int i = 0; i < nl; ++i) lost.push_back((unsigned)ev[p++]);
       vio_updater.trackManager().setTracks(lists[0], lists[1], lists[2], lists[3], lists[4], lost);
+      // range / sun-angle members of the VioMeasurement (vio/types.h:300-305) + the facet the track manager reports
+      std::vector<int> facet;
+      if (ev[p++] != 0.0) {
+        m.range.timestamp = ev[p]; m.range.range = ev[p + 1];
+        m.range.img_pt_n.setX(ev[p + 2]); m.range.img_pt_n.setY(ev[p + 3]);
+        facet = {(int)ev[p + 4], (int)ev[p + 5], (int)ev[p + 6]};
+        p += 7;
+      }
+      vio_updater.trackManager().setFacet(facet);
+      if (ev[p++] != 0.0) {
+        m.sun_angle.timestamp = ev[p]; m.sun_angle.x_angle = ev[p + 1]; m.sun_angle.y_angle = ev[p + 2];
+        p += 3;
+      }
       vio_updater.setMeasurement(m);
       auto updated_state = ekf.processUpdateMeasurement();
       if (!updated_state.has_value()) { fprintf(stderr, "update returned nullopt\n"); return 3; }

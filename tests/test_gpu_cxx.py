@@ -33,11 +33,19 @@ def _serialise(cfg, ev, max_tracks):
                     out += list(t.ravel())
             out.append(float(len(m.lost_slam_trk_idxs)))
             out += [float(i) for i in m.lost_slam_trk_idxs]
+            if m.range is not None:
+                out += [1.0, m.range.timestamp, m.range.range, *m.range.img_pt_n, *[float(i) for i in m.range.tr_feat_ids]]
+            else:
+                out.append(0.0)
+            if m.sun_angle is not None:
+                out += [1.0, m.sun_angle.timestamp, m.sun_angle.x_angle, m.sun_angle.y_angle]
+            else:
+                out.append(0.0)
     return np.asarray(out, dtype=np.float64)
 
 
 def test_cxx_binding_replays_identically(tmp_path):
-    cfg = SynthConfig(M=6, F=6, K=12, seed=2, n_short=2, churn=1)
+    cfg = SynthConfig(M=6, F=6, K=12, seed=2, n_short=2, churn=1, range_every=2, sun_every=3)  # + LRF and sun-sensor rows
     ev = record(Scenario(cfg), 12)
     exe = tmp_path / "test_x_api"
     libdir = ROOT / "x_multi_agent_b200"
@@ -51,7 +59,7 @@ def test_cxx_binding_replays_identically(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     got = np.fromfile(tmp_path / "out.bin")
-    dev = Filter(cfg.M, cfg.F, max_tracks=16, n_slots=64, sigma_img=cfg.sigma_img)
+    dev = Filter(cfg.M, cfg.F, max_tracks=16, n_slots=64, sigma_img=cfg.sigma_img, sigma_range=0.05)
     states = []
     replay(ev, dev, lambda k, m, st: states.append(st.x.copy()))
     states.append(dev.get_state().x)

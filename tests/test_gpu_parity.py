@@ -854,3 +854,65 @@ def test_two_filters_on_one_gpu_run_concurrently():
         assert not t.is_alive(), "a filter hung while the other one was running"
     for a in range(2):
         assert np.array_equal(alone[a][0], both[a][0])
+
+
+# ---- range (laser range finder) and sun-sensor rows ---------------------------------------------------
+SENSOR_CASES = {
+    # rows <= N + 1: no QR compression in the reference, the sensor rows keep their own variances
+    "slam_only_no_qr": (dict(M=5, F=6, K=0, seed=5, churn=1, range_every=1, sun_every=3), 16, 1.0),
+    # rows > N + 1: the reference QR-compresses and weights EVERY row sigma_img^2 (vio_updater.cpp:490-508); the range row
+    # then acts like a 3 mm measurement and the later updates are ill-conditioned (round-off x10 per update in the
+    # reference binary and the oracle alike, tests/test_ref_pinning.py): loose final tolerance, tight early one
+    "msckf_slam_qr": (dict(M=6, F=6, K=14, seed=11, n_short=2, churn=1, range_every=1, sun_every=2), 16, 1e3),
+    # sun sensor before the first SLAM feature exists (sparse part = the two sun rows only) and IEKF: the sensor rows
+    # enter the first iteration only (vio_updater.cpp:381, 402)
+    "sun_first_iekf2": (dict(M=8, F=8, K=10, seed=5, n_short=3, churn=2, slam_init_frame=3, range_every=2, sun_every=1), 14, 10.0),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(SENSOR_CASES))
+@pytest.mark.parametrize("no_overlap", ["0", "1"])
+def test_range_and_sun_rows_match_oracle(case, no_overlap, monkeypatch):
+    """RangeUpdate (range_update.cpp:61-265) + SolarUpdate (solar_update.cpp:39-94) stacked under the visual rows
+    (vio_updater.cpp:352-403): gates, every update's state and the final covariance against the oracle (which is pinned
+    to the reference's own sources for exactly these cases), on the side-stream schedule and in order."""
+    kw, frames, loose = SENSOR_CASES[case]
+    cfg = SynthConfig(**kw)
+    iekf = 2 if case == "sun_first_iekf2" else 1
+    ev = record(Scenario(cfg), frames)
+    ora = OracleFilter(cfg.M, cfg.F, sigma_img=cfg.sigma_img, n_slots=64, iekf_iter=iekf, sigma_range=cfg.sigma_range)
+    monkeypatch.setenv("XB_NO_OVERLAP", no_overlap)
+    dev = make_filter(cfg, iekf_iter=iekf, sigma_range=cfg.sigma_range)
+    o_states, d_states, o_gate, d_gate = [], [], [], []
+
+    def on_oracle(k, m, st):
+        o_states.append(st.copy())
+        ru = ora.upd.last.get("range")
+        o_gate.append((k, ru.inlier, ru.gamma) if ru is not None else None)
+
+    def on_dev(k, m, st):
+        d_states.append(st)
+        used = m.range is not None and len(m.slam_trks) > 0
+        d_gate.append((k, bool(dev.debug_int("range_inlier", 1)[0]), dev.debug("range_gamma", 1)[0]) if used else None)
+
+    replay(ev, ora, on_oracle)
+    replay(ev, dev, on_dev)
+    rp = Report()
+    n_gated = 0
+    for go, gd in zip(o_gate, d_gate):
+        assert (go is None) == (gd is None)
+        if go is not None:
+            n_gated += 1
+            assert go[1] == gd[1], f"range gate differs at update {go[0]}"
+            rp.check(f"range gamma upd{go[0]}", abs(gd[2] - go[2]) / abs(go[2]), 1e-7 * loose)
+    assert n_gated >= 3 and any(g[1] for g in o_gate if g is not None)
+    first = next(i for i, g in enumerate(o_gate) if g is not None and g[1])
+    compare_state(rp, f"upd{first}(first range inlier)", d_states[first], o_states[first], cfg.M, cfg.F, tol_scale=10.0, cov=False)
+    compare_state(rp, f"upd{frames - 1}", d_states[-1], o_states[-1], cfg.M, cfg.F, tol_scale=10.0 * loose, cov=False)
+    dn = dev.get_state()
+    dn.cov = dev.get_covariance()
+    compare_state(rp, "newest(repropagated)", dn, ora.newest(), cfg.M, cfg.F, tol_scale=10.0 * loose)
+    dev.synchronize()
+    rp.done()
+    dev.close()

@@ -195,3 +195,31 @@ def test_cxx_track_manager_through_the_reference_api(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([os.fspath(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_delaunay_facet_lookup_matches_scipy():
+    """TrackManager::featureTriangleAtPoint (track_manager.cpp:443-560) picks the Delaunay facet of the SLAM features'
+    image positions that contains the LRF image point.  cv::Subdiv2D is not available here; the Delaunay triangulation of
+    points in general position is unique, so qhull (scipy.spatial.Delaunay) on the same single-precision points is an
+    independent oracle: same three vertices, or no facet on both sides when the point lies outside the hull."""
+    import ctypes as C
+
+    from scipy.spatial import Delaunay
+
+    from x_multi_agent_b200 import lib as L
+    lib = L.load()
+    rng = np.random.default_rng(0)
+    found = 0
+    for trial in range(200):
+        n = int(rng.integers(3, 200))
+        xy = np.ascontiguousarray(rng.uniform([20, 20], [620, 460], (n, 2)).astype(np.float32).astype(np.float64))
+        q = (320.5, 240.5) if trial % 2 else tuple(rng.uniform([60, 60], [580, 420]))
+        ids = (C.c_int * 3)()
+        r = lib.xb_tm_delaunay_facet(xy.ctypes.data_as(C.POINTER(C.c_double)), n, 640, 480, q[0], q[1], ids)
+        tri = Delaunay(xy)
+        s = tri.find_simplex(np.array([q], dtype=np.float32).astype(np.float64))[0]
+        want = set(int(i) for i in tri.simplices[s]) if s >= 0 else None
+        got = set(int(i) for i in ids) if r == 3 else None
+        assert got == want, (trial, n, got, want)
+        found += got is not None
+    assert found > 150

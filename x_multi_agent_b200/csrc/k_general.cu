@@ -21,7 +21,12 @@ __global__ void k_gen_densify(UpdateDims d, const int* __restrict__ scols, const
   const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (r >= d.m || c >= d.N) return;
   double v = 0.0;
-  if (r < d.ns2) {
+  if (r >= 2 * d.nslam && r < d.ns2) {  // wide row (range / sun sensor)
+    const int w = r - 2 * d.nslam;
+    for (int e = 0; e < XB_WNZ; ++e)
+      if (d.wcols[XB_WNZ * w + e] == c) v += d.wvals[XB_WNZ * w + e];
+    if (c == 0) res[r] = d.wres[w];
+  } else if (r < d.ns2) {
     const int j = r >> 1, h = r & 1;
     for (int e = 0; e < 15; ++e)
       if (scols[15 * j + e] == c) v += svals[30 * j + 15 * h + e];

@@ -883,6 +883,166 @@ void launch_slam_rows(cudaStream_t s, const SlamParams& sp) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Range and sun-sensor rows (range_update.cpp:61-265, solar_update.cpp:39-94): one warp.  Lane 0 evaluates the (tiny)
+// closed forms, the warp evaluates the range gate h P h^T over the 33 x 33 gathered covariance entries.
+// Row w of the output: XB_WNZ (column, value) entries (duplicates add: the anchor blocks of the range row accumulate
+// exactly like range_update.cpp:217-242 when anchors coincide), unused entries are (0, 0.0).
+// ------------------------------------------------------------------------------------------------
+__device__ inline void xb_cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+// row vector (1x3) times 3x3 matrix
+__device__ inline void xb_vtm33(const double* v, const double* A, double* y) {
+  for (int c = 0; c < 3; ++c) y[c] = v[0] * A[c] + v[1] * A[3 + c] + v[2] * A[6 + c];
+}
+__global__ void __launch_bounds__(32) k_sensor_rows(SensorParams sp) {
+  __shared__ int lc[XB_WMAX * XB_WNZ];
+  __shared__ double h[XB_WMAX * XB_WNZ];
+  __shared__ double rs[XB_WMAX];
+  __shared__ int ok;
+  const int lane = threadIdx.x;
+  const int M = sp.M, np = sp.n_poses, N = sp.N;
+  const double* parr = sp.xv + XV_ARR;
+  const double* qarr = sp.xv + XV_ARR + 3 * M;
+  const double* farr = sp.xv + XV_ARR + 7 * M;
+  for (int e = lane; e < XB_WMAX * XB_WNZ; e += 32) { lc[e] = 0; h[e] = 0.0; }
+  if (lane < XB_WMAX) rs[lane] = 0.0;
+  if (lane == 0) ok = 0;
+  __syncwarp();
+  int row = 0;
+  if (sp.range_on) {
+    if (lane == 0) {
+      double Gf[3][3], Ra[3][9], al[3], be[3], rho[3];
+      int an[3];
+      bool valid = np >= 1;
+      for (int j = 0; j < 3 && valid; ++j) {  // range_update.cpp:76-97
+        const int id = sp.tri[j];
+        al[j] = farr[3 * id]; be[j] = farr[3 * id + 1]; rho[j] = farr[3 * id + 2];
+        an[j] = sp.anchor[id];
+        if (an[j] < 0 || an[j] >= np) { valid = false; break; }
+        xb_rot(qarr + 4 * an[j], Ra[j]);
+        const double ab1[3] = {al[j], be[j], 1.0};
+        double t3[3];
+        xb_mv33(Ra[j], ab1, t3);
+        for (int e = 0; e < 3; ++e) Gf[j][e] = 1.0 / rho[j] * t3[e] + parr[3 * an[j] + e];
+      }
+      if (valid) {
+        double Ri[9], d01[3], d21[3], Gn[3];
+        xb_rot(qarr + 4 * (np - 1), Ri);
+        const double* pci = parr + 3 * (np - 1);
+        for (int e = 0; e < 3; ++e) { d01[e] = Gf[0][e] - Gf[1][e]; d21[e] = Gf[2][e] - Gf[1][e]; }
+        xb_cross3(d01, d21, Gn);  // :123
+        const double pt[3] = {sp.pt_x, sp.pt_y, 1.0};
+        double RtGn[3];
+        xb_mtv33(Ri, Gn, RtGn);
+        double a = 0.0, b = 0.0;
+        for (int e = 0; e < 3; ++e) { a += (Gf[1][e] - pci[e]) * Gn[e]; b += pt[e] * RtGn[e]; }
+        const double res = sp.range - a / b;  // :129-139
+        double GnR[3], skpt[9], Jqc[3], Rpt[3], Gpr[3], bary[3];
+        xb_vtm33(Gn, Ri, GnR);
+        xb_skew(pt, skpt);
+        xb_vtm33(GnR, skpt, Jqc);
+        xb_mv33(Ri, pt, Rpt);
+        for (int e = 0; e < 3; ++e) {
+          Gpr[e] = a / b * Rpt[e] + pci[e];
+          bary[e] = 1.0 / 3.0 * (Gf[0][e] + Gf[1][e] + Gf[2][e]);
+        }
+        const int pos = np - 1;
+        for (int c = 0; c < 3; ++c) {  // :148-153, :209-215
+          lc[c] = XB_CORE + 3 * pos + c;
+          h[c] = -1.0 / b * Gn[c];
+          lc[3 + c] = XB_CORE + 3 * M + 3 * pos + c;
+          h[3 + c] = a / (b * b) * Jqc[c];
+        }
+        const int ep[3] = {2, 0, 1}, eq[3] = {1, 2, 0};  // :162, :178, :194
+        for (int j = 0; j < 3; ++j) {
+          double ed[3], bd[3], cr[3], Jf[3], JfR[3], skab[9], Jqa[3], m3[9], Jfi[3];
+          for (int e = 0; e < 3; ++e) { ed[e] = Gf[ep[j]][e] - Gf[eq[j]][e]; bd[e] = bary[e] - Gpr[e]; }
+          xb_cross3(ed, bd, cr);
+          for (int e = 0; e < 3; ++e) Jf[e] = 1.0 / b * (1.0 / 3.0 * Gn[e] + cr[e]);
+          xb_vtm33(Jf, Ra[j], JfR);
+          const double ab1[3] = {al[j], be[j], 1.0};
+          xb_skew(ab1, skab);
+          xb_vtm33(JfR, skab, Jqa);
+          xb_mat_ivd(al[j], be[j], rho[j], m3);
+          xb_vtm33(JfR, m3, Jfi);
+          const int o = 6 + 9 * j;
+          for (int c = 0; c < 3; ++c) {
+            lc[o + c] = XB_CORE + 3 * an[j] + c;
+            h[o + c] = Jf[c];
+            lc[o + 3 + c] = XB_CORE + 3 * M + 3 * an[j] + c;
+            h[o + 3 + c] = -1.0 / rho[j] * Jqa[c];
+            lc[o + 6 + c] = XB_CORE + (2 * M + sp.tri[j]) * 3 + c;
+            h[o + 6 + c] = 1.0 / rho[j] * Jfi[c];
+          }
+        }
+        rs[0] = res;
+        ok = 1;
+      }
+    }
+    __syncwarp();
+    // gate: gamma = res^2 / (h P h^T + sigma_range^2) < chi2(0.9, 1)   (range_update.cpp:246-252)
+    double s = 0.0;
+    if (ok) {
+      for (int e = lane; e < 33 * 33; e += 32) {
+        const int d = e / 33, c = e % 33;
+        s = fma(h[d] * sp.P[(size_t)lc[d] * N + lc[c]], h[c], s);
+      }
+    }
+    s = xb_warp_sum(s) + sp.var_range;
+    const double gamma = ok ? rs[0] * rs[0] / s : NAN;
+    const int inl = ok && gamma < sp.chi2_1;
+    if (lane == 0) { sp.gamma[0] = gamma; sp.inlier[0] = inl; }
+    __syncwarp();
+    for (int e = lane; e < XB_WNZ; e += 32) h[e] = inl ? h[e] * sp.w_range : 0.0;  // an outlier leaves a zero row (:254)
+    if (lane == 0) rs[0] = inl ? rs[0] * sp.w_range : 0.0;
+    row = 1;
+  }
+  __syncwarp();
+  if (sp.sun_on && lane == 0) {  // solar_update.cpp:39-94 (calibration constants as hard-coded there)
+    const double SqI[4] = {-0.063338979194957, 0.007502445522018, 0.930635612981541, 0.360346005598587};  // (x,y,z,w)
+    double gs[3] = {-0.29385515271891938, -0.55080445540063927, 0.78119370269565391};
+    const double gn = sqrt(gs[0] * gs[0] + gs[1] * gs[1] + gs[2] * gs[2]);
+    for (int e = 0; e < 3; ++e) gs[e] /= gn;
+    double Rs[9], Rq[9], sv[3], sh[3];
+    xb_rot(SqI, Rs);
+    xb_rot(sp.xv + 6, Rq);
+    xb_mtv33(Rq, gs, sv);
+    xb_mtv33(Rs, sv, sh);
+    const double sn = sqrt(sh[0] * sh[0] + sh[1] * sh[1] + sh[2] * sh[2]);
+    for (int e = 0; e < 3; ++e) sh[e] /= sn;
+    const double RAD2DEG = 57.2957795130;
+    const double r0 = sp.sun_x - RAD2DEG * atan2(sh[0], sh[2]), r1 = sp.sun_y - RAD2DEG * atan2(sh[1], sh[2]);
+    const double d0 = sh[0] * sh[0] + sh[2] * sh[2], d1 = sh[1] * sh[1] + sh[2] * sh[2];
+    const double mat[6] = {sh[2] / d0, 0.0, -sh[0] / d0, 0.0, sh[2] / d1, -sh[1] / d1};
+    double Rst[9], sk[9], m1[6], J[6];
+    for (int rr = 0; rr < 3; ++rr)
+      for (int c = 0; c < 3; ++c) Rst[rr * 3 + c] = Rs[c * 3 + rr];
+    xb_skew(sv, sk);
+    xb_mm23(mat, Rst, m1);
+    xb_mm23(m1, sk, J);
+    for (int rr = 0; rr < 2; ++rr) {
+      for (int c = 0; c < 3; ++c) {
+        lc[(row + rr) * XB_WNZ + c] = 6 + c;  // kIdxQ
+        h[(row + rr) * XB_WNZ + c] = RAD2DEG * J[rr * 3 + c] * sp.w_sun;
+      }
+    }
+    rs[row] = r0 * sp.w_sun;
+    rs[row + 1] = r1 * sp.w_sun;
+  }
+  __syncwarp();
+  for (int e = lane; e < XB_WMAX * XB_WNZ; e += 32) { sp.cols[e] = lc[e]; sp.vals[e] = h[e]; }
+  if (lane < XB_WMAX) sp.res[lane] = rs[lane];
+}
+void launch_sensor_rows(cudaStream_t s, const SensorParams& sp) {
+  if (!sp.range_on && !sp.sun_on) return;
+  k_sensor_rows<<<1, 32, 0, s>>>(sp);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Gram stage:  G = sum_inliers [J|r]^T [J|r] - B_all^T B_all + D^T D   ((6M+1) x (6M+1))
 //   k_gram_partial: split-K  A^T A  of a tall row-major matrix A [rows x W] -> partial[z][W x W]
 //   k_gram_reduce : fixed-order sum of the partials (deterministic), block-diagonal J^T J terms and

@@ -55,6 +55,29 @@ __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int
   row[1] = a1;
 }
 
+// Wide rows (range / sun sensor, XB_WNZ entries each): PHt[i, 2 nslam + w] = sum_e P[i, col_e] * val[w][e]
+__global__ void k_pht_wide(UpdateDims d, const double* __restrict__ P, double* __restrict__ T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
+  if (i >= d.N) return;
+  double a = 0.0;
+  for (int e = 0; e < XB_WNZ; ++e) {
+    const double v = d.wvals[XB_WNZ * w + e];
+    if (v != 0.0) a = fma(P[(size_t)i * d.N + d.wcols[XB_WNZ * w + e]], v, a);
+  }
+  T[(size_t)(d.m_pad + i) * d.ld + 2 * d.nslam + w] = a;
+}
+// S[2 nslam + w, c] = sum_e val[w][e] * PHt[col_e, c] for every sparse-part column c
+__global__ void k_s_wide(UpdateDims d, double* __restrict__ T) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
+  if (c >= d.ns2) return;
+  double a = 0.0;
+  for (int e = 0; e < XB_WNZ; ++e) {
+    const double v = d.wvals[XB_WNZ * w + e];
+    if (v != 0.0) a = fma(v, T[(size_t)(d.m_pad + d.wcols[XB_WNZ * w + e]) * d.ld + c], a);
+  }
+  T[(size_t)(2 * d.nslam + w) * d.ld + c] = a;
+}
+
 // After the SLAM tile columns are factored (S11 = L11 L11^T, W1s = (P Hs^T) L11^-T, W2s on the Omega rows), the
 // sub-diagonal block of the factor needs no triangular solve:
 //   L21 = S21 L11^-T = Rg (sym(P) Hs^T)[pose rows] L11^-T = Rg * Wsym,   Wsym = (W1s + W2s)/2 on the pose rows
@@ -69,7 +92,7 @@ __global__ void k_wsym(UpdateDims d, const int* __restrict__ omega_inv, const do
   Bc[(size_t)b * d.s_pad + c] = v;
 }
 void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc) {
-  if (d.nslam <= 0) return;
+  if (d.ns2 <= 0) return;
   dim3 g((d.s_pad + 127) / 128, d.ms);
   k_wsym<<<g, 128, 0, s>>>(d, omega_inv, T, Bc);
   count_launch();
@@ -113,6 +136,11 @@ __global__ void k_s_finish(UpdateDims d, int c0, int nc, const double* __restric
     r = zg[ar];
     if (corr)
       for (int b = 0; b < d.ms; ++b) r = fma(Lg[(size_t)b * ldr + ar], corr[XB_CORE + b], r);  // Rg[a][b] = Lg[b][a]
+  } else if (a >= 2 * d.nslam) {  // wide row (range / sun sensor)
+    const int w = a - 2 * d.nslam;
+    r = d.wres[w];
+    if (corr)
+      for (int e = 0; e < XB_WNZ; ++e) r = fma(d.wvals[XB_WNZ * w + e], corr[d.wcols[XB_WNZ * w + e]], r);
   } else {
     const int j = a >> 1, h = a & 1;
     r = sres[2 * j + h];
@@ -130,15 +158,25 @@ void launch_omega_rows(cudaStream_t s, const UpdateDims& d, int c0, int nc, cons
 void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,
                             const double* sres, const double* corr_total, double var, const int* omega, const int* omega_inv,
                             double* T) {
-  if (d.nslam <= 0) return;
-  {
+  if (d.ns2 <= 0) return;
+  if (d.nslam > 0) {
     dim3 g((d.N + 127) / 128, d.nslam);
     k_pht_slam<<<g, 128, 0, s>>>(d, P, scols, svals, omega_inv, T);
     count_launch();
   }
-  {
+  if (d.nw > 0) {
+    dim3 g((d.N + 127) / 128, d.nw);
+    k_pht_wide<<<g, 128, 0, s>>>(d, P, T);
+    count_launch();
+  }
+  if (d.nslam > 0) {
     dim3 g((d.ns2 + 127) / 128, d.nslam);
     k_s_slam<<<g, 128, 0, s>>>(d, 0, d.ns2, scols, svals, T);
+    count_launch();
+  }
+  if (d.nw > 0) {
+    dim3 g((d.ns2 + 127) / 128, d.nw);
+    k_s_wide<<<g, 128, 0, s>>>(d, T);
     count_launch();
   }
   launch_sym_lower(s, T, d.ld, 0, d.ns2, 0);
@@ -190,7 +228,7 @@ __global__ void k_omega_gather(UpdateDims d, const double* __restrict__ P, const
 // Rg (the transposed Gram factor) is only materialised for the CUDA-core GEMM fallback; the tensor-core kernel takes the
 // factor Lg = Rg^T as a k-major / [K x N] operand directly (Rg == nullptr).
 void launch_slab_l21(cudaStream_t s, const UpdateDims& d, const double* Rg, const double* Lg, int ldr, double* T, const double* Bc) {
-  if (d.nslam <= 0) return;
+  if (d.ns2 <= 0) return;
   if (Rg) gemm_nn(s, d.ms, d.ns2, d.ms, 1.0, Rg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
   else gemm_tn(s, d.ms, d.ns2, d.ms, 1.0, Lg, ldr, Bc, d.s_pad, 0.0, T + (size_t)d.ro * d.ld, d.ld);
 }
@@ -223,7 +261,7 @@ void launch_slab_s22(cudaStream_t s, const UpdateDims& d, const double* P, const
   }
 }
 void launch_slab_schur(cudaStream_t s, const UpdateDims& d, double* T) {
-  if (d.nslam <= 0) return;
+  if (d.ns2 <= 0) return;
   // Schur complement of the factored SLAM columns on every row from the slab rows down (S22, P H^T, r_eff, Omega, V):
   //   T[ro:, ro:] -= T[ro:, 0:s_pad] * L21^T     -- after it the slab columns are a plain tall factorisation of their own
   const int rows = d.m_pad - d.ro + d.n_pad + 96;
@@ -269,6 +307,17 @@ __global__ void k_omega_rows(UpdateDims d, int c0, int nc, const double* __restr
     const int ar = a - d.ro;
     if (ok >= XB_CORE && ok < XB_CORE + d.ms) v = Lg[(size_t)(ok - XB_CORE) * ldr + ar];  // Rg[a][b] = Lg[b][a]
     for (int b = 0; b < d.ms; ++b) a2 = fma(P[(size_t)(XB_CORE + b) * d.N + ok], Lg[(size_t)b * ldr + ar], a2);
+  } else if (a >= 2 * d.nslam) {  // wide row (range / sun sensor)
+    const int w = a - 2 * d.nslam;
+    if (w < d.nw)
+      for (int e = 0; e < XB_WNZ; ++e) {
+        const double hv = d.wvals[XB_WNZ * w + e];
+        const int col = d.wcols[XB_WNZ * w + e];
+        if (hv != 0.0) {
+          if (col == ok) v += hv;
+          a2 = fma(P[(size_t)col * d.N + ok], hv, a2);
+        }
+      }
   } else {
     const int j = a >> 1, h = a & 1;
     int col[15];

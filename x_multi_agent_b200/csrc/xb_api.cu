@@ -205,6 +205,12 @@ struct xb_filter {
   int* d_inl1;
   // slam rows
   int* d_scols; double *d_svals, *d_sres, *d_sgamma; int* d_sinl; int* d_anchor;
+  // range / sun-sensor rows (xb_vio_set_sensors): pending measurement + device rows
+  int* d_wcols = nullptr; double *d_wvals = nullptr, *d_wres = nullptr, *d_wgamma = nullptr; int* d_winl = nullptr;
+  xb_range_measurement sens_range{};
+  xb_sun_angle_measurement sens_sun{};
+  bool sens_range_on = false, sens_sun_on = false;
+  int last_nw = 0;
   // gram
   double *d_partB, *d_partD, *d_blocks, *d_Tg, *d_Rg, *d_diag0;
   int gcols_pad = 0, grows_pad = 0, nz = 1;
@@ -447,6 +453,11 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_sgamma, std::max(1, F), double);
   DA(f->d_sinl, std::max(1, F), int);
   DA(f->d_anchor, std::max(1, F), int);
+  DA(f->d_wcols, XB_WMAX * XB_WNZ, int);
+  DA(f->d_wvals, XB_WMAX * XB_WNZ, double);
+  DA(f->d_wres, XB_WMAX, double);
+  DA(f->d_wgamma, 1, double);
+  DA(f->d_winl, 1, int);
 
   const int tiles = (W + 63) / 64;
   f->nz = std::max(1, std::min(32, (148 + tiles * tiles - 1) / (tiles * tiles)));
@@ -460,12 +471,13 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   DA(f->d_diag0, f->gcols_pad, double);
 
   // structured path: SLAM columns and slab columns are padded separately; dense-H path allows up to N rows
-  const int m_pad = std::max(pad32(2 * F) + pad32(6 * M), pad32(N)), n_pad = pad32(N);
+  // (+ XB_WMAX: the range / sun-sensor rows share the column group of the SLAM rows)
+  const int m_pad = std::max(pad32(2 * F + XB_WMAX) + pad32(6 * M), pad32(N)), n_pad = pad32(N);
   f->T_doubles = (size_t)(m_pad + n_pad + 96) * m_pad;
   DA(f->d_T, f->T_doubles, double);
   DA(f->d_flags, (size_t)((m_pad + n_pad + 96) / 32 + 2) * (m_pad / 32) + 128, int);
   DA(f->d_flags_g, (size_t)(f->grows_pad / 32 + 2) * (f->gcols_pad / 32) + 128, int);
-  DA(f->d_Bc, (size_t)6 * M * std::max(32, pad32(2 * F)), double);
+  DA(f->d_Bc, (size_t)6 * M * std::max(32, pad32(2 * F + XB_WMAX)), double);
   DA(f->d_FQ2, (size_t)128 * 450, double);
   DA(f->d_Gp, (size_t)32 * 6 * M, double);
   DA(f->d_omega, 32, int);
@@ -854,6 +866,27 @@ extern "C" int xb_vio_set_measurement(xb_filter* f, const xb_measurement* m) {
     CK(cudaMemcpyAsync(f->d_slam_chi2, pc, sizeof(double) * f->l_slam.n, cudaMemcpyHostToDevice, f->stream));
   }
   CK(cudaEventRecord(f->pin_ev[f->pin_cur], f->stream));
+  f->sens_range_on = f->sens_sun_on = false;  // setMeasurement replaces the whole VioMeasurement (vio_updater.cpp:122-124)
+  return XB_OK;
+}
+
+// VioMeasurement::range / sun_angle (include/x/vio/types.h:300-305) of the measurement set last; each is consumed by the
+// first constructUpdate that uses it (vio_updater.cpp:381, 402).
+extern "C" int xb_vio_set_sensors(xb_filter* f, const xb_range_measurement* range, const xb_sun_angle_measurement* sun) {
+  if (!f) return fail(XB_E_INVALID, "null argument");
+  f->sens_range_on = f->sens_sun_on = false;
+  if (range && range->timestamp > 0.1 && range->n_tr_feat_ids > 0) {  // vio_updater.cpp:358, 369
+    if (range->n_tr_feat_ids != 3) return fail(XB_E_INVALID, "range: the facet has three SLAM feature ids");
+    for (int j = 0; j < 3; ++j)
+      if (range->tr_feat_ids[j] < 0 || range->tr_feat_ids[j] >= f->F)
+        return fail(XB_E_INVALID, "range: facet feature id out of range");
+    f->sens_range = *range;
+    f->sens_range_on = true;
+  }
+  if (sun && sun->timestamp > -1.0) {  // vio_updater.cpp:390
+    f->sens_sun = *sun;
+    f->sens_sun_on = true;
+  }
   return XB_OK;
 }
 
@@ -1174,7 +1207,7 @@ extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
   return XB_OK;
 }
 
-static UpdateDims update_dims(const xb_filter* f, int nslam);
+static UpdateDims update_dims(const xb_filter* f, int nslam, int nw);
 static int set_omega(xb_filter* f);
 
 static void launch_slam_rows_on(xb_filter* f, cudaStream_t st, int ns) {
@@ -1185,12 +1218,43 @@ static void launch_slam_rows_on(xb_filter* f, cudaStream_t st, int ns) {
   sp.cols = f->d_scols; sp.vals = f->d_svals; sp.res = f->d_sres; sp.gamma = f->d_sgamma; sp.inlier = f->d_sinl;
   launch_slam_rows(st, sp);
 }
+// Range / sun-sensor rows pending for this constructUpdate (vio_updater.cpp:352-403).  Returns the number of rows.
+static int sensor_row_count(const xb_filter* f, int which, int ns) {
+  if (which != 0) return 0;
+  return ((f->sens_range_on && ns > 0) ? 1 : 0) + (f->sens_sun_on ? 2 : 0);
+}
+static void launch_sensor_rows_on(xb_filter* f, cudaStream_t st, int ns) {
+  SensorParams sp{};
+  sp.xv = f->d_xw; sp.M = f->M; sp.N = f->N; sp.n_poses = f->n_poses; sp.P = f->d_Pw; sp.anchor = f->d_anchor;
+  sp.range_on = f->sens_range_on && ns > 0;
+  sp.sun_on = f->sens_sun_on;
+  if (!sp.range_on && !sp.sun_on) return;
+  const int nw = (sp.range_on ? 1 : 0) + (sp.sun_on ? 2 : 0);
+  // rows the reference stacks (every track keeps its 2L - 3 rows, gated out or not: msckf_update.cpp:50-52); more than
+  // N + 1 of them -> QR compression, after which EVERY row is weighted sigma_img^2 (vio_updater.cpp:490-508)
+  const long rows_total = 2L * f->l_msckf.n_obs - 3L * f->l_msckf.n + 2L * f->l_newms.n_obs - 3L * f->l_newms.n + 2L * ns + nw;
+  const bool qr = rows_total > (long)f->N + 1;
+  const double var_sun = 10000 * 0.01777777777;  // solar_update.cpp:48
+  sp.range = f->sens_range.range; sp.pt_x = f->sens_range.img_pt_n[0]; sp.pt_y = f->sens_range.img_pt_n[1];
+  for (int j = 0; j < 3; ++j) sp.tri[j] = f->sens_range.tr_feat_ids[j];
+  sp.var_range = f->cfg.sigma_range * f->cfg.sigma_range;
+  static const double chi2_1 = xb_chi2_quantile(0.9, 1.0);  // range_update.cpp:249-250
+  sp.chi2_1 = chi2_1;
+  sp.w_range = qr ? 1.0 : f->cfg.sigma_img / f->cfg.sigma_range;
+  sp.w_sun = qr ? 1.0 : f->cfg.sigma_img / std::sqrt(var_sun);
+  sp.sun_x = f->sens_sun.x_angle; sp.sun_y = f->sens_sun.y_angle;
+  sp.cols = f->d_wcols; sp.vals = f->d_wvals; sp.res = f->d_wres; sp.gamma = f->d_wgamma; sp.inlier = f->d_winl;
+  launch_sensor_rows(st, sp);
+}
 // SLAM rows + everything of the tall buffer on their columns + the first s_pad/32 tile columns of its factorisation + Wsym
 static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int stage_build, int stage_chol, int share,
                        bool with_rows) {
   {
     StageTimer st_(f, stage_build, st);
-    if (with_rows) launch_slam_rows_on(f, st, d.nslam);
+    if (with_rows) {
+      launch_slam_rows_on(f, st, d.nslam);
+      launch_sensor_rows_on(f, st, d.nslam);
+    }
     launch_build_slam_part(st, d, f->d_Pw, f->d_scols, f->d_svals, f->d_sres, f->corr_zero ? nullptr : f->d_corr,
                            f->cfg.sigma_img * f->cfg.sigma_img, f->d_omega, f->d_omega_inv, f->d_T);
   }
@@ -1212,10 +1276,13 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     int rci = invalidate_early(f);
     if (rci) return rci;
   }
+  const int nw = sensor_row_count(f, which, ns);
+  if (nw > 0 && f->cfg.sigma_range <= 0.0 && f->sens_range_on) return fail(XB_E_INVALID, "range measurement with sigma_range <= 0");
   f->slam_part_done = false;
   f->last_which = which;
   f->last_nslam = ns;
-  f->constructed_any = (n0 + n1 + ns) > 0;
+  f->last_nw = nw;
+  f->constructed_any = (n0 + n1 + ns + nw) > 0;
   if (!f->constructed_any) return XB_OK;
   if (f->n_poses < 1) return fail(XB_E_INVALID, "empty pose window");
   const size_t gbytes = sizeof(double) * (size_t)f->grows_pad * f->gcols_pad;
@@ -1225,14 +1292,14 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     int rcm = mm_prepare(f, which, l0, mp);
     if (rcm < 0) return rcm;
   }
-  if (ns > 0) {
+  if (ns + nw > 0) {
     // The SLAM rows and everything of the Kalman update that lives on their columns need only P and the estimates: they
     // are forked onto the side stream here and run next to the MSCKF track pipeline below.  Not with MSCKF-MSCKF matches:
     // their CI corrections change P between construct and apply (updater.cpp:84-97).
     const bool early = f->overlap && f->mm_G == 0 && !(f->cfg.multi_uav && which == 1) && f->asym_clones <= 1;
     CK(cudaMemcpyAsync(f->d_anchor, f->anchor.data(), sizeof(int) * f->F, cudaMemcpyHostToDevice, f->stream));
     if (early) {
-      const UpdateDims d = update_dims(f, ns);
+      const UpdateDims d = update_dims(f, ns, nw);
       int rc0 = set_omega(f);
       if (rc0) return rc0;
       CK(cudaMemsetAsync(f->d_T, 0, tall_bytes(d), f->stream));
@@ -1262,7 +1329,9 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
       // gates are part of constructUpdate (inlier masks are observable right after it); the tall-buffer part follows in apply
       StageTimer st_(f, ST_SLAMROWS);
       launch_slam_rows_on(f, f->stream, ns);
+      launch_sensor_rows_on(f, f->stream, ns);
     }
+    if (which == 0) f->sens_range_on = f->sens_sun_on = false;  // "don't reuse measurement" (vio_updater.cpp:381, 402)
   }
   if (n0 + n1 > 0) {
     {
@@ -1299,12 +1368,14 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   return XB_OK;
 }
 
-static UpdateDims update_dims(const xb_filter* f, int nslam) {
+static UpdateDims update_dims(const xb_filter* f, int nslam, int nw) {
   UpdateDims d;
   d.M = f->M; d.F = f->F; d.N = f->N;
   d.ms = 6 * f->M;
   d.nslam = nslam;
-  d.ns2 = 2 * nslam;
+  d.nw = nw;
+  d.wcols = f->d_wcols; d.wvals = f->d_wvals; d.wres = f->d_wres;
+  d.ns2 = 2 * nslam + nw;
   d.s_pad = pad32(d.ns2);
   d.ro = d.s_pad;
   d.m = d.ms + d.ns2;
@@ -1394,7 +1465,7 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   materialize(f);
   if (!f->constructed_any) return XB_OK;  // h.size() == 0 (updater.cpp:106)
-  const UpdateDims d = update_dims(f, f->last_nslam);
+  const UpdateDims d = update_dims(f, f->last_nslam, f->last_nw);
   const double var = f->cfg.sigma_img * f->cfg.sigma_img;
   const double* corr = f->corr_zero ? nullptr : f->d_corr;
   if (f->asym_clones > 1) {
@@ -1421,7 +1492,7 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
       f->side_pending = false;
     } else {
       CK(cudaMemsetAsync(f->d_T, 0, tall_bytes(d), f->stream));
-      if (d.nslam > 0) slam_phase(f, f->stream, d, ST_SIDE_SLAM, ST_SIDE_CHOL, 1, false);
+      if (d.ns2 > 0) slam_phase(f, f->stream, d, ST_SIDE_SLAM, ST_SIDE_CHOL, 1, false);
     }
     chol_from = d.s_pad;
     if (f->overlap) {
@@ -1958,6 +2029,9 @@ extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int ma
   else if (n == "H2") { src = f->d_H2; cnt = 9 * (size_t)f->l_newms.n; }
   else if (n == "B0") { src = f->d_B0; cnt = (size_t)(f->last_which ? f->l_short.n : f->l_msckf.n) * 3 * W; }
   else if (n == "slam_gamma") { src = f->d_sgamma; cnt = f->l_slam.n; }
+  else if (n == "range_gamma") { src = f->d_wgamma; cnt = 1; }
+  else if (n == "wide_vals") { src = f->d_wvals; cnt = XB_WMAX * XB_WNZ; }
+  else if (n == "wide_res") { src = f->d_wres; cnt = XB_WMAX; }
   else if (n == "slam_vals") { src = f->d_svals; cnt = 30 * (size_t)f->l_slam.n; }
   else if (n == "slam_res") { src = f->d_sres; cnt = 2 * (size_t)f->l_slam.n; }
   else if (n == "Tg") { src = f->d_Tg; cnt = (size_t)f->grows_pad * f->gcols_pad; }
@@ -2004,6 +2078,8 @@ extern "C" int xb_debug_read_int(xb_filter* f, const char* name, int* out, int m
   if (n == "inlier0") { src = f->d_inl0; cnt = f->last_which ? f->l_short.n : f->l_msckf.n; }
   else if (n == "inlier1") { src = f->d_inl1; cnt = f->l_newms.n; }
   else if (n == "slam_inlier") { src = f->d_sinl; cnt = f->l_slam.n; }
+  else if (n == "range_inlier") { src = f->d_winl; cnt = 1; }
+  else if (n == "wide_cols") { src = f->d_wcols; cnt = XB_WMAX * XB_WNZ; }
   else if (n == "slam_cols") { src = f->d_scols; cnt = 15 * (size_t)f->l_slam.n; }
   else if (n == "slot_gen") {
     cnt = std::min((size_t)max_ints, (size_t)f->NS);

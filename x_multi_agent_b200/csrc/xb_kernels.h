@@ -105,6 +105,32 @@ struct SlamParams {
 };
 void launch_slam_rows(cudaStream_t s, const SlamParams& sp);
 
+// Range (laser range finder) and sun-sensor rows of VioUpdater::constructUpdate (vio_updater.cpp:352-403;
+// range_update.cpp:61-265, solar_update.cpp:39-94): up to XB_WMAX "wide" sparse rows of XB_WNZ entries each, stored after
+// the SLAM row pairs of the compressed measurement.  Every row is scaled to the variance sigma_img^2 of the image rows:
+// by sigma_img / sigma_row when the reference keeps the row's own variance (rows <= N + 1: no QR compression), by 1 when
+// the reference's QR compression re-weights every row with sigma_img^2 (vio_updater.cpp:507-508).
+#define XB_WMAX 3
+#define XB_WNZ 36
+struct SensorParams {
+  const double* xv;
+  int M, N, n_poses;
+  const double* P;
+  const int* anchor;
+  int range_on, sun_on;
+  double range, pt_x, pt_y;   // RangeMeasurement::range, img_pt_n
+  int tri[3];                 // TrackManager::featureTriangleAtPoint: the facet's SLAM feature ids
+  double var_range, chi2_1;   // sigma_range^2, quantile(0.9, 1)
+  double w_range, w_sun;      // row scales (see above)
+  double sun_x, sun_y;        // SunAngleMeasurement, degrees
+  int* cols;      // [XB_WMAX][XB_WNZ]
+  double* vals;   // [XB_WMAX][XB_WNZ]
+  double* res;    // [XB_WMAX]
+  double* gamma;  // [1] range gate
+  int* inlier;    // [1]
+};
+void launch_sensor_rows(cudaStream_t s, const SensorParams& sp);
+
 struct GramParams {
   int M, n_poses;
   const double* B; int rowsB; int nzB; double* partB;
@@ -122,13 +148,17 @@ struct UpdateDims {
   int M, F, N;
   int ms;       // slab rows = 6M
   int nslam;    // SLAM tracks (2 rows each)
-  int ns2;      // 2*nslam
-  int s_pad;    // SLAM columns rounded up to 32 (0 without SLAM rows)
+  int nw;       // wide rows (range, sun sensor) after the SLAM row pairs: rows [2*nslam, 2*nslam + nw)
+  int ns2;      // 2*nslam + nw: real rows of the sparse part
+  int s_pad;    // sparse-part columns rounded up to 32 (0 without such rows)
   int ro;       // first slab column (= s_pad)
-  int m;        // real rows: ms + 2*nslam
+  int m;        // real rows: ms + ns2
   int m_pad;    // s_pad + ms rounded up to 32
   int n_pad;    // N rounded up to 32
   int ld;       // leading dimension of the tall buffer (= m_pad)
+  const int* wcols;     // [nw][XB_WNZ]
+  const double* wvals;  // [nw][XB_WNZ]
+  const double* wres;   // [nw]
 };
 // Tall-buffer pieces on the SLAM columns (no Rg needed) and on the slab columns (k_update.cu)
 void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P, const int* scols, const double* svals,

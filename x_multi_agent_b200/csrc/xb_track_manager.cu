@@ -366,4 +366,90 @@ XB_API int xb_tm_counts(const xb_track_manager* tm, int* n_slam, int* n_new_slam
   return XB_OK;
 }
 
+// The Delaunay facet of a point set that contains the query point (TrackManager::featureTriangleAtPoint,
+// track_manager.cpp:443-560).  The reference inserts the points into a cv::Subdiv2D over the rectangle
+// (-1, -1, w + 2, h + 2) and locates the query; Subdiv2D stores single-precision points and bounds the plane with three
+// virtual vertices at (rx + B, ry), (rx, ry + B), (rx - B, ry - B), B = 3 max(w + 2, h + 2): a facet that touches one of
+// them is not a facet of SLAM features (the reference then reports none).  The Delaunay triangulation of points in
+// general position is unique, so the same point set is triangulated here by Bowyer-Watson insertion; a query exactly on
+// an edge or a vertex takes the first facet found (the reference takes the one its edge walk ends in).
+// xy: n x 2 (distorted pixel coordinates).  Returns 3 and the vertex indexes, or 0 when there is no such facet.
+XB_API int xb_tm_delaunay_facet(const double* xy, int n, int img_width, int img_height, double qx, double qy, int* ids) {
+  if (!xy || !ids || n < 3) return 0;
+  struct P2 { double x, y; };
+  std::vector<P2> p(3 + (size_t)n);
+  const double rx = -1.0, ry = -1.0, B = 3.0 * std::max(img_width + 2, img_height + 2);
+  p[0] = {rx + B, ry};
+  p[1] = {rx, ry + B};
+  p[2] = {rx - B, ry - B};
+  for (int i = 0; i < n; ++i) p[3 + i] = {(double)(float)xy[2 * i], (double)(float)xy[2 * i + 1]};
+  struct Tri { int a, b, c; };
+  auto orient = [&](const P2& a, const P2& b, const P2& c) { return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x); };
+  std::vector<Tri> tris;
+  tris.push_back(orient(p[0], p[1], p[2]) > 0 ? Tri{0, 1, 2} : Tri{0, 2, 1});  // counter-clockwise
+  auto in_circle = [&](const Tri& t, const P2& d) {
+    const double ax = p[t.a].x - d.x, ay = p[t.a].y - d.y, bx = p[t.b].x - d.x, by = p[t.b].y - d.y;
+    const double cx = p[t.c].x - d.x, cy = p[t.c].y - d.y;
+    const double det = (ax * ax + ay * ay) * (bx * cy - cx * by) - (bx * bx + by * by) * (ax * cy - cx * ay) +
+                       (cx * cx + cy * cy) * (ax * by - bx * ay);
+    return det > 0.0;
+  };
+  std::vector<Tri> keep;
+  std::vector<std::pair<int, int>> edges;
+  for (int i = 3; i < 3 + n; ++i) {
+    bool dup = false;
+    for (int j = 0; j < i && !dup; ++j) dup = p[j].x == p[i].x && p[j].y == p[i].y;
+    if (dup) continue;  // Subdiv2D::insert returns the existing vertex
+    keep.clear();
+    edges.clear();
+    for (const Tri& t : tris) {
+      if (!in_circle(t, p[i])) { keep.push_back(t); continue; }
+      const int e[3][2] = {{t.a, t.b}, {t.b, t.c}, {t.c, t.a}};
+      for (const auto& ed : e) {
+        bool shared = false;
+        for (size_t k = 0; k < edges.size(); ++k)
+          if (edges[k].first == ed[1] && edges[k].second == ed[0]) { edges.erase(edges.begin() + k); shared = true; break; }
+        if (!shared) edges.emplace_back(ed[0], ed[1]);
+      }
+    }
+    for (const auto& ed : edges) keep.push_back({ed.first, ed.second, i});
+    tris.swap(keep);
+  }
+  const P2 q = {(double)(float)qx, (double)(float)qy};
+  for (const Tri& t : tris) {
+    if (orient(p[t.a], p[t.b], q) < 0 || orient(p[t.b], p[t.c], q) < 0 || orient(p[t.c], p[t.a], q) < 0) continue;
+    if (t.a < 3 || t.b < 3 || t.c < 3) return 0;  // bounded by a virtual vertex: not a facet of features
+    ids[0] = t.a - 3; ids[1] = t.b - 3; ids[2] = t.c - 3;
+    return 3;
+  }
+  return 0;
+}
+
+// Camera::undistort + Camera::normalize of one image point (camera.cpp:69-87, 95-101): how VIO::processMatchesMeasurement
+// turns the LRF image point into RangeMeasurement::img_pt_n (vio.cpp:288-294).  out = normalised (x, y).
+XB_API int xb_tm_normalize_point(const xb_track_manager* tm, double x_dist, double y_dist, double* out) {
+  if (!tm || !out) return XB_E_INVALID;
+  Feat f;
+  f.xd = x_dist;
+  f.yd = y_dist;
+  tm->undistort(f);
+  out[0] = f.x * tm->inv_fx - tm->cx_n;
+  out[1] = f.y * tm->inv_fy - tm->cy_n;
+  return XB_OK;
+}
+
+// TrackManager::featureTriangleAtPoint (track_manager.cpp:443-560) on the last observations of the persistent (SLAM)
+// tracks: the ids of the three SLAM features around the LRF image point (distorted pixel coordinates), or 0.
+XB_API int xb_tm_feature_triangle_at_point(const xb_track_manager* tm, double x_dist, double y_dist, int* ids) {
+  if (!tm || !ids) return XB_E_INVALID;
+  std::vector<double> xy;
+  xy.reserve(2 * tm->slam.size());
+  for (const Trk& t : tm->slam) {
+    if (t.f.empty()) return 0;
+    xy.push_back(t.f.back().xd);
+    xy.push_back(t.f.back().yd);
+  }
+  return xb_tm_delaunay_facet(xy.data(), (int)tm->slam.size(), (int)tm->cfg.img_width, (int)tm->cfg.img_height, x_dist, y_dist, ids);
+}
+
 }  // extern "C"

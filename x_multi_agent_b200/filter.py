@@ -152,6 +152,7 @@ class PackedMeasurement:
         self.keep.append(lost)
         self.c.n_lost = len(lost)
         self.c.lost_slam_idxs = L.iptr(lost)
+        self.range, self.sun_angle = getattr(m, "range", None), getattr(m, "sun_angle", None)
 
     def __del__(self):
         for lib, ptr in getattr(self, "_pinned", []):
@@ -218,6 +219,17 @@ class Filter:
         pm = m if isinstance(m, PackedMeasurement) else PackedMeasurement(m)
         self._pm = pm
         L.check(self.lib.xb_vio_set_measurement(self.h, C.byref(pm.c)))
+        rng, sun = pm.range, pm.sun_angle
+        if rng is not None or sun is not None:  # VioMeasurement::range / sun_angle (vio/types.h:300-305)
+            cr, cs = None, None
+            if rng is not None:
+                ids = list(rng.tr_feat_ids)
+                cr = L.XbRangeMeasurement(rng.timestamp, rng.range, (C.c_double * 2)(*rng.img_pt_n), len(ids),
+                                          (C.c_int * 3)(*(ids + [0] * 3)[:3]))
+            if sun is not None:
+                cs = L.XbSunAngleMeasurement(sun.timestamp, sun.x_angle, sun.y_angle)
+            L.check(self.lib.xb_vio_set_sensors(self.h, C.byref(cr) if cr is not None else None,
+                                                C.byref(cs) if cs is not None else None))
         return pm
 
     def process_update_measurement(self, want_state=True):

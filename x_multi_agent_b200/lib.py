@@ -39,6 +39,17 @@ class XbMeasurement(C.Structure):
                 ("lost_slam_idxs", c_int_p)]
 
 
+class XbRangeMeasurement(C.Structure):
+    """xb_range_measurement (include/xb200.h)."""
+    _fields_ = [("timestamp", C.c_double), ("range", C.c_double), ("img_pt_n", C.c_double * 2),
+                ("n_tr_feat_ids", C.c_int), ("tr_feat_ids", C.c_int * 3)]
+
+
+class XbSunAngleMeasurement(C.Structure):
+    """xb_sun_angle_measurement (include/xb200.h)."""
+    _fields_ = [("timestamp", C.c_double), ("x_angle", C.c_double), ("y_angle", C.c_double)]
+
+
 class XbPeerState(C.Structure):
     _fields_ = [("n_poses_max", C.c_int), ("n_features_max", C.c_int), ("positions", c_double_p),
                 ("orientations", c_double_p), ("features", c_double_p), ("anchor_idxs", c_int_p), ("cov", c_double_p),
@@ -76,6 +87,10 @@ SIGNATURES = {
     "xb_tm_remove_new_persistent_tracks": (C.c_int, [_VP, C.POINTER(C.c_uint), C.c_int]),
     "xb_tm_set_opp_ids": (C.c_int, [_VP, C.POINTER(C.c_ulonglong), C.c_int]),
     "xb_tm_counts": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "xb_tm_feature_triangle_at_point": (C.c_int, [_VP, C.c_double, C.c_double, C.POINTER(C.c_int)]),
+    "xb_tm_normalize_point": (C.c_int, [_VP, C.c_double, C.c_double, C.POINTER(C.c_double)]),
+    "xb_tm_delaunay_facet": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                       C.POINTER(C.c_int)]),
     "xb_default_config": (None, [C.POINTER(XbConfig)]),
     "xb_create": (C.c_int, [C.POINTER(XbConfig), C.POINTER(_VP)]),
     "xb_destroy": (C.c_int, [_VP]),
@@ -88,6 +103,7 @@ SIGNATURES = {
     "xb_ekf_initialize_from_state": (C.c_int, [_VP, c_double_p, c_double_p, C.c_int]),
     "xb_ekf_process_imu": (C.c_int, [_VP, C.c_double, C.c_uint, c_double_p, c_double_p, c_double_p]),
     "xb_vio_set_measurement": (C.c_int, [_VP, C.POINTER(XbMeasurement)]),
+    "xb_vio_set_sensors": (C.c_int, [_VP, C.POINTER(XbRangeMeasurement), C.POINTER(XbSunAngleMeasurement)]),
     "xb_host_alloc": (_VP, [C.c_size_t]),
     "xb_host_free": (None, [_VP]),
     "xb_ekf_process_update": (C.c_int, [_VP, c_double_p]),

@@ -65,6 +65,19 @@ class TrackManager:
         L.check(self.lib.xb_tm_counts(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def feature_triangle_at_point(self, x_dist, y_dist):
+        """TrackManager::featureTriangleAtPoint (track_manager.cpp:443-560): ids of the three SLAM features whose Delaunay
+        facet contains the image point, or []."""
+        ids = (C.c_int * 3)()
+        n = L.check(self.lib.xb_tm_feature_triangle_at_point(self.h, float(x_dist), float(y_dist), ids))
+        return [int(i) for i in ids] if n == 3 else []
+
+    def normalize_point(self, x_dist, y_dist):
+        """Camera::undistort + Camera::normalize (camera.cpp:69-101) of one distorted pixel position."""
+        out = (C.c_double * 2)()
+        L.check(self.lib.xb_tm_normalize_point(self.h, float(x_dist), float(y_dist), out))
+        return float(out[0]), float(out[1])
+
     def measurement(self, timestamp, n_poses_max):
         """The VioMeasurement-side seam: what VioUpdater::preProcess hands to the update (vio_updater.cpp:165-179)."""
         def tl(which, size_out=0):

@@ -6,11 +6,12 @@ attitude list -> TrackManager::manageTracks -> the five track lists).
 
 What runs where: parameters, the camera attitude list and the track management are host code (TrackManager: xb_tm_* in
 libxb200.so); everything from the track lists on is the device filter (Filter: xb_ekf_* / xb_vio_*).  Out of scope here, as
-in SURVEY 2: images (Tracker / KLT), range and sun-sensor measurements, place recognition.
+in SURVEY 2: images (Tracker / KLT), place recognition.  Range and sun-sensor measurements (setLastRangeMeasurement /
+setLastSunAngleMeasurement, vio.cpp:217-224) are forwarded to the filter.
 """
 import numpy as np
 
-from .filter import Filter, State
+from .filter import Filter, RangeMeasurement, State, SunAngleMeasurement
 from .track_manager import TrackManager
 
 # keys of the reference's YAML files (vio.cpp:576-707) -> (default, length); vectors are lists, quaternions are [w, x, y, z]
@@ -70,7 +71,7 @@ class VIO:
         if self.filter:
             self.filter.close()
         self.filter = Filter(p["n_poses_max"], p["n_slam_features_max"], n_slots=p["state_buffer_size"], device=device,
-                             sigma_img=p["sigma_img"], rho_0=p["rho_0"], sigma_rho_0=p["sigma_rho_0"], iekf_iter=p["iekf_iter"],
+                             sigma_img=p["sigma_img"], sigma_range=p["sigma_range"], rho_0=p["rho_0"], sigma_rho_0=p["sigma_rho_0"], iekf_iter=p["iekf_iter"],
                              min_track_length=p["min_track_length"],
                              n_w=p["n_w"], n_bw=p["n_bw"], n_a=p["n_a"], n_ba=p["n_ba"], g=tuple(p["g"]), **filter_kw)
         self.initialized = False
@@ -119,6 +120,29 @@ class VIO:
         qic = state.q_ic / np.linalg.norm(state.q_ic)
         return np.vstack([qa[n_poses - size_out:], _qmul(q, qic)[None]])
 
+    def set_last_range_measurement(self, timestamp, range_m):
+        """VIO::setLastRangeMeasurement (vio.cpp:217-219): kept until replaced, applied with every image after it."""
+        self.last_range = (float(timestamp), float(range_m))
+
+    def set_last_sun_angle_measurement(self, timestamp, x_angle, y_angle):
+        """VIO::setLastSunAngleMeasurement (vio.cpp:221-224)."""
+        self.last_sun = SunAngleMeasurement(float(timestamp), float(x_angle), float(y_angle))
+
+    def _sensors(self, m):
+        """The range / sun-angle members of the VioMeasurement (vio.cpp:288-298) and the facet lookup of
+        VioUpdater::constructUpdate (vio_updater.cpp:358-369: the hard-coded image point (320.5, 240.5))."""
+        p, tm = self.params, self.track_manager
+        rng = getattr(self, "last_range", None)
+        if rng is not None and rng[0] > 0.1 and m.slam_trks:
+            ids = tm.feature_triangle_at_point(320.5, 240.5)
+            if ids:
+                pt = tm.normalize_point((p["cam1_img_width"] + 1) / 2.0, (p["cam1_img_height"] + 1) / 2.0)
+                m.range = RangeMeasurement(rng[0], rng[1], pt, ids)
+        sun = getattr(self, "last_sun", None)
+        if sun is not None and sun.timestamp > -1:
+            m.sun_angle = sun
+        return m
+
     def process_matches_measurement(self, timestamp, seq, match_vector):
         """VIO::processMatchesMeasurement (vio.cpp:274-323): time correction, match import (skipped for the first image, before
         any pose is in the window), track management, Ekf::processUpdateMeasurement."""
@@ -135,7 +159,7 @@ class VIO:
             return None
         rots = self.camera_attitudes(state, flt.n_poses)
         tm.manage_tracks(mv, rots, p["n_poses_max"], p["n_slam_features_max"], p["min_track_length"])
-        flt.set_measurement(tm.measurement(t, p["n_poses_max"]))
+        flt.set_measurement(self._sensors(tm.measurement(t, p["n_poses_max"])))
         flt.updater_update()                           # Updater::update (updater.cpp:39-115)
         updated = flt.update_end()
         if updated is not None:
