@@ -278,6 +278,11 @@ XB_API int xb_ekf_last_update_slot(const xb_filter* f);
 
 /* ---- introspection for tests / profiling ------------------------------------------------------ */
 XB_API int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles); /* returns count */
+/* Test / measurement hook for the dense contraction kernels of Updater::applyUpdate (updater.cpp:124-136): C = beta C +
+ * alpha A B^T on host buffers (op 0: as the update dispatches it, 1: cp.async kernel, 2: symmetric downdate
+ * C <- (C + C^T)/2 - A A^T).  Returns 1 if the TMA-staged kernel ran; ms_out: average device time of `reps` launches. */
+XB_API int xb_debug_gemm(int op, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double alpha,
+                         double beta, double* C, int ldc, int reps, double* ms_out);
 XB_API int xb_debug_read_int(xb_filter* f, const char* name, int* out, int max_ints);
 /* per-stage CUDA-event timers on the filter's stream (bench.py roofline line); names/ms/counts must hold XB_MAX_STAGES entries */
 #define XB_MAX_STAGES 32

@@ -293,6 +293,12 @@ static bool small_gemm(int M, int N, int nz) { return (size_t)((M + 63) / 64) * 
 void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
+  if (g_use_mma && gemm_nt_tma(s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc)) return;  // large shapes: TMA-staged tiles
+  gemm_nt_cpasync(s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+void gemm_nt_cpasync(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                     double beta, double* C, int ldc) {
+  if (M <= 0 || N <= 0) return;
   if (g_use_mma) {
     dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM);
     k_gemm_mma<true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
@@ -1271,6 +1277,12 @@ void downdate_f64_range(cudaStream_t s, const double* Pin, double* Pout, int n, 
                         int kend, int do_sym, int do_tail, const int* omega_inv, const double* Zb, const double* Yb,
                         const double* Qb) {
   const int nt = (n + D3 - 1) / D3;
+  // large covariances: TMA-staged 128 x 64 tiles (k_gemm_tma.cu).  Without do_sym the input is symmetric to the bit (it is
+  // the output of the do_sym pass), so symmetrising again changes nothing.
+  if (g_use_mma && downdate_sym_tma(s, n, kend - kbeg, T + (size_t)m_pad * m_pad + kbeg, m_pad, Pin, Pout, n,
+                                    do_tail ? omega_inv : nullptr, do_tail ? Zb : nullptr, do_tail ? Yb : nullptr,
+                                    do_tail ? Qb : nullptr))
+    return;
   if (g_use_mma)
     k_downdate_mma<<<nt * (nt + 1) / 2, 128, 0, s>>>(Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
                                                      omega_inv, Zb, Yb, Qb);

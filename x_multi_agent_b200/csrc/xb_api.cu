@@ -2016,6 +2016,48 @@ extern "C" int xb_mm_last_gates(xb_filter* f, int which, double* out, int max_gr
 }
 
 // ---- introspection ----------------------------------------------------------------------------------------------------------
+// Test / measurement hook for the dense contraction kernels: C = beta C + alpha A B^T (A: M x K, B: N x K, row-major, host
+// buffers).  op 0: gemm_nt as the update calls it (TMA-staged tiles when the shape qualifies), 1: the cp.async kernel,
+// 2: symmetric downdate C <- (C + C^T)/2 - A A^T through the TMA kernel (M == N, B ignored).  Returns 1 when the TMA kernel
+// ran (op 0, 2), 0 otherwise; ms_out (optional) receives the average device time of `reps` launches.
+extern "C" int xb_debug_gemm(int op, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double alpha,
+                             double beta, double* C, int ldc, int reps, double* ms_out) {
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr, *dC0 = nullptr;
+  const size_t ba = sizeof(double) * (size_t)M * lda, bb = sizeof(double) * (size_t)N * ldb, bc = sizeof(double) * (size_t)M * ldc;
+  if (cudaMalloc(&dA, ba) || cudaMalloc(&dB, std::max<size_t>(bb, 8)) || cudaMalloc(&dC, bc) || cudaMalloc(&dC0, bc))
+    return fail(XB_E_CUDA, "xb_debug_gemm: allocation");
+  CK(cudaMemcpy(dA, A, ba, cudaMemcpyHostToDevice));
+  if (op != 2) CK(cudaMemcpy(dB, B, bb, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dC0, C, bc, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int used_tma = 0;
+  float ms_tot = 0.f;
+  for (int r = 0; r < std::max(1, reps); ++r) {
+    CK(cudaMemcpy(dC, dC0, bc, cudaMemcpyDeviceToDevice));
+    CK(cudaEventRecord(e0, 0));
+    if (op == 0) {
+      used_tma = gemm_nt_tma(0, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc) ? 1 : 0;
+      if (!used_tma) gemm_nt_cpasync(0, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc);
+    } else if (op == 1) {
+      gemm_nt_cpasync(0, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc);
+    } else {
+      used_tma = downdate_sym_tma(0, M, K, dA, lda, dC, dC, ldc) ? 1 : 0;
+    }
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 || reps <= 1) ms_tot += ms;
+  }
+  if (ms_out) *ms_out = ms_tot / std::max(1, reps > 1 ? reps - 1 : 1);
+  CK(cudaMemcpy(C, dC, bc, cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dC0);
+  return used_tma;
+}
+
 extern "C" int xb_debug_read(xb_filter* f, const char* name, double* out, int max_doubles) {
   const std::string n(name);
   const double* src = nullptr;

@@ -25,6 +25,14 @@ void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, in
 void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ, int second = 0);
 
 // ---- dense linear algebra -----------------------------------------------------------------------
+// TMA-staged DMMA tiles for large shapes (k_gemm_tma.cu); return false when the shape / alignment does not qualify
+bool gemm_nt_tma(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+                 double* C, int ldc);
+void gemm_nt_cpasync(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                     double beta, double* C, int ldc);
+bool downdate_sym_tma(cudaStream_t s, int n, int K, const double* W, int ldw, const double* Pin, double* Pout, int ldp,
+                      const int* omega_inv = nullptr, const double* Zb = nullptr, const double* Yb = nullptr,
+                      const double* Qb = nullptr);
 void gemm_nt(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
              double beta, double* C, int ldc);
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,

@@ -91,6 +91,8 @@ SIGNATURES = {
     "xb_tm_normalize_point": (C.c_int, [_VP, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "xb_tm_delaunay_facet": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                        C.POINTER(C.c_int)]),
+    "xb_debug_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, C.c_double,
+                                C.c_double, c_double_p, C.c_int, C.c_int, c_double_p]),
     "xb_default_config": (None, [C.POINTER(XbConfig)]),
     "xb_create": (C.c_int, [C.POINTER(XbConfig), C.POINTER(_VP)]),
     "xb_destroy": (C.c_int, [_VP]),
