@@ -24,7 +24,7 @@ def _gemm(op, A, B, Cm, alpha, beta, reps=1):
     return Cm, used, ms.value
 
 
-@pytest.mark.parametrize("M,N,K", [(3136, 320, 1600), (1000, 250, 130), (2715 + 96, 333, 72), (4096, 64, 64)])
+@pytest.mark.parametrize("M,N,K", [(3136, 320, 1600), (1000, 250, 130), (2715 + 96, 333, 72), (4096, 200, 64), (12288, 64, 64)])
 def test_tma_gemm_matches_numpy(M, N, K):
     rng = np.random.default_rng(M + N + K)
     lda = K + (K % 2)          # TMA: 16-byte aligned rows
@@ -35,14 +35,15 @@ def test_tma_gemm_matches_numpy(M, N, K):
     want[:, :N] = 0.5 * C0[:, :N] - 1.25 * A[:, :K] @ B[:, :K].T
     got, used, _ = _gemm(0, A[:, :lda], B[:, :lda], C0, -1.25, 0.5)
     # the debug entry passes K = lda; the padding columns are zero
-    assert used == 1, "shape did not take the TMA path"
+    big = ((M + 127) // 128) * ((N + 63) // 64) >= 96    # smaller problems stay on the cp.async tiles (launch latency)
+    assert used == int(big), "unexpected kernel choice"
     assert np.abs(got[:, :N] - want[:, :N]).max() < 1e-11 * K
     assert np.array_equal(got[:, N:], C0[:, N:])
     ref, used1, _ = _gemm(1, A[:, :lda], B[:, :lda], C0, -1.25, 0.5)
     assert used1 == 0 and np.abs(ref[:, :N] - want[:, :N]).max() < 1e-11 * K
 
 
-@pytest.mark.parametrize("n,K", [(2715, 1600), (2715, 320), (1111, 100)])
+@pytest.mark.parametrize("n,K", [(2715, 1600), (2715, 320), (1301, 100)])
 def test_tma_symmetric_downdate_matches_numpy(n, K):
     rng = np.random.default_rng(n + K)
     ldw = K + (K % 2)

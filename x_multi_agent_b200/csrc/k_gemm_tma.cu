@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(288) k_gemm_tma(const __grid_constant__ CUtens
                                                   int M, int N, int K, double alpha, double beta, const double* Cin, double* __restrict__ C,
                                                   int ldc, const __grid_constant__ TmaTail tail, int ntail,
                                                   const int* __restrict__ omega_inv, const double* __restrict__ Qb) {
+  XB_PDL_LONG();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(base);
@@ -214,12 +215,7 @@ static bool make_map(CUtensorMap* tm, const double* base, int rows, int K, int l
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 static bool tma_ok(const double* A, int lda, const double* B, int ldb) {
-  // opt-in until the GPU parity run of this kernel is green (XB_TMA=1); XB_NO_TMA=1 always disables
-  static const bool off = [] {
-    const char* e = getenv("XB_NO_TMA");
-    const char* on = getenv("XB_TMA");
-    return (e && e[0] == '1') || !(on && on[0] == '1');
-  }();
+  static const bool off = [] { const char* e = getenv("XB_NO_TMA"); return e && e[0] == '1'; }();  // A/B switch
   return !off && encode_fn() && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && lda % 2 == 0 && ldb % 2 == 0;
 }
 static bool g_attr_set = false;
@@ -237,7 +233,7 @@ bool gemm_nt_tma(cudaStream_t s, int M, int N, int K, double alpha, const double
   if (!g_attr_set) { set_attr<false>(); set_attr<true>(); g_attr_set = true; }
   dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM);
   static const TmaTail no_tail{};
-  k_gemm_tma<false><<<grid, 288, TG_SMEM, s>>>(ta, tb, M, N, K, alpha, beta, nullptr, C, ldc, no_tail, 0, nullptr, nullptr);
+  XB_LAUNCH((k_gemm_tma<false>), grid, 288, TG_SMEM, s, ta, tb, M, N, K, alpha, beta, nullptr, C, ldc, no_tail, 0, nullptr, nullptr);
   count_launch();
   return true;
 }
@@ -259,7 +255,7 @@ bool downdate_sym_tma(cudaStream_t s, int n, int K, const double* W, int ldw, co
     ntail = 4;
   }
   if (!g_attr_set) { set_attr<false>(); set_attr<true>(); g_attr_set = true; }
-  k_gemm_tma<true><<<nb * (nb + 1), 288, TG_SMEM, s>>>(ta, tb, n, n, K, -1.0, 0.0, Pin, Pout, ldp, tail, ntail, omega_inv, Qb);
+  XB_LAUNCH((k_gemm_tma<true>), nb * (nb + 1), 288, TG_SMEM, s, ta, tb, n, n, K, -1.0, 0.0, Pin, Pout, ldp, tail, ntail, omega_inv, Qb);
   count_launch();
   return true;
 }

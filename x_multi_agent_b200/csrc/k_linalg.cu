@@ -24,6 +24,7 @@ template <bool TRANS_B>
 __global__ void __launch_bounds__(256) k_gemm(int M, int N, int Kfull, double alpha, const double* __restrict__ A,
                                               int lda, const double* __restrict__ B, int ldb, double beta,
                                               double* __restrict__ C, int ldc, int kchunk, size_t strideC) {
+  XB_PDL_SHORT();
   __shared__ double As[16][64 + 4];
   __shared__ double Bs[16][64 + 4];
   // split-K: blockIdx.z handles k in [z*kchunk, min(K, (z+1)*kchunk)) and writes its own partial C + z*strideC
@@ -100,6 +101,7 @@ template <bool TRANS_B>
 __global__ void __launch_bounds__(128) k_gemm32(int M, int N, int Kfull, double alpha, const double* __restrict__ A,
                                                 int lda, const double* __restrict__ B, int ldb, double beta,
                                                 double* __restrict__ C, int ldc, int kchunk, size_t strideC) {
+  XB_PDL_SHORT();
   __shared__ __align__(16) double As[32][32 + 2];  // [k][row]
   __shared__ __align__(16) double Bs[32][32 + 4];  // [k][col]
   const int kbeg = blockIdx.z * kchunk;
@@ -195,6 +197,7 @@ template <bool TRANS_B, bool TRANS_A = false>  // TRANS_A: A is given k-major, [
 __global__ void __launch_bounds__(128) k_gemm_mma(int M, int N, int Kfull, double alpha, const double* __restrict__ A, int lda,
                                                   const double* __restrict__ B, int ldb, double beta, double* __restrict__ C,
                                                   int ldc, int kchunk, size_t strideC) {
+  XB_PDL_SHORT();
   __shared__ double As[MG_ST][TRANS_A ? MG_BK * MG_LDM : MG_BM * MG_LDK];
   __shared__ double Bs[MG_ST][TRANS_B ? MG_BN * MG_LDK : MG_BK * MG_LDN];
   const int kbeg = blockIdx.z * kchunk;
@@ -301,13 +304,13 @@ void gemm_nt_cpasync(cudaStream_t s, int M, int N, int K, double alpha, const do
   if (M <= 0 || N <= 0) return;
   if (g_use_mma) {
     dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM);
-    k_gemm_mma<true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+    XB_LAUNCH((k_gemm_mma<true>), grid, 128, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   } else if (small_gemm(M, N, 1)) {
     dim3 grid((N + 31) / 32, (M + 31) / 32);
-    k_gemm32<true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+    XB_LAUNCH((k_gemm32<true>), grid, 128, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   } else {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+    XB_LAUNCH((k_gemm<true>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   }
   count_launch();
 }
@@ -317,15 +320,15 @@ void gemm_nt_splitk(cudaStream_t s, int M, int N, int K, const double* A, int ld
   if (g_use_mma) {
     const int kchunk = ((K + nz - 1) / nz + MG_BK - 1) / MG_BK * MG_BK;
     dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM, nz);
-    k_gemm_mma<true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+    XB_LAUNCH((k_gemm_mma<true>), grid, 128, 0, s, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   } else if (small_gemm(M, N, nz)) {
     const int kchunk = ((K + nz - 1) / nz + 31) / 32 * 32;
     dim3 grid((N + 31) / 32, (M + 31) / 32, nz);
-    k_gemm32<true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+    XB_LAUNCH((k_gemm32<true>), grid, 128, 0, s, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   } else {
     const int kchunk = ((K + nz - 1) / nz + 15) / 16 * 16;
     dim3 grid((N + 63) / 64, (M + 63) / 64, nz);
-    k_gemm<true><<<grid, 256, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+    XB_LAUNCH((k_gemm<true>), grid, 256, 0, s, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   }
   count_launch();
 }
@@ -334,7 +337,7 @@ void gemm_tn_splitk(cudaStream_t s, int M, int N, int K, const double* A, int ld
                     size_t strideC, int nz) {
   const int kchunk = ((K + nz - 1) / nz + MG_BK - 1) / MG_BK * MG_BK;
   dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM, nz);
-  k_gemm_mma<false, true><<<grid, 128, 0, s>>>(M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
+  XB_LAUNCH((k_gemm_mma<false, true>), grid, 128, 0, s, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, kchunk, strideC);
   count_launch();
 }
 bool gemm_uses_tensor_cores() { return g_use_mma; }
@@ -343,7 +346,7 @@ void gemm_tn(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
              double* C, int ldc) {
   if (M <= 0 || N <= 0) return;
   dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM);
-  k_gemm_mma<false, true><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+  XB_LAUNCH((k_gemm_mma<false, true>), grid, 128, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   count_launch();
 }
 void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
@@ -351,13 +354,13 @@ void gemm_nn(cudaStream_t s, int M, int N, int K, double alpha, const double* A,
   if (M <= 0 || N <= 0) return;
   if (g_use_mma) {
     dim3 grid((N + MG_BN - 1) / MG_BN, (M + MG_BM - 1) / MG_BM);
-    k_gemm_mma<false><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+    XB_LAUNCH((k_gemm_mma<false>), grid, 128, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   } else if (small_gemm(M, N, 1)) {
     dim3 grid((N + 31) / 32, (M + 31) / 32);
-    k_gemm32<false><<<grid, 128, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+    XB_LAUNCH((k_gemm32<false>), grid, 128, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   } else {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    k_gemm<false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
+    XB_LAUNCH((k_gemm<false>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, K, 0);
   }
   count_launch();
 }
@@ -670,6 +673,7 @@ __global__ void __launch_bounds__(CP_THREADS, 4) k_tallchol(double* __restrict__
                                                          int* __restrict__ flags, int* __restrict__ err, double piv_tol,
                                                          const double* __restrict__ diag0, long long* __restrict__ trace,
                                                          int epoch) {
+  XB_PDL_LONG();
   extern __shared__ double tc_smem[];
   Tile Ds = (Tile)tc_smem, Ws = (Tile)(tc_smem + 2 * TC_TILE_DOUBLES), Ls = (Tile)(tc_smem + 3 * TC_TILE_DOUBLES);
   Tile Es[2] = {(Tile)(tc_smem + 1 * TC_TILE_DOUBLES), (Tile)(tc_smem + 4 * TC_TILE_DOUBLES)};
@@ -899,6 +903,7 @@ void tallchol(cudaStream_t s, double* T, int ld, int rows_pad, int cols_pad, int
 __global__ void __launch_bounds__(256) k_downdate(double* __restrict__ P, int n, const double* __restrict__ T, int m_pad,
                                                   int n_pad, const int* __restrict__ omega_inv, const double* __restrict__ Zb,
                                                   const double* __restrict__ Yb, const double* __restrict__ Qb) {
+  XB_PDL_LONG();
   const int nt = (n + DT - 1) / DT;
   int b = blockIdx.x, I = 0;
   while (b >= nt - I) { b -= nt - I; ++I; }
@@ -1041,6 +1046,7 @@ __global__ void __launch_bounds__(128) k_downdate32(const double* __restrict__ P
                                                     int do_tail, const int* __restrict__ omega_inv,
                                                     const double* __restrict__ Zb, const double* __restrict__ Yb,
                                                     const double* __restrict__ Qb) {
+  XB_PDL_LONG();
   const int nt = (n + D3 - 1) / D3;
   int b = blockIdx.x, I = 0;
   while (b >= nt - I) { b -= nt - I; ++I; }
@@ -1169,6 +1175,7 @@ __global__ void __launch_bounds__(128) k_downdate_mma(const double* __restrict__
                                                       int do_tail, const int* __restrict__ omega_inv,
                                                       const double* __restrict__ Zb, const double* __restrict__ Yb,
                                                       const double* __restrict__ Qb) {
+  XB_PDL_LONG();
   const int nt = (n + D3 - 1) / D3;
   int b = blockIdx.x, I = 0;
   while (b >= nt - I) { b -= nt - I; ++I; }
@@ -1284,10 +1291,10 @@ void downdate_f64_range(cudaStream_t s, const double* Pin, double* Pout, int n, 
                                     do_tail ? Qb : nullptr))
     return;
   if (g_use_mma)
-    k_downdate_mma<<<nt * (nt + 1) / 2, 128, 0, s>>>(Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
+    XB_LAUNCH(k_downdate_mma, nt * (nt + 1) / 2, 128, 0, s, Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
                                                      omega_inv, Zb, Yb, Qb);
   else
-    k_downdate32<<<nt * (nt + 1) / 2, 128, 0, s>>>(Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
+    XB_LAUNCH(k_downdate32, nt * (nt + 1) / 2, 128, 0, s, Pin, Pout, n, T + (size_t)m_pad * m_pad, m_pad, kbeg, kend, do_sym, do_tail,
                                                    omega_inv, Zb, Yb, Qb);
   count_launch();
 }
@@ -1299,12 +1306,13 @@ void downdate_f64(cudaStream_t s, double* P, int n, const double* T, int m_pad, 
     downdate_f64_range(s, P, P, n, T, m_pad, n_pad, 0, m_pad, 1, 1, omega_inv, Zb, Yb, Qb);
     return;
   }
-  k_downdate<<<nt * (nt + 1) / 2, 256, 0, s>>>(P, n, T, m_pad, n_pad, omega_inv, Zb, Yb, Qb);
+  XB_LAUNCH(k_downdate, nt * (nt + 1) / 2, 256, 0, s, P, n, T, m_pad, n_pad, omega_inv, Zb, Yb, Qb);
   count_launch();
 }
 
 // P <- (P + P^T)/2 only (cov_update path with an empty measurement never reaches here; used by applyCI glue).
 __global__ void k_symmetrise(double* __restrict__ P, int n) {
+  XB_PDL_SHORT();
   const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
   if (i < n && j < n && i < j) {
     const double v = 0.5 * (P[(size_t)i * n + j] + P[(size_t)j * n + i]);
@@ -1314,13 +1322,14 @@ __global__ void k_symmetrise(double* __restrict__ P, int n) {
 }
 void symmetrise(cudaStream_t s, double* P, int n) {
   dim3 g((n + 15) / 16, (n + 15) / 16), b(16, 16);
-  k_symmetrise<<<g, b, 0, s>>>(P, n);
+  XB_LAUNCH(k_symmetrise, g, b, 0, s, P, n);
   count_launch();
 }
 
 // y[r] = sum_k A[r, k] * x[k]   (one warp per row)
 __global__ void k_gemv(int rows, int cols, const double* __restrict__ A, int lda, const double* __restrict__ x,
                        double* __restrict__ y) {
+  XB_PDL_SHORT();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= rows) return;
   double s = 0.0;
@@ -1330,12 +1339,13 @@ __global__ void k_gemv(int rows, int cols, const double* __restrict__ A, int lda
 }
 void gemv(cudaStream_t s, int rows, int cols, const double* A, int lda, const double* x, double* y) {
   if (rows <= 0) return;
-  k_gemv<<<(rows * 32 + 127) / 128, 128, 0, s>>>(rows, cols, A, lda, x, y);
+  XB_LAUNCH(k_gemv, (rows * 32 + 127) / 128, 128, 0, s, rows, cols, A, lda, x, y);
   count_launch();
 }
 
 // out (cols x rows) = in (rows x cols)^T
 __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int rows, int cols) {
+  XB_PDL_SHORT();
   __shared__ double tile[32][33];
   int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
   for (int k = 0; k < 32; k += 8)
@@ -1348,7 +1358,7 @@ __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ 
 }
 void transpose(cudaStream_t s, const double* in, double* out, int rows, int cols) {
   dim3 g((cols + 31) / 32, (rows + 31) / 32), b(32, 8);
-  k_transpose<<<g, b, 0, s>>>(in, out, rows, cols);
+  XB_LAUNCH(k_transpose, g, b, 0, s, in, out, rows, cols);
   count_launch();
 }
 

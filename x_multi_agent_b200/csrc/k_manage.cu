@@ -21,6 +21,7 @@ struct ManageDev {
 };
 
 __global__ void __launch_bounds__(128) k_manage_prep(ManageDev md, double* __restrict__ xv) {
+  XB_PDL_SHORT();
   const int t = threadIdx.x, nt = blockDim.x;
   const int M = md.M, F = md.F;
   double* parr = xv + XV_ARR;
@@ -150,6 +151,7 @@ struct PSrc {
 // measurement, state_manager.cpp:273-349 then copies unsymmetric blocks from clone to clone).
 __global__ void k_manage_T(int N, int n_comp, const int* __restrict__ ccols, const double* __restrict__ cvals, PSrc P,
                            double* __restrict__ T, double* __restrict__ T2, int general) {
+  XB_PDL_SHORT();
   const int ci = blockIdx.y;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= n_comp || b >= N) return;
@@ -168,6 +170,7 @@ __global__ void k_manage_T(int N, int n_comp, const int* __restrict__ ccols, con
 __global__ void __launch_bounds__(256) k_manage_apply(int N, const int* __restrict__ rowmap, const int* __restrict__ ccols,
                                                        const double* __restrict__ cvals, PSrc P, const double* __restrict__ T,
                                                        const double* __restrict__ T2, double* __restrict__ Pn, int general) {
+  XB_PDL_SHORT();
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
   if (j >= N) return;
@@ -199,21 +202,22 @@ void launch_manage_dev(cudaStream_t s, int M, int F, int N, int n_poses, int n_f
                        double* d_cvals, double* d_scratch, double* xv, const double* Pold, double* Pnew, double* Tm,
                        double* T2, const double* strip, const double* gen, const double* strip2, int general) {
   ManageDev md{M, F, N, n_poses, n_features, slide, n_reanch, d_feat_src, d_reanch, d_cvals, d_scratch};
-  k_manage_prep<<<1, 128, 0, s>>>(md, xv);
+  XB_LAUNCH(k_manage_prep, 1, 128, 0, s, md, xv);
   count_launch();
   const PSrc src{Pold, strip, strip2 ? strip2 : strip, gen, N};  // Pold == nullptr: read the slot's strips + generation directly
   const int n_comp = 6 + 3 * n_reanch;
   dim3 gt((N + 127) / 128, n_comp);
-  k_manage_T<<<gt, 128, 0, s>>>(N, n_comp, d_ccols, d_cvals, src, Tm, T2, general);
+  XB_LAUNCH(k_manage_T, gt, 128, 0, s, N, n_comp, d_ccols, d_cvals, src, Tm, T2, general);
   count_launch();
   dim3 ga((N + 31) / 32, (N + 31) / 32);
-  k_manage_apply<<<ga, 256, 0, s>>>(N, d_rowmap, d_ccols, d_cvals, src, Tm, T2, Pnew, general);
+  XB_LAUNCH(k_manage_apply, ga, 256, 0, s, N, d_rowmap, d_ccols, d_cvals, src, Tm, T2, Pnew, general);
   count_launch();
 }
 
 // ---- assemble / extract: strip <-> full covariance ------------------------------------------------
 __global__ void k_assemble(int N, const double* __restrict__ strip, const double* __restrict__ strip2,
                            const double* __restrict__ Pg, double* __restrict__ Pw) {
+  XB_PDL_SHORT();
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (j >= N) return;
   double v;
@@ -224,17 +228,18 @@ __global__ void k_assemble(int N, const double* __restrict__ strip, const double
 }
 void launch_assemble(cudaStream_t s, int N, const double* strip, const double* Pgen, double* Pwork, const double* strip2) {
   dim3 g((N + 255) / 256, N);
-  k_assemble<<<g, 256, 0, s>>>(N, strip, strip2 ? strip2 : strip, Pgen, Pwork);
+  XB_LAUNCH(k_assemble, g, 256, 0, s, N, strip, strip2 ? strip2 : strip, Pgen, Pwork);
   count_launch();
 }
 // strip2[r][j] = Pwork[j][r]: the first 15 columns of the work covariance, stored like the row strip
 __global__ void k_extract_cols(int N, const double* __restrict__ Pw, double* __restrict__ strip2) {
+  XB_PDL_SHORT();
   const int j = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (j < N) strip2[(size_t)r * N + j] = Pw[(size_t)j * N + r];
 }
 void launch_extract_strip2(cudaStream_t s, int N, const double* Pwork, double* strip2) {
   dim3 g((N + 255) / 256, XB_CORE);
-  k_extract_cols<<<g, 256, 0, s>>>(N, Pwork, strip2);
+  XB_LAUNCH(k_extract_cols, g, 256, 0, s, N, Pwork, strip2);
   count_launch();
 }
 void launch_extract_strip(cudaStream_t s, int N, const double* Pwork, double* strip) {
@@ -244,6 +249,7 @@ void launch_extract_strip(cudaStream_t s, int N, const double* Pwork, double* st
 // ---- feature initialisation ------------------------------------------------------------------------
 // E[3t+r][b] = (H2_t^-1 H1_t)[r][b]  (3n x 6M);  f_new = f - E corr_pose + H2^-1 r1   (state_manager.cpp:151-174)
 __global__ void k_featinit_E(FeatInitParams fp, double* __restrict__ E, double* __restrict__ H2inv, double* __restrict__ xv) {
+  XB_PDL_SHORT();
   const int t = blockIdx.x;
   const int W = 6 * fp.M + 1;
   __shared__ double Hi[9];
@@ -277,6 +283,7 @@ __global__ void k_featinit_E(FeatInitParams fp, double* __restrict__ E, double* 
 // write cross and diagonal blocks (state_manager.cpp:216-219): rows/cols ns..ns+3n
 __global__ void k_featinit_write(int N, int ns, int n3, const double* __restrict__ C, const double* __restrict__ Pdd,
                                  const double* __restrict__ H2inv, double var, double* __restrict__ P) {
+  XB_PDL_SHORT();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (c >= N || r >= n3) return;
   double v;
@@ -302,19 +309,20 @@ void launch_init_msckf_slam(cudaStream_t s, const FeatInitParams& fp, double* xv
   double* H2inv = E + (size_t)n3 * K6;       // n_new x 9
   double* C = H2inv + 9 * (size_t)fp.n_new;  // n3 x N
   double* Pdd = C + (size_t)n3 * N;          // n3 x n3
-  k_featinit_E<<<fp.n_new, 128, 0, s>>>(fp, E, H2inv, xv);
+  XB_LAUNCH(k_featinit_E, fp.n_new, 128, 0, s, fp, E, H2inv, xv);
   count_launch();
   gemm_nn(s, n3, N, K6, 1.0, E, K6, P + (size_t)XB_CORE * N, N, 0.0, C, N);
   gemm_nt(s, n3, n3, K6, 1.0, C + XB_CORE, N, E, K6, 0.0, Pdd, n3);
   const int ns = XB_CORE + 6 * fp.M + 3 * fp.n_features;
   dim3 g((N + 127) / 128, n3);
-  k_featinit_write<<<g, 128, 0, s>>>(N, ns, n3, C, Pdd, H2inv, fp.var_img, P);
+  XB_LAUNCH(k_featinit_write, g, 128, 0, s, N, ns, n3, C, Pdd, H2inv, fp.var_img, P);
   count_launch();
 }
 
 // state_manager.cpp:176-198 + slam_update.cpp:216-242
 __global__ void k_init_std(int M, int N, int n_features, int n_new, const int* __restrict__ off, const double* __restrict__ obs,
                            double rho0, double var_img, double var_rho0, double* __restrict__ xv, double* __restrict__ P) {
+  XB_PDL_SHORT();
   const int ns = XB_CORE + 6 * M + 3 * n_features;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int n3 = 3 * n_new;
@@ -335,12 +343,13 @@ void launch_init_std_slam(cudaStream_t s, int M, int F, int N, int n_features, i
                           const double* obs, double rho0, double var_img, double var_rho0, double* xv, double* P) {
   (void)F;
   const int tot = 3 * n_new * N;
-  k_init_std<<<(tot + 255) / 256, 256, 0, s>>>(M, N, n_features, n_new, off, obs, rho0, var_img, var_rho0, xv, P);
+  XB_LAUNCH(k_init_std, (tot + 255) / 256, 256, 0, s, M, N, n_features, n_new, off, obs, rho0, var_img, var_rho0, xv, P);
   count_launch();
 }
 
 // P_j: scale listed 3x3 diagonal blocks by w (msckf_update.cpp:258-267, multi_slam_update.cpp:229-239)
 __global__ void k_scale_blocks(double* P, int N, const int* cols, int n_blocks, double w) {
+  XB_PDL_SHORT();
   const int b = blockIdx.x, e = threadIdx.x;
   if (b >= n_blocks || e >= 9) return;
   const int c = cols[b];
@@ -348,16 +357,17 @@ __global__ void k_scale_blocks(double* P, int N, const int* cols, int n_blocks, 
 }
 void launch_scale_blocks(cudaStream_t s, double* P, int N, const int* cols, int n_blocks, double w) {
   if (n_blocks <= 0) return;
-  k_scale_blocks<<<n_blocks, 32, 0, s>>>(P, N, cols, n_blocks, w);
+  XB_LAUNCH(k_scale_blocks, n_blocks, 32, 0, s, P, N, cols, n_blocks, w);
   count_launch();
 }
 
 __global__ void k_add_diag(double* A, int ld, int n, double v) {
+  XB_PDL_SHORT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) A[(size_t)i * ld + i] += v;
 }
 void launch_add_diag(cudaStream_t s, double* A, int ld, int n, double v) {
-  k_add_diag<<<(n + 255) / 256, 256, 0, s>>>(A, ld, n, v);
+  XB_LAUNCH(k_add_diag, (n + 255) / 256, 256, 0, s, A, ld, n, v);
   count_launch();
 }
 

@@ -99,6 +99,7 @@ __device__ __noinline__ void state_transition_call(double dt, const double* w, c
 // (47 us for 10 steps, the longest item next to the covariance downdate).
 __global__ void __launch_bounds__(512) k_prop_means(double* __restrict__ xv, int LX, int NS, int start, int n_steps,
                                                     ImuSample in, PropParams pp, double* __restrict__ FQ) {
+  XB_PDL_SHORT();
   __shared__ double imu[129][8];  // slots start .. start + k: w_m[3], a_m[3], time
   __shared__ double Dm[128][16];  // quaternion-integrator matrices of the steps 1 .. k
   __shared__ double wsc[16][80];  // per-warp scratch of the integrator: O1, O0, A, Ak, Tm4
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(512) k_prop_means(double* __restrict__ xv, int
 // is the transpose of P_ii and therefore takes Q_d^T.
 __global__ void __launch_bounds__(128) k_prop_strips(double* __restrict__ strip, int N, int NS, int start, int n_steps,
                                                      const double* __restrict__ FQ, int second) {
+  XB_PDL_SHORT();
   // F_d (and Q_d for the core block) of several steps are brought into shared memory at once: one global-memory latency
   // per 8 / 16 steps of the chain instead of one per step
   __shared__ double buf[3600], Pa[225], Pb[225];
@@ -350,6 +352,7 @@ __device__ __noinline__ void state_transition_call(double dt, const double* w, c
 // single sample) is cut to its longest partition.
 __global__ void __launch_bounds__(512) k_prop_step(double* __restrict__ xv, int LX, double* __restrict__ strip, int N, int NS,
                                                    int start, ImuSample in, PropParams pp, double* __restrict__ FQ) {
+  XB_PDL_LONG();
   __shared__ double x0s[32], x1s[32], O1[16], O0[16], A[16], Ak[16], Tm4[16], Dm[16], w1s[3], a1s[3], Cs[9];
   __shared__ double Fs[225], Qs[225], Pii[225], Tm[225], Sq[XB_QD_NTEMP];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -520,20 +523,20 @@ __global__ void __launch_bounds__(512) k_prop_step(double* __restrict__ xv, int 
 
 void launch_prop_step(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, const ImuSample& in,
                       const PropParams& pp, double* FQ) {
-  k_prop_step<<<1 + (N - XB_CORE + 511) / 512, 512, 0, s>>>(xv, LX, strip, N, NS, start, in, pp, FQ);
+  XB_LAUNCH(k_prop_step, 1 + (N - XB_CORE + 511) / 512, 512, 0, s, xv, LX, strip, N, NS, start, in, pp, FQ);
   count_launch();
 }
 
 void launch_prop_means(cudaStream_t s, double* xv, int LX, int NS, int start, int n_steps, const ImuSample& in,
                        const PropParams& pp, double* FQ) {
   if (n_steps <= 0) return;
-  k_prop_means<<<n_steps, 512, 0, s>>>(xv, LX, NS, start, n_steps, in, pp, FQ);
+  XB_LAUNCH(k_prop_means, n_steps, 512, 0, s, xv, LX, NS, start, n_steps, in, pp, FQ);
   count_launch();
 }
 void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start, int n_steps, const double* FQ, int second) {
   if (n_steps <= 0) return;
   dim3 grid(1 + (N - XB_CORE + 127) / 128, n_steps);
-  k_prop_strips<<<grid, 128, 0, s>>>(strip, N, NS, start, n_steps, FQ, second);
+  XB_LAUNCH(k_prop_strips, grid, 128, 0, s, strip, N, NS, start, n_steps, FQ, second);
   count_launch();
 }
 void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,

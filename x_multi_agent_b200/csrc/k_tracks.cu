@@ -140,7 +140,8 @@ __device__ __forceinline__ bool gate_chol_blocked(double* __restrict__ X, int R2
 }
 
 template <int OPL>  // observations per lane (track length <= 32*OPL)
-__global__ void __launch_bounds__(128, 3) k_tracks(TrackParams tp) {  // <= 168 registers: leaves the register file room for the side-stream kernels
+__global__ void __launch_bounds__(128, 3) k_tracks(TrackParams tp) {
+  XB_PDL_LONG();  // <= 168 registers: leaves the register file room for the side-stream kernels
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int M = tp.M, np = tp.n_poses;
@@ -750,10 +751,10 @@ int launch_tracks(cudaStream_t s, const TrackParams& tp) {
   const int grid = (tp.n_tracks + warps - 1) / warps;
   if (tp.Lmax <= 32) {
     cudaFuncSetAttribute(k_tracks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    k_tracks<1><<<grid, warps * 32, bytes, s>>>(tp);
+    XB_LAUNCH((k_tracks<1>), grid, warps * 32, bytes, s, tp);
   } else if (tp.Lmax <= 64) {
     cudaFuncSetAttribute(k_tracks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    k_tracks<2><<<grid, warps * 32, bytes, s>>>(tp);
+    XB_LAUNCH((k_tracks<2>), grid, warps * 32, bytes, s, tp);
   } else {
     return -1;
   }
@@ -765,6 +766,7 @@ int launch_tracks(cudaStream_t s, const TrackParams& tp) {
 // SLAM rows (slam_update.cpp:49-214): one warp per SLAM feature; emits 2 sparse rows (<=15 columns).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_slam_rows(SlamParams sp) {
+  XB_PDL_SHORT();
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (j >= sp.n_tracks) return;
   const int M = sp.M, np = sp.n_poses, N = sp.N;
@@ -878,7 +880,7 @@ __global__ void __launch_bounds__(128) k_slam_rows(SlamParams sp) {
 
 void launch_slam_rows(cudaStream_t s, const SlamParams& sp) {
   if (sp.n_tracks <= 0) return;
-  k_slam_rows<<<(sp.n_tracks + 3) / 4, 128, 0, s>>>(sp);
+  XB_LAUNCH(k_slam_rows, (sp.n_tracks + 3) / 4, 128, 0, s, sp);
   count_launch();
 }
 
@@ -898,6 +900,7 @@ __device__ inline void xb_vtm33(const double* v, const double* A, double* y) {
   for (int c = 0; c < 3; ++c) y[c] = v[0] * A[c] + v[1] * A[3 + c] + v[2] * A[6 + c];
 }
 __global__ void __launch_bounds__(32) k_sensor_rows(SensorParams sp) {
+  XB_PDL_LONG();
   __shared__ int lc[XB_WMAX * XB_WNZ];
   __shared__ double h[XB_WMAX * XB_WNZ];
   __shared__ double rs[XB_WMAX];
@@ -1038,7 +1041,7 @@ __global__ void __launch_bounds__(32) k_sensor_rows(SensorParams sp) {
 }
 void launch_sensor_rows(cudaStream_t s, const SensorParams& sp) {
   if (!sp.range_on && !sp.sun_on) return;
-  k_sensor_rows<<<1, 32, 0, s>>>(sp);
+  XB_LAUNCH(k_sensor_rows, 1, 32, 0, s, sp);
   count_launch();
 }
 
@@ -1051,6 +1054,7 @@ void launch_sensor_rows(cudaStream_t s, const SensorParams& sp) {
 static const bool g_gram_mma = [] { const char* e = getenv("XB_GEMM"); return !(e && e[0] == 'd'); }();  // see k_linalg.cu
 __global__ void __launch_bounds__(256) k_gram_partial(const double* __restrict__ A, int rows, int W, int chunk,
                                                       double* __restrict__ part) {
+  XB_PDL_SHORT();
   __shared__ double As[16][64 + 4];
   __shared__ double Bs[16][64 + 4];
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
@@ -1102,6 +1106,7 @@ __global__ void __launch_bounds__(256) k_gram_partial(const double* __restrict__
 // pose of observation i of track t = n_poses - L_t + i.
 __global__ void __launch_bounds__(128) k_gram_jtj(const int* __restrict__ off, const int* __restrict__ inlier, int n_tracks,
                                                   const double* __restrict__ Jout, int n_poses, double* __restrict__ blocks) {
+  XB_PDL_SHORT();
   const int pose = blockIdx.x;
   __shared__ double red[128][29];
   double acc[28];
@@ -1134,6 +1139,7 @@ __global__ void __launch_bounds__(128) k_gram_jtj(const int* __restrict__ off, c
 __global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const double* __restrict__ partD, int nzD,
                               const double* __restrict__ blocks, int M, int n_poses, double* __restrict__ T, int ld,
                               int rows_pad, int cols_pad, double* __restrict__ diag0) {
+  XB_PDL_SHORT();
   // T is the tall buffer [cols_pad (G) + 32 (row 0 = g^T)] x ld ; everything outside G/g is identity/zero padding.
   const int W = 6 * M + 1;
   const int r = blockIdx.y * 16 + threadIdx.y, c = blockIdx.x * 16 + threadIdx.x;
@@ -1171,7 +1177,7 @@ void launch_gram(cudaStream_t s, const GramParams& gp, cudaStream_t s_jtj, cudaE
   if (fork) {
     cudaEventRecord(ev_fork, s);
     cudaStreamWaitEvent(s_jtj, ev_fork, 0);
-    k_gram_jtj<<<gp.M, 128, 0, s_jtj>>>(gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
+    XB_LAUNCH(k_gram_jtj, gp.M, 128, 0, s_jtj, gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
     count_launch();
     cudaEventRecord(ev_join, s_jtj);
   }
@@ -1184,7 +1190,7 @@ void launch_gram(cudaStream_t s, const GramParams& gp, cudaStream_t s_jtj, cudaE
       gemm_tn_splitk(s, W, W, gp.rowsB, gp.B, W, gp.B, W, gp.partB, W, (size_t)W * W, nzB);
     } else {
       dim3 g(tiles, tiles, nzB);
-      k_gram_partial<<<g, 256, 0, s>>>(gp.B, gp.rowsB, W, chunk, gp.partB);
+      XB_LAUNCH(k_gram_partial, g, 256, 0, s, gp.B, gp.rowsB, W, chunk, gp.partB);
       count_launch();
     }
   }
@@ -1195,18 +1201,18 @@ void launch_gram(cudaStream_t s, const GramParams& gp, cudaStream_t s_jtj, cudaE
       gemm_tn_splitk(s, W, W, gp.rowsD, gp.D, W, gp.D, W, gp.partD, W, (size_t)W * W, nzD);
     } else {
       dim3 g(tiles, tiles, nzD);
-      k_gram_partial<<<g, 256, 0, s>>>(gp.D, gp.rowsD, W, chunk, gp.partD);
+      XB_LAUNCH(k_gram_partial, g, 256, 0, s, gp.D, gp.rowsD, W, chunk, gp.partD);
       count_launch();
     }
   }
   if (fork) {
     cudaStreamWaitEvent(s, ev_join, 0);
   } else {
-    k_gram_jtj<<<gp.M, 128, 0, s>>>(gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
+    XB_LAUNCH(k_gram_jtj, gp.M, 128, 0, s, gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
     count_launch();
   }
   dim3 b(16, 16), g((gp.cols_pad + 15) / 16, (gp.rows_pad + 15) / 16);
-  k_gram_reduce<<<g, b, 0, s>>>(gp.partB, nzB, gp.partD, nzD, gp.blocks, gp.M, gp.n_poses, gp.T, gp.ld, gp.rows_pad,
+  XB_LAUNCH(k_gram_reduce, g, b, 0, s, gp.partB, nzB, gp.partD, nzD, gp.blocks, gp.M, gp.n_poses, gp.T, gp.ld, gp.rows_pad,
                                 gp.cols_pad, gp.diag0);
   count_launch();
 }

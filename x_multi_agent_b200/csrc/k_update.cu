@@ -32,6 +32,7 @@ namespace xb {
 // PHt[i, 2j + r] = sum_e P[i, col_e] * val[j][r][e]
 __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int* __restrict__ scols,
                            const double* __restrict__ svals, const int* __restrict__ omega_inv, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= d.N || j >= d.nslam) return;
   // P[i][col] is read as P[col][i] (consecutive threads -> consecutive addresses; the row-wise form is a stride-N gather
@@ -57,6 +58,7 @@ __global__ void k_pht_slam(UpdateDims d, const double* __restrict__ P, const int
 
 // Wide rows (range / sun sensor, XB_WNZ entries each): PHt[i, 2 nslam + w] = sum_e P[i, col_e] * val[w][e]
 __global__ void k_pht_wide(UpdateDims d, const double* __restrict__ P, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
   if (i >= d.N) return;
   double a = 0.0;
@@ -68,6 +70,7 @@ __global__ void k_pht_wide(UpdateDims d, const double* __restrict__ P, double* _
 }
 // S[2 nslam + w, c] = sum_e val[w][e] * PHt[col_e, c] for every sparse-part column c
 __global__ void k_s_wide(UpdateDims d, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
   if (c >= d.ns2) return;
   double a = 0.0;
@@ -84,6 +87,7 @@ __global__ void k_s_wide(UpdateDims d, double* __restrict__ T) {
 // (W2s differs from W1s on the newest clone's 6 rows only).  This kernel gathers Wsym (6M x s_pad) into Bc, and
 // is multiplied by launch_build_slab_part.
 __global__ void k_wsym(UpdateDims d, const int* __restrict__ omega_inv, const double* __restrict__ T, double* __restrict__ Bc) {
+  XB_PDL_SHORT();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= d.s_pad || b >= d.ms) return;
   double v = T[(size_t)(d.m_pad + XB_CORE + b) * d.ld + c];
@@ -94,13 +98,14 @@ __global__ void k_wsym(UpdateDims d, const int* __restrict__ omega_inv, const do
 void launch_wsym(cudaStream_t s, const UpdateDims& d, const int* omega_inv, const double* T, double* Bc) {
   if (d.ns2 <= 0) return;
   dim3 g((d.s_pad + 127) / 128, d.ms);
-  k_wsym<<<g, 128, 0, s>>>(d, omega_inv, T, Bc);
+  XB_LAUNCH(k_wsym, g, 128, 0, s, d, omega_inv, T, Bc);
   count_launch();
 }
 
 // S[2j + r, c] = sum_e val[j][r][e] * PHt[col_e, c]   for the columns c0 + [0, nc)
 __global__ void k_s_slam(UpdateDims d, int c0, int nc, const int* __restrict__ scols, const double* __restrict__ svals,
                          double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int cl = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (cl >= nc || j >= d.nslam) return;
   const int c = c0 + cl;
@@ -119,6 +124,7 @@ __global__ void k_s_slam(UpdateDims d, int c0, int nc, const int* __restrict__ s
 __global__ void k_s_finish(UpdateDims d, int c0, int nc, const double* __restrict__ Lg, int ldr, const double* __restrict__ zg,
                            const int* __restrict__ scols, const double* __restrict__ svals, const double* __restrict__ sres,
                            const double* __restrict__ corr, double var, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int al = blockIdx.x * blockDim.x + threadIdx.x;
   if (al >= nc) return;
   const int a = c0 + al;
@@ -161,26 +167,26 @@ void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P
   if (d.ns2 <= 0) return;
   if (d.nslam > 0) {
     dim3 g((d.N + 127) / 128, d.nslam);
-    k_pht_slam<<<g, 128, 0, s>>>(d, P, scols, svals, omega_inv, T);
+    XB_LAUNCH(k_pht_slam, g, 128, 0, s, d, P, scols, svals, omega_inv, T);
     count_launch();
   }
   if (d.nw > 0) {
     dim3 g((d.N + 127) / 128, d.nw);
-    k_pht_wide<<<g, 128, 0, s>>>(d, P, T);
+    XB_LAUNCH(k_pht_wide, g, 128, 0, s, d, P, T);
     count_launch();
   }
   if (d.nslam > 0) {
     dim3 g((d.ns2 + 127) / 128, d.nslam);
-    k_s_slam<<<g, 128, 0, s>>>(d, 0, d.ns2, scols, svals, T);
+    XB_LAUNCH(k_s_slam, g, 128, 0, s, d, 0, d.ns2, scols, svals, T);
     count_launch();
   }
   if (d.nw > 0) {
     dim3 g((d.ns2 + 127) / 128, d.nw);
-    k_s_wide<<<g, 128, 0, s>>>(d, T);
+    XB_LAUNCH(k_s_wide, g, 128, 0, s, d, T);
     count_launch();
   }
   launch_sym_lower(s, T, d.ld, 0, d.ns2, 0);
-  k_s_finish<<<(d.s_pad + 127) / 128, 128, 0, s>>>(d, 0, d.s_pad, nullptr, 0, nullptr, scols, svals, sres, corr_total, var, T);
+  XB_LAUNCH(k_s_finish, (d.s_pad + 127) / 128, 128, 0, s, d, 0, d.s_pad, nullptr, 0, nullptr, scols, svals, sres, corr_total, var, T);
   count_launch();
   launch_omega_rows(s, d, 0, d.ns2, P, nullptr, 0, scols, svals, omega, T);
 }
@@ -188,6 +194,7 @@ void launch_build_slam_part(cudaStream_t s, const UpdateDims& d, const double* P
 // lower(S22) <- sym, diagonal (+var on real rows, 1 on padding) and r_eff of the slab block (k_sym_lower + k_s_finish fused)
 __global__ void k_slab_sym_finish(UpdateDims d, const double* __restrict__ Lg, int ldr, const double* __restrict__ zg,
                                   const double* __restrict__ corr, double var, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int c = d.ro + blockIdx.x * blockDim.x + threadIdx.x, r = d.ro + blockIdx.y * blockDim.y + threadIdx.y;
   if (r >= d.m_pad || c > r) return;
   const bool real = r < d.ro + d.ms;
@@ -212,6 +219,7 @@ __global__ void k_slab_sym_finish(UpdateDims d, const double* __restrict__ Lg, i
 // Gp[k][b] = P[15 + b, Omega_k] (32 x 6M, row-major) and the V tile on the slab columns: V^T[k][ro + a] = Rg[a][Omega_k - 15]
 __global__ void k_omega_gather(UpdateDims d, const double* __restrict__ P, const double* __restrict__ Lg, int ldr,
                                const int* __restrict__ omega, double* __restrict__ Gp, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int b = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (b >= d.ms) return;
   const int ok = omega[k];
@@ -237,7 +245,7 @@ void launch_slab_omega(cudaStream_t s, const UpdateDims& d, const double* P, con
   // Omega tile on the slab columns: A2[Omega_k, a] = sum_b P[15+b, Omega_k] Rg[a][b] = (Gp Rg^T)[k][a] with the gathered
   // Gp[k][b] = P[15+b, Omega_k] (k_omega_gather, which also writes the V rows Rg[:, Omega_k]^T); a 21 x 6M x 6M tensor-core GEMM
   dim3 g((d.ms + 127) / 128, NOM);
-  k_omega_gather<<<g, 128, 0, s>>>(d, P, Lg, ldr, omega, Gp, T);
+  XB_LAUNCH(k_omega_gather, g, 128, 0, s, d, P, Lg, ldr, omega, Gp, T);
   count_launch();
   double* dst = T + (size_t)(d.m_pad + d.n_pad + 32) * d.ld + d.ro;
   if (Rg) gemm_nt(s, NOM, d.ms, d.ms, 1.0, Gp, d.ms, Rg, ldr, 0.0, dst, d.ld);
@@ -256,7 +264,7 @@ void launch_slab_s22(cudaStream_t s, const UpdateDims& d, const double* P, const
   }
   {  // symmetrise the slab block, add the measurement variance, identity on the padding, r_eff: one launch
     dim3 b(32, 8), g((d.m_pad - d.ro + 31) / 32, (d.m_pad - d.ro + 7) / 8);
-    k_slab_sym_finish<<<g, b, 0, s>>>(d, Lg, ldr, zg, corr_total, var, T);
+    XB_LAUNCH(k_slab_sym_finish, g, b, 0, s, d, Lg, ldr, zg, corr_total, var, T);
     count_launch();
   }
 }
@@ -280,6 +288,7 @@ void launch_build_slab_part(cudaStream_t s, const UpdateDims& d, const double* P
 // dense-H path: S += diag(rdiag) (+ identity padding), r_eff = res + H corr
 __global__ void k_dense_finish(int m, int m_pad, int n_pad, int N, const double* __restrict__ H, const double* __restrict__ res,
                                const double* __restrict__ rdiag, const double* __restrict__ corr, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= m_pad) return;
   double* reff = T + (size_t)(m_pad + n_pad) * m_pad;
@@ -298,6 +307,7 @@ __global__ void k_dense_finish(int m, int m_pad, int n_pad, int N, const double*
 __global__ void k_omega_rows(UpdateDims d, int c0, int nc, const double* __restrict__ P, const double* __restrict__ Lg, int ldr,
                              const int* __restrict__ scols, const double* __restrict__ svals, const int* __restrict__ omega,
                              double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int al = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (al >= nc) return;
   const int a = c0 + al;
@@ -338,6 +348,7 @@ __global__ void k_omega_rows(UpdateDims d, int c0, int nc, const double* __restr
 // dense-H variant
 __global__ void k_omega_rows_dense(int m, int m_pad, int n_pad, int N, const double* __restrict__ P,
                                    const double* __restrict__ H, const int* __restrict__ omega, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int a = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (a >= m) return;
   const int ok = omega[k];
@@ -348,6 +359,7 @@ __global__ void k_omega_rows_dense(int m, int m_pad, int n_pad, int N, const dou
 }
 // lower(S) <- lower((S + S^T)/2) for the rows [r0, r1), columns >= c0
 __global__ void k_sym_lower(double* __restrict__ T, int ld, int r0, int r1, int c0) {
+  XB_PDL_SHORT();
   const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x, r = r0 + blockIdx.y * blockDim.y + threadIdx.y;
   if (r < r1 && c < r) T[(size_t)r * ld + c] = 0.5 * (T[(size_t)r * ld + c] + T[(size_t)c * ld + r]);
 }
@@ -357,6 +369,7 @@ __global__ void k_sym_lower(double* __restrict__ T, int ld, int r0, int r1, int 
 __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const double* __restrict__ Cb,
                                                      const double* __restrict__ P, const int* __restrict__ omega,
                                                      double* __restrict__ om, int* __restrict__ err) {
+  XB_PDL_SHORT();
   __shared__ double G[NOM][NOM], E[NOM][NOM], A[2][NOM][2 * NOM + 1], q[NOM];
   __shared__ int perm[NOM];
   const int t = threadIdx.x, lane = t & 31;
@@ -450,6 +463,7 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
 
 // Omega tile <- W2_Omega - W1[Omega rows]  (dW: the rows on which W2 differs from W1)
 __global__ void k_omega_delta(int m_pad, int n_pad, const int* __restrict__ omega, double* __restrict__ T) {
+  XB_PDL_SHORT();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (c >= m_pad) return;
   double* dst = T + (size_t)(m_pad + n_pad + 32 + k) * m_pad + c;
@@ -463,6 +477,7 @@ __global__ void __launch_bounds__(128) k_omega_finish(int N, int n_pad, const do
                                                       const double* __restrict__ corr, double* __restrict__ delta,
                                                       double* __restrict__ Zb, double* __restrict__ Yb,
                                                       double* __restrict__ Qb) {
+  XB_PDL_SHORT();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N) return;
   const size_t zs = (size_t)(n_pad + 96) * 96;
@@ -492,6 +507,7 @@ __global__ void __launch_bounds__(128) k_omega_finish(int N, int n_pad, const do
 // State::correct (state.cpp:197-249) + correction_total += correction (updater.cpp:140)
 __global__ void k_correct(int M, int F, int N, const double* __restrict__ delta, double* __restrict__ xv,
                           double* __restrict__ corr) {
+  XB_PDL_SHORT();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < N && corr) corr[t] += delta[t];
   if (t < 3) {
@@ -521,10 +537,10 @@ void launch_dense_prepare(cudaStream_t s, int m, int m_pad, int N, int n_pad, co
   launch_sym_lower(s, T, m_pad, 0, m, 0);
   {
     dim3 g((m + 127) / 128, NOM);
-    k_omega_rows_dense<<<g, 128, 0, s>>>(m, m_pad, n_pad, N, P, H, omega, T);
+    XB_LAUNCH(k_omega_rows_dense, g, 128, 0, s, m, m_pad, n_pad, N, P, H, omega, T);
     count_launch();
   }
-  k_dense_finish<<<(m_pad + 127) / 128, 128, 0, s>>>(m, m_pad, n_pad, N, H, res, rdiag, corr_total, T);
+  XB_LAUNCH(k_dense_finish, (m_pad + 127) / 128, 128, 0, s, m, m_pad, n_pad, N, H, res, rdiag, corr_total, T);
   count_launch();
 }
 
@@ -532,13 +548,13 @@ void launch_omega_rows(cudaStream_t s, const UpdateDims& d, int c0, int nc, cons
                        const int* scols, const double* svals, const int* omega, double* T) {
   if (nc <= 0) return;
   dim3 g((nc + 127) / 128, NOM);
-  k_omega_rows<<<g, 128, 0, s>>>(d, c0, nc, P, Lg, ldr, scols, svals, omega, T);
+  XB_LAUNCH(k_omega_rows, g, 128, 0, s, d, c0, nc, P, Lg, ldr, scols, svals, omega, T);
   count_launch();
 }
 void launch_sym_lower(cudaStream_t s, double* T, int ld, int r0, int r1, int c0) {
   if (r1 <= r0) return;
   dim3 b(32, 8), g((r1 - c0 + 31) / 32, (r1 - r0 + 7) / 8);
-  k_sym_lower<<<g, b, 0, s>>>(T, ld, r0, r1, c0);
+  XB_LAUNCH(k_sym_lower, g, b, 0, s, T, ld, r0, r1, c0);
   count_launch();
 }
 void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, int n_pad, const double* P,
@@ -546,21 +562,22 @@ void launch_correct(cudaStream_t s, int M, int F, int N, double* T, int m_pad, i
                     double* xv, double* corr_total, double* delta_out, int* err) {
   {
     dim3 g((m_pad + 127) / 128, NOM);
-    k_omega_delta<<<g, 128, 0, s>>>(m_pad, n_pad, omega, T);
+    XB_LAUNCH(k_omega_delta, g, 128, 0, s, m_pad, n_pad, omega, T);
     count_launch();
   }
   // Cb[(n_pad + 96) x 96] = [W1 ; aux ; dW ; Vt] * [aux ; dW ; Vt]^T : every dot product the Woodbury step needs
   gemm_nt_splitk(s, n_pad + 96, 96, m_pad, T + (size_t)m_pad * m_pad, m_pad, T + (size_t)(m_pad + n_pad) * m_pad, m_pad, Cb, 96,
                  (size_t)(n_pad + 96) * 96, CBZ);
-  k_omega_small<<<1, 256, 0, s>>>(N, n_pad, Cb, P, omega, om, err);
+  XB_LAUNCH(k_omega_small, 1, 256, 0, s, N, n_pad, Cb, P, omega, om, err);
   count_launch();
-  k_omega_finish<<<(N * 32 + 127) / 128, 128, 0, s>>>(N, n_pad, Cb, om, omega_inv, corr_total, delta_out, Zb, Yb, Qb);
+  XB_LAUNCH(k_omega_finish, (N * 32 + 127) / 128, 128, 0, s, N, n_pad, Cb, om, omega_inv, corr_total, delta_out, Zb, Yb, Qb);
   count_launch();
   launch_apply_delta(s, M, F, N, delta_out, xv, corr_total);
 }
 // P <- sym(P_j - K (H P_j))   (updater.cpp:153-156), m small
 __global__ void __launch_bounds__(256) k_ci_cov(double* __restrict__ P, int N, const double* __restrict__ K,
                                                 const double* __restrict__ HP, int m) {
+  XB_PDL_SHORT();
   const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4);
   if (i >= N || j >= N || i > j) return;
   double a = 0.0, b = 0.0;
@@ -574,11 +591,11 @@ __global__ void __launch_bounds__(256) k_ci_cov(double* __restrict__ P, int N, c
 }
 void launch_ci_cov(cudaStream_t s, double* P, int N, const double* K, const double* HP, int m) {
   dim3 g((N + 15) / 16, (N + 15) / 16);
-  k_ci_cov<<<g, 256, 0, s>>>(P, N, K, HP, m);
+  XB_LAUNCH(k_ci_cov, g, 256, 0, s, P, N, K, HP, m);
   count_launch();
 }
 void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta, double* xv, double* corr_total) {
-  k_correct<<<(N + 127) / 128, 128, 0, s>>>(M, F, N, delta, xv, corr_total);
+  XB_LAUNCH(k_correct, (N + 127) / 128, 128, 0, s, M, F, N, delta, xv, corr_total);
   count_launch();
 }
 
@@ -586,6 +603,7 @@ void launch_apply_delta(cudaStream_t s, int M, int F, int N, const double* delta
 // tiles that contain an Omega row -- written on the stream (no host staging, no synchronisation).
 __global__ void k_set_omega(int* __restrict__ omega, int* __restrict__ omega_inv, int* __restrict__ tileflag, int slot, int M,
                             int n_pad, int nflag) {
+  XB_PDL_SHORT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   auto om = [&](int k) { return k < 15 ? k : (k < 18 ? XB_CORE + 3 * slot + (k - 15) : XB_CORE + 3 * M + 3 * slot + (k - 18)); };
   if (i < 32) omega[i] = i < 21 ? om(i) : 0;
@@ -601,7 +619,7 @@ __global__ void k_set_omega(int* __restrict__ omega, int* __restrict__ omega_inv
   }
 }
 void launch_set_omega(cudaStream_t s, int* omega, int* omega_inv, int* tileflag, int slot, int M, int n_pad, int nflag) {
-  k_set_omega<<<(n_pad + 255) / 256, 256, 0, s>>>(omega, omega_inv, tileflag, slot, M, n_pad, nflag);
+  XB_LAUNCH(k_set_omega, (n_pad + 255) / 256, 256, 0, s, omega, omega_inv, tileflag, slot, M, n_pad, nflag);
   count_launch();
 }
 

@@ -16,6 +16,10 @@
 namespace xb {
 static thread_local long long g_launches = 0;
 void count_launch() { ++g_launches; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("XB_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
 }  // namespace xb
 
 using namespace xb;

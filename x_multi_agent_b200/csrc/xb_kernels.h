@@ -10,6 +10,34 @@ namespace xb {
 
 void count_launch();  // bumps the per-thread kernel-launch counter (xb_kernel_launches)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------------
+// An update is ~45 small dependent launches; with the stream-serialisation attribute a kernel's CTAs are scheduled while its
+// predecessor in the stream is still running and block in griddepcontrol.wait until that grid has completed and flushed,
+// which removes the launch latency from every kernel-to-kernel edge.  Every kernel launched through XB_LAUNCH starts with
+// XB_PDL_SHORT() (let the dependents in early, then wait) or XB_PDL_LONG() (wait only: the dependents of a long-running kernel
+// must not sit resident next to the side-stream kernels for its whole duration).  No global memory is touched before the wait,
+// so the stream order of reads and writes is unchanged.  XB_NO_PDL=1 launches without the attribute (A/B measurements).
+#ifdef __CUDACC__
+#define XB_PDL_SHORT() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+#define XB_PDL_LONG() asm volatile("griddepcontrol.wait;" ::: "memory")
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void xb_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define XB_LAUNCH(kern, grid, block, smem, stream, ...) xb::xb_launch(kern, grid, block, smem, stream, ##__VA_ARGS__)
+#endif
+
 // ---- propagation --------------------------------------------------------------------------------
 struct ImuSample { int valid; double t, seq, w[3], a[3]; };
 struct PropParams { double g[3]; double n_w, n_bw, n_a, n_ba; };
