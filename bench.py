@@ -367,7 +367,42 @@ def main():
                 "msckf_inlier_frac_last_step": float(inl5.mean()),
                 "top_stages_ms": {k: round(v, 3) for k, v in top5},
                 "covariance_bytes": 8 * N5 * N5}
+        # the genuine dense contraction of the path at this size: P <- sym(P) - W1 W1^T (+ Woodbury tail), one launch of the
+        # TMA-staged DMMA kernel (k_gemm_tma<SYM>), timed inside the update by the library's event pair around the stage
+        pad32 = lambda x: (x + 31) // 32 * 32
+        K5 = pad32(2 * CFG5["F"]) + pad32(6 * CFG5["M"]) + 64
+        if "downdate" in st5 and st5["downdate"][1] > 0:
+            dd_ms = st5["downdate"][0] / st5["downdate"][1]
+            fl5, by5 = float(N5) * N5 * K5, 8.0 * (2 * N5 * N5 + N5 * K5)
+            cfg5["roofline"] = {"kernel": "k_gemm_tma<SYM> (covariance downdate, TMA-staged fp64 DMMA tiles)", "bound": "tensor",
+                                "achieved": fl5 / (dd_ms * 1e-3) / 1e12, "peak": 36.9, "unit": "TFLOP/s",
+                                "frac": fl5 / (dd_ms * 1e-3) / 1e12 / 36.9, "traffic": None, "avg_launch_ms": dd_ms,
+                                "algorithmic_flops": fl5, "algorithmic_bytes": by5,
+                                "hbm_gbs_at_this_rate": by5 / (dd_ms * 1e-3) / 1e9,
+                                "peak_source": "fp64 tensor-core (mma.sync.m8n8k4) peak measured with tools/bench_dmma.cu; "
+                                               "B200 has no tcgen05 kind for fp64"}
         f5.close()
+        # covariance-update roofline sweep (BASELINE configs[4]): the symmetric downdate kernel alone at the covariance sizes
+        # of growing windows / maps (N = 15 + 6M + 3F, K = padded compressed rows), inputs resident, 10 timed launches each
+        import ctypes as _C
+        from x_multi_agent_b200 import lib as _L
+        sweep = []
+        _rng = np.random.default_rng(0)
+        for (M_, F_) in ((30, 200), (40, 400), (50, 600), (50, 800)):
+            n_, k_ = 15 + 6 * M_ + 3 * F_, pad32(2 * F_) + pad32(6 * M_)
+            W_ = _rng.normal(size=(n_, k_)) * 0.01
+            P_ = _rng.normal(size=(n_, n_))
+            ms_ = _C.c_double(0.0)
+            used = _L.load().xb_debug_gemm(2, n_, n_, k_, _L.dptr(W_), k_, _L.dptr(W_), k_, 0.0, 0.0, _L.dptr(P_), n_, 11,
+                                           _C.cast(_C.byref(ms_), _L.c_double_p))
+            if used == 1 and ms_.value > 0:
+                sweep.append({"N": n_, "K": k_, "us": round(ms_.value * 1e3, 1),
+                              "tflops": round(float(n_) * n_ * k_ / (ms_.value * 1e-3) / 1e12, 2),
+                              "frac_fp64_tensor_peak": round(float(n_) * n_ * k_ / (ms_.value * 1e-3) / 1e12 / 36.9, 3),
+                              "hbm_gbs": round(8.0 * (2 * n_ * n_ + n_ * k_) / (ms_.value * 1e-3) / 1e9, 1)})
+            else:
+                sweep.append({"N": n_, "K": k_, "kernel": "k_downdate_mma (cp.async tiles: below the TMA kernel's size threshold)"})
+        cfg5["covariance_update_sweep"] = sweep
     # ---- phase B: end to end through the C ABI with host buffers ---------------------------------------------
     e2e_s = 0.0
     barrier()

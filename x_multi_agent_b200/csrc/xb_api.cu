@@ -1430,6 +1430,18 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
     tallchol(f->stream, f->d_T + (size_t)chol_from * m_pad + chol_from, m_pad, m_pad - chol_from + n_pad + 96, m_pad - chol_from,
              f->d_flags, f->d_err, 0.0, nullptr, f->d_trace);
     f->trace_tiles = (m_pad / 32) * (m_pad / 32 + 1) / 2 + ((n_pad + 96) / 32) * (m_pad / 32); }
+  // The slab-column part of the downdate needs only W1 (complete once the factorisation is): it runs on a side stream next
+  // to the Woodbury / State::correct stage; the Woodbury / Omega tail (which needs that stage's Z, Y, Q) follows as a
+  // rank-42 pass of the same kernel with no main slabs.
+  const bool dd_split = cov_update && f->overlap && f->dd_pending && f->dd_cols == chol_from && chol_from > 0;
+  if (dd_split) {
+    CK(cudaEventRecord(f->ev_b0, f->stream));
+    CK(cudaStreamWaitEvent(f->side, f->ev_b0, 0));
+    CK(cudaStreamWaitEvent(f->side, f->ev_dd, 0));
+    downdate_f64_range(f->side, f->d_dd, f->d_dd, N, f->d_T, m_pad, n_pad, chol_from, m_pad, 0, 0, f->d_omega_inv, f->d_Zb,
+                       f->d_Yb, f->d_Qb);
+    CK(cudaEventRecord(f->ev_b1, f->side));
+  }
   {
     StageTimer st_(f, ST_CORRECT);
     launch_correct(f->stream, f->M, f->F, N, f->d_T, m_pad, n_pad, f->d_Pw, f->d_omega, f->d_omega_inv, f->d_om, f->d_Zb,
@@ -1439,7 +1451,12 @@ static int apply_from_tall(xb_filter* f, int m_pad, int n_pad, int cov_update, d
   f->xw_final = true;
   if (cov_update) {
     StageTimer st_(f, ST_DOWNDATE);
-    if (f->dd_pending && f->dd_cols == chol_from && chol_from > 0) {
+    if (dd_split) {
+      CK(cudaStreamWaitEvent(f->stream, f->ev_b1, 0));
+      downdate_f64_range(f->stream, f->d_dd, f->d_dd, N, f->d_T, m_pad, n_pad, m_pad, m_pad, 0, 1, f->d_omega_inv, f->d_Zb,
+                         f->d_Yb, f->d_Qb);
+      f->d_Pw = f->d_dd;
+    } else if (f->dd_pending && f->dd_cols == chol_from && chol_from > 0) {
       // the SLAM-column part is already in d_WA (side2): finish with the slab columns and the Woodbury / Omega terms
       CK(cudaStreamWaitEvent(f->stream, f->ev_dd, 0));
       downdate_f64_range(f->stream, f->d_dd, f->d_dd, N, f->d_T, m_pad, n_pad, chol_from, m_pad, 0, 1, f->d_omega_inv, f->d_Zb,
