@@ -1104,36 +1104,60 @@ __global__ void __launch_bounds__(256) k_gram_partial(const double* __restrict__
 
 // One CTA per window pose: sum over the tracks' observations at that pose of [Jp Ja r]^T [Jp Ja r] (7x7).
 // pose of observation i of track t = n_poses - L_t + i.
-__global__ void __launch_bounds__(128) k_gram_jtj(const int* __restrict__ off, const int* __restrict__ inlier, int n_tracks,
-                                                  const double* __restrict__ Jout, int n_poses, double* __restrict__ blocks) {
+// 512 threads, two tracks per thread and trip with all index loads, then all Jacobian loads, in flight together (the kernel
+// is a chain of three dependent L2 round trips per track: inlier/offsets -> Jacobian block -> products); the 28 sums are
+// reduced by warp shuffles and one fixed-order pass over the 16 warp partials (deterministic).
+#define GJ_THREADS 512
+__global__ void __launch_bounds__(GJ_THREADS) k_gram_jtj(const int* __restrict__ off, const int* __restrict__ inlier, int n_tracks,
+                                                         const double* __restrict__ Jout, int n_poses, double* __restrict__ blocks) {
   XB_PDL_SHORT();
-  const int pose = blockIdx.x;
-  __shared__ double red[128][29];
+  const int pose = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ double red[GJ_THREADS / 32][28];
   double acc[28];
+#pragma unroll
   for (int e = 0; e < 28; ++e) acc[e] = 0.0;
-  for (int t = threadIdx.x; t < n_tracks; t += blockDim.x) {
-    if (!inlier[t]) continue;
-    const int L = off[t + 1] - off[t];
-    const int i = pose - (n_poses - L);
-    if (i < 0 || i >= L) continue;
-    const double* o = Jout + 14 * (size_t)(off[t] + i);
-    // 7 "columns": Jp(:,0..2), Ja(:,0..2), r ; rows 0/1
-    double c0[7], c1[7];
-    for (int e = 0; e < 3; ++e) { c0[e] = o[e]; c1[e] = o[3 + e]; c0[3 + e] = o[6 + e]; c1[3 + e] = o[9 + e]; }
-    c0[6] = o[12];
-    c1[6] = o[13];
-    int q = 0;
-    for (int a = 0; a < 7; ++a)
-      for (int b = a; b < 7; ++b) acc[q++] += c0[a] * c0[b] + c1[a] * c1[b];
+  for (int t0 = 0; t0 < n_tracks; t0 += 2 * GJ_THREADS) {
+    const double* src[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * GJ_THREADS + threadIdx.x;
+      src[u] = nullptr;
+      if (t < n_tracks) {
+        const int o0 = off[t], o1 = off[t + 1], inl = inlier[t];
+        const int i = pose - (n_poses - (o1 - o0));
+        if (inl && i >= 0 && i < o1 - o0) src[u] = Jout + 14 * (size_t)(o0 + i);
+      }
+    }
+    double o[2][14];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int e = 0; e < 14; ++e) o[u][e] = src[u] ? src[u][e] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      // 7 "columns": Jp(:,0..2), Ja(:,0..2), r ; rows 0/1
+      double c0[7], c1[7];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) { c0[e] = o[u][e]; c1[e] = o[u][3 + e]; c0[3 + e] = o[u][6 + e]; c1[3 + e] = o[u][9 + e]; }
+      c0[6] = o[u][12];
+      c1[6] = o[u][13];
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 7; ++a)
+#pragma unroll
+        for (int b = a; b < 7; ++b) { acc[q] += c0[a] * c0[b] + c1[a] * c1[b]; ++q; }
+    }
   }
-  for (int e = 0; e < 28; ++e) red[threadIdx.x][e] = acc[e];
+#pragma unroll
+  for (int e = 0; e < 28; ++e) acc[e] = xb_warp_sum(acc[e]);
+  if (lane == 0)
+    for (int e = 0; e < 28; ++e) red[warp][e] = acc[e];
   __syncthreads();
-  for (int s = 64; s > 0; s >>= 1) {
-    if (threadIdx.x < s)
-      for (int e = 0; e < 28; ++e) red[threadIdx.x][e] += red[threadIdx.x + s][e];
-    __syncthreads();
+  if (threadIdx.x < 28) {
+    double v = 0.0;
+    for (int w = 0; w < GJ_THREADS / 32; ++w) v += red[w][threadIdx.x];
+    blocks[28 * pose + threadIdx.x] = v;
   }
-  if (threadIdx.x < 28) blocks[28 * pose + threadIdx.x] = red[0][threadIdx.x];
 }
 
 __global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const double* __restrict__ partD, int nzD,
@@ -1150,8 +1174,23 @@ __global__ void k_gram_reduce(const double* __restrict__ partB, int nzB, const d
   if (r < n) gr = r;
   else if (r == cols_pad) gr = n;  // augmented row: g^T
   if (gr >= 0 && c < n) {
-    for (int z = 0; z < nzB; ++z) v -= partB[(size_t)z * W * W + (size_t)gr * W + c];
-    for (int z = 0; z < nzD; ++z) v += partD[(size_t)z * W * W + (size_t)gr * W + c];
+    // fixed-order sums of the split-K partials, eight loads in flight at a time (one L2 round trip per eight partials
+    // instead of one per partial)
+    const size_t e0 = (size_t)gr * W + c, zs = (size_t)W * W;
+    for (int z0 = 0; z0 < nzB; z0 += 8) {
+      double p[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) p[u] = z0 + u < nzB ? partB[(size_t)(z0 + u) * zs + e0] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v -= p[u];
+    }
+    for (int z0 = 0; z0 < nzD; z0 += 8) {
+      double p[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) p[u] = z0 + u < nzD ? partD[(size_t)(z0 + u) * zs + e0] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += p[u];
+    }
     // block-diagonal J^T J: element (gr, c) is non-zero when both belong to the same pose (or gr is the r column)
     auto pose_of = [&](int x, int& k) { const bool att = x >= 3 * M; const int xx = att ? x - 3 * M : x; k = (att ? 3 : 0) + xx % 3; return xx / 3; };
     int kc, pc = pose_of(c, kc);
@@ -1177,7 +1216,7 @@ void launch_gram(cudaStream_t s, const GramParams& gp, cudaStream_t s_jtj, cudaE
   if (fork) {
     cudaEventRecord(ev_fork, s);
     cudaStreamWaitEvent(s_jtj, ev_fork, 0);
-    XB_LAUNCH(k_gram_jtj, gp.M, 128, 0, s_jtj, gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
+    XB_LAUNCH(k_gram_jtj, gp.M, GJ_THREADS, 0, s_jtj, gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
     count_launch();
     cudaEventRecord(ev_join, s_jtj);
   }
@@ -1208,7 +1247,7 @@ void launch_gram(cudaStream_t s, const GramParams& gp, cudaStream_t s_jtj, cudaE
   if (fork) {
     cudaStreamWaitEvent(s, ev_join, 0);
   } else {
-    XB_LAUNCH(k_gram_jtj, gp.M, 128, 0, s, gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
+    XB_LAUNCH(k_gram_jtj, gp.M, GJ_THREADS, 0, s, gp.off, gp.inlier, gp.n_tracks_msckf, gp.Jout, gp.n_poses, gp.blocks);
     count_launch();
   }
   dim3 b(16, 16), g((gp.cols_pad + 15) / 16, (gp.rows_pad + 15) / 16);

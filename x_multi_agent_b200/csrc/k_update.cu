@@ -415,14 +415,18 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
   int cur = 0;
   __syncthreads();
   for (int c = 0; c < NOM; ++c) {
-    double bv = (lane < NOM && !((used >> lane) & 1u)) ? fabs(A[cur][lane][c]) : -1.0;
-    int bi = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
+    // first maximum of |A[r][c]| over the unused rows: non-negative doubles order like their bit patterns, so two
+    // warp-wide integer max reductions (high word, then low word among the ties) + a ballot replace the 15 dependent
+    // shuffles of a (value, index) butterfly
+    const bool cand = lane < NOM && !((used >> lane) & 1u);
+    const double av = cand ? fabs(A[cur][lane][c]) : 0.0;
+    const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(av) + 1ull : 0ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const unsigned win = __ballot_sync(0xffffffffu, cand && hi == mh && lo == ml);
+    const int bi = win ? __ffs(win) - 1 : -1;
+    const double bv = __shfl_sync(0xffffffffu, av, bi < 0 ? 0 : bi);
     // a non-finite column (the factorisation met a non-positive pivot: S was not positive definite) must not select a
     // row outside the matrix; the error word makes xb_synchronize report it
     int pv = bi;
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(256) k_omega_small(int N, int n_pad, const dou
       if (!(bv > 0.0) && err) atomicOr(err, 2);
     }
     used |= 1u << pv;
-    const double rp = 1.0 / A[cur][pv][c];
+    const double rp = __drcp_rn(A[cur][pv][c]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = er[u], x = ex[u];
