@@ -634,7 +634,8 @@ def main():
         "side_tallchol_slam_cols": ("k_tallchol (SLAM columns, side stream)", tall(s_pad + n_pad + 96, s_pad),
                                     s_pad ** 3 / 3 + (n_pad + 96) * s_pad ** 2),
         "chol_gram": ("k_tallchol (Gram factor)", tall(r_pad + 32, r_pad), r_pad ** 3 / 3),
-        "downdate": ("k_downdate_mma (slab columns + Woodbury tail)", 8 * (2 * N * N + N * (r_pad + 64)), N * N * (r_pad + 64)),
+        # the slab-column part now runs on a side stream next to State::correct (untimed there); the stage is the tail pass
+        "downdate": ("k_downdate_mma (Woodbury / Omega tail pass)", 8 * (2 * N * N + N * 64), N * N * 64),
         "side_downdate_slam_cols": ("k_downdate_mma (SLAM columns, side stream)", 8 * (2 * N * N + N * s_pad), N * N * s_pad),
     }
     main_single = [k for k in single if k in per_stage and not k.startswith("side_")]

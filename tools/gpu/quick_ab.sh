@@ -1,7 +1,7 @@
-# parity subset + cfg-2 bench twice (stage table)
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py -m gpu -q -x 2>&1 | tail -4
-for v in 1 2; do
-  timeout 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-reference-semantics 2>/dev/null | python -c "
+# cfg-2 bench A/B over an environment switch given as $1 (stage table)
+for v in "" "$1" "" "$1"; do
+  echo "--- env: $v"
+  env $v timeout 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-reference-semantics 2>/dev/null | python -c "
 import sys,json
 l=[x for x in sys.stdin.read().splitlines() if x.startswith('{')][0]
 d=json.loads(l)

@@ -15,7 +15,8 @@
 //     a K-slab of 16 doubles is exactly one 128-byte swizzle row, so the DMMA fragment loads (8 rows x 4 k per instruction)
 //     are bank-conflict free without padding and out-of-range rows / k are zero-filled by the copy engine;
 //   * CTA tile 128 x 64, eight consumer warps with 32 x 32 warp tiles (16 DMMA accumulators): 8 fragment loads per 16 DMMA;
-//   * a ninth warp is the producer; consumers release a stage with one mbarrier arrive per warp.
+//   * lane 0 of warp 0 is the producer in between its own tiles (256 threads x 126 registers fit twice per SM, a ninth
+//     producer warp would not); consumers release a stage with one mbarrier arrive per warp.
 // TMA needs 16-byte aligned rows: the tall buffer (leading dimension m_pad, a multiple of 32) qualifies, the covariance P
 // (leading dimension N, odd at every BASELINE size) is touched by the epilogue only.
 #include <cuda.h>
@@ -79,7 +80,7 @@ struct TmaTail {
   CUtensorMap zA, yA, zB, yB;   // Zb / Yb (n x 32) with the A-side (128 rows) and B-side (64 rows) boxes
 };
 template <bool SYM>
-__global__ void __launch_bounds__(288) k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(256, 2) k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                   int M, int N, int K, double alpha, double beta, const double* Cin, double* __restrict__ C,
                                                   int ldc, const __grid_constant__ TmaTail tail, int ntail,
                                                   const int* __restrict__ omega_inv, const double* __restrict__ Qb) {
@@ -113,25 +114,26 @@ __global__ void __launch_bounds__(288) k_gemm_tma(const __grid_constant__ CUtens
   __syncthreads();
   const int nmain = (K + TG_BK - 1) / TG_BK;
   const int nslab = nmain + (SYM ? ntail : 0);
-  if (warp == 8) {
-    if (lane == 0) {
-      for (int slab = 0; slab < nslab; ++slab) {
-        const int s = slab % TG_ST;
-        if (slab >= TG_ST) mbar_wait(bars + 8 * (TG_ST + s), ((slab / TG_ST) - 1) & 1);
-        const uint32_t full = bars + 8 * s;
-        mbar_expect_tx(full, TG_STAGE_BYTES);
-        if (slab < nmain) {
-          tma_load_2d(sbase + s * TG_STAGE_BYTES, &tmA, slab * TG_BK, m0, full);
-          tma_load_2d(sbase + s * TG_STAGE_BYTES + TG_A_BYTES, &tmB, slab * TG_BK, n0, full);
-        } else {
-          const int ts = slab - nmain, k0 = (ts & 1) * TG_BK;
-          tma_load_2d(sbase + s * TG_STAGE_BYTES, ts < 2 ? &tail.zA : &tail.yA, k0, m0, full);
-          tma_load_2d(sbase + s * TG_STAGE_BYTES + TG_A_BYTES, ts < 2 ? &tail.yB : &tail.zB, k0, n0, full);
-        }
-      }
+  // producer = lane 0 of warp 0, in between its own tiles: slab s + TG_ST - 1 is requested at the top of iteration s, once
+  // every warp has released the stage it goes into (a dedicated ninth warp costs the second CTA per SM: 288 threads x 126
+  // registers do not fit twice)
+  auto produce = [&](int slab) {
+    if (slab >= nslab) return;
+    const int s = slab % TG_ST;
+    if (slab >= TG_ST) mbar_wait(bars + 8 * (TG_ST + s), ((slab / TG_ST) - 1) & 1);
+    const uint32_t full = bars + 8 * s;
+    mbar_expect_tx(full, TG_STAGE_BYTES);
+    if (slab < nmain) {
+      tma_load_2d(sbase + s * TG_STAGE_BYTES, &tmA, slab * TG_BK, m0, full);
+      tma_load_2d(sbase + s * TG_STAGE_BYTES + TG_A_BYTES, &tmB, slab * TG_BK, n0, full);
+    } else {
+      const int ts = slab - nmain, k0 = (ts & 1) * TG_BK;
+      tma_load_2d(sbase + s * TG_STAGE_BYTES, ts < 2 ? &tail.zA : &tail.yA, k0, m0, full);
+      tma_load_2d(sbase + s * TG_STAGE_BYTES + TG_A_BYTES, ts < 2 ? &tail.yB : &tail.zB, k0, n0, full);
     }
-    return;
-  }
+  };
+  if (t == 0)
+    for (int s = 0; s < TG_ST - 1; ++s) produce(s);
   const int g = lane >> 2, tg = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   double acc[4][4][2];
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(288) k_gemm_tma(const __grid_constant__ CUtens
     for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   for (int slab = 0; slab < nslab; ++slab) {
     const int s = slab % TG_ST;
+    if (t == 0) produce(slab + TG_ST - 1);
+    __syncwarp();
     mbar_wait(bars + 8 * s, (slab / TG_ST) & 1);
     const unsigned char* as = base + s * TG_STAGE_BYTES;
     const unsigned char* bs = as + TG_A_BYTES;
@@ -233,7 +237,7 @@ bool gemm_nt_tma(cudaStream_t s, int M, int N, int K, double alpha, const double
   if (!g_attr_set) { set_attr<false>(); set_attr<true>(); g_attr_set = true; }
   dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM);
   static const TmaTail no_tail{};
-  XB_LAUNCH((k_gemm_tma<false>), grid, 288, TG_SMEM, s, ta, tb, M, N, K, alpha, beta, nullptr, C, ldc, no_tail, 0, nullptr, nullptr);
+  XB_LAUNCH((k_gemm_tma<false>), grid, 256, TG_SMEM, s, ta, tb, M, N, K, alpha, beta, nullptr, C, ldc, no_tail, 0, nullptr, nullptr);
   count_launch();
   return true;
 }
@@ -255,7 +259,7 @@ bool downdate_sym_tma(cudaStream_t s, int n, int K, const double* W, int ldw, co
     ntail = 4;
   }
   if (!g_attr_set) { set_attr<false>(); set_attr<true>(); g_attr_set = true; }
-  XB_LAUNCH((k_gemm_tma<true>), nb * (nb + 1), 288, TG_SMEM, s, ta, tb, n, n, K, -1.0, 0.0, Pin, Pout, ldp, tail, ntail, omega_inv, Qb);
+  XB_LAUNCH((k_gemm_tma<true>), nb * (nb + 1), 256, TG_SMEM, s, ta, tb, n, n, K, -1.0, 0.0, Pin, Pout, ldp, tail, ntail, omega_inv, Qb);
   count_launch();
   return true;
 }
