@@ -406,10 +406,13 @@ def main():
     # ---- phase B: end to end through the C ABI with host buffers ---------------------------------------------
     e2e_s = 0.0
     barrier()
+    ib0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+    ib1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
     for j in range(W + K):
         i = W + K + j
-        for (t, seq, w, a) in events[i][0]:
-            flt.process_imu(t, seq, w, a, want_state=False)
+        ib0[j].record(stream)
+        flt.process_imu_batch(events[i][0])      # the frame's IMU samples in one call (xb_ekf_process_imu_batch)
+        ib1[j].record(stream)
         flt.synchronize()
         t0 = time.perf_counter()
         flt.set_measurement(packed[i])                      # host -> device: track lists
@@ -419,6 +422,7 @@ def main():
         if j >= W:
             e2e_s += t1 - t0
     barrier()
+    imu_batch_us = 1e3 * sum(ib0[j].elapsed_time(ib1[j]) for j in range(W, W + K)) / (K * max(len(events[W + K][0]), 1))
     assert np.all(np.isfinite(st.x)), "non-finite state after the benchmark"
     # ---- the same device-timed run with the reference's OC projection as written (N = 1 only) ------------------
     ref_sem = None
@@ -454,17 +458,22 @@ def main():
         PP = flt.pose_payload_len()
         local = torch.zeros(PP, dtype=torch.float64, device="cuda")
         steps_d = []
-        for j in range(W + Kd):
+        NPROF = 4   # extra untimed steps with the library's stage timers on: where the MULTI_UAV step spends its time
+        for j in range(W + Kd + NPROF):
             imu, m = steady_events(scn, k0 + j, 1)[0]
             lms = scn.last_msckf_lms
             win = list(range(k0 + j - CFG2["M"], k0 + j))     # frames held by a peer's window when it packs its payload
             mt = [(p, 0, a * 32 + q, peer_scn[p]._project(lms[a * 32 + q], win)) for a, p in enumerate(peers) for q in range(32)]
             steps_d.append((imu, PackedMeasurement(m), mt))
-        d0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
-        d1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd)]
+        d0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd + NPROF)]
+        d1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd + NPROF)]
         acc, gated = [], []
         barrier()
         for j, (imu, pm, mt) in enumerate(steps_d):
+            if j == W + Kd:
+                flt.synchronize()
+                flt.profile(True)
+                flt.profile_read()
             for (t, seq, w, a) in imu:
                 flt.process_imu(t, seq, w, a, want_state=False)
             flt.set_measurement(pm)
@@ -483,15 +492,20 @@ def main():
                       "n", len(g), file=sys.stderr, flush=True)
             gated.append(float(np.isfinite(g[:, 1]).mean()) if len(g) else 0.0)
             acc.append(float(g[:, 0].mean()) if len(g) else 0.0)
+        mm_prof = flt.profile_read()
+        flt.profile(False)
         barrier()
-        frame_cursor[0] = k0 + W + Kd
+        frame_cursor[0] = k0 + W + Kd + NPROF
         mm_ms = sum(d0[j].elapsed_time(d1[j]) for j in range(W, W + Kd))
         tmm = torch.tensor([mm_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmm, op=dist.ReduceOp.MAX)
         mm = {"multi_uav_updates_per_sec": world * Kd / (float(tmm[0]) * 1e-3), "ms_per_step": float(tmm[0]) / Kd, "steps": Kd,
-              "msckf_matches_per_step": len(steps_d[0][2]), "own_gate_passed_frac_rank0": float(np.mean(gated[W:])),
-              "joint_gate_accepted_frac_rank0": float(np.mean(acc[W:])), "pose_payload_bytes_per_agent": PP * 8,
-              "collective": "all_gather (NCCL), one per update"}
+              "msckf_matches_per_step": len(steps_d[0][2]), "own_gate_passed_frac_rank0": float(np.mean(gated[W:W + Kd])),
+              "joint_gate_accepted_frac_rank0": float(np.mean(acc[W:W + Kd])), "pose_payload_bytes_per_agent": PP * 8,
+              "collective": "all_gather (NCCL), one per update",
+              "stage_ms_rank0": {k: round(v[0] / max(v[1], 1), 4) for k, v in sorted(mm_prof.items(), key=lambda kv: -kv[1][0])
+                                 if v[1] > 0},
+              "profiled_step_ms_rank0": sum(d0[j].elapsed_time(d1[j]) for j in range(W + Kd, W + Kd + NPROF)) / NPROF}
     # ---- phase D (N > 1): covariance-intersection fusion steps with the compressed payload exchanged over NCCL ----
     ci = None
     if world > 1:
@@ -737,7 +751,10 @@ def main():
             "clocks": sampler.summary(), "stage_ms_per_update": stages_ms, "ci": ci, "multi_uav_msckf": mm,
             "gate_inlier_frac_last_step": {"msckf": msckf_inlier_frac, "slam": slam_inlier_frac},
             "reference_semantics": ref_sem, "cfg5": cfg5,
-            "imu_us_per_sample": {"value": round(imu_us, 2), "note": "Ekf::processImu (propagateState + propagateCovariance, "
+            "imu_us_per_sample": {"value": round(imu_us, 2), "batched": round(imu_batch_us, 2),
+                                  "batched_note": "xb_ekf_process_imu_batch: the 10 samples of a frame in one call (three launches), "
+                                                  "device time per sample, used by the end-to-end phase",
+                                  "note": "Ekf::processImu (propagateState + propagateCovariance, "
                                   "ekf.cpp:66-140) between updates: device time per IMU sample over the untimed feed of the "
                                   "steady-state phase (10 samples per frame, one fused launch each, issued back to back)"}}
     emit(line)

@@ -995,6 +995,26 @@ class Ekf {
     out.bindSlot(dev_->f, &dev_->mutex, xb_ekf_newest_slot(dev_->f));
     return out;
   }
+  /** Addition to the reference API: a run of processImu calls in one (xb_ekf_process_imu_batch: three launches for up to
+   *  32 samples instead of one per sample).  Returns the newest propagated state, nullopt if no sample produced one. */
+  std::optional<State> processImuBatch(const std::vector<double>& timestamps, const std::vector<unsigned int>& seqs,
+                                       const std::vector<Vector3>& w_m, const std::vector<Vector3>& a_m) {
+    if (!dev_ || timestamps.empty()) return std::nullopt;
+    if (seqs.size() != timestamps.size() || w_m.size() != timestamps.size() || a_m.size() != timestamps.size())
+      throw std::invalid_argument("Ekf::processImuBatch: argument lengths differ");
+    std::lock_guard<std::mutex> lk(dev_->mutex);
+    std::vector<double> x(XB_XVEC_LEN(M_, F_)), w(3 * timestamps.size()), a(3 * timestamps.size());
+    for (size_t i = 0; i < timestamps.size(); ++i)
+      for (int e = 0; e < 3; ++e) { w[3 * i + e] = w_m[i](e); a[3 * i + e] = a_m[i](e); }
+    const int rc = xb_ekf_process_imu_batch(dev_->f, static_cast<int>(timestamps.size()), timestamps.data(), seqs.data(),
+                                            w.data(), a.data(), x.data());
+    xb_throw(rc);
+    if (rc == 0) return std::nullopt;
+    State out;
+    out.setFromXvec(x.data(), M_, F_);
+    out.bindSlot(dev_->f, &dev_->mutex, xb_ekf_newest_slot(dev_->f));
+    return out;
+  }
   /** ekf.cpp:179-213: closestIdx + copy of the buffered state, Updater::update on it, write-back + re-propagation. */
   std::optional<State> processUpdateMeasurement() {
     if (!dev_) return std::nullopt;

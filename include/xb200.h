@@ -171,6 +171,13 @@ XB_API int xb_ekf_initialize_from_state(xb_filter* f, const double* xvec, const 
 /* Ekf::processImu (ekf.cpp:66-140): 1 = propagated state written to xvec_out (may be NULL), 0 = nullopt. */
 XB_API int xb_ekf_process_imu(xb_filter* f, double timestamp, unsigned seq, const double w_m[3],
                        const double a_m[3], double* xvec_out);
+/* n consecutive Ekf::processImu calls in one (ekf.cpp:66-140 applied per sample: non-increasing timestamps are skipped,
+ * accelerometer spikes repeat the previous reading); the arithmetic of up to 32 samples is three launches instead of one
+ * per sample (the re-propagation kernels of ekf.cpp:227-255).  w_m / a_m: 3 n doubles.  Returns the number of samples that
+ * produced a state; xvec_out (may be NULL) receives the newest state.  Addition to the reference API (a caller that needs
+ * every intermediate state reads them with xb_ekf_get_state). */
+XB_API int xb_ekf_process_imu_batch(xb_filter* f, int n, const double* timestamps, const unsigned* seqs, const double* w_m,
+                                    const double* a_m, double* xvec_out);
 /* VioUpdater::setMeasurement (vio_updater.cpp:122-124) at the preProcess seam: copies the track lists
  * to the device (the only host->device traffic of an update).  Observation arrays that live in page-locked host
  * memory (xb_host_alloc, or the caller's own cudaHostRegister) are copied asynchronously straight from the caller's

@@ -916,3 +916,49 @@ def test_range_and_sun_rows_match_oracle(case, no_overlap, monkeypatch):
     dev.synchronize()
     rp.done()
     dev.close()
+
+
+@pytest.mark.gpu
+def test_imu_batch_equals_per_sample_calls():
+    """xb_ekf_process_imu_batch == the same samples through Ekf::processImu one by one (ekf.cpp:66-140): identical ring
+    bookkeeping (a repeated timestamp is skipped, an accelerometer spike repeats the previous reading), estimates equal to
+    round-off (the batch runs the re-propagation kernels: prefix products instead of a step-by-step recurrence), and a
+    whole sequence with updates in between ends in the same state and covariance."""
+    cfg = SynthConfig(M=6, F=6, K=12, seed=4, n_short=2, churn=1)
+    ev = record(Scenario(cfg), 12)
+    a_dev, b_dev = make_filter(cfg), make_filter(cfg)
+    sa, sb = [], []
+    pending = []
+
+    def flush():
+        if pending:
+            # a duplicate timestamp and an accelerometer spike inside the batch
+            t0, q0, w0, a0 = pending[len(pending) // 2]
+            batch = list(pending) + [(t0, q0, w0, a0)]
+            batch.sort(key=lambda s: s[0])
+            spike = len(batch) - 1
+            batch[spike] = (batch[spike][0], batch[spike][1], batch[spike][2], np.array([500.0, 0.0, 0.0]))
+            for (t, q, w, a) in batch:
+                a_dev.process_imu(t, q, w, a, want_state=False)
+            n = b_dev.process_imu_batch(batch)
+            assert n == len(pending), "the duplicate timestamp must be skipped"
+            pending.clear()
+
+    for e in ev:
+        if e[0] == "init":
+            a_dev.initialize_from_state(e[1]); b_dev.initialize_from_state(e[1])
+        elif e[0] == "imu":
+            pending.append((e[1], e[2], e[3], e[4]))
+        else:
+            flush()
+            assert a_dev.newest_slot() == b_dev.newest_slot()
+            rp0 = np.abs(a_dev.get_state().x - b_dev.get_state().x).max()
+            assert rp0 < 1e-12, rp0
+            for d, out in ((a_dev, sa), (b_dev, sb)):
+                d.set_measurement(e[1])
+                out.append(d.process_update_measurement())
+    rp = Report()
+    rp.check("states, all updates (abs)", max(np.abs(x.x - y.x).max() for x, y in zip(sa, sb)), 1e-11)
+    rp.check("newest covariance", rel(a_dev.get_covariance(), b_dev.get_covariance()), 1e-11)
+    rp.done()
+    a_dev.close(); b_dev.close()

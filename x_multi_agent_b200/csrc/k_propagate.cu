@@ -539,6 +539,19 @@ void launch_prop_strips(cudaStream_t s, double* strip, int N, int NS, int start,
   XB_LAUNCH(k_prop_strips, grid, 128, 0, s, strip, N, NS, start, n_steps, FQ, second);
   count_launch();
 }
+// IMU fields (w_m, a_m, time, seq: xvec 23..30) of the n slots after `start`, written before a batched propagation
+// (State::setImu, state.cpp:145-151): the samples travel as kernel arguments, no staging buffer
+__global__ void k_imu_scatter(double* __restrict__ xv, int LX, int NS, int start, int n, ImuBatch b) {
+  XB_PDL_SHORT();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * 8) return;
+  const int j = e >> 3, c = e & 7;
+  xv[(size_t)((start + 1 + j) % NS) * LX + XV_WM + c] = b.v[j][c];
+}
+void launch_imu_scatter(cudaStream_t s, double* xv, int LX, int NS, int start, int n, const ImuBatch& b) {
+  XB_LAUNCH(k_imu_scatter, (n * 8 + 127) / 128, 128, 0, s, xv, LX, NS, start, n, b);
+  count_launch();
+}
 void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,
                       const ImuSample& in, const PropParams& pp, double* FQ) {
   launch_prop_means(s, xv, LX, NS, start, n_steps, in, pp, FQ);

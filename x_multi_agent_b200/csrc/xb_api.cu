@@ -792,6 +792,65 @@ extern "C" int xb_ekf_process_imu(xb_filter* f, double t, unsigned seq, const do
   return 1;
 }
 
+// A run of Ekf::processImu calls (ekf.cpp:66-140) in one go: the per-sample host logic (time must increase, accelerometer
+// spikes repeat the last reading, ring enqueue) runs for every sample, the arithmetic of up to XB_IMU_BATCH accepted samples
+// is three launches (IMU fields into their slots, all means by one CTA per step, all covariance strips through prefix
+// products -- the kernels of Ekf::repropagateFromStateAtIdx) instead of one launch per sample.  Returns the number of
+// samples that produced a state; xvec_out (optional) receives the newest one.
+extern "C" int xb_ekf_process_imu_batch(xb_filter* f, int n, const double* t, const unsigned* seq, const double* w,
+                                        const double* a, double* xvec_out) {
+  if (!f || n < 0 || (n > 0 && (!t || !seq || !w || !a))) return fail(XB_E_INVALID, "null argument");
+  int done = 0, i = 0;
+  if (f->status == 0) return 0;
+  while (i < n && f->status == 1) {  // the first accepted sample only initialises the newest state's IMU fields
+    const int rc = xb_ekf_process_imu(f, t[i], seq[i], w + 3 * i, a + 3 * i, nullptr);
+    if (rc < 0) return rc;
+    done += rc;
+    ++i;
+  }
+  while (i < n) {
+    ImuBatch b;
+    const int start = f->tail;
+    int m = 0;
+    double t_prev = f->h_time[f->tail];
+    for (; i < n && m < XB_IMU_BATCH && m < f->NS - 1; ++i) {
+      if (t[i] <= t_prev) continue;  // ekf.cpp:97
+      const double an = std::sqrt(a[3 * i] * a[3 * i] + a[3 * i + 1] * a[3 * i + 1] + a[3 * i + 2] * a[3 * i + 2]);
+      const int prev = f->tail;
+      f->last_seq = seq[i];
+      f->tail = (f->tail + 1) % f->NS;   // StateBuffer::enqueueInPlace (state_buffer.cpp:76-88)
+      if (f->n_valid < f->NS) ++f->n_valid; else f->head = (f->head + 1) % f->NS;
+      for (int e = 0; e < 3; ++e) {
+        b.v[m][e] = w[3 * i + e];
+        b.v[m][3 + e] = (an < f->cfg.a_m_max) ? a[3 * i + e] : f->h_am[3 * prev + e];  // accelerometer spike (ekf.cpp:84-92)
+        f->h_am[3 * f->tail + e] = b.v[m][3 + e];
+      }
+      b.v[m][6] = t[i];
+      b.v[m][7] = (double)seq[i];
+      f->h_time[f->tail] = t[i];
+      f->slot_gen[f->tail] = f->slot_gen[prev];
+      f->slot_asym[f->tail] = f->slot_asym[prev];
+      f->slot_serial[f->tail] = ++f->serial;
+      t_prev = t[i];
+      ++m;
+    }
+    if (m == 0) continue;
+    if (m == 1) {   // a single sample: the fused one-launch step
+      ImuSample in;
+      in.valid = 1; in.t = b.v[0][6]; in.seq = b.v[0][7];
+      for (int e = 0; e < 3; ++e) { in.w[e] = b.v[0][e]; in.a[e] = b.v[0][3 + e]; }
+      propagate_chain(f, start, 1, in);
+    } else {
+      ImuSample none{};
+      launch_imu_scatter(f->stream, f->d_xv, f->LX, f->NS, start, m, b);
+      propagate_chain(f, start, m, none);
+    }
+    done += m;
+  }
+  if (xvec_out && done > 0 && xb_ekf_get_state(f, f->tail, xvec_out) < 0) return XB_E_CUDA;
+  return done;
+}
+
 extern "C" int xb_ekf_get_state(xb_filter* f, int slot, double* xvec_out) {
   if (slot < 0) slot = f->tail;
   if (slot >= f->NS) return fail(XB_E_INVALID, "bad slot");

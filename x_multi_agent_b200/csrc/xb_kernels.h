@@ -41,6 +41,9 @@ inline void xb_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
 // ---- propagation --------------------------------------------------------------------------------
 struct ImuSample { int valid; double t, seq, w[3], a[3]; };
 struct PropParams { double g[3]; double n_w, n_bw, n_a, n_ba; };
+#define XB_IMU_BATCH 32
+struct ImuBatch { double v[XB_IMU_BATCH][8]; };   // per sample: w_m[3], a_m[3], time, seq (the xvec order 23..30)
+void launch_imu_scatter(cudaStream_t s, double* xv, int LX, int NS, int start, int n, const ImuBatch& b);
 void launch_propagate(cudaStream_t s, double* xv, int LX, double* strip, int N, int NS, int start, int n_steps,
                       const ImuSample& in, const PropParams& pp, double* FQ);
 // one IMU step (means + row strips) in a single launch

@@ -215,6 +215,19 @@ class Filter:
             return None
         return State(self.M, self.F, out) if want_state else True
 
+    def process_imu_batch(self, samples, want_state=False):
+        """A run of Ekf::processImu calls in one (xb_ekf_process_imu_batch): samples = [(t, seq, w_m, a_m), ...].  Returns the
+        number of samples that produced a state (and the newest state when want_state)."""
+        n = len(samples)
+        t = np.ascontiguousarray([s[0] for s in samples], dtype=np.float64)
+        sq = np.ascontiguousarray([s[1] for s in samples], dtype=np.uint32)
+        w = np.ascontiguousarray([s[2] for s in samples], dtype=np.float64).reshape(-1)
+        a = np.ascontiguousarray([s[3] for s in samples], dtype=np.float64).reshape(-1)
+        out = np.empty(self.LX) if want_state else None
+        rc = L.check(self.lib.xb_ekf_process_imu_batch(self.h, n, L.dptr(t), sq.ctypes.data_as(C.POINTER(C.c_uint)), L.dptr(w),
+                                                       L.dptr(a), L.dptr(out)))
+        return (rc, State(self.M, self.F, out) if rc > 0 else None) if want_state else rc
+
     def set_measurement(self, m):
         pm = m if isinstance(m, PackedMeasurement) else PackedMeasurement(m)
         self._pm = pm

@@ -104,6 +104,7 @@ SIGNATURES = {
     "xb_xvec_len": (C.c_int, [_VP]),
     "xb_ekf_initialize_from_state": (C.c_int, [_VP, c_double_p, c_double_p, C.c_int]),
     "xb_ekf_process_imu": (C.c_int, [_VP, C.c_double, C.c_uint, c_double_p, c_double_p, c_double_p]),
+    "xb_ekf_process_imu_batch": (C.c_int, [_VP, C.c_int, c_double_p, C.POINTER(C.c_uint), c_double_p, c_double_p, c_double_p]),
     "xb_vio_set_measurement": (C.c_int, [_VP, C.POINTER(XbMeasurement)]),
     "xb_vio_set_sensors": (C.c_int, [_VP, C.POINTER(XbRangeMeasurement), C.POINTER(XbSunAngleMeasurement)]),
     "xb_host_alloc": (_VP, [C.c_size_t]),
