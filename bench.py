@@ -266,6 +266,7 @@ def main():
     import torch
     import torch.distributed as dist
     from x_multi_agent_b200 import Filter, PackedMeasurement
+    from x_multi_agent_b200.filter import PackedMsckfMatches
     from x_multi_agent_b200.synth import replay
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -464,7 +465,7 @@ def main():
             lms = scn.last_msckf_lms
             win = list(range(k0 + j - CFG2["M"], k0 + j))     # frames held by a peer's window when it packs its payload
             mt = [(p, 0, a * 32 + q, peer_scn[p]._project(lms[a * 32 + q], win)) for a, p in enumerate(peers) for q in range(32)]
-            steps_d.append((imu, PackedMeasurement(m), mt))
+            steps_d.append((imu, PackedMeasurement(m), PackedMsckfMatches(mt)))
         d0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd + NPROF)]
         d1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + Kd + NPROF)]
         acc, gated = [], []
@@ -500,7 +501,7 @@ def main():
         tmm = torch.tensor([mm_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmm, op=dist.ReduceOp.MAX)
         mm = {"multi_uav_updates_per_sec": world * Kd / (float(tmm[0]) * 1e-3), "ms_per_step": float(tmm[0]) / Kd, "steps": Kd,
-              "msckf_matches_per_step": len(steps_d[0][2]), "own_gate_passed_frac_rank0": float(np.mean(gated[W:W + Kd])),
+              "msckf_matches_per_step": steps_d[0][2].n, "own_gate_passed_frac_rank0": float(np.mean(gated[W:W + Kd])),
               "joint_gate_accepted_frac_rank0": float(np.mean(acc[W:W + Kd])), "pose_payload_bytes_per_agent": PP * 8,
               "collective": "all_gather (NCCL), one per update",
               "stage_ms_rank0": {k: round(v[0] / max(v[1], 1), 4) for k, v in sorted(mm_prof.items(), key=lambda kv: -kv[1][0])

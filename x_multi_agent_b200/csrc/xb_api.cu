@@ -255,6 +255,12 @@ struct xb_filter {
   int *d_mm_grp = nullptr, *d_mm_ent = nullptr, *d_mm_trkgrp = nullptr, *d_mm_last = nullptr;
   int mm_pp_len = 0, mm_max_groups = 512, mm_max_entries = 1024, mm_G = 0, mm_max_tracks = 0;
   int mm_last_G[2] = {0, 0};
+  // page-locked staging of the match-group tables (two regions, each guarded by an event: no stream synchronisation)
+  char* h_mm = nullptr;
+  size_t mm_pin_bytes = 0;
+  int mm_pin_cur = 0;
+  cudaEvent_t mm_pin_ev[2] = {nullptr, nullptr};
+  std::vector<double> chi95_cache;  // chi2(0.95, 2 n_obs - 3) by n_obs (msckf_update.cpp:243-247), filled lazily
   int omega_slot = -2;
   bool corr_zero = false;  // correction_total is known to be all-zero (first IEKF iteration)
   std::vector<void*> allocs;
@@ -551,6 +557,12 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
   if (cudaMallocHost((void**)&f->h_ipin, sizeof(int) * f->ipin_ints * xb_filter::kPinRing) != cudaSuccess)
     return fail(XB_E_CUDA, "cudaMallocHost failed");
   if (cudaMallocHost((void**)&f->h_err, sizeof(int)) != cudaSuccess) return fail(XB_E_CUDA, "cudaMallocHost failed");
+  f->mm_pin_bytes = sizeof(int) * (4 * (size_t)f->mm_max_groups + 3 * (size_t)f->mm_max_entries + (size_t)f->mm_max_tracks + 8) +
+                    sizeof(double) * (2 * (size_t)f->mm_max_entries * f->M + (size_t)f->mm_max_groups + 8);
+  f->mm_pin_bytes = (f->mm_pin_bytes + 255) / 256 * 256;
+  if (cudaMallocHost((void**)&f->h_mm, 2 * f->mm_pin_bytes) != cudaSuccess) return fail(XB_E_CUDA, "cudaMallocHost failed");
+  for (auto& e : f->mm_pin_ev)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(XB_E_CUDA, "cudaEventCreate failed");
   *f->h_err = 0;
   for (int i = 0; i < xb_filter::kPinRing; ++i) {
     CK(cudaEventCreateWithFlags(&f->pin_ev[i], cudaEventDisableTiming));
@@ -574,6 +586,8 @@ extern "C" int xb_destroy(xb_filter* f) {
   if (f->h_pin) cudaFreeHost(f->h_pin);
   if (f->h_ipin) cudaFreeHost(f->h_ipin);
   if (f->h_err) cudaFreeHost(f->h_err);
+  if (f->h_mm) cudaFreeHost(f->h_mm);
+  for (auto e : f->mm_pin_ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < xb_filter::kPinRing; ++i) {
     if (f->pin_ev[i]) cudaEventDestroy(f->pin_ev[i]);
     if (f->ipin_ev[i]) cudaEventDestroy(f->ipin_ev[i]);
@@ -1240,19 +1254,32 @@ static int mm_prepare(xb_filter* f, int which, const ListDev& l0, MmParams& mp) 
       n_tot += m.n_obs;
     }
     grp.push_back(n_tot);
-    chi.push_back(xb_chi2_quantile(0.95, 2.0 * n_tot - 3.0));  // msckf_update.cpp:243-247
+    if ((size_t)n_tot >= f->chi95_cache.size()) f->chi95_cache.resize((size_t)n_tot + 1, -1.0);
+    if (f->chi95_cache[n_tot] < 0.0) f->chi95_cache[n_tot] = xb_chi2_quantile(0.95, 2.0 * n_tot - 3.0);  // msckf_update.cpp:243-247
+    chi.push_back(f->chi95_cache[n_tot]);
     trkgrp[j] = g;
   }
   f->mm_G = (int)grp.size() / 4;
   if (f->mm_G == 0) return 0;
   int rc = check_ci_weight(f->cfg.ci_msckf_w);  // ci.cpp:59-62
   if (rc) return rc;
-  CK(cudaMemcpyAsync(f->d_mm_grp, grp.data(), sizeof(int) * grp.size(), cudaMemcpyHostToDevice, f->stream));
-  CK(cudaMemcpyAsync(f->d_mm_ent, ent.data(), sizeof(int) * ent.size(), cudaMemcpyHostToDevice, f->stream));
-  CK(cudaMemcpyAsync(f->d_mm_trkgrp, trkgrp.data(), sizeof(int) * trkgrp.size(), cudaMemcpyHostToDevice, f->stream));
-  CK(cudaMemcpyAsync(f->d_mm_pobs, pobs.data(), sizeof(double) * pobs.size(), cudaMemcpyHostToDevice, f->stream));
-  CK(cudaMemcpyAsync(f->d_mm_chi2, chi.data(), sizeof(double) * chi.size(), cudaMemcpyHostToDevice, f->stream));
-  CK(cudaStreamSynchronize(f->stream));  // the staging vectors die with this frame
+  // through a page-locked region guarded by an event (the tables die with this frame, the copies are asynchronous): no
+  // stream synchronisation, so the host keeps enqueueing the update while the device still works on what came before
+  if ((int)trkgrp.size() > f->mm_max_tracks) return fail(XB_E_CAPACITY, "too many tracks for the match-group table");
+  f->mm_pin_cur ^= 1;
+  CK(cudaEventSynchronize(f->mm_pin_ev[f->mm_pin_cur]));
+  char* pin = f->h_mm + f->mm_pin_bytes * f->mm_pin_cur;
+  auto stage = [&](void* dst, const void* src, size_t bytes) -> int {
+    std::memcpy(pin, src, bytes);
+    CK(cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, f->stream));
+    pin += (bytes + 15) / 16 * 16;
+    return 0;
+  };
+  if (stage(f->d_mm_grp, grp.data(), sizeof(int) * grp.size()) || stage(f->d_mm_ent, ent.data(), sizeof(int) * ent.size()) ||
+      stage(f->d_mm_trkgrp, trkgrp.data(), sizeof(int) * trkgrp.size()) ||
+      stage(f->d_mm_pobs, pobs.data(), sizeof(double) * pobs.size()) || stage(f->d_mm_chi2, chi.data(), sizeof(double) * chi.size()))
+    return XB_E_CUDA;
+  CK(cudaEventRecord(f->mm_pin_ev[f->mm_pin_cur], f->stream));
   mp = mm_params(f, l0, which);
   return f->mm_G;
 }

@@ -163,6 +163,16 @@ class PackedMeasurement:
         self._pinned = []
 
 
+class PackedMsckfMatches:
+    """MsckfMatches (include/x/vision/types.h:83-100) marshalled once into the xb_msckf_match array the C ABI takes -- the
+    form in which a C++ front end hands them over anyway; keeps the observation buffers alive."""
+
+    def __init__(self, matches):
+        self.keep = []
+        self.n = len(matches)
+        self.c = Filter._msckf_matches(matches, self.keep)
+
+
 class Filter:
     """One agent's filter on one GPU: x::Ekf + x::VioUpdater + x::StateManager behind the C ABI."""
 
@@ -284,9 +294,9 @@ class Filter:
         L.check(self.lib.xb_vio_set_msckf_matches(self.h, cp, len(peers), cm, len(matches)))
 
     def set_msckf_matches_packed(self, gathered_dev_ptr, n_agents, matches):
-        keep = []
-        cm = self._msckf_matches(matches, keep)
-        L.check(self.lib.xb_vio_set_msckf_matches_packed(self.h, C.c_void_p(gathered_dev_ptr), n_agents, cm, len(matches)))
+        """matches: a list of (peer, which, own_track_idx, received_track) or a PackedMsckfMatches (marshalled once)."""
+        pm = matches if isinstance(matches, PackedMsckfMatches) else PackedMsckfMatches(matches)
+        L.check(self.lib.xb_vio_set_msckf_matches_packed(self.h, C.c_void_p(gathered_dev_ptr), n_agents, pm.c, pm.n))
 
     def pose_payload_len(self):
         return self.lib.xb_ci_pose_payload_len(self.h)
