@@ -255,6 +255,10 @@ struct xb_filter {
   int *d_mm_grp = nullptr, *d_mm_ent = nullptr, *d_mm_trkgrp = nullptr, *d_mm_last = nullptr;
   int mm_pp_len = 0, mm_max_groups = 512, mm_max_entries = 1024, mm_G = 0, mm_max_tracks = 0;
   int mm_last_G[2] = {0, 0};
+  // MULTI_UAV with MSCKF-MSCKF matches: the Gram stage of constructUpdate is deferred to applyUpdate so that it runs next
+  // to the SLAM-column part, which can only start once the CI corrections have changed P (updater.cpp:84-97)
+  bool gram_deferred = false;
+  GramParams gram_gp{};
   // page-locked staging of the match-group tables (two regions, each guarded by an event: no stream synchronisation)
   char* h_mm = nullptr;
   size_t mm_pin_bytes = 0;
@@ -1284,6 +1288,11 @@ static int mm_prepare(xb_filter* f, int which, const ListDev& l0, MmParams& mp) 
   return f->mm_G;
 }
 
+static UpdateDims update_dims(const xb_filter* f, int nslam, int nw);
+static int set_omega(xb_filter* f);
+static size_t tall_bytes(const UpdateDims& d);
+static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int stage_build, int stage_chol, int share,
+                       bool with_rows);
 extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   materialize(f);
@@ -1294,6 +1303,21 @@ extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
   MmParams mp = mm_params(f, l0, f->last_which);
   launch_mm_apply(f->stream, mp, f->d_Pw, f->d_xw, f->F, f->d_mm_V, f->mm_max_groups, f->d_mm_D, f->d_mm_K3, f->d_mm_HP3);
   f->mm_G = 0;
+  if (f->gram_deferred && f->last_which == 0 && f->last_nslam + f->last_nw > 0) {
+    // P is final for the applyUpdate that follows: its SLAM-column half (rows linearised before the CI corrections,
+    // S = H P H^T with the corrected P) goes to the side stream, the deferred Gram stage runs next to it on the caller's
+    const UpdateDims d = update_dims(f, f->last_nslam, f->last_nw);
+    int rc0 = set_omega(f);
+    if (rc0) return rc0;
+    CK(cudaMemsetAsync(f->d_T, 0, tall_bytes(d), f->stream));
+    CK(cudaEventRecord(f->ev_fork, f->stream));
+    CK(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+    slam_phase(f, f->side, d, ST_SIDE_SLAM, ST_SIDE_CHOL, f->chol_share, false);
+    CK(cudaEventRecord(f->ev_side, f->side));
+    f->side_pending = true;
+    f->slam_part_done = true;
+    f->side_used_corr = !f->corr_zero;
+  }
   return XB_OK;
 }
 
@@ -1355,9 +1379,20 @@ static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int s
 }
 static size_t tall_bytes(const UpdateDims& d) { return sizeof(double) * (size_t)(d.m_pad + d.n_pad + 96) * d.m_pad; }
 
+// Gram stage of constructUpdate: G = [J|r]^T[J|r] - [B|b]^T[B|b] (+ D^T D), then its guarded Cholesky factor
+static void run_gram(xb_filter* f, const GramParams& gp) {
+  { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp, f->overlap ? f->side3 : nullptr, f->ev_g0, f->ev_g1); }
+  StageTimer st_(f, ST_CHOLG);
+  tallchol_range(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, 0, f->gcols_pad, 0, f->d_flags_g, f->d_err, 1e-14,
+                 f->d_diag0, nullptr, f->side_pending ? f->chol_share : 1);
+  // Rg = L_G^T is only materialised for the CUDA-core GEMM fallback (and on demand for xb_debug_read("Rg"))
+  if (!gemm_uses_tensor_cores()) transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
+}
+
 extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   materialize(f);
+  f->gram_deferred = false;
   const int M = f->M;
   const ListDev& l0 = which == 0 ? f->l_msckf : f->l_short;
   const int n0 = l0.n, n1 = which == 0 ? f->l_newms.n : 0, ns = which == 0 ? f->l_slam.n : 0;
@@ -1444,12 +1479,13 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
     gp.off = l0.d_off; gp.inlier = f->d_inl0; gp.n_tracks_msckf = n0; gp.Jout = f->d_J0;
     gp.blocks = f->d_blocks;
     gp.T = f->d_Tg; gp.ld = f->gcols_pad; gp.rows_pad = f->grows_pad; gp.cols_pad = f->gcols_pad; gp.diag0 = f->d_diag0;
-    { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp, f->overlap ? f->side3 : nullptr, f->ev_g0, f->ev_g1); }
-    StageTimer st_(f, ST_CHOLG);
-    tallchol_range(f->stream, f->d_Tg, f->gcols_pad, f->grows_pad, f->gcols_pad, 0, f->gcols_pad, 0, f->d_flags_g, f->d_err, 1e-14,
-                   f->d_diag0, nullptr, f->side_pending ? f->chol_share : 1);
-    // Rg = L_G^T is only materialised for the CUDA-core GEMM fallback (and on demand for xb_debug_read("Rg"))
-    if (!gemm_uses_tensor_cores()) transpose(f->stream, f->d_Tg, f->d_Rg, f->gcols_pad, f->gcols_pad);
+    static const bool no_defer = getenv("XB_NO_MM_DEFER") != nullptr;
+    if (f->cfg.multi_uav && f->mm_last_G[which] > 0 && f->overlap && ns + nw > 0 && f->asym_clones <= 1 && !no_defer) {
+      f->gram_gp = gp;
+      f->gram_deferred = true;
+      return XB_OK;
+    }
+    run_gram(f, gp);
   } else {
     CK(cudaMemsetAsync(f->d_Tg, 0, gbytes, f->stream));
     if (!gemm_uses_tensor_cores())
@@ -1572,6 +1608,10 @@ extern "C" int xb_updater_apply_constructed(xb_filter* f, int cov_update) {
   if (!f->d_Pw) return fail(XB_E_INVALID, "no work state loaded");
   materialize(f);
   if (!f->constructed_any) return XB_OK;  // h.size() == 0 (updater.cpp:106)
+  if (f->gram_deferred) {
+    run_gram(f, f->gram_gp);
+    f->gram_deferred = false;
+  }
   const UpdateDims d = update_dims(f, f->last_nslam, f->last_nw);
   const double var = f->cfg.sigma_img * f->cfg.sigma_img;
   const double* corr = f->corr_zero ? nullptr : f->d_corr;
