@@ -1291,6 +1291,7 @@ static int mm_prepare(xb_filter* f, int which, const ListDev& l0, MmParams& mp) 
 static UpdateDims update_dims(const xb_filter* f, int nslam, int nw);
 static int set_omega(xb_filter* f);
 static size_t tall_bytes(const UpdateDims& d);
+static int early_downdate(xb_filter* f, const UpdateDims& d);
 static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int stage_build, int stage_chol, int share,
                        bool with_rows);
 extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
@@ -1314,6 +1315,7 @@ extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
     CK(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
     slam_phase(f, f->side, d, ST_SIDE_SLAM, ST_SIDE_CHOL, f->chol_share, false);
     CK(cudaEventRecord(f->ev_side, f->side));
+    if (early_downdate(f, d)) return XB_E_CUDA;
     f->side_pending = true;
     f->slam_part_done = true;
     f->side_used_corr = !f->corr_zero;
@@ -1379,6 +1381,24 @@ static void slam_phase(xb_filter* f, cudaStream_t st, const UpdateDims& d, int s
 }
 static size_t tall_bytes(const UpdateDims& d) { return sizeof(double) * (size_t)(d.m_pad + d.n_pad + 96) * d.m_pad; }
 
+// sym(P) - W1s W1s^T (the SLAM-column part of the covariance downdate, 68 % of its flops at cfg-2) into a spare covariance
+// buffer on a second side stream as soon as the SLAM columns are factored (ev_side); apply finishes it in place
+static int early_downdate(xb_filter* f, const UpdateDims& d) {
+  const int nt64 = (f->N + 63) / 64;
+  const bool dd_early = (f->cfg.iekf_iter <= 1 || f->cfg.multi_uav) && f->cfg.downdate_precision == 0 &&
+                        nt64 * (nt64 + 1) / 2 < 296 && !getenv("XB_NO_EARLY_DOWNDATE");
+  if (!dd_early) return 0;
+  f->d_dd = f->d_spare;
+  CK(cudaStreamWaitEvent(f->side2, f->ev_side, 0));
+  StageTimer st_(f, ST_SIDE_DD, f->side2);
+  downdate_f64_range(f->side2, f->d_Pw, f->d_dd, f->N, f->d_T, d.m_pad, d.n_pad, 0, d.s_pad, 1, 0, f->d_omega_inv, f->d_Zb,
+                     f->d_Yb, f->d_Qb);
+  CK(cudaEventRecord(f->ev_dd, f->side2));
+  f->dd_pending = true;
+  f->dd_cols = d.s_pad;
+  return 0;
+}
+
 // Gram stage of constructUpdate: G = [J|r]^T[J|r] - [B|b]^T[B|b] (+ D^T D), then its guarded Cholesky factor
 static void run_gram(xb_filter* f, const GramParams& gp) {
   { StageTimer st_(f, ST_GRAM); launch_gram(f->stream, gp, f->overlap ? f->side3 : nullptr, f->ev_g0, f->ev_g1); }
@@ -1432,21 +1452,7 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
       CK(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
       slam_phase(f, f->side, d, ST_SIDE_SLAM, ST_SIDE_CHOL, f->chol_share, true);
       CK(cudaEventRecord(f->ev_side, f->side));
-      {
-        const int nt64 = (f->N + 63) / 64;
-        const bool dd_early = f->cfg.iekf_iter <= 1 && f->cfg.downdate_precision == 0 && nt64 * (nt64 + 1) / 2 < 296 &&
-                              !getenv("XB_NO_EARLY_DOWNDATE");
-        if (dd_early) {
-          f->d_dd = f->d_spare;
-          CK(cudaStreamWaitEvent(f->side2, f->ev_side, 0));
-          StageTimer st_(f, ST_SIDE_DD, f->side2);
-          downdate_f64_range(f->side2, f->d_Pw, f->d_dd, f->N, f->d_T, d.m_pad, d.n_pad, 0, d.s_pad, 1, 0, f->d_omega_inv, f->d_Zb,
-                             f->d_Yb, f->d_Qb);
-          CK(cudaEventRecord(f->ev_dd, f->side2));
-          f->dd_pending = true;
-          f->dd_cols = d.s_pad;
-        }
-      }
+      if (early_downdate(f, d)) return XB_E_CUDA;
       f->side_pending = true;
       f->slam_part_done = true;
       f->side_used_corr = !f->corr_zero;
