@@ -191,17 +191,22 @@ static __host__ __device__ size_t mm_smem_doubles(int Lm) {
 }
 
 // ---- per-group construction: peers' 3-row blocks, nullspace, gate, CI --------------------------------------------------
-__global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
+// MM_NW warps per group: warp 0 runs the (short, serial) geometry; the two covariance products M = B P B^T -- 6M columns x
+// 6M rows of L2-resident covariance each, 95 us apiece when one warp walks them -- are spread over all warps.
+#define MM_NW 6
+__global__ void __launch_bounds__(32 * MM_NW) k_mm_construct(MmParams mp) {
   extern __shared__ double sm[];
-  const int lane = threadIdx.x, g = blockIdx.x;
+  __shared__ double Mpart[MM_NW][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = blockIdx.x;
+  const bool is_w0 = warp == 0;
   const int M = mp.M, N = mp.N, np = mp.n_poses, W = 6 * M + 1;
   const int* gd = mp.grp + 4 * g;
   const int trk = gd[0], k = gd[1], e0 = gd[2], n_tot = gd[3];
   double* rec = mp.rec + (size_t)XB_MM_REC * g;
   const int o0 = mp.off[trk], L = mp.off[trk + 1] - o0, i1 = np - L;
-  if (lane < XB_MM_REC) rec[lane] = 0.0;
+  if (is_w0 && lane < XB_MM_REC) rec[lane] = 0.0;
   __syncwarp();
-  if (lane == 0) { rec[16] = trk; rec[17] = i1; rec[18] = L; rec[19] = k; rec[1] = NAN; rec[2] = mp.chi2[g]; }
+  if (is_w0 && lane == 0) { rec[16] = trk; rec[17] = i1; rec[18] = L; rec[19] = k; rec[1] = NAN; rec[2] = mp.chi2[g]; }
   // proceed_with_multi_: the own track must have passed its own gate (msckf_update.cpp:476-481)
   if (!mp.inlier[trk] || k < 1 || k > XB_MM_KMAX) return;
 
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
   const double* B0 = mp.B + (size_t)trk * 3 * W;
   {
     double m0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int c = lane; c < 6 * M; c += 32) {
+    for (int c = threadIdx.x; c < 6 * M; c += 32 * MM_NW) {
       double t0 = 0.0, t1 = 0.0, t2 = 0.0;
       for (int i = 0; i < L; ++i)
         for (int blk = 0; blk < 2; ++blk)
@@ -258,12 +263,20 @@ __global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
       }
     }
     for (int e = 0; e < 9; ++e) m0[e] = xb_warp_sum(m0[e]);
-    if (lane == 0) {
-      for (int e = 0; e < 9; ++e) { Mi[e] = m0[e]; Fs[e] = mp.F0[9 * (size_t)g + e]; }
+    if (lane == 0)
+      for (int e = 0; e < 9; ++e) Mpart[warp][e] = m0[e];
+    __syncthreads();
+    if (is_w0 && lane == 0) {
+      for (int e = 0; e < 9; ++e) {
+        double v = 0.0;
+        for (int w = 0; w < MM_NW; ++w) v += Mpart[w][e];   // fixed order
+        Mi[e] = v;
+        Fs[e] = mp.F0[9 * (size_t)g + e];
+      }
       for (int u = 0; u < 3; ++u) bs[u] = B0[u * W + 6 * M];
     }
   }
-  __syncwarp();
+  __syncthreads();
 
   // ---- peers: processOneTrack(..., is_multi_msckf = true) on the peer's poses with the joint feature position
   for (int e = 0; e < k; ++e) {
@@ -274,6 +287,9 @@ __global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
     const double* pq = pp + 8 + 3 * M;
     const double* pcov = pp + 8 + 7 * M;  // 6M x 6M row-major
     const double* z = mp.pobs + 2 * (size_t)en[1];
+    double ur[3] = {0, 0, 0};
+    double fi[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (is_w0) {
     for (int i = lane; i < Lp; i += 32) {
       double R[9];
       xb_rot(pq + 4 * (s0 + i), R);
@@ -326,7 +342,6 @@ __global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
       __syncwarp();
     }
     // B_i (compact columns), b_i, F_i
-    double ur[3] = {0, 0, 0};
     for (int i = lane; i < Lp; i += 32) {
       const double* U0 = U + 6 * i;
       for (int u = 0; u < 3; ++u) {
@@ -338,13 +353,13 @@ __global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
       }
     }
     for (int u = 0; u < 3; ++u) ur[u] = xb_warp_sum(ur[u]);
-    double fi[9];
     for (int u = 0; u < 3; ++u)
       for (int c = 0; c < 3; ++c) fi[u * 3 + c] = mm_wdot(U + u, 3, Hf + c, 3, R2, lane);
-    __syncwarp();
-    // M_i = B_i P_i B_i^T on the peer's pose covariance block
+    }  // warp 0
+    __syncthreads();
+    // M_i = B_i P_i B_i^T on the peer's pose covariance block (all warps)
     double mi[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int cc = lane; cc < C6; cc += 32) {
+    for (int cc = threadIdx.x; cc < C6; cc += 32 * MM_NW) {
       const int gc = (cc < 3 * Lp) ? 3 * s0 + cc : 3 * M + 3 * s0 + (cc - 3 * Lp);
       double t0 = 0.0, t1 = 0.0, t2 = 0.0;
       for (int rr = 0; rr < C6; ++rr) {
@@ -362,12 +377,21 @@ __global__ void __launch_bounds__(32) k_mm_construct(MmParams mp) {
       }
     }
     for (int q = 0; q < 9; ++q) mi[q] = xb_warp_sum(mi[q]);
-    if (lane == 0) {
-      for (int q = 0; q < 9; ++q) { Mi[9 * (e + 1) + q] = mi[q]; Fs[9 * (e + 1) + q] = fi[q]; }
+    if (lane == 0)
+      for (int q = 0; q < 9; ++q) Mpart[warp][q] = mi[q];
+    __syncthreads();
+    if (is_w0 && lane == 0) {
+      for (int q = 0; q < 9; ++q) {
+        double v = 0.0;
+        for (int w = 0; w < MM_NW; ++w) v += Mpart[w][q];   // fixed order
+        Mi[9 * (e + 1) + q] = v;
+        Fs[9 * (e + 1) + q] = fi[q];
+      }
       for (int u = 0; u < 3; ++u) bs[3 * (e + 1) + u] = ur[u];
     }
-    __syncwarp();
+    __syncthreads();
   }
+  if (!is_w0) return;   // nullspace, gate and CI fusion are 3 (k + 1) x 3 problems: one warp
   (void)Tc;
 
   // ---- nullSpaceProjection (msckf_update.cpp:494-501): full Householder Q of the stacked 3(k+1) x 3 feature Jacobian
@@ -488,7 +512,7 @@ int launch_mm_construct(cudaStream_t s, const MmParams& mp) {
   if (bytes > 200 * 1024) return -1;
   cudaMemsetAsync(mp.last, 0xFF, sizeof(int), s);
   cudaFuncSetAttribute(k_mm_construct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  k_mm_construct<<<mp.n_groups, 32, bytes, s>>>(mp);
+  k_mm_construct<<<mp.n_groups, 32 * MM_NW, bytes, s>>>(mp);
   count_launch();
   return 0;
 }

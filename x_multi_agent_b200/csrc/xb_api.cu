@@ -100,11 +100,13 @@ struct ListDev {
 };
 
 enum { ST_ASSEMBLE, ST_MANAGE, ST_TRACKS, ST_GRAM, ST_CHOLG, ST_SLAMROWS, ST_BUILD, ST_TALLCHOL, ST_CORRECT, ST_DOWNDATE,
-       ST_POST, ST_STORE, ST_PROPAGATE, ST_SIDE_SLAM, ST_SIDE_CHOL, ST_SIDE_MEANS, ST_SIDE_DD, ST_COUNT };
+       ST_POST, ST_STORE, ST_PROPAGATE, ST_SIDE_SLAM, ST_SIDE_CHOL, ST_SIDE_MEANS, ST_SIDE_DD, ST_MM_TRI, ST_MM_CON, ST_MM_APPLY,
+       ST_COUNT };
 // the "side_*" stages run on the filter's internal side streams, concurrently with the stages listed before them
 static const char* kStageNames[ST_COUNT] = {"assemble", "manage", "tracks", "gram", "chol_gram", "slam_rows", "build_s_pht",
                                             "tallchol", "correct", "downdate", "post_update", "store", "propagate",
-                                            "side_slam_part", "side_tallchol_slam_cols", "side_prop_means", "side_downdate_slam_cols"};
+                                            "side_slam_part", "side_tallchol_slam_cols", "side_prop_means", "side_downdate_slam_cols",
+                                            "mm_triangulate", "mm_construct", "mm_apply_ci"};  // the mm_* spans lie inside "tracks" / between stages
 static_assert(ST_COUNT <= XB_MAX_STAGES, "xb_profile_read callers size their arrays with XB_MAX_STAGES");
 struct ProfSpan { int stage; cudaEvent_t e0, e1; };
 
@@ -1302,7 +1304,10 @@ extern "C" int xb_updater_apply_ci_lists(xb_filter* f) {
   if (invalidate_early(f)) return XB_E_CUDA;
   const ListDev& l0 = f->last_which == 0 ? f->l_msckf : f->l_short;
   MmParams mp = mm_params(f, l0, f->last_which);
-  launch_mm_apply(f->stream, mp, f->d_Pw, f->d_xw, f->F, f->d_mm_V, f->mm_max_groups, f->d_mm_D, f->d_mm_K3, f->d_mm_HP3);
+  {
+    StageTimer st_(f, ST_MM_APPLY);
+    launch_mm_apply(f->stream, mp, f->d_Pw, f->d_xw, f->F, f->d_mm_V, f->mm_max_groups, f->d_mm_D, f->d_mm_K3, f->d_mm_HP3);
+  }
   f->mm_G = 0;
   if (f->gram_deferred && f->last_which == 0 && f->last_nslam + f->last_nw > 0) {
     // P is final for the applyUpdate that follows: its SLAM-column half (rows linearised before the CI corrections,
@@ -1469,11 +1474,15 @@ extern "C" int xb_vio_construct_update(xb_filter* f, int which) {
       StageTimer st_(f, ST_TRACKS);
       TrackParams tp0 = track_params(f, l0, 0);
       if (f->mm_G > 0) {
+        StageTimer st2_(f, ST_MM_TRI);
         launch_mm_triangulate(f->stream, mp);
         tp0.mm_grp = f->d_mm_trkgrp; tp0.mm_ivd = f->d_mm_ivd; tp0.mm_F0 = f->d_mm_F0;
       }
       if (n0 > 0 && launch_tracks(f->stream, tp0)) return fail(XB_E_CAPACITY, "track kernel shared memory");
-      if (f->mm_G > 0 && launch_mm_construct(f->stream, mp)) return fail(XB_E_CAPACITY, "multi-MSCKF kernel shared memory");
+      if (f->mm_G > 0) {
+        StageTimer st2_(f, ST_MM_CON);
+        if (launch_mm_construct(f->stream, mp)) return fail(XB_E_CAPACITY, "multi-MSCKF kernel shared memory");
+      }
       if (n1 > 0 && launch_tracks(f->stream, track_params(f, f->l_newms, 1))) return fail(XB_E_CAPACITY, "track kernel shared memory");
     }
     f->mm_last_G[which] = f->mm_G;
