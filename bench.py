@@ -271,8 +271,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         # NCCL's INFO lines (communicator ranks, transport, NVLS) go to stderr: fd 1 already points there
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):   # an inherited WARN / VERSION would hide them
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
