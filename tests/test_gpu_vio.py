@@ -87,8 +87,32 @@ class _OracleVIO:
         def tl(which, so=0):
             off, xy = self.tm.get_list(which, so)
             return [xy[off[i]:off[i + 1]].copy() for i in range(len(off) - 1)]
-        self.f.set_measurement(Measurement(t, tl(4, M), tl(0), tl(1), tl(2), tl(3), [int(i) for i in self.tm.lost]))
+        m = Measurement(t, tl(4, M), tl(0), tl(1), tl(2), tl(3), [int(i) for i in self.tm.lost])
+        self._sensors(m)
+        self.f.set_measurement(m)
         return self.f.process_update_measurement()
+
+    last_range = None   # (timestamp, range) as VIO::setLastRangeMeasurement keeps it
+    last_sun = None
+
+    def _sensors(self, m):
+        """vio.cpp:288-298 + vio_updater.cpp:358-369 from independent pieces: the Delaunay facet around the hard-coded image
+        point (320.5, 240.5) through qhull, the normalised LRF image point through the oracle camera."""
+        from oracle.track_manager import Feat
+        from scipy.spatial import Delaunay
+        from x_multi_agent_b200.filter import RangeMeasurement
+        if self.last_range is not None and self.last_range[0] > 0.1 and m.slam_trks and len(self.tm.slam) >= 3:
+            pts = np.array([[t[-1].xd, t[-1].yd] for t in self.tm.slam], dtype=np.float32).astype(np.float64)
+            tri = Delaunay(pts)
+            sx = tri.find_simplex(np.array([[320.5, 240.5]]))[0]
+            if sx >= 0:
+                f = Feat(xd=(self.p["cam1_img_width"] + 1) / 2.0, yd=(self.p["cam1_img_height"] + 1) / 2.0)
+                self.tm.undistort(f)
+                pt = (f.x * self.tm.inv_fx - self.tm.cx_n, f.y * self.tm.inv_fy - self.tm.cy_n)
+                m.range = RangeMeasurement(self.last_range[0], self.last_range[1], pt, sorted(int(i) for i in tri.simplices[sx]))
+                self.n_range = getattr(self, "n_range", 0) + 1
+        if self.last_sun is not None:
+            m.sun_angle = self.last_sun
 
 
 def test_vio_facade_from_match_vectors_matches_the_oracle_pipeline():
@@ -128,4 +152,54 @@ def test_vio_facade_from_match_vectors_matches_the_oracle_pipeline():
     # the estimate follows the truth (sanity of the whole chain, not a parity statement)
     p_true = scn.pose(events[-1][1])[0]
     assert np.linalg.norm(last_d.p - p_true) < 0.5
+    vio.close()
+
+
+def test_vio_facade_with_range_and_sun_measurements():
+    """VIO::setLastRangeMeasurement / setLastSunAngleMeasurement (vio.cpp:217-224) through the facade: the LRF facet comes
+    from the product's Delaunay lookup on one side and from qhull on the other, the rows from the device and from the
+    oracle; the facet's vertex order is irrelevant to the row (range_update.cpp:141-242 is symmetric
+    under permutations of the three features)."""
+    from x_multi_agent_b200 import VIO
+    from x_multi_agent_b200.filter import SunAngleMeasurement
+    from test_gpu_parity import Report, compare_state
+    scn, events = _stream(11, 30)
+    vio = VIO()
+    params = dict(PARAMS)
+    s0 = scn.initial_state()
+    params.update(p=list(s0.p), v=list(s0.v), q=[s0.q[3], s0.q[0], s0.q[1], s0.q[2]], b_w=list(s0.b_w), b_a=list(s0.b_a),
+                  cam1_p_ic=list(scn.p_ic), cam1_q_ic=[scn.q_ic[3], scn.q_ic[0], scn.q_ic[1], scn.q_ic[2]], sigma_range=0.05)
+    vio.set_up(params, max_tracks=256)
+    vio.init_at_time(0.0)
+    ora = _OracleVIO(vio)
+    ora.f.upd.sigma_range = 0.05
+    ora.f.initialize_from_state(vio.initial_state(0.0))
+    rp = Report()
+    last_d = last_o = None
+    n_upd = 0
+    for ev in events:
+        if ev[0] == "imu":
+            vio.process_imu(*ev[1:])
+            ora.f.process_imu(*ev[1:])
+        else:
+            _, t, k, mv = ev
+            # the camera looks down from ~4 m: a plausible altimeter reading, and a sun-sensor reading on every third frame
+            pc, Rc = scn.cam_pose(t)
+            rng_m = float(pc[2] / max(Rc[2, 2] * -1.0, 0.2)) if Rc[2, 2] < 0 else 4.0
+            vio.set_last_range_measurement(t, rng_m)
+            ora.last_range = (t, rng_m)
+            if k % 3 == 0:
+                sun = scn._sun_measurement(k)
+                vio.set_last_sun_angle_measurement(sun.timestamp, sun.x_angle, sun.y_angle)
+                ora.last_sun = SunAngleMeasurement(sun.timestamp, sun.x_angle, sun.y_angle)
+            d = vio.process_matches_measurement(t, k, mv)
+            o = ora.process_matches(t, mv)
+            assert (d is None) == (o is None)
+            if d is not None:
+                n_upd += 1
+                last_d, last_o = d, o
+    assert n_upd >= 25 and getattr(ora, "n_range", 0) >= 5, (n_upd, getattr(ora, "n_range", 0))
+    compare_state(rp, "last update", last_d, last_o, params["n_poses_max"], params["n_slam_features_max"], tol_scale=1000.0,
+                  cov=False)
+    rp.done()
     vio.close()
