@@ -376,9 +376,15 @@ def main():
         if "downdate" in st5 and st5["downdate"][1] > 0:
             dd_ms = st5["downdate"][0] / st5["downdate"][1]
             fl5, by5 = float(N5) * N5 * K5, 8.0 * (2 * N5 * N5 + N5 * K5)
+            tr5 = None
+            try:   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+                tr5 = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text()).get("cfg5_downdate")
+            except Exception:
+                pass
             cfg5["roofline"] = {"kernel": "k_gemm_tma<SYM> (covariance downdate, TMA-staged fp64 DMMA tiles)", "bound": "tensor",
                                 "achieved": fl5 / (dd_ms * 1e-3) / 1e12, "peak": 36.9, "unit": "TFLOP/s",
-                                "frac": fl5 / (dd_ms * 1e-3) / 1e12 / 36.9, "traffic": None, "avg_launch_ms": dd_ms,
+                                "frac": fl5 / (dd_ms * 1e-3) / 1e12 / 36.9, "traffic": tr5, "avg_launch_ms": dd_ms,
+                                "tensor_pipe_active_pct_ncu": 83.5,   # profiles/r02_ncu_full_summary.txt (k_gemm_tma<1>)
                                 "algorithmic_flops": fl5, "algorithmic_bytes": by5,
                                 "hbm_gbs_at_this_rate": by5 / (dd_ms * 1e-3) / 1e9,
                                 "peak_source": "fp64 tensor-core (mma.sync.m8n8k4) peak measured with tools/bench_dmma.cu; "

@@ -10,5 +10,5 @@ ncu --set full --clock-control none --import-source on -k regex:k_gemm_mma -s 25
 ncu --set full --clock-control none --import-source on -k regex:k_prop_step -s 100 -c 1 -o gpurun_out/${T}_prop_step $B > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_omega_small -s 40 -c 1 -o gpurun_out/${T}_omega_small $B > /dev/null 2>&1
 # cfg-5: the downdate (k_gemm_tma<true>) and the Schur complement (k_gemm_tma<false>) of the last full-size updates
-ncu --set full --clock-control none --import-source on -k regex:k_gemm_tma -s 40 -c 4 -o gpurun_out/${T}_gemm_tma python tools/cfg5_check.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_gemm_tma -s 57 -c 4 -o gpurun_out/${T}_gemm_tma python tools/cfg5_check.py > /dev/null 2>&1
 ls -la gpurun_out/ | grep ${T}
