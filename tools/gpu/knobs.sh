@@ -1,6 +1,6 @@
-for cfg in "XB_NONE=1" "XB_TRACK_WARPS=1" "XB_TRACK_WARPS=4" "XB_CHOL_SHARE=2" "XB_CHOL_SHARE=3" "XB_CHOL_SHARE=6" "XB_NONE=2"; do
+for cfg in "XB_NONE=1" "XB_CHOL_SHARE=5" "XB_CHOL_SHARE=6" "XB_CHOL_SHARE=8" "XB_NONE=2" "XB_CHOL_SHARE=6"; do
 echo "== $cfg"
-env $cfg timeout 300 python bench.py --no-cpu-baseline --no-reference-semantics --steps 40 2>/dev/null | python -c "
+env $cfg timeout 300 python bench.py --no-cpu-baseline --no-reference-semantics --steps 60 2>/dev/null | python -c "
 import sys,json
 l=[x for x in sys.stdin.read().splitlines() if x.startswith('{')][0]
 d=json.loads(l)

@@ -409,6 +409,9 @@ extern "C" int xb_create(const xb_config* cfg, xb_filter** out) {
                          &f->ev_g0, &f->ev_g1})
     CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   if (const char* e = getenv("XB_NO_OVERLAP")) f->overlap = atoi(e) == 0;
+  // cfg-2 sized covariances (N <= 1024): the dataflow launches run out of tiles before they run out of CTAs, a sixth of
+  // the slots each leaves more of every SM to the per-track kernel next to them (measured: tools/gpu/knobs.sh)
+  f->chol_share = f->N <= 1024 ? 6 : 4;
   if (const char* e = getenv("XB_CHOL_SHARE")) f->chol_share = std::max(1, atoi(e));
   const int W = 6 * M + 1;
   const int maxT = std::max(1, cfg->max_tracks);
