@@ -128,16 +128,25 @@ struct SunAngleMeasurement {
   double x_angle{0.0};
   double y_angle{0.0};
 };
-/** include/x/vio/types.h:264-324 without the image front end's members (matches, image). */
+class TiledImage;
+/** include/x/vio/types.h:264-324.  `matches` / `image` are the front end's members: a measurement built with them (the
+ *  reference's constructor) makes VioUpdater::preProcess sort the matches into tracks itself (vio_updater.cpp:142-179);
+ *  without them the track lists are the ones the caller left in the TrackManager (manageTracks / setTracks). */
 struct VioMeasurement {
   double timestamp{0};
   unsigned int seq{0};
+  MatchList matches;
+  unsigned int n_tiles_h{1}, n_tiles_w{1};   // tile grid of `image` (TiledImage without the pixels)
+  bool from_front_end{false};
   RangeMeasurement range;
   SunAngleMeasurement sun_angle;
   VioMeasurement() = default;
   VioMeasurement(const double& timestamp, const unsigned int seq) : timestamp{timestamp}, seq{seq} {}
   VioMeasurement(const double& timestamp, const unsigned int seq, RangeMeasurement range, const SunAngleMeasurement& sun_angle)
       : timestamp{timestamp}, seq{seq}, range{std::move(range)}, sun_angle{sun_angle} {}
+  /** types.h:300-305 (defined below TiledImage) */
+  VioMeasurement(const double& timestamp, const unsigned int seq, MatchList matches, const TiledImage& image,
+                 RangeMeasurement range, const SunAngleMeasurement& sun_angle);
 };
 
 /** x::SimpleState (include/x/ekf/simple_state.h:30-75): another agent's snapshot as it arrives from the network. */
@@ -424,6 +433,20 @@ class Camera {
       : fx_(fx), fy_(fy), cx_(cx), cy_(cy), s_(s), img_width_(img_width), img_height_(img_height) {}
   [[nodiscard]] unsigned int getWidth() const { return img_width_; }
   [[nodiscard]] unsigned int getHeight() const { return img_height_; }
+  /** Camera::undistort followed by Camera::normalize (camera.cpp:69-87, 122-135) of a measured image point, through the
+   *  camera model of the library (xb_tm_normalize_point).  Returns a Feature with the normalised coordinates. */
+  [[nodiscard]] Feature undistortAndNormalize(const Feature& feature) const {
+    xb_tm_config c{};
+    c.fx = fx_; c.fy = fy_; c.cx = cx_; c.cy = cy_; c.s = s_;
+    c.img_width = img_width_; c.img_height = img_height_;
+    c.n_tiles_h = c.n_tiles_w = 1;
+    xb_track_manager* tm = xb_tm_create(&c);
+    if (!tm) throw std::invalid_argument("Camera: invalid intrinsics");
+    double out[2] = {0.0, 0.0};
+    xb_tm_normalize_point(tm, feature.getXDist(), feature.getYDist(), out);
+    xb_tm_destroy(tm);
+    return Feature(feature.getTimestamp(), out[0], out[1], feature.getIntensity());
+  }
   double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0, s_ = 0;  // as given: fractions of the image size (camera.cpp:27-35)
   unsigned int img_width_ = 0, img_height_ = 0;
 };
@@ -437,6 +460,11 @@ class TiledImage {
  private:
   unsigned int n_tiles_h_ = 1, n_tiles_w_ = 1;
 };
+
+inline VioMeasurement::VioMeasurement(const double& timestamp, const unsigned int seq, MatchList matches, const TiledImage& image,
+                                      RangeMeasurement range, const SunAngleMeasurement& sun_angle)
+    : timestamp{timestamp}, seq{seq}, matches{std::move(matches)}, n_tiles_h{image.getNTilesH()}, n_tiles_w{image.getNTilesW()},
+      from_front_end{true}, range{std::move(range)}, sun_angle{sun_angle} {}
 
 /** x::TrackManager (include/x/vio/track_manager.h).  manageTracks (track_manager.cpp:115-436) runs in libxb200.so
  *  (xb_tm_*, host code); the lists can also be injected directly (setTracks) when the caller has its own front end. */
@@ -574,6 +602,19 @@ class StateManager {
   void clear() {
     std::vector<int> a(static_cast<size_t>(std::max(1, n_features_max_)), -1);
     if (f_) xb_sm_set(f_, 0, 0, a.data(), 0);
+  }
+  /** state_manager.cpp:538-565: the last min(max_size, n_poses) camera attitudes of the window (all of them for
+   *  max_size <= 0); `state` must carry its estimates on the host. */
+  [[nodiscard]] AttitudeList convertCameraAttitudesToList(const State& state, const int max_size = 0) const {
+    const int n_poses = static_cast<int>(poseSize());
+    const int size_out = max_size > 0 ? std::min(max_size, n_poses) : n_poses;
+    const Matrix orientation_array = state.getOrientationArray();
+    AttitudeList attitude_list(static_cast<size_t>(size_out), Attitude());
+    const int start_idx = n_poses - size_out;
+    for (int i = start_idx; i < n_poses; i++)
+      attitude_list[static_cast<size_t>(i - start_idx)] = Attitude(orientation_array(4 * i, 0), orientation_array(4 * i + 1, 0),
+                                                                   orientation_array(4 * i + 2, 0), orientation_array(4 * i + 3, 0));
+    return attitude_list;
   }
   /** state_manager.cpp:31-149 on a device-bound state. */
   void manage(State& state, std::vector<unsigned int> del_feat_idx) {
@@ -758,6 +799,9 @@ class VioUpdater : public Updater {
   /** The front-end seam (what the reference's preProcess pulls out of its TrackManager / Tracker copies). */
   TrackManager& trackManager() { return track_manager_; }
   StateManager& stateManager() { return state_manager_; }
+  [[nodiscard]] TiledImage& getFeatureImage() { return feature_img_; }   // vio_updater.h:62
+  /** True when preProcess needs the estimates of the update state on the host (a measurement that carries matches). */
+  [[nodiscard]] bool needsHostState() const { return measurement_.from_front_end; }
 #ifdef MULTI_UAV
   void getMsckfTracks(TrackList& tracks) { tracks = track_manager_.getMsckfTracks(); }
   void getSlamTracks(TrackList& tracks, std::vector<int>& anchor_idxs, const int n_poses_max) {
@@ -786,6 +830,7 @@ class VioUpdater : public Updater {
   std::vector<unsigned int> lost_slam_trk_idxs_;
   MsckfMatches msckf_matches_;
   SlamMatches slam_matches_;
+  TiledImage feature_img_;
 
   struct Csr { std::vector<int> off; std::vector<double> obs; };
   static void pack(const TrackList& tl, Csr& c, xb_track_list& out) {
@@ -804,6 +849,16 @@ class VioUpdater : public Updater {
   void preProcess(const State& state) override {
     xb_filter* f = deviceOf(state);
     const int n_poses_max = state.nPosesMax();
+    if (measurement_.from_front_end) {
+      // vio_updater.cpp:142-170: camera attitudes of the window without its oldest pose, plus the current one (the pose
+      // window has not been slid yet), then the matches are sorted into tracks.  Ekf::processUpdateMeasurement hands a
+      // state with its estimates on the host for such a measurement.
+      AttitudeList cam_rots = state_manager_.convertCameraAttitudesToList(state, n_poses_max - 1);
+      cam_rots.push_back(state.computeCameraAttitude());
+      feature_img_ = TiledImage(measurement_.n_tiles_h, measurement_.n_tiles_w);
+      track_manager_.manageTracks(measurement_.matches, cam_rots, static_cast<size_t>(n_poses_max),
+                                  static_cast<size_t>(state.nFeaturesMax()), static_cast<size_t>(min_track_length_), feature_img_);
+    }
     slam_trks_ = track_manager_.normalizeSlamTracks(n_poses_max);
     msckf_trks_ = track_manager_.getMsckfTracks();
     msckf_short_trks_ = track_manager_.getShortMsckfTracks();
@@ -1020,7 +1075,8 @@ class Ekf {
     if (!dev_) return std::nullopt;
     std::lock_guard<std::mutex> lk(dev_->mutex);
     // the host mirror of the estimates is only filled in for updaters that read it (a device-native VioUpdater does not)
-    const bool native = dynamic_cast<VioUpdater*>(&updater_) != nullptr;
+    const auto* vio_updater = dynamic_cast<VioUpdater*>(&updater_);
+    const bool native = vio_updater != nullptr && !vio_updater->needsHostState();
     std::vector<double> x0(native ? 0 : XB_XVEC_LEN(M_, F_));
     int rc = xb_ekf_update_begin(dev_->f, updater_.getTime(), native ? nullptr : x0.data());
     xb_throw(rc);

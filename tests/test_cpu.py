@@ -466,3 +466,37 @@ def test_vio_params_from_yaml(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         load_params_from_yaml(f)
+
+
+def test_cxx_vio_facade_compiles_and_loads_yaml_params(tmp_path):
+    """include/x/vio/vio.h (x::VIO, x::Params): compiles in both build flavours against the Eigen stand-in, and its
+    loadParamsFromYaml (vio.cpp:576-707 without cv::FileStorage) reads an OpenCV-flavoured parameter file -- directive
+    line, comments, flow sequences over several lines, quaternions as (w, x, y, z) and normalised, quoted strings --
+    leaving absent keys at the defaults of x::Params (vio/types.h:141-160).  No GPU: the facade creates its filter in setUp."""
+    import subprocess
+    src = os.fspath(ROOT / "tests" / "cxx" / "test_x_vio.cpp")
+    inc = [f"-I{ROOT / 'include'}", f"-I{EIGEN_STAND_IN}"]
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DMULTI_UAV", *inc, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    libdir = ROOT / "x_multi_agent_b200"
+    exe = tmp_path / "test_x_vio"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", *inc, "-o", os.fspath(exe), src, f"-L{libdir}", "-lxb200",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    f = tmp_path / "params.yaml"
+    f.write_text("%YAML:1.0\n---\n# initial state\np: [0.0, 0.0, 1.0]\nq: [0.0, 0.0, 0.0, 2.0]   # w x y z\n"
+                 "sigma_dtheta: [1.0,\n  2.5, 3.0]\ncam1_fx: 0.46\ncam1_img_width: 640\ncam1_q_ic: [1, 0, 0, 1]\n"
+                 "sigma_img: 0.002\nn_poses_max: 8\nn_slam_features_max: 6\nmin_track_length: 5\nn_tiles_h: 2\n"
+                 "msckf_baseline: 12.0\nnon_max_supp: true\nvocabulary_path: \"/tmp/voc.bin\"\ng: [0, 0, -9.81]\n")
+    r = subprocess.run([os.fspath(exe), os.fspath(f), "-", "-", "dump"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    v = r.stdout.split()
+    assert [int(e) for e in v[:5]] == [8, 6, 5, 250, 2]           # state_buffer_size absent: default 250
+    got = [float(e) for e in v[5:13]]
+    want = [0.46, 0.002, 0.0, 0.0, np.sqrt(0.5), -9.81, 2.5, 12.0]   # cam_fx, sigma_img, q.w, q.x, q_ic.z, g_z, sigma_dtheta_y, baseline
+    assert np.allclose(got, want, rtol=0, atol=1e-15)
+    assert v[13:] == ["640", "1", "/tmp/voc.bin"]
+    # a vector of the wrong length is an error, as in the Python loader
+    f.write_text("p: [0.0, 1.0]\n")
+    r = subprocess.run([os.fspath(exe), os.fspath(f), "-", "-", "dump"], capture_output=True, text=True)
+    assert r.returncode != 0

@@ -203,3 +203,94 @@ def test_vio_facade_with_range_and_sun_measurements():
                   cov=False)
     rp.done()
     vio.close()
+
+
+def _yaml(params):
+    """The parameter file a caller of the reference writes (OpenCV FileStorage flavour: directive line, flow sequences)."""
+    lines = ["%YAML:1.0", "---"]
+    for k, v in params.items():
+        lines.append(f"{k}: [{', '.join(repr(float(e)) for e in v)}]" if isinstance(v, (list, tuple)) else f"{k}: {v!r}")
+    return "\n".join(lines) + "\n"
+
+
+def test_cxx_vio_facade_equals_the_python_facade(tmp_path):
+    """The C++ x::VIO (include/x/vio/vio.h: loadParamsFromYaml -> setUp -> initAtTime -> processImu /
+    setLastRangeMeasurement / setLastSunAngleMeasurement / processMatchesMeasurement, the reference's public entry points
+    vio.h:43-137) on the stream of the test above: every updated state equals the Python facade's -- both drive the same
+    library, the C++ side through the reference's own template method Updater::update with the matches sorted into tracks
+    inside VioUpdater::preProcess (vio_updater.cpp:142-179)."""
+    import os
+    import subprocess
+    from pathlib import Path
+    from x_multi_agent_b200 import VIO
+    root = Path(__file__).resolve().parents[1]
+    scn, events = _stream(11, 30)
+    params = dict(PARAMS)
+    s0 = scn.initial_state()
+    params.update(p=list(s0.p), v=list(s0.v), q=[s0.q[3], s0.q[0], s0.q[1], s0.q[2]], b_w=list(s0.b_w), b_a=list(s0.b_a),
+                  cam1_p_ic=list(scn.p_ic), cam1_q_ic=[scn.q_ic[3], scn.q_ic[0], scn.q_ic[1], scn.q_ic[2]], sigma_range=0.05,
+                  g=[0.0, 0.0, -9.81])
+    (tmp_path / "params.yaml").write_text(_yaml(params))
+    vio = VIO()
+    vio.set_up(params, max_tracks=256)
+    vio.init_at_time(0.0)
+    out, want = [], []
+    n_upd = 0
+    for ev in events:
+        if ev[0] == "imu":
+            vio.process_imu(*ev[1:])
+            out += [1.0, ev[1], float(ev[2]), *ev[3], *ev[4]]
+        else:
+            _, t, k, mv = ev
+            pc, Rc = scn.cam_pose(t)
+            rng_m = float(pc[2] / max(Rc[2, 2] * -1.0, 0.2)) if Rc[2, 2] < 0 else 4.0
+            vio.set_last_range_measurement(t, rng_m)
+            out += [3.0, t, rng_m]
+            if k % 3 == 0:
+                sun = scn._sun_measurement(k)
+                vio.set_last_sun_angle_measurement(sun.timestamp, sun.x_angle, sun.y_angle)
+                out += [4.0, sun.timestamp, sun.x_angle, sun.y_angle]
+            d = vio.process_matches_measurement(t, k, mv)
+            out += [2.0, t, float(k), float(len(mv)), *np.asarray(mv, dtype=float).ravel()]
+            want.append(1.0 if d is not None else 0.0)
+            want += list(d.x) if d is not None else [0.0] * vio.filter.LX
+            n_upd += d is not None
+    assert n_upd >= 25
+    # SLAM features of the newest state in world coordinates (StateManager::computeSLAMCartesianFeaturesForState)
+    flt = vio.filter
+    s = flt.get_state()
+    M, F = params["n_poses_max"], params["n_slam_features_max"]
+    nf = flt.n_features
+    anchors = flt.anchor_idxs[:nf]
+    np.asarray(out, dtype=np.float64).tofile(tmp_path / "events.bin")
+    exe = tmp_path / "test_x_vio"
+    libdir = root / "x_multi_agent_b200"
+    subprocess.run(["g++", "-std=c++17", "-O2", f"-I{root / 'include'}", f"-I{root / 'oracle' / 'ref_build' / 'shim'}", "-o",
+                    os.fspath(exe), os.fspath(root / "tests" / "cxx" / "test_x_vio.cpp"), f"-L{libdir}", "-lxb200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([os.fspath(exe), os.fspath(tmp_path / "params.yaml"), os.fspath(tmp_path / "events.bin"),
+                        os.fspath(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(tmp_path / "out.bin")
+    want = np.asarray(want)
+    LX = flt.LX
+    assert got.shape[0] >= want.shape[0] + 1
+    g = got[:want.shape[0]].reshape(-1, LX + 1).copy()
+    w = want.reshape(-1, LX + 1).copy()
+    g[:, 1 + 31] = w[:, 1 + 31] = 0.0          # xvec[31] is reserved (not part of x::State)
+    assert np.array_equal(g[:, 0], w[:, 0])
+    err = np.abs(g - w).max()
+    assert err <= 1e-10, err
+    # world coordinates of the SLAM features, against the same formula on the Python side
+    n_xyz = int(got[want.shape[0]])
+    assert n_xyz == nf and nf == F
+    xyz = got[want.shape[0] + 1:].reshape(n_xyz, 3)
+    from oracle.quat import rot as q_rot
+    for i in range(nf):
+        a = int(anchors[i])
+        qa = s.q_array.reshape(M, 4)[a]
+        al, be, rho = s.f_array.reshape(F, 3)[i]
+        ref = s.p_array.reshape(M, 3)[a] + q_rot(qa) @ np.array([al, be, 1.0]) / rho
+        assert np.abs(xyz[i] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+    assert np.all(np.isfinite(xyz))
+    vio.close()

@@ -73,6 +73,7 @@ class VIO:
         self.filter = Filter(p["n_poses_max"], p["n_slam_features_max"], n_slots=p["state_buffer_size"], device=device,
                              sigma_img=p["sigma_img"], sigma_range=p["sigma_range"], rho_0=p["rho_0"], sigma_rho_0=p["sigma_rho_0"], iekf_iter=p["iekf_iter"],
                              min_track_length=p["min_track_length"],
+                             a_m_max=50.0, delta_seq_imu=1, time_margin=0.02,     # Ekf::set arguments of vio.cpp:208-214
                              n_w=p["n_w"], n_bw=p["n_bw"], n_a=p["n_a"], n_ba=p["n_ba"], g=tuple(p["g"]), **filter_kw)
         self.initialized = False
 
