@@ -307,6 +307,60 @@ class VIO {
     return params;
   }
 
+#ifdef MULTI_UAV
+  /** A correspondence between this agent's data and a peer's, as the reference's place recognition reports it
+   *  (PlaceRecognition::findCorrespondences fills the tracker's match lists, vio.cpp:538-546): SLAM feature `current`
+   *  of this agent is the peer's SLAM feature `received`; MSCKF track with id `current` is the peer's MSCKF track number
+   *  `received` of the list it sent.  Descriptor matching on pixels is the front end's job (out of scope): the caller
+   *  delivers the correspondences, as it delivers visual matches. */
+  struct Correspondence { unsigned long long current; int received; };
+
+  /** vio.cpp:440-452 */
+  void getDataToSend(std::shared_ptr<SimpleState>& state_ptr, const State& state, TrackList& msckf_tracks, TrackList& slam_tracks,
+                     std::vector<int>& anchor_idxs, TrackList& opp_tracks) {
+    vio_updater_.getMsckfTracks(msckf_tracks);
+    vio_updater_.getSlamTracks(slam_tracks, anchor_idxs, state.nPosesMax());
+    opp_tracks = vio_updater_.trackManager().getOppTracks();
+    state_ptr = std::make_shared<SimpleState>(state.getDynamicStates(), column(state.getPositionArray()),
+                                              column(state.getOrientationArray()), column(state.getFeatureArray()),
+                                              state.getCovariance(), anchor_idxs);
+  }
+
+  /** vio.cpp:498-574 with the correspondences delivered by the caller: the peer's snapshot becomes a SimpleState, the
+   *  SLAM-SLAM correspondences are fused now (Ekf::processOthersMeasurement -> Updater::collaborativeUpdate: MultiSlamUpdate,
+   *  pair fuseCI, applyCI), the MSCKF-MSCKF ones wait for the next visual update (vio_updater.cpp:185), as in the
+   *  reference.  Returns nullopt when this agent has no SLAM track (vio.cpp:529-531) or no correspondence was found. */
+  std::optional<State> processOtherMeasurements(double timestamp, const int uav_id, const Vectorx& dynamic_state,
+                                                const Vectorx& positions_state, const Vectorx& orientations_state,
+                                                const Vectorx& features_state, const Matrix& cov,
+                                                const TrackListPtr& received_msckf_trcks_ptr,
+                                                const std::vector<int>& anchor_idxs,
+                                                const std::vector<Correspondence>& slam_correspondences,
+                                                const std::vector<Correspondence>& msckf_correspondences) {
+    std::shared_ptr<SimpleState> ptr = std::make_shared<SimpleState>(dynamic_state, positions_state, orientations_state,
+                                                                     features_state, cov, anchor_idxs);
+    TrackList current_slam;
+    std::vector<int> current_anchors;
+    vio_updater_.getSlamTracks(current_slam, current_anchors, params_.n_poses_max);
+    if (current_slam.empty() && vio_updater_.trackManager().getOppTracks().empty()) return std::nullopt;
+    if (slam_correspondences.empty() && msckf_correspondences.empty()) return std::nullopt;   // !place_found
+    SlamMatches slam_matches;
+    for (const auto& c : slam_correspondences)
+      slam_matches.emplace_back(uav_id, static_cast<int>(c.current), c.received, ptr);
+    MsckfMatches msckf_matches;
+    for (const auto& c : msckf_correspondences) {
+      if (c.received < 0 || static_cast<size_t>(c.received) >= received_msckf_trcks_ptr.size() ||
+          !received_msckf_trcks_ptr[static_cast<size_t>(c.received)])
+        throw std::invalid_argument("processOtherMeasurements: MSCKF correspondence outside the received track list");
+      const TrackPtr& trk = received_msckf_trcks_ptr[static_cast<size_t>(c.received)];
+      msckf_matches.emplace_back(uav_id, c.current, trk->getId(), trk, ptr);
+    }
+    vio_updater_.setSlamMatches(slam_matches);
+    vio_updater_.setMsckfMatches(msckf_matches);
+    return ekf_.processOthersMeasurement(timestamp);
+  }
+#endif
+
   /** The operator objects behind the facade (the reference keeps them private; the parity tests read them). */
   Ekf& ekf() { return ekf_; }
   VioUpdater& vioUpdater() { return vio_updater_; }
@@ -340,6 +394,11 @@ class VIO {
     const Vector3 axis = v0.cross(v1);
     const double s = std::sqrt((1.0 + c) * 2.0), invs = 1.0 / s;
     return Quaternion(s * 0.5, axis(0) * invs, axis(1) * invs, axis(2) * invs);
+  }
+  static Vectorx column(const Matrix& m) {
+    Vectorx v(m.rows());
+    for (int i = 0; i < static_cast<int>(m.rows()); ++i) v(i) = m(i, 0);
+    return v;
   }
   static std::string trim(const std::string& s) {
     const size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");

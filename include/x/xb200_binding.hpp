@@ -101,6 +101,7 @@ class Track : public std::vector<Feature> {
 };
 using TrackList = std::vector<Track>;
 using TrackPtr = std::shared_ptr<Track>;
+using TrackListPtr = std::vector<std::shared_ptr<Track>>;   // include/x/vision/types.h:55
 using uniqueId = unsigned long long;
 struct Attitude {
   double ax = 0, ay = 0, az = 0, aw = 0;

@@ -2,6 +2,8 @@
 // initAtTime, processImu, setLastRangeMeasurement / setLastSunAngleMeasurement, processMatchesMeasurement on 10-double
 // match vectors -- over an event stream written by tests/test_gpu_vio.py, and dumps the updated states so that pytest can
 // compare them with the Python facade on the same stream.  Build: g++ -std=c++17 -I include -I <Eigen> ... -lxb200
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -87,5 +89,82 @@ int main(int argc, char** argv) {
   fwrite(out.data(), 8, out.size(), fo);
   fclose(fo);
   printf("ok %d updates\n", n_updates);
+#ifdef MULTI_UAV
+  // -DMULTI_UAV build: a second agent (a second filter on the same GPU) replays the same stream, sends its data
+  // (VIO::getDataToSend, vio.cpp:440-452) and this agent fuses it (VIO::processOtherMeasurements, vio.cpp:498-574) with
+  // every SLAM feature matched to the peer's feature of the same index.  The peer's estimates equal this agent's, so
+  // the landmark residuals are zero: covariance intersection must leave the estimates where they are and return a
+  // finite, symmetric covariance that differs from the prior one.
+  {
+    x::VIO peer;
+    peer.setUp(params, 256);
+    peer.initAtTime(0.0);
+    size_t q = 0;
+    double t_last = 0.0;
+    while (q < ev.size()) {
+      const int type = (int)ev[q++];
+      if (type == 1) {
+        peer.processImu(ev[q], (unsigned)ev[q + 1], x::Vector3(ev[q + 2], ev[q + 3], ev[q + 4]), x::Vector3(ev[q + 5], ev[q + 6], ev[q + 7]));
+        q += 8;
+      } else if (type == 3) {
+        x::RangeMeasurement r; r.timestamp = ev[q]; r.range = ev[q + 1]; q += 2;
+        peer.setLastRangeMeasurement(r);
+      } else if (type == 4) {
+        x::SunAngleMeasurement sa; sa.timestamp = ev[q]; sa.x_angle = ev[q + 1]; sa.y_angle = ev[q + 2]; q += 3;
+        peer.setLastSunAngleMeasurement(sa);
+      } else {
+        const size_t n = (size_t)ev[q + 2];
+        t_last = ev[q];
+        peer.processMatchesMeasurement(ev[q], (unsigned)ev[q + 1], std::vector<double>(ev.begin() + q + 3, ev.begin() + q + 3 + 10 * n));
+        q += 3 + 10 * n;
+      }
+    }
+    // the peer's newest state with its covariance
+    std::vector<double> px(LX);
+    const int N = XB_NERR(M, F);
+    std::vector<double> pc((size_t)N * N);
+    xb_ekf_get_state(peer.ekf().handle(), -1, px.data());
+    xb_ekf_get_covariance(peer.ekf().handle(), -1, pc.data(), XB_COL_MAJOR);
+    x::State ps(M, F);
+    ps.setFromXvec(px.data(), M, F);
+    x::Matrix pcov(N, N);
+    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) pcov(i, j) = pc[(size_t)j * N + i];
+    ps.setCovariance(pcov);
+    std::shared_ptr<x::SimpleState> sent;
+    x::TrackList msckf_tracks, slam_tracks, opp_tracks;
+    std::vector<int> anchors;
+    peer.getDataToSend(sent, ps, msckf_tracks, slam_tracks, anchors, opp_tracks);
+    if (!sent || (int)anchors.size() != F || sent->getErrorStateSize() != N) { fprintf(stderr, "getDataToSend\n"); return 6; }
+    const int nf = (int)xyz.size();
+    std::vector<x::VIO::Correspondence> slam_corr, msckf_corr;
+    for (int i = 0; i < nf; ++i) slam_corr.push_back({(unsigned long long)i, i});
+    x::TrackListPtr received_msckf;
+    for (const auto& t : msckf_tracks) received_msckf.push_back(std::make_shared<x::Track>(t));
+    std::vector<double> before(LX), pb((size_t)N * N);
+    xb_ekf_get_state(vio.ekf().handle(), -1, before.data());
+    xb_ekf_get_covariance(vio.ekf().handle(), -1, pb.data(), XB_COL_MAJOR);
+    // no correspondence: nothing happens (vio.cpp:548-550)
+    if (vio.processOtherMeasurements(t_last, 1, sent->getDynamicState(), sent->getPositionState(), sent->getOrientationState(),
+                                     sent->getFeatureState(), sent->getCovariance(), received_msckf, anchors, {}, {}).has_value()) return 7;
+    const auto fused = vio.processOtherMeasurements(t_last, 1, sent->getDynamicState(), sent->getPositionState(),
+                                                    sent->getOrientationState(), sent->getFeatureState(), sent->getCovariance(),
+                                                    received_msckf, anchors, slam_corr, msckf_corr);
+    if (!fused.has_value()) { fprintf(stderr, "processOtherMeasurements returned nullopt\n"); return 7; }
+    std::vector<double> after(LX), pa((size_t)N * N);
+    xb_ekf_get_state(vio.ekf().handle(), -1, after.data());
+    xb_ekf_get_covariance(vio.ekf().handle(), -1, pa.data(), XB_COL_MAJOR);
+    double dx = 0.0, dp = 0.0, asym = 0.0;
+    for (int i = 0; i < LX; ++i) if (i != 31) dx = std::max(dx, std::fabs(after[i] - before[i]));
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        if (!std::isfinite(pa[(size_t)j * N + i])) { fprintf(stderr, "covariance not finite\n"); return 8; }
+        dp = std::max(dp, std::fabs(pa[(size_t)j * N + i] - pb[(size_t)j * N + i]));
+        asym = std::max(asym, std::fabs(pa[(size_t)j * N + i] - pa[(size_t)i * N + j]));
+      }
+    printf("multi: %d SLAM correspondences, max |dx| = %.3e, max |dP| = %.3e, asym = %.3e\n", nf, dx, dp, asym);
+    if (dx > 1e-9 || dp == 0.0) return 9;
+    printf("multi ok\n");
+  }
+#endif
   return 0;
 }

@@ -229,7 +229,7 @@ def test_cxx_vio_facade_equals_the_python_facade(tmp_path):
     s0 = scn.initial_state()
     params.update(p=list(s0.p), v=list(s0.v), q=[s0.q[3], s0.q[0], s0.q[1], s0.q[2]], b_w=list(s0.b_w), b_a=list(s0.b_a),
                   cam1_p_ic=list(scn.p_ic), cam1_q_ic=[scn.q_ic[3], scn.q_ic[0], scn.q_ic[1], scn.q_ic[2]], sigma_range=0.05,
-                  g=[0.0, 0.0, -9.81])
+                  g=[0.0, 0.0, -9.81], sigma_landmark=0.1, ci_slam_w=0.5, ci_msckf_w=0.5)   # the last three: MULTI_UAV build only
     (tmp_path / "params.yaml").write_text(_yaml(params))
     vio = VIO()
     vio.set_up(params, max_tracks=256)
@@ -294,3 +294,13 @@ def test_cxx_vio_facade_equals_the_python_facade(tmp_path):
         assert np.abs(xyz[i] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
     assert np.all(np.isfinite(xyz))
     vio.close()
+    # -DMULTI_UAV flavour of the same program: two agents (two filters on this GPU) on the stream, VIO::getDataToSend on one,
+    # VIO::processOtherMeasurements on the other with every SLAM feature matched to its twin: zero landmark residuals, so the
+    # SLAM-SLAM covariance intersection moves no estimate and returns a finite covariance that differs from the prior one
+    exe2 = tmp_path / "test_x_vio_multi"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-DMULTI_UAV", f"-I{root / 'include'}", f"-I{root / 'oracle' / 'ref_build' / 'shim'}",
+                    "-o", os.fspath(exe2), os.fspath(root / "tests" / "cxx" / "test_x_vio.cpp"), f"-L{libdir}", "-lxb200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([os.fspath(exe2), os.fspath(tmp_path / "params.yaml"), os.fspath(tmp_path / "events.bin"),
+                        os.fspath(tmp_path / "out_multi.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "multi ok" in r.stdout, r.stdout + r.stderr
