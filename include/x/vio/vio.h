@@ -21,50 +21,6 @@
 namespace x {
 namespace fsm = std::filesystem;
 
-/** x::Params (include/x/vio/types.h:33-160).  The tracker / place-recognition members are carried so that parameter files
- *  and callers of the reference keep working; the back end reads the filter, camera and track-management members. */
-struct Params {
-  Vector3 p{0, 0, 0}, v{0, 0, 0};
-  Quaternion q{1, 0, 0, 0};
-  Vector3 b_w{0, 0, 0}, b_a{0, 0, 0};
-  Vector3 sigma_dp{0, 0, 0}, sigma_dv{0, 0, 0}, sigma_dtheta{0, 0, 0}, sigma_dbw{0, 0, 0}, sigma_dba{0, 0, 0};
-  double cam_fx{0}, cam_fy{0}, cam_cx{0}, cam_cy{0}, cam_s{0};
-  int img_height{0}, img_width{0};
-  Vector3 p_ic{0, 0, 0};
-  Quaternion q_ic{1, 0, 0, 0};
-  double sigma_img{0};
-  double sigma_range{0};
-  Quaternion q_sc{1, 0, 0, 0};
-  Vector3 w_s{0, 0, 1};
-  double n_a{0}, n_ba{0}, n_w{0}, n_bw{0};
-  int fast_detection_delta{0};
-  bool non_max_supp{false};
-  int block_half_length{0}, margin{0}, n_feat_min{0}, outlier_method{0};
-  double outlier_param1{0}, outlier_param2{0};
-  int n_tiles_h{1}, n_tiles_w{1}, max_feat_per_tile{0};
-  double time_offset{0};
-  std::string vocabulary_path;
-  double sigma_landmark{0};
-  float descriptor_scale_factor{0};
-  int descriptor_pyramid{0}, descriptor_patch_size{0};
-  double ci_msckf_w{-1.0}, ci_slam_w{-1.0};
-  int desc_type{0};
-  double pr_score_thr{0}, pr_desc_ratio_thr{0}, pr_desc_min_distance{0};
-  int max_level{0};
-  double min_eig_thr{0};
-  int win_size_w{0}, win_size_h{0};
-  int n_poses_max = 15;
-  int n_slam_features_max = 15;
-  double rho_0 = 0.5;
-  double sigma_rho_0 = 0.25;
-  int iekf_iter = 1;
-  double msckf_baseline = 10;
-  int min_track_length = 15;
-  Vector3 g{0, 0, -9.81};
-  bool self_init_start_ = false;
-  int state_buffer_size = 250;
-};
-
 class VIO {
  public:
   VIO() : ekf_{Ekf(vio_updater_)} {}   // vio.cpp:40
@@ -124,10 +80,9 @@ class VIO {
   void initAtTime(const double& time) {
     initialized_ = false;
     initialize_start_ = self_init_start_;
-    ekf_.lock();
+    ekf_.lock();   // held to the end, as vio.cpp:55-109 does (the mutex of this binding is recursive)
     vio_updater_.track_manager_.clear();
     vio_updater_.state_manager_.clear();
-    ekf_.unlock();
     // initial IMU measurement: gravity reaction along the IMU +Z axis, no rotation
     const Vector3 a_m = -params_.g;
     const Vector3 w_m(0.0, 0.0, 0.0);
@@ -157,6 +112,7 @@ class VIO {
                    "allocated in the buffered states."
                 << std::endl;
     }
+    ekf_.unlock();
     initialized_ = true;
   }
 

@@ -44,6 +44,9 @@ using Vectorx = Eigen::VectorXd;
 using Matrix3 = Eigen::Matrix3d;
 using Matrix4 = Eigen::Matrix4d;
 constexpr double kInvalid = -1.0;
+/** Ekf::mutex_ (ekf.h:185).  Recursive: the reference's VIO::initAtTime calls Ekf::initializeFromState between Ekf::lock()
+ *  and Ekf::unlock() (vio.cpp:55-109), and the entry points of this binding take the lock themselves. */
+using EkfMutex = std::recursive_mutex;
 struct ImuNoise {
   double n_w = 0.0083, n_bw = 0.00083, n_a = 0.0013;
   double n_ba = 0.00013;  // the reference's literal `00013` is octal (= 11); VIO::setUp overrides it (vio.cpp:181-185)
@@ -148,6 +151,50 @@ struct VioMeasurement {
   /** types.h:300-305 (defined below TiledImage) */
   VioMeasurement(const double& timestamp, const unsigned int seq, MatchList matches, const TiledImage& image,
                  RangeMeasurement range, const SunAngleMeasurement& sun_angle);
+};
+
+/** x::Params (include/x/vio/types.h:33-160).  The tracker / place-recognition members are carried so that parameter files
+ *  and callers of the reference keep working; the back end reads the filter, camera and track-management members. */
+struct Params {
+  Vector3 p{0, 0, 0}, v{0, 0, 0};
+  Quaternion q{1, 0, 0, 0};
+  Vector3 b_w{0, 0, 0}, b_a{0, 0, 0};
+  Vector3 sigma_dp{0, 0, 0}, sigma_dv{0, 0, 0}, sigma_dtheta{0, 0, 0}, sigma_dbw{0, 0, 0}, sigma_dba{0, 0, 0};
+  double cam_fx{0}, cam_fy{0}, cam_cx{0}, cam_cy{0}, cam_s{0};
+  int img_height{0}, img_width{0};
+  Vector3 p_ic{0, 0, 0};
+  Quaternion q_ic{1, 0, 0, 0};
+  double sigma_img{0};
+  double sigma_range{0};
+  Quaternion q_sc{1, 0, 0, 0};
+  Vector3 w_s{0, 0, 1};
+  double n_a{0}, n_ba{0}, n_w{0}, n_bw{0};
+  int fast_detection_delta{0};
+  bool non_max_supp{false};
+  int block_half_length{0}, margin{0}, n_feat_min{0}, outlier_method{0};
+  double outlier_param1{0}, outlier_param2{0};
+  int n_tiles_h{1}, n_tiles_w{1}, max_feat_per_tile{0};
+  double time_offset{0};
+  std::string vocabulary_path;
+  double sigma_landmark{0};
+  float descriptor_scale_factor{0};
+  int descriptor_pyramid{0}, descriptor_patch_size{0};
+  double ci_msckf_w{-1.0}, ci_slam_w{-1.0};
+  int desc_type{0};
+  double pr_score_thr{0}, pr_desc_ratio_thr{0}, pr_desc_min_distance{0};
+  int max_level{0};
+  double min_eig_thr{0};
+  int win_size_w{0}, win_size_h{0};
+  int n_poses_max = 15;
+  int n_slam_features_max = 15;
+  double rho_0 = 0.5;
+  double sigma_rho_0 = 0.25;
+  int iekf_iter = 1;
+  double msckf_baseline = 10;
+  int min_track_length = 15;
+  Vector3 g{0, 0, -9.81};
+  bool self_init_start_ = false;
+  int state_buffer_size = 250;
 };
 
 /** x::SimpleState (include/x/ekf/simple_state.h:30-75): another agent's snapshot as it arrives from the network. */
@@ -362,7 +409,7 @@ class State {
   struct DevRef {
     int kind = kHost;
     xb_filter* f = nullptr;
-    std::mutex* mtx = nullptr;  // Ekf::mutex_: downloads from a ring slot take it
+    EkfMutex* mtx = nullptr;  // Ekf::mutex_: downloads from a ring slot take it
     int slot = -1, serial = -1;
     double time = kInvalid;
   };
@@ -379,8 +426,8 @@ class State {
     if (dev_.kind == kWork) {
       xb_throw(xb_work_get(dev_.f, nullptr, cov_.data(), XB_COL_MAJOR));
     } else {
-      std::unique_lock<std::mutex> lk;
-      if (dev_.mtx) lk = std::unique_lock<std::mutex>(*dev_.mtx);
+      std::unique_lock<EkfMutex> lk;
+      if (dev_.mtx) lk = std::unique_lock<EkfMutex>(*dev_.mtx);
       double t = kInvalid;
       int serial = -1;
       xb_throw(xb_ekf_slot_info(dev_.f, dev_.slot, &t, &serial));
@@ -391,7 +438,7 @@ class State {
     }
     cov_valid_ = true;
   }
-  void bindSlot(xb_filter* f, std::mutex* m, int slot) {
+  void bindSlot(xb_filter* f, EkfMutex* m, int slot) {
     dev_ = DevRef{kSlot, f, m, slot, -1, kInvalid};
     xb_ekf_slot_info(f, slot, &dev_.time, &dev_.serial);
     cov_valid_ = false;
@@ -1034,13 +1081,13 @@ class Ekf {
       throw init_bfr_mismatch{};
     const std::vector<double> x = init_state.xvec();
     const Matrix cov = init_state.getCovariance();
-    std::lock_guard<std::mutex> lk(dev_->mutex);
+    std::lock_guard<EkfMutex> lk(dev_->mutex);
     xb_throw(xb_ekf_initialize_from_state(dev_->f, x.data(), cov.data(), XB_COL_MAJOR));
   }
   /** ekf.cpp:66-140 */
   std::optional<State> processImu(const double timestamp, unsigned int seq, const Vector3& w_m, const Vector3& a_m) {
     if (!dev_) return std::nullopt;
-    std::lock_guard<std::mutex> lk(dev_->mutex);
+    std::lock_guard<EkfMutex> lk(dev_->mutex);
     std::vector<double> x(XB_XVEC_LEN(M_, F_));
     const double w[3] = {w_m(0), w_m(1), w_m(2)}, a[3] = {a_m(0), a_m(1), a_m(2)};
     const int rc = xb_ekf_process_imu(dev_->f, timestamp, seq, w, a, x.data());
@@ -1058,7 +1105,7 @@ class Ekf {
     if (!dev_ || timestamps.empty()) return std::nullopt;
     if (seqs.size() != timestamps.size() || w_m.size() != timestamps.size() || a_m.size() != timestamps.size())
       throw std::invalid_argument("Ekf::processImuBatch: argument lengths differ");
-    std::lock_guard<std::mutex> lk(dev_->mutex);
+    std::lock_guard<EkfMutex> lk(dev_->mutex);
     std::vector<double> x(XB_XVEC_LEN(M_, F_)), w(3 * timestamps.size()), a(3 * timestamps.size());
     for (size_t i = 0; i < timestamps.size(); ++i)
       for (int e = 0; e < 3; ++e) { w[3 * i + e] = w_m[i](e); a[3 * i + e] = a_m[i](e); }
@@ -1074,7 +1121,7 @@ class Ekf {
   /** ekf.cpp:179-213: closestIdx + copy of the buffered state, Updater::update on it, write-back + re-propagation. */
   std::optional<State> processUpdateMeasurement() {
     if (!dev_) return std::nullopt;
-    std::lock_guard<std::mutex> lk(dev_->mutex);
+    std::lock_guard<EkfMutex> lk(dev_->mutex);
     // the host mirror of the estimates is only filled in for updaters that read it (a device-native VioUpdater does not)
     const auto* vio_updater = dynamic_cast<VioUpdater*>(&updater_);
     const bool native = vio_updater != nullptr && !vio_updater->needsHostState();
@@ -1098,7 +1145,7 @@ class Ekf {
   /** ekf.cpp:143-176 */
   std::optional<State> processOthersMeasurement(double timestamp) {
     if (!dev_) return std::nullopt;
-    std::lock_guard<std::mutex> lk(dev_->mutex);
+    std::lock_guard<EkfMutex> lk(dev_->mutex);
     int rc = xb_ekf_update_begin(dev_->f, timestamp, nullptr);
     xb_throw(rc);
     if (rc == 0) return std::nullopt;
@@ -1119,7 +1166,7 @@ class Ekf {
   xb_filter* handle() { return dev_ ? dev_->f : nullptr; }
 
  private:
-  struct Dev { xb_filter* f; std::mutex mutex; };
+  struct Dev { xb_filter* f; EkfMutex mutex; };
   Updater& updater_;
   std::shared_ptr<Dev> dev_;
   int M_ = 0, F_ = 0;

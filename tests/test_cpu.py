@@ -321,9 +321,11 @@ def test_cxx_binding_compiles_in_both_build_flavours():
 @pytest.mark.skipif(not Path("/root/reference/src/x/vio/vio.cpp").exists(), reason="reference sources not present")
 def test_reference_call_sites_compile_against_the_binding(tmp_path):
     """Source compatibility: the reference's own call sites of the hot-path API -- VIO::setUp's construction of the
-    updater and Ekf::set (src/x/vio/vio.cpp:201-214), Ekf::processUpdateMeasurement (:257, :310) and Ekf::processImu
-    (:369) -- are cut out of /root/reference at test time, UNMODIFIED, into a class that has VIO's members
-    (include/x/vio/vio.h:225-246) and compiled against include/x/."""
+    updater and Ekf::set (src/x/vio/vio.cpp:201-214), the whole body of VIO::initAtTime (:55-110: Ekf::lock,
+    TrackManager / StateManager::clear through the friendship of VioUpdater, the initial State, Ekf::initializeFromState
+    between lock and unlock), Ekf::processUpdateMeasurement (:257, :310) and Ekf::processImu (:369) -- are cut out of
+    /root/reference at test time, UNMODIFIED, into a class that has VIO's members (include/x/vio/vio.h:225-264) and
+    compiled against include/x/ with the binding's own x::Params (include/x/vio/types.h:33-160)."""
     import subprocess
     lines = Path("/root/reference/src/x/vio/vio.cpp").read_text().splitlines()
     cut = lambda a, b: "\n".join(lines[a - 1:b])
@@ -331,11 +333,11 @@ def test_reference_call_sites_compile_against_the_binding(tmp_path):
 #include "x/ekf/ekf.h"
 #include "x/vio/vio_updater.h"
 namespace x {{
-struct Params {{ double sigma_img, sigma_range, rho_0, sigma_rho_0; int min_track_length, iekf_iter, state_buffer_size; }};
 class VIO {{
  public:
   VIO() : ekf_{{Ekf(vio_updater_)}} {{}}                       // vio.cpp:40
   void setUp(int n_poses_state, int n_features_state);
+  void initAtTime(const double& time);
   std::optional<State> processMatchesMeasurement();
   std::optional<State> processImu(const double& timestamp, const unsigned int seq, const Vector3& w_m, const Vector3& a_m);
  private:
@@ -345,7 +347,11 @@ class VIO {{
   StateManager state_manager_;
   VioUpdater vio_updater_;
   Ekf ekf_;
+  bool initialized_{{false}}, initialize_start_{{false}}, self_init_start_{{false}};
 }};
+void VIO::initAtTime(const double& time) {{
+{cut(55, 110)}
+}}
 void VIO::setUp(int n_poses_state, int n_features_state) {{
   const Vector3 g(0, 0, -9.81);
   ImuNoise imu_noise;
