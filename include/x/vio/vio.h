@@ -163,20 +163,9 @@ class VIO {
     return processMatchesMeasurement(timestamp, seq, match_vector, match_img, feature_img);
   }
 
-  /** vio.cpp:328-332, state_manager.cpp:151-200: inverse-depth SLAM features of `state` in world coordinates. */
+  /** vio.cpp:328-332 */
   std::vector<Vector3> computeSLAMCartesianFeaturesForState(const State& state) {
-    const std::vector<int> anchor_idxs = vio_updater_.state_manager_.getAnchorIdxs();
-    const size_t n_features = vio_updater_.state_manager_.getNFeatures();
-    const Matrix feats = state.getFeatureArray(), poss = state.getPositionArray(), atts = state.getOrientationArray();
-    std::vector<Vector3> out(n_features);
-    for (size_t i = 0; i < n_features; ++i) {
-      const double alpha = feats(3 * i, 0), beta = feats(3 * i + 1, 0), rho = feats(3 * i + 2, 0);
-      const int a = anchor_idxs[i];
-      const Quaternion q_a(atts(4 * a + 3, 0), atts(4 * a, 0), atts(4 * a + 1, 0), atts(4 * a + 2, 0));
-      const Vector3 p_a(poss(3 * a, 0), poss(3 * a + 1, 0), poss(3 * a + 2, 0));
-      out[i] = p_a + 1.0 / rho * (q_a.normalized().toRotationMatrix() * Vector3(alpha, beta, 1.0));
-    }
-    return out;
+    return vio_updater_.state_manager_.computeSLAMCartesianFeaturesForState(state);
   }
 
   /** vio.cpp:576-707 without cv::FileStorage: the flat `key: value` / `key: [a, b, ...]` files the reference ships

@@ -469,7 +469,11 @@ class State {
 };
 
 // ---- front end, opaque (include/x/vision/tracker.h, include/x/vio/track_manager.h) --------------------------------
-class Tracker {};
+class Tracker {
+ public:
+  /** tracker.cpp: draws the matches into the GUI image; there are no pixels here. */
+  static void plotMatches(MatchList&, TiledImage&) {}
+};
 /** Carries what VioUpdater::preProcess reads from the reference's TrackManager (vio_updater.cpp:172-179): the five
  *  normalised track lists and the lost SLAM feature indexes.  Sorting matches into these lists
  *  (TrackManager::manageTracks) is the step before the hot path. */
@@ -481,6 +485,28 @@ class Camera {
       : fx_(fx), fy_(fy), cx_(cx), cy_(cy), s_(s), img_width_(img_width), img_height_(img_height) {}
   [[nodiscard]] unsigned int getWidth() const { return img_width_; }
   [[nodiscard]] unsigned int getHeight() const { return img_height_; }
+  /** camera.cpp:69-87: FOV model; the undistorted pixel coordinates go into the feature's x / y. */
+  void undistort(Feature& feature) const {
+    const double fx = img_width_ * fx_, fy = img_height_ * fy_, cx = img_width_ * cx_, cy = img_height_ * cy_;
+    const double inv_fx = 1.0 / fx, inv_fy = 1.0 / fy, cx_n = cx * inv_fx, cy_n = cy * inv_fy;
+    const double cam_dist_x = feature.getXDist() * inv_fx - cx_n, cam_dist_y = feature.getYDist() * inv_fy - cy_n;
+    const double dist_r = std::sqrt(cam_dist_x * cam_dist_x + cam_dist_y * cam_dist_y);
+    double distortion_factor = 1.0;
+    if (dist_r > 0.01) distortion_factor = inverseTf(dist_r) / dist_r;
+    feature.setX(distortion_factor * cam_dist_x * fx + cx);
+    feature.setY(distortion_factor * cam_dist_y * fy + cy);
+  }
+  /** camera.cpp:122-135: pixel coordinates (x, y) -> normalised image coordinates. */
+  [[nodiscard]] Feature normalize(const Feature& feature) const {
+    const double fx = img_width_ * fx_, fy = img_height_ * fy_, cx = img_width_ * cx_, cy = img_height_ * cy_;
+    const double inv_fx = 1.0 / fx, inv_fy = 1.0 / fy;
+    return Feature(feature.getTimestamp(), feature.getX() * inv_fx - cx * inv_fx, feature.getY() * inv_fy - cy * inv_fy,
+                   feature.getIntensity());
+  }
+  /** camera.cpp:163-169 */
+  [[nodiscard]] double inverseTf(const double& dist) const {
+    return s_ == 0.0 ? dist : std::tan(dist * s_) * (1.0 / (2.0 * std::tan(s_ / 2.0)));
+  }
   /** Camera::undistort followed by Camera::normalize (camera.cpp:69-87, 122-135) of a measured image point, through the
    *  camera model of the library (xb_tm_normalize_point).  Returns a Feature with the normalised coordinates. */
   [[nodiscard]] Feature undistortAndNormalize(const Feature& feature) const {
@@ -663,6 +689,21 @@ class StateManager {
       attitude_list[static_cast<size_t>(i - start_idx)] = Attitude(orientation_array(4 * i, 0), orientation_array(4 * i + 1, 0),
                                                                    orientation_array(4 * i + 2, 0), orientation_array(4 * i + 3, 0));
     return attitude_list;
+  }
+  /** state_manager.cpp:232-271: inverse-depth SLAM features of `state` in world coordinates. */
+  [[nodiscard]] std::vector<Eigen::Vector3d> computeSLAMCartesianFeaturesForState(const State& state) const {
+    const std::vector<int> anchor_idxs = getAnchorIdxs();
+    const size_t n_features = getNFeatures();
+    const Matrix feats = state.getFeatureArray(), poss = state.getPositionArray(), atts = state.getOrientationArray();
+    std::vector<Eigen::Vector3d> features_xyz(n_features);
+    for (size_t i = 0; i < n_features; ++i) {
+      const double alpha = feats(3 * i, 0), beta = feats(3 * i + 1, 0), rho = feats(3 * i + 2, 0);
+      const int a = anchor_idxs[i];
+      const Quaternion q_a(atts(4 * a + 3, 0), atts(4 * a, 0), atts(4 * a + 1, 0), atts(4 * a + 2, 0));
+      const Vector3 p_a(poss(3 * a, 0), poss(3 * a + 1, 0), poss(3 * a + 2, 0));
+      features_xyz[i] = p_a + 1.0 / rho * (q_a.normalized().toRotationMatrix() * Vector3(alpha, beta, 1.0));
+    }
+    return features_xyz;
   }
   /** state_manager.cpp:31-149 on a device-bound state. */
   void manage(State& state, std::vector<unsigned int> del_feat_idx) {

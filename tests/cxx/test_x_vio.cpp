@@ -28,6 +28,24 @@ int main(int argc, char** argv) {
   x::fsm::path yaml(argv[1]);
   const x::Params params = vio.loadParamsFromYaml(yaml);
   if (argc > 4) {   // parameter dump only (CPU test of the loader)
+    // Camera::undistort + Camera::normalize of the binding (camera.cpp:69-87, 122-135) against the camera model of the
+    // library (xb_tm_normalize_point), without and with FOV distortion
+    for (const double s : {0.0, 0.9}) {
+      const x::Camera cam(0.46, 0.61, 0.5, 0.5, s, 640, 480);
+      for (int k = 0; k < 50; ++k) {
+        x::Feature f;
+        f.setXDist(13.0 * k + 0.25);
+        f.setYDist(479.0 - 9.5 * k);
+        const x::Feature lib = cam.undistortAndNormalize(f);
+        cam.undistort(f);
+        const x::Feature own = cam.normalize(f);
+        if (std::fabs(own.getX() - lib.getX()) > 1e-15 || std::fabs(own.getY() - lib.getY()) > 1e-15) {
+          fprintf(stderr, "camera model mismatch at s = %g, k = %d: %.17g %.17g vs %.17g %.17g\n", s, k, own.getX(), own.getY(),
+                  lib.getX(), lib.getY());
+          return 10;
+        }
+      }
+    }
     printf("%d %d %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %d %d %s\n", params.n_poses_max,
            params.n_slam_features_max, params.min_track_length, params.state_buffer_size, params.n_tiles_h, params.cam_fx,
            params.sigma_img, params.q.w(), params.q.x(), params.q_ic.z(), params.g(2), params.sigma_dtheta(1), params.msckf_baseline,

@@ -338,7 +338,12 @@ class VIO {{
   VIO() : ekf_{{Ekf(vio_updater_)}} {{}}                       // vio.cpp:40
   void setUp(int n_poses_state, int n_features_state);
   void initAtTime(const double& time);
-  std::optional<State> processMatchesMeasurement();
+  std::optional<State> processMatchesMeasurementOld();
+  std::optional<State> processMatchesMeasurement(const double& timestamp, const unsigned int seq,
+                                                 const std::vector<double>& match_vector, TiledImage& match_img,
+                                                 TiledImage& feature_img);
+  MatchList importMatches(const std::vector<double>& match_vector, const unsigned int seq, TiledImage& img_plot) const;
+  std::vector<Eigen::Vector3d> computeSLAMCartesianFeaturesForState(const State& state);
   std::optional<State> processImu(const double& timestamp, const unsigned int seq, const Vector3& w_m, const Vector3& a_m);
  private:
   Params params_;
@@ -348,7 +353,21 @@ class VIO {{
   VioUpdater vio_updater_;
   Ekf ekf_;
   bool initialized_{{false}}, initialize_start_{{false}}, self_init_start_{{false}};
+  Camera camera_;
+  RangeMeasurement last_range_measurement_;
+  SunAngleMeasurement last_angle_measurement_;
 }};
+std::optional<State> VIO::processMatchesMeasurement(const double& timestamp, const unsigned int seq,
+                                                    const std::vector<double>& match_vector, TiledImage& match_img,
+                                                    TiledImage& feature_img) {{
+{cut(278, 322)}
+}}
+MatchList VIO::importMatches(const std::vector<double>& match_vector, const unsigned int seq, TiledImage& img_plot) const {{
+{cut(375, 433)}
+}}
+std::vector<Eigen::Vector3d> VIO::computeSLAMCartesianFeaturesForState(const State& state) {{
+{cut(330, 331)}
+}}
 void VIO::initAtTime(const double& time) {{
 {cut(55, 110)}
 }}
@@ -358,7 +377,7 @@ void VIO::setUp(int n_poses_state, int n_features_state) {{
   double sigma_landmark = 0.0, ci_msckf_w = -1.0, ci_slam_w = -1.0;
 {cut(201, 214)}
 }}
-std::optional<State> VIO::processMatchesMeasurement() {{
+std::optional<State> VIO::processMatchesMeasurementOld() {{
 {cut(257, 257)}
   return updated_state;
 }}
