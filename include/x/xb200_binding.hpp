@@ -469,8 +469,14 @@ class State {
 };
 
 // ---- front end, opaque (include/x/vision/tracker.h, include/x/vio/track_manager.h) --------------------------------
+class Camera;
 class Tracker {
  public:
+  Tracker() = default;
+  /** tracker.h:39-62: camera + FAST / KLT / RANSAC parameters of the image front end; accepted and ignored (matches are
+   *  delivered by the caller). */
+  template <typename... FrontEndParams>
+  explicit Tracker(const Camera&, FrontEndParams&&...) {}
   /** tracker.cpp: draws the matches into the GUI image; there are no pixels here. */
   static void plotMatches(MatchList&, TiledImage&) {}
 };
@@ -893,6 +899,7 @@ class VioUpdater : public Updater {
   [[nodiscard]] bool needsHostState() const { return measurement_.from_front_end; }
 #ifdef MULTI_UAV
   void getMsckfTracks(TrackList& tracks) { tracks = track_manager_.getMsckfTracks(); }
+  void getOppTracks(TrackList& tracks) { tracks = track_manager_.getOppTracks(); }   // vio_updater.h:75
   void getSlamTracks(TrackList& tracks, std::vector<int>& anchor_idxs, const int n_poses_max) {
     tracks = track_manager_.normalizeSlamTracks(n_poses_max);
     anchor_idxs = state_manager_.getAnchorIdxs();

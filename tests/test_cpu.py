@@ -323,13 +323,18 @@ def test_reference_call_sites_compile_against_the_binding(tmp_path):
     """Source compatibility: the reference's own call sites of the hot-path API -- VIO::setUp's construction of the
     updater and Ekf::set (src/x/vio/vio.cpp:201-214), the whole body of VIO::initAtTime (:55-110: Ekf::lock,
     TrackManager / StateManager::clear through the friendship of VioUpdater, the initial State, Ekf::initializeFromState
-    between lock and unlock), Ekf::processUpdateMeasurement (:257, :310) and Ekf::processImu (:369) -- are cut out of
-    /root/reference at test time, UNMODIFIED, into a class that has VIO's members (include/x/vio/vio.h:225-264) and
-    compiled against include/x/ with the binding's own x::Params (include/x/vio/types.h:33-160)."""
+    between lock and unlock), the whole bodies of VIO::setUp (:114-214, single-agent flavour: camera, tracker stub, track
+    and state manager, updater, Ekf::set), VIO::processImu (:346-369 with the accelerometer self-initialisation),
+    VIO::processMatchesMeasurement (:278-322), VIO::importMatches (:375-433), computeSLAMCartesianFeaturesForState
+    (:330-331) and, with -DMULTI_UAV, VIO::getDataToSend (:444-450) -- are cut out of /root/reference at test time,
+    UNMODIFIED, into a class that has VIO's members (include/x/vio/vio.h:225-264) and compiled against include/x/ with
+    the binding's own x::Params (include/x/vio/types.h:33-160).  What stays out: the place-recognition calls of the
+    -DMULTI_UAV setUp and of processOtherMeasurements / processOtherRequests, processImageMeasurement (pixels)."""
     import subprocess
     lines = Path("/root/reference/src/x/vio/vio.cpp").read_text().splitlines()
     cut = lambda a, b: "\n".join(lines[a - 1:b])
     tu = f"""
+#include <boost/log/trivial.hpp>                            // vio.cpp:23 (stand-in of the test infrastructure)
 #include "x/ekf/ekf.h"
 #include "x/vio/vio_updater.h"
 namespace x {{
@@ -337,6 +342,12 @@ class VIO {{
  public:
   VIO() : ekf_{{Ekf(vio_updater_)}} {{}}                       // vio.cpp:40
   void setUp(int n_poses_state, int n_features_state);
+  void setUp(const Params& params);
+  std::optional<State> processImuWhole(const double& timestamp, const unsigned int seq, const Vector3& w_m, const Vector3& a_m);
+#ifdef MULTI_UAV
+  void getDataToSend(std::shared_ptr<SimpleState>& state_ptr, const State& state, TrackList& msckf_tracks,
+                     TrackList& slam_tracks, std::vector<int>& anchor_idxs, TrackList& opp_tracks);
+#endif
   void initAtTime(const double& time);
   std::optional<State> processMatchesMeasurementOld();
   std::optional<State> processMatchesMeasurement(const double& timestamp, const unsigned int seq,
@@ -356,7 +367,22 @@ class VIO {{
   Camera camera_;
   RangeMeasurement last_range_measurement_;
   SunAngleMeasurement last_angle_measurement_;
+  double msckf_baseline_x_n_, msckf_baseline_y_n_;
+  std::vector<Vector3> imu_data_batch_{{}};
 }};
+#ifndef MULTI_UAV   // the -DMULTI_UAV flavour of setUp constructs the place-recognition module (front end, out of scope)
+void VIO::setUp(const Params& params) {{
+{cut(114, 214)}
+}}
+#else
+void VIO::getDataToSend(std::shared_ptr<SimpleState>& state_ptr, const State& state, TrackList& msckf_tracks,
+                        TrackList& slam_tracks, std::vector<int>& anchor_idxs, TrackList& opp_tracks) {{
+{cut(444, 450)}
+}}
+#endif
+std::optional<State> VIO::processImuWhole(const double& timestamp, const unsigned int seq, const Vector3& w_m, const Vector3& a_m) {{
+{cut(346, 369)}
+}}
 std::optional<State> VIO::processMatchesMeasurement(const double& timestamp, const unsigned int seq,
                                                     const std::vector<double>& match_vector, TiledImage& match_img,
                                                     TiledImage& feature_img) {{
