@@ -171,7 +171,9 @@ class VIO {
   /** vio.cpp:576-707 without cv::FileStorage: the flat `key: value` / `key: [a, b, ...]` files the reference ships
    *  (the `%YAML:1.0` directive and `---` lines OpenCV writes are skipped).  Vectors and quaternions (w, x, y, z) as there;
    *  a missing key keeps the default of Params. */
-  Params loadParamsFromYaml(fsm::path& path) {
+  Params loadParamsFromYaml(fsm::path& path) { return loadParamsFromYaml(static_cast<const fsm::path&>(path)); }
+  /** The same for a temporary (the reference's README calls it with a string literal). */
+  Params loadParamsFromYaml(const fsm::path& path) {
     std::ifstream in(path);
     if (!in) throw std::invalid_argument("cannot open parameter file " + path.string());
     std::map<std::string, std::vector<std::string>> doc;

@@ -529,6 +529,10 @@ def test_cxx_vio_facade_compiles_and_loads_yaml_params(tmp_path):
     inc = [f"-I{ROOT / 'include'}", f"-I{EIGEN_STAND_IN}"]
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DMULTI_UAV", *inc, src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    # the usage example of the reference's README (README.md:196-252: set-up, sensors, IMU) as a caller writes it
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", *inc, os.fspath(ROOT / "tests" / "cxx" / "readme_usage.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
     libdir = ROOT / "x_multi_agent_b200"
     exe = tmp_path / "test_x_vio"
     r = subprocess.run(["g++", "-std=c++17", "-O1", *inc, "-o", os.fspath(exe), src, f"-L{libdir}", "-lxb200",
